@@ -1,0 +1,197 @@
+// Host side of the tap-GEMM kernel: tensor-map construction, tile-shape choice, launch.
+#include "tapconv_host.h"
+
+#include <cudaTypedefs.h>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "tapconv.cuh"
+
+namespace ob {
+
+static thread_local char g_err[512] = "";
+const char* last_error() { return g_err; }
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+// cuTensorMapEncodeTiled is a driver entry point; fetch it through the runtime so the library
+// has no link-time dependency on libcuda.
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  });
+  return fn;
+}
+
+static CUtensorMapSwizzle swizzle_for_bytes(int inner_bytes) {
+  switch (inner_bytes) {
+    case 128: return CU_TENSOR_MAP_SWIZZLE_128B;
+    case 64: return CU_TENSOR_MAP_SWIZZLE_64B;
+    case 32: return CU_TENSOR_MAP_SWIZZLE_32B;
+    default: return CU_TENSOR_MAP_SWIZZLE_NONE;
+  }
+}
+
+int encode_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_elems,
+                     const uint32_t* box) {
+  auto enc = get_encode();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return OB_ERR_CUDA;
+  }
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[4];
+  cuuint32_t bx[5];
+  cuuint32_t es[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+    if (i > 0) gstr[i - 1] = strides_elems[i] * 2;  // bytes
+  }
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), gdim, gstr, bx, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for_bytes(static_cast<int>(box[0]) * 2),
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed: CUresult %d (rank %d, dims %llu %llu %llu, box %u %u %u)", (int)r, rank,
+              (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)(rank > 2 ? dims[2] : 0),
+              box[0], box[1], rank > 2 ? box[2] : 0);
+    return OB_ERR_CUDA;
+  }
+  return OB_OK;
+}
+
+static int pow2_ceil(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+template <int CHUNK, int BN>
+static int launch_inst(const TapConvParams& p, int grid, cudaStream_t stream) {
+  using Cfg = TapConvCfg<CHUNK, BN>;
+  static bool attr_set = false;  // benign race: setting twice is harmless
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(tapconv_kernel<CHUNK, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(tapconv<%d,%d>, %d B): %s", CHUNK, BN, Cfg::SMEM_BYTES, cudaGetErrorString(e));
+      return OB_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  tapconv_kernel<CHUNK, BN><<<grid, TAPCONV_THREADS, Cfg::SMEM_BYTES, stream>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("tapconv<%d,%d> launch: %s", CHUNK, BN, cudaGetErrorString(e));
+    return OB_ERR_CUDA;
+  }
+  return OB_OK;
+}
+
+template <int CHUNK>
+static int launch_bn(int bn, const TapConvParams& p, int grid, cudaStream_t s) {
+  switch (bn) {
+    case 16: return launch_inst<CHUNK, 16>(p, grid, s);
+    case 32: return launch_inst<CHUNK, 32>(p, grid, s);
+    case 64: return launch_inst<CHUNK, 64>(p, grid, s);
+    case 128: return launch_inst<CHUNK, 128>(p, grid, s);
+    case 256: return launch_inst<CHUNK, 256>(p, grid, s);
+  }
+  set_error("unsupported tile N %d", bn);
+  return OB_ERR_UNSUPPORTED;
+}
+
+int tapconv_launch(const TapConvLaunch& L, cudaStream_t stream) {
+  if (L.Cin % 16 != 0 || L.Cout % 8 != 0) {
+    set_error("tapconv: Cin (%d) must be a multiple of 16 and Cout (%d) of 8", L.Cin, L.Cout);
+    return OB_ERR_INVALID;
+  }
+  if (L.n_items < 1 || L.n_items > TAPCONV_MAX_ITEMS) {
+    set_error("tapconv: bad item count %d", L.n_items);
+    return OB_ERR_INVALID;
+  }
+  if (L.n_seq <= 0 || L.T <= 0) return OB_OK;  // empty problem
+  const int n_acc = L.n_out + (L.epi == EPI_GATED ? 1 : 0);
+  if (n_acc > 3 || L.n_out < 1) {
+    set_error("tapconv: unsupported accumulator count %d", n_acc);
+    return OB_ERR_INVALID;
+  }
+  const int chunk = (L.Cin % 64 == 0) ? 64 : (L.Cin % 32 == 0) ? 32 : 16;
+
+  TapConvParams p;
+  memset(&p, 0, sizeof(p));
+  // ---- pixel tile: 128 rows = bt frames x bh rows x bw cols
+  p.bw = pow2_ceil(L.W) > 128 ? 128 : pow2_ceil(L.W);
+  p.bh = pow2_ceil(L.H);
+  if (p.bh > 128 / p.bw) p.bh = 128 / p.bw;
+  p.bt = 128 / (p.bw * p.bh);
+  p.tiles_w = (L.W + p.bw - 1) / p.bw;
+  p.tiles_h = (L.H + p.bh - 1) / p.bh;
+  p.tiles_t = (L.T + p.bt - 1) / p.bt;
+  const int m_tiles = L.n_seq * p.tiles_t * p.tiles_h * p.tiles_w;
+
+  // ---- tile N: as wide as TMEM allows, narrowed while the grid cannot fill the 148 SMs
+  int bn_max = (n_acc == 3) ? 128 : 256;
+  int bn = pow2_ceil(L.Cout) < 16 ? 16 : pow2_ceil(L.Cout);
+  if (bn > bn_max) bn = bn_max;
+  if (L.force_bn > 0) bn = L.force_bn;
+  else
+    while (bn > 32 && m_tiles * ((L.Cout + bn - 1) / bn) < 148) bn >>= 1;
+  if (n_acc * bn > 512) {
+    set_error("tapconv: %d accumulators x N=%d exceed TMEM", n_acc, bn);
+    return OB_ERR_INVALID;
+  }
+  p.tiles_n = (L.Cout + bn - 1) / bn;
+
+  // ---- tensor maps
+  for (int s = 0; s < 2; ++s) {
+    if (L.a[s] == nullptr) continue;
+    uint64_t dims[5] = {(uint64_t)L.Cin, (uint64_t)L.W, (uint64_t)L.H, (uint64_t)L.a_T[s], (uint64_t)L.a_seq[s]};
+    uint64_t str[5] = {1, (uint64_t)L.a_stride_w[s], (uint64_t)L.a_stride_h[s], (uint64_t)L.a_stride_t[s],
+                       (uint64_t)L.a_stride_seq[s]};
+    uint32_t box[5] = {(uint32_t)chunk, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bt, 1};
+    int r = encode_tmap_bf16(&p.mapA[s], L.a[s], 5, dims, str, box);
+    if (r != OB_OK) return r;
+  }
+  if (L.a[1] == nullptr) p.mapA[1] = p.mapA[0];
+  {
+    uint64_t dims[2] = {(uint64_t)L.w_taps * L.Cin, (uint64_t)L.Cout};
+    uint64_t str[2] = {1, (uint64_t)L.w_taps * L.Cin};
+    uint32_t box[2] = {(uint32_t)chunk, (uint32_t)bn};
+    int r = encode_tmap_bf16(&p.mapB, L.wg, 2, dims, str, box);
+    if (r != OB_OK) return r;
+  }
+  for (int i = 0; i < L.n_items; ++i) {
+    p.items[i] = static_cast<const TapItem*>(L.items)[i];
+    if (L.a[p.items[i].src] == nullptr || p.items[i].acc + p.items[i].n_a > n_acc || p.items[i].wtap >= L.w_taps) {
+      set_error("tapconv: item %d is inconsistent", i);
+      return OB_ERR_INVALID;
+    }
+  }
+  p.n_items = L.n_items;
+  p.n_seq = L.n_seq; p.T = L.T; p.H = L.H; p.W = L.W;
+  p.Cin = L.Cin; p.Cout = L.Cout;
+  p.n_out = L.n_out; p.epi = L.epi; p.out_f32 = L.out_f32;
+  p.alpha = L.alpha; p.beta = L.beta; p.out = L.out; p.out_d = L.out_d;
+
+  const int grid = m_tiles * p.tiles_n;
+  switch (chunk) {
+    case 64: return launch_bn<64>(bn, p, grid, stream);
+    case 32: return launch_bn<32>(bn, p, grid, stream);
+    default: return launch_bn<16>(bn, p, grid, stream);
+  }
+}
+
+}  // namespace ob

@@ -1,0 +1,41 @@
+// Internal host-side interface shared by the kernel translation units and the C-ABI layer.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cstdarg>
+#include <cstdint>
+
+namespace ob {
+
+enum : int { OB_OK = 0, OB_ERR_INVALID = -1, OB_ERR_UNSUPPORTED = -2, OB_ERR_CUDA = -3 };
+
+const char* last_error();
+void set_error(const char* fmt, ...);
+
+struct TapItem;  // defined in tapconv.cuh
+
+int encode_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_elems,
+                     const uint32_t* box);
+
+// One tap-GEMM problem. Activations are bf16 NHWC tensors [seq, T, H, W, Cin] with explicit element
+// strides (channel stride 1); weights are bf16 [Cout, w_taps, Cin] contiguous.
+struct TapConvLaunch {
+  const void* a[2] = {nullptr, nullptr};
+  int a_seq[2] = {0, 0}, a_T[2] = {0, 0};
+  long a_stride_w[2] = {0, 0}, a_stride_h[2] = {0, 0}, a_stride_t[2] = {0, 0}, a_stride_seq[2] = {0, 0};
+  const void* wg = nullptr;
+  int w_taps = 0;
+  const void* items = nullptr;  // TapItem[n_items]
+  int n_items = 0;
+  int n_seq = 0, n_out = 1, T = 0, H = 0, W = 0, Cin = 0, Cout = 0;
+  int epi = 0, out_f32 = 0;
+  const float* alpha = nullptr;
+  const float* beta = nullptr;
+  void* out = nullptr;
+  void* out_d = nullptr;
+  int force_bn = 0;  // test hook: pin the N tile
+};
+
+int tapconv_launch(const TapConvLaunch& L, cudaStream_t stream);
+
+}  // namespace ob
