@@ -39,3 +39,23 @@ struct TapConvLaunch {
 int tapconv_launch(const TapConvLaunch& L, cudaStream_t stream);
 
 }  // namespace ob
+
+namespace ob {
+
+// One weight-gradient problem: up to two (G, A) tensor pairs sharing H, W, Cin, Cout.
+//   G pair p: bf16 [g_seq[p], g_T[p], H, W, Cout] contiguous; A pair p: bf16 [g_seq[p], a_T[p], H, W, Cin] contiguous.
+struct WgradLaunch {
+  const void* g[2] = {nullptr, nullptr};
+  const void* a[2] = {nullptr, nullptr};
+  int g_seq[2] = {0, 0}, g_T[2] = {0, 0}, a_T[2] = {0, 0};
+  const void* items = nullptr;  // WgradItem[n_items]
+  int n_items = 0;
+  int H = 0, W = 0, Cin = 0, Cout = 0, w_taps = 0;
+  int n_split = 1;
+  float* out = nullptr;  // [n_split, Cout, w_taps, Cin]
+};
+
+int wgrad_suggest_split(int n_items, int max_rows, int H, int W, int Cin, int Cout);
+int wgrad_launch(const WgradLaunch& L, cudaStream_t stream);
+
+}  // namespace ob

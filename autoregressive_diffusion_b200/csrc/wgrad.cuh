@@ -1,0 +1,186 @@
+// Weight-gradient tap-GEMM ("MN-major x MN-major"): for every tap item
+//
+//   dW[split, co, wtap, ci] = sum over the CTA's share of pixel rows p:  G[p, co] * A[p + shift, ci]
+//
+// G is the (already gate-scaled) output gradient, A the saved layer input, both bf16 NHWC, so the
+// contraction index (pixels) is the slow axis of both operands. TMA drops [64 pixels][CHUNK channels]
+// boxes into shared memory; those are MN-major UMMA operands (LBO = one box, SBO = 8 rows).
+// grid = (co tiles * ci tiles, items, k-splits); split partials are summed by the weight-norm backward
+// kernel, which has to read dW anyway.  Reference op being differentiated: edm2/conv.py:41,86.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+#include "ptx.cuh"
+#include "tapconv.cuh"
+
+namespace ob {
+
+constexpr int WGRAD_KT = 64;  // pixel rows per pipeline stage
+constexpr int WGRAD_THREADS = 192;
+
+struct WgradItem {
+  int8_t pair;  // which (G, A) tensor pair
+  int8_t dt, dy, dx;
+  int32_t wtap;
+};
+
+struct WgradParams {
+  CUtensorMap mapG[2];
+  CUtensorMap mapA[2];
+  WgradItem items[TAPCONV_MAX_ITEMS];
+  int n_items;
+  int n_seq[2], T[2];  // pixel-row space of each pair (rows of G)
+  int H, W;
+  int Cin, Cout, w_taps;
+  int bw, bh, bt;
+  int tiles_w, tiles_h;
+  int tiles_t[2];
+  int ci_tiles;
+  int n_split;
+  float* out;  // [n_split, Cout, w_taps, Cin] fp32
+};
+
+template <int CHUNK, int BN>
+struct WgradCfg {
+  static constexpr int ROW_BYTES = CHUNK * 2;
+  static constexpr int BOX_BYTES = WGRAD_KT * ROW_BYTES;
+  static constexpr int G_BOXES = 128 / CHUNK;
+  static constexpr int A_BOXES = BN / CHUNK;
+  static constexpr int G_BYTES = G_BOXES * BOX_BYTES;
+  static constexpr int A_BYTES = A_BOXES * BOX_BYTES;
+  static constexpr int STAGE_BYTES = G_BYTES + A_BYTES;
+  static constexpr int STAGES_RAW = (200 * 1024) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr int CW = BN >= 32 ? 32 : 16;
+};
+
+template <int CHUNK, int BN>
+__global__ void __launch_bounds__(WGRAD_THREADS, 1) wgrad_kernel(const __grid_constant__ WgradParams p) {
+  using Cfg = WgradCfg<CHUNK, BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  constexpr uint32_t SWZ = SwizzleFor<CHUNK>::mode;
+  constexpr uint32_t SBO = 8 * Cfg::ROW_BYTES;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  const uint32_t tmem_full_bar = bar_base + 8u * (2 * STAGES);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const WgradItem item = p.items[blockIdx.y];
+  const int pr = item.pair;
+  const int ci_tile = blockIdx.x % p.ci_tiles;
+  const int co_tile = blockIdx.x / p.ci_tiles;
+  const int co0 = co_tile * 128, ci0 = ci_tile * BN;
+  const int k_tiles = p.n_seq[pr] * p.tiles_t[pr] * p.tiles_h * p.tiles_w;
+  const int k_begin = static_cast<int>(static_cast<long>(k_tiles) * blockIdx.z / p.n_split);
+  const int k_end = static_cast<int>(static_cast<long>(k_tiles) * (blockIdx.z + 1) / p.n_split);
+
+  constexpr uint32_t tmem_cols = BN < 32 ? 32 : BN;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&p.mapG[pr]);
+    tma_prefetch_desc(&p.mapA[pr]);
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kt = k_begin; kt < k_end; ++kt) {
+        int r = kt;
+        const int tw_i = r % p.tiles_w; r /= p.tiles_w;
+        const int th_i = r % p.tiles_h; r /= p.tiles_h;
+        const int tt_i = r % p.tiles_t[pr];
+        const int seq = r / p.tiles_t[pr];
+        const int w0 = tw_i * p.bw, h0 = th_i * p.bh, t0 = tt_i * p.bt;
+        mbar_wait(empty_bar(stage), phase ^ 1);
+        const uint32_t sG = smem_base + stage * Cfg::STAGE_BYTES;
+        const uint32_t sA = sG + Cfg::G_BYTES;
+        mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+#pragma unroll
+        for (int j = 0; j < Cfg::G_BOXES; ++j)
+          tma_load_5d(sG + j * Cfg::BOX_BYTES, &p.mapG[pr], full_bar(stage), co0 + j * CHUNK, w0, h0, t0, seq);
+#pragma unroll
+        for (int j = 0; j < Cfg::A_BOXES; ++j)
+          tma_load_5d(sA + j * Cfg::BOX_BYTES, &p.mapA[pr], full_bar(stage), ci0 + j * CHUNK, w0 + item.dx, h0 + item.dy,
+                      t0 + item.dt, seq);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, BN, 1, 1);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kt = k_begin; kt < k_end; ++kt) {
+        mbar_wait(full_bar(stage), phase);
+        tc_fence_after();
+        const uint32_t sG = smem_base + stage * Cfg::STAGE_BYTES;
+        const uint32_t sA = sG + Cfg::G_BYTES;
+#pragma unroll
+        for (int k = 0; k < WGRAD_KT / 16; ++k) {
+          const uint64_t adesc = make_smem_desc(sG + k * 2 * SBO, Cfg::BOX_BYTES, SBO, SWZ);
+          const uint64_t bdesc = make_smem_desc(sA + k * 2 * SBO, Cfg::BOX_BYTES, SBO, SWZ);
+          umma_bf16_ss(tmem_base, adesc, bdesc, idesc, (kt > k_begin) || (k > 0));
+        }
+        umma_commit(empty_bar(stage));
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(tmem_full_bar);
+    }
+  } else {
+    constexpr int CW = Cfg::CW;
+    const int q = warp & 3;
+    const int co = co0 + q * 32 + lane;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    float* dst_row = p.out + ((static_cast<long>(blockIdx.z) * p.Cout + co) * p.w_taps + item.wtap) * p.Cin;
+    const bool have = k_end > k_begin;
+    for (int c = 0; c < BN / CW; ++c) {
+      float v[CW];
+      if constexpr (CW == 32) tmem_ld32(lane_base + c * CW, v);
+      else tmem_ld16(lane_base + c * CW, v);
+      tmem_ld_wait();
+      if (co < p.Cout) {
+        const int col0 = ci0 + c * CW;
+#pragma unroll
+        for (int j = 0; j < CW; j += 4)
+          if (col0 + j + 4 <= p.Cin)
+            *reinterpret_cast<float4*>(dst_row + col0 + j) =
+                have ? make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+}  // namespace ob
