@@ -90,14 +90,15 @@ def weight_operand(w: Tensor, gain=1.0, training: bool = False) -> Tuple[Tensor,
 
     Returns (operand, forced).  In training the reference first overwrites the parameter with its
     normalised value (forced weight norm, under no_grad, in place on the very tensor the next line
-    reads), then normalises *that* differentiably.  ``forced`` is the new parameter value (a leaf the
-    caller may attach gradients to); None in eval mode.
+    reads), then normalises *that* differentiably, so the gradient it stores on the parameter is the
+    gradient w.r.t. the forced value.  Here: ``forced`` is the new parameter value (None in eval mode)
+    and the gradient w.r.t. it is delivered straight through onto ``w``.
     """
     w = w.float()
     forced = None
     if training:
-        forced = normalize(w.detach()).requires_grad_(w.requires_grad)
-        w = forced
+        forced = normalize(w.detach())
+        w = w + (forced - w).detach()
     fan_in = w[0].numel()
     return normalize(w) * (gain / math.sqrt(fan_in)), forced
 
