@@ -1,0 +1,80 @@
+"""ctypes binding of liboniris_b200.so (the C ABI in include/oniris_b200.h).
+
+There is deliberately no fallback: if the library is missing or a call fails, this raises.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liboniris_b200.so")
+
+_lib = None
+
+
+class OnirisError(RuntimeError):
+    pass
+
+
+def _vp(t):
+    """Device pointer of a tensor (or NULL)."""
+    if t is None:
+        return ctypes.c_void_p(0)
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+_SIGS = {
+    # name: argtypes
+    "ob_wnorm_fwd": "ppiiiiiiffip",
+    "ob_wnorm_bwd": "pppiiiiiiiffp",
+    "ob_conv_fwd": "pppppppiiiiiiiiiip",
+    "ob_conv_dgrad": "ppppppiiiiiiiiip",
+    "ob_conv_wgrad_splits": "iiiiiiiii",
+    "ob_conv_wgrad": "pppppiiiiiiiiiip",
+    "ob_gate_bwd": "pppppppppiiilp",
+    "ob_pixnorm_silu_fwd": "ppplifip",
+    "ob_pixnorm_silu_bwd": "pppplifip",
+    "ob_scale_silu_fwd": "pppliip",
+    "ob_scale_silu_bwd": "pppppiiip",
+    "ob_mp_sum_fwd": "ppplffp",
+    "ob_mp_sum_bwd": "pppplffp",
+}
+_CT = {"p": ctypes.c_void_p, "i": ctypes.c_int, "f": ctypes.c_float, "l": ctypes.c_int64}
+
+# Symbols include/oniris_b200.h declares; tests check every one is exported.
+DECLARED = ["ob_version", "ob_last_error"] + sorted(_SIGS)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise OnirisError(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(or `make -C autoregressive_diffusion_b200/csrc`). There is no fallback path.")
+        L = ctypes.CDLL(LIB_PATH)
+        L.ob_last_error.restype = ctypes.c_char_p
+        L.ob_version.restype = ctypes.c_int
+        for name, sig in _SIGS.items():
+            fn = getattr(L, name)
+            fn.argtypes = [_CT[c] for c in sig]
+            fn.restype = ctypes.c_int
+        _lib = L
+    return _lib
+
+
+def call(name, *args):
+    """Invoke an entry point; raise OnirisError with the library's message on a non-zero status."""
+    L = lib()
+    rc = getattr(L, name)(*args)
+    if rc != 0:
+        raise OnirisError(f"{name} failed ({rc}): {L.ob_last_error().decode()}")
+
+
+def query(name, *args):
+    return getattr(lib(), name)(*args)

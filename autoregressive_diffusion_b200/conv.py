@@ -1,0 +1,174 @@
+"""Drop-in counterparts of the reference's edm2/conv.py layers, backed by the sm_100a kernels.
+
+Same class names, constructor arguments, forward signatures, state_dict keys and cache format as
+`edm2.conv` (NormalizedWeight :8-21, MPConv :27-46, MPCausal3DGatedConv :49-101, Gating :104-127), so they
+can be swapped into `edm2.networks_edm2`.  Activations may arrive in any dtype/layout; they leave as bf16
+channels_last tensors of the same logical [(b [s] t), C, H, W] shape.
+"""
+import math
+
+import torch
+from torch import nn
+
+from . import ops
+from .ops import BF16, rows
+
+EPS = 1e-4
+
+
+def _normalize_rows(w, eps=EPS):
+    """edm2/utils.py:83-88 for a weight matrix (all dims but 0), plain torch -- used only by the tiny linear layers."""
+    n = torch.linalg.vector_norm(w.float(), dim=tuple(range(1, w.ndim)), keepdim=True, dtype=torch.float32)
+    return w / (eps + n * math.sqrt(n.numel() / w.numel()))
+
+
+class NormalizedWeight(nn.Module):
+    """Parameter holder with forced + traditional weight normalisation (edm2/conv.py:8-21)."""
+
+    def __init__(self, in_channels, out_channels, kernel):
+        super().__init__()
+        self.weight = nn.Parameter(torch.randn(out_channels, in_channels, *kernel))
+
+    def forward(self, gain=1):
+        """fp32 normalised weight tensor, reference semantics (used by the linear layers and by tests)."""
+        w = self.weight.to(torch.float32)
+        if self.training:
+            with torch.no_grad():
+                self.weight.copy_(_normalize_rows(w))
+        w = _normalize_rows(w)
+        return w * (gain / math.sqrt(w[0].numel()))
+
+
+class _OperandCache:
+    """bf16 GEMM operand of one or two NormalizedWeights, rebuilt only when a parameter or the mode changes.
+
+    The reference re-normalises every weight on every forward, eval included (edm2/conv.py:14-21); the values
+    only change when an optimizer step (or a load) touches the parameter, which bumps its autograd version.
+    """
+
+    def __init__(self):
+        self.key, self.wg = None, None
+
+    def get(self, params, taps, cin, cin_pad, gains, training):
+        key = tuple((p.data_ptr(), p._version) for p in params) + (bool(training), tuple(float(g) for g in gains))
+        if key != self.key:
+            with torch.no_grad():
+                self.wg = ops.weight_operand([p.data for p in params], taps, cin, cin_pad, gains, training)
+            # forced normalisation rewrote the parameters through a raw pointer: the version did not move
+            self.key = key
+        return self.wg
+
+
+class MPConv(nn.Module):
+    """Magnitude-preserving conv / linear (edm2/conv.py:27-46)."""
+
+    def __init__(self, in_channels, out_channels, kernel, dilation=1):
+        super().__init__()
+        self.out_channels = out_channels
+        self.in_channels = in_channels
+        self.weight = NormalizedWeight(in_channels, out_channels, kernel)
+        self.dilation = dilation
+        self.padding = [dilation * (kernel[-1] // 2)] * 4 if len(kernel) != 0 else None
+        self._cache = _OperandCache()
+
+    def forward(self, x, gain=1, out_f32=False):
+        w = self.weight.weight
+        if w.ndim == 2:  # embedding linears: [BT, cemb] rows, far off the roofline -> library GEMM
+            return x @ self.weight(gain).to(x.dtype).t()
+        assert w.ndim == 4 and w.shape[-1] in (1, 3)
+        ops._require_cuda(x)
+        k = w.shape[-1]
+        cin = w.shape[1]
+        cin_pad = ops.ceil_to(cin, 16)
+        g = float(gain)
+        wg = self._cache.get([w], [k * k], cin, cin_pad, [g], self.training)
+        xr = ops.pad_channels(rows(x), 16)
+        return ops.PlainConvFn.apply(xr, w, wg, k, g, out_f32)
+
+    @torch.no_grad()
+    def load_from_2d(self, state_dict):
+        self.weight.weight.copy_(state_dict)
+
+
+class Gating(nn.Module):
+    """Noise- and position-dependent gate (edm2/conv.py:104-127)."""
+
+    def __init__(self):
+        super().__init__()
+        self.offset = nn.Parameter(torch.tensor([0., 0.]))
+        self.mult = nn.Parameter(torch.tensor([1.5, -0.5]))
+        self.max_gating = nn.Parameter(torch.tensor(-5.))
+        self.min_gating = nn.Parameter(torch.tensor(-5.))
+
+    def forward(self, c_noise, n_context_frames=0, just_2d=False):
+        bsz, tdim = c_noise.shape
+        if self.training:
+            tdim = tdim // 2
+        if just_2d:
+            pos = torch.zeros_like(c_noise)
+        else:
+            pos = (torch.arange(c_noise.numel(), device=c_noise.device) % tdim).reshape(bsz, -1) + n_context_frames
+            pos = pos.to(c_noise.dtype).log1p()
+        state = c_noise * self.mult[0] + self.offset[0] + pos * self.mult[1] + self.offset[1]
+        lo, hi = torch.sigmoid(self.min_gating), torch.sigmoid(self.max_gating)
+        return lo + (1 - lo) * hi * torch.sigmoid(state), n_context_frames + tdim
+
+
+class MPCausal3DGatedConv(nn.Module):
+    """3x3 conv on the current frame (+) gated 2x3x3 causal conv on the two previous clean frames
+    (edm2/conv.py:49-101), as ONE tcgen05 implicit-GEMM launch with the gate applied in the epilogue."""
+
+    def __init__(self, in_channels, out_channels, kernel):
+        super().__init__()
+        assert len(kernel) == 3 and tuple(kernel) == (3, 3, 3), "the kernels implement the reference's 3x3x3 case"
+        self.out_channels = out_channels
+        self.in_channels = in_channels
+        self.last_frame_conv = MPConv(in_channels, out_channels, kernel[1:])
+        self.weight = NormalizedWeight(in_channels, out_channels, (kernel[0] - 1, kernel[1], kernel[2]))
+        self.gating = Gating()
+        self._cache = _OperandCache()
+
+    def forward(self, x, emb, batch_size, c_noise, cache=None, update_cache=False, just_2d=False):
+        if just_2d:
+            return self.last_frame_conv(x), cache
+        ops._require_cuda(x)
+        if cache is None:
+            cache = {}
+        w2, w3 = self.last_frame_conv.weight.weight, self.weight.weight
+        cin = w2.shape[1]
+        cin_pad = ops.ceil_to(cin, 16)
+        wg = self._cache.get([w2, w3], [9, 18], cin, cin_pad, [1.0, 1.0], self.training)
+
+        g, n_ctx = self.gating(c_noise.float(), cache.get('n_context_frames', 0))
+        if update_cache:
+            cache['n_context_frames'] = n_ctx
+        g = g.flatten()
+        inv = torch.rsqrt((1 - g) ** 2 + g ** 2)
+        alpha, beta = ((1 - g) * inv).contiguous(), (g * inv).contiguous()
+
+        xr = ops.pad_channels(rows(x), 16)
+        f, _, h, w = xr.shape
+        S = 2 if self.training else 1
+        T = f // (batch_size * S)
+        x5 = xr.permute(0, 2, 3, 1).reshape(batch_size, S * T, h, w, cin_pad)       # physical NHWC view
+        pad = cache.get('activations', None)
+        if pad is None:
+            pad5 = torch.ones(batch_size, 2, h, w, cin_pad, dtype=BF16, device=xr.device)
+            if cin_pad != cin:
+                pad5[..., cin:] = 0
+        else:  # reference layout [B, C, 2, H, W] -> [B, 2, H, W, C]
+            pad5 = pad.permute(0, 2, 3, 4, 1).to(BF16)
+            if cin_pad != cin:
+                pad5 = torch.nn.functional.pad(pad5, (0, cin_pad - cin))
+        ctx5 = torch.cat((pad5, x5[:, :T].detach()), dim=1).contiguous()             # [B, T+2, H, W, C]
+        if update_cache:
+            cache['activations'] = ctx5[:, -2:, :, :, :cin].permute(0, 4, 1, 2, 3).clone()
+        want_grad = torch.is_grad_enabled() and (xr.requires_grad or w2.requires_grad or w3.requires_grad)
+        y = ops.GatedConvFn.apply(xr, ctx5, w2, w3, wg, alpha, beta, batch_size, S, T, want_grad)
+        return y, cache
+
+    @torch.no_grad()
+    def load_from_2d(self, weight):
+        if isinstance(weight, dict):
+            weight = weight['weight']
+        self.last_frame_conv.load_from_2d(weight)

@@ -1,0 +1,158 @@
+// extern "C" surface of liboniris_b200.so (declared in include/oniris_b200.h).
+#include "../../include/oniris_b200.h"
+
+#include <vector>
+
+#include "hbm_host.h"
+#include "tapconv.cuh"
+#include "tapconv_host.h"
+#include "wgrad.cuh"
+
+using namespace ob;
+
+static TapItem tap_item(int src, int dt, int dy, int dx, int n_a, int acc, int seq_mul, int wtap) {
+  TapItem t{};
+  t.src = (int8_t)src; t.dt = (int8_t)dt; t.dy = (int8_t)dy; t.dx = (int8_t)dx;
+  t.n_a = (int8_t)n_a; t.acc = (int8_t)acc; t.seq_mul = (int8_t)seq_mul; t.wtap = wtap;
+  return t;
+}
+static void set_src(TapConvLaunch& L, int s, const void* p, int seq, int T, int H, int W, int C) {
+  L.a[s] = p; L.a_seq[s] = seq; L.a_T[s] = T;
+  L.a_stride_w[s] = C; L.a_stride_h[s] = (long)W * C; L.a_stride_t[s] = (long)H * W * C;
+  L.a_stride_seq[s] = (long)T * H * W * C;
+}
+static int check_shape(const char* who, int n_seq, int S, int T, int H, int W, int ksize, int gated) {
+  if (n_seq < 0 || T < 0 || H <= 0 || W <= 0 || (S != 1 && S != 2) || (ksize != 1 && ksize != 3) || (gated && ksize != 3)) {
+    set_error("%s: bad shape n_seq=%d S=%d T=%d H=%d W=%d ksize=%d gated=%d", who, n_seq, S, T, H, W, ksize, gated);
+    return OB_ERR_INVALID;
+  }
+  return OB_OK;
+}
+
+extern "C" {
+
+int ob_version(void) { return 100; }
+const char* ob_last_error(void) { return last_error(); }
+
+int ob_wnorm_fwd(float* w, void* wg, int cout, int cin, int taps, int cin_pad, int taps_total, int tap_off, float gain,
+                 float eps, int training, void* stream) {
+  return wnorm_fwd(w, wg, cout, cin, taps, cin_pad, taps_total, tap_off, gain, eps, training, (cudaStream_t)stream);
+}
+int ob_wnorm_bwd(const float* w, const float* dwg, float* dw, int cout, int cin, int taps, int cin_pad, int taps_total,
+                 int tap_off, int n_split, float gain, float eps, void* stream) {
+  return wnorm_bwd(w, dwg, dw, cout, cin, taps, cin_pad, taps_total, tap_off, n_split, gain, eps, (cudaStream_t)stream);
+}
+
+int ob_conv_fwd(const void* x, const void* ctx, const void* wg, const float* alpha, const float* beta, void* out,
+                void* out_d, int n_seq, int S, int T, int H, int W, int cin, int cout, int ksize, int gated, int out_f32,
+                void* stream) {
+  if (int r = check_shape("ob_conv_fwd", n_seq, S, T, H, W, ksize, gated)) return r;
+  TapConvLaunch L;
+  std::vector<TapItem> items;
+  if (!gated) {
+    // frames are independent: fold (seq, S, T) into one long frame axis so tiles never straddle less than they must
+    const int frames = n_seq * S * T;
+    set_src(L, 0, x, 1, frames, H, W, cin);
+    for (int ky = 0; ky < ksize; ++ky)
+      for (int kx = 0; kx < ksize; ++kx) items.push_back(tap_item(0, 0, ky - ksize / 2, kx - ksize / 2, 1, 0, 1, ky * ksize + kx));
+    L.n_seq = 1; L.n_out = 1; L.T = frames; L.w_taps = ksize * ksize; L.epi = EPI_PLAIN;
+  } else {
+    set_src(L, 0, x, n_seq * S, T, H, W, cin);
+    set_src(L, 1, ctx, n_seq, T + 2, H, W, cin);
+    for (int k = 0; k < 9; ++k) items.push_back(tap_item(0, 0, k / 3 - 1, k % 3 - 1, S, 0, S, k));
+    for (int tau = 0; tau < 2; ++tau)
+      for (int k = 0; k < 9; ++k) items.push_back(tap_item(1, tau, k / 3 - 1, k % 3 - 1, 1, S, 1, 9 + tau * 9 + k));
+    L.n_seq = n_seq; L.n_out = S; L.T = T; L.w_taps = 27; L.epi = EPI_GATED;
+    L.alpha = alpha; L.beta = beta; L.out_d = out_d;
+  }
+  L.wg = wg; L.items = items.data(); L.n_items = (int)items.size();
+  L.H = H; L.W = W; L.Cin = cin; L.Cout = cout; L.out_f32 = out_f32; L.out = out;
+  return tapconv_launch(L, (cudaStream_t)stream);
+}
+
+int ob_conv_dgrad(const void* gy, const void* gb, const void* wg, const float* alpha, const float* beta, void* dx,
+                  int n_seq, int S, int T, int H, int W, int cin, int cout, int ksize, int gated, void* stream) {
+  if (int r = check_shape("ob_conv_dgrad", n_seq, S, T, H, W, ksize, gated)) return r;
+  // transposed problem: GEMM K = cout (channels of the incoming gradient), GEMM N = cin
+  TapConvLaunch L;
+  std::vector<TapItem> items;
+  if (!gated) {
+    const int frames = n_seq * S * T;
+    set_src(L, 0, gy, 1, frames, H, W, cout);
+    for (int ky = 0; ky < ksize; ++ky)
+      for (int kx = 0; kx < ksize; ++kx) items.push_back(tap_item(0, 0, ksize / 2 - ky, ksize / 2 - kx, 1, 0, 1, ky * ksize + kx));
+    L.n_seq = 1; L.n_out = 1; L.T = frames; L.w_taps = ksize * ksize; L.epi = EPI_PLAIN;
+  } else {
+    set_src(L, 0, gy, n_seq * S, T, H, W, cout);
+    set_src(L, 1, gb, n_seq, T, H, W, cout);
+    for (int k = 0; k < 9; ++k) items.push_back(tap_item(0, 0, 1 - k / 3, 1 - k % 3, S, 0, S, k));
+    // context frame t' fed output frames t'+2-tau through tap tau; that term goes to its own accumulator and the
+    // epilogue adds it with weight beta (1 on clean rows, 0 on noised rows), so dy itself is never pre-scaled.
+    for (int tau = 0; tau < 2; ++tau)
+      for (int k = 0; k < 9; ++k) items.push_back(tap_item(1, 2 - tau, 1 - k / 3, 1 - k % 3, 1, S, 1, 9 + tau * 9 + k));
+    L.n_seq = n_seq; L.n_out = S; L.T = T; L.w_taps = 27; L.epi = EPI_GATED;
+    L.alpha = alpha; L.beta = beta;
+  }
+  L.b_mn_major = 1;
+  L.wg = wg; L.items = items.data(); L.n_items = (int)items.size();
+  L.H = H; L.W = W; L.Cin = cout; L.Cout = cin; L.out_f32 = 0; L.out = dx;
+  return tapconv_launch(L, (cudaStream_t)stream);
+}
+
+int ob_conv_wgrad_splits(int n_seq, int S, int T, int H, int W, int cin, int cout, int ksize, int gated) {
+  return wgrad_suggest_split(gated ? 27 : ksize * ksize, n_seq * S * T, H, W, cin, cout);
+}
+
+int ob_conv_wgrad(const void* gya, const void* x, const void* gb, const void* ctx, float* dwg, int n_seq, int S, int T,
+                  int H, int W, int cin, int cout, int ksize, int gated, int n_split, void* stream) {
+  if (int r = check_shape("ob_conv_wgrad", n_seq, S, T, H, W, ksize, gated)) return r;
+  WgradLaunch L;
+  std::vector<WgradItem> items;
+  auto mk = [](int pair, int dt, int dy, int dx, int wtap) {
+    WgradItem t{}; t.pair = (int8_t)pair; t.dt = (int8_t)dt; t.dy = (int8_t)dy; t.dx = (int8_t)dx; t.wtap = wtap; return t;
+  };
+  if (!gated) {
+    const int frames = n_seq * S * T;
+    L.g[0] = gya; L.a[0] = x; L.g_seq[0] = 1; L.g_T[0] = frames; L.a_T[0] = frames;
+    for (int ky = 0; ky < ksize; ++ky)
+      for (int kx = 0; kx < ksize; ++kx) items.push_back(mk(0, 0, ky - ksize / 2, kx - ksize / 2, ky * ksize + kx));
+    L.w_taps = ksize * ksize;
+  } else {
+    L.g[0] = gya; L.a[0] = x; L.g_seq[0] = n_seq * S; L.g_T[0] = T; L.a_T[0] = T;
+    L.g[1] = gb; L.a[1] = ctx; L.g_seq[1] = n_seq; L.g_T[1] = T; L.a_T[1] = T + 2;
+    for (int k = 0; k < 9; ++k) items.push_back(mk(0, 0, k / 3 - 1, k % 3 - 1, k));
+    for (int tau = 0; tau < 2; ++tau)
+      for (int k = 0; k < 9; ++k) items.push_back(mk(1, tau, k / 3 - 1, k % 3 - 1, 9 + tau * 9 + k));
+    L.w_taps = 27;
+  }
+  L.items = items.data(); L.n_items = (int)items.size();
+  L.H = H; L.W = W; L.Cin = cin; L.Cout = cout; L.n_split = n_split; L.out = dwg;
+  return wgrad_launch(L, (cudaStream_t)stream);
+}
+
+int ob_gate_bwd(const void* dy, const void* y, const void* d, const float* alpha, const float* beta, void* gya, void* gb,
+                float* s_y, float* s_d, int n_seq, int S, int T, int64_t frame_elems, void* stream) {
+  return gate_bwd(dy, y, d, alpha, beta, gya, gb, s_y, s_d, n_seq, S, T, (long)frame_elems, (cudaStream_t)stream);
+}
+int ob_pixnorm_silu_fwd(const void* x, void* xn, void* act, int64_t rows, int c, float eps, int mode, void* stream) {
+  return pixnorm_silu_fwd(x, xn, act, (long)rows, c, eps, mode, (cudaStream_t)stream);
+}
+int ob_pixnorm_silu_bwd(const void* x, const void* g_xn, const void* g_act, void* dx, int64_t rows, int c, float eps,
+                        int mode, void* stream) {
+  return pixnorm_silu_bwd(x, g_xn, g_act, dx, (long)rows, c, eps, mode, (cudaStream_t)stream);
+}
+int ob_scale_silu_fwd(const void* y, const float* cscale, void* out, int64_t rows, int c, int rows_per_frame, void* stream) {
+  return scale_silu_fwd(y, cscale, out, (long)rows, c, rows_per_frame, (cudaStream_t)stream);
+}
+int ob_scale_silu_bwd(const void* y, const float* cscale, const void* g, void* dy, float* dc, int frames, int c,
+                      int rows_per_frame, void* stream) {
+  return scale_silu_bwd(y, cscale, g, dy, dc, frames, c, rows_per_frame, (cudaStream_t)stream);
+}
+int ob_mp_sum_fwd(const void* a, const void* b, void* out, int64_t n, float t, float clip, void* stream) {
+  return mp_sum_fwd(a, b, out, (long)n, t, clip, (cudaStream_t)stream);
+}
+int ob_mp_sum_bwd(const void* g, const void* out, void* da, void* db, int64_t n, float t, float clip, void* stream) {
+  return mp_sum_bwd(g, out, da, db, (long)n, t, clip, (cudaStream_t)stream);
+}
+
+}  // extern "C"

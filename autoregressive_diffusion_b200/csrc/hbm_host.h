@@ -1,0 +1,20 @@
+// Host launchers of the bandwidth-bound kernels (hbm_kernels.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+namespace ob {
+int wnorm_fwd(float* w, void* wg, int Co, int Ci, int taps, int Ci_pad, int taps_total, int tap_off, float gain, float eps,
+              int training, cudaStream_t st);
+int wnorm_bwd(const float* w, const float* dwg, float* dw, int Co, int Ci, int taps, int Ci_pad, int taps_total,
+              int tap_off, int n_split, float gain, float eps, cudaStream_t st);
+int gate_bwd(const void* dy, const void* y, const void* d, const float* alpha, const float* beta, void* gya, void* gb,
+             float* s_y, float* s_d, int n_seq, int S, int T, long frame_elems, cudaStream_t st);
+int pixnorm_silu_fwd(const void* x, void* xn, void* act, long rows, int C, float eps, int mode, cudaStream_t st);
+int pixnorm_silu_bwd(const void* x, const void* g_xn, const void* g_act, void* dx, long rows, int C, float eps, int mode,
+                     cudaStream_t st);
+int scale_silu_fwd(const void* y, const float* cscale, void* out, long rows, int C, int rows_per_frame, cudaStream_t st);
+int scale_silu_bwd(const void* y, const float* cscale, const void* g, void* dy, float* dc, int frames, int C,
+                   int rows_per_frame, cudaStream_t st);
+int mp_sum_fwd(const void* a, const void* b, void* out, long n, float t, float clip, cudaStream_t st);
+int mp_sum_bwd(const void* g, const void* out, void* da, void* db, long n, float t, float clip, cudaStream_t st);
+}  // namespace ob

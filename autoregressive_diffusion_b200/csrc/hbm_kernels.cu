@@ -1,0 +1,526 @@
+// Bandwidth-bound kernels of the Oniris hot path: magnitude-preserving weight normalisation
+// (forward + backward), the gate backward pre-pass, pixel-norm / mp_silu / mp_sum epilogues.
+// All activations are bf16 NHWC ([rows, C], channel-contiguous); all arithmetic is fp32.
+// 128-bit global accesses, warp-shuffle reductions, one pass over HBM per tensor.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+
+#include "tapconv_host.h"
+
+namespace ob {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Block-wide sum; every thread gets the result. red must hold 32 floats.
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float t = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.f;
+  if (warp == 0) {
+    t = warp_sum(t);
+    if (lane == 0) red[0] = t;
+  }
+  __syncthreads();
+  return red[0];
+}
+
+__device__ __forceinline__ float bf2f(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+struct alignas(16) bf16x8 {
+  __nv_bfloat162 v[4];
+};
+__device__ __forceinline__ void unpack8(const bf16x8& p, float* f) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 t = __bfloat1622float2(p.v[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ bf16x8 pack8(const float* f) {
+  bf16x8 p;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) p.v[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return p;
+}
+
+// ============================================================================ weight norm
+// Reference: edm2/conv.py:14-21 (NormalizedWeight.forward) + edm2/utils.py:83-88 (normalize).
+// One CTA per output channel. w: fp32 [Co][Ci][taps]. Operand out: bf16 [Co][taps_total][Ci_pad] at tap_off,
+// i.e. transposed to tap-major / channel-minor so the conv kernels read it K-major; pad channels are zeroed.
+// training: w <- w/(eps+rms(w)) in place (forced weight norm), operand = normalize(that) * gain/sqrt(fan_in).
+// inv_out[co] receives the factor d(operand)/d(w_forced) scale needed by the backward pass.
+__global__ void __launch_bounds__(256) wnorm_fwd_kernel(float* __restrict__ w, __nv_bfloat16* __restrict__ wg, int Ci,
+                                                        int taps, int Ci_pad, int taps_total, int tap_off, float gain,
+                                                        float eps, int training) {
+  __shared__ float red[32];
+  const int co = blockIdx.x;
+  const int K = Ci * taps;
+  float* wr = w + static_cast<long>(co) * K;
+  float ss = 0.f;
+  if ((K & 3) == 0) {
+    const float4* w4 = reinterpret_cast<const float4*>(wr);
+    for (int i = threadIdx.x; i < K / 4; i += blockDim.x) {
+      float4 v = w4[i];
+      ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    }
+  } else {
+    for (int i = threadIdx.x; i < K; i += blockDim.x) ss += wr[i] * wr[i];
+  }
+  ss = block_sum(ss, red);
+  const float rms = sqrtf(ss / K);
+  float s1 = 1.f / (eps + rms);          // first normalisation
+  float scale;
+  if (training) {
+    const float rms1 = rms * s1;          // rms of the forced weights
+    scale = s1 / (eps + rms1);
+  } else {
+    scale = s1;
+  }
+  scale *= gain * rsqrtf(static_cast<float>(K));
+  // operand, gathered in destination order (tap-major) so the bf16 writes coalesce
+  __nv_bfloat16* dst = wg + (static_cast<long>(co) * taps_total + tap_off) * Ci_pad;
+  for (int j = threadIdx.x; j < taps * Ci_pad; j += blockDim.x) {
+    const int tap = j / Ci_pad, ci = j - tap * Ci_pad;
+    const float v = (ci < Ci) ? wr[ci * taps + tap] * scale : 0.f;
+    dst[j] = __float2bfloat16(v);
+  }
+  if (training) {
+    __syncthreads();  // all gathers of the old values are done before the in-place overwrite
+    for (int i = threadIdx.x; i < K; i += blockDim.x) wr[i] *= s1;
+  }
+}
+
+// Backward of operand = normalize(w) * gain/sqrt(K) w.r.t. the (forced) weights w.
+// dwg: fp32 [n_split][Co][taps_total][Ci_pad] partial sums from the wgrad kernel; dw: fp32 [Co][Ci][taps].
+//   d = eps + rms(w);  dw_i = c/d * (g_i - w_i * <g,w> / (K * rms * d))
+__global__ void __launch_bounds__(256) wnorm_bwd_kernel(const float* __restrict__ w, const float* __restrict__ dwg,
+                                                        float* __restrict__ dw, int Co, int Ci, int taps, int Ci_pad,
+                                                        int taps_total, int tap_off, int n_split, float gain, float eps) {
+  __shared__ float red[32];
+  extern __shared__ float gbuf[];  // [taps*Ci] gathered, split-reduced gradient in w's own order
+  const int co = blockIdx.x;
+  const int K = Ci * taps;
+  const float* wr = w + static_cast<long>(co) * K;
+  const long split_stride = static_cast<long>(Co) * taps_total * Ci_pad;
+  const float* gsrc = dwg + (static_cast<long>(co) * taps_total + tap_off) * Ci_pad;
+  float ss = 0.f, dot = 0.f;
+  for (int j = threadIdx.x; j < taps * Ci_pad; j += blockDim.x) {  // coalesced over the operand layout
+    const int tap = j / Ci_pad, ci = j - tap * Ci_pad;
+    if (ci >= Ci) continue;
+    float g = 0.f;
+    for (int s = 0; s < n_split; ++s) g += gsrc[s * split_stride + j];
+    const float wv = wr[ci * taps + tap];
+    gbuf[ci * taps + tap] = g;
+    ss += wv * wv;
+    dot += g * wv;
+  }
+  ss = block_sum(ss, red);
+  dot = block_sum(dot, red);
+  const float rms = sqrtf(ss / K);
+  const float d = eps + rms;
+  const float c = gain * rsqrtf(static_cast<float>(K)) / d;
+  const float proj = (rms > 0.f) ? dot / (K * rms * d) : 0.f;
+  float* dwr = dw + static_cast<long>(co) * K;
+  for (int i = threadIdx.x; i < K; i += blockDim.x) dwr[i] = c * (gbuf[i] - wr[i] * proj);
+}
+
+// ============================================================================ gate backward pre-pass
+// Reference: the mp_sum(last_frame_conv, context, gating) of edm2/conv.py:95 differentiated.
+//   y = alpha*a + beta*b  (alpha,beta per frame), saved: y (bf16) and d = b - a (fp32).
+// Produces in ONE pass over dy:  gya = alpha*dy (all frames), gb[b,t] = sum_s beta_s*dy_s (context rows),
+// and per-frame <dy,y>, <dy,d> (what the 5 gate scalars' gradients need).  S = 1 (eval-style) or 2 (clean+noised).
+__global__ void __launch_bounds__(256) gate_bwd_kernel(const __nv_bfloat16* __restrict__ dy,
+                                                       const __nv_bfloat16* __restrict__ y,
+                                                       const float* __restrict__ d,
+                                                       const float* __restrict__ alpha, const float* __restrict__ beta,
+                                                       __nv_bfloat16* __restrict__ gya, __nv_bfloat16* __restrict__ gb,
+                                                       float* __restrict__ s_y, float* __restrict__ s_d, int n_seq, int S,
+                                                       int T, long frame_elems) {
+  __shared__ float red[32];
+  const int bt = blockIdx.y;  // (b, t)
+  const int b = bt / T, t = bt - b * T;
+  const long chunk0 = static_cast<long>(blockIdx.x) * blockDim.x * 8 + threadIdx.x * 8;
+  const long stride = static_cast<long>(gridDim.x) * blockDim.x * 8;
+  float acc_b[8];
+  float sy[2] = {0.f, 0.f}, sd[2] = {0.f, 0.f};
+  for (long e = chunk0; e < frame_elems; e += stride) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc_b[j] = 0.f;
+    for (int s = 0; s < S; ++s) {
+      const long f = (static_cast<long>(b) * S + s) * T + t;
+      const long off = f * frame_elems + e;
+      float g[8], yv[8], dv[8], o[8];
+      unpack8(*reinterpret_cast<const bf16x8*>(dy + off), g);
+      unpack8(*reinterpret_cast<const bf16x8*>(y + off), yv);
+      const float4 d0 = *reinterpret_cast<const float4*>(d + off), d1 = *reinterpret_cast<const float4*>(d + off + 4);
+      dv[0] = d0.x; dv[1] = d0.y; dv[2] = d0.z; dv[3] = d0.w; dv[4] = d1.x; dv[5] = d1.y; dv[6] = d1.z; dv[7] = d1.w;
+      const float al = alpha[f], be = beta[f];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        o[j] = al * g[j];
+        acc_b[j] += be * g[j];
+        sy[s] += g[j] * yv[j];
+        sd[s] += g[j] * dv[j];
+      }
+      *reinterpret_cast<bf16x8*>(gya + off) = pack8(o);
+    }
+    *reinterpret_cast<bf16x8*>(gb + static_cast<long>(bt) * frame_elems + e) = pack8(acc_b);
+  }
+  for (int s = 0; s < S; ++s) {
+    const long f = (static_cast<long>(b) * S + s) * T + t;
+    const float a = block_sum(sy[s], red);
+    const float c = block_sum(sd[s], red);
+    if (threadIdx.x == 0) {
+      atomicAdd(&s_y[f], a);
+      atomicAdd(&s_d[f], c);
+    }
+  }
+}
+
+// ============================================================================ pixel norm (+ mp_silu)
+// Reference: edm2/networks_edm2.py:70 normalize(x, dim=1) followed by mp_silu (edm2/utils.py:112-113).
+// One warp per pixel row of C channels. Writes xn (the residual stream) and, optionally, act = mp_silu(xn).
+// mode 0: xn = normalize(x), act = mp_silu(xn).  mode 1 (decoder blocks): no norm, act = mp_silu(x) only.
+template <int MODE>
+__global__ void __launch_bounds__(256) pixnorm_silu_fwd_kernel(const __nv_bfloat16* __restrict__ x,
+                                                               __nv_bfloat16* __restrict__ xn,
+                                                               __nv_bfloat16* __restrict__ act, long rows, int C,
+                                                               float eps) {
+  const int lane = threadIdx.x & 31;
+  const long row = (static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (row >= rows) return;
+  const __nv_bfloat16* xr = x + row * C;
+  float inv = 1.f;
+  if (MODE == 0) {
+    float ss = 0.f;
+    for (int c = lane * 8; c < C; c += 256) {
+      float f[8];
+      unpack8(*reinterpret_cast<const bf16x8*>(xr + c), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) ss += f[j] * f[j];
+    }
+    ss = warp_sum(ss);
+    inv = 1.f / (eps + sqrtf(ss / C));
+  }
+  for (int c = lane * 8; c < C; c += 256) {
+    float f[8], a[8];
+    unpack8(*reinterpret_cast<const bf16x8*>(xr + c), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      f[j] *= inv;
+      a[j] = f[j] / (1.f + __expf(-f[j])) * (1.f / 0.596f);
+    }
+    if (MODE == 0) *reinterpret_cast<bf16x8*>(xn + row * C + c) = pack8(f);
+    *reinterpret_cast<bf16x8*>(act + row * C + c) = pack8(a);
+  }
+}
+
+__device__ __forceinline__ float mp_silu_grad(float v) {
+  const float sg = 1.f / (1.f + __expf(-v));
+  return sg * (1.f + v * (1.f - sg)) * (1.f / 0.596f);
+}
+
+// Backward: dx = d(normalize)(g_xn + g_act * silu'(xn)) ; mode 1: dx = g_x + g_act * silu'(x).
+//   y = x/d, d = eps + rms:  dx = (g - y * <g,y> * (1/(C*rms)) ... ) / d   (per pixel row)
+template <int MODE>
+__global__ void __launch_bounds__(256) pixnorm_silu_bwd_kernel(const __nv_bfloat16* __restrict__ x,
+                                                               const __nv_bfloat16* __restrict__ g_xn,
+                                                               const __nv_bfloat16* __restrict__ g_act,
+                                                               __nv_bfloat16* __restrict__ dx, long rows, int C,
+                                                               float eps) {
+  const int lane = threadIdx.x & 31;
+  const long row = (static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (row >= rows) return;
+  const __nv_bfloat16* xr = x + row * C;
+  float inv = 1.f, rms = 1.f, dot = 0.f;
+  if (MODE == 0) {
+    float ss = 0.f;
+    for (int c = lane * 8; c < C; c += 256) {
+      float f[8];
+      unpack8(*reinterpret_cast<const bf16x8*>(xr + c), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) ss += f[j] * f[j];
+    }
+    ss = warp_sum(ss);
+    rms = sqrtf(ss / C);
+    inv = 1.f / (eps + rms);
+    for (int c = lane * 8; c < C; c += 256) {
+      float f[8], g1[8], g2[8];
+      unpack8(*reinterpret_cast<const bf16x8*>(xr + c), f);
+      unpack8(*reinterpret_cast<const bf16x8*>(g_act + row * C + c), g2);
+      if (g_xn) unpack8(*reinterpret_cast<const bf16x8*>(g_xn + row * C + c), g1);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float yv = f[j] * inv;
+        const float g = (g_xn ? g1[j] : 0.f) + g2[j] * mp_silu_grad(yv);
+        dot += g * yv;
+      }
+    }
+    dot = warp_sum(dot);
+  }
+  const float proj = (MODE == 0 && rms > 0.f) ? dot / (C * rms) : 0.f;
+  for (int c = lane * 8; c < C; c += 256) {
+    float f[8], g1[8], g2[8], o[8];
+    unpack8(*reinterpret_cast<const bf16x8*>(xr + c), f);
+    unpack8(*reinterpret_cast<const bf16x8*>(g_act + row * C + c), g2);
+    if (g_xn) unpack8(*reinterpret_cast<const bf16x8*>(g_xn + row * C + c), g1);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float yv = f[j] * inv;
+      const float g = (g_xn ? g1[j] : 0.f) + g2[j] * mp_silu_grad(yv);
+      o[j] = (MODE == 0) ? (g - yv * proj) * inv : g;
+    }
+    *reinterpret_cast<bf16x8*>(dx + row * C + c) = pack8(o);
+  }
+}
+
+// ============================================================================ emb-scale + mp_silu
+// Reference: edm2/networks_edm2.py:75-77:  y = mp_silu(y * c[frame, channel])   (c = emb_linear(emb)+1).
+__global__ void __launch_bounds__(256) scale_silu_fwd_kernel(const __nv_bfloat16* __restrict__ y,
+                                                             const float* __restrict__ cscale,
+                                                             __nv_bfloat16* __restrict__ out, long rows, int C,
+                                                             int rows_per_frame) {
+  const long vec = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int vec_per_row = C >> 3;
+  if (vec >= rows * vec_per_row) return;
+  const long row = vec / vec_per_row;
+  const int c = static_cast<int>(vec - row * vec_per_row) << 3;
+  const long frame = row / rows_per_frame;
+  float f[8], o[8];
+  unpack8(*reinterpret_cast<const bf16x8*>(y + row * C + c), f);
+  const float4 s0 = *reinterpret_cast<const float4*>(cscale + frame * C + c);
+  const float4 s1 = *reinterpret_cast<const float4*>(cscale + frame * C + c + 4);
+  const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float z = f[j] * sc[j];
+    o[j] = z / (1.f + __expf(-z)) * (1.f / 0.596f);
+  }
+  *reinterpret_cast<bf16x8*>(out + row * C + c) = pack8(o);
+}
+
+// Backward: dy = g * silu'(y*c) * c ;  dc[frame, ch] = sum over the frame's pixels of g * silu'(y*c) * y.
+// grid = (channel groups of 8*? , frames); each CTA owns one frame and loops over its pixels so dc needs no atomics.
+__global__ void __launch_bounds__(256) scale_silu_bwd_kernel(const __nv_bfloat16* __restrict__ y,
+                                                             const float* __restrict__ cscale,
+                                                             const __nv_bfloat16* __restrict__ g,
+                                                             __nv_bfloat16* __restrict__ dy, float* __restrict__ dc, int C,
+                                                             int rows_per_frame) {
+  // thread -> (pixel lane p0, channel vector cv); blockDim.x = 256 = PL pixel lanes * CV channel vectors
+  const int frame = blockIdx.y;
+  const int cv_per_blk = min(C >> 3, 32);
+  const int pl = blockDim.x / cv_per_blk;
+  const int cv = threadIdx.x % cv_per_blk, p0 = threadIdx.x / cv_per_blk;
+  const int c = (blockIdx.x * cv_per_blk + cv) << 3;
+  __shared__ float part[256][9];
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (c < C) {
+    const float4 s0 = *reinterpret_cast<const float4*>(cscale + static_cast<long>(frame) * C + c);
+    const float4 s1 = *reinterpret_cast<const float4*>(cscale + static_cast<long>(frame) * C + c + 4);
+    const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+    for (int p = p0; p < rows_per_frame; p += pl) {
+      const long off = (static_cast<long>(frame) * rows_per_frame + p) * C + c;
+      float yv[8], gv[8], o[8];
+      unpack8(*reinterpret_cast<const bf16x8*>(y + off), yv);
+      unpack8(*reinterpret_cast<const bf16x8*>(g + off), gv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float t = gv[j] * mp_silu_grad(yv[j] * sc[j]);
+        o[j] = t * sc[j];
+        acc[j] += t * yv[j];
+      }
+      *reinterpret_cast<bf16x8*>(dy + off) = pack8(o);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) part[threadIdx.x][j] = acc[j];
+  __syncthreads();
+  if (p0 == 0 && c < C) {
+    for (int q = 1; q < pl; ++q)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += part[q * cv_per_blk + cv][j];
+    float* o = dc + static_cast<long>(frame) * C + c;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = acc[j];
+  }
+}
+
+// ============================================================================ mp_sum (+ clip)
+// Reference: edm2/utils.py:118-123 with float t, then edm2/networks_edm2.py:93 clip_(+-clip).
+//   out = clamp((a*(1-t) + b*t) / sqrt((1-t)^2+t^2), +-clip)     (clip <= 0: no clamp)
+__global__ void __launch_bounds__(256) mp_sum_fwd_kernel(const __nv_bfloat16* __restrict__ a,
+                                                         const __nv_bfloat16* __restrict__ b,
+                                                         __nv_bfloat16* __restrict__ out, long n8, float wa, float wb,
+                                                         float clip) {
+  const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  float fa[8], fb[8], o[8];
+  unpack8(reinterpret_cast<const bf16x8*>(a)[i], fa);
+  unpack8(reinterpret_cast<const bf16x8*>(b)[i], fb);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float v = fa[j] * wa + fb[j] * wb;
+    if (clip > 0.f) v = fminf(fmaxf(v, -clip), clip);
+    o[j] = v;
+  }
+  reinterpret_cast<bf16x8*>(out)[i] = pack8(o);
+}
+// Backward: gradients pass where the (saved) output is strictly inside the clip range (torch clamp semantics: <=).
+__global__ void __launch_bounds__(256) mp_sum_bwd_kernel(const __nv_bfloat16* __restrict__ g,
+                                                         const __nv_bfloat16* __restrict__ out,
+                                                         __nv_bfloat16* __restrict__ da, __nv_bfloat16* __restrict__ db,
+                                                         long n8, float wa, float wb, float clip) {
+  const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  float fg[8], fo[8], oa[8], ob_[8];
+  unpack8(reinterpret_cast<const bf16x8*>(g)[i], fg);
+  if (clip > 0.f) unpack8(reinterpret_cast<const bf16x8*>(out)[i], fo);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float v = fg[j];
+    if (clip > 0.f && (fo[j] >= clip || fo[j] <= -clip)) v = 0.f;
+    oa[j] = v * wa;
+    ob_[j] = v * wb;
+  }
+  reinterpret_cast<bf16x8*>(da)[i] = pack8(oa);
+  reinterpret_cast<bf16x8*>(db)[i] = pack8(ob_);
+}
+
+// ============================================================================ host launchers
+static int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s launch: %s", what, cudaGetErrorString(e));
+    return OB_ERR_CUDA;
+  }
+  return OB_OK;
+}
+
+int wnorm_fwd(float* w, void* wg, int Co, int Ci, int taps, int Ci_pad, int taps_total, int tap_off, float gain, float eps,
+              int training, cudaStream_t st) {
+  if (Co <= 0) return OB_OK;
+  wnorm_fwd_kernel<<<Co, 256, 0, st>>>(w, static_cast<__nv_bfloat16*>(wg), Ci, taps, Ci_pad, taps_total, tap_off, gain,
+                                       eps, training);
+  return check_launch("wnorm_fwd");
+}
+
+int wnorm_bwd(const float* w, const float* dwg, float* dw, int Co, int Ci, int taps, int Ci_pad, int taps_total,
+              int tap_off, int n_split, float gain, float eps, cudaStream_t st) {
+  if (Co <= 0) return OB_OK;
+  const size_t smem = static_cast<size_t>(Ci) * taps * sizeof(float);
+  if (smem > 200 * 1024) {
+    set_error("wnorm_bwd: row of %d x %d floats exceeds shared memory", Ci, taps);
+    return OB_ERR_UNSUPPORTED;
+  }
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    cudaFuncSetAttribute(wnorm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    configured = 200 * 1024;
+  }
+  wnorm_bwd_kernel<<<Co, 256, smem, st>>>(w, dwg, dw, Co, Ci, taps, Ci_pad, taps_total, tap_off, n_split, gain, eps);
+  return check_launch("wnorm_bwd");
+}
+
+int gate_bwd(const void* dy, const void* y, const void* d, const float* alpha, const float* beta, void* gya, void* gb,
+             float* s_y, float* s_d, int n_seq, int S, int T, long frame_elems, cudaStream_t st) {
+  if (frame_elems % 8 != 0 || S < 1 || S > 2) {
+    set_error("gate_bwd: frame size %ld must be a multiple of 8 and S in {1,2}", frame_elems);
+    return OB_ERR_INVALID;
+  }
+  if (n_seq * T <= 0) return OB_OK;
+  int bx = static_cast<int>((frame_elems / 8 + 255) / 256);
+  if (bx > 64) bx = 64;
+  dim3 grid(bx, n_seq * T);
+  gate_bwd_kernel<<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(y),
+                                        static_cast<const float*>(d), alpha, beta,
+                                        static_cast<__nv_bfloat16*>(gya), static_cast<__nv_bfloat16*>(gb), s_y, s_d, n_seq,
+                                        S, T, frame_elems);
+  return check_launch("gate_bwd");
+}
+
+int pixnorm_silu_fwd(const void* x, void* xn, void* act, long rows, int C, float eps, int mode, cudaStream_t st) {
+  if (C % 8 != 0) { set_error("pixnorm_silu: C=%d must be a multiple of 8", C); return OB_ERR_INVALID; }
+  if (rows <= 0) return OB_OK;
+  const long blocks = (rows * 32 + 255) / 256;
+  if (mode == 0)
+    pixnorm_silu_fwd_kernel<0><<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(xn),
+                                                       static_cast<__nv_bfloat16*>(act), rows, C, eps);
+  else
+    pixnorm_silu_fwd_kernel<1><<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), nullptr,
+                                                       static_cast<__nv_bfloat16*>(act), rows, C, eps);
+  return check_launch("pixnorm_silu_fwd");
+}
+
+int pixnorm_silu_bwd(const void* x, const void* g_xn, const void* g_act, void* dx, long rows, int C, float eps, int mode,
+                     cudaStream_t st) {
+  if (C % 8 != 0) { set_error("pixnorm_silu: C=%d must be a multiple of 8", C); return OB_ERR_INVALID; }
+  if (rows <= 0) return OB_OK;
+  const long blocks = (rows * 32 + 255) / 256;
+  if (mode == 0)
+    pixnorm_silu_bwd_kernel<0><<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x),
+                                                       static_cast<const __nv_bfloat16*>(g_xn),
+                                                       static_cast<const __nv_bfloat16*>(g_act),
+                                                       static_cast<__nv_bfloat16*>(dx), rows, C, eps);
+  else
+    pixnorm_silu_bwd_kernel<1><<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x),
+                                                       static_cast<const __nv_bfloat16*>(g_xn),
+                                                       static_cast<const __nv_bfloat16*>(g_act),
+                                                       static_cast<__nv_bfloat16*>(dx), rows, C, eps);
+  return check_launch("pixnorm_silu_bwd");
+}
+
+int scale_silu_fwd(const void* y, const float* cscale, void* out, long rows, int C, int rows_per_frame, cudaStream_t st) {
+  if (C % 8 != 0) { set_error("scale_silu: C=%d must be a multiple of 8", C); return OB_ERR_INVALID; }
+  if (rows <= 0) return OB_OK;
+  const long n = rows * (C / 8);
+  scale_silu_fwd_kernel<<<(n + 255) / 256, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(y), cscale,
+                                                         static_cast<__nv_bfloat16*>(out), rows, C, rows_per_frame);
+  return check_launch("scale_silu_fwd");
+}
+
+int scale_silu_bwd(const void* y, const float* cscale, const void* g, void* dy, float* dc, int frames, int C,
+                   int rows_per_frame, cudaStream_t st) {
+  if (C % 8 != 0) { set_error("scale_silu: C=%d must be a multiple of 8", C); return OB_ERR_INVALID; }
+  if (frames <= 0) return OB_OK;
+  const int cv = C / 8;
+  const int cv_per_blk = cv < 32 ? cv : 32;
+  if (256 % cv_per_blk != 0) { set_error("scale_silu_bwd: C/8=%d must divide 256 or be >=32", cv); return OB_ERR_UNSUPPORTED; }
+  dim3 grid((cv + cv_per_blk - 1) / cv_per_blk, frames);
+  scale_silu_bwd_kernel<<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(y), cscale,
+                                              static_cast<const __nv_bfloat16*>(g), static_cast<__nv_bfloat16*>(dy), dc, C,
+                                              rows_per_frame);
+  return check_launch("scale_silu_bwd");
+}
+
+int mp_sum_fwd(const void* a, const void* b, void* out, long n, float t, float clip, cudaStream_t st) {
+  if (n % 8 != 0) { set_error("mp_sum: element count %ld must be a multiple of 8", n); return OB_ERR_INVALID; }
+  if (n <= 0) return OB_OK;
+  const float nrm = 1.f / sqrtf((1.f - t) * (1.f - t) + t * t);
+  mp_sum_fwd_kernel<<<(n / 8 + 255) / 256, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(a),
+                                                         static_cast<const __nv_bfloat16*>(b),
+                                                         static_cast<__nv_bfloat16*>(out), n / 8, (1.f - t) * nrm, t * nrm,
+                                                         clip);
+  return check_launch("mp_sum_fwd");
+}
+
+int mp_sum_bwd(const void* g, const void* out, void* da, void* db, long n, float t, float clip, cudaStream_t st) {
+  if (n % 8 != 0) { set_error("mp_sum: element count %ld must be a multiple of 8", n); return OB_ERR_INVALID; }
+  if (n <= 0) return OB_OK;
+  const float nrm = 1.f / sqrtf((1.f - t) * (1.f - t) + t * t);
+  mp_sum_bwd_kernel<<<(n / 8 + 255) / 256, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(g),
+                                                         static_cast<const __nv_bfloat16*>(out),
+                                                         static_cast<__nv_bfloat16*>(da), static_cast<__nv_bfloat16*>(db),
+                                                         n / 8, (1.f - t) * nrm, t * nrm, clip);
+  return check_launch("mp_sum_bwd");
+}
+
+}  // namespace ob

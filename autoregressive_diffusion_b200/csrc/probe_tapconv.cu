@@ -25,6 +25,7 @@ struct Problem {
   int w_taps;
   std::vector<TapItem> items;
   int force_bn;
+  int bmn;
 };
 
 static TapItem mk(int src, int dt, int dy, int dx, int n_a, int acc, int seq_mul, int wtap) {
@@ -49,7 +50,13 @@ static bool run(const Problem& P, bool check, int reps) {
   size_t nw = (size_t)P.Cout * P.w_taps * P.Cin;
   std::vector<float> Wt(nw);
   std::vector<__nv_bfloat16> hw(nw);
-  for (size_t i = 0; i < nw; ++i) { Wt[i] = bf16r(frand() * 0.1f); hw[i] = __float2bfloat16(Wt[i]); }
+  // Wt is indexed [n][tap][c]; in MN-major mode the device copy is stored [c][tap][n]
+  for (size_t i = 0; i < nw; ++i) Wt[i] = bf16r(frand() * 0.1f);
+  for (int n = 0; n < P.Cout; ++n) for (int tp = 0; tp < P.w_taps; ++tp) for (int c = 0; c < P.Cin; ++c) {
+    size_t src = ((size_t)n * P.w_taps + tp) * P.Cin + c;
+    size_t dst = P.bmn ? ((size_t)c * P.w_taps + tp) * P.Cout + n : src;
+    hw[dst] = __float2bfloat16(Wt[src]);
+  }
   __nv_bfloat16* dW; cudaMalloc(&dW, nw * 2); cudaMemcpy(dW, hw.data(), nw * 2, cudaMemcpyHostToDevice);
   const int frames = P.n_seq * P.n_out * P.T;
   std::vector<float> al(frames), be(frames);
@@ -59,7 +66,7 @@ static bool run(const Problem& P, bool check, int reps) {
   cudaMemcpy(dbe, be.data(), frames * 4, cudaMemcpyHostToDevice);
   size_t nout = (size_t)frames * P.H * P.W * P.Cout;
   void* dOut; cudaMalloc(&dOut, nout * 4); cudaMemset(dOut, 0xFF, nout * 4);
-  __nv_bfloat16* dD; cudaMalloc(&dD, nout * 2); cudaMemset(dD, 0xFF, nout * 2);
+  float* dD; cudaMalloc(&dD, nout * 4); cudaMemset(dD, 0xFF, nout * 4);
 
   TapConvLaunch L;
   for (int s = 0; s < 2; ++s) {
@@ -70,7 +77,7 @@ static bool run(const Problem& P, bool check, int reps) {
   L.wg = dW; L.w_taps = P.w_taps; L.items = P.items.data(); L.n_items = (int)P.items.size();
   L.n_seq = P.n_seq; L.n_out = P.n_out; L.T = P.T; L.H = P.H; L.W = P.W; L.Cin = P.Cin; L.Cout = P.Cout;
   L.epi = P.epi; L.out_f32 = P.out_f32; L.alpha = dal; L.beta = dbe; L.out = dOut;
-  L.out_d = (P.epi == EPI_GATED) ? dD : nullptr; L.force_bn = P.force_bn;
+  L.out_d = (P.epi == EPI_GATED) ? dD : nullptr; L.force_bn = P.force_bn; L.b_mn_major = P.bmn;
 
   int rc = tapconv_launch(L, 0);
   cudaError_t e = cudaDeviceSynchronize();
@@ -87,8 +94,8 @@ static bool run(const Problem& P, bool check, int reps) {
       cudaMemcpy(hb.data(), dOut, nout * 2, cudaMemcpyDeviceToHost);
       for (size_t i = 0; i < nout; ++i) got[i] = __bfloat162float(hb[i]);
     }
-    std::vector<__nv_bfloat16> hd(nout);
-    cudaMemcpy(hd.data(), dD, nout * 2, cudaMemcpyDeviceToHost);
+    std::vector<float> hd(nout);
+    cudaMemcpy(hd.data(), dD, nout * 4, cudaMemcpyDeviceToHost);
     double max_err = 0, max_ref = 0, max_err_d = 0;
     std::vector<double> acc(n_acc);
     for (int seq = 0; seq < P.n_seq; ++seq)
@@ -114,7 +121,7 @@ static bool run(const Problem& P, bool check, int reps) {
                 if (P.epi == EPI_GATED) { ref = al[frame] * acc[o] + be[frame] * acc[P.n_out]; refd = acc[P.n_out] - acc[o]; }
                 max_ref = fmax(max_ref, fabs(ref));
                 max_err = fmax(max_err, fabs(ref - got[idx]));
-                if (P.epi == EPI_GATED) max_err_d = fmax(max_err_d, fabs(refd - __bfloat162float(hd[idx])));
+                if (P.epi == EPI_GATED) max_err_d = fmax(max_err_d, fabs(refd - hd[idx]));
               }
             }
     double rel = max_err / (max_ref + 1e-30);
@@ -158,8 +165,9 @@ static Problem plain(const char* name, int F, int H, int W, int Cin, int Cout, i
   return P;
 }
 // input-gradient shape of the gated conv: dual rows from src0, causal terms (dt=+1,+2) from src1 into acc 0
-static Problem dgrad(const char* name, int B, int n, int H, int W, int Cin, int Cout) {
+static Problem dgrad(const char* name, int B, int n, int H, int W, int Cin, int Cout, int bmn = 0) {
   Problem P{};
+  P.bmn = bmn;
   P.name = name; P.n_seq = B; P.n_out = 2; P.T = n; P.H = H; P.W = W; P.Cin = Cin; P.Cout = Cout;
   P.epi = EPI_PLAIN; P.out_f32 = 0; P.seqA[0] = B * 2; P.TA[0] = n; P.seqA[1] = B; P.TA[1] = n; P.w_taps = 27;
   for (int ky = 0; ky < 3; ++ky) for (int kx = 0; kx < 3; ++kx) P.items.push_back(mk(0, 0, ky - 1, kx - 1, 2, 0, 2, ky * 3 + kx));
@@ -187,6 +195,11 @@ int main(int argc, char** argv) {
   fails += !run(gated("gated eval c64 n256 8x8 B2 T5 bn256", 2, 1, 5, 8, 8, 64, 256, 256), true, 0);
   fails += !run(gated("gated eval decode c128 n128 4x4 B3 T1", 3, 1, 1, 4, 4, 128, 128), true, 0);
   fails += !run(dgrad("dgrad dual c128 n64 8x8 B2 n4", 2, 4, 8, 8, 128, 64), true, 0);
+  fails += !run(dgrad("dgrad dual BMN c128 n64 8x8 B2 n4", 2, 4, 8, 8, 128, 64, 1), true, 0);
+  fails += !run(dgrad("dgrad dual BMN c64 n256 4x4 B2 n8", 2, 8, 4, 4, 64, 256, 1), true, 0);
+  fails += !run(dgrad("dgrad dual BMN c32 n96 8x8 B1 n3", 1, 3, 8, 8, 32, 96, 1), true, 0);
+  fails += !run(dgrad("dgrad dual BMN c16 n32 16x16 B1 n2", 1, 2, 16, 16, 16, 32, 1), true, 0);
+  fails += !run(dgrad("dgrad dual BMN c8(16) n64 8x8 B1 n2", 1, 2, 8, 8, 16, 64, 1), true, 0);
   printf("== correctness: %d failing ==\n", fails);
   if (perf) {
     run(gated("CS 512->512 16x16 B2 n16", 2, 2, 16, 16, 16, 512, 512), false, 20);
@@ -200,6 +213,8 @@ int main(int argc, char** argv) {
     run(plain("gemm 16384x512x512 bn128", 64, 16, 16, 512, 512, 1, 0, 128), false, 20);
     run(plain("conv3x3 512->512 16x16 F64 bn256", 64, 16, 16, 512, 512, 3, 0, 256), false, 20);
     run(plain("conv3x3 512->512 16x16 F64 bn128", 64, 16, 16, 512, 512, 3, 0, 128), false, 20);
+    run(dgrad("dgrad BMN 512->512 16x16 B2 n16", 2, 16, 16, 16, 512, 512, 1), false, 20);
+    run(dgrad("dgrad BMN 128->128 32x32 B2 n16", 2, 16, 32, 32, 128, 128, 1), false, 20);
   }
   return fails;
 }

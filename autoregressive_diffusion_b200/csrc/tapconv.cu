@@ -78,44 +78,49 @@ static int pow2_ceil(int v) {
   return p;
 }
 
-template <int CHUNK, int BN>
+template <int CHUNK, int BN, bool BMN>
 static int launch_inst(const TapConvParams& p, int grid, cudaStream_t stream) {
   using Cfg = TapConvCfg<CHUNK, BN>;
-  static bool attr_set = false;  // benign race: setting twice is harmless
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(tapconv_kernel<CHUNK, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Cfg::SMEM_BYTES);
+  if constexpr (BMN && (BN % CHUNK != 0)) {
+    set_error("tapconv: MN-major weights need tile N %d to be a multiple of %d", BN, CHUNK);
+    return OB_ERR_UNSUPPORTED;
+  } else {
+    static bool attr_set = false;  // benign race: setting twice is harmless
+    if (!attr_set) {
+      cudaError_t e = cudaFuncSetAttribute(tapconv_kernel<CHUNK, BN, BMN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           Cfg::SMEM_BYTES);
+      if (e != cudaSuccess) {
+        set_error("cudaFuncSetAttribute(tapconv<%d,%d>, %d B): %s", CHUNK, BN, Cfg::SMEM_BYTES, cudaGetErrorString(e));
+        return OB_ERR_CUDA;
+      }
+      attr_set = true;
+    }
+    tapconv_kernel<CHUNK, BN, BMN><<<grid, TAPCONV_THREADS, Cfg::SMEM_BYTES, stream>>>(p);
+    cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
-      set_error("cudaFuncSetAttribute(tapconv<%d,%d>, %d B): %s", CHUNK, BN, Cfg::SMEM_BYTES, cudaGetErrorString(e));
+      set_error("tapconv<%d,%d> launch: %s", CHUNK, BN, cudaGetErrorString(e));
       return OB_ERR_CUDA;
     }
-    attr_set = true;
+    return OB_OK;
   }
-  tapconv_kernel<CHUNK, BN><<<grid, TAPCONV_THREADS, Cfg::SMEM_BYTES, stream>>>(p);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) {
-    set_error("tapconv<%d,%d> launch: %s", CHUNK, BN, cudaGetErrorString(e));
-    return OB_ERR_CUDA;
-  }
-  return OB_OK;
 }
 
-template <int CHUNK>
+template <int CHUNK, bool BMN>
 static int launch_bn(int bn, const TapConvParams& p, int grid, cudaStream_t s) {
   switch (bn) {
-    case 16: return launch_inst<CHUNK, 16>(p, grid, s);
-    case 32: return launch_inst<CHUNK, 32>(p, grid, s);
-    case 64: return launch_inst<CHUNK, 64>(p, grid, s);
-    case 128: return launch_inst<CHUNK, 128>(p, grid, s);
-    case 256: return launch_inst<CHUNK, 256>(p, grid, s);
+    case 16: return launch_inst<CHUNK, 16, BMN>(p, grid, s);
+    case 32: return launch_inst<CHUNK, 32, BMN>(p, grid, s);
+    case 64: return launch_inst<CHUNK, 64, BMN>(p, grid, s);
+    case 128: return launch_inst<CHUNK, 128, BMN>(p, grid, s);
+    case 256: return launch_inst<CHUNK, 256, BMN>(p, grid, s);
   }
   set_error("unsupported tile N %d", bn);
   return OB_ERR_UNSUPPORTED;
 }
 
 int tapconv_launch(const TapConvLaunch& L, cudaStream_t stream) {
-  if (L.Cin % 16 != 0 || L.Cout % 8 != 0) {
-    set_error("tapconv: Cin (%d) must be a multiple of 16 and Cout (%d) of 8", L.Cin, L.Cout);
+  if (L.Cin % 8 != 0 || L.Cout % 8 != 0) {
+    set_error("tapconv: Cin (%d) and Cout (%d) must be multiples of 8", L.Cin, L.Cout);
     return OB_ERR_INVALID;
   }
   if (L.n_items < 1 || L.n_items > TAPCONV_MAX_ITEMS) {
@@ -149,6 +154,7 @@ int tapconv_launch(const TapConvLaunch& L, cudaStream_t stream) {
   if (L.force_bn > 0) bn = L.force_bn;
   else
     while (bn > 32 && m_tiles * ((L.Cout + bn - 1) / bn) < 148) bn >>= 1;
+  if (L.b_mn_major && bn < chunk) bn = chunk;
   if (n_acc * bn > 512) {
     set_error("tapconv: %d accumulators x N=%d exceed TMEM", n_acc, bn);
     return OB_ERR_INVALID;
@@ -166,10 +172,16 @@ int tapconv_launch(const TapConvLaunch& L, cudaStream_t stream) {
     if (r != OB_OK) return r;
   }
   if (L.a[1] == nullptr) p.mapA[1] = p.mapA[0];
-  {
+  if (!L.b_mn_major) {  // weights [Cout][w_taps*Cin]
     uint64_t dims[2] = {(uint64_t)L.w_taps * L.Cin, (uint64_t)L.Cout};
     uint64_t str[2] = {1, (uint64_t)L.w_taps * L.Cin};
     uint32_t box[2] = {(uint32_t)chunk, (uint32_t)bn};
+    int r = encode_tmap_bf16(&p.mapB, L.wg, 2, dims, str, box);
+    if (r != OB_OK) return r;
+  } else {  // weights [Cin][w_taps*Cout] (the forward matrix of the transposed problem)
+    uint64_t dims[2] = {(uint64_t)L.w_taps * L.Cout, (uint64_t)L.Cin};
+    uint64_t str[2] = {1, (uint64_t)L.w_taps * L.Cout};
+    uint32_t box[2] = {(uint32_t)chunk, (uint32_t)chunk};
     int r = encode_tmap_bf16(&p.mapB, L.wg, 2, dims, str, box);
     if (r != OB_OK) return r;
   }
@@ -187,10 +199,17 @@ int tapconv_launch(const TapConvLaunch& L, cudaStream_t stream) {
   p.alpha = L.alpha; p.beta = L.beta; p.out = L.out; p.out_d = L.out_d;
 
   const int grid = m_tiles * p.tiles_n;
+  if (L.b_mn_major) {
+    switch (chunk) {
+      case 64: return launch_bn<64, true>(bn, p, grid, stream);
+      case 32: return launch_bn<32, true>(bn, p, grid, stream);
+      default: return launch_bn<16, true>(bn, p, grid, stream);
+    }
+  }
   switch (chunk) {
-    case 64: return launch_bn<64>(bn, p, grid, stream);
-    case 32: return launch_bn<32>(bn, p, grid, stream);
-    default: return launch_bn<16>(bn, p, grid, stream);
+    case 64: return launch_bn<64, false>(bn, p, grid, stream);
+    case 32: return launch_bn<32, false>(bn, p, grid, stream);
+    default: return launch_bn<16, false>(bn, p, grid, stream);
   }
 }
 

@@ -53,7 +53,7 @@ struct TapConvParams {
   const float* alpha;  // [n_seq*n_out*T] per output frame (EPI_GATED)
   const float* beta;
   void* out;    // [n_seq*n_out*T, H, W, Cout]
-  void* out_d;  // optional (EPI_GATED): shared - own accumulator, bf16, same shape as out
+  void* out_d;  // optional (EPI_GATED): shared - own accumulator, fp32, same shape as out
 };
 
 template <int CHUNK>
@@ -79,9 +79,13 @@ struct TapConvCfg {
   static constexpr int CW = BN >= 32 ? 32 : 16;  // epilogue column chunk
 };
 
-template <int CHUNK, int BN>
+// BMN=false: weights are [N rows][K contiguous] (forward convs).  BMN=true: weights are [K rows][N contiguous],
+// i.e. the SAME forward weight matrix read as an MN-major B operand, which is what the input-gradient pass
+// needs -- no transposed weight copy is ever materialised.
+template <int CHUNK, int BN, bool BMN>
 __global__ void __launch_bounds__(TAPCONV_THREADS, 1) tapconv_kernel(const __grid_constant__ TapConvParams p) {
   using Cfg = TapConvCfg<CHUNK, BN>;
+  static_assert(!BMN || BN % CHUNK == 0, "MN-major weights need BN to be a multiple of CHUNK");
   constexpr int STAGES = Cfg::STAGES;
   constexpr uint32_t SWZ = SwizzleFor<CHUNK>::mode;
   constexpr uint32_t SBO = 8 * Cfg::ROW_BYTES;
@@ -114,7 +118,7 @@ __global__ void __launch_bounds__(TAPCONV_THREADS, 1) tapconv_kernel(const __gri
   const int n_acc = p.n_out + (p.epi == EPI_GATED ? 1 : 0);
   uint32_t tmem_cols = 32;
   while (tmem_cols < static_cast<uint32_t>(n_acc * BN)) tmem_cols <<= 1;
-  const int n_chunks = p.Cin / CHUNK;
+  const int n_chunks = (p.Cin + CHUNK - 1) / CHUNK;  // a ragged last chunk is TMA zero-filled
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -154,7 +158,14 @@ __global__ void __launch_bounds__(TAPCONV_THREADS, 1) tapconv_kernel(const __gri
             tma_load_5d(sA + i * Cfg::A_BYTES, mapA, full_bar(stage), ck * CHUNK, w0 + item.dx, h0 + item.dy,
                         t0 + item.dt, seq * item.seq_mul + i);
           }
-          tma_load_2d(sB, &p.mapB, full_bar(stage), item.wtap * p.Cin + ck * CHUNK, n0);
+          if constexpr (!BMN) {
+            tma_load_2d(sB, &p.mapB, full_bar(stage), item.wtap * p.Cin + ck * CHUNK, n0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN / CHUNK; ++j)
+              tma_load_2d(sB + j * (CHUNK * Cfg::ROW_BYTES), &p.mapB, full_bar(stage), item.wtap * p.Cout + n0 + j * CHUNK,
+                          ck * CHUNK);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -162,7 +173,7 @@ __global__ void __launch_bounds__(TAPCONV_THREADS, 1) tapconv_kernel(const __gri
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
+      constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, BMN ? 1 : 0);
       int stage = 0;
       uint32_t phase = 0;
       uint32_t started = 0;  // bit j: accumulator j already holds a partial sum
@@ -179,7 +190,8 @@ __global__ void __launch_bounds__(TAPCONV_THREADS, 1) tapconv_kernel(const __gri
 #pragma unroll
             for (int k = 0; k < CHUNK / 16; ++k) {
               const uint64_t adesc = make_smem_desc(sA + i * Cfg::A_BYTES + k * 32, 16, SBO, SWZ);
-              const uint64_t bdesc = make_smem_desc(sB + k * 32, 16, SBO, SWZ);
+              const uint64_t bdesc = BMN ? make_smem_desc(sB + k * 2 * SBO, CHUNK * Cfg::ROW_BYTES, SBO, SWZ)
+                                         : make_smem_desc(sB + k * 32, 16, SBO, SWZ);
               umma_bf16_ss(d_tmem, adesc, bdesc, idesc, (k > 0) || ((started >> acc) & 1u));
             }
             started |= 1u << acc;
@@ -244,15 +256,13 @@ __global__ void __launch_bounds__(TAPCONV_THREADS, 1) tapconv_kernel(const __gri
                                                                 pack_bf16x2(y[j + 4], y[j + 5]), pack_bf16x2(y[j + 6], y[j + 7]));
           }
           if (p.epi == EPI_GATED && p.out_d != nullptr) {
-            __nv_bfloat16* dd = static_cast<__nv_bfloat16*>(p.out_d) + row_off + col0;
+            // fp32 on purpose: <dy, d> feeds the gate scalars' gradients and bf16 rounding of d shows up there at ~2%
+            float* dd = static_cast<float*>(p.out_d) + row_off + col0;
 #pragma unroll
-            for (int j = 0; j < CW; j += 8)
-              if (col0 + j + 8 <= p.Cout)
-                *reinterpret_cast<uint4*>(dd + j) =
-                    make_uint4(pack_bf16x2(shr[j] - own[j], shr[j + 1] - own[j + 1]),
-                               pack_bf16x2(shr[j + 2] - own[j + 2], shr[j + 3] - own[j + 3]),
-                               pack_bf16x2(shr[j + 4] - own[j + 4], shr[j + 5] - own[j + 5]),
-                               pack_bf16x2(shr[j + 6] - own[j + 6], shr[j + 7] - own[j + 7]));
+            for (int j = 0; j < CW; j += 4)
+              if (col0 + j + 4 <= p.Cout)
+                *reinterpret_cast<float4*>(dd + j) =
+                    make_float4(shr[j] - own[j], shr[j + 1] - own[j + 1], shr[j + 2] - own[j + 2], shr[j + 3] - own[j + 3]);
           }
         }
       }

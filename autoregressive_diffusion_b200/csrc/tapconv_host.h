@@ -5,9 +5,9 @@
 #include <cstdarg>
 #include <cstdint>
 
-namespace ob {
+#include "../../include/oniris_b200.h"  // OB_OK / OB_ERR_* status codes
 
-enum : int { OB_OK = 0, OB_ERR_INVALID = -1, OB_ERR_UNSUPPORTED = -2, OB_ERR_CUDA = -3 };
+namespace ob {
 
 const char* last_error();
 void set_error(const char* fmt, ...);
@@ -34,6 +34,7 @@ struct TapConvLaunch {
   void* out = nullptr;
   void* out_d = nullptr;
   int force_bn = 0;  // test hook: pin the N tile
+  int b_mn_major = 0;  // weights given as [Cin][w_taps][Cout] (input-gradient passes)
 };
 
 int tapconv_launch(const TapConvLaunch& L, cudaStream_t stream);

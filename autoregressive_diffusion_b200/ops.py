@@ -1,0 +1,257 @@
+"""torch.autograd glue over the C ABI: every Function's forward/backward is one or a few kernel launches.
+
+Tensor convention: activations are bf16 tensors of LOGICAL shape [frames, C, H, W] in channels_last memory
+format, i.e. physically [frames, H, W, C] -- the NHWC rows the kernels read.  `rows()` converts anything else.
+"""
+import math
+
+import torch
+
+from ._lib import _vp, call, query, stream_ptr
+
+BF16 = torch.bfloat16
+CL = torch.channels_last
+
+
+def rows(x):
+    """bf16 NHWC view of a logical [F, C, H, W] tensor (no copy when it already is one)."""
+    if x.dtype != BF16:
+        x = x.to(BF16)
+    if not x.is_contiguous(memory_format=CL):
+        x = x.contiguous(memory_format=CL)
+    return x
+
+
+def empty_rows(f, c, h, w, device, dtype=BF16):
+    return torch.empty((f, c, h, w), dtype=dtype, device=device, memory_format=CL)
+
+
+def pad_channels(x, mult):
+    c = x.shape[1]
+    if c % mult == 0:
+        return x
+    return rows(torch.nn.functional.pad(x, (0, 0, 0, 0, 0, mult - c % mult)))
+
+
+def _require_cuda(x):
+    if not x.is_cuda:
+        raise RuntimeError("autoregressive_diffusion_b200 runs on CUDA tensors only (no CPU fallback); got a CPU tensor")
+
+
+# ----------------------------------------------------------------------------- weights
+
+
+def ceil_to(v, m):
+    return (v + m - 1) // m * m
+
+
+def weight_operand(params, taps, cin, cin_pad, gains, training, eps=1e-4):
+    """Run ob_wnorm_fwd for each fp32 parameter [Cout, Cin, *k] and pack the bf16 operand [Cout_pad8, sum(taps), cin_pad].
+
+    Mirrors NormalizedWeight.forward (edm2/conv.py:14-21), including the in-place forced normalisation in training.
+    """
+    cout = params[0].shape[0]
+    total = sum(taps)
+    cout_pad = ceil_to(cout, 8)
+    alloc = torch.empty if cout_pad == cout else torch.zeros
+    wg = alloc((cout_pad, total, cin_pad), dtype=BF16, device=params[0].device)
+    off = 0
+    for p, t, g in zip(params, taps, gains):
+        assert p.dtype == torch.float32 and p.is_contiguous()
+        call("ob_wnorm_fwd", _vp(p), _vp(wg), cout, cin, t, cin_pad, total, off, float(g), eps, int(training), stream_ptr())
+        off += t
+    return wg
+
+
+def weight_grad(params, taps, cin, cin_pad, gains, dwg, n_split, eps=1e-4):
+    """ob_wnorm_bwd for each parameter: split-K partials dwg [n_split, Cout, sum(taps), cin_pad] -> dW like the params."""
+    cout = params[0].shape[0]
+    total = sum(taps)
+    if dwg.shape[1] != cout:      # Cout was padded to a multiple of 8: fold the splits and drop the pad rows
+        dwg = dwg.sum(0, keepdim=True)[:, :cout].contiguous()
+        n_split = 1
+    outs, off = [], 0
+    for p, t, g in zip(params, taps, gains):
+        dw = torch.empty_like(p)
+        call("ob_wnorm_bwd", _vp(p), _vp(dwg), _vp(dw), cout, cin, t, cin_pad, total, off, n_split, float(g), eps, stream_ptr())
+        outs.append(dw)
+        off += t
+    return outs
+
+
+# ----------------------------------------------------------------------------- convolutions
+
+
+class PlainConvFn(torch.autograd.Function):
+    """MPConv with a 1x1 or 3x3 kernel (edm2/conv.py:36-42): y = conv2d(x, normalize(w)*gain/sqrt(fan_in))."""
+
+    @staticmethod
+    def forward(ctx, x, w, wg, ksize, gain, out_f32):
+        f, cin_pad, h, wd = x.shape
+        cout, cout_pad = w.shape[0], wg.shape[0]
+        out = empty_rows(f, cout_pad, h, wd, x.device, torch.float32 if out_f32 else BF16)
+        call("ob_conv_fwd", _vp(x), None, _vp(wg), None, None, _vp(out), None, 1, 1, f, h, wd, cin_pad, cout_pad, ksize, 0,
+             int(out_f32), stream_ptr())
+        ctx.save_for_backward(x, w, wg)
+        ctx.ksize, ctx.gain = ksize, gain
+        return out if cout_pad == cout else out[:, :cout]
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w, wg = ctx.saved_tensors
+        f, cin_pad, h, wd = x.shape
+        cout, cin = wg.shape[0], w.shape[1]
+        k = ctx.ksize
+        gy = pad_channels(rows(gy), 8)
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            dx = empty_rows(f, cin_pad, h, wd, x.device)
+            call("ob_conv_dgrad", _vp(gy), None, _vp(wg), None, None, _vp(dx), 1, 1, f, h, wd, cin_pad, cout, k, 0, stream_ptr())
+        if ctx.needs_input_grad[1]:
+            ns = query("ob_conv_wgrad_splits", 1, 1, f, h, wd, cin_pad, cout, k, 0)
+            dwg = torch.empty((ns, cout, k * k, cin_pad), dtype=torch.float32, device=x.device)
+            call("ob_conv_wgrad", _vp(gy), _vp(x), None, None, _vp(dwg), 1, 1, f, h, wd, cin_pad, cout, k, 0, ns, stream_ptr())
+            (dw,) = weight_grad([w], [k * k], cin, cin_pad, [ctx.gain], dwg, ns)
+        return dx, dw, None, None, None, None
+
+
+class GatedConvFn(torch.autograd.Function):
+    """MPCausal3DGatedConv core (edm2/conv.py:59-95): y = alpha*conv2d(x) + beta*conv3d(context)."""
+
+    @staticmethod
+    def forward(ctx, x, cx, w2, w3, wg, alpha, beta, n_seq, S, T, want_grad):
+        f, cin_pad, h, wd = x.shape
+        cout = wg.shape[0]
+        out = empty_rows(f, cout, h, wd, x.device)
+        out_d = empty_rows(f, cout, h, wd, x.device, torch.float32) if want_grad else None
+        call("ob_conv_fwd", _vp(x), _vp(cx), _vp(wg), _vp(alpha), _vp(beta), _vp(out), _vp(out_d), n_seq, S, T, h, wd,
+             cin_pad, cout, 3, 1, 0, stream_ptr())
+        if want_grad:
+            ctx.save_for_backward(x, cx, w2, w3, wg, alpha, beta, out, out_d)
+        ctx.dims = (n_seq, S, T)
+        return out if cout == w2.shape[0] else out[:, : w2.shape[0]]
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, cx, w2, w3, wg, alpha, beta, y, d = ctx.saved_tensors
+        n_seq, S, T = ctx.dims
+        f, cin_pad, h, wd = x.shape
+        cout, cin = wg.shape[0], w2.shape[1]
+        gy = pad_channels(rows(gy), 8)
+        gya = empty_rows(f, cout, h, wd, x.device)
+        gb = empty_rows(n_seq * T, cout, h, wd, x.device)
+        sums = torch.zeros((2, f), dtype=torch.float32, device=x.device)
+        call("ob_gate_bwd", _vp(gy), _vp(y), _vp(d), _vp(alpha), _vp(beta), _vp(gya), _vp(gb), _vp(sums[0]), _vp(sums[1]),
+             n_seq, S, T, h * wd * cout, stream_ptr())
+        dx = dw2 = dw3 = dal = dbe = None
+        if ctx.needs_input_grad[0]:
+            dx = empty_rows(f, cin_pad, h, wd, x.device)
+            clean = torch.zeros((n_seq, S, T), dtype=torch.float32, device=x.device)
+            clean[:, 0] = 1.0   # the causal context was built from the clean rows only
+            call("ob_conv_dgrad", _vp(gy), _vp(gb), _vp(wg), _vp(alpha), _vp(clean), _vp(dx), n_seq, S, T, h, wd, cin_pad,
+                 cout, 3, 1, stream_ptr())
+        if ctx.needs_input_grad[2] or ctx.needs_input_grad[3]:
+            ns = query("ob_conv_wgrad_splits", n_seq, S, T, h, wd, cin_pad, cout, 3, 1)
+            dwg = torch.empty((ns, cout, 27, cin_pad), dtype=torch.float32, device=x.device)
+            call("ob_conv_wgrad", _vp(gya), _vp(x), _vp(gb), _vp(cx), _vp(dwg), n_seq, S, T, h, wd, cin_pad, cout, 3, 1, ns,
+                 stream_ptr())
+            dw2, dw3 = weight_grad([w2, w3], [9, 18], cin, cin_pad, [1.0, 1.0], dwg, ns)
+        if ctx.needs_input_grad[5] or ctx.needs_input_grad[6]:
+            # y = alpha*a + beta*b, d = b - a  =>  <dy,a> = (<dy,y> - beta*<dy,d>)/(alpha+beta), <dy,b> = <dy,a> + <dy,d>
+            dal = (sums[0] - beta * sums[1]) / (alpha + beta)
+            dbe = dal + sums[1]
+        return dx, None, dw2, dw3, None, dal, dbe, None, None, None, None
+
+
+# ----------------------------------------------------------------------------- elementwise
+
+
+class PixnormSiluFn(torch.autograd.Function):
+    """mode 0: (normalize(x, dim=1), mp_silu(normalize(x)))   [edm2/networks_edm2.py:70,73]
+       mode 1: mp_silu(x)                                       [decoder blocks skip the pixel norm]"""
+
+    @staticmethod
+    def forward(ctx, x, mode, eps):
+        f, c, h, w = x.shape
+        act = torch.empty_like(x, memory_format=CL)
+        xn = torch.empty_like(x, memory_format=CL) if mode == 0 else None
+        call("ob_pixnorm_silu_fwd", _vp(x), _vp(xn), _vp(act), f * h * w, c, eps, mode, stream_ptr())
+        ctx.save_for_backward(x)
+        ctx.mode, ctx.eps = mode, eps
+        if mode == 0:
+            return xn, act
+        return act
+
+    @staticmethod
+    def backward(ctx, *grads):
+        (x,) = ctx.saved_tensors
+        f, c, h, w = x.shape
+        if ctx.mode == 0:
+            g_xn, g_act = grads
+        else:
+            g_xn, g_act = None, grads[0]
+        g_act = rows(g_act) if g_act is not None else torch.zeros_like(x, memory_format=CL)
+        g_xn = rows(g_xn) if g_xn is not None else None
+        dx = torch.empty_like(x, memory_format=CL)
+        call("ob_pixnorm_silu_bwd", _vp(x), _vp(g_xn), _vp(g_act), _vp(dx), f * h * w, c, ctx.eps, ctx.mode, stream_ptr())
+        return dx, None, None
+
+
+class ScaleSiluFn(torch.autograd.Function):
+    """mp_silu(y * c[frame, channel])   [edm2/networks_edm2.py:75-77]"""
+
+    @staticmethod
+    def forward(ctx, y, cscale):
+        f, c, h, w = y.shape
+        out = torch.empty_like(y, memory_format=CL)
+        call("ob_scale_silu_fwd", _vp(y), _vp(cscale), _vp(out), f * h * w, c, h * w, stream_ptr())
+        ctx.save_for_backward(y, cscale)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        y, cscale = ctx.saved_tensors
+        f, c, h, w = y.shape
+        g = rows(g)
+        dy = torch.empty_like(y, memory_format=CL)
+        dc = torch.empty_like(cscale)
+        call("ob_scale_silu_bwd", _vp(y), _vp(cscale), _vp(g), _vp(dy), _vp(dc), f, c, h * w, stream_ptr())
+        return dy, dc
+
+
+class MpSumFn(torch.autograd.Function):
+    """clip(mp_sum(a, b, t))   [edm2/utils.py:118-123, edm2/networks_edm2.py:93]"""
+
+    @staticmethod
+    def forward(ctx, a, b, t, clip):
+        out = torch.empty_like(a, memory_format=CL)
+        call("ob_mp_sum_fwd", _vp(a), _vp(b), _vp(out), a.numel(), t, clip, stream_ptr())
+        ctx.t, ctx.clip = t, clip
+        if clip > 0:
+            ctx.save_for_backward(out)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        out = ctx.saved_tensors[0] if ctx.clip > 0 else None
+        g = rows(g)
+        da = torch.empty_like(g, memory_format=CL)
+        db = torch.empty_like(g, memory_format=CL)
+        call("ob_mp_sum_bwd", _vp(g), _vp(out), _vp(da), _vp(db), g.numel(), ctx.t, ctx.clip, stream_ptr())
+        return da, db, None, None
+
+
+def pixnorm_silu(x, eps=1e-4):
+    return PixnormSiluFn.apply(rows(x), 0, eps)
+
+
+def silu_only(x):
+    return PixnormSiluFn.apply(rows(x), 1, 0.0)
+
+
+def scale_silu(y, cscale):
+    return ScaleSiluFn.apply(rows(y), cscale.float().contiguous())
+
+
+def mp_sum_clip(a, b, t, clip=0.0):
+    return MpSumFn.apply(rows(a), rows(b), float(t), float(clip))

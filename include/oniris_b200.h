@@ -1,0 +1,105 @@
+/* oniris_b200.h -- C ABI of the B200-native Oniris denoiser hot path.
+ *
+ * The reference (Francesco215/autoregressive_diffusion) has no FFI: its "operator interface" for this path is
+ * the Python module API of edm2/conv.py, edm2/attention/ and edm2/utils.py, whose leaves are PyTorch library
+ * calls.  Each entry point below replaces one such leaf (or one fused group of leaves); the reference call
+ * site it stands in for is cited on every declaration (paths relative to the reference root).
+ *
+ * Conventions
+ *  - Every pointer is a DEVICE pointer unless stated otherwise.  The library never allocates, frees or keeps
+ *    caller memory; outputs and workspaces are caller-allocated.
+ *  - Activations are bf16, NHWC: [frames, H, W, C] with C contiguous ("rows x channels").  Frames are ordered
+ *    (b, s, t): batch-major, then the clean (s=0) / noised (s=1) half of the DART training sequence, then time.
+ *    S=1 means a plain (eval) sequence.
+ *  - Conv weights travel as ONE bf16 operand matrix wg[Cout][taps][Cin] produced by ob_wnorm_fwd
+ *    (taps = k*k for plain convs; 27 = 9 current-frame + 2x9 causal taps for the gated conv).
+ *  - All work is enqueued on `stream` (a cudaStream_t passed as void*); no entry point synchronises.
+ *  - Return value: 0 = ok, <0 = error (OB_ERR_*); ob_last_error() returns a thread-local message.
+ *  - Channel counts must be multiples of 8 (16 for conv inputs); the Python layer pads where the model's are not.
+ */
+#ifndef ONIRIS_B200_H
+#define ONIRIS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OB_OK 0
+#define OB_ERR_INVALID (-1)
+#define OB_ERR_UNSUPPORTED (-2)
+#define OB_ERR_CUDA (-3)
+
+int ob_version(void);
+const char* ob_last_error(void);
+
+/* ---------------------------------------------------------------------------------------------- weights
+ * edm2/conv.py:14-21 NormalizedWeight.forward (+ edm2/utils.py:83-88 normalize).
+ * w: fp32 [Cout][Cin][taps] (the nn.Parameter, row-major).  Writes the bf16 GEMM operand
+ * wg[Cout][taps_total][cin_pad] at tap offset tap_off (channels >= Cin zero-filled).  training != 0 also
+ * overwrites w in place with its forced-normalised value and normalises THAT for the operand, exactly as the
+ * reference's in-place copy_ + second normalize does. */
+int ob_wnorm_fwd(float* w, void* wg, int cout, int cin, int taps, int cin_pad, int taps_total, int tap_off, float gain,
+                 float eps, int training, void* stream);
+
+/* Backward of the above w.r.t. the (forced) weights: dwg fp32 [n_split][Cout][taps_total][cin_pad] are the
+ * split-K partial sums written by ob_conv_wgrad; dw fp32 [Cout][Cin][taps] is overwritten. */
+int ob_wnorm_bwd(const float* w, const float* dwg, float* dw, int cout, int cin, int taps, int cin_pad, int taps_total,
+                 int tap_off, int n_split, float gain, float eps, void* stream);
+
+/* ---------------------------------------------------------------------------------------------- convolutions
+ * edm2/conv.py:36-42 (MPConv: F.conv2d k=1|3) and :59-95 (MPCausal3DGatedConv: F.conv2d + F.conv3d + mp_sum).
+ *   gated == 0:  out[f] = conv_kxk(x[f], wg)                                   x: [n_seq*S*T frames, H, W, Cin]
+ *   gated != 0:  out[b,s,t] = alpha[b,s,t] * conv3x3(x[b,s,t], wg[:, 0:9])
+ *                           + beta[b,s,t]  * sum_{tau in {0,1}} conv3x3(ctx[b, t+tau], wg[:, 9+9*tau : 18+9*tau])
+ *                ctx: bf16 [n_seq, T+2, H, W, Cin] = two pad frames (ones, or the cached activations) followed
+ *                by the T clean frames; the context term is computed ONCE per (b,t) and shared by both halves.
+ *                out_d (optional, may be NULL): fp32, context term minus current-frame term (saved for backward).
+ * out: [n_seq*S*T, H, W, Cout], bf16 or (out_f32 != 0) fp32.  alpha/beta: fp32 [n_seq*S*T]. */
+int ob_conv_fwd(const void* x, const void* ctx, const void* wg, const float* alpha, const float* beta, void* out,
+                void* out_d, int n_seq, int S, int T, int H, int W, int cin, int cout, int ksize, int gated, int out_f32,
+                void* stream);
+
+/* Input gradient of ob_conv_fwd.  gy: bf16 [n_seq*S*T, H, W, Cout] = dL/dout (unscaled);
+ * gated: gb: bf16 [n_seq*T, H, W, Cout] = sum_s beta_s*dL/dout_s (from ob_gate_bwd) and
+ *        dx[b,s,t] = alpha[b,s,t] * convT3x3(gy[b,s,t]) + beta[b,s,t] * causal_convT(gb[b, t+1..t+2]),
+ *        where the caller passes beta = 1 on clean rows and 0 on noised rows (the context is built from clean rows).
+ * plain: dx = convT(gy); alpha/beta ignored (may be NULL).
+ * dx: bf16 [n_seq*S*T, H, W, Cin].  Reads the SAME wg as the forward pass (as an MN-major operand). */
+int ob_conv_dgrad(const void* gy, const void* gb, const void* wg, const float* alpha, const float* beta, void* dx,
+                  int n_seq, int S, int T, int H, int W, int cin, int cout, int ksize, int gated, void* stream);
+
+/* Weight gradient of ob_conv_fwd into dwg fp32 [n_split][Cout][taps][Cin] (taps = k*k or 27).  n_split must come
+ * from ob_conv_wgrad_splits for the same shape. */
+int ob_conv_wgrad_splits(int n_seq, int S, int T, int H, int W, int cin, int cout, int ksize, int gated);
+int ob_conv_wgrad(const void* gya, const void* x, const void* gb, const void* ctx, float* dwg, int n_seq, int S, int T,
+                  int H, int W, int cin, int cout, int ksize, int gated, int n_split, void* stream);
+
+/* Backward pre-pass of the gate (mp_sum with a per-frame tensor t, edm2/conv.py:95 -> edm2/utils.py:122-123):
+ * from dy, the saved y (bf16) and d (fp32) it emits gya = alpha*dy, gb = sum_s beta*dy and the per-frame inner products
+ * s_y[f] += <dy,y>, s_d[f] += <dy,d> (fp32 [n_seq*S*T], must be zeroed by the caller) that the five Gating
+ * scalars' gradients are built from. */
+int ob_gate_bwd(const void* dy, const void* y, const void* d, const float* alpha, const float* beta, void* gya, void* gb,
+                float* s_y, float* s_d, int n_seq, int S, int T, int64_t frame_elems, void* stream);
+
+/* ---------------------------------------------------------------------------------------------- elementwise
+ * edm2/networks_edm2.py:70 normalize(x, dim=1) + edm2/utils.py:112-113 mp_silu, one pass.
+ * mode 0: xn = x/(eps+rms_C(x)), act = mp_silu(xn).   mode 1: act = mp_silu(x) (xn unused, may be NULL). */
+int ob_pixnorm_silu_fwd(const void* x, void* xn, void* act, int64_t rows, int c, float eps, int mode, void* stream);
+int ob_pixnorm_silu_bwd(const void* x, const void* g_xn, const void* g_act, void* dx, int64_t rows, int c, float eps,
+                        int mode, void* stream);
+
+/* edm2/networks_edm2.py:75-77: out = mp_silu(y * cscale[frame, channel]); cscale fp32 [frames][C]. */
+int ob_scale_silu_fwd(const void* y, const float* cscale, void* out, int64_t rows, int c, int rows_per_frame, void* stream);
+int ob_scale_silu_bwd(const void* y, const float* cscale, const void* g, void* dy, float* dc, int frames, int c,
+                      int rows_per_frame, void* stream);
+
+/* edm2/utils.py:118-123 mp_sum with float t, fused with the clip_ of edm2/networks_edm2.py:93 (clip <= 0: none). */
+int ob_mp_sum_fwd(const void* a, const void* b, void* out, int64_t n, float t, float clip, void* stream);
+int ob_mp_sum_bwd(const void* g, const void* out, void* da, void* db, int64_t n, float t, float clip, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ONIRIS_B200_H */
