@@ -43,6 +43,7 @@ _SIGS = {
     "ob_scale_silu_bwd": "pppppiiip",
     "ob_mp_sum_fwd": "ppplffp",
     "ob_mp_sum_bwd": "pppplffp",
+    "ob_attn_fwd": "pppppiiiiiifp",
 }
 _CT = {"p": ctypes.c_void_p, "i": ctypes.c_int, "f": ctypes.c_float, "l": ctypes.c_int64}
 

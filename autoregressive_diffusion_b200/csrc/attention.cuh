@@ -1,0 +1,277 @@
+// Frame-structured attention on tcgen05/TMEM (reference: edm2/attention/attention_modules.py:59-77 --
+// compiled FlexAttention with make_train_mask / make_infer_mask, and F.scaled_dot_product_attention).
+//
+// q, k, v: bf16 [BH, L, 64] token-major, q/k already RMS-normalised and rotary-embedded, so every logit
+// q.k/8 lies in [-8, 8] (|q|,|k| <= 8 and the xPos factor of an allowed pair is <= 1).  That bound replaces
+// the running max of online softmax: p = exp(s - 8) can neither overflow nor vanish, the O accumulator in
+// TMEM is never rescaled, and the row statistic saved for backward is lse = 8 + log(sum p).
+//
+// Masks are functions of FRAME indices (token / hw), evaluated in registers; only KV tiles that contain an
+// allowed frame are visited, so the DART training mask costs n(n+1) frame pairs instead of (2n)^2.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+#include "ptx.cuh"
+
+namespace ob {
+
+enum : int { ATTN_FULL = 0, ATTN_CAUSAL = 1, ATTN_DART = 2 };
+
+constexpr int ATTN_BM = 128;  // query rows per CTA
+constexpr int ATTN_BN = 128;  // key rows per step
+constexpr int ATTN_D = 64;    // head dim
+constexpr float ATTN_SMAX = 8.0f;
+
+struct AttnParams {
+  CUtensorMap mapQ, mapK, mapV;  // 3D: (64, L, BH), box (64, 128, 1)
+  int BH, Lq, Lk;
+  int hw;         // tokens per frame
+  int n_frames;   // DART: frames per half (clean / noised)
+  int mask;
+  float scale;    // 1/sqrt(64)
+  __nv_bfloat16* o;  // [BH, Lq, 64]
+  float* lse;        // [BH, Lq]
+};
+
+// Is key frame kf visible from query frame qf?
+__device__ __forceinline__ bool frame_visible(int mask, int n, int qf, int kf) {
+  if (mask == ATTN_FULL) return true;
+  if (mask == ATTN_CAUSAL) return kf <= qf;
+  // DART (attention_masking.py:15-24): clean->clean causal, noised->strictly earlier clean, noised->itself
+  if (qf < n) return kf <= qf;
+  return (kf < qf - n) || (kf == qf);
+}
+
+// KV tiles a query tile must visit: [0, n1) and [s2, e2) (tile indices, second range may be empty).
+struct KvRange {
+  int n1, s2, e2;
+  __device__ __forceinline__ int count() const { return n1 + (e2 > s2 ? e2 - s2 : 0); }
+  __device__ __forceinline__ int tile(int j) const { return j < n1 ? j : s2 + (j - n1); }
+};
+
+__device__ __forceinline__ KvRange kv_range(const AttnParams& p, int q0) {
+  KvRange r;
+  const int kv_tiles = (p.Lk + ATTN_BN - 1) / ATTN_BN;
+  const int q_last = min(q0 + ATTN_BM, p.Lq) - 1;
+  r.s2 = r.e2 = 0;
+  if (p.mask == ATTN_FULL) {
+    r.n1 = kv_tiles;
+  } else if (p.mask == ATTN_CAUSAL) {
+    const int qf_hi = q_last / p.hw;
+    r.n1 = min(kv_tiles, ((qf_hi + 1) * p.hw + ATTN_BN - 1) / ATTN_BN);
+  } else {
+    const int n = p.n_frames;
+    const int qf_lo = q0 / p.hw, qf_hi = q_last / p.hw;
+    int end1;  // clean keys [0, end1)
+    if (qf_hi < n) end1 = (qf_hi + 1) * p.hw;                 // all rows clean
+    else {
+      end1 = (qf_hi - n) * p.hw;                               // noised rows: clean frames < qf-n
+      if (qf_lo < n) end1 = max(end1, n * p.hw);               // tile straddles the halves: clean rows see up to frame n-1
+    }
+    r.n1 = min(kv_tiles, (end1 + ATTN_BN - 1) / ATTN_BN);
+    if (qf_hi >= n) {                                          // noised rows also see their own frame
+      const int lo = max(qf_lo, n) * p.hw, hi = (qf_hi + 1) * p.hw;
+      r.s2 = max(r.n1, lo / ATTN_BN);
+      r.e2 = min(kv_tiles, (hi + ATTN_BN - 1) / ATTN_BN);
+      if (r.e2 < r.s2) r.e2 = r.s2;
+    }
+  }
+  return r;
+}
+
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+constexpr int ATTN_KV_STAGES = 3;
+constexpr int ATTN_TILE_BYTES = 128 * 128;  // [128 rows][64 bf16]
+constexpr int ATTN_SMEM_BYTES = 1024 + ATTN_TILE_BYTES /*Q*/ + ATTN_KV_STAGES * 2 * ATTN_TILE_BYTES /*K,V*/ +
+                                2 * 2 * ATTN_TILE_BYTES /*P x2*/ + 256;
+constexpr int ATTN_THREADS = 192;
+
+__global__ void __launch_bounds__(ATTN_THREADS, 1) attn_fwd_kernel(const __grid_constant__ AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sQ = base;
+  const uint32_t sKV = sQ + ATTN_TILE_BYTES;                       // stage s: K at +s*32K, V at +s*32K+16K
+  const uint32_t sP = sKV + ATTN_KV_STAGES * 2 * ATTN_TILE_BYTES;  // buffer b: two 16 KB K-major sub-tiles
+  const uint32_t bar = sP + 2 * 2 * ATTN_TILE_BYTES;
+  const uint32_t q_full = bar;
+  auto kv_full = [&](int s) { return bar + 8u * (1 + s); };
+  auto kv_empty = [&](int s) { return bar + 8u * (1 + ATTN_KV_STAGES + s); };
+  auto s_full = [&](int b) { return bar + 8u * (1 + 2 * ATTN_KV_STAGES + b); };
+  auto s_empty = [&](int b) { return bar + 8u * (3 + 2 * ATTN_KV_STAGES + b); };
+  auto p_full = [&](int b) { return bar + 8u * (5 + 2 * ATTN_KV_STAGES + b); };
+  auto p_empty = [&](int b) { return bar + 8u * (7 + 2 * ATTN_KV_STAGES + b); };
+  const uint32_t o_full = bar + 8u * (9 + 2 * ATTN_KV_STAGES);
+  const uint32_t tmem_slot = bar + 8u * (10 + 2 * ATTN_KV_STAGES);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int bh = blockIdx.y;
+  const int q0 = blockIdx.x * ATTN_BM;
+  const KvRange kr = kv_range(p, q0);
+  const int n_kv = kr.count();
+
+  if (threadIdx.x == 0) {
+    mbar_init(q_full, 1);
+    for (int s = 0; s < ATTN_KV_STAGES; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(s_full(b), 1); mbar_init(s_empty(b), 4); mbar_init(p_full(b), 4); mbar_init(p_empty(b), 1); }
+    mbar_init(o_full, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&p.mapQ); tma_prefetch_desc(&p.mapK); tma_prefetch_desc(&p.mapV);
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem) : "r"(tmem_slot));
+  const uint32_t tS0 = tmem, tO = tmem + 256;  // S buffers at cols [0,128) and [128,256); O at [256,320)
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(q_full, ATTN_TILE_BYTES);
+      tma_load_3d(sQ, &p.mapQ, q_full, 0, q0, bh);
+      for (int j = 0; j < n_kv; ++j) {
+        const int st = j % ATTN_KV_STAGES;
+        mbar_wait(kv_empty(st), ((j / ATTN_KV_STAGES) & 1) ^ 1);
+        const uint32_t sK = sKV + st * 2 * ATTN_TILE_BYTES, sV = sK + ATTN_TILE_BYTES;
+        mbar_arrive_expect_tx(kv_full(st), 2 * ATTN_TILE_BYTES);
+        const int k0 = kr.tile(j) * ATTN_BN;
+        tma_load_3d(sK, &p.mapK, kv_full(st), 0, k0, bh);
+        tma_load_3d(sV, &p.mapV, kv_full(st), 0, k0, bh);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && n_kv > 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, ATTN_BN, 0, 0);
+      constexpr uint32_t idesc_o = make_idesc_bf16(128, ATTN_D, 0, 1);
+      auto issue_s = [&](int j) {
+        const int st = j % ATTN_KV_STAGES, b = j & 1;
+        mbar_wait(kv_full(st), (j / ATTN_KV_STAGES) & 1);
+        if (j >= 2) mbar_wait(s_empty(b), ((j >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t sK = sKV + st * 2 * ATTN_TILE_BYTES;
+#pragma unroll
+        for (int k = 0; k < ATTN_D / 16; ++k)
+          umma_bf16_ss(tS0 + b * ATTN_BN, make_smem_desc(sQ + k * 32, 16, 1024, SWZ_128B),
+                       make_smem_desc(sK + k * 32, 16, 1024, SWZ_128B), idesc_s, k > 0);
+        umma_commit(s_full(b));
+      };
+      mbar_wait(q_full, 0);
+      issue_s(0);
+      for (int j = 0; j < n_kv; ++j) {
+        if (j + 1 < n_kv) issue_s(j + 1);
+        const int st = j % ATTN_KV_STAGES, b = j & 1;
+        mbar_wait(p_full(b), (j >> 1) & 1);
+        tc_fence_after();
+        const uint32_t sV = sKV + st * 2 * ATTN_TILE_BYTES + ATTN_TILE_BYTES;
+        const uint32_t sPb = sP + b * 2 * ATTN_TILE_BYTES;
+#pragma unroll
+        for (int kk = 0; kk < ATTN_BN / 16; ++kk)
+          umma_bf16_ss(tO, make_smem_desc(sPb + (kk >> 2) * ATTN_TILE_BYTES + (kk & 3) * 32, 16, 1024, SWZ_128B),
+                       make_smem_desc(sV + kk * 2048, ATTN_TILE_BYTES, 1024, SWZ_128B), idesc_o, (j > 0) || (kk > 0));
+        umma_commit(kv_empty(st));
+        umma_commit(p_empty(b));
+      }
+      umma_commit(o_full);
+    }
+  } else {
+    const int qw = warp & 3;
+    const int r = qw * 32 + lane;          // row of the tile == TMEM lane
+    const int iq = q0 + r;
+    const int qf = iq / p.hw;
+    const uint32_t lane_off = static_cast<uint32_t>(qw * 32) << 16;
+    const float c1 = p.scale * 1.4426950408889634f, c2 = ATTN_SMAX * 1.4426950408889634f;
+    float l = 0.f;
+    for (int j = 0; j < n_kv; ++j) {
+      const int b = j & 1;
+      const int k0 = kr.tile(j) * ATTN_BN;
+      mbar_wait(s_full(b), (j >> 1) & 1);
+      tc_fence_after();
+      if (j >= 2) mbar_wait(p_empty(b), ((j >> 1) & 1) ^ 1);
+      const uint32_t sPb = sP + b * 2 * ATTN_TILE_BYTES;
+      // does this row see EVERY key of the tile?  (then the per-element frame test is skipped)
+      bool all_vis;
+      {
+        const int kf_a = k0 / p.hw, kf_b = (k0 + ATTN_BN - 1) / p.hw;
+        all_vis = (k0 + ATTN_BN <= p.Lk);
+        if (p.mask == ATTN_CAUSAL) all_vis = all_vis && (kf_b <= qf);
+        else if (p.mask == ATTN_DART)
+          all_vis = all_vis && ((qf < p.n_frames) ? (kf_b <= qf) : ((kf_b < qf - p.n_frames) || (kf_a == qf && kf_b == qf)));
+      }
+#pragma unroll 1
+      for (int c = 0; c < ATTN_BN / 32; ++c) {
+        float s[32];
+        tmem_ld32(tS0 + lane_off + b * ATTN_BN + c * 32, s);
+        tmem_ld_wait();
+        uint32_t packed[16];
+        const int ik0 = k0 + c * 32;
+        int kf = ik0 / p.hw;
+        int rem = ik0 - kf * p.hw;
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float pv[2];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            bool ok = true;
+            if (!all_vis) {
+              ok = (ik0 + i + u < p.Lk) && frame_visible(p.mask, p.n_frames, qf, kf);
+              if (++rem == p.hw) { rem = 0; ++kf; }
+            }
+            pv[u] = ok ? fast_exp2(s[i + u] * c1 - c2) : 0.f;
+          }
+          const uint32_t pk = pack_bf16x2(pv[0], pv[1]);
+          packed[i >> 1] = pk;
+          // accumulate what the tensor core will actually see
+          l += __uint_as_float(pk << 16) + __uint_as_float(pk & 0xffff0000u);
+        }
+        // columns [c*32, c*32+32) of the P tile: sub-tile c>>1, 16-byte chunks (c&1)*4 .. +3, 128B-swizzled
+        const uint32_t row_base = sPb + (c >> 1) * ATTN_TILE_BYTES + r * 128;
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          const uint32_t chunk = static_cast<uint32_t>((c & 1) * 4 + ch) ^ static_cast<uint32_t>(r & 7);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row_base + (chunk << 4)), "r"(packed[ch * 4]),
+                       "r"(packed[ch * 4 + 1]), "r"(packed[ch * 4 + 2]), "r"(packed[ch * 4 + 3])
+                       : "memory");
+        }
+      }
+      tc_fence_before();
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(s_empty(b)); mbar_arrive(p_full(b)); }
+    }
+    // epilogue: O / l
+    if (n_kv > 0) {
+      mbar_wait(o_full, 0);
+      tc_fence_after();
+    }
+    const float inv_l = l > 0.f ? 1.f / l : 0.f;
+    __nv_bfloat16* orow = p.o + (static_cast<long>(bh) * p.Lq + iq) * ATTN_D;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      float o[32];
+      if (n_kv > 0) { tmem_ld32(tO + lane_off + c * 32, o); tmem_ld_wait(); }
+      else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[i] = 0.f;
+      }
+      if (iq < p.Lq) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 8)
+          *reinterpret_cast<uint4*>(orow + c * 32 + i) =
+              make_uint4(pack_bf16x2(o[i] * inv_l, o[i + 1] * inv_l), pack_bf16x2(o[i + 2] * inv_l, o[i + 3] * inv_l),
+                         pack_bf16x2(o[i + 4] * inv_l, o[i + 5] * inv_l), pack_bf16x2(o[i + 6] * inv_l, o[i + 7] * inv_l));
+      }
+    }
+    if (iq < p.Lq && p.lse != nullptr) p.lse[static_cast<long>(bh) * p.Lq + iq] = ATTN_SMAX + __logf(fmaxf(l, 1e-37f));
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+}
+
+}  // namespace ob

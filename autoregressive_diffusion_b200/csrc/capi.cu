@@ -10,6 +10,11 @@
 
 using namespace ob;
 
+namespace ob {
+int attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int BH, int Lq, int Lk, int hw, int n_frames,
+             int mask, float scale, cudaStream_t st);
+}
+
 static TapItem tap_item(int src, int dt, int dy, int dx, int n_a, int acc, int seq_mul, int wtap) {
   TapItem t{};
   t.src = (int8_t)src; t.dt = (int8_t)dt; t.dy = (int8_t)dy; t.dx = (int8_t)dx;
@@ -153,6 +158,11 @@ int ob_mp_sum_fwd(const void* a, const void* b, void* out, int64_t n, float t, f
 }
 int ob_mp_sum_bwd(const void* g, const void* out, void* da, void* db, int64_t n, float t, float clip, void* stream) {
   return mp_sum_bwd(g, out, da, db, (long)n, t, clip, (cudaStream_t)stream);
+}
+
+int ob_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int bh, int lq, int lk, int hw,
+                int n_frames, int mask, float scale, void* stream) {
+  return attn_fwd(q, k, v, o, lse, bh, lq, lk, hw, n_frames, mask, scale, (cudaStream_t)stream);
 }
 
 }  // extern "C"

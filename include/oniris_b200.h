@@ -99,6 +99,19 @@ int ob_scale_silu_bwd(const void* y, const float* cscale, const void* g, void* d
 int ob_mp_sum_fwd(const void* a, const void* b, void* out, int64_t n, float t, float clip, void* stream);
 int ob_mp_sum_bwd(const void* g, const void* out, void* da, void* db, int64_t n, float t, float clip, void* stream);
 
+/* ---------------------------------------------------------------------------------------------- attention
+ * edm2/attention/attention_modules.py:59-77: compiled_flex_attention(q,k,v, make_train_mask / make_infer_mask) and
+ * F.scaled_dot_product_attention.  q: bf16 [BH, Lq, 64], k,v: bf16 [BH, Lk, 64], token-major; q,k RMS-normalised and
+ * rotary-embedded by the caller (logits bounded by 8, which the kernel relies on).  mask: OB_ATTN_FULL (one new
+ * frame vs the whole cache; per-frame attention), OB_ATTN_CAUSAL (frame-causal prefill, InferenceMask
+ * attention_masking.py:56-62) or OB_ATTN_DART (TrainingMask attention_masking.py:8-24 over 2*n_frames frames).
+ * hw = tokens per frame.  o: bf16 [BH, Lq, 64]; lse: fp32 [BH, Lq] (log-sum-exp of the scaled logits), may be NULL. */
+#define OB_ATTN_FULL 0
+#define OB_ATTN_CAUSAL 1
+#define OB_ATTN_DART 2
+int ob_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int bh, int lq, int lk, int hw,
+                int n_frames, int mask, float scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
