@@ -44,6 +44,7 @@ _SIGS = {
     "ob_mp_sum_fwd": "ppplffp",
     "ob_mp_sum_bwd": "pppplffp",
     "ob_attn_fwd": "pppppiiiiiifp",
+    "ob_attn_bwd": "ppppppppppiiiiiifp",
 }
 _CT = {"p": ctypes.c_void_p, "i": ctypes.c_int, "f": ctypes.c_float, "l": ctypes.c_int64}
 

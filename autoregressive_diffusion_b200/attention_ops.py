@@ -15,3 +15,31 @@ def attn_fwd(q, k, v, hw, n_frames, mask):
     lse = torch.empty((bh, lq), dtype=torch.float32, device=q.device)
     call("ob_attn_fwd", _vp(q), _vp(k), _vp(v), _vp(o), _vp(lse), bh, lq, lk, hw, n_frames, mask, 0.125, stream_ptr())
     return o, lse
+
+
+def attn_bwd(q, k, v, o, lse, dout, hw, n_frames, mask):
+    """Gradients (dq, dk, dv) of attn_fwd; all bf16 [BH, L, 64] contiguous."""
+    bh, lq, _ = q.shape
+    lk = k.shape[1]
+    dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+    dsum = torch.empty((bh, lq), dtype=torch.float32, device=q.device)
+    call("ob_attn_bwd", _vp(q), _vp(k), _vp(v), _vp(o), _vp(dout), _vp(lse), _vp(dsum), _vp(dq), _vp(dk), _vp(dv), bh, lq, lk,
+         hw, n_frames, mask, 0.125, stream_ptr())
+    return dq, dk, dv
+
+
+class AttentionFn(torch.autograd.Function):
+    """Frame-masked attention over token-major q, k, v (attention_modules.py:66,70,75)."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, hw, n_frames, mask):
+        o, lse = attn_fwd(q, k, v, hw, n_frames, mask)
+        ctx.save_for_backward(q, k, v, o, lse)
+        ctx.cfg = (hw, n_frames, mask)
+        return o
+
+    @staticmethod
+    def backward(ctx, do):
+        q, k, v, o, lse = ctx.saved_tensors
+        dq, dk, dv = attn_bwd(q, k, v, o, lse, do.contiguous(), *ctx.cfg)
+        return dq, dk, dv, None, None, None

@@ -1,5 +1,6 @@
 // Host side of the attention kernels.
 #include "attention.cuh"
+#include "attention_bwd.cuh"
 
 #include <cstring>
 
@@ -7,10 +8,10 @@
 
 namespace ob {
 
-static int make_qkv_map(CUtensorMap* m, const void* ptr, int BH, int L) {
+static int make_qkv_map(CUtensorMap* m, const void* ptr, int BH, int L, int box_rows = 128) {
   uint64_t dims[3] = {64, (uint64_t)L, (uint64_t)BH};
   uint64_t str[3] = {1, 64, (uint64_t)L * 64};
-  uint32_t box[3] = {64, 128, 1};
+  uint32_t box[3] = {64, (uint32_t)box_rows, 1};
   return encode_tmap_bf16(m, ptr, 3, dims, str, box);
 }
 
@@ -39,6 +40,45 @@ int attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, i
   attn_fwd_kernel<<<grid, ATTN_THREADS, ATTN_SMEM_BYTES, st>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("attn_fwd launch: %s", cudaGetErrorString(e)); return OB_ERR_CUDA; }
+  return OB_OK;
+}
+
+int attn_bwd(const void* q, const void* k, const void* v, const void* o, const void* dout, const float* lse, float* dsum,
+             void* dq, void* dk, void* dv, int BH, int Lq, int Lk, int hw, int n_frames, int mask, float scale,
+             cudaStream_t st) {
+  if (BH <= 0 || Lq <= 0 || Lk <= 0) return OB_OK;
+  if (hw <= 0 || mask < ATTN_FULL || mask > ATTN_DART || (mask == ATTN_DART && (n_frames <= 0 || Lq != Lk || Lq != 2 * n_frames * hw)) ||
+      (mask == ATTN_CAUSAL && Lq != Lk)) {
+    set_error("attn_bwd: inconsistent arguments (Lq=%d Lk=%d hw=%d n_frames=%d mask=%d)", Lq, Lk, hw, n_frames, mask);
+    return OB_ERR_INVALID;
+  }
+  AttnBwdParams p;
+  memset(&p, 0, sizeof(p));
+  if (int r = make_qkv_map(&p.mapQ128, q, BH, Lq, 128)) return r;
+  if (int r = make_qkv_map(&p.mapdO128, dout, BH, Lq, 128)) return r;
+  if (int r = make_qkv_map(&p.mapK64, k, BH, Lk, 64)) return r;
+  if (int r = make_qkv_map(&p.mapV64, v, BH, Lk, 64)) return r;
+  if (int r = make_qkv_map(&p.mapK128, k, BH, Lk, 128)) return r;
+  if (int r = make_qkv_map(&p.mapV128, v, BH, Lk, 128)) return r;
+  if (int r = make_qkv_map(&p.mapQ64, q, BH, Lq, 64)) return r;
+  if (int r = make_qkv_map(&p.mapdO64, dout, BH, Lq, 64)) return r;
+  p.BH = BH; p.Lq = Lq; p.Lk = Lk; p.hw = hw; p.n_frames = n_frames; p.mask = mask; p.scale = scale;
+  p.lse = lse; p.dsum = dsum;
+  p.dq = static_cast<__nv_bfloat16*>(dq); p.dk = static_cast<__nv_bfloat16*>(dk); p.dv = static_cast<__nv_bfloat16*>(dv);
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ABW_DQ_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ABW_DKV_SMEM);
+    if (e != cudaSuccess) { set_error("attn_bwd smem attr: %s", cudaGetErrorString(e)); return OB_ERR_CUDA; }
+    attr = true;
+  }
+  const long rows = static_cast<long>(BH) * Lq;
+  attn_bwd_prep_kernel<<<(rows * 8 + 255) / 256, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(o),
+                                                               static_cast<const __nv_bfloat16*>(dout), dsum, rows);
+  attn_bwd_dq_kernel<<<dim3((Lq + ABW_BM - 1) / ABW_BM, BH), ABW_THREADS, ABW_DQ_SMEM, st>>>(p);
+  attn_bwd_dkv_kernel<<<dim3((Lk + ABW_BM - 1) / ABW_BM, BH), ABW_THREADS, ABW_DKV_SMEM, st>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error("attn_bwd launch: %s", cudaGetErrorString(e)); return OB_ERR_CUDA; }
   return OB_OK;
 }
 

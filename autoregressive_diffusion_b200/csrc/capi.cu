@@ -13,6 +13,9 @@ using namespace ob;
 namespace ob {
 int attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int BH, int Lq, int Lk, int hw, int n_frames,
              int mask, float scale, cudaStream_t st);
+int attn_bwd(const void* q, const void* k, const void* v, const void* o, const void* dout, const float* lse, float* dsum,
+             void* dq, void* dk, void* dv, int BH, int Lq, int Lk, int hw, int n_frames, int mask, float scale,
+             cudaStream_t st);
 }
 
 static TapItem tap_item(int src, int dt, int dy, int dx, int n_a, int acc, int seq_mul, int wtap) {
@@ -163,6 +166,12 @@ int ob_mp_sum_bwd(const void* g, const void* out, void* da, void* db, int64_t n,
 int ob_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int bh, int lq, int lk, int hw,
                 int n_frames, int mask, float scale, void* stream) {
   return attn_fwd(q, k, v, o, lse, bh, lq, lk, hw, n_frames, mask, scale, (cudaStream_t)stream);
+}
+
+int ob_attn_bwd(const void* q, const void* k, const void* v, const void* o, const void* dout, const float* lse,
+                float* dsum, void* dq, void* dk, void* dv, int bh, int lq, int lk, int hw, int n_frames, int mask,
+                float scale, void* stream) {
+  return attn_bwd(q, k, v, o, dout, lse, dsum, dq, dk, dv, bh, lq, lk, hw, n_frames, mask, scale, (cudaStream_t)stream);
 }
 
 }  // extern "C"

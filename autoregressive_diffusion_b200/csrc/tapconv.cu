@@ -45,6 +45,13 @@ static CUtensorMapSwizzle swizzle_for_bytes(int inner_bytes) {
 
 int encode_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_elems,
                      const uint32_t* box) {
+  // cuTensorMapEncodeTiled is a driver call: it needs the primary context to be current on THIS host thread
+  // (autograd's backward threads may reach us before making any runtime call of their own).
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) {
+    cudaFree(nullptr);
+    ctx_bound = true;
+  }
   auto enc = get_encode();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled entry point not available");

@@ -112,6 +112,13 @@ int ob_mp_sum_bwd(const void* g, const void* out, void* da, void* db, int64_t n,
 int ob_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int bh, int lq, int lk, int hw,
                 int n_frames, int mask, float scale, void* stream);
 
+/* Backward of ob_attn_fwd (autograd of the same reference calls).  o, lse: the forward's outputs; dout: bf16
+ * [BH, Lq, 64]; dsum: fp32 [BH, Lq] workspace (receives rowsum(dout*o)).  Writes dq [BH,Lq,64], dk, dv [BH,Lk,64] bf16.
+ * Every output element is produced by exactly one CTA (no atomics, deterministic). */
+int ob_attn_bwd(const void* q, const void* k, const void* v, const void* o, const void* dout, const float* lse,
+                float* dsum, void* dq, void* dk, void* dv, int bh, int lq, int lk, int hw, int n_frames, int mask,
+                float scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

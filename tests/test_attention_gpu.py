@@ -58,3 +58,21 @@ def test_attn_fwd(kind, bh, lq, lk, hw, n):
     o, lse = A.attn_fwd(q.cuda().to(torch.bfloat16), k.cuda().to(torch.bfloat16), v.cuda().to(torch.bfloat16), hw, n, kind)
     assert_close(o.float(), ref, "o")
     assert_close(lse, lse_ref, "lse", 1e-3, 1e-4)
+
+
+@pytest.mark.parametrize("kind,bh,lq,lk,hw,n", CASES)
+def test_attn_bwd(kind, bh, lq, lk, hw, n):
+    from autoregressive_diffusion_b200 import attention_ops as A
+    q, k, v = _qkv(bh, lq, lk, seed=1)
+    do = bf16r(torch.randn(bh, lq, 64, generator=torch.Generator().manual_seed(5)))
+    qr, kr_, vr = (t.clone().requires_grad_(True) for t in (q, k, v))
+    ref = O._dense_attention(qr, kr_, vr, _mask(kind, lq, lk, hw, n))
+    ref.backward(do)
+    qg, kg, vg = (t.cuda().to(torch.bfloat16).requires_grad_(True) for t in (q, k, v))
+    o = A.AttentionFn.apply(qg, kg, vg, hw, n, kind)
+    o.backward(do.cuda().to(torch.bfloat16))
+    assert_close(o.float(), ref, "o")
+    # one extra bf16 rounding sits inside (P and dS are rounded before their second GEMM): mean budget 3e-3
+    assert_close(qg.grad.float(), qr.grad, "dq", mean_rel=3e-3)
+    assert_close(kg.grad.float(), kr_.grad, "dk", mean_rel=3e-3)
+    assert_close(vg.grad.float(), vr.grad, "dv", mean_rel=3e-3)
