@@ -43,8 +43,11 @@ _SIGS = {
     "ob_scale_silu_bwd": "pppppiiip",
     "ob_mp_sum_fwd": "ppplffp",
     "ob_mp_sum_bwd": "pppplffp",
-    "ob_attn_fwd": "pppppiiiiiifp",
-    "ob_attn_bwd": "ppppppppppiiiiiifp",
+    "ob_qkv_prep_fwd": "pppppppppplliifp".replace("ll", "l"),
+    "ob_qkv_prep_bwd": "ppppppppppliifp",
+    "ob_rope_k": "ppppppliip",
+    "ob_attn_fwd": "pppppiiiiiiifp",
+    "ob_attn_bwd": "ppppppppppiiiiiiifp",
 }
 _CT = {"p": ctypes.c_void_p, "i": ctypes.c_int, "f": ctypes.c_float, "l": ctypes.c_int64}
 

@@ -7,24 +7,25 @@ FULL, CAUSAL, DART = 0, 1, 2
 
 
 def attn_fwd(q, k, v, hw, n_frames, mask):
-    """q [BH, Lq, 64], k/v [BH, Lk, 64] bf16 contiguous -> (o [BH, Lq, 64] bf16, lse [BH, Lq] fp32)."""
-    bh, lq, d = q.shape
+    """q [B, Lq, heads, 64], k/v [B, Lk, heads, 64] bf16 contiguous -> (o like q, lse [B, heads, Lq] fp32)."""
+    b, lq, heads, d = q.shape
     lk = k.shape[1]
     assert d == 64, "the attention kernels are specialised for 64 channels per head (the reference default)"
+    assert q.is_contiguous() and k.is_contiguous() and v.is_contiguous()
     o = torch.empty_like(q)
-    lse = torch.empty((bh, lq), dtype=torch.float32, device=q.device)
-    call("ob_attn_fwd", _vp(q), _vp(k), _vp(v), _vp(o), _vp(lse), bh, lq, lk, hw, n_frames, mask, 0.125, stream_ptr())
+    lse = torch.empty((b, heads, lq), dtype=torch.float32, device=q.device)
+    call("ob_attn_fwd", _vp(q), _vp(k), _vp(v), _vp(o), _vp(lse), b, heads, lq, lk, hw, n_frames, mask, 0.125, stream_ptr())
     return o, lse
 
 
 def attn_bwd(q, k, v, o, lse, dout, hw, n_frames, mask):
-    """Gradients (dq, dk, dv) of attn_fwd; all bf16 [BH, L, 64] contiguous."""
-    bh, lq, _ = q.shape
+    """Gradients (dq, dk, dv) of attn_fwd; all bf16 [B, L, heads, 64] contiguous."""
+    b, lq, heads, _ = q.shape
     lk = k.shape[1]
     dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
-    dsum = torch.empty((bh, lq), dtype=torch.float32, device=q.device)
-    call("ob_attn_bwd", _vp(q), _vp(k), _vp(v), _vp(o), _vp(dout), _vp(lse), _vp(dsum), _vp(dq), _vp(dk), _vp(dv), bh, lq, lk,
-         hw, n_frames, mask, 0.125, stream_ptr())
+    dsum = torch.empty((b, heads, lq), dtype=torch.float32, device=q.device)
+    call("ob_attn_bwd", _vp(q), _vp(k), _vp(v), _vp(o), _vp(dout), _vp(lse), _vp(dsum), _vp(dq), _vp(dk), _vp(dv), b, heads,
+         lq, lk, hw, n_frames, mask, 0.125, stream_ptr())
     return dq, dk, dv
 
 

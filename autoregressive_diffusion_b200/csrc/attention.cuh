@@ -1,7 +1,7 @@
 // Frame-structured attention on tcgen05/TMEM (reference: edm2/attention/attention_modules.py:59-77 --
 // compiled FlexAttention with make_train_mask / make_infer_mask, and F.scaled_dot_product_attention).
 //
-// q, k, v: bf16 [BH, L, 64] token-major, q/k already RMS-normalised and rotary-embedded, so every logit
+// q, k, v: bf16 [B, L, heads, 64] (token-major rows of heads*64 channels -- the NHWC activation layout), q/k already RMS-normalised and rotary-embedded, so every logit
 // q.k/8 lies in [-8, 8] (|q|,|k| <= 8 and the xPos factor of an allowed pair is <= 1).  That bound replaces
 // the running max of online softmax: p = exp(s - 8) can neither overflow nor vanish, the O accumulator in
 // TMEM is never rescaled, and the row statistic saved for backward is lse = 8 + log(sum p).
@@ -24,13 +24,13 @@ constexpr int ATTN_D = 64;    // head dim
 constexpr float ATTN_SMAX = 8.0f;
 
 struct AttnParams {
-  CUtensorMap mapQ, mapK, mapV;  // 3D: (64, L, BH), box (64, 128, 1)
-  int BH, Lq, Lk;
+  CUtensorMap mapQ, mapK, mapV;  // 4D: (64, L, heads, B), box (64, 128, 1, 1)
+  int BH, heads, Lq, Lk;
   int hw;         // tokens per frame
   int n_frames;   // DART: frames per half (clean / noised)
   int mask;
   float scale;    // 1/sqrt(64)
-  __nv_bfloat16* o;  // [BH, Lq, 64]
+  __nv_bfloat16* o;  // [B, Lq, heads, 64]
   float* lse;        // [BH, Lq]
 };
 
@@ -111,6 +111,7 @@ __global__ void __launch_bounds__(ATTN_THREADS, 1) attn_fwd_kernel(const __grid_
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int bh = blockIdx.y;
+  const int bb = bh / p.heads, hh = bh - bb * p.heads;
   const int q0 = blockIdx.x * ATTN_BM;
   const KvRange kr = kv_range(p, q0);
   const int n_kv = kr.count();
@@ -134,15 +135,15 @@ __global__ void __launch_bounds__(ATTN_THREADS, 1) attn_fwd_kernel(const __grid_
   if (warp == 0) {
     if (lane == 0) {
       mbar_arrive_expect_tx(q_full, ATTN_TILE_BYTES);
-      tma_load_3d(sQ, &p.mapQ, q_full, 0, q0, bh);
+      tma_load_4d(sQ, &p.mapQ, q_full, 0, q0, hh, bb);
       for (int j = 0; j < n_kv; ++j) {
         const int st = j % ATTN_KV_STAGES;
         mbar_wait(kv_empty(st), ((j / ATTN_KV_STAGES) & 1) ^ 1);
         const uint32_t sK = sKV + st * 2 * ATTN_TILE_BYTES, sV = sK + ATTN_TILE_BYTES;
         mbar_arrive_expect_tx(kv_full(st), 2 * ATTN_TILE_BYTES);
         const int k0 = kr.tile(j) * ATTN_BN;
-        tma_load_3d(sK, &p.mapK, kv_full(st), 0, k0, bh);
-        tma_load_3d(sV, &p.mapV, kv_full(st), 0, k0, bh);
+        tma_load_4d(sK, &p.mapK, kv_full(st), 0, k0, hh, bb);
+        tma_load_4d(sV, &p.mapV, kv_full(st), 0, k0, hh, bb);
       }
     }
   } else if (warp == 1) {
@@ -250,7 +251,7 @@ __global__ void __launch_bounds__(ATTN_THREADS, 1) attn_fwd_kernel(const __grid_
       tc_fence_after();
     }
     const float inv_l = l > 0.f ? 1.f / l : 0.f;
-    __nv_bfloat16* orow = p.o + (static_cast<long>(bh) * p.Lq + iq) * ATTN_D;
+    __nv_bfloat16* orow = p.o + ((static_cast<long>(bb) * p.Lq + iq) * p.heads + hh) * ATTN_D;
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
       float o[32];

@@ -20,7 +20,7 @@ constexpr int ABW_BN = 64;   // rows streamed per step
 struct AttnBwdParams {
   CUtensorMap mapQ128, mapdO128, mapK64, mapV64;   // dq kernel
   CUtensorMap mapK128, mapV128, mapQ64, mapdO64;   // dkv kernel
-  int BH, Lq, Lk, hw, n_frames, mask;
+  int BH, heads, Lq, Lk, hw, n_frames, mask;
   float scale;
   const float* lse;  // [BH, Lq]
   const float* dsum; // [BH, Lq]  D = rowsum(dO*O)
@@ -92,10 +92,10 @@ __device__ __forceinline__ TileRanges visible_queries(const AttnBwdParams& p, in
   return r;
 }
 
-// D = rowsum(dO * O): one 8-lane group per row.
+// D = rowsum(dO * O): one 8-lane group per (token, head) row of the [B, L, heads, 64] tensors; dsum is [B, heads, L].
 __global__ void __launch_bounds__(256) attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ o,
                                                             const __nv_bfloat16* __restrict__ dout,
-                                                            float* __restrict__ dsum, long rows) {
+                                                            float* __restrict__ dsum, long rows, int L, int heads) {
   const long gid = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long row = gid >> 3;
   const int sub = static_cast<int>(gid & 7);
@@ -112,7 +112,12 @@ __global__ void __launch_bounds__(256) attn_bwd_prep_kernel(const __nv_bfloat16*
   acc += __shfl_xor_sync(0xffffffffu, acc, 1);
   acc += __shfl_xor_sync(0xffffffffu, acc, 2);
   acc += __shfl_xor_sync(0xffffffffu, acc, 4);
-  if (row < rows && sub == 0) dsum[row] = acc;
+  if (row < rows && sub == 0) {
+    const long tok = row / heads;
+    const int hh = static_cast<int>(row - tok * heads);
+    const long bb = tok / L;
+    dsum[(bb * heads + hh) * L + (tok - bb * L)] = acc;
+  }
 }
 
 constexpr int ABW_STAGES = 3;
@@ -154,6 +159,7 @@ __global__ void __launch_bounds__(ABW_THREADS, 1) attn_bwd_dq_kernel(const __gri
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int bh = blockIdx.y;
+  const int bb = bh / p.heads, hh = bh - bb * p.heads;
   const int q0 = blockIdx.x * ABW_BM;
   const TileRanges kr = visible_keys(p, q0, min(q0 + ABW_BM, p.Lq));
   const int n_kv = kr.count();
@@ -176,16 +182,16 @@ __global__ void __launch_bounds__(ABW_THREADS, 1) attn_bwd_dq_kernel(const __gri
   if (warp == 0) {
     if (lane == 0) {
       mbar_arrive_expect_tx(q_full, 2 * ABW_T128);
-      tma_load_3d(sQ, &p.mapQ128, q_full, 0, q0, bh);
-      tma_load_3d(sdO, &p.mapdO128, q_full, 0, q0, bh);
+      tma_load_4d(sQ, &p.mapQ128, q_full, 0, q0, hh, bb);
+      tma_load_4d(sdO, &p.mapdO128, q_full, 0, q0, hh, bb);
       for (int j = 0; j < n_kv; ++j) {
         const int st = j % ABW_STAGES;
         mbar_wait(kv_empty(st), ((j / ABW_STAGES) & 1) ^ 1);
         const uint32_t sK = sKV + st * 2 * ABW_T64, sV = sK + ABW_T64;
         mbar_arrive_expect_tx(kv_full(st), 2 * ABW_T64);
         const int k0 = kr.tile(j) * ABW_BN;
-        tma_load_3d(sK, &p.mapK64, kv_full(st), 0, k0, bh);
-        tma_load_3d(sV, &p.mapV64, kv_full(st), 0, k0, bh);
+        tma_load_4d(sK, &p.mapK64, kv_full(st), 0, k0, hh, bb);
+        tma_load_4d(sV, &p.mapV64, kv_full(st), 0, k0, hh, bb);
       }
     }
   } else if (warp == 1) {
@@ -274,7 +280,7 @@ __global__ void __launch_bounds__(ABW_THREADS, 1) attn_bwd_dq_kernel(const __gri
       if (lane == 0) { mbar_arrive(sdp_empty(b)); mbar_arrive(ds_full(b)); }
     }
     if (n_kv > 0) { mbar_wait(acc_full, 0); tc_fence_after(); }
-    __nv_bfloat16* drow = p.dq + (static_cast<long>(bh) * p.Lq + iq) * ATTN_D;
+    __nv_bfloat16* drow = p.dq + ((static_cast<long>(bb) * p.Lq + iq) * p.heads + hh) * ATTN_D;
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
       float o[32];
@@ -317,6 +323,7 @@ __global__ void __launch_bounds__(ABW_THREADS, 1) attn_bwd_dkv_kernel(const __gr
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int bh = blockIdx.y;
+  const int bb = bh / p.heads, hh = bh - bb * p.heads;
   const int k0 = blockIdx.x * ABW_BM;
   const TileRanges qr = visible_queries(p, k0, min(k0 + ABW_BM, p.Lk));
   const int n_q = qr.count();
@@ -339,16 +346,16 @@ __global__ void __launch_bounds__(ABW_THREADS, 1) attn_bwd_dkv_kernel(const __gr
   if (warp == 0) {
     if (lane == 0) {
       mbar_arrive_expect_tx(kv_full, 2 * ABW_T128);
-      tma_load_3d(sK, &p.mapK128, kv_full, 0, k0, bh);
-      tma_load_3d(sV, &p.mapV128, kv_full, 0, k0, bh);
+      tma_load_4d(sK, &p.mapK128, kv_full, 0, k0, hh, bb);
+      tma_load_4d(sV, &p.mapV128, kv_full, 0, k0, hh, bb);
       for (int j = 0; j < n_q; ++j) {
         const int st = j % ABW_STAGES;
         mbar_wait(q_empty(st), ((j / ABW_STAGES) & 1) ^ 1);
         const uint32_t sQ = sQdO + st * 2 * ABW_T64, sdO = sQ + ABW_T64;
         mbar_arrive_expect_tx(q_full(st), 2 * ABW_T64);
         const int q0 = qr.tile(j) * ABW_BN;
-        tma_load_3d(sQ, &p.mapQ64, q_full(st), 0, q0, bh);
-        tma_load_3d(sdO, &p.mapdO64, q_full(st), 0, q0, bh);
+        tma_load_4d(sQ, &p.mapQ64, q_full(st), 0, q0, hh, bb);
+        tma_load_4d(sdO, &p.mapdO64, q_full(st), 0, q0, hh, bb);
       }
     }
   } else if (warp == 1) {
@@ -452,7 +459,7 @@ __global__ void __launch_bounds__(ABW_THREADS, 1) attn_bwd_dkv_kernel(const __gr
     if (n_q > 0) { mbar_wait(acc_full, 0); tc_fence_after(); }
 #pragma unroll
     for (int which = 0; which < 2; ++which) {
-      __nv_bfloat16* drow = (which == 0 ? p.dk : p.dv) + (static_cast<long>(bh) * p.Lk + ik) * ATTN_D;
+      __nv_bfloat16* drow = (which == 0 ? p.dk : p.dv) + ((static_cast<long>(bb) * p.Lk + ik) * p.heads + hh) * ATTN_D;
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         float o[32];

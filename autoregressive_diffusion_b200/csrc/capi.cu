@@ -11,10 +11,10 @@
 using namespace ob;
 
 namespace ob {
-int attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int BH, int Lq, int Lk, int hw, int n_frames,
-             int mask, float scale, cudaStream_t st);
+int attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B, int heads, int Lq, int Lk, int hw,
+             int n_frames, int mask, float scale, cudaStream_t st);
 int attn_bwd(const void* q, const void* k, const void* v, const void* o, const void* dout, const float* lse, float* dsum,
-             void* dq, void* dk, void* dv, int BH, int Lq, int Lk, int hw, int n_frames, int mask, float scale,
+             void* dq, void* dk, void* dv, int B, int heads, int Lq, int Lk, int hw, int n_frames, int mask, float scale,
              cudaStream_t st);
 }
 
@@ -163,15 +163,32 @@ int ob_mp_sum_bwd(const void* g, const void* out, void* da, void* db, int64_t n,
   return mp_sum_bwd(g, out, da, db, (long)n, t, clip, (cudaStream_t)stream);
 }
 
-int ob_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int bh, int lq, int lk, int hw,
+int ob_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int b, int heads, int lq, int lk, int hw,
                 int n_frames, int mask, float scale, void* stream) {
-  return attn_fwd(q, k, v, o, lse, bh, lq, lk, hw, n_frames, mask, scale, (cudaStream_t)stream);
+  return attn_fwd(q, k, v, o, lse, b, heads, lq, lk, hw, n_frames, mask, scale, (cudaStream_t)stream);
 }
 
 int ob_attn_bwd(const void* q, const void* k, const void* v, const void* o, const void* dout, const float* lse,
-                float* dsum, void* dq, void* dk, void* dv, int bh, int lq, int lk, int hw, int n_frames, int mask,
-                float scale, void* stream) {
-  return attn_bwd(q, k, v, o, dout, lse, dsum, dq, dk, dv, bh, lq, lk, hw, n_frames, mask, scale, (cudaStream_t)stream);
+                float* dsum, void* dq, void* dk, void* dv, int b, int heads, int lq, int lk, int hw, int n_frames,
+                int mask, float scale, void* stream) {
+  return attn_bwd(q, k, v, o, dout, lse, dsum, dq, dk, dv, b, heads, lq, lk, hw, n_frames, mask, scale,
+                  (cudaStream_t)stream);
+}
+
+int ob_qkv_prep_fwd(const void* qkv, void* q, void* k, void* v, void* k_raw, const float* cos_t, const float* sin_t,
+                    const float* scl_t, const int* pos_q, const int* pos_k, int64_t rows, int heads, int hw, float eps,
+                    void* stream) {
+  return qkv_prep_fwd(qkv, q, k, v, k_raw, cos_t, sin_t, scl_t, pos_q, pos_k, (long)rows, heads, hw, eps, (cudaStream_t)stream);
+}
+int ob_qkv_prep_bwd(const void* qkv, const void* dq, const void* dk, const void* dv, void* dqkv, const float* cos_t,
+                    const float* sin_t, const float* scl_t, const int* pos_q, const int* pos_k, int64_t rows, int heads,
+                    int hw, float eps, void* stream) {
+  return qkv_prep_bwd(qkv, dq, dk, dv, dqkv, cos_t, sin_t, scl_t, pos_q, pos_k, (long)rows, heads, hw, eps,
+                      (cudaStream_t)stream);
+}
+int ob_rope_k(const void* x, void* y, const float* cos_t, const float* sin_t, const float* scl_t, const int* pos,
+              int64_t rows, int heads, int hw, void* stream) {
+  return rope_k(x, y, cos_t, sin_t, scl_t, pos, (long)rows, heads, hw, (cudaStream_t)stream);
 }
 
 }  // extern "C"

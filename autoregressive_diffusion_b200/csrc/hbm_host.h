@@ -17,4 +17,12 @@ int scale_silu_bwd(const void* y, const float* cscale, const void* g, void* dy, 
                    int rows_per_frame, cudaStream_t st);
 int mp_sum_fwd(const void* a, const void* b, void* out, long n, float t, float clip, cudaStream_t st);
 int mp_sum_bwd(const void* g, const void* out, void* da, void* db, long n, float t, float clip, cudaStream_t st);
+int qkv_prep_fwd(const void* qkv, void* q, void* k, void* v, void* k_raw, const float* cosT, const float* sinT,
+                 const float* sclT, const int* pos_q, const int* pos_k, long rows, int heads, int hw, float eps,
+                 cudaStream_t st);
+int qkv_prep_bwd(const void* qkv, const void* dq, const void* dk, const void* dv, void* dqkv, const float* cosT,
+                 const float* sinT, const float* sclT, const int* pos_q, const int* pos_k, long rows, int heads, int hw,
+                 float eps, cudaStream_t st);
+int rope_k(const void* x, void* y, const float* cosT, const float* sinT, const float* sclT, const int* pos, long rows,
+           int heads, int hw, cudaStream_t st);
 }  // namespace ob

@@ -230,7 +230,7 @@ __device__ __forceinline__ float mp_silu_grad(float v) {
 }
 
 // Backward: dx = d(normalize)(g_xn + g_act * silu'(xn)) ; mode 1: dx = g_x + g_act * silu'(x).
-//   y = x/d, d = eps + rms:  dx = (g - y * <g,y> * (1/(C*rms)) ... ) / d   (per pixel row)
+//   y = x/d, d = eps + rms:  dx = g/d - y * <g,y> / (C*rms)   (per pixel row)
 template <int MODE>
 __global__ void __launch_bounds__(256) pixnorm_silu_bwd_kernel(const __nv_bfloat16* __restrict__ x,
                                                                const __nv_bfloat16* __restrict__ g_xn,
@@ -277,7 +277,7 @@ __global__ void __launch_bounds__(256) pixnorm_silu_bwd_kernel(const __nv_bfloat
     for (int j = 0; j < 8; ++j) {
       const float yv = f[j] * inv;
       const float g = (g_xn ? g1[j] : 0.f) + g2[j] * mp_silu_grad(yv);
-      o[j] = (MODE == 0) ? (g - yv * proj) * inv : g;
+      o[j] = (MODE == 0) ? (g * inv - yv * proj) : g;
     }
     *reinterpret_cast<bf16x8*>(dx + row * C + c) = pack8(o);
   }

@@ -101,23 +101,39 @@ int ob_mp_sum_bwd(const void* g, const void* out, void* da, void* db, int64_t n,
 
 /* ---------------------------------------------------------------------------------------------- attention
  * edm2/attention/attention_modules.py:59-77: compiled_flex_attention(q,k,v, make_train_mask / make_infer_mask) and
- * F.scaled_dot_product_attention.  q: bf16 [BH, Lq, 64], k,v: bf16 [BH, Lk, 64], token-major; q,k RMS-normalised and
+ * F.scaled_dot_product_attention.  q: bf16 [B, Lq, heads, 64], k,v: bf16 [B, Lk, heads, 64] (NHWC rows); q,k RMS-normalised and
  * rotary-embedded by the caller (logits bounded by 8, which the kernel relies on).  mask: OB_ATTN_FULL (one new
  * frame vs the whole cache; per-frame attention), OB_ATTN_CAUSAL (frame-causal prefill, InferenceMask
  * attention_masking.py:56-62) or OB_ATTN_DART (TrainingMask attention_masking.py:8-24 over 2*n_frames frames).
- * hw = tokens per frame.  o: bf16 [BH, Lq, 64]; lse: fp32 [BH, Lq] (log-sum-exp of the scaled logits), may be NULL. */
+ * hw = tokens per frame.  o: bf16 [B, Lq, heads, 64]; lse: fp32 [B, heads, Lq] (log-sum-exp of the scaled logits), may be NULL. */
 #define OB_ATTN_FULL 0
 #define OB_ATTN_CAUSAL 1
 #define OB_ATTN_DART 2
-int ob_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int bh, int lq, int lk, int hw,
+int ob_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int b, int heads, int lq, int lk, int hw,
                 int n_frames, int mask, float scale, void* stream);
 
+/* q/k/v preparation, edm2/attention/attention_modules.py:48-49 (split of the (head, c, {q,k,v}) channel order +
+ * normalize(dim=-1) of q, k and v) fused with edm2/attention/RoPe.py:43-74 (rotary + xPos on q and k).
+ * qkv: bf16 [rows, heads*192] (the 1x1 conv output, NHWC).  q, k, v: bf16 [rows, heads*64].  k_raw (optional): the
+ * normalised but un-rotated keys (what the reference keeps in its KV cache).  cos_t/sin_t/scl_t: fp32 [P][64] tables
+ * (already fp16-rounded like RoPe.py:24,28); pos_q/pos_k: int32 table row per FRAME (row / hw), <0 or NULL = no rotary. */
+int ob_qkv_prep_fwd(const void* qkv, void* q, void* k, void* v, void* k_raw, const float* cos_t, const float* sin_t,
+                    const float* scl_t, const int* pos_q, const int* pos_k, int64_t rows, int heads, int hw, float eps,
+                    void* stream);
+int ob_qkv_prep_bwd(const void* qkv, const void* dq, const void* dk, const void* dv, void* dqkv, const float* cos_t,
+                    const float* sin_t, const float* scl_t, const int* pos_q, const int* pos_k, int64_t rows, int heads,
+                    int hw, float eps, void* stream);
+/* Rotary (key flavour: divided by the xPos scale) over cached un-rotated keys x -> y, both bf16 [rows, heads*64]. */
+int ob_rope_k(const void* x, void* y, const float* cos_t, const float* sin_t, const float* scl_t, const int* pos,
+              int64_t rows, int heads, int hw, void* stream);
+
 /* Backward of ob_attn_fwd (autograd of the same reference calls).  o, lse: the forward's outputs; dout: bf16
- * [BH, Lq, 64]; dsum: fp32 [BH, Lq] workspace (receives rowsum(dout*o)).  Writes dq [BH,Lq,64], dk, dv [BH,Lk,64] bf16.
+ * [B, Lq, heads, 64]; dsum: fp32 [B, heads, Lq] workspace (receives rowsum(dout*o)).  Writes dq, dk, dv (bf16, shaped
+ * like q, k, v).
  * Every output element is produced by exactly one CTA (no atomics, deterministic). */
 int ob_attn_bwd(const void* q, const void* k, const void* v, const void* o, const void* dout, const float* lse,
-                float* dsum, void* dq, void* dk, void* dv, int bh, int lq, int lk, int hw, int n_frames, int mask,
-                float scale, void* stream);
+                float* dsum, void* dq, void* dk, void* dv, int b, int heads, int lq, int lk, int hw, int n_frames,
+                int mask, float scale, void* stream);
 
 #ifdef __cplusplus
 }

@@ -22,6 +22,21 @@ def _qkv(bh, lq, lk, seed=0):
     return q, k, v
 
 
+HEADS = {3: 3, 8: 4, 2: 2, 4: 2, 1: 1}   # bh -> heads (the rest is batch)
+
+
+def _dev(t):
+    """[bh, L, 64] (b-major, head-minor) -> the kernels' [B, L, heads, 64] bf16 layout on the GPU."""
+    bh, L, d = t.shape
+    h = HEADS[bh]
+    return t.reshape(bh // h, h, L, d).permute(0, 2, 1, 3).contiguous().cuda().to(torch.bfloat16)
+
+
+def _back(t):
+    b, L, h, d = t.shape
+    return t.permute(0, 2, 1, 3).reshape(b * h, L, d).float()
+
+
 def _mask(kind, lq, lk, hw, n):
     if kind == 0:
         return None
@@ -55,9 +70,9 @@ def test_attn_fwd(kind, bh, lq, lk, hw, n):
     if m is not None:
         s = s.masked_fill(~m, float("-inf"))
     lse_ref = torch.logsumexp(s, dim=-1)
-    o, lse = A.attn_fwd(q.cuda().to(torch.bfloat16), k.cuda().to(torch.bfloat16), v.cuda().to(torch.bfloat16), hw, n, kind)
-    assert_close(o.float(), ref, "o")
-    assert_close(lse, lse_ref, "lse", 1e-3, 1e-4)
+    o, lse = A.attn_fwd(_dev(q), _dev(k), _dev(v), hw, n, kind)
+    assert_close(_back(o), ref, "o")
+    assert_close(lse.reshape(bh, lq), lse_ref, "lse", 1e-3, 1e-4)
 
 
 @pytest.mark.parametrize("kind,bh,lq,lk,hw,n", CASES)
@@ -68,11 +83,11 @@ def test_attn_bwd(kind, bh, lq, lk, hw, n):
     qr, kr_, vr = (t.clone().requires_grad_(True) for t in (q, k, v))
     ref = O._dense_attention(qr, kr_, vr, _mask(kind, lq, lk, hw, n))
     ref.backward(do)
-    qg, kg, vg = (t.cuda().to(torch.bfloat16).requires_grad_(True) for t in (q, k, v))
+    qg, kg, vg = (_dev(t).requires_grad_(True) for t in (q, k, v))
     o = A.AttentionFn.apply(qg, kg, vg, hw, n, kind)
-    o.backward(do.cuda().to(torch.bfloat16))
-    assert_close(o.float(), ref, "o")
+    o.backward(_dev(do))
+    assert_close(_back(o), ref, "o")
     # one extra bf16 rounding sits inside (P and dS are rounded before their second GEMM): mean budget 3e-3
-    assert_close(qg.grad.float(), qr.grad, "dq", mean_rel=3e-3)
-    assert_close(kg.grad.float(), kr_.grad, "dk", mean_rel=3e-3)
-    assert_close(vg.grad.float(), vr.grad, "dv", mean_rel=3e-3)
+    assert_close(_back(qg.grad), qr.grad, "dq", mean_rel=3e-3)
+    assert_close(_back(kg.grad), kr_.grad, "dk", mean_rel=3e-3)
+    assert_close(_back(vg.grad), vr.grad, "dv", mean_rel=3e-3)
