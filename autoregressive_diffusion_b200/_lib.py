@@ -31,19 +31,22 @@ def stream_ptr():
 _SIGS = {
     # name: argtypes
     "ob_wnorm_fwd": "ppiiiiiiffip",
-    "ob_wnorm_bwd": "pppiiiiiiiffp",
+    "ob_wnorm_bwd": "pppiiiiiiiffip",
     "ob_conv_fwd": "pppppppiiiiiiiiiip",
     "ob_conv_dgrad": "ppppppiiiiiiiiip",
     "ob_conv_wgrad_splits": "iiiiiiiii",
     "ob_conv_wgrad": "pppppiiiiiiiiiip",
     "ob_gate_bwd": "pppppppppiiilp",
+    "ob_gate_fwd": "pppppppiiiip",
+    "ob_gate_bwd_params": "pppppppppppppiiiip",
+    "ob_ctx_build": "pppiiiliip",
     "ob_pixnorm_silu_fwd": "ppplifip",
     "ob_pixnorm_silu_bwd": "pppplifip",
     "ob_scale_silu_fwd": "pppliip",
     "ob_scale_silu_bwd": "pppppiiip",
     "ob_mp_sum_fwd": "ppplffp",
     "ob_mp_sum_bwd": "pppplffp",
-    "ob_qkv_prep_fwd": "pppppppppplliifp".replace("ll", "l"),
+    "ob_qkv_prep_fwd": "ppppppppppliifp",
     "ob_qkv_prep_bwd": "ppppppppppliifp",
     "ob_rope_k": "ppppppliip",
     "ob_attn_fwd": "pppppiiiiiiifp",
@@ -73,10 +76,23 @@ def lib():
     return _lib
 
 
+_profiler = None
+
+
+def set_profiler(p):
+    """Install an object with before(name, args) -> token / after(name, args, token) hooks (bench.py's kernel timer)."""
+    global _profiler
+    _profiler = p
+
+
 def call(name, *args):
     """Invoke an entry point; raise OnirisError with the library's message on a non-zero status."""
     L = lib()
+    prof = _profiler
+    tok = prof.before(name, args) if prof is not None else None
     rc = getattr(L, name)(*args)
+    if prof is not None:
+        prof.after(name, args, tok)
     if rc != 0:
         raise OnirisError(f"{name} failed ({rc}): {L.ob_last_error().decode()}")
 

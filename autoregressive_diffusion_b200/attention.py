@@ -126,8 +126,15 @@ class _QkvPrepFn(torch.autograd.Function):
         return dqkv, None, None, None, None, None, None, None, None
 
 
-def _frame_positions(values, device):
-    return torch.as_tensor(values, dtype=torch.int32, device=device).contiguous()
+_POS_CACHE = {}
+
+
+def _frame_positions(lo, hi, repeat, device):
+    """int32 device tensor tile(arange(lo, hi), repeat), cached (no host-to-device copy on the hot path)."""
+    key = (lo, hi, repeat, device)
+    if key not in _POS_CACHE:
+        _POS_CACHE[key] = torch.arange(lo, hi, dtype=torch.int32, device=device).repeat(repeat).contiguous()
+    return _POS_CACHE[key]
 
 
 class _AttentionBase(nn.Module):
@@ -185,7 +192,7 @@ class VideoAttention(_AttentionBase):
         if self.training:
             n = f // (batch_size * 2)
             cos_t, sin_t, scl_t = self.rope.tables(n)
-            pos = _frame_positions(np.tile(np.arange(n), 2 * batch_size), dev)     # both halves use positions 0..n-1
+            pos = _frame_positions(0, n, 2 * batch_size, dev)                       # both halves use positions 0..n-1
             q, k, v = _QkvPrepFn.apply(y, cos_t, sin_t, scl_t, pos, pos, m, hw, False)
             shape = (batch_size, 2 * n * hw, m, 64)
             o = AttentionFn.apply(q.view(shape), k.view(shape), v.view(shape), hw, n, DART)
@@ -194,7 +201,7 @@ class VideoAttention(_AttentionBase):
             t_old = 0 if cache is None else cache[0].shape[2]
             t_all = t_old + t_new
             cos_t, sin_t, scl_t = self.rope.tables(t_all)
-            pos_new = _frame_positions(np.tile(np.arange(t_old, t_all), batch_size), dev)
+            pos_new = _frame_positions(t_old, t_all, batch_size, dev)
             if cache is None:
                 outs = _QkvPrepFn.apply(y, cos_t, sin_t, scl_t, pos_new, pos_new, m, hw, update_cache)
                 q, k, v = outs[:3]
@@ -209,7 +216,7 @@ class VideoAttention(_AttentionBase):
                 k_raw_all = torch.cat((ck, k_raw.view(batch_size, t_new * hw, m, 64)), dim=1)
                 v_all = torch.cat((cv, v.view(batch_size, t_new * hw, m, 64)), dim=1)
                 k_all = torch.empty_like(k_raw_all)
-                pos_all = _frame_positions(np.tile(np.arange(t_all), batch_size), dev)
+                pos_all = _frame_positions(0, t_all, batch_size, dev)
                 call("ob_rope_k", _vp(k_raw_all), _vp(k_all), _vp(cos_t), _vp(sin_t), _vp(scl_t), _vp(pos_all),
                      batch_size * t_all * hw, m, hw, stream_ptr())
             if update_cache:

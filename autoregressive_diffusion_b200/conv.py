@@ -139,32 +139,26 @@ class MPCausal3DGatedConv(nn.Module):
         cin_pad = ops.ceil_to(cin, 16)
         wg = self._cache.get([w2, w3], [9, 18], cin, cin_pad, [1.0, 1.0], self.training)
 
-        g, n_ctx = self.gating(c_noise.float(), cache.get('n_context_frames', 0))
-        if update_cache:
-            cache['n_context_frames'] = n_ctx
-        g = g.flatten()
-        inv = torch.rsqrt((1 - g) ** 2 + g ** 2)
-        alpha, beta = ((1 - g) * inv).contiguous(), (g * inv).contiguous()
-
         xr = ops.pad_channels(rows(x), 16)
         f, _, h, w = xr.shape
         S = 2 if self.training else 1
         T = f // (batch_size * S)
-        x5 = xr.permute(0, 2, 3, 1).reshape(batch_size, S * T, h, w, cin_pad)       # physical NHWC view
+        n_ctx = cache.get('n_context_frames', 0)
+        if update_cache:
+            cache['n_context_frames'] = n_ctx + T                       # Gating.forward's second return (conv.py:127)
         pad = cache.get('activations', None)
-        if pad is None:
-            pad5 = torch.ones(batch_size, 2, h, w, cin_pad, dtype=BF16, device=xr.device)
-            if cin_pad != cin:
-                pad5[..., cin:] = 0
-        else:  # reference layout [B, C, 2, H, W] -> [B, 2, H, W, C]
+        pad5 = None
+        if pad is not None:  # reference layout [B, C, 2, H, W] -> NHWC rows [B, 2, H, W, C]
             pad5 = pad.permute(0, 2, 3, 4, 1).to(BF16)
             if cin_pad != cin:
                 pad5 = torch.nn.functional.pad(pad5, (0, cin_pad - cin))
-        ctx5 = torch.cat((pad5, x5[:, :T].detach()), dim=1).contiguous()             # [B, T+2, H, W, C]
-        if update_cache:
-            cache['activations'] = ctx5[:, -2:, :, :, :cin].permute(0, 4, 1, 2, 3).clone()
+            pad5 = pad5.contiguous()
+        gt = self.gating
         want_grad = torch.is_grad_enabled() and (xr.requires_grad or w2.requires_grad or w3.requires_grad)
-        y = ops.GatedConvFn.apply(xr, ctx5, w2, w3, wg, alpha, beta, batch_size, S, T, want_grad)
+        y, ctx5 = ops.GatedConvFn.apply(xr, pad5, w2, w3, wg, gt.offset, gt.mult, gt.max_gating, gt.min_gating,
+                                        c_noise.reshape(-1).float().contiguous(), batch_size, S, T, n_ctx, want_grad)
+        if update_cache:
+            cache['activations'] = ctx5[:, -2:, :, :, :cin].permute(0, 4, 1, 2, 3)
         return y, cache
 
     @torch.no_grad()

@@ -47,8 +47,9 @@ int ob_wnorm_fwd(float* w, void* wg, int cout, int cin, int taps, int cin_pad, i
   return wnorm_fwd(w, wg, cout, cin, taps, cin_pad, taps_total, tap_off, gain, eps, training, (cudaStream_t)stream);
 }
 int ob_wnorm_bwd(const float* w, const float* dwg, float* dw, int cout, int cin, int taps, int cin_pad, int taps_total,
-                 int tap_off, int n_split, float gain, float eps, void* stream) {
-  return wnorm_bwd(w, dwg, dw, cout, cin, taps, cin_pad, taps_total, tap_off, n_split, gain, eps, (cudaStream_t)stream);
+                 int tap_off, int n_split, float gain, float eps, int accumulate, void* stream) {
+  return wnorm_bwd(w, dwg, dw, cout, cin, taps, cin_pad, taps_total, tap_off, n_split, gain, eps, accumulate,
+                   (cudaStream_t)stream);
 }
 
 int ob_conv_fwd(const void* x, const void* ctx, const void* wg, const float* alpha, const float* beta, void* out,
@@ -141,6 +142,21 @@ int ob_conv_wgrad(const void* gya, const void* x, const void* gb, const void* ct
 int ob_gate_bwd(const void* dy, const void* y, const void* d, const float* alpha, const float* beta, void* gya, void* gb,
                 float* s_y, float* s_d, int n_seq, int S, int T, int64_t frame_elems, void* stream) {
   return gate_bwd(dy, y, d, alpha, beta, gya, gb, s_y, s_d, n_seq, S, T, (long)frame_elems, (cudaStream_t)stream);
+}
+int ob_gate_fwd(const float* offset, const float* mult, const float* max_gating, const float* min_gating,
+                const float* c_noise, float* alpha, float* beta, int frames, int T, int half, int n_ctx, void* stream) {
+  return gate_fwd(offset, mult, max_gating, min_gating, c_noise, alpha, beta, frames, T, half, n_ctx, (cudaStream_t)stream);
+}
+int ob_gate_bwd_params(const float* offset, const float* mult, const float* max_gating, const float* min_gating,
+                       const float* c_noise, const float* alpha, const float* beta, const float* s_y, const float* s_d,
+                       float* g_offset, float* g_mult, float* g_max, float* g_min, int frames, int T, int half, int n_ctx,
+                       void* stream) {
+  return gate_bwd_params(offset, mult, max_gating, min_gating, c_noise, alpha, beta, s_y, s_d, g_offset, g_mult, g_max,
+                         g_min, frames, T, half, n_ctx, (cudaStream_t)stream);
+}
+int ob_ctx_build(const void* x, const void* pad, void* ctx, int b, int S, int T, int64_t frame_elems, int cin, int cin_pad,
+                 void* stream) {
+  return ctx_build(x, pad, ctx, b, S, T, (long)frame_elems, cin, cin_pad, (cudaStream_t)stream);
 }
 int ob_pixnorm_silu_fwd(const void* x, void* xn, void* act, int64_t rows, int c, float eps, int mode, void* stream) {
   return pixnorm_silu_fwd(x, xn, act, (long)rows, c, eps, mode, (cudaStream_t)stream);

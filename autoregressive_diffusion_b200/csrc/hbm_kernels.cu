@@ -102,26 +102,36 @@ __global__ void __launch_bounds__(256) wnorm_fwd_kernel(float* __restrict__ w, _
 // Backward of operand = normalize(w) * gain/sqrt(K) w.r.t. the (forced) weights w.
 // dwg: fp32 [n_split][Co][taps_total][Ci_pad] partial sums from the wgrad kernel; dw: fp32 [Co][Ci][taps].
 //   d = eps + rms(w);  dw_i = c/d * (g_i - w_i * <g,w> / (K * rms * d))
+// One CTA per output channel: the split-reduced gradient row is staged in shared memory in its own (tap-major)
+// order with a +1 row pad, so both the global reads (dwg, w) and the global write (dw) are fully coalesced and the
+// [tap][ci] -> [ci][tap] transpose happens on conflict-free shared-memory reads.  accumulate != 0: dw += result
+// (gradient accumulation over micro-batches without a separate add pass).
 __global__ void __launch_bounds__(256) wnorm_bwd_kernel(const float* __restrict__ w, const float* __restrict__ dwg,
                                                         float* __restrict__ dw, int Co, int Ci, int taps, int Ci_pad,
-                                                        int taps_total, int tap_off, int n_split, float gain, float eps) {
+                                                        int taps_total, int tap_off, int n_split, float gain, float eps,
+                                                        int accumulate) {
   __shared__ float red[32];
-  extern __shared__ float gbuf[];  // [taps*Ci] gathered, split-reduced gradient in w's own order
+  extern __shared__ float gbuf[];  // [taps][Ci + 1]
   const int co = blockIdx.x;
   const int K = Ci * taps;
+  const int ld = Ci + 1;
   const float* wr = w + static_cast<long>(co) * K;
   const long split_stride = static_cast<long>(Co) * taps_total * Ci_pad;
   const float* gsrc = dwg + (static_cast<long>(co) * taps_total + tap_off) * Ci_pad;
-  float ss = 0.f, dot = 0.f;
-  for (int j = threadIdx.x; j < taps * Ci_pad; j += blockDim.x) {  // coalesced over the operand layout
+  for (int j = threadIdx.x; j < taps * Ci_pad; j += blockDim.x) {
     const int tap = j / Ci_pad, ci = j - tap * Ci_pad;
     if (ci >= Ci) continue;
     float g = 0.f;
     for (int s = 0; s < n_split; ++s) g += gsrc[s * split_stride + j];
-    const float wv = wr[ci * taps + tap];
-    gbuf[ci * taps + tap] = g;
+    gbuf[tap * ld + ci] = g;
+  }
+  __syncthreads();
+  float ss = 0.f, dot = 0.f;
+  for (int i = threadIdx.x; i < K; i += blockDim.x) {
+    const int ci = i / taps, tap = i - ci * taps;
+    const float wv = wr[i];
     ss += wv * wv;
-    dot += g * wv;
+    dot += gbuf[tap * ld + ci] * wv;
   }
   ss = block_sum(ss, red);
   dot = block_sum(dot, red);
@@ -130,7 +140,11 @@ __global__ void __launch_bounds__(256) wnorm_bwd_kernel(const float* __restrict_
   const float c = gain * rsqrtf(static_cast<float>(K)) / d;
   const float proj = (rms > 0.f) ? dot / (K * rms * d) : 0.f;
   float* dwr = dw + static_cast<long>(co) * K;
-  for (int i = threadIdx.x; i < K; i += blockDim.x) dwr[i] = c * (gbuf[i] - wr[i] * proj);
+  for (int i = threadIdx.x; i < K; i += blockDim.x) {
+    const int ci = i / taps, tap = i - ci * taps;
+    const float v = c * (gbuf[tap * ld + ci] - wr[i] * proj);
+    dwr[i] = accumulate ? dwr[i] + v : v;
+  }
 }
 
 // ============================================================================ gate backward pre-pass
@@ -184,6 +198,100 @@ __global__ void __launch_bounds__(256) gate_bwd_kernel(const __nv_bfloat16* __re
       atomicAdd(&s_d[f], c);
     }
   }
+}
+
+// ============================================================================ gate scalars (forward / backward)
+// Reference: edm2/conv.py:113-127 (Gating.forward) followed by the mp_sum weights of edm2/utils.py:122-123:
+//   g = lo + (1-lo)*hi*sigmoid(mult0*c_noise + off0 + mult1*log1p(pos) + off1),  lo = sigmoid(min_gating), hi = sigmoid(max_gating)
+//   alpha = (1-g)/sqrt((1-g)^2+g^2),  beta = g/sqrt(...)       pos = (frame index within its sequence) % half + n_ctx
+// One launch replaces ~15 eager ops per conv layer (and ~25 in backward).
+__global__ void gate_fwd_kernel(const float* __restrict__ offset, const float* __restrict__ mult,
+                                const float* __restrict__ max_g, const float* __restrict__ min_g,
+                                const float* __restrict__ c_noise, float* __restrict__ alpha, float* __restrict__ beta,
+                                int frames, int T, int half, int n_ctx) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= frames) return;
+  const float lo = 1.f / (1.f + expf(-min_g[0])), hi = 1.f / (1.f + expf(-max_g[0]));
+  const float pos = log1pf(static_cast<float>((f % T) % half + n_ctx));
+  const float state = c_noise[f] * mult[0] + offset[0] + pos * mult[1] + offset[1];
+  const float g = lo + (1.f - lo) * hi / (1.f + expf(-state));
+  const float inv = rsqrtf((1.f - g) * (1.f - g) + g * g);
+  alpha[f] = (1.f - g) * inv;
+  beta[f] = g * inv;
+}
+
+// From the per-frame inner products s_y = <dy,y>, s_d = <dy,d> (y = alpha*a + beta*b, d = b - a):
+//   <dy,a> = (s_y - beta*s_d)/(alpha+beta), <dy,b> = <dy,a> + s_d;  dg = (-g*<dy,a> + (1-g)*<dy,b>) / D^{3/2}
+// then the chain rule through the gate; the six scalar gradients are ADDED to g_* (single CTA, no atomics).
+__global__ void __launch_bounds__(128) gate_bwd_params_kernel(const float* __restrict__ offset, const float* __restrict__ mult,
+                                                              const float* __restrict__ max_g, const float* __restrict__ min_g,
+                                                              const float* __restrict__ c_noise, const float* __restrict__ alpha,
+                                                              const float* __restrict__ beta, const float* __restrict__ s_y,
+                                                              const float* __restrict__ s_d, float* __restrict__ g_offset,
+                                                              float* __restrict__ g_mult, float* __restrict__ g_max,
+                                                              float* __restrict__ g_min, int frames, int T, int half, int n_ctx) {
+  __shared__ float red[32];
+  const float lo = 1.f / (1.f + expf(-min_g[0])), hi = 1.f / (1.f + expf(-max_g[0]));
+  float a_state = 0.f, a_m0 = 0.f, a_m1 = 0.f, a_lo = 0.f, a_hi = 0.f;
+  for (int f = threadIdx.x; f < frames; f += blockDim.x) {
+    const float pos = log1pf(static_cast<float>((f % T) % half + n_ctx));
+    const float cn = c_noise[f];
+    const float state = cn * mult[0] + offset[0] + pos * mult[1] + offset[1];
+    const float sg = 1.f / (1.f + expf(-state));
+    const float g = lo + (1.f - lo) * hi * sg;
+    const float al = alpha[f], be = beta[f];
+    const float da = (s_y[f] - be * s_d[f]) / (al + be);
+    const float db = da + s_d[f];
+    const float D = (1.f - g) * (1.f - g) + g * g;
+    const float dg = (-g * da + (1.f - g) * db) / (D * sqrtf(D));
+    const float dstate = dg * (1.f - lo) * hi * sg * (1.f - sg);
+    a_state += dstate;
+    a_m0 += dstate * cn;
+    a_m1 += dstate * pos;
+    a_lo += dg * (1.f - hi * sg);
+    a_hi += dg * (1.f - lo) * sg;
+  }
+  a_state = block_sum(a_state, red);
+  a_m0 = block_sum(a_m0, red);
+  a_m1 = block_sum(a_m1, red);
+  a_lo = block_sum(a_lo, red);
+  a_hi = block_sum(a_hi, red);
+  if (threadIdx.x == 0) {
+    g_offset[0] += a_state; g_offset[1] += a_state;
+    g_mult[0] += a_m0; g_mult[1] += a_m1;
+    g_min[0] += a_lo * lo * (1.f - lo);
+    g_max[0] += a_hi * hi * (1.f - hi);
+  }
+}
+
+// ============================================================================ causal context assembly
+// Reference: edm2/conv.py:68-69,78-84 (causal_pad / cache['activations'] + torch.cat with the clean frames).
+// ctx[b, 0:2] = pad[b] (or ones on the first `cin` channels when pad == nullptr), ctx[b, 2+t] = x[(b*S + 0)*T + t].
+__global__ void __launch_bounds__(256) ctx_build_kernel(const __nv_bfloat16* __restrict__ x,
+                                                        const __nv_bfloat16* __restrict__ pad,
+                                                        __nv_bfloat16* __restrict__ ctx, int S, int T, long frame_elems,
+                                                        int cin, int cin_pad, long total_vec) {
+  const long v = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (v >= total_vec) return;
+  const long e = v * 8;
+  const long per_b = static_cast<long>(T + 2) * frame_elems;
+  const long b = e / per_b;
+  const long r = e - b * per_b;
+  const long t = r / frame_elems;        // 0..T+1
+  const long off = r - t * frame_elems;
+  bf16x8 out;
+  if (t >= 2) {
+    out = *reinterpret_cast<const bf16x8*>(x + ((b * S) * T + (t - 2)) * frame_elems + off);
+  } else if (pad != nullptr) {
+    out = *reinterpret_cast<const bf16x8*>(pad + (b * 2 + t) * frame_elems + off);
+  } else {
+    float f[8];
+    const int c0 = static_cast<int>(off % cin_pad);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = (c0 + j < cin) ? 1.f : 0.f;
+    out = pack8(f);
+  }
+  *reinterpret_cast<bf16x8*>(ctx + e) = out;
 }
 
 // ============================================================================ pixel norm (+ mp_silu)
@@ -414,9 +522,9 @@ int wnorm_fwd(float* w, void* wg, int Co, int Ci, int taps, int Ci_pad, int taps
 }
 
 int wnorm_bwd(const float* w, const float* dwg, float* dw, int Co, int Ci, int taps, int Ci_pad, int taps_total,
-              int tap_off, int n_split, float gain, float eps, cudaStream_t st) {
+              int tap_off, int n_split, float gain, float eps, int accumulate, cudaStream_t st) {
   if (Co <= 0) return OB_OK;
-  const size_t smem = static_cast<size_t>(Ci) * taps * sizeof(float);
+  const size_t smem = static_cast<size_t>(Ci + 1) * taps * sizeof(float);
   if (smem > 200 * 1024) {
     set_error("wnorm_bwd: row of %d x %d floats exceeds shared memory", Ci, taps);
     return OB_ERR_UNSUPPORTED;
@@ -426,7 +534,8 @@ int wnorm_bwd(const float* w, const float* dwg, float* dw, int Co, int Ci, int t
     cudaFuncSetAttribute(wnorm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     configured = 200 * 1024;
   }
-  wnorm_bwd_kernel<<<Co, 256, smem, st>>>(w, dwg, dw, Co, Ci, taps, Ci_pad, taps_total, tap_off, n_split, gain, eps);
+  wnorm_bwd_kernel<<<Co, 256, smem, st>>>(w, dwg, dw, Co, Ci, taps, Ci_pad, taps_total, tap_off, n_split, gain, eps,
+                                          accumulate);
   return check_launch("wnorm_bwd");
 }
 
@@ -445,6 +554,34 @@ int gate_bwd(const void* dy, const void* y, const void* d, const float* alpha, c
                                         static_cast<__nv_bfloat16*>(gya), static_cast<__nv_bfloat16*>(gb), s_y, s_d, n_seq,
                                         S, T, frame_elems);
   return check_launch("gate_bwd");
+}
+
+int gate_fwd(const float* offset, const float* mult, const float* max_g, const float* min_g, const float* c_noise,
+             float* alpha, float* beta, int frames, int T, int half, int n_ctx, cudaStream_t st) {
+  if (frames <= 0) return OB_OK;
+  gate_fwd_kernel<<<(frames + 127) / 128, 128, 0, st>>>(offset, mult, max_g, min_g, c_noise, alpha, beta, frames, T, half, n_ctx);
+  return check_launch("gate_fwd");
+}
+
+int gate_bwd_params(const float* offset, const float* mult, const float* max_g, const float* min_g, const float* c_noise,
+                    const float* alpha, const float* beta, const float* s_y, const float* s_d, float* g_offset,
+                    float* g_mult, float* g_max, float* g_min, int frames, int T, int half, int n_ctx, cudaStream_t st) {
+  if (frames <= 0) return OB_OK;
+  gate_bwd_params_kernel<<<1, 128, 0, st>>>(offset, mult, max_g, min_g, c_noise, alpha, beta, s_y, s_d, g_offset, g_mult,
+                                            g_max, g_min, frames, T, half, n_ctx);
+  return check_launch("gate_bwd_params");
+}
+
+int ctx_build(const void* x, const void* pad, void* ctx, int B, int S, int T, long frame_elems, int cin, int cin_pad,
+              cudaStream_t st) {
+  if (frame_elems % 8 != 0 || cin_pad % 8 != 0) { set_error("ctx_build: frame size must be a multiple of 8"); return OB_ERR_INVALID; }
+  const long total_vec = static_cast<long>(B) * (T + 2) * frame_elems / 8;
+  if (total_vec <= 0) return OB_OK;
+  ctx_build_kernel<<<(total_vec + 255) / 256, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x),
+                                                            static_cast<const __nv_bfloat16*>(pad),
+                                                            static_cast<__nv_bfloat16*>(ctx), S, T, frame_elems, cin, cin_pad,
+                                                            total_vec);
+  return check_launch("ctx_build");
 }
 
 int pixnorm_silu_fwd(const void* x, void* xn, void* act, long rows, int C, float eps, int mode, cudaStream_t st) {

@@ -12,7 +12,7 @@ from torch import nn
 
 from . import ops
 from .attention import FrameAttention, VideoAttention
-from .conv import Gating, MPCausal3DGatedConv, MPConv
+from .conv import Gating, MPCausal3DGatedConv, MPConv, _normalize_rows
 from .utils import MPFourier, mp_cat, mp_silu, mp_sum, resample
 
 
@@ -39,7 +39,7 @@ class Block(nn.Module):
         attn_cls = VideoAttention if attention == 'video' else FrameAttention
         self.attn = attn_cls(out_channels, self.num_heads, attn_balance)
 
-    def forward(self, x, emb, batch_size, c_noise, cache=None, update_cache=False, just_2d=False):
+    def forward(self, x, emb, batch_size, c_noise, cache=None, update_cache=False, just_2d=False, emb_scale=None):
         if cache is None:
             cache = {}
         clip = float(self.clip_act) if self.clip_act is not None else 0.0
@@ -52,7 +52,7 @@ class Block(nn.Module):
             x = ops.rows(x)
             act = ops.silu_only(x)
         y, cache['conv_res0'] = self.conv_res0(act, emb, batch_size, c_noise, cache.get('conv_res0', None), update_cache, just_2d)
-        c = self.emb_linear(emb, gain=self.emb_gain) + 1
+        c = emb_scale if emb_scale is not None else self.emb_linear(emb, gain=self.emb_gain) + 1
         y = ops.scale_silu(y, c)                         # y * c -> mp_silu (:75-77)
         if self.training and self.dropout != 0:
             y = torch.nn.functional.dropout(y, p=self.dropout)
@@ -158,6 +158,25 @@ class UNet(BetterModule):
                 self.dec[f'{res}x{res}_block{idx}'] = Block(cin, cout, cemb, flavor='dec', attention=attn_at(res), **block_kwargs)
         self.out_conv = MPCausal3DGatedConv(cout, img_channels, kernel=[3, 3, 3])
 
+    def _emb_scales(self, emb):
+        """c = emb_linear(emb, gain=emb_gain) + 1 for EVERY block at once (edm2/networks_edm2.py:75 x 28 blocks): the 28
+        [Cout, cemb] weights are normalised as one concatenated matrix and applied with a single GEMM."""
+        blocks = [b for b in list(self.enc.values()) + list(self.dec.values()) if isinstance(b, Block)]
+        ws = [b.emb_linear.weight.weight for b in blocks]
+        counts = [w.shape[0] for w in ws]
+        if self.training:
+            with torch.no_grad():       # forced weight normalisation (edm2/conv.py:16-18)
+                torch._foreach_copy_(ws, list(_normalize_rows(torch.cat(ws, 0)).split(counts)))
+        w_hat = _normalize_rows(torch.cat(ws, 0)) * (1.0 / ws[0].shape[1] ** 0.5)
+        key = (tuple(counts), emb.device)
+        if getattr(self, "_emb_rows_key", None) != key:
+            self._emb_rows = torch.repeat_interleave(torch.arange(len(counts), device=emb.device),
+                                                     torch.tensor(counts, device=emb.device))
+            self._emb_rows_key = key
+        gains = torch.stack([b.emb_gain for b in blocks])[self._emb_rows]
+        c_all = (emb @ w_hat.t()) * gains + 1
+        return {id(b): c for b, c in zip(blocks, c_all.split(counts, dim=1))}
+
     def forward(self, x, c_noise, conditioning=None, cache=None, update_cache=False, just_2d=False):
         if cache is None:
             cache = {}
@@ -174,17 +193,19 @@ class UNet(BetterModule):
         emb = mp_silu(emb)
         c_noise = c_noise.reshape(batch_size, tdim)
 
+        scales = self._emb_scales(emb)
         x = torch.cat([x, torch.ones_like(x[:, :1])], dim=1)
         skips = []
         for name, block in self.enc.items():
+            kw = {"emb_scale": scales[id(block)].contiguous()} if isinstance(block, Block) else {}
             x, cache['enc', name] = block(x, emb, batch_size, c_noise, cache=cache.get(('enc', name), None),
-                                          update_cache=update_cache, just_2d=just_2d)
+                                          update_cache=update_cache, just_2d=just_2d, **kw)
             skips.append(x)
         for name, block in self.dec.items():
             if 'block' in name:
                 x = mp_cat(x, skips.pop(), t=self.concat_balance)
             x, cache['dec', name] = block(x, emb, batch_size, c_noise, cache=cache.get(('dec', name), None),
-                                          update_cache=update_cache, just_2d=just_2d)
+                                          update_cache=update_cache, just_2d=just_2d, emb_scale=scales[id(block)].contiguous())
         x, cache['out_conv'] = self.out_conv(x, emb, batch_size, c_noise, cache=cache.get('out_conv', None),
                                              update_cache=update_cache, just_2d=just_2d)
         x = x.reshape(batch_size, tdim, *x.shape[1:]).float() * self.out_gain

@@ -63,27 +63,49 @@ def weight_operand(params, taps, cin, cin_pad, gains, training, eps=1e-4):
     return wg
 
 
+def grad_buffer(p):
+    """The parameter's .grad, created zero-filled on first use; kernels accumulate into it directly."""
+    if p.grad is None:
+        p.grad = torch.zeros_like(p, memory_format=torch.contiguous_format)
+    return p.grad
+
+
 def weight_grad(params, taps, cin, cin_pad, gains, dwg, n_split, eps=1e-4):
-    """ob_wnorm_bwd for each parameter: split-K partials dwg [n_split, Cout, sum(taps), cin_pad] -> dW like the params."""
+    """ob_wnorm_bwd for each parameter: split-K partials dwg [n_split, Cout, sum(taps), cin_pad] are reduced, pushed
+    through the weight-normalisation backward and ACCUMULATED into p.grad in the same pass (so gradient accumulation
+    over micro-batches, cs_train.py:108-109, costs no extra add kernels).  Autograd therefore sees None for them."""
     cout = params[0].shape[0]
     total = sum(taps)
     if dwg.shape[1] != cout:      # Cout was padded to a multiple of 8: fold the splits and drop the pad rows
         dwg = dwg.sum(0, keepdim=True)[:, :cout].contiguous()
         n_split = 1
-    outs, off = [], 0
+    off = 0
     for p, t, g in zip(params, taps, gains):
-        dw = torch.empty_like(p)
-        call("ob_wnorm_bwd", _vp(p), _vp(dwg), _vp(dw), cout, cin, t, cin_pad, total, off, n_split, float(g), eps, stream_ptr())
-        outs.append(dw)
+        if p.requires_grad:
+            call("ob_wnorm_bwd", _vp(p), _vp(dwg), _vp(grad_buffer(p)), cout, cin, t, cin_pad, total, off, n_split, float(g),
+                 eps, 1, stream_ptr())
         off += t
-    return outs
+
+
+_CONST = {}
+
+
+def clean_rows_mask(n_seq, S, T, device):
+    """beta for the dgrad epilogue: 1 on clean rows (which fed the causal context), 0 on noised rows."""
+    key = ("clean", n_seq, S, T, device)
+    if key not in _CONST:
+        m = torch.zeros((n_seq, S, T), dtype=torch.float32, device=device)
+        m[:, 0] = 1.0
+        _CONST[key] = m
+    return _CONST[key]
 
 
 # ----------------------------------------------------------------------------- convolutions
 
 
 class PlainConvFn(torch.autograd.Function):
-    """MPConv with a 1x1 or 3x3 kernel (edm2/conv.py:36-42): y = conv2d(x, normalize(w)*gain/sqrt(fan_in))."""
+    """MPConv with a 1x1 or 3x3 kernel (edm2/conv.py:36-42): y = conv2d(x, normalize(w)*gain/sqrt(fan_in)).
+    The weight gradient is accumulated straight into w.grad (see weight_grad)."""
 
     @staticmethod
     def forward(ctx, x, w, wg, ksize, gain, out_f32):
@@ -103,64 +125,76 @@ class PlainConvFn(torch.autograd.Function):
         cout, cin = wg.shape[0], w.shape[1]
         k = ctx.ksize
         gy = pad_channels(rows(gy), 8)
-        dx = dw = None
+        dx = None
         if ctx.needs_input_grad[0]:
             dx = empty_rows(f, cin_pad, h, wd, x.device)
             call("ob_conv_dgrad", _vp(gy), None, _vp(wg), None, None, _vp(dx), 1, 1, f, h, wd, cin_pad, cout, k, 0, stream_ptr())
-        if ctx.needs_input_grad[1]:
+        if w.requires_grad:
             ns = query("ob_conv_wgrad_splits", 1, 1, f, h, wd, cin_pad, cout, k, 0)
             dwg = torch.empty((ns, cout, k * k, cin_pad), dtype=torch.float32, device=x.device)
             call("ob_conv_wgrad", _vp(gy), _vp(x), None, None, _vp(dwg), 1, 1, f, h, wd, cin_pad, cout, k, 0, ns, stream_ptr())
-            (dw,) = weight_grad([w], [k * k], cin, cin_pad, [ctx.gain], dwg, ns)
-        return dx, dw, None, None, None, None
+            weight_grad([w], [k * k], cin, cin_pad, [ctx.gain], dwg, ns)
+        return dx, None, None, None, None, None
 
 
 class GatedConvFn(torch.autograd.Function):
-    """MPCausal3DGatedConv core (edm2/conv.py:59-95): y = alpha*conv2d(x) + beta*conv3d(context)."""
+    """MPCausal3DGatedConv (edm2/conv.py:59-95) as three launches: gate scalars, causal-context assembly, and ONE
+    tcgen05 implicit GEMM  y = alpha*conv2d(x) + beta*conv3d(context)  with the gate applied in its epilogue.
+    Backward: gate pre-pass, input gradient, weight gradient (+ weight-norm backward) and the gate scalars' gradients;
+    parameter gradients are accumulated straight into .grad."""
 
     @staticmethod
-    def forward(ctx, x, cx, w2, w3, wg, alpha, beta, n_seq, S, T, want_grad):
+    def forward(ctx, x, pad5, w2, w3, wg, g_offset, g_mult, g_max, g_min, c_noise, n_seq, S, T, n_ctx, want_grad):
         f, cin_pad, h, wd = x.shape
-        cout = wg.shape[0]
-        out = empty_rows(f, cout, h, wd, x.device)
-        out_d = empty_rows(f, cout, h, wd, x.device, torch.float32) if want_grad else None
+        cin, cout = w2.shape[1], wg.shape[0]
+        dev = x.device
+        ab = torch.empty((2, f), dtype=torch.float32, device=dev)
+        alpha, beta = ab[0], ab[1]
+        call("ob_gate_fwd", _vp(g_offset), _vp(g_mult), _vp(g_max), _vp(g_min), _vp(c_noise), _vp(alpha), _vp(beta), f, S * T, T,
+             n_ctx, stream_ptr())
+        cx = torch.empty((n_seq, T + 2, h, wd, cin_pad), dtype=BF16, device=dev)
+        call("ob_ctx_build", _vp(x), _vp(pad5), _vp(cx), n_seq, S, T, h * wd * cin_pad, cin, cin_pad, stream_ptr())
+        out = empty_rows(f, cout, h, wd, dev)
+        out_d = empty_rows(f, cout, h, wd, dev, torch.float32) if want_grad else None
         call("ob_conv_fwd", _vp(x), _vp(cx), _vp(wg), _vp(alpha), _vp(beta), _vp(out), _vp(out_d), n_seq, S, T, h, wd,
              cin_pad, cout, 3, 1, 0, stream_ptr())
         if want_grad:
-            ctx.save_for_backward(x, cx, w2, w3, wg, alpha, beta, out, out_d)
-        ctx.dims = (n_seq, S, T)
-        return out if cout == w2.shape[0] else out[:, : w2.shape[0]]
+            ctx.save_for_backward(x, cx, w2, w3, wg, ab, out, out_d, g_offset, g_mult, g_max, g_min, c_noise)
+        ctx.dims = (n_seq, S, T, n_ctx)
+        ctx.mark_non_differentiable(cx)
+        y = out if cout == w2.shape[0] else out[:, : w2.shape[0]]
+        return y, cx
 
     @staticmethod
-    def backward(ctx, gy):
-        x, cx, w2, w3, wg, alpha, beta, y, d = ctx.saved_tensors
-        n_seq, S, T = ctx.dims
+    def backward(ctx, gy, _gcx):
+        x, cx, w2, w3, wg, ab, y, d, g_offset, g_mult, g_max, g_min, c_noise = ctx.saved_tensors
+        n_seq, S, T, n_ctx = ctx.dims
         f, cin_pad, h, wd = x.shape
         cout, cin = wg.shape[0], w2.shape[1]
+        dev = x.device
+        alpha, beta = ab[0], ab[1]
         gy = pad_channels(rows(gy), 8)
-        gya = empty_rows(f, cout, h, wd, x.device)
-        gb = empty_rows(n_seq * T, cout, h, wd, x.device)
-        sums = torch.zeros((2, f), dtype=torch.float32, device=x.device)
+        gya = empty_rows(f, cout, h, wd, dev)
+        gb = empty_rows(n_seq * T, cout, h, wd, dev)
+        sums = torch.zeros((2, f), dtype=torch.float32, device=dev)
         call("ob_gate_bwd", _vp(gy), _vp(y), _vp(d), _vp(alpha), _vp(beta), _vp(gya), _vp(gb), _vp(sums[0]), _vp(sums[1]),
              n_seq, S, T, h * wd * cout, stream_ptr())
-        dx = dw2 = dw3 = dal = dbe = None
+        dx = None
         if ctx.needs_input_grad[0]:
-            dx = empty_rows(f, cin_pad, h, wd, x.device)
-            clean = torch.zeros((n_seq, S, T), dtype=torch.float32, device=x.device)
-            clean[:, 0] = 1.0   # the causal context was built from the clean rows only
-            call("ob_conv_dgrad", _vp(gy), _vp(gb), _vp(wg), _vp(alpha), _vp(clean), _vp(dx), n_seq, S, T, h, wd, cin_pad,
-                 cout, 3, 1, stream_ptr())
-        if ctx.needs_input_grad[2] or ctx.needs_input_grad[3]:
+            dx = empty_rows(f, cin_pad, h, wd, dev)
+            call("ob_conv_dgrad", _vp(gy), _vp(gb), _vp(wg), _vp(alpha), _vp(clean_rows_mask(n_seq, S, T, dev)), _vp(dx), n_seq,
+                 S, T, h, wd, cin_pad, cout, 3, 1, stream_ptr())
+        if w2.requires_grad or w3.requires_grad:
             ns = query("ob_conv_wgrad_splits", n_seq, S, T, h, wd, cin_pad, cout, 3, 1)
-            dwg = torch.empty((ns, cout, 27, cin_pad), dtype=torch.float32, device=x.device)
+            dwg = torch.empty((ns, cout, 27, cin_pad), dtype=torch.float32, device=dev)
             call("ob_conv_wgrad", _vp(gya), _vp(x), _vp(gb), _vp(cx), _vp(dwg), n_seq, S, T, h, wd, cin_pad, cout, 3, 1, ns,
                  stream_ptr())
-            dw2, dw3 = weight_grad([w2, w3], [9, 18], cin, cin_pad, [1.0, 1.0], dwg, ns)
-        if ctx.needs_input_grad[5] or ctx.needs_input_grad[6]:
-            # y = alpha*a + beta*b, d = b - a  =>  <dy,a> = (<dy,y> - beta*<dy,d>)/(alpha+beta), <dy,b> = <dy,a> + <dy,d>
-            dal = (sums[0] - beta * sums[1]) / (alpha + beta)
-            dbe = dal + sums[1]
-        return dx, None, dw2, dw3, None, dal, dbe, None, None, None, None
+            weight_grad([w2, w3], [9, 18], cin, cin_pad, [1.0, 1.0], dwg, ns)
+        if g_offset.requires_grad:
+            call("ob_gate_bwd_params", _vp(g_offset), _vp(g_mult), _vp(g_max), _vp(g_min), _vp(c_noise), _vp(alpha), _vp(beta),
+                 _vp(sums[0]), _vp(sums[1]), _vp(grad_buffer(g_offset)), _vp(grad_buffer(g_mult)), _vp(grad_buffer(g_max)),
+                 _vp(grad_buffer(g_min)), f, S * T, T, n_ctx, stream_ptr())
+        return (dx,) + (None,) * 14
 
 
 # ----------------------------------------------------------------------------- elementwise

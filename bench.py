@@ -1,0 +1,280 @@
+#!/usr/bin/env python
+"""Headline benchmark: data-parallel training of the Counter-Strike latent UNet (BASELINE.json configs[2]).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a path (one process per GPU under torchrun)
+  python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm's CPU path (oracle port) on host cores
+
+A "step" is one micro-batch pass of the hot path: forward + backward of the 310 M-parameter UNet over a
+[2, 16, 8, 32, 32] synthetic latent clip (32 frames with the clean (+) noised DART sequence); every 4th step also
+all-reduces the gradients over the ranks and runs AdamW + the two EMA updates, as cs_train.py:97-127 does.
+Metric: target frames per second = ranks * 2 * 16 / step time (weak scaling: per-GPU work is fixed).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+MICRO_BATCH, CLIP = 2, 16
+KERNELS_PER_CALL = {"ob_attn_bwd": 3}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return d.get("bf16_tflops_sustained", 1400.0), d.get("hbm_gbs", 6650.0), "measured"
+    return 1400.0, 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index, self.proc, self.path = gpu_index, None, f"/tmp/oniris_clocks_{os.getpid()}.csv"
+
+    def start(self):
+        try:
+            self.out = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu_index)], stdout=self.out, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.proc.wait()
+        self.out.close()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx = float(f[2])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+class ConvProfiler:
+    """CUDA-event timing of the dominant kernel (the tcgen05 tap-GEMM behind ob_conv_fwd / ob_conv_dgrad) on the
+    launching stream, plus a count of every kernel launched through the C ABI."""
+
+    def __init__(self, timed_names=("ob_conv_fwd", "ob_conv_dgrad")):
+        self.timed, self.events, self.flops, self.launches = set(timed_names), [], 0.0, 0
+
+    @staticmethod
+    def conv_flops(name, a):
+        # ob_conv_fwd(x,ctx,wg,alpha,beta,out,out_d, n_seq,S,T,H,W,cin,cout,ksize,gated,...) / ob_conv_dgrad(gy,gb,wg,alpha,beta,dx, ...)
+        off = 7 if name == "ob_conv_fwd" else 6
+        n_seq, S, T, H, W, cin, cout, k, gated = a[off:off + 9]
+        px = n_seq * T * H * W
+        if gated:
+            return 2.0 * px * S * cin * cout * 9 + 2.0 * px * cin * cout * 18
+        return 2.0 * px * S * cin * cout * k * k
+
+    def before(self, name, args):
+        self.launches += KERNELS_PER_CALL.get(name, 1)
+        if name in self.timed:
+            e0 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            return e0
+        return None
+
+    def after(self, name, args, e0):
+        if e0 is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            self.events.append((e0, e1))
+            self.flops += self.conv_flops(name, args)
+
+    def summary(self):
+        ms = sum(a.elapsed_time(b) for a, b in self.events)
+        return ms, self.flops, len(self.events)
+
+
+def oracle_cpu_step(batch, seed=0):
+    """The reference algorithm (oracle port, fp32, dense-masked attention) for one CS micro-step on the host cores."""
+    from oracle import oniris_oracle as O
+    from autoregressive_diffusion_b200.train import CS_UNET as C
+    torch.set_num_threads(os.cpu_count())
+    lay = O.unet_layout(C["img_resolution"], C["img_channels"], C["label_dim"], C["model_channels"], C["channel_mult"],
+                        C["num_blocks"], C["video_attn_resolutions"], C["frame_attn_resolutions"])
+    sd = O.unet_init_state(lay, C["model_channels"], seed)
+    g = torch.Generator().manual_seed(seed)
+    images = torch.randn(batch, CLIP, 8, 32, 32, generator=g)
+    sigma = torch.cat((torch.rand(batch, 1, generator=g).expand(-1, CLIP) * 0.1,
+                       (torch.randn(batch, CLIP, generator=g) * 1.0 + 0.9).exp()), dim=1)
+    noise = torch.randn(batch, 2 * CLIP, 8, 32, 32, generator=g)
+
+    def step():
+        t0 = time.perf_counter()
+        O.train_step(sd, lay, images, sigma, noise)
+        return time.perf_counter() - t0
+    return step
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    batch = 1   # bounded sample: half the micro-batch (one 32-frame DART sequence) per step
+    step = oracle_cpu_step(batch)
+    for _ in range(args.warmup):
+        step()
+    times = [step() for _ in range(args.steps)]
+    ms = 1e3 * sum(times) / len(times)
+    fps = batch * CLIP / (ms / 1e3)
+    line = {
+        "impl": "reference", "metric": "train frames/s", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "cs_train.py Counter-Strike UNet (310M), DART 32-frame sequence, fwd+bwd micro-step on CPU",
+                   "micro_batch": batch, "clip_frames": CLIP, "latent": [8, 32, 32]},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
+                         "sample": f"1 of the {MICRO_BATCH} sequences of a micro-batch per step (fwd+bwd, no optimizer), "
+                                   f"oracle/oniris_oracle.py fp32 on {os.cpu_count()} threads"},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    from autoregressive_diffusion_b200 import _lib
+    from autoregressive_diffusion_b200.train import CS_UNET, Trainer, init_distributed
+    rank, world, local = init_distributed()
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback for the product path)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    tr = Trainer(CS_UNET, accumulation_steps=4, device=dev, seed=42)
+    shape = (MICRO_BATCH, CLIP, 8, 32, 32)
+    g = torch.Generator().manual_seed(1234 + rank)
+    n_host = 4
+    host = [torch.randn(shape, generator=g).pin_memory() for _ in range(n_host)]
+    resident = [h.to(dev) for h in host]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    use_graph = not args.eager
+
+    def one_step(i, e2e):
+        if use_graph:
+            loss = tr.graphed_micro_step(host[i % n_host] if e2e else resident[i % n_host])
+        else:
+            x = host[i % n_host].to(dev, non_blocking=True) if e2e else resident[i % n_host]
+            loss, _ = tr.micro_step(x)
+        if e2e:
+            loss.item()          # device->host read of the step's result, every step
+
+    def timed(k, e2e):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(k):
+            one_step(i, e2e)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item() / k
+
+    # Kernel census + dominant-kernel timing: one eager accumulation cycle with CUDA events around every tap-GEMM
+    # launch on the launching stream (the graph replays exactly this kernel sequence).
+    for i in range(4):
+        tr.micro_step(resident[i % n_host])
+    prof = ConvProfiler()
+    _lib.set_profiler(prof)
+    torch.cuda.synchronize()
+    for i in range(4):
+        tr.micro_step(resident[i % n_host])
+    torch.cuda.synchronize()
+    _lib.set_profiler(None)
+    launches_per_step = prof.launches / 4
+    if use_graph:
+        tr.capture(resident[0])
+    for i in range(max(args.warmup, 3)):
+        one_step(i, False)
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    ms = timed(args.steps, e2e=False)
+    clk = clocks.stop() if rank == 0 else None
+    ms_e2e = timed(args.steps, e2e=True)
+    if rank != 0:
+        return
+    fps = world * MICRO_BATCH * CLIP / (ms / 1e3)
+    fps_e2e = world * MICRO_BATCH * CLIP / (ms_e2e / 1e3)
+    conv_ms, conv_flops, conv_launches = prof.summary()
+    peak_tf, _, peak_kind = measured_peaks()
+    achieved = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+    line = {
+        "metric": "train frames/s", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "cs_train.py Counter-Strike UNet (310M params), DART 32-frame sequence, fwd+bwd micro-step; "
+                               "gradient all-reduce + AdamW + 2 EMAs every 4th step",
+                   "micro_batch_per_gpu": MICRO_BATCH, "clip_frames": CLIP, "latent": [8, 32, 32], "accumulation": 4,
+                   "parallelism": f"dp{world}", "launch": "cuda-graph replay per micro-step" if use_graph else "eager",
+                   "l2": "no explicit flush: each step streams >2 GB of weights/operands/activations (>> 126 MB L2)"},
+        "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": MICRO_BATCH * CLIP * 8 * 32 * 32 * 4,
+                "d2h_bytes_per_step": 4},
+        "gpu_launches": int(launches_per_step * args.steps),
+        "clocks": clk,
+        "roofline": {"bound": "tensor", "kernel": "tapconv_kernel (gated 3D causal conv fwd + dgrad, tcgen05)",
+                     "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+                     "peak_kind": f"{peak_kind} bf16_tflops_sustained", "launches": conv_launches,
+                     "share_of_step": (conv_ms / 4) / ms, "traffic": None,
+                     "how": "CUDA events around each launch over one eager 4-step cycle on the launching stream"},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        step = oracle_cpu_step(1)
+        step()
+        t = step()
+        line["cpu_baseline"] = {"value": CLIP / t, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
+                                "sample": "one 32-frame DART sequence (half a micro-batch), fwd+bwd, 1 warm-up + 1 timed step"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=4)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--eager", action="store_true", help="launch kernels from Python instead of replaying CUDA graphs")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

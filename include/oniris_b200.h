@@ -44,9 +44,10 @@ int ob_wnorm_fwd(float* w, void* wg, int cout, int cin, int taps, int cin_pad, i
                  float eps, int training, void* stream);
 
 /* Backward of the above w.r.t. the (forced) weights: dwg fp32 [n_split][Cout][taps_total][cin_pad] are the
- * split-K partial sums written by ob_conv_wgrad; dw fp32 [Cout][Cin][taps] is overwritten. */
+ * split-K partial sums written by ob_conv_wgrad; dw fp32 [Cout][Cin][taps] is overwritten, or (accumulate != 0)
+ * added to -- gradient accumulation over micro-batches (cs_train.py:108-109) without a separate pass. */
 int ob_wnorm_bwd(const float* w, const float* dwg, float* dw, int cout, int cin, int taps, int cin_pad, int taps_total,
-                 int tap_off, int n_split, float gain, float eps, void* stream);
+                 int tap_off, int n_split, float gain, float eps, int accumulate, void* stream);
 
 /* ---------------------------------------------------------------------------------------------- convolutions
  * edm2/conv.py:36-42 (MPConv: F.conv2d k=1|3) and :59-95 (MPCausal3DGatedConv: F.conv2d + F.conv3d + mp_sum).
@@ -82,6 +83,22 @@ int ob_conv_wgrad(const void* gya, const void* x, const void* gb, const void* ct
  * scalars' gradients are built from. */
 int ob_gate_bwd(const void* dy, const void* y, const void* d, const float* alpha, const float* beta, void* gya, void* gb,
                 float* s_y, float* s_d, int n_seq, int S, int T, int64_t frame_elems, void* stream);
+
+/* edm2/conv.py:113-127 Gating.forward + the mp_sum weights of edm2/utils.py:122-123, one launch:
+ * alpha[f] = (1-g)/sqrt((1-g)^2+g^2), beta[f] = g/sqrt(..); position of frame f = (f % T) % half + n_ctx where T is
+ * the frames per batch row of c_noise [frames] and half = T/2 in training (clean+noised halves share positions). */
+int ob_gate_fwd(const float* offset, const float* mult, const float* max_gating, const float* min_gating,
+                const float* c_noise, float* alpha, float* beta, int frames, int T, int half, int n_ctx, void* stream);
+/* Gradients of the six gate scalars from ob_gate_bwd's inner products; ADDED into g_offset[2], g_mult[2], g_max[1],
+ * g_min[1] (the parameters' .grad buffers). */
+int ob_gate_bwd_params(const float* offset, const float* mult, const float* max_gating, const float* min_gating,
+                       const float* c_noise, const float* alpha, const float* beta, const float* s_y, const float* s_d,
+                       float* g_offset, float* g_mult, float* g_max, float* g_min, int frames, int T, int half, int n_ctx,
+                       void* stream);
+/* edm2/conv.py:68-69,78-84: ctx[b] = [pad frames (cache['activations'] or ones) | clean frames of x], bf16
+ * [B, T+2, H, W, cin_pad]; x: [B*S*T, H, W, cin_pad]; pad: [B, 2, H, W, cin_pad] or NULL (ones on channels < cin). */
+int ob_ctx_build(const void* x, const void* pad, void* ctx, int b, int S, int T, int64_t frame_elems, int cin, int cin_pad,
+                 void* stream);
 
 /* ---------------------------------------------------------------------------------------------- elementwise
  * edm2/networks_edm2.py:70 normalize(x, dim=1) + edm2/utils.py:112-113 mp_silu, one pass.

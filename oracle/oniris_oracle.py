@@ -527,3 +527,66 @@ def sample_frame(sd, layout, cache, x_init, conditioning=None, num_steps=32, sig
             d_prime = (x_next - x_pred) / t_next
             x_next = x_hat + (t_next - t_hat) * (0.5 * d_cur + 0.5 * d_prime)
     return x_next, cache
+
+
+# ----------------------------------------------------------------------------- random-init state (bench / smoke inputs)
+
+
+def unet_init_state(layout, model_channels, seed=0) -> Dict[str, Tensor]:
+    """A random state dict with the key names and shapes of edm2/networks_edm2.py:117-189 (UNet.__init__) for `layout`.
+
+    Values follow the reference initialisers (randn weights, Gating defaults conv.py:107-110, zero emb_gain) except
+    out_gain = 1 so that the output path is live (SURVEY 8c caveat)."""
+    g = torch.Generator().manual_seed(seed)
+    sd: Dict[str, Tensor] = {}
+    cemb, cnoise = layout["cemb"], layout["cnoise"]
+
+    def gated(prefix, cin, cout):
+        sd[f"{prefix}last_frame_conv.weight.weight"] = torch.randn(cout, cin, 3, 3, generator=g)
+        sd[f"{prefix}weight.weight"] = torch.randn(cout, cin, 2, 3, 3, generator=g)
+        sd[f"{prefix}gating.offset"] = torch.tensor([0., 0.])
+        sd[f"{prefix}gating.mult"] = torch.tensor([1.5, -0.5])
+        sd[f"{prefix}gating.max_gating"] = torch.tensor(-5.)
+        sd[f"{prefix}gating.min_gating"] = torch.tensor(-5.)
+
+    def block(prefix, m):
+        sd[f"{prefix}emb_gain"] = torch.zeros([])
+        sd[f"{prefix}emb_linear.weight.weight"] = torch.randn(m["cout"], cemb, generator=g)
+        gated(f"{prefix}conv_res0.", m["cout"] if m["flavor"] == "enc" else m["cin"], m["cout"])
+        gated(f"{prefix}conv_res1.", m["cout"], m["cout"])
+        if m["has_skip"]:
+            sd[f"{prefix}conv_skip.weight.weight"] = torch.randn(m["cout"], m["cin"], 1, 1, generator=g)
+        if m["num_heads"] > 0:
+            sd[f"{prefix}attn.attn_qkv.weight.weight"] = torch.randn(3 * m["cout"], m["cout"], 1, 1, generator=g)
+            sd[f"{prefix}attn.attn_proj.weight.weight"] = torch.randn(m["cout"], m["cout"], 1, 1, generator=g)
+            if m["attention"] == "video":
+                sd[f"{prefix}attn.rope.inv_freq"], sd[f"{prefix}attn.rope.scale"] = rope_buffers(m["cout"] // m["num_heads"])
+
+    sd["out_gain"] = torch.ones([])
+    for name in ("offset", "mult", "max_gating", "min_gating"):
+        sd[f"out_res.{name}"] = {"offset": torch.tensor([0., 0.]), "mult": torch.tensor([1.5, -0.5]),
+                                 "max_gating": torch.tensor(-5.), "min_gating": torch.tensor(-5.)}[name]
+    for f in ("sigma", "time"):
+        sd[f"emb_fourier_{f}.freqs"] = 2 * math.pi * torch.randn(cnoise, generator=g)
+        sd[f"emb_fourier_{f}.phases"] = 2 * math.pi * torch.rand(cnoise, generator=g)
+    sd["emb_noise.weight.weight"] = torch.randn(cemb, cnoise, generator=g)
+    sd["emb_time.weight.weight"] = torch.randn(cemb, cnoise, generator=g)
+    if layout["label_dim"]:
+        sd["emb_label.weight.weight"] = torch.randn(cemb, layout["label_dim"], generator=g)
+    for side in ("enc", "dec"):
+        for name, m in layout[side]:
+            if m["kind"] == "conv":
+                gated(f"{side}.{name}.", m["cin"], m["cout"])
+            else:
+                block(f"{side}.{name}.", m)
+    gated("out_conv.", layout["cout"], layout["img_channels"])
+    return sd
+
+
+def train_step(sd, layout, images, sigma, noise, conditioning=None, sigma_data: float = 1.0):
+    """One reference-style training micro-step on CPU: loss (edm2/loss.py) + backward; returns (loss, grads)."""
+    leaves = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and ".rope." not in k and "fourier" not in k else v)
+              for k, v in sd.items()}
+    loss = edm2_loss(leaves, layout, images, sigma, noise, conditioning, sigma_data)
+    loss.backward()
+    return loss.detach(), {k: v.grad for k, v in leaves.items() if isinstance(v, Tensor) and v.requires_grad}
