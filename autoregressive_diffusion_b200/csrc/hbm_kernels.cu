@@ -118,20 +118,58 @@ __global__ void __launch_bounds__(256) wnorm_bwd_kernel(const float* __restrict_
   const float* wr = w + static_cast<long>(co) * K;
   const long split_stride = static_cast<long>(Co) * taps_total * Ci_pad;
   const float* gsrc = dwg + (static_cast<long>(co) * taps_total + tap_off) * Ci_pad;
-  for (int j = threadIdx.x; j < taps * Ci_pad; j += blockDim.x) {
-    const int tap = j / Ci_pad, ci = j - tap * Ci_pad;
-    if (ci >= Ci) continue;
-    float g = 0.f;
-    for (int s = 0; s < n_split; ++s) g += gsrc[s * split_stride + j];
-    gbuf[tap * ld + ci] = g;
+  const bool vec = ((Ci_pad & 3) == 0) && ((K & 3) == 0) && ((reinterpret_cast<uintptr_t>(gsrc) & 15) == 0) &&
+                   ((split_stride & 3) == 0);
+  // ---- stage 1: reduce the split partials, keep the row in shared memory (tap-major, padded)
+  if (vec) {
+    const int n4 = taps * Ci_pad / 4;
+    for (int j4 = threadIdx.x; j4 < n4; j4 += blockDim.x) {
+      float4 g = *reinterpret_cast<const float4*>(gsrc + j4 * 4);
+      for (int s = 1; s < n_split; ++s) {
+        const float4 t = *reinterpret_cast<const float4*>(gsrc + s * split_stride + j4 * 4);
+        g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w;
+      }
+      const int j = j4 * 4;
+      const int tap = j / Ci_pad, ci = j - tap * Ci_pad;
+      float* dst = gbuf + tap * ld + ci;
+      if (ci + 3 < Ci) { dst[0] = g.x; dst[1] = g.y; dst[2] = g.z; dst[3] = g.w; }
+      else {
+        if (ci < Ci) dst[0] = g.x;
+        if (ci + 1 < Ci) dst[1] = g.y;
+        if (ci + 2 < Ci) dst[2] = g.z;
+      }
+    }
+  } else {
+    for (int j = threadIdx.x; j < taps * Ci_pad; j += blockDim.x) {
+      const int tap = j / Ci_pad, ci = j - tap * Ci_pad;
+      if (ci >= Ci) continue;
+      float g = 0.f;
+      for (int s = 0; s < n_split; ++s) g += gsrc[s * split_stride + j];
+      gbuf[tap * ld + ci] = g;
+    }
   }
   __syncthreads();
+  // ---- stage 2: <g,w> and |w|^2 in the parameter's own order (coalesced w, conflict-free smem gather)
   float ss = 0.f, dot = 0.f;
-  for (int i = threadIdx.x; i < K; i += blockDim.x) {
-    const int ci = i / taps, tap = i - ci * taps;
-    const float wv = wr[i];
-    ss += wv * wv;
-    dot += gbuf[tap * ld + ci] * wv;
+  if (vec) {
+    for (int i4 = threadIdx.x; i4 < K / 4; i4 += blockDim.x) {
+      const float4 wv = *reinterpret_cast<const float4*>(wr + i4 * 4);
+      const float wa[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i4 * 4 + u;
+        const int ci = i / taps, tap = i - ci * taps;
+        ss += wa[u] * wa[u];
+        dot += gbuf[tap * ld + ci] * wa[u];
+      }
+    }
+  } else {
+    for (int i = threadIdx.x; i < K; i += blockDim.x) {
+      const int ci = i / taps, tap = i - ci * taps;
+      const float wv = wr[i];
+      ss += wv * wv;
+      dot += gbuf[tap * ld + ci] * wv;
+    }
   }
   ss = block_sum(ss, red);
   dot = block_sum(dot, red);
@@ -140,10 +178,31 @@ __global__ void __launch_bounds__(256) wnorm_bwd_kernel(const float* __restrict_
   const float c = gain * rsqrtf(static_cast<float>(K)) / d;
   const float proj = (rms > 0.f) ? dot / (K * rms * d) : 0.f;
   float* dwr = dw + static_cast<long>(co) * K;
-  for (int i = threadIdx.x; i < K; i += blockDim.x) {
-    const int ci = i / taps, tap = i - ci * taps;
-    const float v = c * (gbuf[tap * ld + ci] - wr[i] * proj);
-    dwr[i] = accumulate ? dwr[i] + v : v;
+  // ---- stage 3: dw (+)= c * (g - w * proj)
+  if (vec) {
+    for (int i4 = threadIdx.x; i4 < K / 4; i4 += blockDim.x) {
+      const float4 wv = *reinterpret_cast<const float4*>(wr + i4 * 4);
+      const float wa[4] = {wv.x, wv.y, wv.z, wv.w};
+      float o[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i4 * 4 + u;
+        const int ci = i / taps, tap = i - ci * taps;
+        o[u] = c * (gbuf[tap * ld + ci] - wa[u] * proj);
+      }
+      float4* dst = reinterpret_cast<float4*>(dwr + i4 * 4);
+      if (accumulate) {
+        const float4 old = *dst;
+        o[0] += old.x; o[1] += old.y; o[2] += old.z; o[3] += old.w;
+      }
+      *dst = make_float4(o[0], o[1], o[2], o[3]);
+    }
+  } else {
+    for (int i = threadIdx.x; i < K; i += blockDim.x) {
+      const int ci = i / taps, tap = i - ci * taps;
+      const float v = c * (gbuf[tap * ld + ci] - wr[i] * proj);
+      dwr[i] = accumulate ? dwr[i] + v : v;
+    }
   }
 }
 

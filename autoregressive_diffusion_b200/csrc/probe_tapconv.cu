@@ -209,6 +209,12 @@ int main(int argc, char** argv) {
     run(gated("CS 512->512 4x4 B2 n16", 2, 2, 16, 4, 4, 512, 512), false, 20);
     run(gated("CS 1024->512 8x8 B2 n16", 2, 2, 16, 8, 8, 1024, 512), false, 20);
     run(gated("CS 512->512 16x16 bn64", 2, 2, 16, 16, 16, 512, 512, 64), false, 20);
+    run(gated("CS 512->512 8x8 bn128", 2, 2, 16, 8, 8, 512, 512, 128), false, 20);
+    run(gated("CS 512->512 8x8 bn64", 2, 2, 16, 8, 8, 512, 512, 64), false, 20);
+    run(gated("CS 512->512 8x8 bn32", 2, 2, 16, 8, 8, 512, 512, 32), false, 20);
+    run(gated("CS 512->512 4x4 bn128", 2, 2, 16, 4, 4, 512, 512, 128), false, 20);
+    run(gated("CS 512->512 4x4 bn64", 2, 2, 16, 4, 4, 512, 512, 64), false, 20);
+    run(gated("CS 512->512 4x4 bn32", 2, 2, 16, 4, 4, 512, 512, 32), false, 20);
     run(plain("gemm 16384x512x1536", 64, 16, 16, 512, 1536, 1, 0), false, 20);
     run(plain("gemm 16384x512x512 bn128", 64, 16, 16, 512, 512, 1, 0, 128), false, 20);
     run(plain("conv3x3 512->512 16x16 F64 bn256", 64, 16, 16, 512, 512, 3, 0, 256), false, 20);

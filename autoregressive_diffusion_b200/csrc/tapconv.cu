@@ -160,7 +160,7 @@ int tapconv_launch(const TapConvLaunch& L, cudaStream_t stream) {
   if (bn > bn_max) bn = bn_max;
   if (L.force_bn > 0) bn = L.force_bn;
   else
-    while (bn > 32 && m_tiles * ((L.Cout + bn - 1) / bn) < 148) bn >>= 1;
+    while (bn > 64 && m_tiles * ((L.Cout + bn - 1) / bn) < 148) bn >>= 1;  // below 64 the A re-reads cost more than the idle SMs
   if (L.b_mn_major && bn < chunk) bn = chunk;
   if (n_acc * bn > 512) {
     set_error("tapconv: %d accumulators x N=%d exceed TMEM", n_acc, bn);

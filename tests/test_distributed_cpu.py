@@ -1,0 +1,45 @@
+"""world_size-2 gloo tests of the data-parallel plumbing (bucketed gradient mean, env:// init) on CPU."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    from autoregressive_diffusion_b200.train import GradientBuckets, init_distributed
+    r, w, _ = init_distributed()
+    assert (r, w) == (rank, world) and dist.get_backend() == "gloo"
+    torch.manual_seed(0)
+    params = [torch.nn.Parameter(torch.zeros(n)) for n in (7, 1000, 3, 64 * 64)]
+    params.append(torch.nn.Parameter(torch.zeros(5)))           # never receives a gradient (like emb_time / out_res)
+    for i, p in enumerate(params[:-1]):
+        p.grad = torch.full_like(p, float(rank + 1) * (i + 1))
+    buckets = GradientBuckets(params, bucket_bytes=2048)        # several small buckets
+    buckets.all_reduce_mean()
+    ok = all(torch.allclose(p.grad, torch.full_like(p, 1.5 * (i + 1))) for i, p in enumerate(params[:-1]))
+    ok = ok and params[-1].grad is None and len(buckets.buckets) >= 2
+    out.put((rank, ok))
+    dist.destroy_process_group()
+
+
+def test_bucketed_gradient_mean_world2():
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = sorted(out.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert results == [(0, True), (1, True)]

@@ -1,0 +1,131 @@
+"""CPU-only checks: the C-ABI library loads and exports every declared symbol, the header and the binding agree,
+the host-side module mirror keeps the reference's interface, and the product refuses to run without CUDA."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    text = open(os.path.join(ROOT, "include", "oniris_b200.h")).read()
+    return sorted(set(re.findall(r"\b(ob_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from autoregressive_diffusion_b200 import _lib
+    lib = _lib.lib()           # raises if the .so is missing: build() must have produced it
+    declared = _header_symbols()
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/oniris_b200.h but not exported"
+    assert sorted(_lib.DECLARED) == declared, "ctypes binding and header disagree on the symbol set"
+    assert lib.ob_version() >= 100
+    assert isinstance(lib.ob_last_error(), bytes)
+
+
+def test_binding_arity_matches_header():
+    from autoregressive_diffusion_b200 import _lib
+    text = open(os.path.join(ROOT, "include", "oniris_b200.h")).read()
+    for name, sig in _lib._SIGS.items():
+        m = re.search(r"\b" + name + r"\s*\(([^;]*?)\)\s*;", text, re.S)
+        assert m, name
+        n_args = len([a for a in m.group(1).split(",") if a.strip() and a.strip() != "void"])
+        assert n_args == len(sig), f"{name}: header has {n_args} parameters, binding {len(sig)}"
+
+
+def test_no_cpu_fallback():
+    import autoregressive_diffusion_b200 as ob
+    conv = ob.MPCausal3DGatedConv(16, 16, (3, 3, 3))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        conv(torch.randn(4, 16, 8, 8), None, 2, torch.zeros(2, 2))
+    m = ob.MPConv(16, 16, [3, 3])
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.randn(2, 16, 8, 8))
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "autoregressive_diffusion_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert "oracle" not in src.replace("# oracle", ""), f"{fn} mentions the oracle"
+
+
+def test_state_dict_keys_match_reference_golden(golden):
+    import autoregressive_diffusion_b200 as ob
+    g = golden("unet")
+    unet = ob.UNet(**g["kwargs"])
+    ours = {k: tuple(v.shape) for k, v in unet.state_dict().items()}
+    ref = {k: tuple(s) for k, s in g["shapes"]}
+    assert ours == ref
+    for name, gold in (("gated_conv", ob.MPCausal3DGatedConv(16, 24, (3, 3, 3))), ("video_attention", ob.VideoAttention(128, 2)),
+                       ("frame_attention", ob.FrameAttention(128, 2))):
+        assert set(gold.state_dict()) == set(golden(name)["sd0"]), name
+
+
+def test_block_lists_bit_exact(golden):
+    """kv_num_blocks / kv_indices of make_train_mask / make_infer_mask, int32, against the reference's own tensors."""
+    import autoregressive_diffusion_b200 as ob
+    n_checked = 0
+    for (kind, n, hw), ref in golden("block_lists").items():
+        got = ob.make_train_mask(2, 3, n, hw) if kind == "train" else ob.make_infer_mask(2, 3, n, hw)
+        if ref is None:
+            assert got is None
+            continue
+        assert got["BLOCK_SIZE"] == ref[2]
+        assert got["kv_num_blocks"].dtype == np.int32 and got["kv_indices"].dtype == np.int32
+        assert np.array_equal(got["kv_num_blocks"][1, 2], ref[0].numpy())
+        assert np.array_equal(got["kv_indices"][0, 1], ref[1].numpy())
+        n_checked += 1
+    assert n_checked >= 20
+
+
+def test_rope_tables_match_reference(golden):
+    import autoregressive_diffusion_b200 as ob
+    g = golden("rope")
+    rope = ob.RotaryEmbedding(64)
+    assert torch.equal(rope.inv_freq, g["inv_freq"]) and torch.equal(rope.scale, g["scale"])
+    cos_t, sin_t, scl_t = rope.tables(9)
+    assert torch.equal(cos_t, g["ang9"][:, 0].cos().float())
+    assert torch.equal(sin_t, g["ang9"][:, 0].sin().float())
+    assert torch.equal(scl_t, g["scale9"][:, 0].float())
+
+
+def test_gating_and_linear_layers_on_cpu(golden):
+    """The tiny host-side pieces (Gating, the embedding linears' NormalizedWeight) are plain torch and must match the oracle."""
+    import autoregressive_diffusion_b200 as ob
+    from oracle import oniris_oracle as O
+    torch.manual_seed(0)
+    gt = ob.Gating()
+    cn = torch.randn(3, 8)
+    for training in (True, False):
+        gt.train(training)
+        got, n = gt(cn, 5)
+        gp = {k: getattr(gt, k).detach() for k in ("offset", "mult", "max_gating", "min_gating")}
+        ref, n_ref = O.gating(cn, gp, 5, training)
+        assert n == n_ref and torch.allclose(got, ref, atol=1e-6)
+    lin = ob.MPConv(32, 48, kernel=[])
+    w0 = lin.weight.weight.detach().clone()
+    x = torch.randn(5, 32)
+    lin.eval()
+    assert torch.allclose(lin(x, gain=0.7), O.mp_conv(x, w0, 0.7, False), atol=1e-5)
+    lin.train()
+    assert torch.allclose(lin(x, gain=0.7), O.mp_conv(x, w0, 0.7, True), atol=1e-5)
+    assert torch.allclose(lin.weight.weight.detach(), O.normalize(w0), atol=1e-6)
+
+
+def test_functional_utils_on_cpu(golden):
+    import autoregressive_diffusion_b200 as ob
+    g = golden("elementwise")
+    a, b, t = g["a"], g["b"], g["t"]
+    assert torch.allclose(ob.mp_sum(a, b, 0.3), g["mp_sum_f"], atol=1e-6)
+    assert torch.allclose(ob.mp_sum(a, b, t), g["mp_sum_t"], atol=1e-6)
+    assert torch.allclose(ob.mp_silu(a), g["mp_silu"], atol=1e-6)
+    assert torch.allclose(ob.mp_cat(a, b[:, :4], t=0.5), g["mp_cat"], atol=1e-6)
+    assert torch.allclose(ob.normalize(a, dim=1), g["norm1"], atol=1e-6)
+    assert torch.allclose(ob.resample(a, mode="down"), g["down"], atol=1e-6)
+    assert torch.allclose(ob.resample(a, mode="up"), g["up"], atol=1e-6)
