@@ -18,11 +18,24 @@ int attn_bwd(const void* q, const void* k, const void* v, const void* o, const v
              cudaStream_t st);
 }
 
-static TapItem tap_item(int src, int dt, int dy, int dx, int n_a, int acc, int seq_mul, int wtap) {
-  TapItem t{};
-  t.src = (int8_t)src; t.dt = (int8_t)dt; t.dy = (int8_t)dy; t.dx = (int8_t)dx;
-  t.n_a = (int8_t)n_a; t.acc = (int8_t)acc; t.seq_mul = (int8_t)seq_mul; t.wtap = wtap;
-  return t;
+// A column of vertical taps at horizontal shift dx.  `flip` mirrors the kernel (input-gradient passes): the tap applied
+// at shift (dy, dx) is then the forward tap (-dy, -dx).  tap_base: first tap of this 3x3 slice in the weight matrix.
+static TapCol tap_col3(int src, int dt, int dx, int n_a, int acc, int seq_mul, int tap_base, bool flip) {
+  TapCol c{};
+  c.src = (int8_t)src; c.dt = (int8_t)dt; c.dx = (int8_t)dx; c.n_a = (int8_t)n_a; c.acc = (int8_t)acc;
+  c.seq_mul = (int8_t)seq_mul; c.n_taps = 3;
+  for (int d = 0; d < 3; ++d) {
+    const int dy = d - 1;
+    const int ky = flip ? 1 - dy : dy + 1, kx = flip ? 1 - dx : dx + 1;
+    c.wtap[d] = tap_base + ky * 3 + kx;
+  }
+  return c;
+}
+static TapCol tap_col1(int src, int n_a, int acc, int seq_mul) {
+  TapCol c{};
+  c.src = (int8_t)src; c.n_a = (int8_t)n_a; c.acc = (int8_t)acc; c.seq_mul = (int8_t)seq_mul; c.n_taps = 1;
+  c.wtap[0] = 0;
+  return c;
 }
 static void set_src(TapConvLaunch& L, int s, const void* p, int seq, int T, int H, int W, int C) {
   L.a[s] = p; L.a_seq[s] = seq; L.a_T[s] = T;
@@ -57,24 +70,24 @@ int ob_conv_fwd(const void* x, const void* ctx, const void* wg, const float* alp
                 void* stream) {
   if (int r = check_shape("ob_conv_fwd", n_seq, S, T, H, W, ksize, gated)) return r;
   TapConvLaunch L;
-  std::vector<TapItem> items;
+  std::vector<TapCol> cols;
   if (!gated) {
     // frames are independent: fold (seq, S, T) into one long frame axis so tiles never straddle less than they must
     const int frames = n_seq * S * T;
     set_src(L, 0, x, 1, frames, H, W, cin);
-    for (int ky = 0; ky < ksize; ++ky)
-      for (int kx = 0; kx < ksize; ++kx) items.push_back(tap_item(0, 0, ky - ksize / 2, kx - ksize / 2, 1, 0, 1, ky * ksize + kx));
-    L.n_seq = 1; L.n_out = 1; L.T = frames; L.w_taps = ksize * ksize; L.epi = EPI_PLAIN;
+    if (ksize == 1) cols.push_back(tap_col1(0, 1, 0, 1));
+    else for (int dx = -1; dx <= 1; ++dx) cols.push_back(tap_col3(0, 0, dx, 1, 0, 1, 0, false));
+    L.n_seq = 1; L.n_out = 1; L.T = frames; L.w_taps = ksize * ksize; L.epi = EPI_PLAIN; L.halo = ksize == 3;
   } else {
     set_src(L, 0, x, n_seq * S, T, H, W, cin);
     set_src(L, 1, ctx, n_seq, T + 2, H, W, cin);
-    for (int k = 0; k < 9; ++k) items.push_back(tap_item(0, 0, k / 3 - 1, k % 3 - 1, S, 0, S, k));
+    for (int dx = -1; dx <= 1; ++dx) cols.push_back(tap_col3(0, 0, dx, S, 0, S, 0, false));
     for (int tau = 0; tau < 2; ++tau)
-      for (int k = 0; k < 9; ++k) items.push_back(tap_item(1, tau, k / 3 - 1, k % 3 - 1, 1, S, 1, 9 + tau * 9 + k));
-    L.n_seq = n_seq; L.n_out = S; L.T = T; L.w_taps = 27; L.epi = EPI_GATED;
+      for (int dx = -1; dx <= 1; ++dx) cols.push_back(tap_col3(1, tau, dx, 1, S, 1, 9 + tau * 9, false));
+    L.n_seq = n_seq; L.n_out = S; L.T = T; L.w_taps = 27; L.epi = EPI_GATED; L.halo = 1;
     L.alpha = alpha; L.beta = beta; L.out_d = out_d;
   }
-  L.wg = wg; L.items = items.data(); L.n_items = (int)items.size();
+  L.wg = wg; L.cols = cols.data(); L.n_cols = (int)cols.size();
   L.H = H; L.W = W; L.Cin = cin; L.Cout = cout; L.out_f32 = out_f32; L.out = out;
   return tapconv_launch(L, (cudaStream_t)stream);
 }
@@ -82,28 +95,28 @@ int ob_conv_fwd(const void* x, const void* ctx, const void* wg, const float* alp
 int ob_conv_dgrad(const void* gy, const void* gb, const void* wg, const float* alpha, const float* beta, void* dx,
                   int n_seq, int S, int T, int H, int W, int cin, int cout, int ksize, int gated, void* stream) {
   if (int r = check_shape("ob_conv_dgrad", n_seq, S, T, H, W, ksize, gated)) return r;
-  // transposed problem: GEMM K = cout (channels of the incoming gradient), GEMM N = cin
+  // transposed problem: GEMM K = cout (channels of the incoming gradient), GEMM N = cin; taps are mirrored
   TapConvLaunch L;
-  std::vector<TapItem> items;
+  std::vector<TapCol> cols;
   if (!gated) {
     const int frames = n_seq * S * T;
     set_src(L, 0, gy, 1, frames, H, W, cout);
-    for (int ky = 0; ky < ksize; ++ky)
-      for (int kx = 0; kx < ksize; ++kx) items.push_back(tap_item(0, 0, ksize / 2 - ky, ksize / 2 - kx, 1, 0, 1, ky * ksize + kx));
-    L.n_seq = 1; L.n_out = 1; L.T = frames; L.w_taps = ksize * ksize; L.epi = EPI_PLAIN;
+    if (ksize == 1) cols.push_back(tap_col1(0, 1, 0, 1));
+    else for (int sx = -1; sx <= 1; ++sx) cols.push_back(tap_col3(0, 0, sx, 1, 0, 1, 0, true));
+    L.n_seq = 1; L.n_out = 1; L.T = frames; L.w_taps = ksize * ksize; L.epi = EPI_PLAIN; L.halo = ksize == 3;
   } else {
     set_src(L, 0, gy, n_seq * S, T, H, W, cout);
     set_src(L, 1, gb, n_seq, T, H, W, cout);
-    for (int k = 0; k < 9; ++k) items.push_back(tap_item(0, 0, 1 - k / 3, 1 - k % 3, S, 0, S, k));
+    for (int sx = -1; sx <= 1; ++sx) cols.push_back(tap_col3(0, 0, sx, S, 0, S, 0, true));
     // context frame t' fed output frames t'+2-tau through tap tau; that term goes to its own accumulator and the
     // epilogue adds it with weight beta (1 on clean rows, 0 on noised rows), so dy itself is never pre-scaled.
     for (int tau = 0; tau < 2; ++tau)
-      for (int k = 0; k < 9; ++k) items.push_back(tap_item(1, 2 - tau, 1 - k / 3, 1 - k % 3, 1, S, 1, 9 + tau * 9 + k));
-    L.n_seq = n_seq; L.n_out = S; L.T = T; L.w_taps = 27; L.epi = EPI_GATED;
+      for (int sx = -1; sx <= 1; ++sx) cols.push_back(tap_col3(1, 2 - tau, sx, 1, S, 1, 9 + tau * 9, true));
+    L.n_seq = n_seq; L.n_out = S; L.T = T; L.w_taps = 27; L.epi = EPI_GATED; L.halo = 1;
     L.alpha = alpha; L.beta = beta;
   }
   L.b_mn_major = 1;
-  L.wg = wg; L.items = items.data(); L.n_items = (int)items.size();
+  L.wg = wg; L.cols = cols.data(); L.n_cols = (int)cols.size();
   L.H = H; L.W = W; L.Cin = cout; L.Cout = cin; L.out_f32 = 0; L.out = dx;
   return tapconv_launch(L, (cudaStream_t)stream);
 }

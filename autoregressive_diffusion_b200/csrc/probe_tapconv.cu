@@ -23,15 +23,27 @@ struct Problem {
   int n_seq, n_out, T, H, W, Cin, Cout, epi, out_f32;
   int seqA[2], TA[2];
   int w_taps;
-  std::vector<TapItem> items;
+  std::vector<TapCol> cols;
   int force_bn;
   int bmn;
+  int halo;
 };
 
-static TapItem mk(int src, int dt, int dy, int dx, int n_a, int acc, int seq_mul, int wtap) {
-  TapItem t{};
-  t.src = src; t.dt = dt; t.dy = dy; t.dx = dx; t.n_a = n_a; t.acc = acc; t.seq_mul = seq_mul; t.wtap = wtap;
-  return t;
+// column of vertical taps at horizontal shift dx; flip mirrors the kernel (input-gradient form)
+static TapCol mk3(int src, int dt, int dx, int n_a, int acc, int seq_mul, int tap_base, bool flip) {
+  TapCol c{};
+  c.src = src; c.dt = dt; c.dx = dx; c.n_a = n_a; c.acc = acc; c.seq_mul = seq_mul; c.n_taps = 3;
+  for (int d = 0; d < 3; ++d) {
+    int dy = d - 1;
+    int ky = flip ? 1 - dy : dy + 1, kx = flip ? 1 - dx : dx + 1;
+    c.wtap[d] = tap_base + ky * 3 + kx;
+  }
+  return c;
+}
+static TapCol mk1(int src, int n_a, int acc, int seq_mul) {
+  TapCol c{};
+  c.src = src; c.n_a = n_a; c.acc = acc; c.seq_mul = seq_mul; c.n_taps = 1; c.wtap[0] = 0;
+  return c;
 }
 
 static bool run(const Problem& P, bool check, int reps) {
@@ -74,7 +86,7 @@ static bool run(const Problem& P, bool check, int reps) {
     L.a_stride_w[s] = P.Cin; L.a_stride_h[s] = (long)P.W * P.Cin; L.a_stride_t[s] = (long)P.H * P.W * P.Cin;
     L.a_stride_seq[s] = (long)P.TA[s] * P.H * P.W * P.Cin;
   }
-  L.wg = dW; L.w_taps = P.w_taps; L.items = P.items.data(); L.n_items = (int)P.items.size();
+  L.wg = dW; L.w_taps = P.w_taps; L.cols = P.cols.data(); L.n_cols = (int)P.cols.size(); L.halo = P.halo;
   L.n_seq = P.n_seq; L.n_out = P.n_out; L.T = P.T; L.H = P.H; L.W = P.W; L.Cin = P.Cin; L.Cout = P.Cout;
   L.epi = P.epi; L.out_f32 = P.out_f32; L.alpha = dal; L.beta = dbe; L.out = dOut;
   L.out_d = (P.epi == EPI_GATED) ? dD : nullptr; L.force_bn = P.force_bn; L.b_mn_major = P.bmn;
@@ -104,16 +116,18 @@ static bool run(const Problem& P, bool check, int reps) {
           for (int w = 0; w < P.W; ++w)
             for (int n = 0; n < P.Cout; ++n) {
               for (auto& a : acc) a = 0;
-              for (const TapItem& it : P.items)
-                for (int i = 0; i < it.n_a; ++i) {
-                  int sq = seq * it.seq_mul + i, tt = t + it.dt, hh = h + it.dy, ww = w + it.dx;
-                  if (tt < 0 || tt >= P.TA[it.src] || hh < 0 || hh >= P.H || ww < 0 || ww >= P.W) continue;
-                  const float* ap = &A[it.src][((((size_t)sq * P.TA[it.src] + tt) * P.H + hh) * P.W + ww) * P.Cin];
-                  const float* wp = &Wt[((size_t)n * P.w_taps + it.wtap) * P.Cin];
-                  double s = 0;
-                  for (int c = 0; c < P.Cin; ++c) s += (double)ap[c] * wp[c];
-                  acc[it.acc + i] += s;
-                }
+              for (const TapCol& it : P.cols)
+                for (int d = 0; d < it.n_taps; ++d)
+                  for (int i = 0; i < it.n_a; ++i) {
+                    int dy = it.n_taps == 3 ? d - 1 : 0;
+                    int sq = seq * it.seq_mul + i, tt = t + it.dt, hh = h + dy, ww = w + it.dx;
+                    if (tt < 0 || tt >= P.TA[it.src] || hh < 0 || hh >= P.H || ww < 0 || ww >= P.W) continue;
+                    const float* ap = &A[it.src][((((size_t)sq * P.TA[it.src] + tt) * P.H + hh) * P.W + ww) * P.Cin];
+                    const float* wp = &Wt[((size_t)n * P.w_taps + it.wtap[d]) * P.Cin];
+                    double s = 0;
+                    for (int c = 0; c < P.Cin; ++c) s += (double)ap[c] * wp[c];
+                    acc[it.acc + i] += s;
+                  }
               for (int o = 0; o < P.n_out; ++o) {
                 size_t frame = (size_t)(seq * P.n_out + o) * P.T + t;
                 size_t idx = ((frame * P.H + h) * P.W + w) * P.Cout + n;
@@ -137,7 +151,7 @@ static bool run(const Problem& P, bool check, int reps) {
     cudaEventRecord(e1); cudaEventSynchronize(e1);
     float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= reps;
     double flops = 0;
-    for (const TapItem& it : P.items) flops += 2.0 * it.n_a * P.n_seq * P.T * P.H * P.W * (double)P.Cin * P.Cout;
+    for (const TapCol& it : P.cols) flops += 2.0 * it.n_taps * it.n_a * P.n_seq * P.T * P.H * P.W * (double)P.Cin * P.Cout;
     printf("[%s] time %.1f us  %.1f TFLOP/s  (%.3f GFLOP)\n", P.name, ms * 1e3, flops / ms / 1e9, flops / 1e9);
   }
   for (int s = 0; s < 2; ++s) cudaFree(dA[s]);
@@ -149,19 +163,19 @@ static Problem gated(const char* name, int B, int S, int n, int H, int W, int Ci
   Problem P{};
   P.name = name; P.n_seq = B; P.n_out = S; P.T = n; P.H = H; P.W = W; P.Cin = Cin; P.Cout = Cout;
   P.epi = EPI_GATED; P.out_f32 = 0; P.seqA[0] = B * S; P.TA[0] = n; P.seqA[1] = B; P.TA[1] = n + 2; P.w_taps = 27;
-  P.force_bn = force_bn;
-  for (int ky = 0; ky < 3; ++ky) for (int kx = 0; kx < 3; ++kx) P.items.push_back(mk(0, 0, ky - 1, kx - 1, S, 0, S, ky * 3 + kx));
+  P.force_bn = force_bn; P.halo = 1;
+  for (int dx = -1; dx <= 1; ++dx) P.cols.push_back(mk3(0, 0, dx, S, 0, S, 0, false));
   for (int tau = 0; tau < 2; ++tau)
-    for (int ky = 0; ky < 3; ++ky) for (int kx = 0; kx < 3; ++kx)
-      P.items.push_back(mk(1, tau, ky - 1, kx - 1, 1, S, 1, 9 + tau * 9 + ky * 3 + kx));
+    for (int dx = -1; dx <= 1; ++dx) P.cols.push_back(mk3(1, tau, dx, 1, S, 1, 9 + tau * 9, false));
   return P;
 }
 static Problem plain(const char* name, int F, int H, int W, int Cin, int Cout, int k, int f32, int force_bn = 0) {
   Problem P{};
   P.name = name; P.n_seq = 1; P.n_out = 1; P.T = F; P.H = H; P.W = W; P.Cin = Cin; P.Cout = Cout;
   P.epi = EPI_PLAIN; P.out_f32 = f32; P.seqA[0] = 1; P.TA[0] = F; P.seqA[1] = 0; P.TA[1] = 0; P.w_taps = k * k;
-  P.force_bn = force_bn;
-  for (int ky = 0; ky < k; ++ky) for (int kx = 0; kx < k; ++kx) P.items.push_back(mk(0, 0, ky - k / 2, kx - k / 2, 1, 0, 1, ky * k + kx));
+  P.force_bn = force_bn; P.halo = (k == 3);
+  if (k == 1) P.cols.push_back(mk1(0, 1, 0, 1));
+  else for (int dx = -1; dx <= 1; ++dx) P.cols.push_back(mk3(0, 0, dx, 1, 0, 1, 0, false));
   return P;
 }
 // input-gradient shape of the gated conv: dual rows from src0, causal terms (dt=+1,+2) from src1 into acc 0
@@ -170,10 +184,10 @@ static Problem dgrad(const char* name, int B, int n, int H, int W, int Cin, int 
   P.bmn = bmn;
   P.name = name; P.n_seq = B; P.n_out = 2; P.T = n; P.H = H; P.W = W; P.Cin = Cin; P.Cout = Cout;
   P.epi = EPI_PLAIN; P.out_f32 = 0; P.seqA[0] = B * 2; P.TA[0] = n; P.seqA[1] = B; P.TA[1] = n; P.w_taps = 27;
-  for (int ky = 0; ky < 3; ++ky) for (int kx = 0; kx < 3; ++kx) P.items.push_back(mk(0, 0, ky - 1, kx - 1, 2, 0, 2, ky * 3 + kx));
+  P.halo = 1;
+  for (int dx = -1; dx <= 1; ++dx) P.cols.push_back(mk3(0, 0, dx, 2, 0, 2, 0, true));
   for (int tau = 0; tau < 2; ++tau)
-    for (int ky = 0; ky < 3; ++ky) for (int kx = 0; kx < 3; ++kx)
-      P.items.push_back(mk(1, 2 - tau, ky - 1, kx - 1, 1, 0, 1, 9 + tau * 9 + ky * 3 + kx));
+    for (int dx = -1; dx <= 1; ++dx) P.cols.push_back(mk3(1, 2 - tau, dx, 1, 0, 1, 9 + tau * 9, true));
   return P;
 }
 

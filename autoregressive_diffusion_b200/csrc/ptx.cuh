@@ -46,6 +46,28 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+// Long waits by whole warps (epilogue waiting for the main loop): back off so the pollers do not steal issue
+// slots from the single producer / MMA-issuer threads that share their SM sub-partitions.
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(256);
+    if (++spins > (1u << 24)) __trap();
+  }
+}
+
+// One lane of a fully converged warp (warp-uniform code keeps descriptors in uniform registers; wrapping single-thread
+// instructions in `if (lane == 0)` instead makes the compiler emit a uniformisation loop around every UTCHMMA).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ----------------------------------------------------------------------------- TMA
 __device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");

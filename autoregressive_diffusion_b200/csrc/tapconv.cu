@@ -92,17 +92,18 @@ static int launch_inst(const TapConvParams& p, int grid, cudaStream_t stream) {
     set_error("tapconv: MN-major weights need tile N %d to be a multiple of %d", BN, CHUNK);
     return OB_ERR_UNSUPPORTED;
   } else {
+    constexpr int MAX_DYN = 226 * 1024;
     static bool attr_set = false;  // benign race: setting twice is harmless
     if (!attr_set) {
-      cudaError_t e = cudaFuncSetAttribute(tapconv_kernel<CHUNK, BN, BMN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           Cfg::SMEM_BYTES);
+      cudaError_t e = cudaFuncSetAttribute(tapconv_kernel<CHUNK, BN, BMN>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN);
       if (e != cudaSuccess) {
-        set_error("cudaFuncSetAttribute(tapconv<%d,%d>, %d B): %s", CHUNK, BN, Cfg::SMEM_BYTES, cudaGetErrorString(e));
+        set_error("cudaFuncSetAttribute(tapconv<%d,%d>, %d B): %s", CHUNK, BN, MAX_DYN, cudaGetErrorString(e));
         return OB_ERR_CUDA;
       }
       attr_set = true;
     }
-    tapconv_kernel<CHUNK, BN, BMN><<<grid, TAPCONV_THREADS, Cfg::SMEM_BYTES, stream>>>(p);
+    const int smem = 1024 + p.a_slots * p.a_slot_bytes + p.b_slots * Cfg::B_BYTES_AL + 256;
+    tapconv_kernel<CHUNK, BN, BMN><<<grid, TAPCONV_THREADS, smem, stream>>>(p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
       set_error("tapconv<%d,%d> launch: %s", CHUNK, BN, cudaGetErrorString(e));
@@ -130,8 +131,8 @@ int tapconv_launch(const TapConvLaunch& L, cudaStream_t stream) {
     set_error("tapconv: Cin (%d) and Cout (%d) must be multiples of 8", L.Cin, L.Cout);
     return OB_ERR_INVALID;
   }
-  if (L.n_items < 1 || L.n_items > TAPCONV_MAX_ITEMS) {
-    set_error("tapconv: bad item count %d", L.n_items);
+  if (L.n_cols < 1 || L.n_cols > TAPCONV_MAX_COLS) {
+    set_error("tapconv: bad column count %d", L.n_cols);
     return OB_ERR_INVALID;
   }
   if (L.n_seq <= 0 || L.T <= 0) return OB_OK;  // empty problem
@@ -144,11 +145,13 @@ int tapconv_launch(const TapConvLaunch& L, cudaStream_t stream) {
 
   TapConvParams p;
   memset(&p, 0, sizeof(p));
-  // ---- pixel tile: 128 rows = bt frames x bh rows x bw cols
+  // ---- pixel tile: 128 rows ordered (hh, tt, ww); bt*bw >= 8 keeps a vertical shift a whole number of swizzle atoms
   p.bw = pow2_ceil(L.W) > 128 ? 128 : pow2_ceil(L.W);
   p.bh = pow2_ceil(L.H);
   if (p.bh > 128 / p.bw) p.bh = 128 / p.bw;
+  if (p.bh > 16) p.bh = 16;
   p.bt = 128 / (p.bw * p.bh);
+  p.halo = L.halo ? 1 : 0;
   p.tiles_w = (L.W + p.bw - 1) / p.bw;
   p.tiles_h = (L.H + p.bh - 1) / p.bh;
   p.tiles_t = (L.T + p.bt - 1) / p.bt;
@@ -160,7 +163,7 @@ int tapconv_launch(const TapConvLaunch& L, cudaStream_t stream) {
   if (bn > bn_max) bn = bn_max;
   if (L.force_bn > 0) bn = L.force_bn;
   else
-    while (bn > 64 && m_tiles * ((L.Cout + bn - 1) / bn) < 148) bn >>= 1;  // below 64 the A re-reads cost more than the idle SMs
+    while (bn > 64 && m_tiles * ((L.Cout + bn - 1) / bn) < 148) bn >>= 1;  // below 64 the A re-reads cost more than idle SMs
   if (L.b_mn_major && bn < chunk) bn = chunk;
   if (n_acc * bn > 512) {
     set_error("tapconv: %d accumulators x N=%d exceed TMEM", n_acc, bn);
@@ -168,13 +171,28 @@ int tapconv_launch(const TapConvLaunch& L, cudaStream_t stream) {
   }
   p.tiles_n = (L.Cout + bn - 1) / bn;
 
-  // ---- tensor maps
+  // ---- shared-memory rings
+  const int rows_a = (p.bh + 2 * p.halo) * p.bt * p.bw;
+  p.a_tile_bytes = rows_a * chunk * 2;
+  p.a_slot_bytes = (L.n_out * p.a_tile_bytes + 1023) / 1024 * 1024;
+  const int b_al = (bn * chunk * 2 + 1023) / 1024 * 1024;
+  const int budget = 208 * 1024;
+  p.a_slots = 3;
+  if ((budget - p.a_slots * p.a_slot_bytes) / b_al < 4) p.a_slots = 2;   // keep at least 4 weight tiles in flight
+  p.b_slots = (budget - p.a_slots * p.a_slot_bytes) / b_al;
+  if (p.b_slots > 8) p.b_slots = 8;
+  if (p.b_slots < 2) {
+    set_error("tapconv: shared memory cannot hold the rings (A slot %d B, B tile %d B)", p.a_slot_bytes, b_al);
+    return OB_ERR_UNSUPPORTED;
+  }
+
+  // ---- tensor maps: activations as (C, W, T, H, SEQ) so that the tile's rows come out ordered (hh, tt, ww)
   for (int s = 0; s < 2; ++s) {
     if (L.a[s] == nullptr) continue;
-    uint64_t dims[5] = {(uint64_t)L.Cin, (uint64_t)L.W, (uint64_t)L.H, (uint64_t)L.a_T[s], (uint64_t)L.a_seq[s]};
-    uint64_t str[5] = {1, (uint64_t)L.a_stride_w[s], (uint64_t)L.a_stride_h[s], (uint64_t)L.a_stride_t[s],
+    uint64_t dims[5] = {(uint64_t)L.Cin, (uint64_t)L.W, (uint64_t)L.a_T[s], (uint64_t)L.H, (uint64_t)L.a_seq[s]};
+    uint64_t str[5] = {1, (uint64_t)L.a_stride_w[s], (uint64_t)L.a_stride_t[s], (uint64_t)L.a_stride_h[s],
                        (uint64_t)L.a_stride_seq[s]};
-    uint32_t box[5] = {(uint32_t)chunk, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bt, 1};
+    uint32_t box[5] = {(uint32_t)chunk, (uint32_t)p.bw, (uint32_t)p.bt, (uint32_t)(p.bh + 2 * p.halo), 1};
     int r = encode_tmap_bf16(&p.mapA[s], L.a[s], 5, dims, str, box);
     if (r != OB_OK) return r;
   }
@@ -192,14 +210,17 @@ int tapconv_launch(const TapConvLaunch& L, cudaStream_t stream) {
     int r = encode_tmap_bf16(&p.mapB, L.wg, 2, dims, str, box);
     if (r != OB_OK) return r;
   }
-  for (int i = 0; i < L.n_items; ++i) {
-    p.items[i] = static_cast<const TapItem*>(L.items)[i];
-    if (L.a[p.items[i].src] == nullptr || p.items[i].acc + p.items[i].n_a > n_acc || p.items[i].wtap >= L.w_taps) {
-      set_error("tapconv: item %d is inconsistent", i);
+  for (int i = 0; i < L.n_cols; ++i) {
+    p.cols[i] = static_cast<const TapCol*>(L.cols)[i];
+    const TapCol& c = p.cols[i];
+    bool ok = L.a[c.src] != nullptr && c.acc + c.n_a <= n_acc && c.n_a <= L.n_out && (c.n_taps == 1 || (c.n_taps == 3 && p.halo));
+    for (int d = 0; ok && d < c.n_taps; ++d) ok = c.wtap[d] >= 0 && c.wtap[d] < L.w_taps;
+    if (!ok) {
+      set_error("tapconv: tap column %d is inconsistent", i);
       return OB_ERR_INVALID;
     }
   }
-  p.n_items = L.n_items;
+  p.n_cols = L.n_cols;
   p.n_seq = L.n_seq; p.T = L.T; p.H = L.H; p.W = L.W;
   p.Cin = L.Cin; p.Cout = L.Cout;
   p.n_out = L.n_out; p.epi = L.epi; p.out_f32 = L.out_f32;

@@ -1,19 +1,24 @@
-// Tap-GEMM: the one tensor-core kernel behind every "K-major x K-major" contraction on the
-// Oniris denoiser hot path (reference: edm2/conv.py:36-42 MPConv, :59-95 MPCausal3DGatedConv;
-// their input-gradient passes reuse it with flipped/transposed weights).
+// Tap-GEMM: the one tensor-core kernel behind every "activations x weights" contraction on the Oniris
+// denoiser hot path (reference: edm2/conv.py:36-42 MPConv, :59-95 MPCausal3DGatedConv; their input-gradient
+// passes reuse it with the same weight matrix read as an MN-major operand).
 //
-//   acc_j[m, n] = sum over items i with acc(i)=j, over channels c:  A_i[m + shift_i, c] * Wg[n, wtap_i, c]
+//   acc_j[m, n] = sum over taps (dt,dy,dx) routed to accumulator j, over channels c:
+//                     A[m shifted by (dt,dy,dx), c] * Wg[n, tap, c]
 //
-// * m walks a 128-row tile of output pixels laid out (frames bt) x (rows bh) x (cols bw) of an NHWC
-//   activation tensor; an item's shift (dt,dy,dx) is applied through the TMA box coordinates, so spatial
-//   zero padding and "frame past the end" are TMA out-of-bounds zero fill. No im2col buffer exists.
-// * A tiles land in shared memory as [128 rows][CHUNK channels] with the hardware swizzle that matches
-//   CHUNK*2 bytes; weights as [BN rows][CHUNK]. Both are K-major UMMA operands.
-// * tcgen05.mma (cta_group::1, M=128, N=BN, K=16) accumulates in TMEM; up to 3 accumulators per tile
-//   (clean rows, noised rows, shared causal-context term) so the context term of the DART training
-//   sequence is computed once for both halves (edm2/conv.py:90-91 duplicates it instead).
-// * Warp roles: warp0 = TMA producer, warp1 = TMEM owner + MMA issuer, warps 2..5 = epilogue
-//   (TMEM -> registers -> gated combine -> global).
+// * m walks a 128-row tile of output pixels ordered (row hh, frame tt, column ww) -- bh x bt x bw = 128.  With
+//   that order a vertical shift dy moves an operand by a whole number of 8-row swizzle atoms, so ONE shared-
+//   memory tile holding bh+2 image rows serves the three taps dy = -1, 0, +1 through three UMMA descriptors that
+//   differ only in their start address.  The activation tile is therefore fetched once per (dt, dx, channel
+//   chunk) instead of once per tap: 3x less L2->SM traffic on the operand that dominates it.
+// * Horizontal / temporal shifts and all zero padding are TMA box coordinates + out-of-bounds zero fill.
+//   No im2col buffer exists.  Channel chunks of 64/32/16 use the 128/64/32-byte hardware swizzle.
+// * Two independent smem rings: big activation tiles (A ring) and weight tiles (B ring, one per tap).
+// * tcgen05.mma (cta_group::1, M=128, N=BN, K=16) accumulates in TMEM; up to 3 accumulators per tile (clean
+//   rows, noised rows, shared causal-context term) so the context term of the DART training sequence is computed
+//   once for both halves (edm2/conv.py:90-91 duplicates it) and each current-frame weight tile feeds two MMAs.
+// * Warp roles: warp0 = activation TMA, warp1 = TMEM owner + MMA issuer, warp2 = weight TMA, warps 3..6 = epilogue
+//   (TMEM -> registers -> gated combine -> global).  Producer/MMA loops are warp-uniform with one elected lane
+//   issuing, which keeps descriptors in uniform registers (4 UTCHMMA back to back instead of an ELECT loop each).
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -22,30 +27,39 @@
 
 namespace ob {
 
-constexpr int TAPCONV_MAX_ITEMS = 32;
-constexpr int TAPCONV_THREADS = 192;
+constexpr int TAPCONV_MAX_COLS = 12;
+constexpr int TAPCONV_THREADS = 224;   // warp0: activation TMA, warp1: MMA, warp2: weight TMA, warps 3..6: epilogue
+constexpr int TAPCONV_MAX_A_SLOTS = 4;
 
 enum : int { EPI_PLAIN = 0, EPI_GATED = 1 };
 
-struct TapItem {
+// One "column" of taps: fixed (source, dt, dx); its n_taps entries are the vertical taps dy = -1,0,+1 (or the single
+// centre tap of a 1x1 kernel).
+struct TapCol {
   int8_t src;      // which activation tensor map (0 or 1)
   int8_t dt;       // frame shift
-  int8_t dy, dx;   // spatial shift
-  int8_t n_a;      // number of A tiles sharing this weight tile (1, or 2 in dual mode)
+  int8_t dx;       // horizontal shift
+  int8_t n_a;      // number of A tiles sharing each weight tile (1, or 2 in dual mode)
   int8_t acc;      // accumulator of A tile 0 (tile i goes to acc+i)
   int8_t seq_mul;  // source sequence coordinate = seq*seq_mul + i
+  int8_t n_taps;   // 1 or 3
   int8_t pad_;
-  int32_t wtap;    // column block of the weight matrix (in units of Cin)
+  int32_t wtap[3]; // weight column block (units of Cin) for dy = -1, 0, +1  (n_taps == 1: wtap[0])
 };
 
 struct TapConvParams {
   CUtensorMap mapA[2];
   CUtensorMap mapB;
-  TapItem items[TAPCONV_MAX_ITEMS];
-  int n_items;
+  TapCol cols[TAPCONV_MAX_COLS];
+  int n_cols;
   int n_seq, T, H, W;
   int Cin, Cout;
   int bw, bh, bt;
+  int halo;            // 1: A tiles carry one extra image row above and below (3x3 kernels)
+  int a_tile_bytes;    // (bh + 2*halo) * bt * bw rows * CHUNK*2 bytes
+  int a_slot_bytes;    // n_out tiles, rounded up to 1024
+  int a_slots;
+  int b_slots;
   int tiles_w, tiles_h, tiles_t, tiles_n;
   int n_out;    // output row sets per tile (2 in dual mode)
   int epi;      // EPI_*
@@ -68,15 +82,11 @@ struct SwizzleFor<16> { static constexpr uint32_t mode = SWZ_32B; };
 template <int CHUNK, int BN>
 struct TapConvCfg {
   static constexpr int ROW_BYTES = CHUNK * 2;
-  static constexpr int A_BYTES = 128 * ROW_BYTES;
   static constexpr int B_BYTES = BN * ROW_BYTES;
   static constexpr int B_BYTES_AL = (B_BYTES + 1023) / 1024 * 1024;
-  static constexpr int STAGE_BYTES = 2 * A_BYTES + B_BYTES_AL;  // room for two A tiles (dual mode)
   static constexpr int MAX_SMEM = 200 * 1024;
-  static constexpr int STAGES_RAW = MAX_SMEM / STAGE_BYTES;
-  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
   static constexpr int CW = BN >= 32 ? 32 : 16;  // epilogue column chunk
+  static constexpr int MAX_B_SLOTS = 8;
 };
 
 // BMN=false: weights are [N rows][K contiguous] (forward convs).  BMN=true: weights are [K rows][N contiguous],
@@ -86,18 +96,23 @@ template <int CHUNK, int BN, bool BMN>
 __global__ void __launch_bounds__(TAPCONV_THREADS, 1) tapconv_kernel(const __grid_constant__ TapConvParams p) {
   using Cfg = TapConvCfg<CHUNK, BN>;
   static_assert(!BMN || BN % CHUNK == 0, "MN-major weights need BN to be a multiple of CHUNK");
-  constexpr int STAGES = Cfg::STAGES;
   constexpr uint32_t SWZ = SwizzleFor<CHUNK>::mode;
   constexpr uint32_t SBO = 8 * Cfg::ROW_BYTES;
+  constexpr int MAXB = Cfg::MAX_B_SLOTS;
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
-  // barriers: full[STAGES], empty[STAGES], tmem_full, then the TMEM base address slot
-  auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
-  const uint32_t tmem_full_bar = bar_base + 8u * (2 * STAGES);
-  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 1);
+  const uint32_t sA0 = smem_base;
+  const uint32_t sB0 = sA0 + p.a_slots * p.a_slot_bytes;
+  const uint32_t bar_base = sB0 + p.b_slots * Cfg::B_BYTES_AL;
+  // barriers: a_full[MAXA], a_empty[MAXA], b_full[MAXB], b_empty[MAXB], tmem_full, then the TMEM base address slot
+  constexpr int MAXA = TAPCONV_MAX_A_SLOTS;
+  auto a_full = [&](int s) { return bar_base + 8u * s; };
+  auto a_empty = [&](int s) { return bar_base + 8u * (MAXA + s); };
+  auto b_full = [&](int s) { return bar_base + 8u * (2 * MAXA + s); };
+  auto b_empty = [&](int s) { return bar_base + 8u * (2 * MAXA + MAXB + s); };
+  const uint32_t tmem_full_bar = bar_base + 8u * (2 * MAXA + 2 * MAXB);
+  const uint32_t tmem_slot = tmem_full_bar + 8u;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -119,12 +134,11 @@ __global__ void __launch_bounds__(TAPCONV_THREADS, 1) tapconv_kernel(const __gri
   uint32_t tmem_cols = 32;
   while (tmem_cols < static_cast<uint32_t>(n_acc * BN)) tmem_cols <<= 1;
   const int n_chunks = (p.Cin + CHUNK - 1) / CHUNK;  // a ragged last chunk is TMA zero-filled
+  const uint32_t dy_stride = static_cast<uint32_t>(p.bt * p.bw) * Cfg::ROW_BYTES;  // one image row of the tile
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
-    }
+    for (int s = 0; s < p.a_slots; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
+    for (int s = 0; s < p.b_slots; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
     mbar_init(tmem_full_bar, 1);
     fence_barrier_init();
     tma_prefetch_desc(&p.mapA[0]);
@@ -142,79 +156,108 @@ __global__ void __launch_bounds__(TAPCONV_THREADS, 1) tapconv_kernel(const __gri
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int it = 0; it < p.n_items; ++it) {
-        const TapItem item = p.items[it];
-        const void* mapA = &p.mapA[item.src];
-        for (int ck = 0; ck < n_chunks; ++ck) {
-          mbar_wait(empty_bar(stage), phase ^ 1);
-          const uint32_t sA = smem_base + stage * Cfg::STAGE_BYTES;
-          const uint32_t sB = sA + 2 * Cfg::A_BYTES;
-          mbar_arrive_expect_tx(full_bar(stage), item.n_a * Cfg::A_BYTES + Cfg::B_BYTES);
-          for (int i = 0; i < item.n_a; ++i) {
-            tma_load_5d(sA + i * Cfg::A_BYTES, mapA, full_bar(stage), ck * CHUNK, w0 + item.dx, h0 + item.dy,
-                        t0 + item.dt, seq * item.seq_mul + i);
-          }
-          if constexpr (!BMN) {
-            tma_load_2d(sB, &p.mapB, full_bar(stage), item.wtap * p.Cin + ck * CHUNK, n0);
-          } else {
+    // ===================== activation (A) TMA producer (warp-uniform loop, one elected lane issues) ============
+    int as = 0;
+    uint32_t aph = 0;
+    for (int ic = 0; ic < p.n_cols; ++ic) {
+      const TapCol col = p.cols[ic];
+      const void* mapA = &p.mapA[col.src];
+      for (int ck = 0; ck < n_chunks; ++ck) {
+        mbar_wait(a_empty(as), aph ^ 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(a_full(as), col.n_a * p.a_tile_bytes);
+          for (int i = 0; i < col.n_a; ++i)
+            tma_load_5d(sA0 + as * p.a_slot_bytes + i * p.a_tile_bytes, mapA, a_full(as), ck * CHUNK, w0 + col.dx,
+                        t0 + col.dt, h0 - p.halo, seq * col.seq_mul + i);
+        }
+        __syncwarp();
+        if (++as == p.a_slots) { as = 0; aph ^= 1; }
+      }
+    }
+  } else if (warp == 2) {
+    // ===================== weight (B) TMA producer: runs ahead independently of the A ring =====================
+    int bs = 0;
+    uint32_t bph = 0;
+    for (int ic = 0; ic < p.n_cols; ++ic) {
+      const TapCol col = p.cols[ic];
+      for (int ck = 0; ck < n_chunks; ++ck) {
+        for (int d = 0; d < col.n_taps; ++d) {
+          mbar_wait(b_empty(bs), bph ^ 1);
+          if (elect_one()) {
+            const uint32_t sB = sB0 + bs * Cfg::B_BYTES_AL;
+            mbar_arrive_expect_tx(b_full(bs), Cfg::B_BYTES);
+            if constexpr (!BMN) {
+              tma_load_2d(sB, &p.mapB, b_full(bs), col.wtap[d] * p.Cin + ck * CHUNK, n0);
+            } else {
 #pragma unroll
-            for (int j = 0; j < BN / CHUNK; ++j)
-              tma_load_2d(sB + j * (CHUNK * Cfg::ROW_BYTES), &p.mapB, full_bar(stage), item.wtap * p.Cout + n0 + j * CHUNK,
-                          ck * CHUNK);
+              for (int j = 0; j < BN / CHUNK; ++j)
+                tma_load_2d(sB + j * (CHUNK * Cfg::ROW_BYTES), &p.mapB, b_full(bs), col.wtap[d] * p.Cout + n0 + j * CHUNK,
+                            ck * CHUNK);
+            }
           }
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          __syncwarp();
+          if (++bs == p.b_slots) { bs = 0; bph ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, BMN ? 1 : 0);
-      int stage = 0;
-      uint32_t phase = 0;
-      uint32_t started = 0;  // bit j: accumulator j already holds a partial sum
-      for (int it = 0; it < p.n_items; ++it) {
-        const TapItem item = p.items[it];
-        for (int ck = 0; ck < n_chunks; ++ck) {
-          mbar_wait(full_bar(stage), phase);
+    // The whole warp walks the (warp-uniform) loop; one elected lane issues.  Descriptors differ only in their
+    // 14-bit start-address field, so they are formed by adding to a base descriptor.
+    constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, BMN ? 1 : 0);
+    const uint64_t adesc0 = make_smem_desc(0, 16, SBO, SWZ);
+    const uint64_t bdesc0 = BMN ? make_smem_desc(0, CHUNK * Cfg::ROW_BYTES, SBO, SWZ) : make_smem_desc(0, 16, SBO, SWZ);
+    constexpr uint32_t B_KSTEP = BMN ? (2 * SBO) >> 4 : 32 >> 4;   // descriptor units of 16 bytes
+    int as = 0, bs = 0;
+    uint32_t aph = 0, bph = 0;
+    uint32_t started = 0;  // bit j: accumulator j already holds a partial sum
+    for (int ic = 0; ic < p.n_cols; ++ic) {
+      const TapCol col = p.cols[ic];
+      for (int ck = 0; ck < n_chunks; ++ck) {
+        mbar_wait(a_full(as), aph);
+        const uint32_t sA = sA0 + as * p.a_slot_bytes;
+        for (int d = 0; d < col.n_taps; ++d) {
+          mbar_wait(b_full(bs), bph);
           tc_fence_after();
-          const uint32_t sA = smem_base + stage * Cfg::STAGE_BYTES;
-          const uint32_t sB = sA + 2 * Cfg::A_BYTES;
-          for (int i = 0; i < item.n_a; ++i) {
-            const int acc = item.acc + i;
-            const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+          const uint64_t bdesc = bdesc0 + ((sB0 + bs * Cfg::B_BYTES_AL) >> 4);
+          if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < CHUNK / 16; ++k) {
-              const uint64_t adesc = make_smem_desc(sA + i * Cfg::A_BYTES + k * 32, 16, SBO, SWZ);
-              const uint64_t bdesc = BMN ? make_smem_desc(sB + k * 2 * SBO, CHUNK * Cfg::ROW_BYTES, SBO, SWZ)
-                                         : make_smem_desc(sB + k * 32, 16, SBO, SWZ);
-              umma_bf16_ss(d_tmem, adesc, bdesc, idesc, (k > 0) || ((started >> acc) & 1u));
+            for (int i = 0; i < 2; ++i) {
+              if (i < col.n_a) {
+                const int acc = col.acc + i;
+                const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+                const uint64_t adesc = adesc0 + ((sA + i * p.a_tile_bytes + d * dy_stride) >> 4);
+                umma_bf16_ss(d_tmem, adesc, bdesc, idesc, (started >> acc) & 1u);
+#pragma unroll
+                for (int k = 1; k < CHUNK / 16; ++k) umma_bf16_ss(d_tmem, adesc + 2 * k, bdesc + B_KSTEP * k, idesc, 1u);
+              }
             }
-            started |= 1u << acc;
+            umma_commit(b_empty(bs));  // frees the weight slot once these MMAs retire
           }
-          umma_commit(empty_bar(stage));  // frees the smem slot once these MMAs retire
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          __syncwarp();
+          started |= ((1u << col.n_a) - 1u) << col.acc;
+          if (++bs == p.b_slots) { bs = 0; bph ^= 1; }
         }
+        if (elect_one()) umma_commit(a_empty(as));  // ... and the activation slot after its last tap
+        __syncwarp();
+        if (++as == p.a_slots) { as = 0; aph ^= 1; }
       }
-      umma_commit(tmem_full_bar);  // all accumulators final
     }
+    if (elect_one()) umma_commit(tmem_full_bar);  // all accumulators final
+    __syncwarp();
   } else {
-    // ===================== epilogue (warps 2..5) =====================
+    // ===================== epilogue (warps 3..6) =====================
     constexpr int CW = Cfg::CW;
     const int q = warp & 3;  // TMEM lane quarter this warp may read
     const int m = q * 32 + lane;
-    const int tt = m / (p.bh * p.bw);
-    const int rem = m - tt * (p.bh * p.bw);
-    const int hh = rem / p.bw;
-    const int ww = rem - hh * p.bw;
+    const int hh = m / (p.bt * p.bw);        // tile rows are ordered (hh, tt, ww)
+    const int rem = m - hh * (p.bt * p.bw);
+    const int tt = rem / p.bw;
+    const int ww = rem - tt * p.bw;
     const int t = t0 + tt, h = h0 + hh, w = w0 + ww;
     const bool row_ok = (t < p.T) && (h < p.H) && (w < p.W);
 
-    mbar_wait(tmem_full_bar, 0);
+    mbar_wait_sleep(tmem_full_bar, 0);
     tc_fence_after();
 
     const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16);

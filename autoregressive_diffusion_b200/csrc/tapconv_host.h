@@ -12,7 +12,7 @@ namespace ob {
 const char* last_error();
 void set_error(const char* fmt, ...);
 
-struct TapItem;  // defined in tapconv.cuh
+struct TapCol;  // defined in tapconv.cuh
 
 int encode_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_elems,
                      const uint32_t* box);
@@ -25,8 +25,9 @@ struct TapConvLaunch {
   long a_stride_w[2] = {0, 0}, a_stride_h[2] = {0, 0}, a_stride_t[2] = {0, 0}, a_stride_seq[2] = {0, 0};
   const void* wg = nullptr;
   int w_taps = 0;
-  const void* items = nullptr;  // TapItem[n_items]
-  int n_items = 0;
+  const void* cols = nullptr;  // TapCol[n_cols]
+  int n_cols = 0;
+  int halo = 1;  // 1 for 3x3 kernels (taps dy = -1,0,+1 share one activation tile), 0 for 1x1
   int n_seq = 0, n_out = 1, T = 0, H = 0, W = 0, Cin = 0, Cout = 0;
   int epi = 0, out_f32 = 0;
   const float* alpha = nullptr;

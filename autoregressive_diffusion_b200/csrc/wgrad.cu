@@ -87,7 +87,7 @@ int wgrad_launch(const WgradLaunch& L, cudaStream_t stream) {
     set_error("wgrad: Cin (%d) and Cout (%d) must be multiples of 8", L.Cin, L.Cout);
     return OB_ERR_INVALID;
   }
-  if (L.n_items < 1 || L.n_items > TAPCONV_MAX_ITEMS || L.n_split < 1) {
+  if (L.n_items < 1 || L.n_items > WGRAD_MAX_ITEMS || L.n_split < 1) {
     set_error("wgrad: bad item count %d / split %d", L.n_items, L.n_split);
     return OB_ERR_INVALID;
   }

@@ -18,6 +18,7 @@ namespace ob {
 
 constexpr int WGRAD_KT = 64;  // pixel rows per pipeline stage
 constexpr int WGRAD_THREADS = 192;
+constexpr int WGRAD_MAX_ITEMS = 32;
 
 struct WgradItem {
   int8_t pair;  // which (G, A) tensor pair
@@ -28,7 +29,7 @@ struct WgradItem {
 struct WgradParams {
   CUtensorMap mapG[2];
   CUtensorMap mapA[2];
-  WgradItem items[TAPCONV_MAX_ITEMS];
+  WgradItem items[WGRAD_MAX_ITEMS];
   int n_items;
   int n_seq[2], T[2];  // pixel-row space of each pair (rows of G)
   int H, W;
@@ -106,17 +107,17 @@ __global__ void __launch_bounds__(WGRAD_THREADS, 1) wgrad_kernel(const __grid_co
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
   if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int kt = k_begin; kt < k_end; ++kt) {
-        int r = kt;
-        const int tw_i = r % p.tiles_w; r /= p.tiles_w;
-        const int th_i = r % p.tiles_h; r /= p.tiles_h;
-        const int tt_i = r % p.tiles_t[pr];
-        const int seq = r / p.tiles_t[pr];
-        const int w0 = tw_i * p.bw, h0 = th_i * p.bh, t0 = tt_i * p.bt;
-        mbar_wait(empty_bar(stage), phase ^ 1);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int kt = k_begin; kt < k_end; ++kt) {
+      int r = kt;
+      const int tw_i = r % p.tiles_w; r /= p.tiles_w;
+      const int th_i = r % p.tiles_h; r /= p.tiles_h;
+      const int tt_i = r % p.tiles_t[pr];
+      const int seq = r / p.tiles_t[pr];
+      const int w0 = tw_i * p.bw, h0 = th_i * p.bh, t0 = tt_i * p.bt;
+      mbar_wait(empty_bar(stage), phase ^ 1);
+      if (elect_one()) {
         const uint32_t sG = smem_base + stage * Cfg::STAGE_BYTES;
         const uint32_t sA = sG + Cfg::G_BYTES;
         mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
@@ -127,35 +128,37 @@ __global__ void __launch_bounds__(WGRAD_THREADS, 1) wgrad_kernel(const __grid_co
         for (int j = 0; j < Cfg::A_BOXES; ++j)
           tma_load_5d(sA + j * Cfg::BOX_BYTES, &p.mapA[pr], full_bar(stage), ci0 + j * CHUNK, w0 + item.dx, h0 + item.dy,
                       t0 + item.dt, seq);
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
+      __syncwarp();
+      if (++stage == STAGES) { stage = 0; phase ^= 1; }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(128, BN, 1, 1);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int kt = k_begin; kt < k_end; ++kt) {
-        mbar_wait(full_bar(stage), phase);
-        tc_fence_after();
+    constexpr uint32_t idesc = make_idesc_bf16(128, BN, 1, 1);
+    const uint64_t desc0 = make_smem_desc(0, Cfg::BOX_BYTES, SBO, SWZ);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int kt = k_begin; kt < k_end; ++kt) {
+      mbar_wait(full_bar(stage), phase);
+      tc_fence_after();
+      if (elect_one()) {
         const uint32_t sG = smem_base + stage * Cfg::STAGE_BYTES;
-        const uint32_t sA = sG + Cfg::G_BYTES;
+        const uint64_t adesc = desc0 + (sG >> 4), bdesc = desc0 + ((sG + Cfg::G_BYTES) >> 4);
+        umma_bf16_ss(tmem_base, adesc, bdesc, idesc, kt > k_begin ? 1u : 0u);
 #pragma unroll
-        for (int k = 0; k < WGRAD_KT / 16; ++k) {
-          const uint64_t adesc = make_smem_desc(sG + k * 2 * SBO, Cfg::BOX_BYTES, SBO, SWZ);
-          const uint64_t bdesc = make_smem_desc(sA + k * 2 * SBO, Cfg::BOX_BYTES, SBO, SWZ);
-          umma_bf16_ss(tmem_base, adesc, bdesc, idesc, (kt > k_begin) || (k > 0));
-        }
+        for (int k = 1; k < WGRAD_KT / 16; ++k)
+          umma_bf16_ss(tmem_base, adesc + k * ((2 * SBO) >> 4), bdesc + k * ((2 * SBO) >> 4), idesc, 1u);
         umma_commit(empty_bar(stage));
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
-      umma_commit(tmem_full_bar);
+      __syncwarp();
+      if (++stage == STAGES) { stage = 0; phase ^= 1; }
     }
+    if (elect_one()) umma_commit(tmem_full_bar);
+    __syncwarp();
   } else {
     constexpr int CW = Cfg::CW;
     const int q = warp & 3;
     const int co = co0 + q * 32 + lane;
-    mbar_wait(tmem_full_bar, 0);
+    mbar_wait_sleep(tmem_full_bar, 0);
     tc_fence_after();
     const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     float* dst_row = p.out + ((static_cast<long>(blockIdx.z) * p.Cout + co) * p.w_taps + item.wtap) * p.Cin;
