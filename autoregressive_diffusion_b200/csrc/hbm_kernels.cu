@@ -118,8 +118,9 @@ __global__ void __launch_bounds__(256) wnorm_bwd_kernel(const float* __restrict_
   const float* wr = w + static_cast<long>(co) * K;
   const long split_stride = static_cast<long>(Co) * taps_total * Ci_pad;
   const float* gsrc = dwg + (static_cast<long>(co) * taps_total + tap_off) * Ci_pad;
-  const bool vec = ((Ci_pad & 3) == 0) && ((K & 3) == 0) && ((reinterpret_cast<uintptr_t>(gsrc) & 15) == 0) &&
-                   ((split_stride & 3) == 0);
+  float* dwr = dw + static_cast<long>(co) * K;
+  const bool vec = ((Ci_pad & 3) == 0) && ((K & 3) == 0) && ((split_stride & 3) == 0) &&
+                   (((reinterpret_cast<uintptr_t>(gsrc) | reinterpret_cast<uintptr_t>(wr) | reinterpret_cast<uintptr_t>(dwr)) & 15) == 0);
   // ---- stage 1: reduce the split partials, keep the row in shared memory (tap-major, padded)
   if (vec) {
     const int n4 = taps * Ci_pad / 4;
@@ -177,7 +178,6 @@ __global__ void __launch_bounds__(256) wnorm_bwd_kernel(const float* __restrict_
   const float d = eps + rms;
   const float c = gain * rsqrtf(static_cast<float>(K)) / d;
   const float proj = (rms > 0.f) ? dot / (K * rms * d) : 0.f;
-  float* dwr = dw + static_cast<long>(co) * K;
   // ---- stage 3: dw (+)= c * (g - w * proj)
   if (vec) {
     for (int i4 = threadIdx.x; i4 < K / 4; i4 += blockDim.x) {

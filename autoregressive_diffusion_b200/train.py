@@ -38,43 +38,45 @@ def init_distributed():
 
 
 class GradientBuckets:
-    """Flat fp32 buckets over the parameters that receive gradients; all-reduce(mean) on a side stream."""
+    """Gradient mean over the data-parallel ranks (the job DistributedDataParallel does in cs_train.py:54,108-109).
+
+    After the first backward has shown which parameters receive gradients (emb_time, out_res, ... never do), their
+    .grad tensors are re-homed as views of ONE flat fp32 buffer; the all-reduce then runs in place on 256 MB slices of
+    that buffer (no flatten / unflatten copies), on a side stream, and the result is divided by the world size."""
 
     def __init__(self, params, bucket_bytes=256 << 20):
         self.params = [p for p in params if p.requires_grad]
-        self.bucket_bytes = bucket_bytes
+        self.bucket_elems = max(1, bucket_bytes // 4)
+        self.flat = None
         self.buckets = None
         self.stream = torch.cuda.Stream() if torch.cuda.is_available() else None
 
-    def _build(self):
+    def flatten(self):
         live = [p for p in self.params if p.grad is not None]
-        self.buckets, cur, size = [], [], 0
+        pad = lambda n: (n + 63) // 64 * 64          # keep every view 256-byte aligned (the kernels use 128-bit accesses)
+        total = sum(pad(p.numel()) for p in live)
+        self.flat = torch.zeros(total, dtype=torch.float32, device=live[0].device)
+        off = 0
         for p in live:
-            cur.append(p)
-            size += p.numel() * 4
-            if size >= self.bucket_bytes:
-                self.buckets.append(cur)
-                cur, size = [], 0
-        if cur:
-            self.buckets.append(cur)
+            view = self.flat[off:off + p.numel()].view_as(p)
+            view.copy_(p.grad)
+            p.grad = view
+            off += pad(p.numel())
+        self.buckets = [self.flat[i:i + self.bucket_elems] for i in range(0, total, self.bucket_elems)]
 
     def all_reduce_mean(self):
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
             return
-        if self.buckets is None:
-            self._build()
+        if self.flat is None:
+            self.flatten()
         world = dist.get_world_size()
         if self.stream is not None:
             self.stream.wait_stream(torch.cuda.current_stream())
         ctx = torch.cuda.stream(self.stream) if self.stream is not None else _Null()
         with ctx:
-            for bucket in self.buckets:
-                grads = [p.grad for p in bucket]
-                flat = torch._utils._flatten_dense_tensors(grads)
-                dist.all_reduce(flat)
-                flat.div_(world)
-                for g, f in zip(grads, torch._utils._unflatten_dense_tensors(flat, grads)):
-                    g.copy_(f)
+            for b in self.buckets:
+                dist.all_reduce(b)
+                b.div_(world)
         if self.stream is not None:
             torch.cuda.current_stream().wait_stream(self.stream)
 
@@ -113,27 +115,35 @@ class Trainer:
 
         self.graphs = None
 
-    def micro_step(self, latents, conditioning=None):
-        """One micro-batch forward+backward; every `accum`-th call also syncs gradients and steps the optimizer."""
+    def _forward_backward(self, latents, conditioning=None):
         self.micro += 1
         just_2d = bool(self.just_2d_every) and (self.micro % self.just_2d_every == 0)
         loss, unweighted = self.loss_fn(self.precond, latents, conditioning, just_2d=just_2d)
         (loss / self.accum).backward()
+        return loss.detach(), unweighted
+
+    def _optimizer_step(self):
+        self.opt.step()
+        self.opt.zero_grad(set_to_none=False)
+        with torch.no_grad():
+            for beta, shadow in zip(self.ema_betas, self.ema):
+                torch._foreach_lerp_(shadow, self.params, 1 - beta)
+
+    def micro_step(self, latents, conditioning=None):
+        """One micro-batch forward+backward; every `accum`-th call also syncs gradients and steps the optimizer."""
+        out = self._forward_backward(latents, conditioning)
         if self.micro % self.accum == 0:
             self.buckets.all_reduce_mean()
-            self.opt.step()
-            self.opt.zero_grad(set_to_none=False)
-            with torch.no_grad():
-                for beta, shadow in zip(self.ema_betas, self.ema):
-                    torch._foreach_lerp_(shadow, self.params, 1 - beta)
-        return loss.detach(), unweighted
+            self._optimizer_step()
+        return out
 
     # ------------------------------------------------------------------ CUDA-graph replay of the micro-step
     def capture(self, example_latents):
-        """Capture the three distinct micro-steps of an accumulation cycle as CUDA graphs:
-          "first" (re-normalises the weights the optimizer just changed), "mid" (operands cached), "last" (gradient
-        all-reduce + AdamW + EMA).  A cycle replays first, mid x (accum-2), last.  ~1400 kernel launches per step
-        become one graph launch, which is what removes the host from the critical path."""
+        """Capture the distinct pieces of an accumulation cycle as CUDA graphs:
+          "first" (forward+backward; re-normalises the weights the optimizer just changed), "mid" (operands cached),
+          "last" (forward+backward of the final micro-batch) and "opt" (AdamW + EMA + gradient reset).
+        A cycle replays first, mid x (accum-2), last, [NCCL gradient mean, launched eagerly between the two graphs], opt.
+        ~1400 kernel launches per step become one graph launch, which removes the host from the critical path."""
         assert self.accum >= 2 and self.micro % self.accum == 0 and not self.just_2d_every
         self.static_x = torch.empty_like(example_latents)
         self.static_x.copy_(example_latents)
@@ -144,6 +154,8 @@ class Trainer:
                 self.micro_step(self.static_x)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        if self.buckets.flat is None and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            self.buckets.flatten()             # gradient views must be in place before their addresses are captured
         self.graphs = {}
         plan = ["first"] + ["mid"] * (self.accum - 2) + ["last"]
         for kind in plan:
@@ -152,21 +164,27 @@ class Trainer:
                 continue
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                loss, _ = self.micro_step(self.static_x)
+                loss, _ = self._forward_backward(self.static_x)
             self.graphs[kind] = (g, loss)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._optimizer_step()
+        self.graphs["opt"] = (g, None)
         self._plan = plan
+        self._replayed = 0
         # the captures recorded but did not execute a cycle: gradients are still zero, weights unchanged
         return self
 
     def graphed_micro_step(self, latents=None):
         """Replay the next micro-step of the cycle on `latents` (copied into the static input buffer; any source,
         e.g. pinned host memory).  Returns the static loss tensor of that step."""
-        kind = self._plan[self._replayed % self.accum] if hasattr(self, "_replayed") else self._plan[0]
-        if not hasattr(self, "_replayed"):
-            self._replayed = 0
+        kind = self._plan[self._replayed % self.accum]
         if latents is not None:
             self.static_x.copy_(latents, non_blocking=True)
         g, loss = self.graphs[kind]
         g.replay()
+        if kind == "last":
+            self.buckets.all_reduce_mean()     # the one collective on the path, outside the graphs
+            self.graphs["opt"][0].replay()
         self._replayed += 1
         return loss

@@ -27,6 +27,12 @@ def _worker(rank, world, port, out):
     buckets.all_reduce_mean()
     ok = all(torch.allclose(p.grad, torch.full_like(p, 1.5 * (i + 1))) for i, p in enumerate(params[:-1]))
     ok = ok and params[-1].grad is None and len(buckets.buckets) >= 2
+    # gradients now live in one flat buffer: a second reduction works in place on the same views
+    for i, p in enumerate(params[:-1]):
+        p.grad.fill_(float(rank) * (i + 1))
+    buckets.all_reduce_mean()
+    ok = ok and all(torch.allclose(p.grad, torch.full_like(p, 0.5 * (i + 1))) for i, p in enumerate(params[:-1]))
+    ok = ok and all(p.grad.data_ptr() >= buckets.flat.data_ptr() for p in params[:-1])
     out.put((rank, ok))
     dist.destroy_process_group()
 
