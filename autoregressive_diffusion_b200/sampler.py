@@ -10,19 +10,54 @@ def sigma_schedule(num_steps, sigma_min, sigma_max, rho, device, dtype=torch.flo
     return torch.cat([t, torch.zeros_like(t[:1])])
 
 
+class _GraphedEval:
+    """CUDA-graph replay of the cached one-frame denoiser evaluation.
+
+    Within one generated frame the sampler calls the network 2*num_steps-1 times on identical shapes against an
+    unchanged cache; each call is ~500 tiny launches, i.e. launch-bound.  The second call is captured, the rest are
+    replays with the noisy frame and sigma copied into static buffers.  The cache tensors are baked in by address, so a
+    new graph is captured for every generated frame (the cache objects are replaced when it is updated)."""
+
+    def __init__(self, net, conditioning):
+        self.net, self.conditioning = net, conditioning
+        self.graph, self.calls = None, 0
+
+    def __call__(self, x, tt, cache):
+        self.calls += 1
+        if self.calls == 1:                      # eager warm-up (library handles, operand caches, rotary tables)
+            return self.net(x, tt, self.conditioning, cache=cache, update_cache=False, just_2d=False)[0]
+        if self.graph is None:
+            self.sx, self.st = x.clone(), tt.clone()
+            torch.cuda.synchronize()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.out = self.net(self.sx, self.st, self.conditioning, cache=cache, update_cache=False, just_2d=False)[0]
+        self.sx.copy_(x)
+        self.st.copy_(tt)
+        self.graph.replay()
+        return self.out.clone()
+
+
 @torch.no_grad()
 def edm_sampler_with_mse(net, cache, target=None, gnet=None, conditioning=None, num_steps=32, sigma_min=0.002, sigma_max=80,
                          rho=7, guidance=1, S_churn=0, S_min=0, S_max=float('inf'), S_noise=1, dtype=torch.float32,
-                         x_init=None):
+                         x_init=None, use_cuda_graph=False):
     """Generate ONE frame after the frames summarised in `cache`.  Returns (frame, mse, mse_pred, cache) like the reference;
-    `x_init` (unit-variance noise [b,1,c,h,w]) lets a caller fix the randomness."""
+    `x_init` (unit-variance noise [b,1,c,h,w]) lets a caller fix the randomness; `use_cuda_graph` replays the
+    non-updating network evaluations from a CUDA graph (guidance == 1 only)."""
     was_training = net.training
     net.eval()
     b, _, c, h, w = cache.get('shape', (None,) * 5)
     device = net.device
+    graphed = _GraphedEval(net, conditioning) if (use_cuda_graph and guidance == 1 and device.type == "cuda") else None
 
     def denoise(x, t, cache, update_cache):
         tt = torch.ones(b, 1, device=device, dtype=dtype) * t
+        if graphed is not None and not update_cache:
+            shape = cache['shape']
+            out = graphed(x, tt, cache)
+            cache['shape'] = shape
+            return out, cache
         dx, cache = net(x, tt, conditioning, cache=cache, update_cache=update_cache, just_2d=False)
         if guidance == 1:
             return dx, cache
