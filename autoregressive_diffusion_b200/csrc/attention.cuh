@@ -89,8 +89,36 @@ __device__ __forceinline__ float fast_exp2(float x) {
 constexpr int ATTN_KV_STAGES = 3;
 constexpr int ATTN_TILE_BYTES = 128 * 128;  // [128 rows][64 bf16]
 constexpr int ATTN_SMEM_BYTES = 1024 + ATTN_TILE_BYTES /*Q*/ + ATTN_KV_STAGES * 2 * ATTN_TILE_BYTES /*K,V*/ +
-                                2 * 2 * ATTN_TILE_BYTES /*P x2*/ + 256;
-constexpr int ATTN_THREADS = 192;
+                                2 * 2 * ATTN_TILE_BYTES /*P x2*/ + 1024 /*row sums*/ + 256;
+constexpr int ATTN_SOFTMAX_WARPS = 8;   // two warps per TMEM lane quarter, each owning 64 of the 128 key columns
+constexpr int ATTN_THREADS = 64 + 32 * ATTN_SOFTMAX_WARPS;
+
+// p = exp2(s*c1 - c2) for 32 logits, rounded to bf16 pairs; returns the (fp32) sum.  MASKED: keys are tested one by
+// one against the frame rule (only for tiles that straddle a mask edge).
+template <bool MASKED>
+__device__ __forceinline__ float softmax_chunk(const float (&s)[32], uint32_t (&packed)[16], float c1, float c2, int mask,
+                                               int n_frames, int qf, int ik0, int Lk, int hw) {
+  float sum = 0.f;
+  int kf = 0, rem = 0;
+  if (MASKED) { kf = ik0 / hw; rem = ik0 - kf * hw; }
+#pragma unroll
+  for (int i = 0; i < 32; i += 2) {
+    float pv[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      float e = fast_exp2(s[i + u] * c1 - c2);
+      if (MASKED) {
+        const bool ok = (ik0 + i + u < Lk) && frame_visible(mask, n_frames, qf, kf);
+        if (++rem == hw) { rem = 0; ++kf; }
+        e = ok ? e : 0.f;
+      }
+      pv[u] = e;
+    }
+    sum += pv[0] + pv[1];
+    packed[i >> 1] = pack_bf16x2(pv[0], pv[1]);
+  }
+  return sum;
+}
 
 __global__ void __launch_bounds__(ATTN_THREADS, 1) attn_fwd_kernel(const __grid_constant__ AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -98,7 +126,8 @@ __global__ void __launch_bounds__(ATTN_THREADS, 1) attn_fwd_kernel(const __grid_
   const uint32_t sQ = base;
   const uint32_t sKV = sQ + ATTN_TILE_BYTES;                       // stage s: K at +s*32K, V at +s*32K+16K
   const uint32_t sP = sKV + ATTN_KV_STAGES * 2 * ATTN_TILE_BYTES;  // buffer b: two 16 KB K-major sub-tiles
-  const uint32_t bar = sP + 2 * 2 * ATTN_TILE_BYTES;
+  const uint32_t sL = sP + 2 * 2 * ATTN_TILE_BYTES;                // [2 halves][128 rows] partial row sums
+  const uint32_t bar = sL + 1024;
   const uint32_t q_full = bar;
   auto kv_full = [&](int s) { return bar + 8u * (1 + s); };
   auto kv_empty = [&](int s) { return bar + 8u * (1 + ATTN_KV_STAGES + s); };
@@ -119,7 +148,10 @@ __global__ void __launch_bounds__(ATTN_THREADS, 1) attn_fwd_kernel(const __grid_
   if (threadIdx.x == 0) {
     mbar_init(q_full, 1);
     for (int s = 0; s < ATTN_KV_STAGES; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(s_full(b), 1); mbar_init(s_empty(b), 4); mbar_init(p_full(b), 4); mbar_init(p_empty(b), 1); }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(s_full(b), 1); mbar_init(s_empty(b), ATTN_SOFTMAX_WARPS);
+      mbar_init(p_full(b), ATTN_SOFTMAX_WARPS); mbar_init(p_empty(b), 1);
+    }
     mbar_init(o_full, 1);
     fence_barrier_init();
     tma_prefetch_desc(&p.mapQ); tma_prefetch_desc(&p.mapK); tma_prefetch_desc(&p.mapV);
@@ -133,34 +165,43 @@ __global__ void __launch_bounds__(ATTN_THREADS, 1) attn_fwd_kernel(const __grid_
   const uint32_t tS0 = tmem, tO = tmem + 256;  // S buffers at cols [0,128) and [128,256); O at [256,320)
 
   if (warp == 0) {
-    if (lane == 0) {
+    // ---- TMA producer (warp-uniform loop, elected lane issues)
+    if (elect_one()) {
       mbar_arrive_expect_tx(q_full, ATTN_TILE_BYTES);
       tma_load_4d(sQ, &p.mapQ, q_full, 0, q0, hh, bb);
-      for (int j = 0; j < n_kv; ++j) {
-        const int st = j % ATTN_KV_STAGES;
-        mbar_wait(kv_empty(st), ((j / ATTN_KV_STAGES) & 1) ^ 1);
+    }
+    __syncwarp();
+    for (int j = 0; j < n_kv; ++j) {
+      const int st = j % ATTN_KV_STAGES;
+      mbar_wait(kv_empty(st), ((j / ATTN_KV_STAGES) & 1) ^ 1);
+      if (elect_one()) {
         const uint32_t sK = sKV + st * 2 * ATTN_TILE_BYTES, sV = sK + ATTN_TILE_BYTES;
         mbar_arrive_expect_tx(kv_full(st), 2 * ATTN_TILE_BYTES);
         const int k0 = kr.tile(j) * ATTN_BN;
         tma_load_4d(sK, &p.mapK, kv_full(st), 0, k0, hh, bb);
         tma_load_4d(sV, &p.mapV, kv_full(st), 0, k0, hh, bb);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    if (lane == 0 && n_kv > 0) {
+    // ---- MMA issuer
+    if (n_kv > 0) {
       constexpr uint32_t idesc_s = make_idesc_bf16(128, ATTN_BN, 0, 0);
       constexpr uint32_t idesc_o = make_idesc_bf16(128, ATTN_D, 0, 1);
+      const uint64_t kdesc0 = make_smem_desc(0, 16, 1024, SWZ_128B);               // K-major operands (Q, K, P)
+      const uint64_t vdesc0 = make_smem_desc(0, ATTN_TILE_BYTES, 1024, SWZ_128B);  // MN-major operand (V)
       auto issue_s = [&](int j) {
         const int st = j % ATTN_KV_STAGES, b = j & 1;
         mbar_wait(kv_full(st), (j / ATTN_KV_STAGES) & 1);
         if (j >= 2) mbar_wait(s_empty(b), ((j >> 1) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t sK = sKV + st * 2 * ATTN_TILE_BYTES;
+        if (elect_one()) {
+          const uint64_t qd = kdesc0 + (sQ >> 4), kd = kdesc0 + ((sKV + st * 2 * ATTN_TILE_BYTES) >> 4);
 #pragma unroll
-        for (int k = 0; k < ATTN_D / 16; ++k)
-          umma_bf16_ss(tS0 + b * ATTN_BN, make_smem_desc(sQ + k * 32, 16, 1024, SWZ_128B),
-                       make_smem_desc(sK + k * 32, 16, 1024, SWZ_128B), idesc_s, k > 0);
-        umma_commit(s_full(b));
+          for (int k = 0; k < ATTN_D / 16; ++k) umma_bf16_ss(tS0 + b * ATTN_BN, qd + 2 * k, kd + 2 * k, idesc_s, k > 0);
+          umma_commit(s_full(b));
+        }
+        __syncwarp();
       };
       mbar_wait(q_full, 0);
       issue_s(0);
@@ -169,19 +210,26 @@ __global__ void __launch_bounds__(ATTN_THREADS, 1) attn_fwd_kernel(const __grid_
         const int st = j % ATTN_KV_STAGES, b = j & 1;
         mbar_wait(p_full(b), (j >> 1) & 1);
         tc_fence_after();
-        const uint32_t sV = sKV + st * 2 * ATTN_TILE_BYTES + ATTN_TILE_BYTES;
-        const uint32_t sPb = sP + b * 2 * ATTN_TILE_BYTES;
+        if (elect_one()) {
+          const uint64_t vd = vdesc0 + ((sKV + st * 2 * ATTN_TILE_BYTES + ATTN_TILE_BYTES) >> 4);
+          const uint64_t pd = kdesc0 + ((sP + b * 2 * ATTN_TILE_BYTES) >> 4);
 #pragma unroll
-        for (int kk = 0; kk < ATTN_BN / 16; ++kk)
-          umma_bf16_ss(tO, make_smem_desc(sPb + (kk >> 2) * ATTN_TILE_BYTES + (kk & 3) * 32, 16, 1024, SWZ_128B),
-                       make_smem_desc(sV + kk * 2048, ATTN_TILE_BYTES, 1024, SWZ_128B), idesc_o, (j > 0) || (kk > 0));
-        umma_commit(kv_empty(st));
-        umma_commit(p_empty(b));
+          for (int kk = 0; kk < ATTN_BN / 16; ++kk)
+            umma_bf16_ss(tO, pd + (kk >> 2) * (ATTN_TILE_BYTES >> 4) + (kk & 3) * 2, vd + kk * (2048 >> 4), idesc_o,
+                         (j > 0) || (kk > 0));
+          umma_commit(kv_empty(st));
+          umma_commit(p_empty(b));
+        }
+        __syncwarp();
       }
-      umma_commit(o_full);
+      if (elect_one()) umma_commit(o_full);
+      __syncwarp();
     }
   } else {
+    // ---- softmax: 8 warps; warp pair (q, q+4) shares TMEM lane quarter q, each owns 64 key columns of the tile
+    const int sw = warp - 2;
     const int qw = warp & 3;
+    const int half = sw >> 2;
     const int r = qw * 32 + lane;          // row of the tile == TMEM lane
     const int iq = q0 + r;
     const int qf = iq / p.hw;
@@ -191,10 +239,6 @@ __global__ void __launch_bounds__(ATTN_THREADS, 1) attn_fwd_kernel(const __grid_
     for (int j = 0; j < n_kv; ++j) {
       const int b = j & 1;
       const int k0 = kr.tile(j) * ATTN_BN;
-      mbar_wait(s_full(b), (j >> 1) & 1);
-      tc_fence_after();
-      if (j >= 2) mbar_wait(p_empty(b), ((j >> 1) & 1) ^ 1);
-      const uint32_t sPb = sP + b * 2 * ATTN_TILE_BYTES;
       // does this row see EVERY key of the tile?  (then the per-element frame test is skipped)
       bool all_vis;
       {
@@ -204,71 +248,65 @@ __global__ void __launch_bounds__(ATTN_THREADS, 1) attn_fwd_kernel(const __grid_
         else if (p.mask == ATTN_DART)
           all_vis = all_vis && ((qf < p.n_frames) ? (kf_b <= qf) : ((kf_b < qf - p.n_frames) || (kf_a == qf && kf_b == qf)));
       }
-#pragma unroll 1
-      for (int c = 0; c < ATTN_BN / 32; ++c) {
-        float s[32];
-        tmem_ld32(tS0 + lane_off + b * ATTN_BN + c * 32, s);
-        tmem_ld_wait();
-        uint32_t packed[16];
-        const int ik0 = k0 + c * 32;
-        int kf = ik0 / p.hw;
-        int rem = ik0 - kf * p.hw;
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float pv[2];
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            bool ok = true;
-            if (!all_vis) {
-              ok = (ik0 + i + u < p.Lk) && frame_visible(p.mask, p.n_frames, qf, kf);
-              if (++rem == p.hw) { rem = 0; ++kf; }
-            }
-            pv[u] = ok ? fast_exp2(s[i + u] * c1 - c2) : 0.f;
-          }
-          const uint32_t pk = pack_bf16x2(pv[0], pv[1]);
-          packed[i >> 1] = pk;
-          // accumulate what the tensor core will actually see
-          l += __uint_as_float(pk << 16) + __uint_as_float(pk & 0xffff0000u);
-        }
-        // columns [c*32, c*32+32) of the P tile: sub-tile c>>1, 16-byte chunks (c&1)*4 .. +3, 128B-swizzled
-        const uint32_t row_base = sPb + (c >> 1) * ATTN_TILE_BYTES + r * 128;
-#pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
-          const uint32_t chunk = static_cast<uint32_t>((c & 1) * 4 + ch) ^ static_cast<uint32_t>(r & 7);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row_base + (chunk << 4)), "r"(packed[ch * 4]),
-                       "r"(packed[ch * 4 + 1]), "r"(packed[ch * 4 + 2]), "r"(packed[ch * 4 + 3])
-                       : "memory");
-        }
-      }
+      mbar_wait(s_full(b), (j >> 1) & 1);
+      tc_fence_after();
+      if (j >= 2) mbar_wait(p_empty(b), ((j >> 1) & 1) ^ 1);
+      const uint32_t sPb = sP + b * 2 * ATTN_TILE_BYTES + half * ATTN_TILE_BYTES;   // this half's K-major sub-tile
+      float s0[32], s1[32];
+      tmem_ld32(tS0 + lane_off + b * ATTN_BN + half * 64, s0);
+      tmem_ld32(tS0 + lane_off + b * ATTN_BN + half * 64 + 32, s1);
+      tmem_ld_wait();
       tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_empty(b));          // S buffer may be overwritten by the MMA of tile j+2
+      uint32_t pk0[16], pk1[16];
+      const int ik0 = k0 + half * 64;
+      if (all_vis) {
+        l += softmax_chunk<false>(s0, pk0, c1, c2, p.mask, p.n_frames, qf, ik0, p.Lk, p.hw);
+        l += softmax_chunk<false>(s1, pk1, c1, c2, p.mask, p.n_frames, qf, ik0 + 32, p.Lk, p.hw);
+      } else {
+        l += softmax_chunk<true>(s0, pk0, c1, c2, p.mask, p.n_frames, qf, ik0, p.Lk, p.hw);
+        l += softmax_chunk<true>(s1, pk1, c1, c2, p.mask, p.n_frames, qf, ik0 + 32, p.Lk, p.hw);
+      }
+      const uint32_t row_base = sPb + r * 128;
+#pragma unroll
+      for (int ch = 0; ch < 8; ++ch) {
+        const uint32_t chunk = static_cast<uint32_t>(ch) ^ static_cast<uint32_t>(r & 7);
+        const uint32_t* src = ch < 4 ? &pk0[ch * 4] : &pk1[(ch - 4) * 4];
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row_base + (chunk << 4)), "r"(src[0]), "r"(src[1]),
+                     "r"(src[2]), "r"(src[3])
+                     : "memory");
+      }
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) { mbar_arrive(s_empty(b)); mbar_arrive(p_full(b)); }
+      if (lane == 0) mbar_arrive(p_full(b));
     }
-    // epilogue: O / l
+    // ---- combine the two halves' row sums, then O / l; each half writes 32 of the 64 output channels
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(sL + (half * 128 + r) * 4), "f"(l) : "memory");
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    float l_other;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(l_other) : "r"(sL + ((half ^ 1) * 128 + r) * 4));
+    l += l_other;
     if (n_kv > 0) {
       mbar_wait(o_full, 0);
       tc_fence_after();
     }
     const float inv_l = l > 0.f ? 1.f / l : 0.f;
-    __nv_bfloat16* orow = p.o + ((static_cast<long>(bb) * p.Lq + iq) * p.heads + hh) * ATTN_D;
+    __nv_bfloat16* orow = p.o + ((static_cast<long>(bb) * p.Lq + iq) * p.heads + hh) * ATTN_D + half * 32;
+    float o[32];
+    if (n_kv > 0) { tmem_ld32(tO + lane_off + half * 32, o); tmem_ld_wait(); }
+    else {
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      float o[32];
-      if (n_kv > 0) { tmem_ld32(tO + lane_off + c * 32, o); tmem_ld_wait(); }
-      else {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o[i] = 0.f;
-      }
-      if (iq < p.Lq) {
-#pragma unroll
-        for (int i = 0; i < 32; i += 8)
-          *reinterpret_cast<uint4*>(orow + c * 32 + i) =
-              make_uint4(pack_bf16x2(o[i] * inv_l, o[i + 1] * inv_l), pack_bf16x2(o[i + 2] * inv_l, o[i + 3] * inv_l),
-                         pack_bf16x2(o[i + 4] * inv_l, o[i + 5] * inv_l), pack_bf16x2(o[i + 6] * inv_l, o[i + 7] * inv_l));
-      }
+      for (int i = 0; i < 32; ++i) o[i] = 0.f;
     }
-    if (iq < p.Lq && p.lse != nullptr) p.lse[static_cast<long>(bh) * p.Lq + iq] = ATTN_SMAX + __logf(fmaxf(l, 1e-37f));
+    if (iq < p.Lq) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 8)
+        *reinterpret_cast<uint4*>(orow + i) =
+            make_uint4(pack_bf16x2(o[i] * inv_l, o[i + 1] * inv_l), pack_bf16x2(o[i + 2] * inv_l, o[i + 3] * inv_l),
+                       pack_bf16x2(o[i + 4] * inv_l, o[i + 5] * inv_l), pack_bf16x2(o[i + 6] * inv_l, o[i + 7] * inv_l));
+      if (half == 0 && p.lse != nullptr) p.lse[static_cast<long>(bh) * p.Lq + iq] = ATTN_SMAX + __logf(fmaxf(l, 1e-37f));
+    }
     tc_fence_before();
   }
   __syncthreads();

@@ -123,7 +123,8 @@ __global__ void __launch_bounds__(256) attn_bwd_prep_kernel(const __nv_bfloat16*
 constexpr int ABW_STAGES = 3;
 constexpr int ABW_T128 = 128 * 128;  // [128 rows][64 bf16]
 constexpr int ABW_T64 = 64 * 128;    // [64 rows][64 bf16]
-constexpr int ABW_THREADS = 192;
+constexpr int ABW_SM_WARPS = 8;      // two softmax warps per TMEM lane quarter, 32 streamed columns each
+constexpr int ABW_THREADS = 64 + 32 * ABW_SM_WARPS;
 constexpr int ABW_DQ_SMEM = 1024 + 2 * ABW_T128 + ABW_STAGES * 2 * ABW_T64 + 2 * ABW_T128 + 256;
 constexpr int ABW_DKV_SMEM = 1024 + 2 * ABW_T128 + ABW_STAGES * 2 * ABW_T64 + 4 * ABW_T128 + 2 * 2 * 64 * 4 + 256;
 
@@ -136,6 +137,61 @@ __device__ __forceinline__ void store_row_chunk(uint32_t tile_base, int r, int c
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row_base + (chunk << 4)), "r"(packed[ch * 4]),
                  "r"(packed[ch * 4 + 1]), "r"(packed[ch * 4 + 2]), "r"(packed[ch * 4 + 3])
                  : "memory");
+  }
+}
+
+// dS = P * (dP - D) * scale for 32 (query row, key) pairs of one row; P = exp2(s*c1 - lse2).
+template <bool MASKED>
+__device__ __forceinline__ void ds_chunk_row(const float (&s)[32], const float (&dp)[32], uint32_t (&packed)[16], float c1,
+                                             float lse2, float dsum, float scale, int mask, int n_frames, int qf, int ik0,
+                                             int Lk, int hw) {
+  int kf = 0, rem = 0;
+  if (MASKED) { kf = ik0 / hw; rem = ik0 - kf * hw; }
+#pragma unroll
+  for (int i = 0; i < 32; i += 2) {
+    float ds[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      float pr = fast_exp2(s[i + u] * c1 - lse2);
+      if (MASKED) {
+        const bool ok = (ik0 + i + u < Lk) && frame_visible(mask, n_frames, qf, kf);
+        if (++rem == hw) { rem = 0; ++kf; }
+        pr = ok ? pr : 0.f;
+      }
+      ds[u] = pr * (dp[i + u] - dsum) * scale;
+    }
+    packed[i >> 1] = pack_bf16x2(ds[0], ds[1]);
+  }
+}
+
+// Transposed flavour (one key row, 32 query columns with their own lse / D read from shared memory).
+template <bool MASKED>
+__device__ __forceinline__ void pds_chunk_col(const float (&s)[32], const float (&dp)[32], uint32_t (&pk_p)[16],
+                                              uint32_t (&pk_ds)[16], float c1, float scale, uint32_t stat_lse,
+                                              uint32_t stat_d, int mask, int n_frames, int kf, int iq0, int Lq, int hw) {
+  int qf = 0, rem = 0;
+  if (MASKED) { qf = iq0 / hw; rem = iq0 - qf * hw; }
+#pragma unroll
+  for (int i = 0; i < 32; i += 4) {
+    float l4[4], d4[4];
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(l4[0]), "=f"(l4[1]), "=f"(l4[2]), "=f"(l4[3]) : "r"(stat_lse + i * 4));
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(d4[0]), "=f"(d4[1]), "=f"(d4[2]), "=f"(d4[3]) : "r"(stat_d + i * 4));
+    float pv[4], ds[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float pr = fast_exp2(s[i + u] * c1 - l4[u]);
+      if (MASKED) {
+        const bool ok = (iq0 + i + u < Lq) && frame_visible(mask, n_frames, qf, kf);
+        if (++rem == hw) { rem = 0; ++qf; }
+        pr = ok ? pr : 0.f;
+      }
+      pv[u] = pr;
+      ds[u] = pr * (dp[i + u] - d4[u]) * scale;
+    }
+    pk_p[i >> 1] = pack_bf16x2(pv[0], pv[1]);
+    pk_p[(i >> 1) + 1] = pack_bf16x2(pv[2], pv[3]);
+    pk_ds[i >> 1] = pack_bf16x2(ds[0], ds[1]);
+    pk_ds[(i >> 1) + 1] = pack_bf16x2(ds[2], ds[3]);
   }
 }
 
@@ -167,7 +223,7 @@ __global__ void __launch_bounds__(ABW_THREADS, 1) attn_bwd_dq_kernel(const __gri
   if (threadIdx.x == 0) {
     mbar_init(q_full, 1);
     for (int s = 0; s < ABW_STAGES; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(sdp_full(b), 1); mbar_init(sdp_empty(b), 4); mbar_init(ds_full(b), 4); mbar_init(ds_empty(b), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(sdp_full(b), 1); mbar_init(sdp_empty(b), ABW_SM_WARPS); mbar_init(ds_full(b), ABW_SM_WARPS); mbar_init(ds_empty(b), 1); }
     mbar_init(acc_full, 1);
     fence_barrier_init();
   }
@@ -180,39 +236,45 @@ __global__ void __launch_bounds__(ABW_THREADS, 1) attn_bwd_dq_kernel(const __gri
   // S buffers: cols [0,64) [64,128); dP buffers: [128,192) [192,256); dQ: [256,320)
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_arrive_expect_tx(q_full, 2 * ABW_T128);
       tma_load_4d(sQ, &p.mapQ128, q_full, 0, q0, hh, bb);
       tma_load_4d(sdO, &p.mapdO128, q_full, 0, q0, hh, bb);
-      for (int j = 0; j < n_kv; ++j) {
-        const int st = j % ABW_STAGES;
-        mbar_wait(kv_empty(st), ((j / ABW_STAGES) & 1) ^ 1);
+    }
+    __syncwarp();
+    for (int j = 0; j < n_kv; ++j) {
+      const int st = j % ABW_STAGES;
+      mbar_wait(kv_empty(st), ((j / ABW_STAGES) & 1) ^ 1);
+      if (elect_one()) {
         const uint32_t sK = sKV + st * 2 * ABW_T64, sV = sK + ABW_T64;
         mbar_arrive_expect_tx(kv_full(st), 2 * ABW_T64);
         const int k0 = kr.tile(j) * ABW_BN;
         tma_load_4d(sK, &p.mapK64, kv_full(st), 0, k0, hh, bb);
         tma_load_4d(sV, &p.mapV64, kv_full(st), 0, k0, hh, bb);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    if (lane == 0 && n_kv > 0) {
+    if (n_kv > 0) {
       constexpr uint32_t idesc_s = make_idesc_bf16(128, ABW_BN, 0, 0);
       constexpr uint32_t idesc_q = make_idesc_bf16(128, ATTN_D, 0, 1);
+      const uint64_t kdesc0 = make_smem_desc(0, 16, 1024, SWZ_128B);
+      const uint64_t mdesc0 = make_smem_desc(0, ABW_T64, 1024, SWZ_128B);
       auto issue_sdp = [&](int j) {
         const int st = j % ABW_STAGES, b = j & 1;
         mbar_wait(kv_full(st), (j / ABW_STAGES) & 1);
         if (j >= 2) mbar_wait(sdp_empty(b), ((j >> 1) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t sK = sKV + st * 2 * ABW_T64, sV = sK + ABW_T64;
+        if (elect_one()) {
+          const uint32_t sK = sKV + st * 2 * ABW_T64, sV = sK + ABW_T64;
+          const uint64_t qd = kdesc0 + (sQ >> 4), dod = kdesc0 + (sdO >> 4), kd = kdesc0 + (sK >> 4), vd = kdesc0 + (sV >> 4);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16_ss(tmem + b * 64, make_smem_desc(sQ + k * 32, 16, 1024, SWZ_128B),
-                       make_smem_desc(sK + k * 32, 16, 1024, SWZ_128B), idesc_s, k > 0);
+          for (int k = 0; k < 4; ++k) umma_bf16_ss(tmem + b * 64, qd + 2 * k, kd + 2 * k, idesc_s, k > 0);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16_ss(tmem + 128 + b * 64, make_smem_desc(sdO + k * 32, 16, 1024, SWZ_128B),
-                       make_smem_desc(sV + k * 32, 16, 1024, SWZ_128B), idesc_s, k > 0);
-        umma_commit(sdp_full(b));
+          for (int k = 0; k < 4; ++k) umma_bf16_ss(tmem + 128 + b * 64, dod + 2 * k, vd + 2 * k, idesc_s, k > 0);
+          umma_commit(sdp_full(b));
+        }
+        __syncwarp();
       };
       mbar_wait(q_full, 0);
       issue_sdp(0);
@@ -221,18 +283,23 @@ __global__ void __launch_bounds__(ABW_THREADS, 1) attn_bwd_dq_kernel(const __gri
         const int st = j % ABW_STAGES, b = j & 1;
         mbar_wait(ds_full(b), (j >> 1) & 1);
         tc_fence_after();
-        const uint32_t sK = sKV + st * 2 * ABW_T64;
+        if (elect_one()) {
+          const uint64_t dsd = kdesc0 + ((sdS + b * ABW_T128) >> 4);
+          const uint64_t kd = mdesc0 + ((sKV + st * 2 * ABW_T64) >> 4);
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk)   // dQ += dS[128 x 64 keys] * K[64 keys x 64]
-          umma_bf16_ss(tmem + 256, make_smem_desc(sdS + b * ABW_T128 + kk * 32, 16, 1024, SWZ_128B),
-                       make_smem_desc(sK + kk * 2048, ABW_T64, 1024, SWZ_128B), idesc_q, (j > 0) || (kk > 0));
-        umma_commit(kv_empty(st));
-        umma_commit(ds_empty(b));
+          for (int kk = 0; kk < 4; ++kk)   // dQ += dS[128 x 64 keys] * K[64 keys x 64]
+            umma_bf16_ss(tmem + 256, dsd + 2 * kk, kd + kk * (2048 >> 4), idesc_q, (j > 0) || (kk > 0));
+          umma_commit(kv_empty(st));
+          umma_commit(ds_empty(b));
+        }
+        __syncwarp();
       }
-      umma_commit(acc_full);
+      if (elect_one()) umma_commit(acc_full);
+      __syncwarp();
     }
   } else {
     const int qw = warp & 3;
+    const int half = (warp - 2) >> 2;      // which 32 of the 64 streamed key columns this warp owns
     const int r = qw * 32 + lane;
     const int iq = q0 + r;
     const int qf = iq / p.hw;
@@ -250,41 +317,38 @@ __global__ void __launch_bounds__(ABW_THREADS, 1) attn_bwd_dq_kernel(const __gri
       mbar_wait(sdp_full(b), (j >> 1) & 1);
       tc_fence_after();
       if (j >= 2) mbar_wait(ds_empty(b), ((j >> 1) & 1) ^ 1);
-#pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
-        float s[32], dp[32];
-        tmem_ld32(tmem + lane_off + b * 64 + c * 32, s);
-        tmem_ld32(tmem + lane_off + 128 + b * 64 + c * 32, dp);
-        tmem_ld_wait();
-        uint32_t packed[16];
-        const int ik0 = k0 + c * 32;
-        int kf = ik0 / p.hw;
-        int rem = ik0 - kf * p.hw;
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float ds[2];
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const bool ok = (iq < p.Lq) && (ik0 + i + u < p.Lk) && frame_visible(p.mask, p.n_frames, qf, kf);
-            if (++rem == p.hw) { rem = 0; ++kf; }
-            const float pr = ok ? fast_exp2(s[i + u] * c1 - lse2) : 0.f;
-            ds[u] = pr * (dp[i + u] - dsum) * p.scale;
-          }
-          packed[i >> 1] = pack_bf16x2(ds[0], ds[1]);
-        }
-        store_row_chunk(sdS + b * ABW_T128, r, c, packed);
-      }
+      float s[32], dp[32];
+      tmem_ld32(tmem + lane_off + b * 64 + half * 32, s);
+      tmem_ld32(tmem + lane_off + 128 + b * 64 + half * 32, dp);
+      tmem_ld_wait();
       tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sdp_empty(b));
+      uint32_t packed[16];
+      const int ik0 = k0 + half * 32;
+      bool all_vis = (iq < p.Lq) && (ik0 + 32 <= p.Lk);
+      {
+        const int kf_a = ik0 / p.hw, kf_b = (ik0 + 31) / p.hw;
+        if (p.mask == ATTN_CAUSAL) all_vis = all_vis && (kf_b <= qf);
+        else if (p.mask == ATTN_DART)
+          all_vis = all_vis && ((qf < p.n_frames) ? (kf_b <= qf) : ((kf_b < qf - p.n_frames) || (kf_a == qf && kf_b == qf)));
+      }
+      if (all_vis) ds_chunk_row<false>(s, dp, packed, c1, lse2, dsum, p.scale, p.mask, p.n_frames, qf, ik0, p.Lk, p.hw);
+      else if (iq < p.Lq) ds_chunk_row<true>(s, dp, packed, c1, lse2, dsum, p.scale, p.mask, p.n_frames, qf, ik0, p.Lk, p.hw);
+      else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) packed[i] = 0u;
+      }
+      store_row_chunk(sdS + b * ABW_T128, r, half, packed);
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) { mbar_arrive(sdp_empty(b)); mbar_arrive(ds_full(b)); }
+      if (lane == 0) mbar_arrive(ds_full(b));
     }
     if (n_kv > 0) { mbar_wait(acc_full, 0); tc_fence_after(); }
-    __nv_bfloat16* drow = p.dq + ((static_cast<long>(bb) * p.Lq + iq) * p.heads + hh) * ATTN_D;
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
+    __nv_bfloat16* drow = p.dq + ((static_cast<long>(bb) * p.Lq + iq) * p.heads + hh) * ATTN_D + half * 32;
+    {
       float o[32];
-      if (n_kv > 0) { tmem_ld32(tmem + lane_off + 256 + c * 32, o); tmem_ld_wait(); }
+      if (n_kv > 0) { tmem_ld32(tmem + lane_off + 256 + half * 32, o); tmem_ld_wait(); }
       else {
 #pragma unroll
         for (int i = 0; i < 32; ++i) o[i] = 0.f;
@@ -292,8 +356,8 @@ __global__ void __launch_bounds__(ABW_THREADS, 1) attn_bwd_dq_kernel(const __gri
       if (iq < p.Lq) {
 #pragma unroll
         for (int i = 0; i < 32; i += 8)
-          *reinterpret_cast<uint4*>(drow + c * 32 + i) = make_uint4(pack_bf16x2(o[i], o[i + 1]), pack_bf16x2(o[i + 2], o[i + 3]),
-                                                                    pack_bf16x2(o[i + 4], o[i + 5]), pack_bf16x2(o[i + 6], o[i + 7]));
+          *reinterpret_cast<uint4*>(drow + i) = make_uint4(pack_bf16x2(o[i], o[i + 1]), pack_bf16x2(o[i + 2], o[i + 3]),
+                                                           pack_bf16x2(o[i + 4], o[i + 5]), pack_bf16x2(o[i + 6], o[i + 7]));
       }
     }
     tc_fence_before();
@@ -331,7 +395,7 @@ __global__ void __launch_bounds__(ABW_THREADS, 1) attn_bwd_dkv_kernel(const __gr
   if (threadIdx.x == 0) {
     mbar_init(kv_full, 1);
     for (int s = 0; s < ABW_STAGES; ++s) { mbar_init(q_full(s), 1); mbar_init(q_empty(s), 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(sdp_full(b), 1); mbar_init(sdp_empty(b), 4); mbar_init(pds_full(b), 4); mbar_init(pds_empty(b), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(sdp_full(b), 1); mbar_init(sdp_empty(b), ABW_SM_WARPS); mbar_init(pds_full(b), ABW_SM_WARPS); mbar_init(pds_empty(b), 1); }
     mbar_init(acc_full, 1);
     fence_barrier_init();
   }
@@ -344,39 +408,45 @@ __global__ void __launch_bounds__(ABW_THREADS, 1) attn_bwd_dkv_kernel(const __gr
   // S^T buffers: cols [0,64) [64,128); dP^T: [128,192) [192,256); dK: [256,320); dV: [320,384)
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_arrive_expect_tx(kv_full, 2 * ABW_T128);
       tma_load_4d(sK, &p.mapK128, kv_full, 0, k0, hh, bb);
       tma_load_4d(sV, &p.mapV128, kv_full, 0, k0, hh, bb);
-      for (int j = 0; j < n_q; ++j) {
-        const int st = j % ABW_STAGES;
-        mbar_wait(q_empty(st), ((j / ABW_STAGES) & 1) ^ 1);
+    }
+    __syncwarp();
+    for (int j = 0; j < n_q; ++j) {
+      const int st = j % ABW_STAGES;
+      mbar_wait(q_empty(st), ((j / ABW_STAGES) & 1) ^ 1);
+      if (elect_one()) {
         const uint32_t sQ = sQdO + st * 2 * ABW_T64, sdO = sQ + ABW_T64;
         mbar_arrive_expect_tx(q_full(st), 2 * ABW_T64);
         const int q0 = qr.tile(j) * ABW_BN;
         tma_load_4d(sQ, &p.mapQ64, q_full(st), 0, q0, hh, bb);
         tma_load_4d(sdO, &p.mapdO64, q_full(st), 0, q0, hh, bb);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    if (lane == 0 && n_q > 0) {
+    if (n_q > 0) {
       constexpr uint32_t idesc_s = make_idesc_bf16(128, ABW_BN, 0, 0);
       constexpr uint32_t idesc_a = make_idesc_bf16(128, ATTN_D, 0, 1);
+      const uint64_t kdesc0 = make_smem_desc(0, 16, 1024, SWZ_128B);
+      const uint64_t mdesc0 = make_smem_desc(0, ABW_T64, 1024, SWZ_128B);
       auto issue_sdp = [&](int j) {
         const int st = j % ABW_STAGES, b = j & 1;
         mbar_wait(q_full(st), (j / ABW_STAGES) & 1);
         if (j >= 2) mbar_wait(sdp_empty(b), ((j >> 1) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t sQ = sQdO + st * 2 * ABW_T64, sdO = sQ + ABW_T64;
+        if (elect_one()) {
+          const uint32_t sQ = sQdO + st * 2 * ABW_T64, sdO = sQ + ABW_T64;
+          const uint64_t kd = kdesc0 + (sK >> 4), vd = kdesc0 + (sV >> 4), qd = kdesc0 + (sQ >> 4), dod = kdesc0 + (sdO >> 4);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)   // S^T = K Q^T
-          umma_bf16_ss(tmem + b * 64, make_smem_desc(sK + k * 32, 16, 1024, SWZ_128B),
-                       make_smem_desc(sQ + k * 32, 16, 1024, SWZ_128B), idesc_s, k > 0);
+          for (int k = 0; k < 4; ++k) umma_bf16_ss(tmem + b * 64, kd + 2 * k, qd + 2 * k, idesc_s, k > 0);          // S^T = K Q^T
 #pragma unroll
-        for (int k = 0; k < 4; ++k)   // dP^T = V dO^T
-          umma_bf16_ss(tmem + 128 + b * 64, make_smem_desc(sV + k * 32, 16, 1024, SWZ_128B),
-                       make_smem_desc(sdO + k * 32, 16, 1024, SWZ_128B), idesc_s, k > 0);
-        umma_commit(sdp_full(b));
+          for (int k = 0; k < 4; ++k) umma_bf16_ss(tmem + 128 + b * 64, vd + 2 * k, dod + 2 * k, idesc_s, k > 0);   // dP^T = V dO^T
+          umma_commit(sdp_full(b));
+        }
+        __syncwarp();
       };
       mbar_wait(kv_full, 0);
       issue_sdp(0);
@@ -385,24 +455,29 @@ __global__ void __launch_bounds__(ABW_THREADS, 1) attn_bwd_dkv_kernel(const __gr
         const int st = j % ABW_STAGES, b = j & 1;
         mbar_wait(pds_full(b), (j >> 1) & 1);
         tc_fence_after();
-        const uint32_t sQ = sQdO + st * 2 * ABW_T64, sdO = sQ + ABW_T64;
+        if (elect_one()) {
+          const uint32_t sQ = sQdO + st * 2 * ABW_T64, sdO = sQ + ABW_T64;
+          const uint64_t pd = kdesc0 + ((sP + b * ABW_T128) >> 4), dsd = kdesc0 + ((sP + (2 + b) * ABW_T128) >> 4);
+          const uint64_t dod = mdesc0 + (sdO >> 4), qd = mdesc0 + (sQ >> 4);
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk)   // dV += P^T[128 keys x 64 q] * dO[64 q x 64]
-          umma_bf16_ss(tmem + 320, make_smem_desc(sP + b * ABW_T128 + kk * 32, 16, 1024, SWZ_128B),
-                       make_smem_desc(sdO + kk * 2048, ABW_T64, 1024, SWZ_128B), idesc_a, (j > 0) || (kk > 0));
+          for (int kk = 0; kk < 4; ++kk)   // dV += P^T[128 keys x 64 q] * dO[64 q x 64]
+            umma_bf16_ss(tmem + 320, pd + 2 * kk, dod + kk * (2048 >> 4), idesc_a, (j > 0) || (kk > 0));
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk)   // dK += dS^T * Q
-          umma_bf16_ss(tmem + 256, make_smem_desc(sP + (2 + b) * ABW_T128 + kk * 32, 16, 1024, SWZ_128B),
-                       make_smem_desc(sQ + kk * 2048, ABW_T64, 1024, SWZ_128B), idesc_a, (j > 0) || (kk > 0));
-        umma_commit(q_empty(st));
-        umma_commit(pds_empty(b));
+          for (int kk = 0; kk < 4; ++kk)   // dK += dS^T * Q
+            umma_bf16_ss(tmem + 256, dsd + 2 * kk, qd + kk * (2048 >> 4), idesc_a, (j > 0) || (kk > 0));
+          umma_commit(q_empty(st));
+          umma_commit(pds_empty(b));
+        }
+        __syncwarp();
       }
-      umma_commit(acc_full);
+      if (elect_one()) umma_commit(acc_full);
+      __syncwarp();
     }
   } else {
     const int qw = warp & 3;
+    const int half = (warp - 2) >> 2;     // which 32 of the 64 streamed query columns this warp owns
     const int r = qw * 32 + lane;         // key row of the tile
-    const int tid = threadIdx.x - 64;     // 0..127 among the softmax threads
+    const int tid = threadIdx.x - 64;     // 0..255 among the softmax threads
     const int ik = k0 + r;
     const int kf = ik / p.hw;
     const uint32_t lane_off = static_cast<uint32_t>(qw * 32) << 16;
@@ -412,68 +487,64 @@ __global__ void __launch_bounds__(ABW_THREADS, 1) attn_bwd_dkv_kernel(const __gr
       const int b = j & 1;
       const int q0 = qr.tile(j) * ABW_BN;
       {  // stage this step's 64 (lse, D) pairs; the named barrier also orders reuse of the buffer (see header note)
-        const int i = tid & 63;
-        const long gi = static_cast<long>(bh) * p.Lq + q0 + i;
-        float v = 0.f;
-        if (q0 + i < p.Lq) v = (tid < 64) ? p.lse[gi] * LOG2E : p.dsum[gi];
-        asm volatile("st.shared.f32 [%0], %1;" ::"r"(sStat + (b * 128 + tid) * 4), "f"(v) : "memory");
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (tid < 128) {
+          const int i = tid & 63;
+          const long gi = static_cast<long>(bh) * p.Lq + q0 + i;
+          float v = 0.f;
+          if (q0 + i < p.Lq) v = (tid < 64) ? p.lse[gi] * LOG2E : p.dsum[gi];
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(sStat + (b * 128 + tid) * 4), "f"(v) : "memory");
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
       }
       mbar_wait(sdp_full(b), (j >> 1) & 1);
       tc_fence_after();
       if (j >= 2) mbar_wait(pds_empty(b), ((j >> 1) & 1) ^ 1);
-#pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
-        float s[32], dp[32];
-        tmem_ld32(tmem + lane_off + b * 64 + c * 32, s);
-        tmem_ld32(tmem + lane_off + 128 + b * 64 + c * 32, dp);
-        tmem_ld_wait();
-        uint32_t pk_p[16], pk_ds[16];
-        const int iq0 = q0 + c * 32;
-        int qf = iq0 / p.hw;
-        int rem = iq0 - qf * p.hw;
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float pv[2], ds[2];
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const bool ok = (ik < p.Lk) && (iq0 + i + u < p.Lq) && frame_visible(p.mask, p.n_frames, qf, kf);
-            if (++rem == p.hw) { rem = 0; ++qf; }
-            float lse2, dsum;
-            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(lse2) : "r"(sStat + (b * 128 + c * 32 + i + u) * 4));
-            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(dsum) : "r"(sStat + (b * 128 + 64 + c * 32 + i + u) * 4));
-            pv[u] = ok ? fast_exp2(s[i + u] * c1 - lse2) : 0.f;
-            ds[u] = pv[u] * (dp[i + u] - dsum) * p.scale;
-          }
-          pk_p[i >> 1] = pack_bf16x2(pv[0], pv[1]);
-          pk_ds[i >> 1] = pack_bf16x2(ds[0], ds[1]);
-        }
-        store_row_chunk(sP + b * ABW_T128, r, c, pk_p);
-        store_row_chunk(sP + (2 + b) * ABW_T128, r, c, pk_ds);
-      }
+      float s[32], dp[32];
+      tmem_ld32(tmem + lane_off + b * 64 + half * 32, s);
+      tmem_ld32(tmem + lane_off + 128 + b * 64 + half * 32, dp);
+      tmem_ld_wait();
       tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sdp_empty(b));
+      uint32_t pk_p[16], pk_ds[16];
+      const int iq0 = q0 + half * 32;
+      bool all_vis = (ik < p.Lk) && (iq0 + 32 <= p.Lq);
+      {
+        const int qf_a = iq0 / p.hw, qf_b = (iq0 + 31) / p.hw, n = p.n_frames;
+        if (p.mask == ATTN_CAUSAL) all_vis = all_vis && (kf <= qf_a);
+        else if (p.mask == ATTN_DART) {
+          if (kf < n) all_vis = all_vis && ((qf_b < n && kf <= qf_a) || (qf_a >= n && kf < qf_a - n));
+          else all_vis = all_vis && (qf_a == kf && qf_b == kf);
+        }
+      }
+      const uint32_t st_l = sStat + (b * 128 + half * 32) * 4, st_d = sStat + (b * 128 + 64 + half * 32) * 4;
+      if (all_vis) pds_chunk_col<false>(s, dp, pk_p, pk_ds, c1, p.scale, st_l, st_d, p.mask, p.n_frames, kf, iq0, p.Lq, p.hw);
+      else if (ik < p.Lk) pds_chunk_col<true>(s, dp, pk_p, pk_ds, c1, p.scale, st_l, st_d, p.mask, p.n_frames, kf, iq0, p.Lq, p.hw);
+      else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { pk_p[i] = 0u; pk_ds[i] = 0u; }
+      }
+      store_row_chunk(sP + b * ABW_T128, r, half, pk_p);
+      store_row_chunk(sP + (2 + b) * ABW_T128, r, half, pk_ds);
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) { mbar_arrive(sdp_empty(b)); mbar_arrive(pds_full(b)); }
+      if (lane == 0) mbar_arrive(pds_full(b));
     }
     if (n_q > 0) { mbar_wait(acc_full, 0); tc_fence_after(); }
 #pragma unroll
     for (int which = 0; which < 2; ++which) {
-      __nv_bfloat16* drow = (which == 0 ? p.dk : p.dv) + ((static_cast<long>(bb) * p.Lk + ik) * p.heads + hh) * ATTN_D;
+      __nv_bfloat16* drow = (which == 0 ? p.dk : p.dv) + ((static_cast<long>(bb) * p.Lk + ik) * p.heads + hh) * ATTN_D + half * 32;
+      float o[32];
+      if (n_q > 0) { tmem_ld32(tmem + lane_off + 256 + which * 64 + half * 32, o); tmem_ld_wait(); }
+      else {
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        float o[32];
-        if (n_q > 0) { tmem_ld32(tmem + lane_off + 256 + which * 64 + c * 32, o); tmem_ld_wait(); }
-        else {
+        for (int i = 0; i < 32; ++i) o[i] = 0.f;
+      }
+      if (ik < p.Lk) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) o[i] = 0.f;
-        }
-        if (ik < p.Lk) {
-#pragma unroll
-          for (int i = 0; i < 32; i += 8)
-            *reinterpret_cast<uint4*>(drow + c * 32 + i) = make_uint4(pack_bf16x2(o[i], o[i + 1]), pack_bf16x2(o[i + 2], o[i + 3]),
-                                                                      pack_bf16x2(o[i + 4], o[i + 5]), pack_bf16x2(o[i + 6], o[i + 7]));
-        }
+        for (int i = 0; i < 32; i += 8)
+          *reinterpret_cast<uint4*>(drow + i) = make_uint4(pack_bf16x2(o[i], o[i + 1]), pack_bf16x2(o[i + 2], o[i + 3]),
+                                                           pack_bf16x2(o[i + 4], o[i + 5]), pack_bf16x2(o[i + 6], o[i + 7]));
       }
     }
     tc_fence_before();
