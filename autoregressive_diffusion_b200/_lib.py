@@ -32,8 +32,9 @@ _SIGS = {
     # name: argtypes
     "ob_wnorm_fwd": "ppiiiiiiffip",
     "ob_wnorm_bwd": "pppiiiiiiiffip",
-    "ob_conv_fwd": "pppppppiiiiiiiiiip",
-    "ob_conv_dgrad": "ppppppiiiiiiiiip",
+    "ob_conv_fwd": "ppppppppiiiiiiiiiip",
+    "ob_conv_dgrad": "pppppppiiiiiiiiip",
+    "ob_conv_split_ws_bytes": "iiiiiiiii",
     "ob_conv_wgrad_splits": "iiiiiiiii",
     "ob_conv_wgrad": "pppppiiiiiiiiiip",
     "ob_gate_bwd": "pppppppppiiilp",
@@ -71,7 +72,7 @@ def lib():
         for name, sig in _SIGS.items():
             fn = getattr(L, name)
             fn.argtypes = [_CT[c] for c in sig]
-            fn.restype = ctypes.c_int
+            fn.restype = ctypes.c_int64 if name.endswith("_bytes") else ctypes.c_int
         _lib = L
     return _lib
 

@@ -65,9 +65,16 @@ int ob_wnorm_bwd(const float* w, const float* dwg, float* dw, int cout, int cin,
                    (cudaStream_t)stream);
 }
 
+int64_t ob_conv_split_ws_bytes(int n_seq, int S, int T, int H, int W, int cin, int cout, int ksize, int gated) {
+  int ks; long wsb;
+  if (gated) tapconv_plan(n_seq, S, 1, T, H, W, cin, cout, &ks, &wsb);
+  else tapconv_plan(1, 1, 0, n_seq * S * T, H, W, cin, cout, &ks, &wsb);
+  return (int64_t)wsb;
+}
+
 int ob_conv_fwd(const void* x, const void* ctx, const void* wg, const float* alpha, const float* beta, void* out,
-                void* out_d, int n_seq, int S, int T, int H, int W, int cin, int cout, int ksize, int gated, int out_f32,
-                void* stream) {
+                void* out_d, void* split_ws, int n_seq, int S, int T, int H, int W, int cin, int cout, int ksize, int gated,
+                int out_f32, void* stream) {
   if (int r = check_shape("ob_conv_fwd", n_seq, S, T, H, W, ksize, gated)) return r;
   TapConvLaunch L;
   std::vector<TapCol> cols;
@@ -88,12 +95,13 @@ int ob_conv_fwd(const void* x, const void* ctx, const void* wg, const float* alp
     L.alpha = alpha; L.beta = beta; L.out_d = out_d;
   }
   L.wg = wg; L.cols = cols.data(); L.n_cols = (int)cols.size();
-  L.H = H; L.W = W; L.Cin = cin; L.Cout = cout; L.out_f32 = out_f32; L.out = out;
+  L.H = H; L.W = W; L.Cin = cin; L.Cout = cout; L.out_f32 = out_f32; L.out = out; L.split_ws = (float*)split_ws;
   return tapconv_launch(L, (cudaStream_t)stream);
 }
 
 int ob_conv_dgrad(const void* gy, const void* gb, const void* wg, const float* alpha, const float* beta, void* dx,
-                  int n_seq, int S, int T, int H, int W, int cin, int cout, int ksize, int gated, void* stream) {
+                  void* split_ws, int n_seq, int S, int T, int H, int W, int cin, int cout, int ksize, int gated,
+                  void* stream) {
   if (int r = check_shape("ob_conv_dgrad", n_seq, S, T, H, W, ksize, gated)) return r;
   // transposed problem: GEMM K = cout (channels of the incoming gradient), GEMM N = cin; taps are mirrored
   TapConvLaunch L;
@@ -117,7 +125,7 @@ int ob_conv_dgrad(const void* gy, const void* gb, const void* wg, const float* a
   }
   L.b_mn_major = 1;
   L.wg = wg; L.cols = cols.data(); L.n_cols = (int)cols.size();
-  L.H = H; L.W = W; L.Cin = cout; L.Cout = cin; L.out_f32 = 0; L.out = dx;
+  L.H = H; L.W = W; L.Cin = cout; L.Cout = cin; L.out_f32 = 0; L.out = dx; L.split_ws = (float*)split_ws;
   return tapconv_launch(L, (cudaStream_t)stream);
 }
 

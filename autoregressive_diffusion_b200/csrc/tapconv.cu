@@ -86,7 +86,7 @@ static int pow2_ceil(int v) {
 }
 
 template <int CHUNK, int BN, bool BMN>
-static int launch_inst(const TapConvParams& p, int grid, cudaStream_t stream) {
+static int launch_inst(const TapConvParams& p, dim3 grid, cudaStream_t stream) {
   using Cfg = TapConvCfg<CHUNK, BN>;
   if constexpr (BMN && (BN % CHUNK != 0)) {
     set_error("tapconv: MN-major weights need tile N %d to be a multiple of %d", BN, CHUNK);
@@ -114,7 +114,7 @@ static int launch_inst(const TapConvParams& p, int grid, cudaStream_t stream) {
 }
 
 template <int CHUNK, bool BMN>
-static int launch_bn(int bn, const TapConvParams& p, int grid, cudaStream_t s) {
+static int launch_bn(int bn, const TapConvParams& p, dim3 grid, cudaStream_t s) {
   switch (bn) {
     case 16: return launch_inst<CHUNK, 16, BMN>(p, grid, s);
     case 32: return launch_inst<CHUNK, 32, BMN>(p, grid, s);
@@ -124,6 +124,47 @@ static int launch_bn(int bn, const TapConvParams& p, int grid, cudaStream_t s) {
   }
   set_error("unsupported tile N %d", bn);
   return OB_ERR_UNSUPPORTED;
+}
+
+static void tile_shape(int H, int W, int* bw, int* bh, int* bt) {
+  *bw = pow2_ceil(W) > 128 ? 128 : pow2_ceil(W);
+  *bh = pow2_ceil(H);
+  if (*bh > 128 / *bw) *bh = 128 / *bw;
+  if (*bh > 16) *bh = 16;
+  *bt = 128 / (*bw * *bh);
+}
+
+static int pick_bn(int n_acc, int Cout, int m_tiles, int force_bn, int chunk, int b_mn_major) {
+  int bn_max = (n_acc == 3) ? 128 : 256;
+  int bn = pow2_ceil(Cout) < 16 ? 16 : pow2_ceil(Cout);
+  if (bn > bn_max) bn = bn_max;
+  if (force_bn > 0) bn = force_bn;
+  else
+    while (bn > 64 && m_tiles * ((Cout + bn - 1) / bn) < 148) bn >>= 1;  // below 64 the A re-reads cost more than idle SMs
+  if (b_mn_major && bn < chunk) bn = chunk;
+  return bn;
+}
+
+// Small-spatial layers (the 4x4 / 8x8 levels) have too few output tiles to occupy 148 SMs while their K loop is
+// hundreds of steps long: slice the channel chunks over blockIdx.y and reduce in an fp32 workspace.
+void tapconv_plan(int n_seq, int n_out, int gated, int T, int H, int W, int Cin, int Cout, int* ksplit, long* ws_bytes) {
+  int bw, bh, bt;
+  tile_shape(H, W, &bw, &bh, &bt);
+  const int m_tiles = n_seq * ((T + bt - 1) / bt) * ((H + bh - 1) / bh) * ((W + bw - 1) / bw);
+  const int n_acc = n_out + (gated ? 1 : 0);
+  const int chunk = (Cin % 64 == 0) ? 64 : (Cin % 32 == 0) ? 32 : 16;
+  const int bn = pick_bn(n_acc, Cout, m_tiles, 0, chunk, 0);
+  const int tiles = m_tiles * ((Cout + bn - 1) / bn);
+  const int n_chunks = (Cin + chunk - 1) / chunk;
+  int ks = 1;
+  if (tiles <= 74 && n_chunks >= 4 && Cout % 4 == 0) {
+    ks = 148 / tiles;
+    if (ks > n_chunks / 2) ks = n_chunks / 2;   // at least two chunks per slice
+    if (ks > 8) ks = 8;
+    if (ks < 1) ks = 1;
+  }
+  *ksplit = ks;
+  *ws_bytes = ks > 1 ? static_cast<long>(n_acc) * n_seq * T * H * W * Cout * 4 : 0;
 }
 
 int tapconv_launch(const TapConvLaunch& L, cudaStream_t stream) {
@@ -146,11 +187,7 @@ int tapconv_launch(const TapConvLaunch& L, cudaStream_t stream) {
   TapConvParams p;
   memset(&p, 0, sizeof(p));
   // ---- pixel tile: 128 rows ordered (hh, tt, ww); bt*bw >= 8 keeps a vertical shift a whole number of swizzle atoms
-  p.bw = pow2_ceil(L.W) > 128 ? 128 : pow2_ceil(L.W);
-  p.bh = pow2_ceil(L.H);
-  if (p.bh > 128 / p.bw) p.bh = 128 / p.bw;
-  if (p.bh > 16) p.bh = 16;
-  p.bt = 128 / (p.bw * p.bh);
+  tile_shape(L.H, L.W, &p.bw, &p.bh, &p.bt);
   p.halo = L.halo ? 1 : 0;
   p.tiles_w = (L.W + p.bw - 1) / p.bw;
   p.tiles_h = (L.H + p.bh - 1) / p.bh;
@@ -158,13 +195,7 @@ int tapconv_launch(const TapConvLaunch& L, cudaStream_t stream) {
   const int m_tiles = L.n_seq * p.tiles_t * p.tiles_h * p.tiles_w;
 
   // ---- tile N: as wide as TMEM allows, narrowed while the grid cannot fill the 148 SMs
-  int bn_max = (n_acc == 3) ? 128 : 256;
-  int bn = pow2_ceil(L.Cout) < 16 ? 16 : pow2_ceil(L.Cout);
-  if (bn > bn_max) bn = bn_max;
-  if (L.force_bn > 0) bn = L.force_bn;
-  else
-    while (bn > 64 && m_tiles * ((L.Cout + bn - 1) / bn) < 148) bn >>= 1;  // below 64 the A re-reads cost more than idle SMs
-  if (L.b_mn_major && bn < chunk) bn = chunk;
+  const int bn = pick_bn(n_acc, L.Cout, m_tiles, L.force_bn, chunk, L.b_mn_major);
   if (n_acc * bn > 512) {
     set_error("tapconv: %d accumulators x N=%d exceed TMEM", n_acc, bn);
     return OB_ERR_INVALID;
@@ -226,19 +257,43 @@ int tapconv_launch(const TapConvLaunch& L, cudaStream_t stream) {
   p.n_out = L.n_out; p.epi = L.epi; p.out_f32 = L.out_f32;
   p.alpha = L.alpha; p.beta = L.beta; p.out = L.out; p.out_d = L.out_d;
 
-  const int grid = m_tiles * p.tiles_n;
-  if (L.b_mn_major) {
-    switch (chunk) {
-      case 64: return launch_bn<64, true>(bn, p, grid, stream);
-      case 32: return launch_bn<32, true>(bn, p, grid, stream);
-      default: return launch_bn<16, true>(bn, p, grid, stream);
+  p.ksplit = 1;
+  p.split_ws = nullptr;
+  if (L.split_ws != nullptr && L.force_bn == 0) {
+    int ks; long wsb;
+    tapconv_plan(L.n_seq, L.n_out, L.epi == EPI_GATED, L.T, L.H, L.W, L.Cin, L.Cout, &ks, &wsb);
+    if (ks > 1) {
+      p.ksplit = ks;
+      p.split_ws = L.split_ws;
+      cudaError_t e = cudaMemsetAsync(L.split_ws, 0, static_cast<size_t>(wsb), stream);
+      if (e != cudaSuccess) { set_error("tapconv: workspace memset: %s", cudaGetErrorString(e)); return OB_ERR_CUDA; }
     }
   }
-  switch (chunk) {
-    case 64: return launch_bn<64, false>(bn, p, grid, stream);
-    case 32: return launch_bn<32, false>(bn, p, grid, stream);
-    default: return launch_bn<16, false>(bn, p, grid, stream);
+  const dim3 grid(m_tiles * p.tiles_n, p.ksplit);
+  int rc;
+  if (L.b_mn_major) {
+    switch (chunk) {
+      case 64: rc = launch_bn<64, true>(bn, p, grid, stream); break;
+      case 32: rc = launch_bn<32, true>(bn, p, grid, stream); break;
+      default: rc = launch_bn<16, true>(bn, p, grid, stream); break;
+    }
+  } else {
+    switch (chunk) {
+      case 64: rc = launch_bn<64, false>(bn, p, grid, stream); break;
+      case 32: rc = launch_bn<32, false>(bn, p, grid, stream); break;
+      default: rc = launch_bn<16, false>(bn, p, grid, stream); break;
+    }
   }
+  if (rc != OB_OK || p.ksplit == 1) return rc;
+  {
+    const long hw = static_cast<long>(L.H) * L.W;
+    const long total = static_cast<long>(L.n_seq) * L.n_out * L.T * hw * (L.Cout / 4);
+    tapconv_finish_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
+        p.split_ws, p.alpha, p.beta, p.out, static_cast<float*>(p.out_d), L.n_seq, L.n_out, L.T, hw, L.Cout, p.epi, p.out_f32);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error("tapconv_finish launch: %s", cudaGetErrorString(e)); return OB_ERR_CUDA; }
+  }
+  return OB_OK;
 }
 
 }  // namespace ob

@@ -68,6 +68,8 @@ struct TapConvParams {
   const float* beta;
   void* out;    // [n_seq*n_out*T, H, W, Cout]
   void* out_d;  // optional (EPI_GATED): shared - own accumulator, fp32, same shape as out
+  int ksplit;   // >1: blockIdx.y owns a slice of the channel chunks; raw accumulators are reduced into split_ws
+  float* split_ws;  // [n_acc][n_seq*n_out*T*H*W][Cout] fp32, zeroed by the host (shared acc uses rows of set 0)
 };
 
 template <int CHUNK>
@@ -133,7 +135,10 @@ __global__ void __launch_bounds__(TAPCONV_THREADS, 1) tapconv_kernel(const __gri
   const int n_acc = p.n_out + (p.epi == EPI_GATED ? 1 : 0);
   uint32_t tmem_cols = 32;
   while (tmem_cols < static_cast<uint32_t>(n_acc * BN)) tmem_cols <<= 1;
-  const int n_chunks = (p.Cin + CHUNK - 1) / CHUNK;  // a ragged last chunk is TMA zero-filled
+  const int n_chunks_all = (p.Cin + CHUNK - 1) / CHUNK;  // a ragged last chunk is TMA zero-filled
+  // split-K: this CTA owns channel chunks [ck_lo, ck_hi)
+  const int ck_lo = static_cast<int>(static_cast<long>(n_chunks_all) * blockIdx.y / p.ksplit);
+  const int ck_hi = static_cast<int>(static_cast<long>(n_chunks_all) * (blockIdx.y + 1) / p.ksplit);
   const uint32_t dy_stride = static_cast<uint32_t>(p.bt * p.bw) * Cfg::ROW_BYTES;  // one image row of the tile
 
   if (threadIdx.x == 0) {
@@ -162,7 +167,7 @@ __global__ void __launch_bounds__(TAPCONV_THREADS, 1) tapconv_kernel(const __gri
     for (int ic = 0; ic < p.n_cols; ++ic) {
       const TapCol col = p.cols[ic];
       const void* mapA = &p.mapA[col.src];
-      for (int ck = 0; ck < n_chunks; ++ck) {
+      for (int ck = ck_lo; ck < ck_hi; ++ck) {
         mbar_wait(a_empty(as), aph ^ 1);
         if (elect_one()) {
           mbar_arrive_expect_tx(a_full(as), col.n_a * p.a_tile_bytes);
@@ -180,7 +185,7 @@ __global__ void __launch_bounds__(TAPCONV_THREADS, 1) tapconv_kernel(const __gri
     uint32_t bph = 0;
     for (int ic = 0; ic < p.n_cols; ++ic) {
       const TapCol col = p.cols[ic];
-      for (int ck = 0; ck < n_chunks; ++ck) {
+      for (int ck = ck_lo; ck < ck_hi; ++ck) {
         for (int d = 0; d < col.n_taps; ++d) {
           mbar_wait(b_empty(bs), bph ^ 1);
           if (elect_one()) {
@@ -213,7 +218,7 @@ __global__ void __launch_bounds__(TAPCONV_THREADS, 1) tapconv_kernel(const __gri
     uint32_t started = 0;  // bit j: accumulator j already holds a partial sum
     for (int ic = 0; ic < p.n_cols; ++ic) {
       const TapCol col = p.cols[ic];
-      for (int ck = 0; ck < n_chunks; ++ck) {
+      for (int ck = ck_lo; ck < ck_hi; ++ck) {
         mbar_wait(a_full(as), aph);
         const uint32_t sA = sA0 + as * p.a_slot_bytes;
         for (int d = 0; d < col.n_taps; ++d) {
@@ -261,6 +266,30 @@ __global__ void __launch_bounds__(TAPCONV_THREADS, 1) tapconv_kernel(const __gri
     tc_fence_after();
 
     const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    if (p.ksplit > 1) {
+      // partial sums: add the raw accumulators into the fp32 workspace; tapconv_finish_kernel applies the epilogue
+      const long rows_per_set = static_cast<long>(p.n_seq) * p.T * p.H * p.W;   // pixel rows of ONE output set
+      const long pix = ((static_cast<long>(seq) * p.T + t) * p.H + h) * p.W + w;
+      for (int a = 0; a < n_acc; ++a) {
+        // own accumulators: row = (set a, pixel); shared accumulator: stored after the n_out own sets
+        float* dst_row = p.split_ws + (static_cast<long>(a) * rows_per_set + pix) * p.Cout;
+        for (int c = 0; c < BN / CW; ++c) {
+          float v[CW];
+          if constexpr (CW == 32) tmem_ld32(lane_base + a * BN + c * CW, v);
+          else tmem_ld16(lane_base + a * BN + c * CW, v);
+          tmem_ld_wait();
+          const int col0 = n0 + c * CW;
+          if (row_ok && ck_hi > ck_lo) {
+#pragma unroll
+            for (int j = 0; j < CW; j += 4)
+              if (col0 + j + 4 <= p.Cout)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst_row + col0 + j), "f"(v[j]), "f"(v[j + 1]),
+                             "f"(v[j + 2]), "f"(v[j + 3])
+                             : "memory");
+          }
+        }
+      }
+    } else
     for (int o = 0; o < p.n_out; ++o) {
       const long frame = static_cast<long>(seq * p.n_out + o) * p.T + t;
       float al = 1.f, be = 0.f;
@@ -318,6 +347,38 @@ __global__ void __launch_bounds__(TAPCONV_THREADS, 1) tapconv_kernel(const __gri
     tc_fence_after();
     tmem_dealloc(tmem_base, tmem_cols);
   }
+}
+
+// Epilogue of a split-K launch: reads the reduced accumulators from the workspace and applies the same output stage
+// as the fused epilogue (gate combine, bf16 / fp32 store, optional fp32 difference tensor).
+static __global__ void __launch_bounds__(256) tapconv_finish_kernel(const float* __restrict__ ws, const float* __restrict__ alpha,
+                                                             const float* __restrict__ beta, void* __restrict__ out,
+                                                             float* __restrict__ out_d, int n_seq, int n_out, int T,
+                                                             long hw, int Cout, int epi, int out_f32) {
+  const long rows_per_set = static_cast<long>(n_seq) * T * hw;
+  const long vec = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;   // one float4 of one output row
+  const int v_per_row = Cout >> 2;
+  const long total = rows_per_set * n_out * v_per_row;
+  if (vec >= total) return;
+  const long orow = vec / v_per_row;                 // output row: ((seq*n_out + o)*T + t)*hw + px
+  const int c = static_cast<int>(vec - orow * v_per_row) << 2;
+  const long frame = orow / hw;
+  const long px = orow - frame * hw;
+  const long so = frame / T;                          // seq*n_out + o
+  const int t = static_cast<int>(frame - so * T);
+  const long sq = so / n_out;
+  const int o = static_cast<int>(so - sq * n_out);
+  const long pix = (sq * T + t) * hw + px;
+  const float4 own = *reinterpret_cast<const float4*>(ws + (static_cast<long>(o) * rows_per_set + pix) * Cout + c);
+  float4 y = own;
+  if (epi == EPI_GATED) {
+    const float4 shr = *reinterpret_cast<const float4*>(ws + (static_cast<long>(n_out) * rows_per_set + pix) * Cout + c);
+    const float al = alpha[frame], be = beta[frame];
+    y = make_float4(al * own.x + be * shr.x, al * own.y + be * shr.y, al * own.z + be * shr.z, al * own.w + be * shr.w);
+    if (out_d) *reinterpret_cast<float4*>(out_d + orow * Cout + c) = make_float4(shr.x - own.x, shr.y - own.y, shr.z - own.z, shr.w - own.w);
+  }
+  if (out_f32) *reinterpret_cast<float4*>(static_cast<float*>(out) + orow * Cout + c) = y;
+  else *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(out) + orow * Cout + c) = make_uint2(pack_bf16x2(y.x, y.y), pack_bf16x2(y.z, y.w));
 }
 
 }  // namespace ob

@@ -90,6 +90,12 @@ def weight_grad(params, taps, cin, cin_pad, gains, dwg, n_split, eps=1e-4):
 _CONST = {}
 
 
+def split_workspace(n_seq, S, T, h, w, cin, cout, ksize, gated, device):
+    """fp32 scratch for a split-K conv launch, or None when the layer fills the GPU without it."""
+    nbytes = query("ob_conv_split_ws_bytes", n_seq, S, T, h, w, cin, cout, ksize, gated)
+    return torch.empty(nbytes // 4, dtype=torch.float32, device=device) if nbytes > 0 else None
+
+
 def clean_rows_mask(n_seq, S, T, device):
     """beta for the dgrad epilogue: 1 on clean rows (which fed the causal context), 0 on noised rows."""
     key = ("clean", n_seq, S, T, device)
@@ -112,8 +118,9 @@ class PlainConvFn(torch.autograd.Function):
         f, cin_pad, h, wd = x.shape
         cout, cout_pad = w.shape[0], wg.shape[0]
         out = empty_rows(f, cout_pad, h, wd, x.device, torch.float32 if out_f32 else BF16)
-        call("ob_conv_fwd", _vp(x), None, _vp(wg), None, None, _vp(out), None, 1, 1, f, h, wd, cin_pad, cout_pad, ksize, 0,
-             int(out_f32), stream_ptr())
+        ws = split_workspace(1, 1, f, h, wd, cin_pad, cout_pad, ksize, 0, x.device)
+        call("ob_conv_fwd", _vp(x), None, _vp(wg), None, None, _vp(out), None, _vp(ws), 1, 1, f, h, wd, cin_pad, cout_pad, ksize,
+             0, int(out_f32), stream_ptr())
         ctx.save_for_backward(x, w, wg)
         ctx.ksize, ctx.gain = ksize, gain
         return out if cout_pad == cout else out[:, :cout]
@@ -128,7 +135,9 @@ class PlainConvFn(torch.autograd.Function):
         dx = None
         if ctx.needs_input_grad[0]:
             dx = empty_rows(f, cin_pad, h, wd, x.device)
-            call("ob_conv_dgrad", _vp(gy), None, _vp(wg), None, None, _vp(dx), 1, 1, f, h, wd, cin_pad, cout, k, 0, stream_ptr())
+            ws = split_workspace(1, 1, f, h, wd, cout, cin_pad, k, 0, x.device)
+            call("ob_conv_dgrad", _vp(gy), None, _vp(wg), None, None, _vp(dx), _vp(ws), 1, 1, f, h, wd, cin_pad, cout, k, 0,
+                 stream_ptr())
         if w.requires_grad:
             ns = query("ob_conv_wgrad_splits", 1, 1, f, h, wd, cin_pad, cout, k, 0)
             dwg = torch.empty((ns, cout, k * k, cin_pad), dtype=torch.float32, device=x.device)
@@ -156,7 +165,8 @@ class GatedConvFn(torch.autograd.Function):
         call("ob_ctx_build", _vp(x), _vp(pad5), _vp(cx), n_seq, S, T, h * wd * cin_pad, cin, cin_pad, stream_ptr())
         out = empty_rows(f, cout, h, wd, dev)
         out_d = empty_rows(f, cout, h, wd, dev, torch.float32) if want_grad else None
-        call("ob_conv_fwd", _vp(x), _vp(cx), _vp(wg), _vp(alpha), _vp(beta), _vp(out), _vp(out_d), n_seq, S, T, h, wd,
+        ws = split_workspace(n_seq, S, T, h, wd, cin_pad, cout, 3, 1, dev)
+        call("ob_conv_fwd", _vp(x), _vp(cx), _vp(wg), _vp(alpha), _vp(beta), _vp(out), _vp(out_d), _vp(ws), n_seq, S, T, h, wd,
              cin_pad, cout, 3, 1, 0, stream_ptr())
         if want_grad:
             ctx.save_for_backward(x, cx, w2, w3, wg, ab, out, out_d, g_offset, g_mult, g_max, g_min, c_noise)
@@ -182,8 +192,9 @@ class GatedConvFn(torch.autograd.Function):
         dx = None
         if ctx.needs_input_grad[0]:
             dx = empty_rows(f, cin_pad, h, wd, dev)
-            call("ob_conv_dgrad", _vp(gy), _vp(gb), _vp(wg), _vp(alpha), _vp(clean_rows_mask(n_seq, S, T, dev)), _vp(dx), n_seq,
-                 S, T, h, wd, cin_pad, cout, 3, 1, stream_ptr())
+            ws = split_workspace(n_seq, S, T, h, wd, cout, cin_pad, 3, 1, dev)
+            call("ob_conv_dgrad", _vp(gy), _vp(gb), _vp(wg), _vp(alpha), _vp(clean_rows_mask(n_seq, S, T, dev)), _vp(dx),
+                 _vp(ws), n_seq, S, T, h, wd, cin_pad, cout, 3, 1, stream_ptr())
         if w2.requires_grad or w3.requires_grad:
             ns = query("ob_conv_wgrad_splits", n_seq, S, T, h, wd, cin_pad, cout, 3, 1)
             dwg = torch.empty((ns, cout, 27, cin_pad), dtype=torch.float32, device=dev)

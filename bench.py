@@ -85,7 +85,7 @@ class ConvProfiler:
     @staticmethod
     def conv_flops(name, a):
         # ob_conv_fwd(x,ctx,wg,alpha,beta,out,out_d, n_seq,S,T,H,W,cin,cout,ksize,gated,...) / ob_conv_dgrad(gy,gb,wg,alpha,beta,dx, ...)
-        off = 7 if name == "ob_conv_fwd" else 6
+        off = 8 if name == "ob_conv_fwd" else 7
         n_seq, S, T, H, W, cin, cout, k, gated = a[off:off + 9]
         px = n_seq * T * H * W
         if gated:

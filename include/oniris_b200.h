@@ -57,10 +57,15 @@ int ob_wnorm_bwd(const float* w, const float* dwg, float* dw, int cout, int cin,
  *                ctx: bf16 [n_seq, T+2, H, W, Cin] = two pad frames (ones, or the cached activations) followed
  *                by the T clean frames; the context term is computed ONCE per (b,t) and shared by both halves.
  *                out_d (optional, may be NULL): fp32, context term minus current-frame term (saved for backward).
- * out: [n_seq*S*T, H, W, Cout], bf16 or (out_f32 != 0) fp32.  alpha/beta: fp32 [n_seq*S*T]. */
+ * out: [n_seq*S*T, H, W, Cout], bf16 or (out_f32 != 0) fp32.  alpha/beta: fp32 [n_seq*S*T].
+ * split_ws (optional, may be NULL): fp32 scratch sized by ob_conv_split_ws_bytes.  When given and the layer has too
+ * few output tiles for 148 SMs (the 4x4 / 8x8 levels), the channel chunks are sliced over extra CTAs and reduced there
+ * (split-K); the call zeroes it itself.  For the input gradient pass query with cin/cout SWAPPED (it is the transposed
+ * problem). */
+int64_t ob_conv_split_ws_bytes(int n_seq, int S, int T, int H, int W, int cin, int cout, int ksize, int gated);
 int ob_conv_fwd(const void* x, const void* ctx, const void* wg, const float* alpha, const float* beta, void* out,
-                void* out_d, int n_seq, int S, int T, int H, int W, int cin, int cout, int ksize, int gated, int out_f32,
-                void* stream);
+                void* out_d, void* split_ws, int n_seq, int S, int T, int H, int W, int cin, int cout, int ksize, int gated,
+                int out_f32, void* stream);
 
 /* Input gradient of ob_conv_fwd.  gy: bf16 [n_seq*S*T, H, W, Cout] = dL/dout (unscaled);
  * gated: gb: bf16 [n_seq*T, H, W, Cout] = sum_s beta_s*dL/dout_s (from ob_gate_bwd) and
@@ -69,7 +74,8 @@ int ob_conv_fwd(const void* x, const void* ctx, const void* wg, const float* alp
  * plain: dx = convT(gy); alpha/beta ignored (may be NULL).
  * dx: bf16 [n_seq*S*T, H, W, Cin].  Reads the SAME wg as the forward pass (as an MN-major operand). */
 int ob_conv_dgrad(const void* gy, const void* gb, const void* wg, const float* alpha, const float* beta, void* dx,
-                  int n_seq, int S, int T, int H, int W, int cin, int cout, int ksize, int gated, void* stream);
+                  void* split_ws, int n_seq, int S, int T, int H, int W, int cin, int cout, int ksize, int gated,
+                  void* stream);
 
 /* Weight gradient of ob_conv_fwd into dwg fp32 [n_split][Cout][taps][Cin] (taps = k*k or 27).  n_split must come
  * from ob_conv_wgrad_splits for the same shape. */
