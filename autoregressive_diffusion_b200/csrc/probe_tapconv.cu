@@ -27,6 +27,7 @@ struct Problem {
   int force_bn;
   int bmn;
   int halo;
+  int split;   // give the launch a split-K workspace
 };
 
 // column of vertical taps at horizontal shift dx; flip mirrors the kernel (input-gradient form)
@@ -90,6 +91,8 @@ static bool run(const Problem& P, bool check, int reps) {
   L.n_seq = P.n_seq; L.n_out = P.n_out; L.T = P.T; L.H = P.H; L.W = P.W; L.Cin = P.Cin; L.Cout = P.Cout;
   L.epi = P.epi; L.out_f32 = P.out_f32; L.alpha = dal; L.beta = dbe; L.out = dOut;
   L.out_d = (P.epi == EPI_GATED) ? dD : nullptr; L.force_bn = P.force_bn; L.b_mn_major = P.bmn;
+  float* dWs = nullptr;
+  if (P.split) { cudaMalloc(&dWs, (size_t)n_acc * nout / P.n_out * 4); L.split_ws = dWs; }
 
   int rc = tapconv_launch(L, 0);
   cudaError_t e = cudaDeviceSynchronize();
@@ -159,8 +162,9 @@ static bool run(const Problem& P, bool check, int reps) {
   return ok;
 }
 
-static Problem gated(const char* name, int B, int S, int n, int H, int W, int Cin, int Cout, int force_bn = 0) {
+static Problem gated(const char* name, int B, int S, int n, int H, int W, int Cin, int Cout, int force_bn = 0, int split = 0) {
   Problem P{};
+  P.split = split;
   P.name = name; P.n_seq = B; P.n_out = S; P.T = n; P.H = H; P.W = W; P.Cin = Cin; P.Cout = Cout;
   P.epi = EPI_GATED; P.out_f32 = 0; P.seqA[0] = B * S; P.TA[0] = n; P.seqA[1] = B; P.TA[1] = n + 2; P.w_taps = 27;
   P.force_bn = force_bn; P.halo = 1;
@@ -208,6 +212,8 @@ int main(int argc, char** argv) {
   fails += !run(gated("gated dual c64 n128 16x16 B1 n3 bn128", 1, 2, 3, 16, 16, 64, 128, 128), true, 0);
   fails += !run(gated("gated eval c64 n256 8x8 B2 T5 bn256", 2, 1, 5, 8, 8, 64, 256, 256), true, 0);
   fails += !run(gated("gated eval decode c128 n128 4x4 B3 T1", 3, 1, 1, 4, 4, 128, 128), true, 0);
+  fails += !run(gated("gated dual split c256 n128 4x4 B1 n8", 1, 2, 8, 4, 4, 256, 128, 0, 1), true, 0);
+  fails += !run(gated("gated eval split c256 n64 4x4 B2 T4", 2, 1, 4, 4, 4, 256, 64, 0, 1), true, 0);
   fails += !run(dgrad("dgrad dual c128 n64 8x8 B2 n4", 2, 4, 8, 8, 128, 64), true, 0);
   fails += !run(dgrad("dgrad dual BMN c128 n64 8x8 B2 n4", 2, 4, 8, 8, 128, 64, 1), true, 0);
   fails += !run(dgrad("dgrad dual BMN c64 n256 4x4 B2 n8", 2, 8, 4, 4, 64, 256, 1), true, 0);
@@ -226,6 +232,14 @@ int main(int argc, char** argv) {
     run(gated("CS 512->512 8x8 bn128", 2, 2, 16, 8, 8, 512, 512, 128), false, 20);
     run(gated("CS 512->512 8x8 bn64", 2, 2, 16, 8, 8, 512, 512, 64), false, 20);
     run(gated("CS 512->512 8x8 bn32", 2, 2, 16, 8, 8, 512, 512, 32), false, 20);
+    run(gated("CS 512->512 8x8 split auto", 2, 2, 16, 8, 8, 512, 512, 0, 1), false, 20);
+    run(gated("CS 512->512 8x8 split bn128", 2, 2, 16, 8, 8, 512, 512, 128, 1), false, 20);
+    run(gated("CS 1024->512 8x8 split auto", 2, 2, 16, 8, 8, 1024, 512, 0, 1), false, 20);
+    run(gated("CS 512->512 4x4 split auto", 2, 2, 16, 4, 4, 512, 512, 0, 1), false, 20);
+    run(gated("CS 512->512 4x4 split bn128", 2, 2, 16, 4, 4, 512, 512, 128, 1), false, 20);
+    run(gated("CS 256->256 16x16 bn128", 2, 2, 16, 16, 16, 256, 256, 128), false, 20);
+    run(gated("CS 256->256 16x16 bn64", 2, 2, 16, 16, 16, 256, 256, 64), false, 20);
+    run(gated("CS 128->128 32x32 bn64", 2, 2, 16, 32, 32, 128, 128, 64), false, 20);
     run(gated("CS 512->512 4x4 bn128", 2, 2, 16, 4, 4, 512, 512, 128), false, 20);
     run(gated("CS 512->512 4x4 bn64", 2, 2, 16, 4, 4, 512, 512, 64), false, 20);
     run(gated("CS 512->512 4x4 bn32", 2, 2, 16, 4, 4, 512, 512, 32), false, 20);

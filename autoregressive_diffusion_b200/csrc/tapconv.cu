@@ -134,15 +134,37 @@ static void tile_shape(int H, int W, int* bw, int* bh, int* bt) {
   *bt = 128 / (*bw * *bh);
 }
 
-static int pick_bn(int n_acc, int Cout, int m_tiles, int force_bn, int chunk, int b_mn_major) {
-  int bn_max = (n_acc == 3) ? 128 : 256;
+// Tile-N and split-K policy.  Wide N keeps the MMA off the shared-memory read limit (N=64 re-reads the activation
+// tile twice as often per FLOP), so when a layer has too few output tiles for 148 SMs the first remedy is to slice
+// its K loop (channel chunks) over extra CTAs, and only then to narrow N.
+static void pick_tiling(int n_acc, int Cout, int Cin, int chunk, int m_tiles, int force_bn, int b_mn_major, bool can_split,
+                        int* bn_out, int* ks_out) {
+  const int bn_max = (n_acc == 3) ? 128 : 256;
   int bn = pow2_ceil(Cout) < 16 ? 16 : pow2_ceil(Cout);
   if (bn > bn_max) bn = bn_max;
+  const int n_chunks = (Cin + chunk - 1) / chunk;
+  auto split_for = [&](int b) {
+    const int tiles = m_tiles * ((Cout + b - 1) / b);
+    int ks = 1;
+    if (can_split && tiles <= 74 && n_chunks >= 4 && Cout % 4 == 0) {
+      ks = 148 / tiles;
+      if (ks > n_chunks / 2) ks = n_chunks / 2;   // at least two chunks per slice
+      if (ks > 8) ks = 8;
+      if (ks < 1) ks = 1;
+    }
+    return ks;
+  };
   if (force_bn > 0) bn = force_bn;
-  else
-    while (bn > 64 && m_tiles * ((Cout + bn - 1) / bn) < 148) bn >>= 1;  // below 64 the A re-reads cost more than idle SMs
+  else {
+    while (bn > 64) {
+      const int tiles = m_tiles * ((Cout + bn - 1) / bn);
+      if (tiles * split_for(bn) >= 100) break;
+      bn >>= 1;
+    }
+  }
   if (b_mn_major && bn < chunk) bn = chunk;
-  return bn;
+  *bn_out = bn;
+  *ks_out = split_for(bn);
 }
 
 // Small-spatial layers (the 4x4 / 8x8 levels) have too few output tiles to occupy 148 SMs while their K loop is
@@ -153,16 +175,8 @@ void tapconv_plan(int n_seq, int n_out, int gated, int T, int H, int W, int Cin,
   const int m_tiles = n_seq * ((T + bt - 1) / bt) * ((H + bh - 1) / bh) * ((W + bw - 1) / bw);
   const int n_acc = n_out + (gated ? 1 : 0);
   const int chunk = (Cin % 64 == 0) ? 64 : (Cin % 32 == 0) ? 32 : 16;
-  const int bn = pick_bn(n_acc, Cout, m_tiles, 0, chunk, 0);
-  const int tiles = m_tiles * ((Cout + bn - 1) / bn);
-  const int n_chunks = (Cin + chunk - 1) / chunk;
-  int ks = 1;
-  if (tiles <= 74 && n_chunks >= 4 && Cout % 4 == 0) {
-    ks = 148 / tiles;
-    if (ks > n_chunks / 2) ks = n_chunks / 2;   // at least two chunks per slice
-    if (ks > 8) ks = 8;
-    if (ks < 1) ks = 1;
-  }
+  int bn, ks;
+  pick_tiling(n_acc, Cout, Cin, chunk, m_tiles, 0, 0, true, &bn, &ks);
   *ksplit = ks;
   *ws_bytes = ks > 1 ? static_cast<long>(n_acc) * n_seq * T * H * W * Cout * 4 : 0;
 }
@@ -195,7 +209,8 @@ int tapconv_launch(const TapConvLaunch& L, cudaStream_t stream) {
   const int m_tiles = L.n_seq * p.tiles_t * p.tiles_h * p.tiles_w;
 
   // ---- tile N: as wide as TMEM allows, narrowed while the grid cannot fill the 148 SMs
-  const int bn = pick_bn(n_acc, L.Cout, m_tiles, L.force_bn, chunk, L.b_mn_major);
+  int bn, ks_plan;
+  pick_tiling(n_acc, L.Cout, L.Cin, chunk, m_tiles, L.force_bn, L.b_mn_major, L.split_ws != nullptr, &bn, &ks_plan);
   if (n_acc * bn > 512) {
     set_error("tapconv: %d accumulators x N=%d exceed TMEM", n_acc, bn);
     return OB_ERR_INVALID;
@@ -259,9 +274,9 @@ int tapconv_launch(const TapConvLaunch& L, cudaStream_t stream) {
 
   p.ksplit = 1;
   p.split_ws = nullptr;
-  if (L.split_ws != nullptr && L.force_bn == 0) {
-    int ks; long wsb;
-    tapconv_plan(L.n_seq, L.n_out, L.epi == EPI_GATED, L.T, L.H, L.W, L.Cin, L.Cout, &ks, &wsb);
+  if (L.split_ws != nullptr) {
+    const int ks = ks_plan;
+    const long wsb = static_cast<long>(n_acc) * L.n_seq * L.T * L.H * L.W * L.Cout * 4;
     if (ks > 1) {
       p.ksplit = ks;
       p.split_ws = L.split_ws;
