@@ -38,6 +38,8 @@ _SIGS = {
     "ob_conv_wgrad_splits": "iiiiiiiii",
     "ob_conv_wgrad": "pppppiiiiiiiiiip",
     "ob_gate_bwd": "pppppppppiiilp",
+    "ob_conv_prologue": "pppiiiliippppppppip",
+    "ob_gate_bwd_fused": "ppppppppiiilpppppppppip",
     "ob_gate_fwd": "pppppppiiiip",
     "ob_gate_bwd_params": "pppppppppppppiiiip",
     "ob_ctx_build": "pppiiiliip",

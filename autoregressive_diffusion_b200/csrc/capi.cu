@@ -162,7 +162,23 @@ int ob_conv_wgrad(const void* gya, const void* x, const void* gb, const void* ct
 
 int ob_gate_bwd(const void* dy, const void* y, const void* d, const float* alpha, const float* beta, void* gya, void* gb,
                 float* s_y, float* s_d, int n_seq, int S, int T, int64_t frame_elems, void* stream) {
-  return gate_bwd(dy, y, d, alpha, beta, gya, gb, s_y, s_d, n_seq, S, T, (long)frame_elems, (cudaStream_t)stream);
+  return gate_bwd(dy, y, d, alpha, beta, gya, gb, s_y, s_d, n_seq, S, T, (long)frame_elems, nullptr, nullptr, nullptr,
+                  nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, (cudaStream_t)stream);
+}
+int ob_gate_bwd_fused(const void* dy, const void* y, const void* d, const float* alpha, const float* beta, void* gya,
+                      void* gb, float* scratch, int n_seq, int S, int T, int64_t frame_elems, const float* offset,
+                      const float* mult, const float* max_gating, const float* min_gating, const float* c_noise,
+                      float* g_offset, float* g_mult, float* g_max, float* g_min, int n_ctx, void* stream) {
+  const int f = n_seq * S * T;
+  return gate_bwd(dy, y, d, alpha, beta, gya, gb, scratch, scratch + f, n_seq, S, T, (long)frame_elems, offset, mult,
+                  max_gating, min_gating, c_noise, g_offset, g_mult, g_max, g_min, reinterpret_cast<unsigned*>(scratch + 2 * f),
+                  n_ctx, (cudaStream_t)stream);
+}
+int ob_conv_prologue(const void* x, const void* pad, void* ctx, int b, int S, int T, int64_t frame_elems, int cin,
+                     int cin_pad, const float* offset, const float* mult, const float* max_gating, const float* min_gating,
+                     const float* c_noise, float* alpha, float* beta, float* scratch, int n_ctx, void* stream) {
+  return conv_prologue(x, pad, ctx, b, S, T, (long)frame_elems, cin, cin_pad, offset, mult, max_gating, min_gating, c_noise,
+                       alpha, beta, scratch, scratch ? 2 * b * S * T + 1 : 0, n_ctx, (cudaStream_t)stream);
 }
 int ob_gate_fwd(const float* offset, const float* mult, const float* max_gating, const float* min_gating,
                 const float* c_noise, float* alpha, float* beta, int frames, int T, int half, int n_ctx, void* stream) {

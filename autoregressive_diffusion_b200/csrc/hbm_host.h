@@ -8,7 +8,12 @@ int wnorm_fwd(float* w, void* wg, int Co, int Ci, int taps, int Ci_pad, int taps
 int wnorm_bwd(const float* w, const float* dwg, float* dw, int Co, int Ci, int taps, int Ci_pad, int taps_total,
               int tap_off, int n_split, float gain, float eps, int accumulate, cudaStream_t st);
 int gate_bwd(const void* dy, const void* y, const void* d, const float* alpha, const float* beta, void* gya, void* gb,
-             float* s_y, float* s_d, int n_seq, int S, int T, long frame_elems, cudaStream_t st);
+             float* s_y, float* s_d, int n_seq, int S, int T, long frame_elems, const float* offset, const float* mult,
+             const float* max_g, const float* min_g, const float* c_noise, float* g_offset, float* g_mult, float* g_max,
+             float* g_min, unsigned* counter, int n_ctx, cudaStream_t st);
+int conv_prologue(const void* x, const void* pad, void* ctx, int B, int S, int T, long frame_elems, int cin, int cin_pad,
+                  const float* offset, const float* mult, const float* max_g, const float* min_g, const float* c_noise,
+                  float* alpha, float* beta, float* scratch, int scratch_n, int n_ctx, cudaStream_t st);
 int gate_fwd(const float* offset, const float* mult, const float* max_g, const float* min_g, const float* c_noise,
              float* alpha, float* beta, int frames, int T, int half, int n_ctx, cudaStream_t st);
 int gate_bwd_params(const float* offset, const float* mult, const float* max_g, const float* min_g, const float* c_noise,

@@ -106,53 +106,66 @@ __global__ void __launch_bounds__(256) wnorm_fwd_kernel(float* __restrict__ w, _
 // order with a +1 row pad, so both the global reads (dwg, w) and the global write (dw) are fully coalesced and the
 // [tap][ci] -> [ci][tap] transpose happens on conflict-free shared-memory reads.  accumulate != 0: dw += result
 // (gradient accumulation over micro-batches without a separate add pass).
+// TAPS is a compile-time constant (1, 9 or 18 on this path; 0 = generic) so that the [ci][tap] <-> [tap][ci] index
+// arithmetic compiles to multiply-shift instead of integer division.
+template <int TAPS>
 __global__ void __launch_bounds__(256) wnorm_bwd_kernel(const float* __restrict__ w, const float* __restrict__ dwg,
-                                                        float* __restrict__ dw, int Co, int Ci, int taps, int Ci_pad,
+                                                        float* __restrict__ dw, int Co, int Ci, int taps_rt, int Ci_pad,
                                                         int taps_total, int tap_off, int n_split, float gain, float eps,
                                                         int accumulate) {
   __shared__ float red[32];
   extern __shared__ float gbuf[];  // [taps][Ci + 1]
+  const int taps = TAPS > 0 ? TAPS : taps_rt;
   const int co = blockIdx.x;
   const int K = Ci * taps;
   const int ld = Ci + 1;
   const float* wr = w + static_cast<long>(co) * K;
+  float* dwr = dw + static_cast<long>(co) * K;
   const long split_stride = static_cast<long>(Co) * taps_total * Ci_pad;
   const float* gsrc = dwg + (static_cast<long>(co) * taps_total + tap_off) * Ci_pad;
-  float* dwr = dw + static_cast<long>(co) * K;
-  const bool vec = ((Ci_pad & 3) == 0) && ((K & 3) == 0) && ((split_stride & 3) == 0) &&
-                   (((reinterpret_cast<uintptr_t>(gsrc) | reinterpret_cast<uintptr_t>(wr) | reinterpret_cast<uintptr_t>(dwr)) & 15) == 0);
-  // ---- stage 1: reduce the split partials, keep the row in shared memory (tap-major, padded)
-  if (vec) {
-    const int n4 = taps * Ci_pad / 4;
-    for (int j4 = threadIdx.x; j4 < n4; j4 += blockDim.x) {
-      float4 g = *reinterpret_cast<const float4*>(gsrc + j4 * 4);
-      for (int s = 1; s < n_split; ++s) {
-        const float4 t = *reinterpret_cast<const float4*>(gsrc + s * split_stride + j4 * 4);
-        g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w;
+  const bool vec_g = ((Ci_pad & 3) == 0) && ((split_stride & 3) == 0) && ((reinterpret_cast<uintptr_t>(gsrc) & 15) == 0);
+  const bool vec_w = ((K & 3) == 0) && (((reinterpret_cast<uintptr_t>(wr) | reinterpret_cast<uintptr_t>(dwr)) & 15) == 0);
+  // ---- stage 1: reduce the split partials, keep the row in shared memory (tap-major, padded).
+  //      warp <-> tap, lane <-> channel group: no index divisions, every thread busy, loads independent
+  {
+    // (1x1 kernels have a single tap: then the whole block walks the channels)
+    const bool flat = (TAPS == 1);
+    const int warp = flat ? 0 : (threadIdx.x >> 5), nwarps = flat ? 1 : (blockDim.x >> 5);
+    const int lane = flat ? threadIdx.x : (threadIdx.x & 31);
+    const int lanes = flat ? blockDim.x : 32;
+    for (int tap = warp; tap < taps; tap += nwarps) {
+      const float* src = gsrc + tap * Ci_pad;
+      float* dst = gbuf + tap * ld;
+      if (vec_g) {
+#pragma unroll 4
+        for (int c4 = lane; c4 < Ci_pad / 4; c4 += lanes) {
+          float4 g = *reinterpret_cast<const float4*>(src + c4 * 4);
+          for (int sp = 1; sp < n_split; ++sp) {
+            const float4 t = *reinterpret_cast<const float4*>(src + sp * split_stride + c4 * 4);
+            g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w;
+          }
+          const int ci = c4 * 4;
+          if (ci + 3 < Ci) { dst[ci] = g.x; dst[ci + 1] = g.y; dst[ci + 2] = g.z; dst[ci + 3] = g.w; }
+          else {
+            if (ci < Ci) dst[ci] = g.x;
+            if (ci + 1 < Ci) dst[ci + 1] = g.y;
+            if (ci + 2 < Ci) dst[ci + 2] = g.z;
+          }
+        }
+      } else {
+        for (int ci = lane; ci < Ci; ci += lanes) {
+          float g = 0.f;
+          for (int sp = 0; sp < n_split; ++sp) g += src[sp * split_stride + ci];
+          dst[ci] = g;
+        }
       }
-      const int j = j4 * 4;
-      const int tap = j / Ci_pad, ci = j - tap * Ci_pad;
-      float* dst = gbuf + tap * ld + ci;
-      if (ci + 3 < Ci) { dst[0] = g.x; dst[1] = g.y; dst[2] = g.z; dst[3] = g.w; }
-      else {
-        if (ci < Ci) dst[0] = g.x;
-        if (ci + 1 < Ci) dst[1] = g.y;
-        if (ci + 2 < Ci) dst[2] = g.z;
-      }
-    }
-  } else {
-    for (int j = threadIdx.x; j < taps * Ci_pad; j += blockDim.x) {
-      const int tap = j / Ci_pad, ci = j - tap * Ci_pad;
-      if (ci >= Ci) continue;
-      float g = 0.f;
-      for (int s = 0; s < n_split; ++s) g += gsrc[s * split_stride + j];
-      gbuf[tap * ld + ci] = g;
     }
   }
   __syncthreads();
-  // ---- stage 2: <g,w> and |w|^2 in the parameter's own order (coalesced w, conflict-free smem gather)
+  // ---- stage 2: <g,w> and |w|^2 in the parameter's own order (coalesced 128-bit reads of w, conflict-free smem gather)
   float ss = 0.f, dot = 0.f;
-  if (vec) {
+  if (vec_w) {
+#pragma unroll 3
     for (int i4 = threadIdx.x; i4 < K / 4; i4 += blockDim.x) {
       const float4 wv = *reinterpret_cast<const float4*>(wr + i4 * 4);
       const float wa[4] = {wv.x, wv.y, wv.z, wv.w};
@@ -179,7 +192,8 @@ __global__ void __launch_bounds__(256) wnorm_bwd_kernel(const float* __restrict_
   const float c = gain * rsqrtf(static_cast<float>(K)) / d;
   const float proj = (rms > 0.f) ? dot / (K * rms * d) : 0.f;
   // ---- stage 3: dw (+)= c * (g - w * proj)
-  if (vec) {
+  if (vec_w) {
+#pragma unroll 3
     for (int i4 = threadIdx.x; i4 < K / 4; i4 += blockDim.x) {
       const float4 wv = *reinterpret_cast<const float4*>(wr + i4 * 4);
       const float wa[4] = {wv.x, wv.y, wv.z, wv.w};
@@ -211,13 +225,21 @@ __global__ void __launch_bounds__(256) wnorm_bwd_kernel(const float* __restrict_
 //   y = alpha*a + beta*b  (alpha,beta per frame), saved: y (bf16) and d = b - a (fp32).
 // Produces in ONE pass over dy:  gya = alpha*dy (all frames), gb[b,t] = sum_s beta_s*dy_s (context rows),
 // and per-frame <dy,y>, <dy,d> (what the 5 gate scalars' gradients need).  S = 1 (eval-style) or 2 (clean+noised).
+// Optional tail of gate_bwd_kernel: the gate parameters, their gradient buffers and a zeroed ticket counter.
+struct GateGradArgs {
+  const float *offset, *mult, *max_g, *min_g, *c_noise;
+  float *g_offset, *g_mult, *g_max, *g_min;
+  unsigned* counter;   // nullptr: skip (gradients are then produced by gate_bwd_params_kernel)
+  int n_ctx;
+};
+
 __global__ void __launch_bounds__(256) gate_bwd_kernel(const __nv_bfloat16* __restrict__ dy,
                                                        const __nv_bfloat16* __restrict__ y,
                                                        const float* __restrict__ d,
                                                        const float* __restrict__ alpha, const float* __restrict__ beta,
                                                        __nv_bfloat16* __restrict__ gya, __nv_bfloat16* __restrict__ gb,
                                                        float* __restrict__ s_y, float* __restrict__ s_d, int n_seq, int S,
-                                                       int T, long frame_elems) {
+                                                       int T, long frame_elems, GateGradArgs gg) {
   __shared__ float red[32];
   const int bt = blockIdx.y;  // (b, t)
   const int b = bt / T, t = bt - b * T;
@@ -256,6 +278,48 @@ __global__ void __launch_bounds__(256) gate_bwd_kernel(const __nv_bfloat16* __re
       atomicAdd(&s_y[f], a);
       atomicAdd(&s_d[f], c);
     }
+  }
+  if (gg.counter == nullptr) return;
+  // ---- last CTA to finish turns the completed inner products into the six gate-scalar gradients
+  __shared__ unsigned last;
+  __threadfence();
+  if (threadIdx.x == 0) last = (atomicAdd(gg.counter, 1u) == gridDim.x * gridDim.y - 1) ? 1u : 0u;
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  const int frames = n_seq * S * T;
+  const int Trow = S * T;
+  const float lo = 1.f / (1.f + expf(-gg.min_g[0])), hi = 1.f / (1.f + expf(-gg.max_g[0]));
+  float a_state = 0.f, a_m0 = 0.f, a_m1 = 0.f, a_lo = 0.f, a_hi = 0.f;
+  for (int f = threadIdx.x; f < frames; f += blockDim.x) {
+    const float pos = log1pf(static_cast<float>((f % Trow) % T + gg.n_ctx));
+    const float cn = gg.c_noise[f];
+    const float state = cn * gg.mult[0] + gg.offset[0] + pos * gg.mult[1] + gg.offset[1];
+    const float sg = 1.f / (1.f + expf(-state));
+    const float g = lo + (1.f - lo) * hi * sg;
+    const float al = alpha[f], be = beta[f];
+    const float sy = __ldcg(&s_y[f]), sd = __ldcg(&s_d[f]);
+    const float da = (sy - be * sd) / (al + be);
+    const float db = da + sd;
+    const float D = (1.f - g) * (1.f - g) + g * g;
+    const float dg = (-g * da + (1.f - g) * db) / (D * sqrtf(D));
+    const float dstate = dg * (1.f - lo) * hi * sg * (1.f - sg);
+    a_state += dstate;
+    a_m0 += dstate * cn;
+    a_m1 += dstate * pos;
+    a_lo += dg * (1.f - hi * sg);
+    a_hi += dg * (1.f - lo) * sg;
+  }
+  a_state = block_sum(a_state, red);
+  a_m0 = block_sum(a_m0, red);
+  a_m1 = block_sum(a_m1, red);
+  a_lo = block_sum(a_lo, red);
+  a_hi = block_sum(a_hi, red);
+  if (threadIdx.x == 0) {
+    gg.g_offset[0] += a_state; gg.g_offset[1] += a_state;
+    gg.g_mult[0] += a_m0; gg.g_mult[1] += a_m1;
+    gg.g_min[0] += a_lo * lo * (1.f - lo);
+    gg.g_max[0] += a_hi * hi * (1.f - hi);
   }
 }
 
@@ -337,6 +401,56 @@ __global__ void __launch_bounds__(256) ctx_build_kernel(const __nv_bfloat16* __r
   const long b = e / per_b;
   const long r = e - b * per_b;
   const long t = r / frame_elems;        // 0..T+1
+  const long off = r - t * frame_elems;
+  bf16x8 out;
+  if (t >= 2) {
+    out = *reinterpret_cast<const bf16x8*>(x + ((b * S) * T + (t - 2)) * frame_elems + off);
+  } else if (pad != nullptr) {
+    out = *reinterpret_cast<const bf16x8*>(pad + (b * 2 + t) * frame_elems + off);
+  } else {
+    float f[8];
+    const int c0 = static_cast<int>(off % cin_pad);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = (c0 + j < cin) ? 1.f : 0.f;
+    out = pack8(f);
+  }
+  *reinterpret_cast<bf16x8*>(ctx + e) = out;
+}
+
+// Forward prologue of the gated conv in ONE launch: blocks [0, gridDim.x-1) assemble the causal context (as
+// ctx_build_kernel), the last block evaluates the gate (as gate_fwd_kernel) and zeroes the scratch that the backward
+// pre-pass accumulates its per-frame inner products into.
+__global__ void __launch_bounds__(256) conv_prologue_kernel(const __nv_bfloat16* __restrict__ x,
+                                                            const __nv_bfloat16* __restrict__ pad,
+                                                            __nv_bfloat16* __restrict__ ctx, int S, int T, long frame_elems,
+                                                            int cin, int cin_pad, long total_vec,
+                                                            const float* __restrict__ offset, const float* __restrict__ mult,
+                                                            const float* __restrict__ max_g, const float* __restrict__ min_g,
+                                                            const float* __restrict__ c_noise, float* __restrict__ alpha,
+                                                            float* __restrict__ beta, float* __restrict__ scratch,
+                                                            int scratch_n, int frames, int n_ctx) {
+  if (blockIdx.x == gridDim.x - 1) {
+    const float lo = 1.f / (1.f + expf(-min_g[0])), hi = 1.f / (1.f + expf(-max_g[0]));
+    const int Trow = S * T;
+    for (int f = threadIdx.x; f < frames; f += blockDim.x) {
+      const float pos = log1pf(static_cast<float>((f % Trow) % T + n_ctx));
+      const float state = c_noise[f] * mult[0] + offset[0] + pos * mult[1] + offset[1];
+      const float g = lo + (1.f - lo) * hi / (1.f + expf(-state));
+      const float inv = rsqrtf((1.f - g) * (1.f - g) + g * g);
+      alpha[f] = (1.f - g) * inv;
+      beta[f] = g * inv;
+    }
+    if (scratch != nullptr)
+      for (int i = threadIdx.x; i < scratch_n; i += blockDim.x) scratch[i] = 0.f;
+    return;
+  }
+  const long v = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (v >= total_vec) return;
+  const long e = v * 8;
+  const long per_b = static_cast<long>(T + 2) * frame_elems;
+  const long b = e / per_b;
+  const long r = e - b * per_b;
+  const long t = r / frame_elems;
   const long off = r - t * frame_elems;
   bf16x8 out;
   if (t >= 2) {
@@ -476,25 +590,27 @@ __global__ void __launch_bounds__(256) scale_silu_fwd_kernel(const __nv_bfloat16
 }
 
 // Backward: dy = g * silu'(y*c) * c ;  dc[frame, ch] = sum over the frame's pixels of g * silu'(y*c) * y.
-// grid = (channel groups of 8*? , frames); each CTA owns one frame and loops over its pixels so dc needs no atomics.
+// grid = (channel groups, pixel chunks, frames): enough CTAs to saturate HBM; each CTA reduces its pixels in registers
+// and shared memory, then adds one partial per channel into dc (zeroed by the launcher).
 __global__ void __launch_bounds__(256) scale_silu_bwd_kernel(const __nv_bfloat16* __restrict__ y,
                                                              const float* __restrict__ cscale,
                                                              const __nv_bfloat16* __restrict__ g,
                                                              __nv_bfloat16* __restrict__ dy, float* __restrict__ dc, int C,
-                                                             int rows_per_frame) {
-  // thread -> (pixel lane p0, channel vector cv); blockDim.x = 256 = PL pixel lanes * CV channel vectors
-  const int frame = blockIdx.y;
+                                                             int rows_per_frame, int rows_per_chunk) {
+  const int frame = blockIdx.z;
   const int cv_per_blk = min(C >> 3, 32);
   const int pl = blockDim.x / cv_per_blk;
   const int cv = threadIdx.x % cv_per_blk, p0 = threadIdx.x / cv_per_blk;
   const int c = (blockIdx.x * cv_per_blk + cv) << 3;
+  const int r_lo = blockIdx.y * rows_per_chunk;
+  const int r_hi = min(r_lo + rows_per_chunk, rows_per_frame);
   __shared__ float part[256][9];
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (c < C) {
     const float4 s0 = *reinterpret_cast<const float4*>(cscale + static_cast<long>(frame) * C + c);
     const float4 s1 = *reinterpret_cast<const float4*>(cscale + static_cast<long>(frame) * C + c + 4);
     const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-    for (int p = p0; p < rows_per_frame; p += pl) {
+    for (int p = r_lo + p0; p < r_hi; p += pl) {
       const long off = (static_cast<long>(frame) * rows_per_frame + p) * C + c;
       float yv[8], gv[8], o[8];
       unpack8(*reinterpret_cast<const bf16x8*>(y + off), yv);
@@ -517,7 +633,7 @@ __global__ void __launch_bounds__(256) scale_silu_bwd_kernel(const __nv_bfloat16
       for (int j = 0; j < 8; ++j) acc[j] += part[q * cv_per_blk + cv][j];
     float* o = dc + static_cast<long>(frame) * C + c;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = acc[j];
+    for (int j = 0; j < 8; ++j) atomicAdd(o + j, acc[j]);
   }
 }
 
@@ -588,18 +704,27 @@ int wnorm_bwd(const float* w, const float* dwg, float* dw, int Co, int Ci, int t
     set_error("wnorm_bwd: row of %d x %d floats exceeds shared memory", Ci, taps);
     return OB_ERR_UNSUPPORTED;
   }
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    cudaFuncSetAttribute(wnorm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    configured = 200 * 1024;
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(wnorm_bwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(wnorm_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(wnorm_bwd_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(wnorm_bwd_kernel<18>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    configured = true;
   }
-  wnorm_bwd_kernel<<<Co, 256, smem, st>>>(w, dwg, dw, Co, Ci, taps, Ci_pad, taps_total, tap_off, n_split, gain, eps,
-                                          accumulate);
+#define OB_WNORM_BWD(T) wnorm_bwd_kernel<T><<<Co, 256, smem, st>>>(w, dwg, dw, Co, Ci, taps, Ci_pad, taps_total, tap_off, n_split, gain, eps, accumulate)
+  if (taps == 1) OB_WNORM_BWD(1);
+  else if (taps == 9) OB_WNORM_BWD(9);
+  else if (taps == 18) OB_WNORM_BWD(18);
+  else OB_WNORM_BWD(0);
+#undef OB_WNORM_BWD
   return check_launch("wnorm_bwd");
 }
 
 int gate_bwd(const void* dy, const void* y, const void* d, const float* alpha, const float* beta, void* gya, void* gb,
-             float* s_y, float* s_d, int n_seq, int S, int T, long frame_elems, cudaStream_t st) {
+             float* s_y, float* s_d, int n_seq, int S, int T, long frame_elems, const float* offset, const float* mult,
+             const float* max_g, const float* min_g, const float* c_noise, float* g_offset, float* g_mult, float* g_max,
+             float* g_min, unsigned* counter, int n_ctx, cudaStream_t st) {
   if (frame_elems % 8 != 0 || S < 1 || S > 2) {
     set_error("gate_bwd: frame size %ld must be a multiple of 8 and S in {1,2}", frame_elems);
     return OB_ERR_INVALID;
@@ -611,7 +736,9 @@ int gate_bwd(const void* dy, const void* y, const void* d, const float* alpha, c
   gate_bwd_kernel<<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(y),
                                         static_cast<const float*>(d), alpha, beta,
                                         static_cast<__nv_bfloat16*>(gya), static_cast<__nv_bfloat16*>(gb), s_y, s_d, n_seq,
-                                        S, T, frame_elems);
+                                        S, T, frame_elems,
+                                        GateGradArgs{offset, mult, max_g, min_g, c_noise, g_offset, g_mult, g_max, g_min,
+                                                     (offset != nullptr) ? counter : nullptr, n_ctx});
   return check_launch("gate_bwd");
 }
 
@@ -641,6 +768,20 @@ int ctx_build(const void* x, const void* pad, void* ctx, int B, int S, int T, lo
                                                             static_cast<__nv_bfloat16*>(ctx), S, T, frame_elems, cin, cin_pad,
                                                             total_vec);
   return check_launch("ctx_build");
+}
+
+int conv_prologue(const void* x, const void* pad, void* ctx, int B, int S, int T, long frame_elems, int cin, int cin_pad,
+                  const float* offset, const float* mult, const float* max_g, const float* min_g, const float* c_noise,
+                  float* alpha, float* beta, float* scratch, int scratch_n, int n_ctx, cudaStream_t st) {
+  if (frame_elems % 8 != 0 || cin_pad % 8 != 0) { set_error("conv_prologue: frame size must be a multiple of 8"); return OB_ERR_INVALID; }
+  const long total_vec = static_cast<long>(B) * (T + 2) * frame_elems / 8;
+  if (total_vec <= 0) return OB_OK;
+  const unsigned blocks = static_cast<unsigned>((total_vec + 255) / 256) + 1;
+  conv_prologue_kernel<<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(pad),
+                                               static_cast<__nv_bfloat16*>(ctx), S, T, frame_elems, cin, cin_pad, total_vec,
+                                               offset, mult, max_g, min_g, c_noise, alpha, beta, scratch, scratch_n,
+                                               B * S * T, n_ctx);
+  return check_launch("conv_prologue");
 }
 
 int pixnorm_silu_fwd(const void* x, void* xn, void* act, long rows, int C, float eps, int mode, cudaStream_t st) {
@@ -690,10 +831,18 @@ int scale_silu_bwd(const void* y, const float* cscale, const void* g, void* dy, 
   const int cv = C / 8;
   const int cv_per_blk = cv < 32 ? cv : 32;
   if (256 % cv_per_blk != 0) { set_error("scale_silu_bwd: C/8=%d must divide 256 or be >=32", cv); return OB_ERR_UNSUPPORTED; }
-  dim3 grid((cv + cv_per_blk - 1) / cv_per_blk, frames);
+  const int pl = 256 / cv_per_blk;                       // pixel lanes per CTA
+  const int cgroups = (cv + cv_per_blk - 1) / cv_per_blk;
+  int chunks = (4 * 148 + cgroups * frames - 1) / (cgroups * frames);   // aim for ~4 CTAs per SM
+  const int max_chunks = (rows_per_frame + pl - 1) / pl;
+  if (chunks > max_chunks) chunks = max_chunks;
+  if (chunks < 1) chunks = 1;
+  const int rows_per_chunk = (rows_per_frame + chunks - 1) / chunks;
+  cudaMemsetAsync(dc, 0, static_cast<size_t>(frames) * C * sizeof(float), st);
+  dim3 grid(cgroups, chunks, frames);
   scale_silu_bwd_kernel<<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(y), cscale,
                                               static_cast<const __nv_bfloat16*>(g), static_cast<__nv_bfloat16*>(dy), dc, C,
-                                              rows_per_frame);
+                                              rows_per_frame, rows_per_chunk);
   return check_launch("scale_silu_bwd");
 }
 

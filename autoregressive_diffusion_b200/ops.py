@@ -159,17 +159,17 @@ class GatedConvFn(torch.autograd.Function):
         dev = x.device
         ab = torch.empty((2, f), dtype=torch.float32, device=dev)
         alpha, beta = ab[0], ab[1]
-        call("ob_gate_fwd", _vp(g_offset), _vp(g_mult), _vp(g_max), _vp(g_min), _vp(c_noise), _vp(alpha), _vp(beta), f, S * T, T,
-             n_ctx, stream_ptr())
+        scratch = torch.empty(2 * f + 1, dtype=torch.float32, device=dev) if want_grad else None
         cx = torch.empty((n_seq, T + 2, h, wd, cin_pad), dtype=BF16, device=dev)
-        call("ob_ctx_build", _vp(x), _vp(pad5), _vp(cx), n_seq, S, T, h * wd * cin_pad, cin, cin_pad, stream_ptr())
+        call("ob_conv_prologue", _vp(x), _vp(pad5), _vp(cx), n_seq, S, T, h * wd * cin_pad, cin, cin_pad, _vp(g_offset),
+             _vp(g_mult), _vp(g_max), _vp(g_min), _vp(c_noise), _vp(alpha), _vp(beta), _vp(scratch), n_ctx, stream_ptr())
         out = empty_rows(f, cout, h, wd, dev)
         out_d = empty_rows(f, cout, h, wd, dev, torch.float32) if want_grad else None
         ws = split_workspace(n_seq, S, T, h, wd, cin_pad, cout, 3, 1, dev)
         call("ob_conv_fwd", _vp(x), _vp(cx), _vp(wg), _vp(alpha), _vp(beta), _vp(out), _vp(out_d), _vp(ws), n_seq, S, T, h, wd,
              cin_pad, cout, 3, 1, 0, stream_ptr())
         if want_grad:
-            ctx.save_for_backward(x, cx, w2, w3, wg, ab, out, out_d, g_offset, g_mult, g_max, g_min, c_noise)
+            ctx.save_for_backward(x, cx, w2, w3, wg, ab, out, out_d, g_offset, g_mult, g_max, g_min, c_noise, scratch)
         ctx.dims = (n_seq, S, T, n_ctx)
         ctx.mark_non_differentiable(cx)
         y = out if cout == w2.shape[0] else out[:, : w2.shape[0]]
@@ -177,7 +177,7 @@ class GatedConvFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, gy, _gcx):
-        x, cx, w2, w3, wg, ab, y, d, g_offset, g_mult, g_max, g_min, c_noise = ctx.saved_tensors
+        x, cx, w2, w3, wg, ab, y, d, g_offset, g_mult, g_max, g_min, c_noise, scratch = ctx.saved_tensors
         n_seq, S, T, n_ctx = ctx.dims
         f, cin_pad, h, wd = x.shape
         cout, cin = wg.shape[0], w2.shape[1]
@@ -186,9 +186,12 @@ class GatedConvFn(torch.autograd.Function):
         gy = pad_channels(rows(gy), 8)
         gya = empty_rows(f, cout, h, wd, dev)
         gb = empty_rows(n_seq * T, cout, h, wd, dev)
-        sums = torch.zeros((2, f), dtype=torch.float32, device=dev)
-        call("ob_gate_bwd", _vp(gy), _vp(y), _vp(d), _vp(alpha), _vp(beta), _vp(gya), _vp(gb), _vp(sums[0]), _vp(sums[1]),
-             n_seq, S, T, h * wd * cout, stream_ptr())
+        want_gate = g_offset.requires_grad
+        call("ob_gate_bwd_fused", _vp(gy), _vp(y), _vp(d), _vp(alpha), _vp(beta), _vp(gya), _vp(gb), _vp(scratch), n_seq, S, T,
+             h * wd * cout, _vp(g_offset) if want_gate else None, _vp(g_mult), _vp(g_max), _vp(g_min), _vp(c_noise),
+             _vp(grad_buffer(g_offset)) if want_gate else None, _vp(grad_buffer(g_mult)) if want_gate else None,
+             _vp(grad_buffer(g_max)) if want_gate else None, _vp(grad_buffer(g_min)) if want_gate else None, n_ctx,
+             stream_ptr())
         dx = None
         if ctx.needs_input_grad[0]:
             dx = empty_rows(f, cin_pad, h, wd, dev)
@@ -201,10 +204,6 @@ class GatedConvFn(torch.autograd.Function):
             call("ob_conv_wgrad", _vp(gya), _vp(x), _vp(gb), _vp(cx), _vp(dwg), n_seq, S, T, h, wd, cin_pad, cout, 3, 1, ns,
                  stream_ptr())
             weight_grad([w2, w3], [9, 18], cin, cin_pad, [1.0, 1.0], dwg, ns)
-        if g_offset.requires_grad:
-            call("ob_gate_bwd_params", _vp(g_offset), _vp(g_mult), _vp(g_max), _vp(g_min), _vp(c_noise), _vp(alpha), _vp(beta),
-                 _vp(sums[0]), _vp(sums[1]), _vp(grad_buffer(g_offset)), _vp(grad_buffer(g_mult)), _vp(grad_buffer(g_max)),
-                 _vp(grad_buffer(g_min)), f, S * T, T, n_ctx, stream_ptr())
         return (dx,) + (None,) * 14
 
 

@@ -90,6 +90,18 @@ int ob_conv_wgrad(const void* gya, const void* x, const void* gb, const void* ct
 int ob_gate_bwd(const void* dy, const void* y, const void* d, const float* alpha, const float* beta, void* gya, void* gb,
                 float* s_y, float* s_d, int n_seq, int S, int T, int64_t frame_elems, void* stream);
 
+/* Fused variants used by the training path (same maths as the three calls they replace, fewer launches):
+ * ob_conv_prologue = ob_ctx_build + ob_gate_fwd + zeroing of `scratch` (fp32 [2*frames + 1], may be NULL in eval);
+ * ob_gate_bwd_fused = ob_gate_bwd with s_y = scratch, s_d = scratch + frames, and the last CTA to finish (ticket
+ * counter at scratch[2*frames]) doing the work of ob_gate_bwd_params. */
+int ob_conv_prologue(const void* x, const void* pad, void* ctx, int b, int S, int T, int64_t frame_elems, int cin,
+                     int cin_pad, const float* offset, const float* mult, const float* max_gating, const float* min_gating,
+                     const float* c_noise, float* alpha, float* beta, float* scratch, int n_ctx, void* stream);
+int ob_gate_bwd_fused(const void* dy, const void* y, const void* d, const float* alpha, const float* beta, void* gya,
+                      void* gb, float* scratch, int n_seq, int S, int T, int64_t frame_elems, const float* offset,
+                      const float* mult, const float* max_gating, const float* min_gating, const float* c_noise,
+                      float* g_offset, float* g_mult, float* g_max, float* g_min, int n_ctx, void* stream);
+
 /* edm2/conv.py:113-127 Gating.forward + the mp_sum weights of edm2/utils.py:122-123, one launch:
  * alpha[f] = (1-g)/sqrt((1-g)^2+g^2), beta[f] = g/sqrt(..); position of frame f = (f % T) % half + n_ctx where T is
  * the frames per batch row of c_noise [frames] and half = T/2 in training (clean+noised halves share positions). */
