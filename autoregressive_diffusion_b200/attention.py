@@ -99,6 +99,7 @@ class _QkvPrepFn(torch.autograd.Function):
              _vp(pos_k), n_rows, heads, hw, 1e-4, stream_ptr())
         ctx.save_for_backward(qkv, cos_t, sin_t, scl_t, pos_q, pos_k)
         ctx.cfg = (heads, hw)
+        ctx.set_materialize_grads(False)
         if want_raw:
             ctx.mark_non_differentiable(k_raw)
             return q, k, v, k_raw

@@ -28,6 +28,7 @@ struct Problem {
   int bmn;
   int halo;
   int split;   // give the launch a split-K workspace
+  int nopair;  // 1: forbid CTA-pair execution
 };
 
 // column of vertical taps at horizontal shift dx; flip mirrors the kernel (input-gradient form)
@@ -91,6 +92,7 @@ static bool run(const Problem& P, bool check, int reps) {
   L.n_seq = P.n_seq; L.n_out = P.n_out; L.T = P.T; L.H = P.H; L.W = P.W; L.Cin = P.Cin; L.Cout = P.Cout;
   L.epi = P.epi; L.out_f32 = P.out_f32; L.alpha = dal; L.beta = dbe; L.out = dOut;
   L.out_d = (P.epi == EPI_GATED) ? dD : nullptr; L.force_bn = P.force_bn; L.b_mn_major = P.bmn;
+  L.use_pair = P.nopair ? 0 : 1;
   float* dWs = nullptr;
   if (P.split) { cudaMalloc(&dWs, (size_t)n_acc * nout / P.n_out * 4); L.split_ws = dWs; }
 
@@ -232,6 +234,9 @@ int main(int argc, char** argv) {
     run(gated("CS 512->512 8x8 bn128", 2, 2, 16, 8, 8, 512, 512, 128), false, 20);
     run(gated("CS 512->512 8x8 bn64", 2, 2, 16, 8, 8, 512, 512, 64), false, 20);
     run(gated("CS 512->512 8x8 bn32", 2, 2, 16, 8, 8, 512, 512, 32), false, 20);
+    { Problem q = gated("CS 512->512 16x16 NOPAIR", 2, 2, 16, 16, 16, 512, 512); q.nopair = 1; run(q, false, 20); }
+    { Problem q = gated("CS 256->256 16x16 bn128 NOPAIR", 2, 2, 16, 16, 16, 256, 256, 128); q.nopair = 1; run(q, false, 20); }
+    { Problem q = plain("conv3x3 512->512 16x16 F64 bn256 NOPAIR", 64, 16, 16, 512, 512, 3, 0, 256); q.nopair = 1; run(q, false, 20); }
     run(gated("CS 512->512 8x8 split auto", 2, 2, 16, 8, 8, 512, 512, 0, 1), false, 20);
     run(gated("CS 512->512 8x8 split bn128", 2, 2, 16, 8, 8, 512, 512, 128, 1), false, 20);
     run(gated("CS 1024->512 8x8 split auto", 2, 2, 16, 8, 8, 1024, 512, 0, 1), false, 20);

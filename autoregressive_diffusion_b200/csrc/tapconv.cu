@@ -86,16 +86,47 @@ static int pow2_ceil(int v) {
 }
 
 template <int CHUNK, int BN, bool BMN>
+static int launch_pair(const TapConvParams& p, dim3 grid, cudaStream_t stream) {
+  using Cfg = TapConvCfg<CHUNK, BN>;
+  if constexpr (BN < 128 || CHUNK != 64) {
+    set_error("tapconv: pair mode needs tile N >= 128 and 64-channel chunks");
+    return OB_ERR_UNSUPPORTED;
+  } else {
+    constexpr int MAX_DYN = 226 * 1024;
+    static bool attr_set = false;
+    auto kern = tapconv_kernel<CHUNK, BN, BMN, true>;
+    if (!attr_set) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN);
+      if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(tapconv pair): %s", cudaGetErrorString(e)); return OB_ERR_CUDA; }
+      attr_set = true;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(TAPCONV_THREADS);
+    cfg.dynamicSmemBytes = 1024 + p.a_slots * p.a_slot_bytes + p.b_slots * (Cfg::B_BYTES_AL / 2) + 256;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, p);
+    if (e != cudaSuccess) { set_error("tapconv pair<%d,%d> launch: %s", CHUNK, BN, cudaGetErrorString(e)); return OB_ERR_CUDA; }
+    return OB_OK;
+  }
+}
+
+template <int CHUNK, int BN, bool BMN>
 static int launch_inst(const TapConvParams& p, dim3 grid, cudaStream_t stream) {
   using Cfg = TapConvCfg<CHUNK, BN>;
   if constexpr (BMN && (BN % CHUNK != 0)) {
     set_error("tapconv: MN-major weights need tile N %d to be a multiple of %d", BN, CHUNK);
     return OB_ERR_UNSUPPORTED;
   } else {
+    if (p.m_tiles_pad > 0) return launch_pair<CHUNK, BN, BMN>(p, grid, stream);
     constexpr int MAX_DYN = 226 * 1024;
     static bool attr_set = false;  // benign race: setting twice is harmless
     if (!attr_set) {
-      cudaError_t e = cudaFuncSetAttribute(tapconv_kernel<CHUNK, BN, BMN>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN);
+      cudaError_t e = cudaFuncSetAttribute(tapconv_kernel<CHUNK, BN, BMN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN);
       if (e != cudaSuccess) {
         set_error("cudaFuncSetAttribute(tapconv<%d,%d>, %d B): %s", CHUNK, BN, MAX_DYN, cudaGetErrorString(e));
         return OB_ERR_CUDA;
@@ -103,7 +134,7 @@ static int launch_inst(const TapConvParams& p, dim3 grid, cudaStream_t stream) {
       attr_set = true;
     }
     const int smem = 1024 + p.a_slots * p.a_slot_bytes + p.b_slots * Cfg::B_BYTES_AL + 256;
-    tapconv_kernel<CHUNK, BN, BMN><<<grid, TAPCONV_THREADS, smem, stream>>>(p);
+    tapconv_kernel<CHUNK, BN, BMN, false><<<grid, TAPCONV_THREADS, smem, stream>>>(p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
       set_error("tapconv<%d,%d> launch: %s", CHUNK, BN, cudaGetErrorString(e));
@@ -217,14 +248,19 @@ int tapconv_launch(const TapConvLaunch& L, cudaStream_t stream) {
   }
   p.tiles_n = (L.Cout + bn - 1) / bn;
 
+  // CTA pairs (cta_group::2) for the wide-N, 64-channel-chunk layers with at least one full pair of pixel tiles:
+  // each CTA of a pair stages only half of every weight tile
+  const bool pair = (L.use_pair != 0) && bn >= 128 && chunk == 64 && m_tiles >= 2;
+  p.m_tiles_pad = pair ? (m_tiles + 1) / 2 * 2 : 0;
+
   // ---- shared-memory rings
   const int rows_a = (p.bh + 2 * p.halo) * p.bt * p.bw;
   p.a_tile_bytes = rows_a * chunk * 2;
   p.a_slot_bytes = (L.n_out * p.a_tile_bytes + 1023) / 1024 * 1024;
-  const int b_al = (bn * chunk * 2 + 1023) / 1024 * 1024;
+  const int b_al = ((bn * chunk * 2 + 1023) / 1024 * 1024) / (pair ? 2 : 1);
   const int budget = 208 * 1024;
-  p.a_slots = 3;
-  if ((budget - p.a_slots * p.a_slot_bytes) / b_al < 4) p.a_slots = 2;   // keep at least 4 weight tiles in flight
+  p.a_slots = pair ? TAPCONV_MAX_A_SLOTS : 3;
+  while (p.a_slots > 2 && (budget - p.a_slots * p.a_slot_bytes) / b_al < 4) --p.a_slots;   // keep >= 4 weight tiles in flight
   p.b_slots = (budget - p.a_slots * p.a_slot_bytes) / b_al;
   if (p.b_slots > 8) p.b_slots = 8;
   if (p.b_slots < 2) {
@@ -246,7 +282,7 @@ int tapconv_launch(const TapConvLaunch& L, cudaStream_t stream) {
   if (!L.b_mn_major) {  // weights [Cout][w_taps*Cin]
     uint64_t dims[2] = {(uint64_t)L.w_taps * L.Cin, (uint64_t)L.Cout};
     uint64_t str[2] = {1, (uint64_t)L.w_taps * L.Cin};
-    uint32_t box[2] = {(uint32_t)chunk, (uint32_t)bn};
+    uint32_t box[2] = {(uint32_t)chunk, (uint32_t)(pair ? bn / 2 : bn)};
     int r = encode_tmap_bf16(&p.mapB, L.wg, 2, dims, str, box);
     if (r != OB_OK) return r;
   } else {  // weights [Cin][w_taps*Cout] (the forward matrix of the transposed problem)
@@ -284,7 +320,7 @@ int tapconv_launch(const TapConvLaunch& L, cudaStream_t stream) {
       if (e != cudaSuccess) { set_error("tapconv: workspace memset: %s", cudaGetErrorString(e)); return OB_ERR_CUDA; }
     }
   }
-  const dim3 grid(m_tiles * p.tiles_n, p.ksplit);
+  const dim3 grid(pair ? p.m_tiles_pad * p.tiles_n : m_tiles * p.tiles_n, p.ksplit);
   int rc;
   if (L.b_mn_major) {
     switch (chunk) {

@@ -61,6 +61,7 @@ struct TapConvParams {
   int a_slots;
   int b_slots;
   int tiles_w, tiles_h, tiles_t, tiles_n;
+  int m_tiles_pad;     // PAIR mode: pixel tiles rounded up to a multiple of 2 (blockIdx.x = m + m_tiles_pad*n)
   int n_out;    // output row sets per tile (2 in dual mode)
   int epi;      // EPI_*
   int out_f32;  // 0: bf16 out, 1: fp32 out
@@ -94,10 +95,16 @@ struct TapConvCfg {
 // BMN=false: weights are [N rows][K contiguous] (forward convs).  BMN=true: weights are [K rows][N contiguous],
 // i.e. the SAME forward weight matrix read as an MN-major B operand, which is what the input-gradient pass
 // needs -- no transposed weight copy is ever materialised.
-template <int CHUNK, int BN, bool BMN>
+// PAIR=true: launched as clusters of two CTAs that own two adjacent pixel tiles of the same channel tile and execute
+// ONE tcgen05.mma.cta_group::2 stream (M=256): each CTA stages its own activation tiles but only HALF of every weight
+// tile, which halves the weight traffic into shared memory and the shared-memory operand reads per FLOP -- the limit a
+// single-CTA M=128 x N=128 MMA runs into.
+template <int CHUNK, int BN, bool BMN, bool PAIR>
 __global__ void __launch_bounds__(TAPCONV_THREADS, 1) tapconv_kernel(const __grid_constant__ TapConvParams p) {
   using Cfg = TapConvCfg<CHUNK, BN>;
   static_assert(!BMN || BN % CHUNK == 0, "MN-major weights need BN to be a multiple of CHUNK");
+  static_assert(!PAIR || (BN >= 32 && (!BMN || (BN / 2) % CHUNK == 0)), "pair mode needs a splittable weight tile");
+  constexpr int B_STRIDE = PAIR ? Cfg::B_BYTES_AL / 2 : Cfg::B_BYTES_AL;   // weight bytes this CTA stages per tap
   constexpr uint32_t SWZ = SwizzleFor<CHUNK>::mode;
   constexpr uint32_t SBO = 8 * Cfg::ROW_BYTES;
   constexpr int MAXB = Cfg::MAX_B_SLOTS;
@@ -106,7 +113,7 @@ __global__ void __launch_bounds__(TAPCONV_THREADS, 1) tapconv_kernel(const __gri
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sA0 = smem_base;
   const uint32_t sB0 = sA0 + p.a_slots * p.a_slot_bytes;
-  const uint32_t bar_base = sB0 + p.b_slots * Cfg::B_BYTES_AL;
+  const uint32_t bar_base = sB0 + p.b_slots * B_STRIDE;
   // barriers: a_full[MAXA], a_empty[MAXA], b_full[MAXB], b_empty[MAXB], tmem_full, then the TMEM base address slot
   constexpr int MAXA = TAPCONV_MAX_A_SLOTS;
   auto a_full = [&](int s) { return bar_base + 8u * s; };
@@ -121,8 +128,11 @@ __global__ void __launch_bounds__(TAPCONV_THREADS, 1) tapconv_kernel(const __gri
 
   // ---- tile coordinates
   int tile = blockIdx.x;
-  const int n_tile = tile % p.tiles_n;
-  tile /= p.tiles_n;
+  int n_tile;
+  if constexpr (PAIR) { n_tile = tile / p.m_tiles_pad; tile -= n_tile * p.m_tiles_pad; }   // pixel tile fastest: pairs share n
+  else { n_tile = tile % p.tiles_n; tile /= p.tiles_n; }
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
   const int tw_i = tile % p.tiles_w;
   tile /= p.tiles_w;
   const int th_i = tile % p.tiles_h;
@@ -151,11 +161,12 @@ __global__ void __launch_bounds__(TAPCONV_THREADS, 1) tapconv_kernel(const __gri
     tma_prefetch_desc(&p.mapB);
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, tmem_cols);
-    tmem_relinquish();
+    if constexpr (PAIR) { tmem_alloc_pair(tmem_slot, tmem_cols); tmem_relinquish_pair(); }
+    else { tmem_alloc(tmem_slot, tmem_cols); tmem_relinquish(); }
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();   // the peer's barriers exist before anything is signalled across the pair
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
@@ -170,10 +181,17 @@ __global__ void __launch_bounds__(TAPCONV_THREADS, 1) tapconv_kernel(const __gri
       for (int ck = ck_lo; ck < ck_hi; ++ck) {
         mbar_wait(a_empty(as), aph ^ 1);
         if (elect_one()) {
-          mbar_arrive_expect_tx(a_full(as), col.n_a * p.a_tile_bytes);
-          for (int i = 0; i < col.n_a; ++i)
-            tma_load_5d(sA0 + as * p.a_slot_bytes + i * p.a_tile_bytes, mapA, a_full(as), ck * CHUNK, w0 + col.dx,
-                        t0 + col.dt, h0 - p.halo, seq * col.seq_mul + i);
+          if constexpr (PAIR) {
+            if (leader) mbar_arrive_expect_tx(a_full(as), 2 * col.n_a * p.a_tile_bytes);   // both CTAs' tiles
+            for (int i = 0; i < col.n_a; ++i)
+              tma_load_5d_pair(sA0 + as * p.a_slot_bytes + i * p.a_tile_bytes, mapA, a_full(as), ck * CHUNK, w0 + col.dx,
+                               t0 + col.dt, h0 - p.halo, seq * col.seq_mul + i);
+          } else {
+            mbar_arrive_expect_tx(a_full(as), col.n_a * p.a_tile_bytes);
+            for (int i = 0; i < col.n_a; ++i)
+              tma_load_5d(sA0 + as * p.a_slot_bytes + i * p.a_tile_bytes, mapA, a_full(as), ck * CHUNK, w0 + col.dx,
+                          t0 + col.dt, h0 - p.halo, seq * col.seq_mul + i);
+          }
         }
         __syncwarp();
         if (++as == p.a_slots) { as = 0; aph ^= 1; }
@@ -189,15 +207,28 @@ __global__ void __launch_bounds__(TAPCONV_THREADS, 1) tapconv_kernel(const __gri
         for (int d = 0; d < col.n_taps; ++d) {
           mbar_wait(b_empty(bs), bph ^ 1);
           if (elect_one()) {
-            const uint32_t sB = sB0 + bs * Cfg::B_BYTES_AL;
-            mbar_arrive_expect_tx(b_full(bs), Cfg::B_BYTES);
-            if constexpr (!BMN) {
-              tma_load_2d(sB, &p.mapB, b_full(bs), col.wtap[d] * p.Cin + ck * CHUNK, n0);
-            } else {
+            const uint32_t sB = sB0 + bs * B_STRIDE;
+            if constexpr (PAIR) {
+              // this CTA stages output channels [n0 + rank*BN/2, +BN/2) of the tile; the MMA reads both halves
+              if (leader) mbar_arrive_expect_tx(b_full(bs), Cfg::B_BYTES);
+              if constexpr (!BMN) {
+                tma_load_2d_pair(sB, &p.mapB, b_full(bs), col.wtap[d] * p.Cin + ck * CHUNK, n0 + rank * (BN / 2));
+              } else {
 #pragma unroll
-              for (int j = 0; j < BN / CHUNK; ++j)
-                tma_load_2d(sB + j * (CHUNK * Cfg::ROW_BYTES), &p.mapB, b_full(bs), col.wtap[d] * p.Cout + n0 + j * CHUNK,
-                            ck * CHUNK);
+                for (int j = 0; j < BN / 2 / CHUNK; ++j)
+                  tma_load_2d_pair(sB + j * (CHUNK * Cfg::ROW_BYTES), &p.mapB, b_full(bs),
+                                   col.wtap[d] * p.Cout + n0 + rank * (BN / 2) + j * CHUNK, ck * CHUNK);
+              }
+            } else {
+              mbar_arrive_expect_tx(b_full(bs), Cfg::B_BYTES);
+              if constexpr (!BMN) {
+                tma_load_2d(sB, &p.mapB, b_full(bs), col.wtap[d] * p.Cin + ck * CHUNK, n0);
+              } else {
+#pragma unroll
+                for (int j = 0; j < BN / CHUNK; ++j)
+                  tma_load_2d(sB + j * (CHUNK * Cfg::ROW_BYTES), &p.mapB, b_full(bs), col.wtap[d] * p.Cout + n0 + j * CHUNK,
+                              ck * CHUNK);
+              }
             }
           }
           __syncwarp();
@@ -209,13 +240,14 @@ __global__ void __launch_bounds__(TAPCONV_THREADS, 1) tapconv_kernel(const __gri
     // ===================== MMA issuer =====================
     // The whole warp walks the (warp-uniform) loop; one elected lane issues.  Descriptors differ only in their
     // 14-bit start-address field, so they are formed by adding to a base descriptor.
-    constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, BMN ? 1 : 0);
+    constexpr uint32_t idesc = make_idesc_bf16(PAIR ? 256 : 128, BN, 0, BMN ? 1 : 0);
     const uint64_t adesc0 = make_smem_desc(0, 16, SBO, SWZ);
     const uint64_t bdesc0 = BMN ? make_smem_desc(0, CHUNK * Cfg::ROW_BYTES, SBO, SWZ) : make_smem_desc(0, 16, SBO, SWZ);
     constexpr uint32_t B_KSTEP = BMN ? (2 * SBO) >> 4 : 32 >> 4;   // descriptor units of 16 bytes
     int as = 0, bs = 0;
     uint32_t aph = 0, bph = 0;
     uint32_t started = 0;  // bit j: accumulator j already holds a partial sum
+    if (leader) {          // in pair mode the peer's MMA warp only owns its half of the TMEM allocation
     for (int ic = 0; ic < p.n_cols; ++ic) {
       const TapCol col = p.cols[ic];
       for (int ck = ck_lo; ck < ck_hi; ++ck) {
@@ -224,7 +256,7 @@ __global__ void __launch_bounds__(TAPCONV_THREADS, 1) tapconv_kernel(const __gri
         for (int d = 0; d < col.n_taps; ++d) {
           mbar_wait(b_full(bs), bph);
           tc_fence_after();
-          const uint64_t bdesc = bdesc0 + ((sB0 + bs * Cfg::B_BYTES_AL) >> 4);
+          const uint64_t bdesc = bdesc0 + ((sB0 + bs * B_STRIDE) >> 4);
           if (elect_one()) {
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
@@ -232,24 +264,31 @@ __global__ void __launch_bounds__(TAPCONV_THREADS, 1) tapconv_kernel(const __gri
                 const int acc = col.acc + i;
                 const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
                 const uint64_t adesc = adesc0 + ((sA + i * p.a_tile_bytes + d * dy_stride) >> 4);
-                umma_bf16_ss(d_tmem, adesc, bdesc, idesc, (started >> acc) & 1u);
+                if constexpr (PAIR) {
+                  umma_bf16_ss_pair(d_tmem, adesc, bdesc, idesc, (started >> acc) & 1u);
 #pragma unroll
-                for (int k = 1; k < CHUNK / 16; ++k) umma_bf16_ss(d_tmem, adesc + 2 * k, bdesc + B_KSTEP * k, idesc, 1u);
+                  for (int k = 1; k < CHUNK / 16; ++k) umma_bf16_ss_pair(d_tmem, adesc + 2 * k, bdesc + B_KSTEP * k, idesc, 1u);
+                } else {
+                  umma_bf16_ss(d_tmem, adesc, bdesc, idesc, (started >> acc) & 1u);
+#pragma unroll
+                  for (int k = 1; k < CHUNK / 16; ++k) umma_bf16_ss(d_tmem, adesc + 2 * k, bdesc + B_KSTEP * k, idesc, 1u);
+                }
               }
             }
-            umma_commit(b_empty(bs));  // frees the weight slot once these MMAs retire
+            if constexpr (PAIR) umma_commit_pair(b_empty(bs)); else umma_commit(b_empty(bs));  // frees the weight slot(s)
           }
           __syncwarp();
           started |= ((1u << col.n_a) - 1u) << col.acc;
           if (++bs == p.b_slots) { bs = 0; bph ^= 1; }
         }
-        if (elect_one()) umma_commit(a_empty(as));  // ... and the activation slot after its last tap
+        if (elect_one()) { if constexpr (PAIR) umma_commit_pair(a_empty(as)); else umma_commit(a_empty(as)); }
         __syncwarp();
         if (++as == p.a_slots) { as = 0; aph ^= 1; }
       }
     }
-    if (elect_one()) umma_commit(tmem_full_bar);  // all accumulators final
+    if (elect_one()) { if constexpr (PAIR) umma_commit_pair(tmem_full_bar); else umma_commit(tmem_full_bar); }
     __syncwarp();
+    }
   } else {
     // ===================== epilogue (warps 3..6) =====================
     constexpr int CW = Cfg::CW;
@@ -260,7 +299,7 @@ __global__ void __launch_bounds__(TAPCONV_THREADS, 1) tapconv_kernel(const __gri
     const int tt = rem / p.bw;
     const int ww = rem - tt * p.bw;
     const int t = t0 + tt, h = h0 + hh, w = w0 + ww;
-    const bool row_ok = (t < p.T) && (h < p.H) && (w < p.W);
+    const bool row_ok = (t < p.T) && (h < p.H) && (w < p.W) && (seq < p.n_seq);
 
     mbar_wait_sleep(tmem_full_bar, 0);
     tc_fence_after();
@@ -343,9 +382,10 @@ __global__ void __launch_bounds__(TAPCONV_THREADS, 1) tapconv_kernel(const __gri
   }
 
   __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();   // the peer has consumed every multicast arrival and drained its accumulators
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, tmem_cols);
+    if constexpr (PAIR) tmem_dealloc_pair(tmem_base, tmem_cols); else tmem_dealloc(tmem_base, tmem_cols);
   }
 }
 

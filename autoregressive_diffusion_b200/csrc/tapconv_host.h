@@ -37,6 +37,7 @@ struct TapConvLaunch {
   int force_bn = 0;  // test hook: pin the N tile
   int b_mn_major = 0;  // weights given as [Cin][w_taps][Cout] (input-gradient passes)
   float* split_ws = nullptr;   // optional fp32 workspace enabling split-K (size from tapconv_plan)
+  int use_pair = 1;            // allow CTA-pair (cta_group::2) execution where the shape qualifies
 };
 
 // Split-K plan for a problem: number of channel-chunk slices and the fp32 workspace they need (0 = no split).

@@ -172,6 +172,7 @@ class GatedConvFn(torch.autograd.Function):
             ctx.save_for_backward(x, cx, w2, w3, wg, ab, out, out_d, g_offset, g_mult, g_max, g_min, c_noise, scratch)
         ctx.dims = (n_seq, S, T, n_ctx)
         ctx.mark_non_differentiable(cx)
+        ctx.set_materialize_grads(False)   # otherwise autograd zero-fills a context-sized tensor per layer for cx
         y = out if cout == w2.shape[0] else out[:, : w2.shape[0]]
         return y, cx
 
@@ -179,6 +180,8 @@ class GatedConvFn(torch.autograd.Function):
     def backward(ctx, gy, _gcx):
         x, cx, w2, w3, wg, ab, y, d, g_offset, g_mult, g_max, g_min, c_noise, scratch = ctx.saved_tensors
         n_seq, S, T, n_ctx = ctx.dims
+        if gy is None:
+            return (None,) * 15
         f, cin_pad, h, wd = x.shape
         cout, cin = wg.shape[0], w2.shape[1]
         dev = x.device
@@ -222,6 +225,7 @@ class PixnormSiluFn(torch.autograd.Function):
         call("ob_pixnorm_silu_fwd", _vp(x), _vp(xn), _vp(act), f * h * w, c, eps, mode, stream_ptr())
         ctx.save_for_backward(x)
         ctx.mode, ctx.eps = mode, eps
+        ctx.set_materialize_grads(False)
         if mode == 0:
             return xn, act
         return act
@@ -234,6 +238,8 @@ class PixnormSiluFn(torch.autograd.Function):
             g_xn, g_act = grads
         else:
             g_xn, g_act = None, grads[0]
+        if g_act is None and g_xn is None:
+            return None, None, None
         g_act = rows(g_act) if g_act is not None else torch.zeros_like(x, memory_format=CL)
         g_xn = rows(g_xn) if g_xn is not None else None
         dx = torch.empty_like(x, memory_format=CL)
