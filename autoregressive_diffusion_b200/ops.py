@@ -90,6 +90,63 @@ def weight_grad(params, taps, cin, cin_pad, gains, dwg, n_split, eps=1e-4):
 _CONST = {}
 
 
+class WeightGradBranch:
+    """Second CUDA stream for the weight-gradient branch of every conv backward (ob_conv_wgrad + ob_wnorm_bwd).
+
+    The input-gradient chain (gate pre-pass -> dgrad -> elementwise backward) is the critical path of the backward
+    pass; the weight gradients only have to be complete when the pass ends.  Forking them lets the HBM-bound weight-norm
+    backward and the under-filled small-layer wgrad launches run beside the tensor-core-bound dgrad kernels.  Fork and
+    join are event edges, so the same code is captured into a CUDA graph as two parallel branches.
+
+    Tensors the branch reads were allocated on the main stream; they are kept referenced until the main stream has
+    waited on the branch (two layers later, or at the end of the backward pass) so the caching allocator cannot hand
+    their blocks to a main-stream kernel while the branch still reads them.
+    """
+
+    enabled = True
+    _streams = {}
+    _pending = []          # [(done_event, tensors)] in launch order
+    _join_queued = False
+
+    @classmethod
+    def stream(cls, device):
+        key = torch.device(device).index
+        if key not in cls._streams:
+            cls._streams[key] = torch.cuda.Stream(device=device)
+        return cls._streams[key]
+
+    @classmethod
+    def run(cls, device, keep, fn):
+        """Run fn() on the branch stream after everything enqueued so far on the current stream."""
+        if not cls.enabled:
+            fn()
+            return
+        main = torch.cuda.current_stream(device)
+        side = cls.stream(device)
+        while len(cls._pending) >= 2:      # retire old launches: orders later main-stream reuse of their inputs
+            done, _ = cls._pending.pop(0)
+            main.wait_event(done)
+        fork = torch.cuda.Event()
+        fork.record(main)
+        side.wait_event(fork)
+        with torch.cuda.stream(side):
+            fn()
+            done = torch.cuda.Event()
+            done.record(side)
+        cls._pending.append((done, keep))
+        if not cls._join_queued:
+            cls._join_queued = True
+            torch.autograd.Variable._execution_engine.queue_callback(lambda: cls.join(device))
+
+    @classmethod
+    def join(cls, device):
+        """Make the current stream wait for the branch (runs automatically at the end of every backward pass)."""
+        cls._join_queued = False
+        if cls._pending:
+            torch.cuda.current_stream(device).wait_stream(cls.stream(device))
+            cls._pending.clear()
+
+
 def split_workspace(n_seq, S, T, h, w, cin, cout, ksize, gated, device):
     """fp32 scratch for a split-K conv launch, or None when the layer fills the GPU without it."""
     nbytes = query("ob_conv_split_ws_bytes", n_seq, S, T, h, w, cin, cout, ksize, gated)
@@ -139,10 +196,16 @@ class PlainConvFn(torch.autograd.Function):
             call("ob_conv_dgrad", _vp(gy), None, _vp(wg), None, None, _vp(dx), _vp(ws), 1, 1, f, h, wd, cin_pad, cout, k, 0,
                  stream_ptr())
         if w.requires_grad:
-            ns = query("ob_conv_wgrad_splits", 1, 1, f, h, wd, cin_pad, cout, k, 0)
-            dwg = torch.empty((ns, cout, k * k, cin_pad), dtype=torch.float32, device=x.device)
-            call("ob_conv_wgrad", _vp(gy), _vp(x), None, None, _vp(dwg), 1, 1, f, h, wd, cin_pad, cout, k, 0, ns, stream_ptr())
-            weight_grad([w], [k * k], cin, cin_pad, [ctx.gain], dwg, ns)
+            gain = ctx.gain
+
+            def branch():
+                ns = query("ob_conv_wgrad_splits", 1, 1, f, h, wd, cin_pad, cout, k, 0)
+                dwg = torch.empty((ns, cout, k * k, cin_pad), dtype=torch.float32, device=x.device)
+                call("ob_conv_wgrad", _vp(gy), _vp(x), None, None, _vp(dwg), 1, 1, f, h, wd, cin_pad, cout, k, 0, ns,
+                     stream_ptr())
+                weight_grad([w], [k * k], cin, cin_pad, [gain], dwg, ns)
+
+            WeightGradBranch.run(x.device, (gy, x), branch)
         return dx, None, None, None, None, None
 
 
@@ -195,18 +258,22 @@ class GatedConvFn(torch.autograd.Function):
              _vp(grad_buffer(g_offset)) if want_gate else None, _vp(grad_buffer(g_mult)) if want_gate else None,
              _vp(grad_buffer(g_max)) if want_gate else None, _vp(grad_buffer(g_min)) if want_gate else None, n_ctx,
              stream_ptr())
+        if w2.requires_grad or w3.requires_grad:   # forked first: it only needs the gate pre-pass
+
+            def branch():
+                ns = query("ob_conv_wgrad_splits", n_seq, S, T, h, wd, cin_pad, cout, 3, 1)
+                dwg = torch.empty((ns, cout, 27, cin_pad), dtype=torch.float32, device=dev)
+                call("ob_conv_wgrad", _vp(gya), _vp(x), _vp(gb), _vp(cx), _vp(dwg), n_seq, S, T, h, wd, cin_pad, cout, 3, 1,
+                     ns, stream_ptr())
+                weight_grad([w2, w3], [9, 18], cin, cin_pad, [1.0, 1.0], dwg, ns)
+
+            WeightGradBranch.run(dev, (gya, gb, x, cx), branch)
         dx = None
         if ctx.needs_input_grad[0]:
             dx = empty_rows(f, cin_pad, h, wd, dev)
             ws = split_workspace(n_seq, S, T, h, wd, cout, cin_pad, 3, 1, dev)
             call("ob_conv_dgrad", _vp(gy), _vp(gb), _vp(wg), _vp(alpha), _vp(clean_rows_mask(n_seq, S, T, dev)), _vp(dx),
                  _vp(ws), n_seq, S, T, h, wd, cin_pad, cout, 3, 1, stream_ptr())
-        if w2.requires_grad or w3.requires_grad:
-            ns = query("ob_conv_wgrad_splits", n_seq, S, T, h, wd, cin_pad, cout, 3, 1)
-            dwg = torch.empty((ns, cout, 27, cin_pad), dtype=torch.float32, device=dev)
-            call("ob_conv_wgrad", _vp(gya), _vp(x), _vp(gb), _vp(cx), _vp(dwg), n_seq, S, T, h, wd, cin_pad, cout, 3, 1, ns,
-                 stream_ptr())
-            weight_grad([w2, w3], [9, 18], cin, cin_pad, [1.0, 1.0], dwg, ns)
         return (dx,) + (None,) * 14
 
 
