@@ -67,8 +67,8 @@ int ob_wnorm_bwd(const float* w, const float* dwg, float* dw, int cout, int cin,
 
 int64_t ob_conv_split_ws_bytes(int n_seq, int S, int T, int H, int W, int cin, int cout, int ksize, int gated) {
   int ks; long wsb;
-  if (gated) tapconv_plan(n_seq, S, 1, T, H, W, cin, cout, &ks, &wsb);
-  else tapconv_plan(1, 1, 0, n_seq * S * T, H, W, cin, cout, &ks, &wsb);
+  if (gated) tapconv_plan(n_seq, S, 1, 27, T, H, W, cin, cout, &ks, &wsb);
+  else tapconv_plan(1, 1, 0, ksize * ksize, n_seq * S * T, H, W, cin, cout, &ks, &wsb);
   return (int64_t)wsb;
 }
 

@@ -6,6 +6,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
+#include <algorithm>
+#include <climits>
 #include "tapconv.cuh"
 #include "tapconv_host.h"
 
@@ -158,6 +160,32 @@ static bool run(const Problem& P, bool check, int reps) {
     double flops = 0;
     for (const TapCol& it : P.cols) flops += 2.0 * it.n_taps * it.n_a * P.n_seq * P.T * P.H * P.W * (double)P.Cin * P.Cout;
     printf("[%s] time %.1f us  %.1f TFLOP/s  (%.3f GFLOP)\n", P.name, ms * 1e3, flops / ms / 1e9, flops / 1e9);
+    if (getenv("TAPCONV_TRACE")) {
+      const int max_ctas = 1 << 16;
+      long long* dT; cudaMalloc(&dT, (size_t)max_ctas * 8 * 8); cudaMemset(dT, 0, (size_t)max_ctas * 8 * 8);
+      L.trace = dT;
+      tapconv_launch(L, 0); cudaDeviceSynchronize();
+      L.trace = nullptr;
+      std::vector<long long> hT((size_t)max_ctas * 8);
+      cudaMemcpy(hT.data(), dT, hT.size() * 8, cudaMemcpyDeviceToHost);
+      long long tmin = LLONG_MAX, tmax = 0; int n = 0;
+      for (int i = 0; i < max_ctas; ++i) if (hT[i * 8]) { tmin = std::min(tmin, hT[i * 8]); ++n; }
+      double s01 = 0, s12 = 0, s23 = 0, s34 = 0; int n2 = 0, n34 = 0;
+      std::vector<double> starts;
+      for (int i = 0; i < max_ctas; ++i) {
+        const long long* t = &hT[i * 8];
+        if (!t[0]) continue;
+        starts.push_back((t[0] - tmin) * 1e-3);
+        if (t[2]) { s01 += t[1] - t[0]; s12 += t[2] - t[1]; s23 += t[3] - t[2]; ++n2; }
+        if (t[3] && t[4]) { s34 += t[4] - t[3]; ++n34; tmax = std::max(tmax, t[4]); }
+      }
+      std::sort(starts.begin(), starts.end());
+      printf("  trace: %d CTAs (%d leaders)  setup->first tile %.2f us  mainloop issue %.2f us  drain %.2f us  epilogue %.2f us  span %.1f us\n",
+             n, n2, s01 / n2 * 1e-3, s12 / n2 * 1e-3, s23 / n2 * 1e-3, s34 / n34 * 1e-3, (tmax - tmin) * 1e-3);
+      printf("  CTA start times (us): p0 %.1f p25 %.1f p50 %.1f p60 %.1f p75 %.1f p90 %.1f p100 %.1f\n", starts[0], starts[n / 4], starts[n / 2],
+             starts[n * 6 / 10], starts[n * 3 / 4], starts[n * 9 / 10], starts[n - 1]);
+      cudaFree(dT);
+    }
   }
   for (int s = 0; s < 2; ++s) cudaFree(dA[s]);
   cudaFree(dW); cudaFree(dal); cudaFree(dbe); cudaFree(dOut); cudaFree(dD);
@@ -200,6 +228,14 @@ static Problem dgrad(const char* name, int B, int n, int H, int W, int Cin, int 
 int main(int argc, char** argv) {
   bool perf = argc > 1 && atoi(argv[1]) > 0;
   int fails = 0;
+  if (argc > 1 && atoi(argv[1]) == 2) {   // a short list for ncu captures
+    run(gated("CS 128->128 32x32 B2 n16", 2, 2, 16, 32, 32, 128, 128), false, 2);
+    run(gated("CS 512->512 16x16 B2 n16", 2, 2, 16, 16, 16, 512, 512), false, 2);
+    run(plain("1x1 256->128 32x32 F64", 64, 32, 32, 256, 128, 1, 0), false, 2);
+    run(gated("CS 512->512 8x8 split auto", 2, 2, 16, 8, 8, 512, 512, 0, 1), false, 2);
+    run(dgrad("dgrad BMN 128->128 32x32 B2 n16", 2, 16, 32, 32, 128, 128, 1), false, 2);
+    return 0;
+  }
   fails += !run(plain("gemm1x1 c64 n128 16x16 f32", 4, 16, 16, 64, 128, 1, 1), true, 0);
   fails += !run(plain("gemm1x1 c128 n64 16x16", 4, 16, 16, 128, 64, 1, 0), true, 0);
   fails += !run(plain("conv3x3 c64 n64 8x8 T6", 6, 8, 8, 64, 64, 3, 0), true, 0);
@@ -249,6 +285,13 @@ int main(int argc, char** argv) {
     run(gated("CS 512->512 4x4 bn64", 2, 2, 16, 4, 4, 512, 512, 64), false, 20);
     run(gated("CS 512->512 4x4 bn32", 2, 2, 16, 4, 4, 512, 512, 32), false, 20);
     run(plain("gemm 16384x512x1536", 64, 16, 16, 512, 1536, 1, 0), false, 20);
+    for (int bnf : {0, 256, 128, 64}) {
+      { Problem q = plain("1x1 512->512 4x4 F64", 64, 4, 4, 512, 512, 1, 0, bnf); q.split = 1; printf("bn=%d ", bnf); run(q, false, 20); }
+      { Problem q = plain("1x1 512->1536 4x4 F64", 64, 4, 4, 512, 1536, 1, 0, bnf); q.split = 1; printf("bn=%d ", bnf); run(q, false, 20); }
+      { Problem q = plain("1x1 512->512 8x8 F64", 64, 8, 8, 512, 512, 1, 0, bnf); q.split = 1; printf("bn=%d ", bnf); run(q, false, 20); }
+      { Problem q = plain("1x1 512->1536 8x8 F64", 64, 8, 8, 512, 1536, 1, 0, bnf); q.split = 1; printf("bn=%d ", bnf); run(q, false, 20); }
+      { Problem q = plain("1x1 256->128 32x32 F64", 64, 32, 32, 256, 128, 1, 0, bnf); q.split = 1; printf("bn=%d ", bnf); run(q, false, 20); }
+    }
     run(plain("gemm 16384x512x512 bn128", 64, 16, 16, 512, 512, 1, 0, 128), false, 20);
     run(plain("conv3x3 512->512 16x16 F64 bn256", 64, 16, 16, 512, 512, 3, 0, 256), false, 20);
     run(plain("conv3x3 512->512 16x16 F64 bn128", 64, 16, 16, 512, 512, 3, 0, 128), false, 20);

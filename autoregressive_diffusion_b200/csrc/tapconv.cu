@@ -168,7 +168,7 @@ static void tile_shape(int H, int W, int* bw, int* bh, int* bt) {
 // Tile-N and split-K policy.  Wide N keeps the MMA off the shared-memory read limit (N=64 re-reads the activation
 // tile twice as often per FLOP), so when a layer has too few output tiles for 148 SMs the first remedy is to slice
 // its K loop (channel chunks) over extra CTAs, and only then to narrow N.
-static void pick_tiling(int n_acc, int Cout, int Cin, int chunk, int m_tiles, int force_bn, int b_mn_major, bool can_split,
+static void pick_tiling(int n_acc, int Cout, int Cin, int chunk, int taps, int m_tiles, int force_bn, int b_mn_major, bool can_split,
                         int* bn_out, int* ks_out) {
   const int bn_max = (n_acc == 3) ? 128 : 256;
   int bn = pow2_ceil(Cout) < 16 ? 16 : pow2_ceil(Cout);
@@ -177,7 +177,8 @@ static void pick_tiling(int n_acc, int Cout, int Cin, int chunk, int m_tiles, in
   auto split_for = [&](int b) {
     const int tiles = m_tiles * ((Cout + b - 1) / b);
     int ks = 1;
-    if (can_split && tiles <= 74 && n_chunks >= 4 && Cout % 4 == 0) {
+    // a split launch costs a memset and a finishing kernel: only worth it when the K loop is long (3x3 / 3x3x3 taps)
+    if (can_split && tiles <= 74 && n_chunks >= 4 && n_chunks * taps >= 48 && Cout % 4 == 0) {
       ks = 148 / tiles;
       if (ks > n_chunks / 2) ks = n_chunks / 2;   // at least two chunks per slice
       if (ks > 8) ks = 8;
@@ -200,14 +201,14 @@ static void pick_tiling(int n_acc, int Cout, int Cin, int chunk, int m_tiles, in
 
 // Small-spatial layers (the 4x4 / 8x8 levels) have too few output tiles to occupy 148 SMs while their K loop is
 // hundreds of steps long: slice the channel chunks over blockIdx.y and reduce in an fp32 workspace.
-void tapconv_plan(int n_seq, int n_out, int gated, int T, int H, int W, int Cin, int Cout, int* ksplit, long* ws_bytes) {
+void tapconv_plan(int n_seq, int n_out, int gated, int taps, int T, int H, int W, int Cin, int Cout, int* ksplit, long* ws_bytes) {
   int bw, bh, bt;
   tile_shape(H, W, &bw, &bh, &bt);
   const int m_tiles = n_seq * ((T + bt - 1) / bt) * ((H + bh - 1) / bh) * ((W + bw - 1) / bw);
   const int n_acc = n_out + (gated ? 1 : 0);
   const int chunk = (Cin % 64 == 0) ? 64 : (Cin % 32 == 0) ? 32 : 16;
   int bn, ks;
-  pick_tiling(n_acc, Cout, Cin, chunk, m_tiles, 0, 0, true, &bn, &ks);
+  pick_tiling(n_acc, Cout, Cin, chunk, taps, m_tiles, 0, 0, true, &bn, &ks);
   *ksplit = ks;
   *ws_bytes = ks > 1 ? static_cast<long>(n_acc) * n_seq * T * H * W * Cout * 4 : 0;
 }
@@ -241,7 +242,9 @@ int tapconv_launch(const TapConvLaunch& L, cudaStream_t stream) {
 
   // ---- tile N: as wide as TMEM allows, narrowed while the grid cannot fill the 148 SMs
   int bn, ks_plan;
-  pick_tiling(n_acc, L.Cout, L.Cin, chunk, m_tiles, L.force_bn, L.b_mn_major, L.split_ws != nullptr, &bn, &ks_plan);
+  int taps = 0;
+  for (int i = 0; i < L.n_cols; ++i) taps += static_cast<const TapCol*>(L.cols)[i].n_taps;
+  pick_tiling(n_acc, L.Cout, L.Cin, chunk, taps, m_tiles, L.force_bn, L.b_mn_major, L.split_ws != nullptr, &bn, &ks_plan);
   if (n_acc * bn > 512) {
     set_error("tapconv: %d accumulators x N=%d exceed TMEM", n_acc, bn);
     return OB_ERR_INVALID;
@@ -266,6 +269,15 @@ int tapconv_launch(const TapConvLaunch& L, cudaStream_t stream) {
   if (p.b_slots < 2) {
     set_error("tapconv: shared memory cannot hold the rings (A slot %d B, B tile %d B)", p.a_slot_bytes, b_al);
     return OB_ERR_UNSUPPORTED;
+  }
+
+  {
+    // short K loops (1x1 kernels) never fill the rings: shrink them to the loop length so that two CTAs fit on an SM
+    // and one's epilogue overlaps the other's loads
+    const int n_chunks = (L.Cin + chunk - 1) / chunk;
+    const int per_cta = (n_chunks + (L.split_ws != nullptr ? ks_plan : 1) - 1) / (L.split_ws != nullptr ? ks_plan : 1);
+    if (p.a_slots > L.n_cols * per_cta) p.a_slots = L.n_cols * per_cta;
+    if (p.b_slots > taps * per_cta) p.b_slots = taps * per_cta;
   }
 
   // ---- tensor maps: activations as (C, W, T, H, SEQ) so that the tile's rows come out ordered (hh, tt, ww)
@@ -308,6 +320,7 @@ int tapconv_launch(const TapConvLaunch& L, cudaStream_t stream) {
   p.n_out = L.n_out; p.epi = L.epi; p.out_f32 = L.out_f32;
   p.alpha = L.alpha; p.beta = L.beta; p.out = L.out; p.out_d = L.out_d;
 
+  p.trace = L.trace;
   p.ksplit = 1;
   p.split_ws = nullptr;
   if (L.split_ws != nullptr) {

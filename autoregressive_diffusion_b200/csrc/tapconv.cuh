@@ -70,6 +70,7 @@ struct TapConvParams {
   void* out;    // [n_seq*n_out*T, H, W, Cout]
   void* out_d;  // optional (EPI_GATED): shared - own accumulator, fp32, same shape as out
   int ksplit;   // >1: blockIdx.y owns a slice of the channel chunks; raw accumulators are reduced into split_ws
+  long long* trace;   // optional [grid.x*grid.y][8] globaltimer stamps (probe builds only; nullptr in production)
   float* split_ws;  // [n_acc][n_seq*n_out*T*H*W][Cout] fp32, zeroed by the host (shared acc uses rows of set 0)
 };
 
@@ -99,6 +100,14 @@ struct TapConvCfg {
 // ONE tcgen05.mma.cta_group::2 stream (M=256): each CTA stages its own activation tiles but only HALF of every weight
 // tile, which halves the weight traffic into shared memory and the shared-memory operand reads per FLOP -- the limit a
 // single-CTA M=128 x N=128 MMA runs into.
+__device__ __forceinline__ long long global_ns() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define TAPCONV_STAMP(slot) \
+  do { if (p.trace != nullptr && lane == 0) p.trace[(static_cast<long>(blockIdx.y) * gridDim.x + blockIdx.x) * 8 + (slot)] = global_ns(); } while (0)
+
 template <int CHUNK, int BN, bool BMN, bool PAIR>
 __global__ void __launch_bounds__(TAPCONV_THREADS, 1) tapconv_kernel(const __grid_constant__ TapConvParams p) {
   using Cfg = TapConvCfg<CHUNK, BN>;
@@ -170,6 +179,7 @@ __global__ void __launch_bounds__(TAPCONV_THREADS, 1) tapconv_kernel(const __gri
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  if (warp == 1) TAPCONV_STAMP(0);   // setup done
 
   if (warp == 0) {
     // ===================== activation (A) TMA producer (warp-uniform loop, one elected lane issues) ============
@@ -252,6 +262,7 @@ __global__ void __launch_bounds__(TAPCONV_THREADS, 1) tapconv_kernel(const __gri
       const TapCol col = p.cols[ic];
       for (int ck = ck_lo; ck < ck_hi; ++ck) {
         mbar_wait(a_full(as), aph);
+        if (ic == 0 && ck == ck_lo) TAPCONV_STAMP(1);   // first activation tile landed
         const uint32_t sA = sA0 + as * p.a_slot_bytes;
         for (int d = 0; d < col.n_taps; ++d) {
           mbar_wait(b_full(bs), bph);
@@ -288,6 +299,7 @@ __global__ void __launch_bounds__(TAPCONV_THREADS, 1) tapconv_kernel(const __gri
     }
     if (elect_one()) { if constexpr (PAIR) umma_commit_pair(tmem_full_bar); else umma_commit(tmem_full_bar); }
     __syncwarp();
+    TAPCONV_STAMP(2);   // all MMAs issued
     }
   } else {
     // ===================== epilogue (warps 3..6) =====================
@@ -303,6 +315,7 @@ __global__ void __launch_bounds__(TAPCONV_THREADS, 1) tapconv_kernel(const __gri
 
     mbar_wait_sleep(tmem_full_bar, 0);
     tc_fence_after();
+    if (warp == 3) TAPCONV_STAMP(3);   // accumulators complete
 
     const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     if (p.ksplit > 1) {
@@ -379,6 +392,7 @@ __global__ void __launch_bounds__(TAPCONV_THREADS, 1) tapconv_kernel(const __gri
       }
     }
     tc_fence_before();
+    if (warp == 3) TAPCONV_STAMP(4);   // epilogue stores issued
   }
 
   __syncthreads();

@@ -37,11 +37,12 @@ struct TapConvLaunch {
   int force_bn = 0;  // test hook: pin the N tile
   int b_mn_major = 0;  // weights given as [Cin][w_taps][Cout] (input-gradient passes)
   float* split_ws = nullptr;   // optional fp32 workspace enabling split-K (size from tapconv_plan)
+  long long* trace = nullptr;  // probe only: per-CTA globaltimer stamps [ctas][8]
   int use_pair = 1;            // allow CTA-pair (cta_group::2) execution where the shape qualifies
 };
 
 // Split-K plan for a problem: number of channel-chunk slices and the fp32 workspace they need (0 = no split).
-void tapconv_plan(int n_seq, int n_out, int gated, int T, int H, int W, int Cin, int Cout, int* ksplit, long* ws_bytes);
+void tapconv_plan(int n_seq, int n_out, int gated, int taps, int T, int H, int W, int Cin, int Cout, int* ksplit, long* ws_bytes);
 
 int tapconv_launch(const TapConvLaunch& L, cudaStream_t stream);
 
