@@ -88,9 +88,11 @@ int ob_conv_fwd(const void* x, const void* ctx, const void* wg, const float* alp
   } else {
     set_src(L, 0, x, n_seq * S, T, H, W, cin);
     set_src(L, 1, ctx, n_seq, T + 2, H, W, cin);
-    for (int dx = -1; dx <= 1; ++dx) cols.push_back(tap_col3(0, 0, dx, S, 0, S, 0, false));
+    // context taps first: they accumulate into the shared accumulator, which the persistent kernel rotates between two
+    // TMEM ranges, so this half of the main loop overlaps the previous tile's epilogue
     for (int tau = 0; tau < 2; ++tau)
       for (int dx = -1; dx <= 1; ++dx) cols.push_back(tap_col3(1, tau, dx, 1, S, 1, 9 + tau * 9, false));
+    for (int dx = -1; dx <= 1; ++dx) cols.push_back(tap_col3(0, 0, dx, S, 0, S, 0, false));
     L.n_seq = n_seq; L.n_out = S; L.T = T; L.w_taps = 27; L.epi = EPI_GATED; L.halo = 1;
     L.alpha = alpha; L.beta = beta; L.out_d = out_d;
   }

@@ -31,6 +31,7 @@ struct Problem {
   int halo;
   int split;   // give the launch a split-K workspace
   int nopair;  // 1: forbid CTA-pair execution
+  int nopersist;  // 1: one CTA per tile
 };
 
 // column of vertical taps at horizontal shift dx; flip mirrors the kernel (input-gradient form)
@@ -95,6 +96,7 @@ static bool run(const Problem& P, bool check, int reps) {
   L.epi = P.epi; L.out_f32 = P.out_f32; L.alpha = dal; L.beta = dbe; L.out = dOut;
   L.out_d = (P.epi == EPI_GATED) ? dD : nullptr; L.force_bn = P.force_bn; L.b_mn_major = P.bmn;
   L.use_pair = P.nopair ? 0 : 1;
+  L.no_persist = P.nopersist;
   float* dWs = nullptr;
   if (P.split) { cudaMalloc(&dWs, (size_t)n_acc * nout / P.n_out * 4); L.split_ws = dWs; }
 
@@ -198,9 +200,11 @@ static Problem gated(const char* name, int B, int S, int n, int H, int W, int Ci
   P.name = name; P.n_seq = B; P.n_out = S; P.T = n; P.H = H; P.W = W; P.Cin = Cin; P.Cout = Cout;
   P.epi = EPI_GATED; P.out_f32 = 0; P.seqA[0] = B * S; P.TA[0] = n; P.seqA[1] = B; P.TA[1] = n + 2; P.w_taps = 27;
   P.force_bn = force_bn; P.halo = 1;
-  for (int dx = -1; dx <= 1; ++dx) P.cols.push_back(mk3(0, 0, dx, S, 0, S, 0, false));
-  for (int tau = 0; tau < 2; ++tau)
+  const bool cur_first = getenv("TAPCONV_CUR_FIRST") != nullptr;
+  if (cur_first) for (int dx = -1; dx <= 1; ++dx) P.cols.push_back(mk3(0, 0, dx, S, 0, S, 0, false));
+  for (int tau = 0; tau < 2; ++tau)   // context taps first (see capi.cu)
     for (int dx = -1; dx <= 1; ++dx) P.cols.push_back(mk3(1, tau, dx, 1, S, 1, 9 + tau * 9, false));
+  if (!cur_first) for (int dx = -1; dx <= 1; ++dx) P.cols.push_back(mk3(0, 0, dx, S, 0, S, 0, false));
   return P;
 }
 static Problem plain(const char* name, int F, int H, int W, int Cin, int Cout, int k, int f32, int force_bn = 0) {
@@ -230,6 +234,7 @@ int main(int argc, char** argv) {
   int fails = 0;
   if (argc > 1 && atoi(argv[1]) == 2) {   // a short list for ncu captures
     run(gated("CS 128->128 32x32 B2 n16", 2, 2, 16, 32, 32, 128, 128), false, 2);
+    { Problem q = gated("CS 128->128 32x32 B2 n16 NOPERSIST", 2, 2, 16, 32, 32, 128, 128); q.nopersist = 1; run(q, false, 2); }
     run(gated("CS 512->512 16x16 B2 n16", 2, 2, 16, 16, 16, 512, 512), false, 2);
     run(plain("1x1 256->128 32x32 F64", 64, 32, 32, 256, 128, 1, 0), false, 2);
     run(gated("CS 512->512 8x8 split auto", 2, 2, 16, 8, 8, 512, 512, 0, 1), false, 2);
@@ -252,6 +257,13 @@ int main(int argc, char** argv) {
   fails += !run(gated("gated eval decode c128 n128 4x4 B3 T1", 3, 1, 1, 4, 4, 128, 128), true, 0);
   fails += !run(gated("gated dual split c256 n128 4x4 B1 n8", 1, 2, 8, 4, 4, 256, 128, 0, 1), true, 0);
   fails += !run(gated("gated eval split c256 n64 4x4 B2 T4", 2, 1, 4, 4, 4, 256, 64, 0, 1), true, 0);
+  // more tiles than SMs: several rounds of the persistent loop in every TMEM mode (ROTATE, DOUBLE, SINGLE), pair and single
+  fails += !run(gated("gated dual c64 n128 32x32 B2 n12 (rotate, 3 rounds)", 2, 2, 12, 32, 32, 64, 128), true, 0);
+  { Problem q = gated("gated dual c64 n128 32x32 B2 n12 nopair", 2, 2, 12, 32, 32, 64, 128); q.nopair = 1; fails += !run(q, true, 0); }
+  fails += !run(gated("gated dual c64 n64 32x32 B2 n10 (double)", 2, 2, 10, 32, 32, 64, 64), true, 0);
+  fails += !run(gated("gated eval c64 n256 32x32 B2 T10 (single)", 2, 1, 10, 32, 32, 64, 256, 256), true, 0);
+  fails += !run(plain("conv3x3 c64 n128 32x32 F40 (double, pair)", 40, 32, 32, 64, 128, 3, 0), true, 0);
+  fails += !run(plain("gemm1x1 c64 n256 32x32 F30 f32", 30, 32, 32, 64, 256, 1, 1), true, 0);
   fails += !run(dgrad("dgrad dual c128 n64 8x8 B2 n4", 2, 4, 8, 8, 128, 64), true, 0);
   fails += !run(dgrad("dgrad dual BMN c128 n64 8x8 B2 n4", 2, 4, 8, 8, 128, 64, 1), true, 0);
   fails += !run(dgrad("dgrad dual BMN c64 n256 4x4 B2 n8", 2, 8, 4, 4, 64, 256, 1), true, 0);

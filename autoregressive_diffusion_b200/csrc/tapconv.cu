@@ -333,7 +333,24 @@ int tapconv_launch(const TapConvLaunch& L, cudaStream_t stream) {
       if (e != cudaSuccess) { set_error("tapconv: workspace memset: %s", cudaGetErrorString(e)); return OB_ERR_CUDA; }
     }
   }
-  const dim3 grid(pair ? p.m_tiles_pad * p.tiles_n : m_tiles * p.tiles_n, p.ksplit);
+  // accumulator placement for the persistent tile loop (see tapconv.cuh)
+  if (2 * n_acc * bn <= 512) p.tmem_mode = TMEM_DOUBLE;
+  else if (n_acc == 3 && 4 * bn <= 512) p.tmem_mode = TMEM_ROTATE;
+  else p.tmem_mode = TMEM_SINGLE;
+  // persistent grid: at most one CTA per SM (one cluster per SM pair); each walks tiles with stride gridDim.x
+  static int n_sm = 0;
+  if (n_sm == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0) n_sm = 148;
+  }
+  int tiles_x = pair ? p.m_tiles_pad * p.tiles_n : m_tiles * p.tiles_n;
+  int max_x = n_sm / p.ksplit;
+  if (max_x < 1) max_x = 1;
+  if (pair) max_x &= ~1;
+  if (max_x < (pair ? 2 : 1)) max_x = pair ? 2 : 1;
+  if (L.no_persist) max_x = tiles_x;
+  const dim3 grid(tiles_x < max_x ? tiles_x : max_x, p.ksplit);
   int rc;
   if (L.b_mn_major) {
     switch (chunk) {

@@ -61,6 +61,7 @@ struct TapConvParams {
   int a_slots;
   int b_slots;
   int tiles_w, tiles_h, tiles_t, tiles_n;
+  int tmem_mode;       // TMEM_SINGLE / TMEM_DOUBLE / TMEM_ROTATE (accumulator placement per tile parity)
   int m_tiles_pad;     // PAIR mode: pixel tiles rounded up to a multiple of 2 (blockIdx.x = m + m_tiles_pad*n)
   int n_out;    // output row sets per tile (2 in dual mode)
   int epi;      // EPI_*
@@ -100,6 +101,18 @@ struct TapConvCfg {
 // ONE tcgen05.mma.cta_group::2 stream (M=256): each CTA stages its own activation tiles but only HALF of every weight
 // tile, which halves the weight traffic into shared memory and the shared-memory operand reads per FLOP -- the limit a
 // single-CTA M=128 x N=128 MMA runs into.
+//
+// The kernel is PERSISTENT: a CTA (pair) walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...  The producers and the MMA
+// issuer run ahead into the next tile while the epilogue warps drain the previous one; without this every CTA of a
+// wave reaches its epilogue at the same moment and the whole GPU alternates between a tensor-bound and a
+// store-bound phase (measured: 8.4 us of a 27 us tile).  TMEM accumulator placement per tile parity (p.tmem_mode):
+//   TMEM_DOUBLE  2*n_acc*BN <= 512: the whole accumulator set alternates between two column ranges.
+//   TMEM_ROTATE  three accumulators of 128 columns: the two own accumulators stay in place and the shared (context)
+//                accumulator alternates between columns 256 and 384; the host orders the context taps first, so that
+//                half of the next tile's main loop overlaps the previous tile's epilogue.
+//   TMEM_SINGLE  no spare columns: the next tile's MMAs wait for the epilogue (loads still run ahead).
+enum : int { TMEM_SINGLE = 0, TMEM_DOUBLE = 1, TMEM_ROTATE = 2 };
+
 __device__ __forceinline__ long long global_ns() {
   long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -123,37 +136,48 @@ __global__ void __launch_bounds__(TAPCONV_THREADS, 1) tapconv_kernel(const __gri
   const uint32_t sA0 = smem_base;
   const uint32_t sB0 = sA0 + p.a_slots * p.a_slot_bytes;
   const uint32_t bar_base = sB0 + p.b_slots * B_STRIDE;
-  // barriers: a_full[MAXA], a_empty[MAXA], b_full[MAXB], b_empty[MAXB], tmem_full, then the TMEM base address slot
+  // barriers: a_full[MAXA], a_empty[MAXA], b_full[MAXB], b_empty[MAXB], tmem_full[2], tmem_empty[2], TMEM address slot
   constexpr int MAXA = TAPCONV_MAX_A_SLOTS;
   auto a_full = [&](int s) { return bar_base + 8u * s; };
   auto a_empty = [&](int s) { return bar_base + 8u * (MAXA + s); };
   auto b_full = [&](int s) { return bar_base + 8u * (2 * MAXA + s); };
   auto b_empty = [&](int s) { return bar_base + 8u * (2 * MAXA + MAXB + s); };
-  const uint32_t tmem_full_bar = bar_base + 8u * (2 * MAXA + 2 * MAXB);
-  const uint32_t tmem_slot = tmem_full_bar + 8u;
+  auto tmem_full = [&](int s) { return bar_base + 8u * (2 * MAXA + 2 * MAXB + s); };
+  auto tmem_empty = [&](int s) { return bar_base + 8u * (2 * MAXA + 2 * MAXB + 2 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * MAXA + 2 * MAXB + 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-
-  // ---- tile coordinates
-  int tile = blockIdx.x;
-  int n_tile;
-  if constexpr (PAIR) { n_tile = tile / p.m_tiles_pad; tile -= n_tile * p.m_tiles_pad; }   // pixel tile fastest: pairs share n
-  else { n_tile = tile % p.tiles_n; tile /= p.tiles_n; }
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
   const bool leader = rank == 0;
-  const int tw_i = tile % p.tiles_w;
-  tile /= p.tiles_w;
-  const int th_i = tile % p.tiles_h;
-  tile /= p.tiles_h;
-  const int tt_i = tile % p.tiles_t;
-  const int seq = tile / p.tiles_t;
-  const int w0 = tw_i * p.bw, h0 = th_i * p.bh, t0 = tt_i * p.bt;
-  const int n0 = n_tile * BN;
+
+  // ---- tile walk.  PAIR: pixel tile fastest, so tiles (2k, 2k+1) -- the two CTAs of a cluster -- share the channel tile
+  const int total_tiles = PAIR ? p.m_tiles_pad * p.tiles_n : p.tiles_w * p.tiles_h * p.tiles_t * p.n_seq * p.tiles_n;
+  struct Tile { int w0, h0, t0, seq, n0; };
+  auto decode = [&](int tile) {
+    int n_tile;
+    if constexpr (PAIR) { n_tile = tile / p.m_tiles_pad; tile -= n_tile * p.m_tiles_pad; }
+    else { n_tile = tile % p.tiles_n; tile /= p.tiles_n; }
+    Tile c;
+    c.w0 = (tile % p.tiles_w) * p.bw; tile /= p.tiles_w;
+    c.h0 = (tile % p.tiles_h) * p.bh; tile /= p.tiles_h;
+    c.t0 = (tile % p.tiles_t) * p.bt;
+    c.seq = tile / p.tiles_t;             // >= n_seq on the padding tile of an odd pair count: loads zero-fill, stores masked
+    c.n0 = n_tile * BN;
+    return c;
+  };
 
   const int n_acc = p.n_out + (p.epi == EPI_GATED ? 1 : 0);
+  const int mode = p.tmem_mode;
+  const int cols_needed = mode == TMEM_DOUBLE ? 2 * n_acc * BN : mode == TMEM_ROTATE ? 4 * BN : n_acc * BN;
   uint32_t tmem_cols = 32;
-  while (tmem_cols < static_cast<uint32_t>(n_acc * BN)) tmem_cols <<= 1;
+  while (tmem_cols < static_cast<uint32_t>(cols_needed)) tmem_cols <<= 1;
+  // TMEM column of accumulator `acc` for the tile of parity `par`
+  auto acc_col = [&](int acc, int par) -> uint32_t {
+    if (mode == TMEM_DOUBLE) return static_cast<uint32_t>((par * n_acc + acc) * BN);
+    if (mode == TMEM_ROTATE && acc == p.n_out) return static_cast<uint32_t>((2 + par) * BN);
+    return static_cast<uint32_t>(acc * BN);
+  };
   const int n_chunks_all = (p.Cin + CHUNK - 1) / CHUNK;  // a ragged last chunk is TMA zero-filled
   // split-K: this CTA owns channel chunks [ck_lo, ck_hi)
   const int ck_lo = static_cast<int>(static_cast<long>(n_chunks_all) * blockIdx.y / p.ksplit);
@@ -163,7 +187,7 @@ __global__ void __launch_bounds__(TAPCONV_THREADS, 1) tapconv_kernel(const __gri
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.a_slots; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
     for (int s = 0; s < p.b_slots; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
-    mbar_init(tmem_full_bar, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(tmem_full(s), 1); mbar_init(tmem_empty(s), PAIR ? 8 : 4); }
     fence_barrier_init();
     tma_prefetch_desc(&p.mapA[0]);
     tma_prefetch_desc(&p.mapA[1]);
@@ -185,64 +209,70 @@ __global__ void __launch_bounds__(TAPCONV_THREADS, 1) tapconv_kernel(const __gri
     // ===================== activation (A) TMA producer (warp-uniform loop, one elected lane issues) ============
     int as = 0;
     uint32_t aph = 0;
-    for (int ic = 0; ic < p.n_cols; ++ic) {
-      const TapCol col = p.cols[ic];
-      const void* mapA = &p.mapA[col.src];
-      for (int ck = ck_lo; ck < ck_hi; ++ck) {
-        mbar_wait(a_empty(as), aph ^ 1);
-        if (elect_one()) {
-          if constexpr (PAIR) {
-            if (leader) mbar_arrive_expect_tx(a_full(as), 2 * col.n_a * p.a_tile_bytes);   // both CTAs' tiles
-            for (int i = 0; i < col.n_a; ++i)
-              tma_load_5d_pair(sA0 + as * p.a_slot_bytes + i * p.a_tile_bytes, mapA, a_full(as), ck * CHUNK, w0 + col.dx,
-                               t0 + col.dt, h0 - p.halo, seq * col.seq_mul + i);
-          } else {
-            mbar_arrive_expect_tx(a_full(as), col.n_a * p.a_tile_bytes);
-            for (int i = 0; i < col.n_a; ++i)
-              tma_load_5d(sA0 + as * p.a_slot_bytes + i * p.a_tile_bytes, mapA, a_full(as), ck * CHUNK, w0 + col.dx,
-                          t0 + col.dt, h0 - p.halo, seq * col.seq_mul + i);
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const Tile tc = decode(tile);
+      for (int ic = 0; ic < p.n_cols; ++ic) {
+        const TapCol col = p.cols[ic];
+        const void* mapA = &p.mapA[col.src];
+        for (int ck = ck_lo; ck < ck_hi; ++ck) {
+          mbar_wait(a_empty(as), aph ^ 1);
+          if (elect_one()) {
+            if constexpr (PAIR) {
+              if (leader) mbar_arrive_expect_tx(a_full(as), 2 * col.n_a * p.a_tile_bytes);   // both CTAs' tiles
+              for (int i = 0; i < col.n_a; ++i)
+                tma_load_5d_pair(sA0 + as * p.a_slot_bytes + i * p.a_tile_bytes, mapA, a_full(as), ck * CHUNK,
+                                 tc.w0 + col.dx, tc.t0 + col.dt, tc.h0 - p.halo, tc.seq * col.seq_mul + i);
+            } else {
+              mbar_arrive_expect_tx(a_full(as), col.n_a * p.a_tile_bytes);
+              for (int i = 0; i < col.n_a; ++i)
+                tma_load_5d(sA0 + as * p.a_slot_bytes + i * p.a_tile_bytes, mapA, a_full(as), ck * CHUNK, tc.w0 + col.dx,
+                            tc.t0 + col.dt, tc.h0 - p.halo, tc.seq * col.seq_mul + i);
+            }
           }
+          __syncwarp();
+          if (++as == p.a_slots) { as = 0; aph ^= 1; }
         }
-        __syncwarp();
-        if (++as == p.a_slots) { as = 0; aph ^= 1; }
       }
     }
   } else if (warp == 2) {
     // ===================== weight (B) TMA producer: runs ahead independently of the A ring =====================
     int bs = 0;
     uint32_t bph = 0;
-    for (int ic = 0; ic < p.n_cols; ++ic) {
-      const TapCol col = p.cols[ic];
-      for (int ck = ck_lo; ck < ck_hi; ++ck) {
-        for (int d = 0; d < col.n_taps; ++d) {
-          mbar_wait(b_empty(bs), bph ^ 1);
-          if (elect_one()) {
-            const uint32_t sB = sB0 + bs * B_STRIDE;
-            if constexpr (PAIR) {
-              // this CTA stages output channels [n0 + rank*BN/2, +BN/2) of the tile; the MMA reads both halves
-              if (leader) mbar_arrive_expect_tx(b_full(bs), Cfg::B_BYTES);
-              if constexpr (!BMN) {
-                tma_load_2d_pair(sB, &p.mapB, b_full(bs), col.wtap[d] * p.Cin + ck * CHUNK, n0 + rank * (BN / 2));
-              } else {
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int n0 = decode(tile).n0;
+      for (int ic = 0; ic < p.n_cols; ++ic) {
+        const TapCol col = p.cols[ic];
+        for (int ck = ck_lo; ck < ck_hi; ++ck) {
+          for (int d = 0; d < col.n_taps; ++d) {
+            mbar_wait(b_empty(bs), bph ^ 1);
+            if (elect_one()) {
+              const uint32_t sB = sB0 + bs * B_STRIDE;
+              if constexpr (PAIR) {
+                // this CTA stages output channels [n0 + rank*BN/2, +BN/2) of the tile; the MMA reads both halves
+                if (leader) mbar_arrive_expect_tx(b_full(bs), Cfg::B_BYTES);
+                if constexpr (!BMN) {
+                  tma_load_2d_pair(sB, &p.mapB, b_full(bs), col.wtap[d] * p.Cin + ck * CHUNK, n0 + rank * (BN / 2));
+                } else {
 #pragma unroll
-                for (int j = 0; j < BN / 2 / CHUNK; ++j)
-                  tma_load_2d_pair(sB + j * (CHUNK * Cfg::ROW_BYTES), &p.mapB, b_full(bs),
-                                   col.wtap[d] * p.Cout + n0 + rank * (BN / 2) + j * CHUNK, ck * CHUNK);
-              }
-            } else {
-              mbar_arrive_expect_tx(b_full(bs), Cfg::B_BYTES);
-              if constexpr (!BMN) {
-                tma_load_2d(sB, &p.mapB, b_full(bs), col.wtap[d] * p.Cin + ck * CHUNK, n0);
+                  for (int j = 0; j < BN / 2 / CHUNK; ++j)
+                    tma_load_2d_pair(sB + j * (CHUNK * Cfg::ROW_BYTES), &p.mapB, b_full(bs),
+                                     col.wtap[d] * p.Cout + n0 + rank * (BN / 2) + j * CHUNK, ck * CHUNK);
+                }
               } else {
+                mbar_arrive_expect_tx(b_full(bs), Cfg::B_BYTES);
+                if constexpr (!BMN) {
+                  tma_load_2d(sB, &p.mapB, b_full(bs), col.wtap[d] * p.Cin + ck * CHUNK, n0);
+                } else {
 #pragma unroll
-                for (int j = 0; j < BN / CHUNK; ++j)
-                  tma_load_2d(sB + j * (CHUNK * Cfg::ROW_BYTES), &p.mapB, b_full(bs), col.wtap[d] * p.Cout + n0 + j * CHUNK,
-                              ck * CHUNK);
+                  for (int j = 0; j < BN / CHUNK; ++j)
+                    tma_load_2d(sB + j * (CHUNK * Cfg::ROW_BYTES), &p.mapB, b_full(bs), col.wtap[d] * p.Cout + n0 + j * CHUNK,
+                                ck * CHUNK);
+                }
               }
             }
+            __syncwarp();
+            if (++bs == p.b_slots) { bs = 0; bph ^= 1; }
           }
-          __syncwarp();
-          if (++bs == p.b_slots) { bs = 0; bph ^= 1; }
         }
       }
     }
@@ -256,49 +286,67 @@ __global__ void __launch_bounds__(TAPCONV_THREADS, 1) tapconv_kernel(const __gri
     constexpr uint32_t B_KSTEP = BMN ? (2 * SBO) >> 4 : 32 >> 4;   // descriptor units of 16 bytes
     int as = 0, bs = 0;
     uint32_t aph = 0, bph = 0;
-    uint32_t started = 0;  // bit j: accumulator j already holds a partial sum
+    // how many tiles back an accumulator's previous user lies: its epilogue must have drained it first
+    const int own_depth = mode == TMEM_DOUBLE ? 2 : 1;
+    const int shr_depth = mode == TMEM_SINGLE ? 1 : 2;
+    int drained = -1;   // epilogues of iterations <= drained are known complete
     if (leader) {          // in pair mode the peer's MMA warp only owns its half of the TMEM allocation
-    for (int ic = 0; ic < p.n_cols; ++ic) {
-      const TapCol col = p.cols[ic];
-      for (int ck = ck_lo; ck < ck_hi; ++ck) {
-        mbar_wait(a_full(as), aph);
-        if (ic == 0 && ck == ck_lo) TAPCONV_STAMP(1);   // first activation tile landed
-        const uint32_t sA = sA0 + as * p.a_slot_bytes;
-        for (int d = 0; d < col.n_taps; ++d) {
-          mbar_wait(b_full(bs), bph);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int par = it & 1;
+      uint32_t started = 0;  // bit j: accumulator j already holds a partial sum
+      const uint32_t own_base = tmem_base + acc_col(0, par), shr_base = tmem_base + acc_col(p.n_out, par);
+      for (int ic = 0; ic < p.n_cols; ++ic) {
+        const TapCol col = p.cols[ic];
+        const bool is_shr = col.acc >= p.n_out;
+        const uint32_t d_tmem0 = is_shr ? shr_base : own_base + static_cast<uint32_t>(col.acc * BN);
+        const int need = it - (is_shr ? shr_depth : own_depth);
+        while (drained < need) {
+          ++drained;
+          if constexpr (PAIR) mbar_wait_cluster(tmem_empty(drained & 1), (drained >> 1) & 1);
+          else mbar_wait(tmem_empty(drained & 1), (drained >> 1) & 1);
           tc_fence_after();
-          const uint64_t bdesc = bdesc0 + ((sB0 + bs * B_STRIDE) >> 4);
-          if (elect_one()) {
+        }
+        for (int ck = ck_lo; ck < ck_hi; ++ck) {
+          mbar_wait(a_full(as), aph);
+          if (it == 0 && ic == 0 && ck == ck_lo) TAPCONV_STAMP(1);   // first activation tile landed
+          const uint32_t sA = sA0 + as * p.a_slot_bytes;
+          for (int d = 0; d < col.n_taps; ++d) {
+            mbar_wait(b_full(bs), bph);
+            tc_fence_after();
+            const uint64_t bdesc = bdesc0 + ((sB0 + bs * B_STRIDE) >> 4);
+            if (elect_one()) {
 #pragma unroll
-            for (int i = 0; i < 2; ++i) {
-              if (i < col.n_a) {
-                const int acc = col.acc + i;
-                const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
-                const uint64_t adesc = adesc0 + ((sA + i * p.a_tile_bytes + d * dy_stride) >> 4);
-                if constexpr (PAIR) {
-                  umma_bf16_ss_pair(d_tmem, adesc, bdesc, idesc, (started >> acc) & 1u);
+              for (int i = 0; i < 2; ++i) {
+                if (i < col.n_a) {
+                  const int acc = col.acc + i;
+                  const uint32_t d_tmem = d_tmem0 + static_cast<uint32_t>(i * BN);
+                  const uint64_t adesc = adesc0 + ((sA + i * p.a_tile_bytes + d * dy_stride) >> 4);
+                  if constexpr (PAIR) {
+                    umma_bf16_ss_pair(d_tmem, adesc, bdesc, idesc, (started >> acc) & 1u);
 #pragma unroll
-                  for (int k = 1; k < CHUNK / 16; ++k) umma_bf16_ss_pair(d_tmem, adesc + 2 * k, bdesc + B_KSTEP * k, idesc, 1u);
-                } else {
-                  umma_bf16_ss(d_tmem, adesc, bdesc, idesc, (started >> acc) & 1u);
+                    for (int k = 1; k < CHUNK / 16; ++k) umma_bf16_ss_pair(d_tmem, adesc + 2 * k, bdesc + B_KSTEP * k, idesc, 1u);
+                  } else {
+                    umma_bf16_ss(d_tmem, adesc, bdesc, idesc, (started >> acc) & 1u);
 #pragma unroll
-                  for (int k = 1; k < CHUNK / 16; ++k) umma_bf16_ss(d_tmem, adesc + 2 * k, bdesc + B_KSTEP * k, idesc, 1u);
+                    for (int k = 1; k < CHUNK / 16; ++k) umma_bf16_ss(d_tmem, adesc + 2 * k, bdesc + B_KSTEP * k, idesc, 1u);
+                  }
                 }
               }
+              if constexpr (PAIR) umma_commit_pair(b_empty(bs)); else umma_commit(b_empty(bs));  // frees the weight slot(s)
             }
-            if constexpr (PAIR) umma_commit_pair(b_empty(bs)); else umma_commit(b_empty(bs));  // frees the weight slot(s)
+            __syncwarp();
+            started |= ((1u << col.n_a) - 1u) << col.acc;
+            if (++bs == p.b_slots) { bs = 0; bph ^= 1; }
           }
+          if (elect_one()) { if constexpr (PAIR) umma_commit_pair(a_empty(as)); else umma_commit(a_empty(as)); }
           __syncwarp();
-          started |= ((1u << col.n_a) - 1u) << col.acc;
-          if (++bs == p.b_slots) { bs = 0; bph ^= 1; }
+          if (++as == p.a_slots) { as = 0; aph ^= 1; }
         }
-        if (elect_one()) { if constexpr (PAIR) umma_commit_pair(a_empty(as)); else umma_commit(a_empty(as)); }
-        __syncwarp();
-        if (++as == p.a_slots) { as = 0; aph ^= 1; }
       }
+      if (elect_one()) { if constexpr (PAIR) umma_commit_pair(tmem_full(par)); else umma_commit(tmem_full(par)); }
+      __syncwarp();
     }
-    if (elect_one()) { if constexpr (PAIR) umma_commit_pair(tmem_full_bar); else umma_commit(tmem_full_bar); }
-    __syncwarp();
     TAPCONV_STAMP(2);   // all MMAs issued
     }
   } else {
@@ -310,89 +358,112 @@ __global__ void __launch_bounds__(TAPCONV_THREADS, 1) tapconv_kernel(const __gri
     const int rem = m - hh * (p.bt * p.bw);
     const int tt = rem / p.bw;
     const int ww = rem - tt * p.bw;
-    const int t = t0 + tt, h = h0 + hh, w = w0 + ww;
-    const bool row_ok = (t < p.T) && (h < p.H) && (w < p.W) && (seq < p.n_seq);
-
-    mbar_wait_sleep(tmem_full_bar, 0);
-    tc_fence_after();
-    if (warp == 3) TAPCONV_STAMP(3);   // accumulators complete
-
     const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    if (p.ksplit > 1) {
-      // partial sums: add the raw accumulators into the fp32 workspace; tapconv_finish_kernel applies the epilogue
-      const long rows_per_set = static_cast<long>(p.n_seq) * p.T * p.H * p.W;   // pixel rows of ONE output set
-      const long pix = ((static_cast<long>(seq) * p.T + t) * p.H + h) * p.W + w;
-      for (int a = 0; a < n_acc; ++a) {
-        // own accumulators: row = (set a, pixel); shared accumulator: stored after the n_out own sets
-        float* dst_row = p.split_ws + (static_cast<long>(a) * rows_per_set + pix) * p.Cout;
-        for (int c = 0; c < BN / CW; ++c) {
-          float v[CW];
-          if constexpr (CW == 32) tmem_ld32(lane_base + a * BN + c * CW, v);
-          else tmem_ld16(lane_base + a * BN + c * CW, v);
-          tmem_ld_wait();
-          const int col0 = n0 + c * CW;
-          if (row_ok && ck_hi > ck_lo) {
+    const long rows_per_set = static_cast<long>(p.n_seq) * p.T * p.H * p.W;   // pixel rows of ONE output set
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int par = it & 1;
+      const Tile tc = decode(tile);
+      const int seq = tc.seq, n0 = tc.n0;
+      const int t = tc.t0 + tt, h = tc.h0 + hh, w = tc.w0 + ww;
+      const bool row_ok = (t < p.T) && (h < p.H) && (w < p.W) && (seq < p.n_seq);
+
+      mbar_wait_sleep(tmem_full(par), (it >> 1) & 1);
+      tc_fence_after();
+      if (warp == 3 && it == 0) TAPCONV_STAMP(3);   // first tile's accumulators complete
+
+      if (p.ksplit > 1) {
+        // partial sums: add the raw accumulators into the fp32 workspace; tapconv_finish_kernel applies the epilogue
+        const long pix = ((static_cast<long>(seq) * p.T + t) * p.H + h) * p.W + w;
+        for (int a = 0; a < n_acc; ++a) {
+          // own accumulators: row = (set a, pixel); shared accumulator: stored after the n_out own sets
+          float* dst_row = p.split_ws + (static_cast<long>(a) * rows_per_set + pix) * p.Cout;
+          for (int c = 0; c < BN / CW; ++c) {
+            float v[CW];
+            if constexpr (CW == 32) tmem_ld32(lane_base + acc_col(a, par) + c * CW, v);
+            else tmem_ld16(lane_base + acc_col(a, par) + c * CW, v);
+            tmem_ld_wait();
+            const int col0 = n0 + c * CW;
+            if (row_ok && ck_hi > ck_lo) {
 #pragma unroll
-            for (int j = 0; j < CW; j += 4)
-              if (col0 + j + 4 <= p.Cout)
-                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst_row + col0 + j), "f"(v[j]), "f"(v[j + 1]),
-                             "f"(v[j + 2]), "f"(v[j + 3])
-                             : "memory");
+              for (int j = 0; j < CW; j += 4)
+                if (col0 + j + 4 <= p.Cout)
+                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst_row + col0 + j), "f"(v[j]), "f"(v[j + 1]),
+                               "f"(v[j + 2]), "f"(v[j + 3])
+                               : "memory");
+            }
+          }
+        }
+      } else
+      for (int o = 0; o < p.n_out; ++o) {
+        const long frame = static_cast<long>(seq * p.n_out + o) * p.T + t;
+        float al = 1.f, be = 0.f;
+        if (p.epi == EPI_GATED && row_ok) { al = p.alpha[frame]; be = p.beta[frame]; }
+        const long row_off = ((frame * p.H + h) * p.W + w) * static_cast<long>(p.Cout);
+        for (int c = 0; c < BN / CW; ++c) {
+          float own[CW], shr[CW];
+          if constexpr (CW == 32) tmem_ld32(lane_base + acc_col(o, par) + c * CW, own);
+          else tmem_ld16(lane_base + acc_col(o, par) + c * CW, own);
+          if (p.epi == EPI_GATED) {
+            if constexpr (CW == 32) tmem_ld32(lane_base + acc_col(p.n_out, par) + c * CW, shr);
+            else tmem_ld16(lane_base + acc_col(p.n_out, par) + c * CW, shr);
+          }
+          tmem_ld_wait();
+          if (o == p.n_out - 1 && c == BN / CW - 1) {
+            // last TMEM read of this tile: hand the accumulators back to the MMA issuer before the stores go out
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if constexpr (PAIR) mbar_arrive_remote(tmem_empty(par), 0);
+              else mbar_arrive(tmem_empty(par));
+            }
+          }
+          float y[CW];
+          if (p.epi == EPI_GATED) {
+#pragma unroll
+            for (int j = 0; j < CW; ++j) y[j] = al * own[j] + be * shr[j];
+          } else {
+#pragma unroll
+            for (int j = 0; j < CW; ++j) y[j] = own[j];
+          }
+          const int col0 = n0 + c * CW;
+          if (row_ok) {
+            if (p.out_f32) {
+              float* dst = static_cast<float*>(p.out) + row_off + col0;
+#pragma unroll
+              for (int j = 0; j < CW; j += 4)
+                if (col0 + j + 4 <= p.Cout) *reinterpret_cast<float4*>(dst + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
+            } else {
+              __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(p.out) + row_off + col0;
+#pragma unroll
+              for (int j = 0; j < CW; j += 8)
+                if (col0 + j + 8 <= p.Cout)
+                  *reinterpret_cast<uint4*>(dst + j) = make_uint4(pack_bf16x2(y[j], y[j + 1]), pack_bf16x2(y[j + 2], y[j + 3]),
+                                                                  pack_bf16x2(y[j + 4], y[j + 5]), pack_bf16x2(y[j + 6], y[j + 7]));
+            }
+            if (p.epi == EPI_GATED && p.out_d != nullptr) {
+              // fp32 on purpose: <dy, d> feeds the gate scalars' gradients and bf16 rounding of d shows up there at ~2%
+              float* dd = static_cast<float*>(p.out_d) + row_off + col0;
+#pragma unroll
+              for (int j = 0; j < CW; j += 4)
+                if (col0 + j + 4 <= p.Cout)
+                  *reinterpret_cast<float4*>(dd + j) =
+                      make_float4(shr[j] - own[j], shr[j + 1] - own[j + 1], shr[j + 2] - own[j + 2], shr[j + 3] - own[j + 3]);
+            }
           }
         }
       }
-    } else
-    for (int o = 0; o < p.n_out; ++o) {
-      const long frame = static_cast<long>(seq * p.n_out + o) * p.T + t;
-      float al = 1.f, be = 0.f;
-      if (p.epi == EPI_GATED && row_ok) { al = p.alpha[frame]; be = p.beta[frame]; }
-      const long row_off = ((frame * p.H + h) * p.W + w) * static_cast<long>(p.Cout);
-      for (int c = 0; c < BN / CW; ++c) {
-        float own[CW], shr[CW];
-        if constexpr (CW == 32) tmem_ld32(lane_base + o * BN + c * CW, own);
-        else tmem_ld16(lane_base + o * BN + c * CW, own);
-        if (p.epi == EPI_GATED) {
-          if constexpr (CW == 32) tmem_ld32(lane_base + p.n_out * BN + c * CW, shr);
-          else tmem_ld16(lane_base + p.n_out * BN + c * CW, shr);
-        }
-        tmem_ld_wait();
-        float y[CW];
-        if (p.epi == EPI_GATED) {
-#pragma unroll
-          for (int j = 0; j < CW; ++j) y[j] = al * own[j] + be * shr[j];
-        } else {
-#pragma unroll
-          for (int j = 0; j < CW; ++j) y[j] = own[j];
-        }
-        const int col0 = n0 + c * CW;
-        if (row_ok) {
-          if (p.out_f32) {
-            float* dst = static_cast<float*>(p.out) + row_off + col0;
-#pragma unroll
-            for (int j = 0; j < CW; j += 4)
-              if (col0 + j + 4 <= p.Cout) *reinterpret_cast<float4*>(dst + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
-          } else {
-            __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(p.out) + row_off + col0;
-#pragma unroll
-            for (int j = 0; j < CW; j += 8)
-              if (col0 + j + 8 <= p.Cout)
-                *reinterpret_cast<uint4*>(dst + j) = make_uint4(pack_bf16x2(y[j], y[j + 1]), pack_bf16x2(y[j + 2], y[j + 3]),
-                                                                pack_bf16x2(y[j + 4], y[j + 5]), pack_bf16x2(y[j + 6], y[j + 7]));
-          }
-          if (p.epi == EPI_GATED && p.out_d != nullptr) {
-            // fp32 on purpose: <dy, d> feeds the gate scalars' gradients and bf16 rounding of d shows up there at ~2%
-            float* dd = static_cast<float*>(p.out_d) + row_off + col0;
-#pragma unroll
-            for (int j = 0; j < CW; j += 4)
-              if (col0 + j + 4 <= p.Cout)
-                *reinterpret_cast<float4*>(dd + j) =
-                    make_float4(shr[j] - own[j], shr[j + 1] - own[j + 1], shr[j + 2] - own[j + 2], shr[j + 3] - own[j + 3]);
-          }
+      if (p.ksplit > 1) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (PAIR) mbar_arrive_remote(tmem_empty(par), 0);
+          else mbar_arrive(tmem_empty(par));
         }
       }
     }
     tc_fence_before();
-    if (warp == 3) TAPCONV_STAMP(4);   // epilogue stores issued
+    if (warp == 3) TAPCONV_STAMP(4);   // last epilogue's stores issued
   }
 
   __syncthreads();

@@ -38,6 +38,7 @@ struct TapConvLaunch {
   int b_mn_major = 0;  // weights given as [Cin][w_taps][Cout] (input-gradient passes)
   float* split_ws = nullptr;   // optional fp32 workspace enabling split-K (size from tapconv_plan)
   long long* trace = nullptr;  // probe only: per-CTA globaltimer stamps [ctas][8]
+  int no_persist = 0;          // probe only: one CTA per tile (the pre-persistent schedule)
   int use_pair = 1;            // allow CTA-pair (cta_group::2) execution where the shape qualifies
 };
 
