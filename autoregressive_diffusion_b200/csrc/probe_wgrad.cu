@@ -17,6 +17,7 @@ struct Problem {
   const char* name;
   int g_seq[2], g_T[2], a_T[2];
   int H, W, Cin, Cout, w_taps, n_split;
+  int flat;   // WgradLaunch::force_mode
   std::vector<WgradItem> items;
 };
 static WgradItem mk(int pair, int dt, int dy, int dx, int wtap) { WgradItem t{}; t.pair = pair; t.dt = dt; t.dy = dy; t.dx = dx; t.wtap = wtap; return t; }
@@ -40,7 +41,7 @@ static bool run(const Problem& P, bool check, int reps) {
   WgradLaunch L;
   for (int s = 0; s < 2; ++s) { L.g[s] = dG[s]; L.a[s] = dA[s]; L.g_seq[s] = P.g_seq[s]; L.g_T[s] = P.g_T[s]; L.a_T[s] = P.a_T[s]; }
   L.items = P.items.data(); L.n_items = (int)P.items.size(); L.H = P.H; L.W = P.W; L.Cin = P.Cin; L.Cout = P.Cout;
-  L.w_taps = P.w_taps; L.n_split = P.n_split; L.out = dOut;
+  L.w_taps = P.w_taps; L.n_split = P.n_split; L.out = dOut; L.force_mode = P.flat;
   int rc = wgrad_launch(L, 0);
   cudaError_t e = cudaDeviceSynchronize();
   if (rc != OB_OK || e != cudaSuccess) { printf("[%s] LAUNCH FAIL rc=%d (%s) cuda=%s\n", P.name, rc, last_error(), cudaGetErrorString(e)); return false; }
@@ -114,6 +115,13 @@ int main(int argc, char** argv) {
   fails += !run(plain("wgrad linear c256 n128 T37", 37, 1, 1, 256, 128, 1, 1), true, 0);
   fails += !run(gated("wgrad gated c128 n128 8x8 B2 n4", 2, 4, 8, 8, 128, 128, 2), true, 0);
   fails += !run(gated("wgrad gated c64 n192 4x4 B1 n8", 1, 8, 4, 4, 64, 192, 0), true, 0);
+  // CTA pairs (Cout a multiple of 256) and two-tap groups (Cin = 128), alone and combined
+  { Problem q = gated("wgrad gated c256 n256 8x8 B1 n4 (pair)", 1, 4, 8, 8, 256, 256, 2); q.flat = 2; fails += !run(q, true, 0); }
+  { Problem q = gated("wgrad gated c128 n256 8x8 B1 n4 (pair + two-tap)", 1, 4, 8, 8, 128, 256, 2); q.flat = 2; fails += !run(q, true, 0); }
+  fails += !run(gated("wgrad gated c128 n256 8x8 B1 n4 (two-tap)", 1, 4, 8, 8, 128, 256, 2), true, 0);
+  fails += !run(plain("wgrad 3x3 c128 n128 8x8 F6 (two-tap, odd count)", 6, 8, 8, 128, 128, 3, 2), true, 0);
+  { Problem q = plain("wgrad 1x1 c512 n512 4x4 F8 (pair)", 8, 4, 4, 512, 512, 1, 1); q.flat = 2; fails += !run(q, true, 0); }
+  { Problem q = plain("wgrad 3x3 c384 n256 8x8 F3 (pair, ragged ci tile)", 3, 8, 8, 384, 256, 3, 1); q.flat = 2; fails += !run(q, true, 0); }
   printf("== wgrad correctness: %d failing ==\n", fails);
   if (perf) {
     run(gated("CS 512->512 16x16 B2 n16", 2, 16, 16, 16, 512, 512, 0), false, 20);
@@ -122,6 +130,13 @@ int main(int argc, char** argv) {
     run(gated("CS 512->512 8x8 B2 n16", 2, 16, 8, 8, 512, 512, 0), false, 20);
     run(gated("CS 512->512 4x4 B2 n16", 2, 16, 4, 4, 512, 512, 0), false, 20);
     run(gated("CS 1024->512 8x8 B2 n16", 2, 16, 8, 8, 1024, 512, 0), false, 20);
+    { Problem q = gated("CS 512->512 16x16 FLAT", 2, 16, 16, 16, 512, 512, 0); q.flat = 1; run(q, false, 20); }
+    { Problem q = gated("CS 256->256 16x16 FLAT", 2, 16, 16, 16, 256, 256, 0); q.flat = 1; run(q, false, 20); }
+    { Problem q = gated("CS 128->128 32x32 FLAT", 2, 16, 32, 32, 128, 128, 0); q.flat = 1; run(q, false, 20); }
+    { Problem q = gated("CS 512->512 8x8 FLAT", 2, 16, 8, 8, 512, 512, 0); q.flat = 1; run(q, false, 20); }
+    { Problem q = gated("CS 512->512 4x4 FLAT", 2, 16, 4, 4, 512, 512, 0); q.flat = 1; run(q, false, 20); }
+    { Problem q = gated("CS 512->512 16x16 PAIR", 2, 16, 16, 16, 512, 512, 0); q.flat = 2; run(q, false, 20); }
+    run(gated("CS 256->128 32x32 B2 n16", 2, 16, 32, 32, 256, 128, 0), false, 20);
     run(gated("CS 512->512 16x16 split1", 2, 16, 16, 16, 512, 512, 1), false, 20);
     run(gated("CS 512->512 16x16 split4", 2, 16, 16, 16, 512, 512, 4), false, 20);
   }

@@ -26,43 +26,59 @@ struct WgradItem {
   int32_t wtap;
 };
 
+// One CTA's work: NT taps that share the gradient tile (same tensor pair).  wtap[j] < 0 marks a missing tap.
+struct WgradGroup {
+  int8_t pair;
+  int8_t dt[2], dy[2], dx[2];
+  int8_t pad_;
+  int32_t wtap[2];
+};
+
 struct WgradParams {
   CUtensorMap mapG[2];
   CUtensorMap mapA[2];
-  WgradItem items[WGRAD_MAX_ITEMS];
-  int n_items;
+  WgradGroup groups[WGRAD_MAX_ITEMS];
+  int n_groups;
   int n_seq[2], T[2];  // pixel-row space of each pair (rows of G)
   int H, W;
   int Cin, Cout, w_taps;
   int bw, bh, bt;
   int tiles_w, tiles_h;
   int tiles_t[2];
-  int ci_tiles;
+  int ci_tiles, co_tiles;
   int n_split;
   float* out;  // [n_split, Cout, w_taps, Cin] fp32
 };
 
-template <int CHUNK, int BN>
+// BN = input-channel span of one tap; the MMA's N is BN*NT.  PAIR: two CTAs (adjacent output-channel tiles) run one
+// M=256 MMA stream, each staging its own gradient tile but only half of the activation boxes.
+template <int CHUNK, int BN, int NT, bool PAIR>
 struct WgradCfg {
+  static constexpr int N = BN * NT;
   static constexpr int ROW_BYTES = CHUNK * 2;
   static constexpr int BOX_BYTES = WGRAD_KT * ROW_BYTES;
   static constexpr int G_BOXES = 128 / CHUNK;
-  static constexpr int A_BOXES = BN / CHUNK;
+  static constexpr int A_BOXES = N / CHUNK;                         // of the whole MMA
+  static constexpr int A_LOCAL = PAIR ? A_BOXES / 2 : A_BOXES;      // staged by this CTA
+  static constexpr int BOXES_PER_TAP = BN / CHUNK;
   static constexpr int G_BYTES = G_BOXES * BOX_BYTES;
-  static constexpr int A_BYTES = A_BOXES * BOX_BYTES;
+  static constexpr int A_BYTES = A_LOCAL * BOX_BYTES;
   static constexpr int STAGE_BYTES = G_BYTES + A_BYTES;
+  static constexpr int TX_BYTES = PAIR ? 2 * STAGE_BYTES : STAGE_BYTES;   // credited to the leader's barrier
   static constexpr int STAGES_RAW = (200 * 1024) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
-  static constexpr int CW = BN >= 32 ? 32 : 16;
+  static constexpr int CW = N >= 32 ? 32 : 16;
 };
 
-template <int CHUNK, int BN>
+template <int CHUNK, int BN, int NT, bool PAIR>
 __global__ void __launch_bounds__(WGRAD_THREADS, 1) wgrad_kernel(const __grid_constant__ WgradParams p) {
-  using Cfg = WgradCfg<CHUNK, BN>;
+  using Cfg = WgradCfg<CHUNK, BN, NT, PAIR>;
   constexpr int STAGES = Cfg::STAGES;
+  constexpr int N = Cfg::N;
   constexpr uint32_t SWZ = SwizzleFor<CHUNK>::mode;
   constexpr uint32_t SBO = 8 * Cfg::ROW_BYTES;
+  static_assert(!PAIR || Cfg::A_BOXES % 2 == 0, "pair mode splits the activation boxes in two");
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -74,17 +90,19 @@ __global__ void __launch_bounds__(WGRAD_THREADS, 1) wgrad_kernel(const __grid_co
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
 
-  const WgradItem item = p.items[blockIdx.y];
-  const int pr = item.pair;
-  const int ci_tile = blockIdx.x % p.ci_tiles;
-  const int co_tile = blockIdx.x / p.ci_tiles;
+  const WgradGroup grp = p.groups[blockIdx.y];
+  const int pr = grp.pair;
+  const int co_tile = blockIdx.x % p.co_tiles;   // output-channel tile fastest: the CTAs of a pair share the ci tile
+  const int ci_tile = blockIdx.x / p.co_tiles;
   const int co0 = co_tile * 128, ci0 = ci_tile * BN;
   const int k_tiles = p.n_seq[pr] * p.tiles_t[pr] * p.tiles_h * p.tiles_w;
   const int k_begin = static_cast<int>(static_cast<long>(k_tiles) * blockIdx.z / p.n_split);
   const int k_end = static_cast<int>(static_cast<long>(k_tiles) * (blockIdx.z + 1) / p.n_split);
 
-  constexpr uint32_t tmem_cols = BN < 32 ? 32 : BN;
+  constexpr uint32_t tmem_cols = N < 32 ? 32 : N;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -97,11 +115,12 @@ __global__ void __launch_bounds__(WGRAD_THREADS, 1) wgrad_kernel(const __grid_co
     tma_prefetch_desc(&p.mapA[pr]);
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, tmem_cols);
-    tmem_relinquish();
+    if constexpr (PAIR) { tmem_alloc_pair(tmem_slot, tmem_cols); tmem_relinquish_pair(); }
+    else { tmem_alloc(tmem_slot, tmem_cols); tmem_relinquish(); }
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
@@ -120,40 +139,60 @@ __global__ void __launch_bounds__(WGRAD_THREADS, 1) wgrad_kernel(const __grid_co
       if (elect_one()) {
         const uint32_t sG = smem_base + stage * Cfg::STAGE_BYTES;
         const uint32_t sA = sG + Cfg::G_BYTES;
-        mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+        if (!PAIR || leader) mbar_arrive_expect_tx(full_bar(stage), Cfg::TX_BYTES);
 #pragma unroll
-        for (int j = 0; j < Cfg::G_BOXES; ++j)
-          tma_load_5d(sG + j * Cfg::BOX_BYTES, &p.mapG[pr], full_bar(stage), co0 + j * CHUNK, w0, h0, t0, seq);
+        for (int j = 0; j < Cfg::G_BOXES; ++j) {
+          if constexpr (PAIR) tma_load_5d_pair(sG + j * Cfg::BOX_BYTES, &p.mapG[pr], full_bar(stage), co0 + j * CHUNK, w0, h0, t0, seq);
+          else tma_load_5d(sG + j * Cfg::BOX_BYTES, &p.mapG[pr], full_bar(stage), co0 + j * CHUNK, w0, h0, t0, seq);
+        }
 #pragma unroll
-        for (int j = 0; j < Cfg::A_BOXES; ++j)
-          tma_load_5d(sA + j * Cfg::BOX_BYTES, &p.mapA[pr], full_bar(stage), ci0 + j * CHUNK, w0 + item.dx, h0 + item.dy,
-                      t0 + item.dt, seq);
+        for (int jl = 0; jl < Cfg::A_LOCAL; ++jl) {
+          const int j = jl + static_cast<int>(rank) * Cfg::A_LOCAL;   // box index within the whole N extent
+          const int tap = j / Cfg::BOXES_PER_TAP, cb = j % Cfg::BOXES_PER_TAP;
+          const int ca = ci0 + cb * CHUNK;
+          if constexpr (PAIR)
+            tma_load_5d_pair(sA + jl * Cfg::BOX_BYTES, &p.mapA[pr], full_bar(stage), ca, w0 + grp.dx[tap], h0 + grp.dy[tap],
+                             t0 + grp.dt[tap], seq);
+          else
+            tma_load_5d(sA + jl * Cfg::BOX_BYTES, &p.mapA[pr], full_bar(stage), ca, w0 + grp.dx[tap], h0 + grp.dy[tap],
+                        t0 + grp.dt[tap], seq);
+        }
       }
       __syncwarp();
       if (++stage == STAGES) { stage = 0; phase ^= 1; }
     }
   } else if (warp == 1) {
-    constexpr uint32_t idesc = make_idesc_bf16(128, BN, 1, 1);
+    constexpr uint32_t idesc = make_idesc_bf16(PAIR ? 256 : 128, N, 1, 1);
     const uint64_t desc0 = make_smem_desc(0, Cfg::BOX_BYTES, SBO, SWZ);
     int stage = 0;
     uint32_t phase = 0;
-    for (int kt = k_begin; kt < k_end; ++kt) {
-      mbar_wait(full_bar(stage), phase);
-      tc_fence_after();
-      if (elect_one()) {
-        const uint32_t sG = smem_base + stage * Cfg::STAGE_BYTES;
-        const uint64_t adesc = desc0 + (sG >> 4), bdesc = desc0 + ((sG + Cfg::G_BYTES) >> 4);
-        umma_bf16_ss(tmem_base, adesc, bdesc, idesc, kt > k_begin ? 1u : 0u);
+    if (leader) {
+      for (int kt = k_begin; kt < k_end; ++kt) {
+        mbar_wait(full_bar(stage), phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t sG = smem_base + stage * Cfg::STAGE_BYTES;
+          const uint64_t adesc = desc0 + (sG >> 4), bdesc = desc0 + ((sG + Cfg::G_BYTES) >> 4);
+          if constexpr (PAIR) {
+            umma_bf16_ss_pair(tmem_base, adesc, bdesc, idesc, kt > k_begin ? 1u : 0u);
 #pragma unroll
-        for (int k = 1; k < WGRAD_KT / 16; ++k)
-          umma_bf16_ss(tmem_base, adesc + k * ((2 * SBO) >> 4), bdesc + k * ((2 * SBO) >> 4), idesc, 1u);
-        umma_commit(empty_bar(stage));
+            for (int k = 1; k < WGRAD_KT / 16; ++k)
+              umma_bf16_ss_pair(tmem_base, adesc + k * ((2 * SBO) >> 4), bdesc + k * ((2 * SBO) >> 4), idesc, 1u);
+            umma_commit_pair(empty_bar(stage));
+          } else {
+            umma_bf16_ss(tmem_base, adesc, bdesc, idesc, kt > k_begin ? 1u : 0u);
+#pragma unroll
+            for (int k = 1; k < WGRAD_KT / 16; ++k)
+              umma_bf16_ss(tmem_base, adesc + k * ((2 * SBO) >> 4), bdesc + k * ((2 * SBO) >> 4), idesc, 1u);
+            umma_commit(empty_bar(stage));
+          }
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
+      if (elect_one()) { if constexpr (PAIR) umma_commit_pair(tmem_full_bar); else umma_commit(tmem_full_bar); }
       __syncwarp();
-      if (++stage == STAGES) { stage = 0; phase ^= 1; }
     }
-    if (elect_one()) umma_commit(tmem_full_bar);
-    __syncwarp();
   } else {
     constexpr int CW = Cfg::CW;
     const int q = warp & 3;
@@ -161,15 +200,17 @@ __global__ void __launch_bounds__(WGRAD_THREADS, 1) wgrad_kernel(const __grid_co
     mbar_wait_sleep(tmem_full_bar, 0);
     tc_fence_after();
     const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    float* dst_row = p.out + ((static_cast<long>(blockIdx.z) * p.Cout + co) * p.w_taps + item.wtap) * p.Cin;
     const bool have = k_end > k_begin;
-    for (int c = 0; c < BN / CW; ++c) {
+    for (int c = 0; c < N / CW; ++c) {
       float v[CW];
       if constexpr (CW == 32) tmem_ld32(lane_base + c * CW, v);
       else tmem_ld16(lane_base + c * CW, v);
       tmem_ld_wait();
-      if (co < p.Cout) {
-        const int col0 = ci0 + c * CW;
+      const int tap = (c * CW) / BN;              // CW divides BN
+      const int wtap = grp.wtap[tap];
+      if (co < p.Cout && wtap >= 0) {
+        float* dst_row = p.out + ((static_cast<long>(blockIdx.z) * p.Cout + co) * p.w_taps + wtap) * p.Cin;
+        const int col0 = ci0 + (c * CW) % BN;
 #pragma unroll
         for (int j = 0; j < CW; j += 4)
           if (col0 + j + 4 <= p.Cin)
@@ -180,9 +221,10 @@ __global__ void __launch_bounds__(WGRAD_THREADS, 1) wgrad_kernel(const __grid_co
     tc_fence_before();
   }
   __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, tmem_cols);
+    if constexpr (PAIR) tmem_dealloc_pair(tmem_base, tmem_cols); else tmem_dealloc(tmem_base, tmem_cols);
   }
 }
 
