@@ -49,6 +49,7 @@ _SIGS = {
     "ob_scale_silu_bwd": "pppppiiip",
     "ob_mp_sum_fwd": "ppplffp",
     "ob_mp_sum_bwd": "pppplffp",
+    "ob_adamw_ema": "pppppplpffffffp",
     "ob_qkv_prep_fwd": "ppppppppppliifp",
     "ob_qkv_prep_bwd": "ppppppppppliifp",
     "ob_rope_k": "ppppppliip",

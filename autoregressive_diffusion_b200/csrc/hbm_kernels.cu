@@ -868,4 +868,62 @@ int mp_sum_bwd(const void* g, const void* out, void* da, void* db, long n, float
   return check_launch("mp_sum_bwd");
 }
 
+// ----------------------------------------------------------------------------- optimizer
+// AdamW (decoupled weight decay, bias-corrected; the update torch.optim.AdamW applies in cs_train.py:121-124) fused with
+// the two power-function-free EMA copies of the weights (cs_train.py:125) and the gradient reset, over ONE flat fp32
+// range: 6 streams read, 6 written, once per optimizer step.  step_lr points at {step (already incremented), lr}.
+__global__ void __launch_bounds__(256) adamw_ema_kernel(float4* __restrict__ p, float4* __restrict__ g, float4* __restrict__ m,
+                                                        float4* __restrict__ v, float4* __restrict__ e1, float4* __restrict__ e2,
+                                                        long n4, const float* __restrict__ step_lr, float beta1, float beta2,
+                                                        float eps, float wd, float ema1, float ema2) {
+  const float step = step_lr[0], lr = step_lr[1];
+  const float bc1 = 1.f - powf(beta1, step);
+  const float bc2_sqrt = sqrtf(1.f - powf(beta2, step));
+  const float step_size = lr / bc1;
+  const float decay = 1.f - lr * wd;
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    float4 pv = p[i], mv = m[i], vv = v[i];
+    const float4 gv = g[i];
+    float* pp = &pv.x; float* mm = &mv.x; float* vp = &vv.x; const float* gg = &gv.x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      mm[k] = beta1 * mm[k] + (1.f - beta1) * gg[k];
+      vp[k] = beta2 * vp[k] + (1.f - beta2) * gg[k] * gg[k];
+      const float denom = sqrtf(vp[k]) / bc2_sqrt + eps;
+      pp[k] = pp[k] * decay - step_size * (mm[k] / denom);
+    }
+    p[i] = pv; m[i] = mv; v[i] = vv;
+    g[i] = zero;
+    if (e1 != nullptr) {
+      float4 e = e1[i]; float* ee = &e.x;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) ee[k] += (1.f - ema1) * (pp[k] - ee[k]);
+      e1[i] = e;
+    }
+    if (e2 != nullptr) {
+      float4 e = e2[i]; float* ee = &e.x;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) ee[k] += (1.f - ema2) * (pp[k] - ee[k]);
+      e2[i] = e;
+    }
+  }
+}
+
+int adamw_ema(float* p, float* g, float* m, float* v, float* e1, float* e2, long n, const float* step_lr, float beta1,
+              float beta2, float eps, float wd, float ema1, float ema2, cudaStream_t st) {
+  if (n % 4 != 0) { set_error("adamw_ema: element count %ld must be a multiple of 4", n); return OB_ERR_INVALID; }
+  for (const void* q : {(const void*)p, (const void*)g, (const void*)m, (const void*)v, (const void*)e1, (const void*)e2})
+    if (reinterpret_cast<uintptr_t>(q) % 16 != 0) { set_error("adamw_ema: buffers must be 16-byte aligned"); return OB_ERR_INVALID; }
+  if (n <= 0) return OB_OK;
+  const long n4 = n / 4;
+  long blocks = (n4 + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  adamw_ema_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(reinterpret_cast<float4*>(p), reinterpret_cast<float4*>(g),
+                                                                 reinterpret_cast<float4*>(m), reinterpret_cast<float4*>(v),
+                                                                 reinterpret_cast<float4*>(e1), reinterpret_cast<float4*>(e2), n4,
+                                                                 step_lr, beta1, beta2, eps, wd, ema1, ema2);
+  return check_launch("adamw_ema");
+}
+
 }  // namespace ob

@@ -4,6 +4,7 @@
 #include <cudaTypedefs.h>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <mutex>
 
 #include "tapconv.cuh"

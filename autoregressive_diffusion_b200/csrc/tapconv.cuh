@@ -151,13 +151,18 @@ __global__ void __launch_bounds__(TAPCONV_THREADS, 1) tapconv_kernel(const __gri
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
   const bool leader = rank == 0;
 
-  // ---- tile walk.  PAIR: pixel tile fastest, so tiles (2k, 2k+1) -- the two CTAs of a cluster -- share the channel tile
+  // ---- tile walk.  PAIR: tiles (2k, 2k+1) -- the two CTAs of a cluster -- are adjacent pixel tiles of one channel tile
   const int total_tiles = PAIR ? p.m_tiles_pad * p.tiles_n : p.tiles_w * p.tiles_h * p.tiles_t * p.n_seq * p.tiles_n;
   struct Tile { int w0, h0, t0, seq, n0; };
   auto decode = [&](int tile) {
     int n_tile;
-    if constexpr (PAIR) { n_tile = tile / p.m_tiles_pad; tile -= n_tile * p.m_tiles_pad; }
-    else { n_tile = tile % p.tiles_n; tile /= p.tiles_n; }
+    if constexpr (PAIR) {
+      // pairs walk the channel tiles fastest: concurrently running clusters then share activation tiles (same pixel
+      // pair, different channel tile) as well as weight tiles, and L2 merges the coincident reads
+      const int pt = tile >> 1;
+      n_tile = pt % p.tiles_n;
+      tile = 2 * (pt / p.tiles_n) + (tile & 1);
+    } else { n_tile = tile % p.tiles_n; tile /= p.tiles_n; }
     Tile c;
     c.w0 = (tile % p.tiles_w) * p.bw; tile /= p.tiles_w;
     c.h0 = (tile % p.tiles_h) * p.bh; tile /= p.tiles_h;

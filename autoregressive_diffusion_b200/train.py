@@ -37,6 +37,11 @@ def init_distributed():
     return rank, world, local
 
 
+def _pad64(n):
+    """Every per-parameter view starts 256-byte aligned (the kernels use 128-bit accesses)."""
+    return (n + 63) // 64 * 64
+
+
 class GradientBuckets:
     """Gradient mean over the data-parallel ranks (the job DistributedDataParallel does in cs_train.py:54,108-109).
 
@@ -53,15 +58,15 @@ class GradientBuckets:
 
     def flatten(self):
         live = [p for p in self.params if p.grad is not None]
-        pad = lambda n: (n + 63) // 64 * 64          # keep every view 256-byte aligned (the kernels use 128-bit accesses)
-        total = sum(pad(p.numel()) for p in live)
+        total = sum(_pad64(p.numel()) for p in live)
         self.flat = torch.zeros(total, dtype=torch.float32, device=live[0].device)
         off = 0
         for p in live:
             view = self.flat[off:off + p.numel()].view_as(p)
             view.copy_(p.grad)
             p.grad = view
-            off += pad(p.numel())
+            off += _pad64(p.numel())
+        self.live = live
         self.buckets = [self.flat[i:i + self.bucket_elems] for i in range(0, total, self.bucket_elems)]
 
     def all_reduce_mean(self):
@@ -79,6 +84,63 @@ class GradientBuckets:
                 b.div_(world)
         if self.stream is not None:
             torch.cuda.current_stream().wait_stream(self.stream)
+
+
+class FusedAdamWEMA:
+    """AdamW + the EMA copies of the weights + the gradient reset as ONE kernel launch over flat fp32 buffers
+    (cs_train.py:121-125 runs torch.optim.AdamW.step, zero_grad and one lerp per EMA: ~10 passes over the weights).
+
+    After the first backward has shown which parameters are live, their storage is re-homed into one flat buffer laid
+    out exactly like GradientBuckets.flat; exp_avg / exp_avg_sq / each EMA are flat buffers of the same layout (the
+    64-element pads between views hold zeros and stay zero under the update).  Parameters that never receive a gradient
+    are left alone, as torch.optim does."""
+
+    def __init__(self, params, buckets, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01, ema_betas=()):
+        assert len(ema_betas) <= 2
+        self.params, self.buckets = list(params), buckets
+        self.betas, self.eps, self.weight_decay, self.ema_betas = betas, eps, weight_decay, tuple(ema_betas)
+        dev = self.params[0].device
+        self.step_lr = torch.tensor([0.0, float(lr)], dtype=torch.float32, device=dev)   # {step count, learning rate}
+        self.lr = self.step_lr[1:]            # a device tensor: a schedule can write it between (graph-replayed) steps
+        self.ema = [[p.detach().clone() for p in self.params] for _ in self.ema_betas]
+        self.flat_p = None
+
+    def _flatten(self):
+        if self.buckets.flat is None:
+            self.buckets.flatten()
+        g = self.buckets.flat
+        live = self.buckets.live
+        index = {id(p): i for i, p in enumerate(self.params)}
+        self.flat_p = torch.zeros_like(g)
+        self.exp_avg, self.exp_avg_sq = torch.zeros_like(g), torch.zeros_like(g)
+        self.flat_ema = [torch.zeros_like(g) for _ in self.ema_betas]
+        off = 0
+        with torch.no_grad():
+            for p in live:
+                n = p.numel()
+                view = self.flat_p[off:off + n].view_as(p)
+                view.copy_(p)
+                p.data = view
+                for k, fe in enumerate(self.flat_ema):
+                    ev = fe[off:off + n].view_as(p)
+                    ev.copy_(self.ema[k][index[id(p)]])
+                    self.ema[k][index[id(p)]] = ev
+                off += _pad64(n)
+
+    @torch.no_grad()
+    def step(self):
+        """Update from the accumulated (and already all-reduced) gradients, then zero them."""
+        if not self.params[0].is_cuda:
+            raise RuntimeError("FusedAdamWEMA runs on CUDA tensors only (no CPU fallback)")
+        if self.flat_p is None:
+            self._flatten()
+        from ._lib import _vp, call, stream_ptr
+        self.step_lr[:1] += 1
+        e = [_vp(t) for t in self.flat_ema] + [None, None]
+        b = list(self.ema_betas) + [0.0, 0.0]
+        call("ob_adamw_ema", _vp(self.flat_p), _vp(self.buckets.flat), _vp(self.exp_avg), _vp(self.exp_avg_sq), e[0], e[1],
+             self.flat_p.numel(), _vp(self.step_lr), self.betas[0], self.betas[1], self.eps, self.weight_decay, b[0], b[1],
+             stream_ptr())
 
 
 class _Null:
@@ -103,12 +165,12 @@ class Trainer:
         self.loss_fn = EDM2Loss(P_mean=P_mean, P_std=P_std, sigma_data=sigma_data, context_noise_reduction=context_noise_reduction)
         self.params = [p for p in self.precond.parameters() if p.requires_grad]
         on_gpu = self.device.type == "cuda"
-        self.lr = torch.tensor(float(lr), device=self.device) if on_gpu else lr     # a tensor: the schedule can change it
-        self.opt = torch.optim.AdamW(self.params, lr=self.lr, eps=eps, fused=on_gpu, capturable=on_gpu)
-        self.ema = [[p.detach().clone() for p in self.params] for _ in ema_betas]
         self.ema_betas = ema_betas
         self.accum = accumulation_steps
         self.buckets = GradientBuckets(self.params)
+        self.opt = FusedAdamWEMA(self.params, self.buckets, lr=lr, eps=eps, ema_betas=ema_betas)
+        self.lr = self.opt.lr                 # device tensor: the schedule can change it
+        self.ema = self.opt.ema
         self.micro = 0
         self.just_2d_every = just_2d_every
         self.precond.train()
@@ -124,10 +186,6 @@ class Trainer:
 
     def _optimizer_step(self):
         self.opt.step()
-        self.opt.zero_grad(set_to_none=False)
-        with torch.no_grad():
-            for beta, shadow in zip(self.ema_betas, self.ema):
-                torch._foreach_lerp_(shadow, self.params, 1 - beta)
 
     def micro_step(self, latents, conditioning=None):
         """One micro-batch forward+backward; every `accum`-th call also syncs gradients and steps the optimizer."""
@@ -154,8 +212,7 @@ class Trainer:
                 self.micro_step(self.static_x)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        if self.buckets.flat is None and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            self.buckets.flatten()             # gradient views must be in place before their addresses are captured
+        assert self.opt.flat_p is not None     # the warm-up cycles re-homed parameters and gradients into flat buffers
         self.graphs = {}
         plan = ["first"] + ["mid"] * (self.accum - 2) + ["last"]
         for kind in plan:

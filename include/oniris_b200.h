@@ -134,6 +134,14 @@ int ob_scale_silu_bwd(const void* y, const float* cscale, const void* g, void* d
 int ob_mp_sum_fwd(const void* a, const void* b, void* out, int64_t n, float t, float clip, void* stream);
 int ob_mp_sum_bwd(const void* g, const void* out, void* da, void* db, int64_t n, float t, float clip, void* stream);
 
+/* Optimizer step of the training loop (cs_train.py:121-125: torch.optim.AdamW.step, zero_grad, and the EMA copies of
+ * the weights) over one flat fp32 range of n elements (n % 4 == 0, 16-byte aligned buffers):
+ *   m = b1*m + (1-b1)*g;  v = b2*v + (1-b2)*g*g;  p = p*(1 - lr*wd) - lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
+ *   ema_k += (1 - ema_beta_k) * (p - ema_k)   (either pointer may be NULL);   g = 0.
+ * step_lr: device fp32 {t, lr} with t the 1-based step count of THIS update. */
+int ob_adamw_ema(float* p, float* g, float* m, float* v, float* ema1, float* ema2, int64_t n, const float* step_lr,
+                 float beta1, float beta2, float eps, float weight_decay, float ema_beta1, float ema_beta2, void* stream);
+
 /* ---------------------------------------------------------------------------------------------- attention
  * edm2/attention/attention_modules.py:59-77: compiled_flex_attention(q,k,v, make_train_mask / make_infer_mask) and
  * F.scaled_dot_product_attention.  q: bf16 [B, Lq, heads, 64], k,v: bf16 [B, Lk, heads, 64] (NHWC rows); q,k RMS-normalised and
