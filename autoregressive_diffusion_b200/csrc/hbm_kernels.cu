@@ -270,13 +270,23 @@ __global__ void __launch_bounds__(256) gate_bwd_kernel(const __nv_bfloat16* __re
     }
     *reinterpret_cast<bf16x8*>(gb + static_cast<long>(bt) * frame_elems + e) = pack8(acc_b);
   }
-  for (int s = 0; s < S; ++s) {
-    const long f = (static_cast<long>(b) * S + s) * T + t;
-    const float a = block_sum(sy[s], red);
-    const float c = block_sum(sd[s], red);
-    if (threadIdx.x == 0) {
-      atomicAdd(&s_y[f], a);
-      atomicAdd(&s_d[f], c);
+  // one combined block reduction of the four inner products (each CTA carries little data: keep its tail short)
+  {
+    __shared__ float red4[4][8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float v[4] = {warp_sum(sy[0]), warp_sum(sd[0]), warp_sum(sy[1]), warp_sum(sd[1])};
+    if (lane == 0) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) red4[k][warp] = v[k];
+    }
+    __syncthreads();
+    if (threadIdx.x < 2 * S) {
+      const int k = threadIdx.x;            // k = 2*s + {0: <dy,y>, 1: <dy,d>}
+      float tsum = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) tsum += red4[k][w];
+      const long f = (static_cast<long>(b) * S + (k >> 1)) * T + t;
+      atomicAdd((k & 1) ? &s_d[f] : &s_y[f], tsum);
     }
   }
   if (gg.counter == nullptr) return;
@@ -730,8 +740,9 @@ int gate_bwd(const void* dy, const void* y, const void* d, const float* alpha, c
     return OB_ERR_INVALID;
   }
   if (n_seq * T <= 0) return OB_OK;
+  // enough CTAs to fill the GPU, but several 16-byte vectors per thread so a CTA is not all reduction tail
   int bx = static_cast<int>((frame_elems / 8 + 255) / 256);
-  if (bx > 64) bx = 64;
+  while (bx > 1 && static_cast<long>(bx) * n_seq * T > 4 * 148) bx = (bx + 1) / 2;
   dim3 grid(bx, n_seq * T);
   gate_bwd_kernel<<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(y),
                                         static_cast<const float*>(d), alpha, beta,
