@@ -49,6 +49,8 @@ _SIGS = {
     "ob_scale_silu_bwd": "pppppiiip",
     "ob_mp_sum_fwd": "ppplffp",
     "ob_mp_sum_bwd": "pppplffp",
+    "ob_mp_cat_fwd": "pppliifp",
+    "ob_mp_cat_bwd": "pppliifp",
     "ob_adamw_ema": "pppppplpffffffp",
     "ob_qkv_prep_fwd": "ppppppppppliifp",
     "ob_qkv_prep_bwd": "ppppppppppliifp",

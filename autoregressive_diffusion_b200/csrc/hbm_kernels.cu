@@ -879,6 +879,47 @@ int mp_sum_bwd(const void* g, const void* out, void* da, void* db, long n, float
   return check_launch("mp_sum_bwd");
 }
 
+// ============================================================================ mp_cat
+// Reference: edm2/utils.py:128-134 (decoder skip connections, edm2/networks_edm2.py:244): channel concatenation with
+// magnitude-preserving weights, out[row] = [a[row]*wa | b[row]*wb] over NHWC rows.  One pass instead of two scaled
+// copies and a cat; the backward splits and scales the gradient the same way.  DIR 0: forward, 1: backward.
+template <int DIR>
+__global__ void __launch_bounds__(256) mp_cat_kernel(__nv_bfloat16* __restrict__ a, __nv_bfloat16* __restrict__ b,
+                                                     __nv_bfloat16* __restrict__ cat, long rows, int ca8, int cb8, float wa,
+                                                     float wb) {
+  const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int c8 = ca8 + cb8;
+  if (i >= rows * c8) return;
+  const long row = i / c8;
+  const int v = static_cast<int>(i - row * c8);
+  const bool first = v < ca8;
+  bf16x8* side = first ? reinterpret_cast<bf16x8*>(a) + row * ca8 + v : reinterpret_cast<bf16x8*>(b) + row * cb8 + (v - ca8);
+  bf16x8* joint = reinterpret_cast<bf16x8*>(cat) + i;
+  const float w = first ? wa : wb;
+  float f[8];
+  unpack8(DIR == 0 ? *side : *joint, f);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) f[j] *= w;
+  if (DIR == 0) *joint = pack8(f);
+  else *side = pack8(f);
+}
+
+int mp_cat(void* a, void* b, void* cat, long rows, int ca, int cb, float t, int backward, cudaStream_t st) {
+  if (ca % 8 != 0 || cb % 8 != 0) { set_error("mp_cat: channel counts %d, %d must be multiples of 8", ca, cb); return OB_ERR_INVALID; }
+  if (rows <= 0) return OB_OK;
+  const float c = sqrtf(static_cast<float>(ca + cb) / ((1.f - t) * (1.f - t) + t * t));
+  const float wa = c / sqrtf(static_cast<float>(ca)) * (1.f - t), wb = c / sqrtf(static_cast<float>(cb)) * t;
+  const long n = rows * ((ca + cb) / 8);
+  const unsigned blocks = static_cast<unsigned>((n + 255) / 256);
+  if (backward)
+    mp_cat_kernel<1><<<blocks, 256, 0, st>>>(static_cast<__nv_bfloat16*>(a), static_cast<__nv_bfloat16*>(b),
+                                             static_cast<__nv_bfloat16*>(cat), rows, ca / 8, cb / 8, wa, wb);
+  else
+    mp_cat_kernel<0><<<blocks, 256, 0, st>>>(static_cast<__nv_bfloat16*>(a), static_cast<__nv_bfloat16*>(b),
+                                             static_cast<__nv_bfloat16*>(cat), rows, ca / 8, cb / 8, wa, wb);
+  return check_launch("mp_cat");
+}
+
 // ----------------------------------------------------------------------------- optimizer
 // AdamW (decoupled weight decay, bias-corrected; the update torch.optim.AdamW applies in cs_train.py:121-124) fused with
 // the two power-function-free EMA copies of the weights (cs_train.py:125) and the gradient reset, over ONE flat fp32

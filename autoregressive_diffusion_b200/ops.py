@@ -358,6 +358,32 @@ class MpSumFn(torch.autograd.Function):
         return da, db, None, None
 
 
+class MpCatFn(torch.autograd.Function):
+    """mp_cat(a, b, dim=1, t)   [edm2/utils.py:128-134]: one kernel each way instead of two scaled copies + cat."""
+
+    @staticmethod
+    def forward(ctx, a, b, t):
+        f, ca, h, w = a.shape
+        cb = b.shape[1]
+        out = empty_rows(f, ca + cb, h, w, a.device)
+        call("ob_mp_cat_fwd", _vp(a), _vp(b), _vp(out), f * h * w, ca, cb, t, stream_ptr())
+        ctx.dims = (f, ca, cb, h, w, t)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        f, ca, cb, h, w, t = ctx.dims
+        g = rows(g)
+        da = empty_rows(f, ca, h, w, g.device)
+        db = empty_rows(f, cb, h, w, g.device)
+        call("ob_mp_cat_bwd", _vp(g), _vp(da), _vp(db), f * h * w, ca, cb, t, stream_ptr())
+        return da, db, None
+
+
+def mp_cat_rows(a, b, t=0.5):
+    return MpCatFn.apply(rows(a), rows(b), float(t))
+
+
 def pixnorm_silu(x, eps=1e-4):
     return PixnormSiluFn.apply(rows(x), 0, eps)
 

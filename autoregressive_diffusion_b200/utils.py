@@ -50,6 +50,8 @@ def mp_sum(a, b, t=0.5):
 def mp_cat(a, b, dim=1, t=0.5):
     """edm2/utils.py:128-134."""
     na, nb = a.shape[dim], b.shape[dim]
+    if a.ndim == 4 and dim == 1 and a.is_cuda and na % 8 == 0 and nb % 8 == 0 and a.shape[0] == b.shape[0] and a.shape[2:] == b.shape[2:]:
+        return ops.mp_cat_rows(a, b, t)            # one kernel over NHWC rows
     c = math.sqrt((na + nb) / ((1 - t) ** 2 + t ** 2))
     return torch.cat([a * (c / math.sqrt(na) * (1 - t)), b * (c / math.sqrt(nb) * t)], dim=dim)
 

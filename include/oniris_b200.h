@@ -134,6 +134,12 @@ int ob_scale_silu_bwd(const void* y, const float* cscale, const void* g, void* d
 int ob_mp_sum_fwd(const void* a, const void* b, void* out, int64_t n, float t, float clip, void* stream);
 int ob_mp_sum_bwd(const void* g, const void* out, void* da, void* db, int64_t n, float t, float clip, void* stream);
 
+/* mp_cat (edm2/utils.py:128-134; the decoder skip connections, edm2/networks_edm2.py:244) over bf16 NHWC rows:
+ *   out[row] = [ a[row] * wa | b[row] * wb ],  wa = C/sqrt(ca)*(1-t), wb = C/sqrt(cb)*t, C = sqrt((ca+cb)/((1-t)^2+t^2)).
+ * bwd: da = g[:, :ca]*wa, db = g[:, ca:]*wb.  ca, cb multiples of 8. */
+int ob_mp_cat_fwd(const void* a, const void* b, void* out, int64_t rows, int ca, int cb, float t, void* stream);
+int ob_mp_cat_bwd(const void* g, void* da, void* db, int64_t rows, int ca, int cb, float t, void* stream);
+
 /* Optimizer step of the training loop (cs_train.py:121-125: torch.optim.AdamW.step, zero_grad, and the EMA copies of
  * the weights) over one flat fp32 range of n elements (n % 4 == 0, 16-byte aligned buffers):
  *   m = b1*m + (1-b1)*g;  v = b2*v + (1-b2)*g*g;  p = p*(1 - lr*wd) - lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
