@@ -223,6 +223,9 @@ int ob_mp_cat_fwd(const void* a, const void* b, void* out, int64_t rows, int ca,
 int ob_mp_cat_bwd(const void* g, void* da, void* db, int64_t rows, int ca, int cb, float t, void* stream) {
   return mp_cat(da, db, const_cast<void*>(g), (long)rows, ca, cb, t, 1, (cudaStream_t)stream);
 }
+int ob_resample2x(const void* in, void* out, int64_t frames, int h, int w, int c, int pool, float scale, void* stream) {
+  return resample2x(in, out, (long)frames, h, w, c, pool, scale, (cudaStream_t)stream);
+}
 int ob_adamw_ema(float* p, float* g, float* m, float* v, float* ema1, float* ema2, int64_t n, const float* step_lr,
                  float beta1, float beta2, float eps, float weight_decay, float ema_beta1, float ema_beta2, void* stream) {
   return adamw_ema(p, g, m, v, ema1, ema2, (long)n, step_lr, beta1, beta2, eps, weight_decay, ema_beta1, ema_beta2,

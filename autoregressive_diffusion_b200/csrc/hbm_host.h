@@ -30,6 +30,7 @@ int scale_silu_bwd(const void* y, const float* cscale, const void* g, void* dy, 
 int mp_sum_fwd(const void* a, const void* b, void* out, long n, float t, float clip, cudaStream_t st);
 int mp_sum_bwd(const void* g, const void* out, void* da, void* db, long n, float t, float clip, cudaStream_t st);
 int mp_cat(void* a, void* b, void* cat, long rows, int ca, int cb, float t, int backward, cudaStream_t st);
+int resample2x(const void* in, void* out, long frames, int h, int w, int c, int pool, float scale, cudaStream_t st);
 int adamw_ema(float* p, float* g, float* m, float* v, float* e1, float* e2, long n, const float* step_lr, float beta1,
               float beta2, float eps, float wd, float ema1, float ema2, cudaStream_t st);
 int qkv_prep_fwd(const void* qkv, void* q, void* k, void* v, void* k_raw, const float* cosT, const float* sinT,

@@ -920,6 +920,62 @@ int mp_cat(void* a, void* b, void* cat, long rows, int ca, int cb, float t, int 
   return check_launch("mp_cat");
 }
 
+// ============================================================================ 2x resampling
+// Reference: edm2/utils.py:94-107 with the [1,1] filter the UNet uses: 'down' = 2x2 mean, 'up' = nearest-neighbour 2x.
+// Each is the other's transpose, so two kernels cover both directions of both modes:
+//   pool2x2:   out[f, y, x, :] = scale * sum of the 2x2 block of in        (down fwd: 0.25;  up bwd: 1)
+//   expand2x2: out[f, 2y+i, 2x+j, :] = scale * in[f, y, x, :]              (up fwd: 1;       down bwd: 0.25)
+__global__ void __launch_bounds__(256) pool2x2_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out,
+                                                      long n_out8, int ho, int wo, int c8, float scale) {
+  const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n_out8) return;
+  const int v = static_cast<int>(i % c8);
+  long r = i / c8;
+  const int x = static_cast<int>(r % wo); r /= wo;
+  const int y = static_cast<int>(r % ho);
+  const long f = r / ho;
+  const bf16x8* src = reinterpret_cast<const bf16x8*>(in) + ((f * (2 * ho) + 2 * y) * (2 * wo) + 2 * x) * c8 + v;
+  float acc[8], t[8];
+  unpack8(src[0], acc);
+  unpack8(src[c8], t);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] += t[j];
+  unpack8(src[static_cast<long>(2 * wo) * c8], t);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] += t[j];
+  unpack8(src[static_cast<long>(2 * wo) * c8 + c8], t);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = (acc[j] + t[j]) * scale;
+  reinterpret_cast<bf16x8*>(out)[i] = pack8(acc);
+}
+__global__ void __launch_bounds__(256) expand2x2_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out,
+                                                        long n_out8, int ho, int wo, int c8, float scale) {
+  const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n_out8) return;
+  const int v = static_cast<int>(i % c8);
+  long r = i / c8;
+  const int x = static_cast<int>(r % wo); r /= wo;
+  const int y = static_cast<int>(r % ho);
+  const long f = r / ho;
+  float t[8];
+  unpack8(reinterpret_cast<const bf16x8*>(in)[((f * (ho / 2) + y / 2) * (wo / 2) + x / 2) * c8 + v], t);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) t[j] *= scale;
+  reinterpret_cast<bf16x8*>(out)[i] = pack8(t);
+}
+
+// h, w: spatial size of the LARGE side (even).  pool != 0: in is [f,h,w,c] -> out [f,h/2,w/2,c]; else the reverse.
+int resample2x(const void* in, void* out, long frames, int h, int w, int c, int pool, float scale, cudaStream_t st) {
+  if (c % 8 != 0 || h % 2 != 0 || w % 2 != 0) { set_error("resample2x: need c %% 8 == 0 and even h, w (got %d, %d, %d)", c, h, w); return OB_ERR_INVALID; }
+  const int ho = pool ? h / 2 : h, wo = pool ? w / 2 : w;
+  const long n = frames * ho * wo * (c / 8);
+  if (n <= 0) return OB_OK;
+  const unsigned blocks = static_cast<unsigned>((n + 255) / 256);
+  if (pool) pool2x2_kernel<<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(in), static_cast<__nv_bfloat16*>(out), n, ho, wo, c / 8, scale);
+  else expand2x2_kernel<<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(in), static_cast<__nv_bfloat16*>(out), n, ho, wo, c / 8, scale);
+  return check_launch("resample2x");
+}
+
 // ----------------------------------------------------------------------------- optimizer
 // AdamW (decoupled weight decay, bias-corrected; the update torch.optim.AdamW applies in cs_train.py:121-124) fused with
 // the two power-function-free EMA copies of the weights (cs_train.py:125) and the gradient reset, over ONE flat fp32

@@ -380,6 +380,31 @@ class MpCatFn(torch.autograd.Function):
         return da, db, None
 
 
+class Resample2xFn(torch.autograd.Function):
+    """resample(x, [1,1], 'down' | 'up')   [edm2/utils.py:94-107]: 2x2 mean / nearest 2x; each is the other's transpose."""
+
+    @staticmethod
+    def forward(ctx, x, down):
+        f, c, h, w = x.shape
+        ctx.down, ctx.big = down, (h, w) if down else (2 * h, 2 * w)
+        out = empty_rows(f, c, h // 2, w // 2, x.device) if down else empty_rows(f, c, 2 * h, 2 * w, x.device)
+        call("ob_resample2x", _vp(x), _vp(out), f, ctx.big[0], ctx.big[1], c, int(down), 0.25 if down else 1.0, stream_ptr())
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        g = rows(g)
+        f, c = g.shape[:2]
+        h, w = ctx.big
+        dx = empty_rows(f, c, h, w, g.device) if ctx.down else empty_rows(f, c, h // 2, w // 2, g.device)
+        call("ob_resample2x", _vp(g), _vp(dx), f, h, w, c, int(not ctx.down), 0.25 if ctx.down else 1.0, stream_ptr())
+        return dx, None
+
+
+def resample2x(x, down):
+    return Resample2xFn.apply(rows(x), bool(down))
+
+
 def mp_cat_rows(a, b, t=0.5):
     return MpCatFn.apply(rows(a), rows(b), float(t))
 

@@ -140,6 +140,11 @@ int ob_mp_sum_bwd(const void* g, const void* out, void* da, void* db, int64_t n,
 int ob_mp_cat_fwd(const void* a, const void* b, void* out, int64_t rows, int ca, int cb, float t, void* stream);
 int ob_mp_cat_bwd(const void* g, void* da, void* db, int64_t rows, int ca, int cb, float t, void* stream);
 
+/* 2x resampling of bf16 NHWC frames with the UNet's [1,1] filter (edm2/utils.py:94-107).  h, w: the LARGE side.
+ * pool != 0: out[f,y,x,:] = scale * sum of in's 2x2 block (down: scale 0.25; gradient of up: scale 1);
+ * pool == 0: out[f,2y+i,2x+j,:] = scale * in[f,y,x,:]     (up: scale 1; gradient of down: scale 0.25). */
+int ob_resample2x(const void* in, void* out, int64_t frames, int h, int w, int c, int pool, float scale, void* stream);
+
 /* Optimizer step of the training loop (cs_train.py:121-125: torch.optim.AdamW.step, zero_grad, and the EMA copies of
  * the weights) over one flat fp32 range of n elements (n % 4 == 0, 16-byte aligned buffers):
  *   m = b1*m + (1-b1)*g;  v = b2*v + (1-b2)*g*g;  p = p*(1 - lr*wd) - lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
