@@ -163,6 +163,16 @@ def dbg(msg):
         print(f"[rank {os.environ.get('RANK', '0')} +{time.time() % 1000:.1f}s] {msg}", file=sys.stderr, flush=True)
 
 
+def tapconv_traffic():
+    """DRAM bytes per tap-GEMM launch from the committed ncu capture (None when the profile is absent)."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_tapconv_traffic.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["dram_bytes_per_launch"])
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 def run_ours(args):
     import torch.distributed as dist
     from autoregressive_diffusion_b200 import _lib
@@ -264,7 +274,8 @@ def run_ours(args):
         "roofline": {"bound": "tensor", "kernel": "tapconv_kernel (gated 3D causal conv fwd + dgrad, tcgen05)",
                      "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                      "peak_kind": f"{peak_kind} bf16_tflops_sustained", "launches": conv_launches,
-                     "share_of_step": (conv_ms / 4) / ms, "traffic": None,
+                     "share_of_step": (conv_ms / 4) / ms, "traffic": tapconv_traffic(),
+                     "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum per tapconv launch, mean over the 187 launches of one step, from the committed ncu pass profiles/r01_launches_step.csv",
                      "how": "CUDA events around each tap-GEMM launch over one eager 4-step cycle on the launching stream, enqueued ahead of a parked GPU so the intervals hold no host gaps; the weight-gradient stream is kept in line for this cycle so each kernel is timed alone"},
     }
     if world == 1 and not args.no_cpu_baseline:
