@@ -137,6 +137,10 @@ int main(int argc, char** argv) {
     { Problem q = gated("CS 512->512 4x4 FLAT", 2, 16, 4, 4, 512, 512, 0); q.flat = 1; run(q, false, 20); }
     { Problem q = gated("CS 512->512 16x16 PAIR", 2, 16, 16, 16, 512, 512, 0); q.flat = 2; run(q, false, 20); }
     run(gated("CS 256->128 32x32 B2 n16", 2, 16, 32, 32, 256, 128, 0), false, 20);
+    for (int sp : {2, 3, 4, 6, 8}) run(gated("CS 256->256 16x16 splitN", 2, 16, 16, 16, 256, 256, sp), false, 20);
+    for (int sp : {6, 11, 16, 22}) run(gated("CS 128->128 32x32 splitN", 2, 16, 32, 32, 128, 128, sp), false, 20);
+    for (int sp : {3, 6, 11}) run(gated("CS 256->128 32x32 splitN", 2, 16, 32, 32, 256, 128, sp), false, 20);
+    for (int sp : {2, 3, 6}) run(gated("CS 256->256 8x8 splitN", 2, 16, 8, 8, 256, 256, sp), false, 20);
     run(gated("CS 512->512 16x16 split1", 2, 16, 16, 16, 512, 512, 1), false, 20);
     run(gated("CS 512->512 16x16 split4", 2, 16, 16, 16, 512, 512, 4), false, 20);
   }

@@ -56,7 +56,10 @@ int wgrad_suggest_split(int n_items, int max_frames, int H, int W, int Cin, int 
   const WgradPlan q = make_plan(n_items, Cin, Cout);
   const long ctas = static_cast<long>(q.co_tiles) * q.ci_tiles * group_count(n_items, q.nt);
   const long k_tiles = static_cast<long>((max_frames + bt - 1) / bt) * ((H + bh - 1) / bh) * ((W + bw - 1) / bw);
-  long split = (2 * 148 + ctas - 1) / ctas;
+  // ONE wave of CTAs: every extra split is another fp32 copy of dW written here and read back by the weight-norm
+  // backward.  Measured sweeps (us): 512->512 16x16 {1: 125, 2: 141, 4: 161}; 256->256 16x16 {2: 65, 3: 55, 6: 58};
+  // 128->128 32x32 {6: 79, 11: 58, 22: 66}; 256->128 32x32 {3: 144, 6: 89, 11: 97}
+  long split = (148 + ctas - 1) / ctas;
   if (split > k_tiles / 4) split = k_tiles / 4;  // keep >= 4 K tiles per CTA
   if (split < 1) split = 1;
   if (split > 64) split = 64;

@@ -1,0 +1,36 @@
+"""Forward / backward split of one training micro-step (events on a parked stream), with and without the
+weight-gradient side stream."""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from autoregressive_diffusion_b200.ops import WeightGradBranch  # noqa: E402
+from autoregressive_diffusion_b200.train import CS_UNET, Trainer  # noqa: E402
+
+tr = Trainer(CS_UNET, device="cuda")
+x = torch.randn(2, 16, 8, 32, 32, device="cuda")
+for _ in range(6):
+    tr.micro_step(x)
+
+
+def measure():
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    torch.cuda.synchronize()
+    torch.cuda._sleep(int(1.5e9))
+    ev[0].record()
+    tr.micro += 1
+    loss, _ = tr.loss_fn(tr.precond, x, None)
+    ev[1].record()
+    (loss / tr.accum).backward()
+    ev[2].record()
+    torch.cuda.synchronize()
+    return ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])
+
+
+for enabled in (True, False, True, False):
+    WeightGradBranch.enabled = enabled
+    measure()
+    f, b = measure()
+    print(f"weight-gradient stream {'on ' if enabled else 'off'}: forward {f:.2f} ms  backward {b:.2f} ms  total {f + b:.2f} ms")
