@@ -52,6 +52,7 @@ _SIGS = {
     "ob_mp_cat_fwd": "pppliifp",
     "ob_mp_cat_bwd": "pppliifp",
     "ob_resample2x": "ppliiiifp",
+    "ob_set_pdl": "i",
     "ob_adamw_ema": "pppppplpffffffp",
     "ob_qkv_prep_fwd": "ppppppppppliifp",
     "ob_qkv_prep_bwd": "ppppppppppliifp",

@@ -1,5 +1,6 @@
 // Host side of the attention kernels.
 #include "attention.cuh"
+#include "launch.cuh"
 #include "attention_bwd.cuh"
 
 #include <cstring>
@@ -39,7 +40,7 @@ int attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, i
     attr = true;
   }
   dim3 grid((Lq + ATTN_BM - 1) / ATTN_BM, BH);
-  attn_fwd_kernel<<<grid, ATTN_THREADS, ATTN_SMEM_BYTES, st>>>(p);
+  launch(attn_fwd_kernel, grid, ATTN_THREADS, ATTN_SMEM_BYTES, st, 1, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("attn_fwd launch: %s", cudaGetErrorString(e)); return OB_ERR_CUDA; }
   return OB_OK;
@@ -76,10 +77,10 @@ int attn_bwd(const void* q, const void* k, const void* v, const void* o, const v
     attr = true;
   }
   const long rows = static_cast<long>(BH) * Lq;
-  attn_bwd_prep_kernel<<<(rows * 8 + 255) / 256, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(o),
+  launch(attn_bwd_prep_kernel, (rows * 8 + 255) / 256, 256, 0, st, 1, static_cast<const __nv_bfloat16*>(o),
                                                                static_cast<const __nv_bfloat16*>(dout), dsum, rows, Lq, heads);
-  attn_bwd_dq_kernel<<<dim3((Lq + ABW_BM - 1) / ABW_BM, BH), ABW_THREADS, ABW_DQ_SMEM, st>>>(p);
-  attn_bwd_dkv_kernel<<<dim3((Lk + ABW_BM - 1) / ABW_BM, BH), ABW_THREADS, ABW_DKV_SMEM, st>>>(p);
+  launch(attn_bwd_dq_kernel, dim3((Lq + ABW_BM - 1) / ABW_BM, BH), ABW_THREADS, ABW_DQ_SMEM, st, 1, p);
+  launch(attn_bwd_dkv_kernel, dim3((Lk + ABW_BM - 1) / ABW_BM, BH), ABW_THREADS, ABW_DKV_SMEM, st, 1, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("attn_bwd launch: %s", cudaGetErrorString(e)); return OB_ERR_CUDA; }
   return OB_OK;

@@ -10,6 +10,7 @@
 // allowed frame are visited, so the DART training mask costs n(n+1) frame pairs instead of (2n)^2.
 #pragma once
 #include <cuda.h>
+#include "launch.cuh"
 #include <cuda_runtime.h>
 #include <cstdint>
 #include "ptx.cuh"
@@ -121,6 +122,8 @@ __device__ __forceinline__ float softmax_chunk(const float (&s)[32], uint32_t (&
 }
 
 __global__ void __launch_bounds__(ATTN_THREADS, 1) attn_fwd_kernel(const __grid_constant__ AttnParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sQ = base;

@@ -11,6 +11,7 @@
 // D[i] = sum_d dO[i,d]*O[i,d] comes from attn_bwd_prep_kernel.
 #pragma once
 #include "attention.cuh"
+#include "launch.cuh"
 
 namespace ob {
 
@@ -96,6 +97,8 @@ __device__ __forceinline__ TileRanges visible_queries(const AttnBwdParams& p, in
 __global__ void __launch_bounds__(256) attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ o,
                                                             const __nv_bfloat16* __restrict__ dout,
                                                             float* __restrict__ dsum, long rows, int L, int heads) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long gid = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long row = gid >> 3;
   const int sub = static_cast<int>(gid & 7);
@@ -197,6 +200,8 @@ __device__ __forceinline__ void pds_chunk_col(const float (&s)[32], const float 
 
 // ------------------------------------------------------------------------------------------------ dQ
 __global__ void __launch_bounds__(ABW_THREADS, 1) attn_bwd_dq_kernel(const __grid_constant__ AttnBwdParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sQ = base, sdO = sQ + ABW_T128;
@@ -368,6 +373,8 @@ __global__ void __launch_bounds__(ABW_THREADS, 1) attn_bwd_dq_kernel(const __gri
 
 // ------------------------------------------------------------------------------------------------ dK, dV
 __global__ void __launch_bounds__(ABW_THREADS, 1) attn_bwd_dkv_kernel(const __grid_constant__ AttnBwdParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sK = base, sV = sK + ABW_T128;

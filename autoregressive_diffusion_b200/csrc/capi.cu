@@ -1,5 +1,7 @@
 // extern "C" surface of liboniris_b200.so (declared in include/oniris_b200.h).
 #include "../../include/oniris_b200.h"
+#include "launch.cuh"
+#include <cstdlib>
 
 #include <vector>
 
@@ -225,6 +227,12 @@ int ob_mp_cat_bwd(const void* g, void* da, void* db, int64_t rows, int ca, int c
 }
 int ob_resample2x(const void* in, void* out, int64_t frames, int h, int w, int c, int pool, float scale, void* stream) {
   return resample2x(in, out, (long)frames, h, w, c, pool, scale, (cudaStream_t)stream);
+}
+int ob_set_pdl(int enabled) {
+  static const bool forced_off = [] { const char* e = getenv("ONIRIS_PDL"); return e != nullptr && e[0] == '0'; }();
+  const int prev = pdl_enabled() ? 1 : 0;
+  if (!forced_off) pdl_flag().store(enabled ? 1 : 0, std::memory_order_relaxed);
+  return prev;
 }
 int ob_adamw_ema(float* p, float* g, float* m, float* v, float* ema1, float* ema2, int64_t n, const float* step_lr,
                  float beta1, float beta2, float eps, float weight_decay, float ema_beta1, float ema_beta2, void* stream) {

@@ -3,6 +3,7 @@
 // All activations are bf16 NHWC ([rows, C], channel-contiguous); all arithmetic is fp32.
 // 128-bit global accesses, warp-shuffle reductions, one pass over HBM per tensor.
 #include <cuda_bf16.h>
+#include "launch.cuh"
 #include <cuda_runtime.h>
 #include <cstdint>
 
@@ -61,6 +62,8 @@ __device__ __forceinline__ bf16x8 pack8(const float* f) {
 __global__ void __launch_bounds__(256) wnorm_fwd_kernel(float* __restrict__ w, __nv_bfloat16* __restrict__ wg, int Ci,
                                                         int taps, int Ci_pad, int taps_total, int tap_off, float gain,
                                                         float eps, int training) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float red[32];
   const int co = blockIdx.x;
   const int K = Ci * taps;
@@ -113,6 +116,8 @@ __global__ void __launch_bounds__(256) wnorm_bwd_kernel(const float* __restrict_
                                                         float* __restrict__ dw, int Co, int Ci, int taps_rt, int Ci_pad,
                                                         int taps_total, int tap_off, int n_split, float gain, float eps,
                                                         int accumulate) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float red[32];
   extern __shared__ float gbuf[];  // [taps][Ci + 1]
   const int taps = TAPS > 0 ? TAPS : taps_rt;
@@ -240,6 +245,8 @@ __global__ void __launch_bounds__(256) gate_bwd_kernel(const __nv_bfloat16* __re
                                                        __nv_bfloat16* __restrict__ gya, __nv_bfloat16* __restrict__ gb,
                                                        float* __restrict__ s_y, float* __restrict__ s_d, int n_seq, int S,
                                                        int T, long frame_elems, GateGradArgs gg) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float red[32];
   const int bt = blockIdx.y;  // (b, t)
   const int b = bt / T, t = bt - b * T;
@@ -342,6 +349,8 @@ __global__ void gate_fwd_kernel(const float* __restrict__ offset, const float* _
                                 const float* __restrict__ max_g, const float* __restrict__ min_g,
                                 const float* __restrict__ c_noise, float* __restrict__ alpha, float* __restrict__ beta,
                                 int frames, int T, int half, int n_ctx) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
   if (f >= frames) return;
   const float lo = 1.f / (1.f + expf(-min_g[0])), hi = 1.f / (1.f + expf(-max_g[0]));
@@ -363,6 +372,8 @@ __global__ void __launch_bounds__(128) gate_bwd_params_kernel(const float* __res
                                                               const float* __restrict__ s_d, float* __restrict__ g_offset,
                                                               float* __restrict__ g_mult, float* __restrict__ g_max,
                                                               float* __restrict__ g_min, int frames, int T, int half, int n_ctx) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float red[32];
   const float lo = 1.f / (1.f + expf(-min_g[0])), hi = 1.f / (1.f + expf(-max_g[0]));
   float a_state = 0.f, a_m0 = 0.f, a_m1 = 0.f, a_lo = 0.f, a_hi = 0.f;
@@ -404,6 +415,8 @@ __global__ void __launch_bounds__(256) ctx_build_kernel(const __nv_bfloat16* __r
                                                         const __nv_bfloat16* __restrict__ pad,
                                                         __nv_bfloat16* __restrict__ ctx, int S, int T, long frame_elems,
                                                         int cin, int cin_pad, long total_vec) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long v = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (v >= total_vec) return;
   const long e = v * 8;
@@ -439,6 +452,8 @@ __global__ void __launch_bounds__(256) conv_prologue_kernel(const __nv_bfloat16*
                                                             const float* __restrict__ c_noise, float* __restrict__ alpha,
                                                             float* __restrict__ beta, float* __restrict__ scratch,
                                                             int scratch_n, int frames, int n_ctx) {
+  pdl_launch_dependents();
+  pdl_wait();
   if (blockIdx.x == gridDim.x - 1) {
     const float lo = 1.f / (1.f + expf(-min_g[0])), hi = 1.f / (1.f + expf(-max_g[0]));
     const int Trow = S * T;
@@ -486,6 +501,8 @@ __global__ void __launch_bounds__(256) pixnorm_silu_fwd_kernel(const __nv_bfloat
                                                                __nv_bfloat16* __restrict__ xn,
                                                                __nv_bfloat16* __restrict__ act, long rows, int C,
                                                                float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const long row = (static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   if (row >= rows) return;
@@ -528,6 +545,8 @@ __global__ void __launch_bounds__(256) pixnorm_silu_bwd_kernel(const __nv_bfloat
                                                                const __nv_bfloat16* __restrict__ g_act,
                                                                __nv_bfloat16* __restrict__ dx, long rows, int C,
                                                                float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const long row = (static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   if (row >= rows) return;
@@ -580,6 +599,8 @@ __global__ void __launch_bounds__(256) scale_silu_fwd_kernel(const __nv_bfloat16
                                                              const float* __restrict__ cscale,
                                                              __nv_bfloat16* __restrict__ out, long rows, int C,
                                                              int rows_per_frame) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long vec = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int vec_per_row = C >> 3;
   if (vec >= rows * vec_per_row) return;
@@ -607,6 +628,8 @@ __global__ void __launch_bounds__(256) scale_silu_bwd_kernel(const __nv_bfloat16
                                                              const __nv_bfloat16* __restrict__ g,
                                                              __nv_bfloat16* __restrict__ dy, float* __restrict__ dc, int C,
                                                              int rows_per_frame, int rows_per_chunk) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int frame = blockIdx.z;
   const int cv_per_blk = min(C >> 3, 32);
   const int pl = blockDim.x / cv_per_blk;
@@ -654,6 +677,8 @@ __global__ void __launch_bounds__(256) mp_sum_fwd_kernel(const __nv_bfloat16* __
                                                          const __nv_bfloat16* __restrict__ b,
                                                          __nv_bfloat16* __restrict__ out, long n8, float wa, float wb,
                                                          float clip) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n8) return;
   float fa[8], fb[8], o[8];
@@ -672,6 +697,8 @@ __global__ void __launch_bounds__(256) mp_sum_bwd_kernel(const __nv_bfloat16* __
                                                          const __nv_bfloat16* __restrict__ out,
                                                          __nv_bfloat16* __restrict__ da, __nv_bfloat16* __restrict__ db,
                                                          long n8, float wa, float wb, float clip) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n8) return;
   float fg[8], fo[8], oa[8], ob_[8];
@@ -701,7 +728,7 @@ static int check_launch(const char* what) {
 int wnorm_fwd(float* w, void* wg, int Co, int Ci, int taps, int Ci_pad, int taps_total, int tap_off, float gain, float eps,
               int training, cudaStream_t st) {
   if (Co <= 0) return OB_OK;
-  wnorm_fwd_kernel<<<Co, 256, 0, st>>>(w, static_cast<__nv_bfloat16*>(wg), Ci, taps, Ci_pad, taps_total, tap_off, gain,
+  launch(wnorm_fwd_kernel, Co, 256, 0, st, 1, w, static_cast<__nv_bfloat16*>(wg), Ci, taps, Ci_pad, taps_total, tap_off, gain,
                                        eps, training);
   return check_launch("wnorm_fwd");
 }
@@ -722,7 +749,7 @@ int wnorm_bwd(const float* w, const float* dwg, float* dw, int Co, int Ci, int t
     cudaFuncSetAttribute(wnorm_bwd_kernel<18>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     configured = true;
   }
-#define OB_WNORM_BWD(T) wnorm_bwd_kernel<T><<<Co, 256, smem, st>>>(w, dwg, dw, Co, Ci, taps, Ci_pad, taps_total, tap_off, n_split, gain, eps, accumulate)
+#define OB_WNORM_BWD(T) launch(wnorm_bwd_kernel<T>, Co, 256, smem, st, 1, w, dwg, dw, Co, Ci, taps, Ci_pad, taps_total, tap_off, n_split, gain, eps, accumulate)
   if (taps == 1) OB_WNORM_BWD(1);
   else if (taps == 9) OB_WNORM_BWD(9);
   else if (taps == 18) OB_WNORM_BWD(18);
@@ -744,7 +771,7 @@ int gate_bwd(const void* dy, const void* y, const void* d, const float* alpha, c
   int bx = static_cast<int>((frame_elems / 8 + 255) / 256);
   while (bx > 1 && static_cast<long>(bx) * n_seq * T > 4 * 148) bx = (bx + 1) / 2;
   dim3 grid(bx, n_seq * T);
-  gate_bwd_kernel<<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(y),
+  launch(gate_bwd_kernel, grid, 256, 0, st, 1, static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(y),
                                         static_cast<const float*>(d), alpha, beta,
                                         static_cast<__nv_bfloat16*>(gya), static_cast<__nv_bfloat16*>(gb), s_y, s_d, n_seq,
                                         S, T, frame_elems,
@@ -756,7 +783,7 @@ int gate_bwd(const void* dy, const void* y, const void* d, const float* alpha, c
 int gate_fwd(const float* offset, const float* mult, const float* max_g, const float* min_g, const float* c_noise,
              float* alpha, float* beta, int frames, int T, int half, int n_ctx, cudaStream_t st) {
   if (frames <= 0) return OB_OK;
-  gate_fwd_kernel<<<(frames + 127) / 128, 128, 0, st>>>(offset, mult, max_g, min_g, c_noise, alpha, beta, frames, T, half, n_ctx);
+  launch(gate_fwd_kernel, (frames + 127) / 128, 128, 0, st, 1, offset, mult, max_g, min_g, c_noise, alpha, beta, frames, T, half, n_ctx);
   return check_launch("gate_fwd");
 }
 
@@ -764,7 +791,7 @@ int gate_bwd_params(const float* offset, const float* mult, const float* max_g, 
                     const float* alpha, const float* beta, const float* s_y, const float* s_d, float* g_offset,
                     float* g_mult, float* g_max, float* g_min, int frames, int T, int half, int n_ctx, cudaStream_t st) {
   if (frames <= 0) return OB_OK;
-  gate_bwd_params_kernel<<<1, 128, 0, st>>>(offset, mult, max_g, min_g, c_noise, alpha, beta, s_y, s_d, g_offset, g_mult,
+  launch(gate_bwd_params_kernel, 1, 128, 0, st, 1, offset, mult, max_g, min_g, c_noise, alpha, beta, s_y, s_d, g_offset, g_mult,
                                             g_max, g_min, frames, T, half, n_ctx);
   return check_launch("gate_bwd_params");
 }
@@ -774,7 +801,7 @@ int ctx_build(const void* x, const void* pad, void* ctx, int B, int S, int T, lo
   if (frame_elems % 8 != 0 || cin_pad % 8 != 0) { set_error("ctx_build: frame size must be a multiple of 8"); return OB_ERR_INVALID; }
   const long total_vec = static_cast<long>(B) * (T + 2) * frame_elems / 8;
   if (total_vec <= 0) return OB_OK;
-  ctx_build_kernel<<<(total_vec + 255) / 256, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x),
+  launch(ctx_build_kernel, (total_vec + 255) / 256, 256, 0, st, 1, static_cast<const __nv_bfloat16*>(x),
                                                             static_cast<const __nv_bfloat16*>(pad),
                                                             static_cast<__nv_bfloat16*>(ctx), S, T, frame_elems, cin, cin_pad,
                                                             total_vec);
@@ -788,7 +815,7 @@ int conv_prologue(const void* x, const void* pad, void* ctx, int B, int S, int T
   const long total_vec = static_cast<long>(B) * (T + 2) * frame_elems / 8;
   if (total_vec <= 0) return OB_OK;
   const unsigned blocks = static_cast<unsigned>((total_vec + 255) / 256) + 1;
-  conv_prologue_kernel<<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(pad),
+  launch(conv_prologue_kernel, blocks, 256, 0, st, 1, static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(pad),
                                                static_cast<__nv_bfloat16*>(ctx), S, T, frame_elems, cin, cin_pad, total_vec,
                                                offset, mult, max_g, min_g, c_noise, alpha, beta, scratch, scratch_n,
                                                B * S * T, n_ctx);
@@ -800,10 +827,10 @@ int pixnorm_silu_fwd(const void* x, void* xn, void* act, long rows, int C, float
   if (rows <= 0) return OB_OK;
   const long blocks = (rows * 32 + 255) / 256;
   if (mode == 0)
-    pixnorm_silu_fwd_kernel<0><<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(xn),
+    launch(pixnorm_silu_fwd_kernel<0>, blocks, 256, 0, st, 1, static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(xn),
                                                        static_cast<__nv_bfloat16*>(act), rows, C, eps);
   else
-    pixnorm_silu_fwd_kernel<1><<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), nullptr,
+    launch(pixnorm_silu_fwd_kernel<1>, blocks, 256, 0, st, 1, static_cast<const __nv_bfloat16*>(x), nullptr,
                                                        static_cast<__nv_bfloat16*>(act), rows, C, eps);
   return check_launch("pixnorm_silu_fwd");
 }
@@ -814,12 +841,12 @@ int pixnorm_silu_bwd(const void* x, const void* g_xn, const void* g_act, void* d
   if (rows <= 0) return OB_OK;
   const long blocks = (rows * 32 + 255) / 256;
   if (mode == 0)
-    pixnorm_silu_bwd_kernel<0><<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x),
+    launch(pixnorm_silu_bwd_kernel<0>, blocks, 256, 0, st, 1, static_cast<const __nv_bfloat16*>(x),
                                                        static_cast<const __nv_bfloat16*>(g_xn),
                                                        static_cast<const __nv_bfloat16*>(g_act),
                                                        static_cast<__nv_bfloat16*>(dx), rows, C, eps);
   else
-    pixnorm_silu_bwd_kernel<1><<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x),
+    launch(pixnorm_silu_bwd_kernel<1>, blocks, 256, 0, st, 1, static_cast<const __nv_bfloat16*>(x),
                                                        static_cast<const __nv_bfloat16*>(g_xn),
                                                        static_cast<const __nv_bfloat16*>(g_act),
                                                        static_cast<__nv_bfloat16*>(dx), rows, C, eps);
@@ -830,7 +857,7 @@ int scale_silu_fwd(const void* y, const float* cscale, void* out, long rows, int
   if (C % 8 != 0) { set_error("scale_silu: C=%d must be a multiple of 8", C); return OB_ERR_INVALID; }
   if (rows <= 0) return OB_OK;
   const long n = rows * (C / 8);
-  scale_silu_fwd_kernel<<<(n + 255) / 256, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(y), cscale,
+  launch(scale_silu_fwd_kernel, (n + 255) / 256, 256, 0, st, 1, static_cast<const __nv_bfloat16*>(y), cscale,
                                                          static_cast<__nv_bfloat16*>(out), rows, C, rows_per_frame);
   return check_launch("scale_silu_fwd");
 }
@@ -851,7 +878,7 @@ int scale_silu_bwd(const void* y, const float* cscale, const void* g, void* dy, 
   const int rows_per_chunk = (rows_per_frame + chunks - 1) / chunks;
   cudaMemsetAsync(dc, 0, static_cast<size_t>(frames) * C * sizeof(float), st);
   dim3 grid(cgroups, chunks, frames);
-  scale_silu_bwd_kernel<<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(y), cscale,
+  launch(scale_silu_bwd_kernel, grid, 256, 0, st, 1, static_cast<const __nv_bfloat16*>(y), cscale,
                                               static_cast<const __nv_bfloat16*>(g), static_cast<__nv_bfloat16*>(dy), dc, C,
                                               rows_per_frame, rows_per_chunk);
   return check_launch("scale_silu_bwd");
@@ -861,7 +888,7 @@ int mp_sum_fwd(const void* a, const void* b, void* out, long n, float t, float c
   if (n % 8 != 0) { set_error("mp_sum: element count %ld must be a multiple of 8", n); return OB_ERR_INVALID; }
   if (n <= 0) return OB_OK;
   const float nrm = 1.f / sqrtf((1.f - t) * (1.f - t) + t * t);
-  mp_sum_fwd_kernel<<<(n / 8 + 255) / 256, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(a),
+  launch(mp_sum_fwd_kernel, (n / 8 + 255) / 256, 256, 0, st, 1, static_cast<const __nv_bfloat16*>(a),
                                                          static_cast<const __nv_bfloat16*>(b),
                                                          static_cast<__nv_bfloat16*>(out), n / 8, (1.f - t) * nrm, t * nrm,
                                                          clip);
@@ -872,7 +899,7 @@ int mp_sum_bwd(const void* g, const void* out, void* da, void* db, long n, float
   if (n % 8 != 0) { set_error("mp_sum: element count %ld must be a multiple of 8", n); return OB_ERR_INVALID; }
   if (n <= 0) return OB_OK;
   const float nrm = 1.f / sqrtf((1.f - t) * (1.f - t) + t * t);
-  mp_sum_bwd_kernel<<<(n / 8 + 255) / 256, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(g),
+  launch(mp_sum_bwd_kernel, (n / 8 + 255) / 256, 256, 0, st, 1, static_cast<const __nv_bfloat16*>(g),
                                                          static_cast<const __nv_bfloat16*>(out),
                                                          static_cast<__nv_bfloat16*>(da), static_cast<__nv_bfloat16*>(db),
                                                          n / 8, (1.f - t) * nrm, t * nrm, clip);
@@ -887,6 +914,8 @@ template <int DIR>
 __global__ void __launch_bounds__(256) mp_cat_kernel(__nv_bfloat16* __restrict__ a, __nv_bfloat16* __restrict__ b,
                                                      __nv_bfloat16* __restrict__ cat, long rows, int ca8, int cb8, float wa,
                                                      float wb) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int c8 = ca8 + cb8;
   if (i >= rows * c8) return;
@@ -912,10 +941,10 @@ int mp_cat(void* a, void* b, void* cat, long rows, int ca, int cb, float t, int 
   const long n = rows * ((ca + cb) / 8);
   const unsigned blocks = static_cast<unsigned>((n + 255) / 256);
   if (backward)
-    mp_cat_kernel<1><<<blocks, 256, 0, st>>>(static_cast<__nv_bfloat16*>(a), static_cast<__nv_bfloat16*>(b),
+    launch(mp_cat_kernel<1>, blocks, 256, 0, st, 1, static_cast<__nv_bfloat16*>(a), static_cast<__nv_bfloat16*>(b),
                                              static_cast<__nv_bfloat16*>(cat), rows, ca / 8, cb / 8, wa, wb);
   else
-    mp_cat_kernel<0><<<blocks, 256, 0, st>>>(static_cast<__nv_bfloat16*>(a), static_cast<__nv_bfloat16*>(b),
+    launch(mp_cat_kernel<0>, blocks, 256, 0, st, 1, static_cast<__nv_bfloat16*>(a), static_cast<__nv_bfloat16*>(b),
                                              static_cast<__nv_bfloat16*>(cat), rows, ca / 8, cb / 8, wa, wb);
   return check_launch("mp_cat");
 }
@@ -927,6 +956,8 @@ int mp_cat(void* a, void* b, void* cat, long rows, int ca, int cb, float t, int 
 //   expand2x2: out[f, 2y+i, 2x+j, :] = scale * in[f, y, x, :]              (up fwd: 1;       down bwd: 0.25)
 __global__ void __launch_bounds__(256) pool2x2_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out,
                                                       long n_out8, int ho, int wo, int c8, float scale) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n_out8) return;
   const int v = static_cast<int>(i % c8);
@@ -950,6 +981,8 @@ __global__ void __launch_bounds__(256) pool2x2_kernel(const __nv_bfloat16* __res
 }
 __global__ void __launch_bounds__(256) expand2x2_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out,
                                                         long n_out8, int ho, int wo, int c8, float scale) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n_out8) return;
   const int v = static_cast<int>(i % c8);
@@ -971,8 +1004,8 @@ int resample2x(const void* in, void* out, long frames, int h, int w, int c, int 
   const long n = frames * ho * wo * (c / 8);
   if (n <= 0) return OB_OK;
   const unsigned blocks = static_cast<unsigned>((n + 255) / 256);
-  if (pool) pool2x2_kernel<<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(in), static_cast<__nv_bfloat16*>(out), n, ho, wo, c / 8, scale);
-  else expand2x2_kernel<<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(in), static_cast<__nv_bfloat16*>(out), n, ho, wo, c / 8, scale);
+  if (pool) launch(pool2x2_kernel, blocks, 256, 0, st, 1, static_cast<const __nv_bfloat16*>(in), static_cast<__nv_bfloat16*>(out), n, ho, wo, c / 8, scale);
+  else launch(expand2x2_kernel, blocks, 256, 0, st, 1, static_cast<const __nv_bfloat16*>(in), static_cast<__nv_bfloat16*>(out), n, ho, wo, c / 8, scale);
   return check_launch("resample2x");
 }
 
@@ -984,6 +1017,8 @@ __global__ void __launch_bounds__(256) adamw_ema_kernel(float4* __restrict__ p, 
                                                         float4* __restrict__ v, float4* __restrict__ e1, float4* __restrict__ e2,
                                                         long n4, const float* __restrict__ step_lr, float beta1, float beta2,
                                                         float eps, float wd, float ema1, float ema2) {
+  pdl_launch_dependents();
+  pdl_wait();
   const float step = step_lr[0], lr = step_lr[1];
   const float bc1 = 1.f - powf(beta1, step);
   const float bc2_sqrt = sqrtf(1.f - powf(beta2, step));
@@ -1027,7 +1062,7 @@ int adamw_ema(float* p, float* g, float* m, float* v, float* e1, float* e2, long
   const long n4 = n / 4;
   long blocks = (n4 + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  adamw_ema_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(reinterpret_cast<float4*>(p), reinterpret_cast<float4*>(g),
+  launch(adamw_ema_kernel, static_cast<unsigned>(blocks), 256, 0, st, 1, reinterpret_cast<float4*>(p), reinterpret_cast<float4*>(g),
                                                                  reinterpret_cast<float4*>(m), reinterpret_cast<float4*>(v),
                                                                  reinterpret_cast<float4*>(e1), reinterpret_cast<float4*>(e2), n4,
                                                                  step_lr, beta1, beta2, eps, wd, ema1, ema2);

@@ -3,6 +3,7 @@
 // RMS-normalise every 64-vector (q, k AND v), and apply the per-frame rotary + xPos tables to q and k.
 // One warp per (token, head): the 192 interleaved channels of a head are one contiguous 384-byte run.
 #include <cuda_bf16.h>
+#include "launch.cuh"
 #include <cuda_runtime.h>
 #include <cstdint>
 
@@ -42,6 +43,8 @@ __global__ void __launch_bounds__(256) qkv_prep_fwd_kernel(const __nv_bfloat16* 
                                                            const float* __restrict__ sclT, const int* __restrict__ pos_q,
                                                            const int* __restrict__ pos_k, long rows, int heads, int hw,
                                                            float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const long wid = (static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   if (wid >= rows * heads) return;
@@ -89,6 +92,8 @@ __global__ void __launch_bounds__(256) qkv_prep_bwd_kernel(const __nv_bfloat16* 
                                                            const float* __restrict__ sinT, const float* __restrict__ sclT,
                                                            const int* __restrict__ pos_q, const int* __restrict__ pos_k,
                                                            long rows, int heads, int hw, float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const long wid = (static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   if (wid >= rows * heads) return;
@@ -134,6 +139,8 @@ __global__ void __launch_bounds__(256) rope_k_kernel(const __nv_bfloat16* __rest
                                                      const float* __restrict__ cosT, const float* __restrict__ sinT,
                                                      const float* __restrict__ sclT, const int* __restrict__ pos,
                                                      long rows, int heads, int hw) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const long wid = (static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   if (wid >= rows * heads) return;
@@ -159,7 +166,7 @@ int qkv_prep_fwd(const void* qkv, void* q, void* k, void* v, void* k_raw, const 
                  cudaStream_t st) {
   if (rows <= 0 || heads <= 0) return OB_OK;
   const long warps = rows * heads;
-  qkv_prep_fwd_kernel<<<(warps * 32 + 255) / 256, 256, 0, st>>>(
+  launch(qkv_prep_fwd_kernel, (warps * 32 + 255) / 256, 256, 0, st, 1, 
       static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(q), static_cast<__nv_bfloat16*>(k),
       static_cast<__nv_bfloat16*>(v), static_cast<__nv_bfloat16*>(k_raw), cosT, sinT, sclT, pos_q, pos_k, rows, heads, hw, eps);
   return chk("qkv_prep_fwd");
@@ -169,7 +176,7 @@ int qkv_prep_bwd(const void* qkv, const void* dq, const void* dk, const void* dv
                  float eps, cudaStream_t st) {
   if (rows <= 0 || heads <= 0) return OB_OK;
   const long warps = rows * heads;
-  qkv_prep_bwd_kernel<<<(warps * 32 + 255) / 256, 256, 0, st>>>(
+  launch(qkv_prep_bwd_kernel, (warps * 32 + 255) / 256, 256, 0, st, 1, 
       static_cast<const __nv_bfloat16*>(qkv), static_cast<const __nv_bfloat16*>(dq), static_cast<const __nv_bfloat16*>(dk),
       static_cast<const __nv_bfloat16*>(dv), static_cast<__nv_bfloat16*>(dqkv), cosT, sinT, sclT, pos_q, pos_k, rows, heads,
       hw, eps);
@@ -179,7 +186,7 @@ int rope_k(const void* x, void* y, const float* cosT, const float* sinT, const f
            int heads, int hw, cudaStream_t st) {
   if (rows <= 0 || heads <= 0) return OB_OK;
   const long warps = rows * heads;
-  rope_k_kernel<<<(warps * 32 + 255) / 256, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y),
+  launch(rope_k_kernel, (warps * 32 + 255) / 256, 256, 0, st, 1, static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y),
                                                           cosT, sinT, sclT, pos, rows, heads, hw);
   return chk("rope_k");
 }

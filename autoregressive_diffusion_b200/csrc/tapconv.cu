@@ -1,5 +1,6 @@
 // Host side of the tap-GEMM kernel: tensor-map construction, tile-shape choice, launch.
 #include "tapconv_host.h"
+#include "launch.cuh"
 
 #include <cudaTypedefs.h>
 #include <cstdio>
@@ -101,16 +102,8 @@ static int launch_pair(const TapConvParams& p, dim3 grid, cudaStream_t stream) {
       if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(tapconv pair): %s", cudaGetErrorString(e)); return OB_ERR_CUDA; }
       attr_set = true;
     }
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = grid;
-    cfg.blockDim = dim3(TAPCONV_THREADS);
-    cfg.dynamicSmemBytes = 1024 + p.a_slots * p.a_slot_bytes + p.b_slots * (Cfg::B_BYTES_AL / 2) + 256;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, p);
+    const size_t smem = 1024 + p.a_slots * p.a_slot_bytes + p.b_slots * (Cfg::B_BYTES_AL / 2) + 256;
+    cudaError_t e = launch(kern, grid, dim3(TAPCONV_THREADS), smem, stream, 2, p);
     if (e != cudaSuccess) { set_error("tapconv pair<%d,%d> launch: %s", CHUNK, BN, cudaGetErrorString(e)); return OB_ERR_CUDA; }
     return OB_OK;
   }
@@ -135,7 +128,7 @@ static int launch_inst(const TapConvParams& p, dim3 grid, cudaStream_t stream) {
       attr_set = true;
     }
     const int smem = 1024 + p.a_slots * p.a_slot_bytes + p.b_slots * Cfg::B_BYTES_AL + 256;
-    tapconv_kernel<CHUNK, BN, BMN, false><<<grid, TAPCONV_THREADS, smem, stream>>>(p);
+    launch(tapconv_kernel<CHUNK, BN, BMN, false>, grid, TAPCONV_THREADS, smem, stream, 1, p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
       set_error("tapconv<%d,%d> launch: %s", CHUNK, BN, cudaGetErrorString(e));
@@ -370,7 +363,7 @@ int tapconv_launch(const TapConvLaunch& L, cudaStream_t stream) {
   {
     const long hw = static_cast<long>(L.H) * L.W;
     const long total = static_cast<long>(L.n_seq) * L.n_out * L.T * hw * (L.Cout / 4);
-    tapconv_finish_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
+    launch(tapconv_finish_kernel, static_cast<unsigned>((total + 255) / 256), 256, 0, stream, 1, 
         p.split_ws, p.alpha, p.beta, p.out, static_cast<float*>(p.out_d), L.n_seq, L.n_out, L.T, hw, L.Cout, p.epi, p.out_f32);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("tapconv_finish launch: %s", cudaGetErrorString(e)); return OB_ERR_CUDA; }

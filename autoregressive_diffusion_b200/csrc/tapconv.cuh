@@ -24,6 +24,7 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include "ptx.cuh"
+#include "launch.cuh"
 
 namespace ob {
 
@@ -131,6 +132,7 @@ __global__ void __launch_bounds__(TAPCONV_THREADS, 1) tapconv_kernel(const __gri
   constexpr uint32_t SBO = 8 * Cfg::ROW_BYTES;
   constexpr int MAXB = Cfg::MAX_B_SLOTS;
 
+  pdl_launch_dependents();   // the next kernel may start its prologue; it still waits for this grid to complete
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sA0 = smem_base;
@@ -209,6 +211,7 @@ __global__ void __launch_bounds__(TAPCONV_THREADS, 1) tapconv_kernel(const __gri
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
   if (warp == 1) TAPCONV_STAMP(0);   // setup done
+  pdl_wait();   // everything above overlapped the previous kernel's tail; global memory is touched only from here on
 
   if (warp == 0) {
     // ===================== activation (A) TMA producer (warp-uniform loop, one elected lane issues) ============
@@ -485,6 +488,8 @@ static __global__ void __launch_bounds__(256) tapconv_finish_kernel(const float*
                                                              const float* __restrict__ beta, void* __restrict__ out,
                                                              float* __restrict__ out_d, int n_seq, int n_out, int T,
                                                              long hw, int Cout, int epi, int out_f32) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long rows_per_set = static_cast<long>(n_seq) * T * hw;
   const long vec = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;   // one float4 of one output row
   const int v_per_row = Cout >> 2;

@@ -1,5 +1,6 @@
 // Host side of the weight-gradient kernel.
 #include "wgrad.cuh"
+#include "launch.cuh"
 
 #include <cstring>
 
@@ -83,16 +84,7 @@ static int launch_inst(const WgradParams& p, dim3 grid, cudaStream_t stream) {
       }
       attr_set = true;
     }
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = grid;
-    cfg.blockDim = dim3(WGRAD_THREADS);
-    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = PAIR ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, p);
+    cudaError_t e = launch(kern, grid, dim3(WGRAD_THREADS), Cfg::SMEM_BYTES, stream, PAIR ? 2 : 1, p);
     if (e != cudaSuccess) {
       set_error("wgrad<%d,%d,%d,%d> launch: %s", CHUNK, BN, NT, (int)PAIR, cudaGetErrorString(e));
       return OB_ERR_CUDA;

@@ -80,6 +80,7 @@ __global__ void __launch_bounds__(WGRAD_THREADS, 1) wgrad_kernel(const __grid_co
   constexpr uint32_t SBO = 8 * Cfg::ROW_BYTES;
   static_assert(!PAIR || Cfg::A_BOXES % 2 == 0, "pair mode splits the activation boxes in two");
 
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
@@ -124,6 +125,7 @@ __global__ void __launch_bounds__(WGRAD_THREADS, 1) wgrad_kernel(const __grid_co
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  pdl_wait();   // setup above overlapped the previous kernel's tail
 
   if (warp == 0) {
     int stage = 0;

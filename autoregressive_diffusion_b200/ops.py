@@ -136,12 +136,14 @@ class WeightGradBranch:
         cls._pending.append((done, keep))
         if not cls._join_queued:
             cls._join_queued = True
+            query("ob_set_pdl", 0)     # two active streams: early-resident dependents would take the other stream's SMs
             torch.autograd.Variable._execution_engine.queue_callback(lambda: cls.join(device))
 
     @classmethod
     def join(cls, device):
         """Make the current stream wait for the branch (runs automatically at the end of every backward pass)."""
         cls._join_queued = False
+        query("ob_set_pdl", 1)
         if cls._pending:
             torch.cuda.current_stream(device).wait_stream(cls.stream(device))
             cls._pending.clear()

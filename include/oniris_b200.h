@@ -145,6 +145,11 @@ int ob_mp_cat_bwd(const void* g, void* da, void* db, int64_t rows, int ca, int c
  * pool == 0: out[f,2y+i,2x+j,:] = scale * in[f,y,x,:]     (up: scale 1; gradient of down: scale 0.25). */
 int ob_resample2x(const void* in, void* out, int64_t frames, int h, int w, int c, int pool, float scale, void* stream);
 
+/* Programmatic dependent launch: when on (default; ONIRIS_PDL=0 in the environment forces it off), every kernel of the
+ * library is launched so that its prologue overlaps the tail of the previous kernel on the stream.  Returns the previous
+ * setting.  The training backward pass switches it off while its second stream is active (see csrc/launch.cuh). */
+int ob_set_pdl(int enabled);
+
 /* Optimizer step of the training loop (cs_train.py:121-125: torch.optim.AdamW.step, zero_grad, and the EMA copies of
  * the weights) over one flat fp32 range of n elements (n % 4 == 0, 16-byte aligned buffers):
  *   m = b1*m + (1-b1)*g;  v = b2*v + (1-b2)*g*g;  p = p*(1 - lr*wd) - lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
