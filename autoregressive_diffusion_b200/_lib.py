@@ -38,15 +38,15 @@ _SIGS = {
     "ob_conv_wgrad_splits": "iiiiiiiii",
     "ob_conv_wgrad": "pppppiiiiiiiiiip",
     "ob_gate_bwd": "pppppppppiiilp",
-    "ob_conv_prologue": "pppiiiliippppppppip",
+    "ob_conv_prologue": "pppiiiliippppppppilp",
     "ob_gate_bwd_fused": "ppppppppiiilpppppppppip",
     "ob_gate_fwd": "pppppppiiiip",
     "ob_gate_bwd_params": "pppppppppppppiiiip",
     "ob_ctx_build": "pppiiiliip",
     "ob_pixnorm_silu_fwd": "ppplifip",
     "ob_pixnorm_silu_bwd": "pppplifip",
-    "ob_scale_silu_fwd": "pppliip",
-    "ob_scale_silu_bwd": "pppppiiip",
+    "ob_scale_silu_fwd": "pppliiip",
+    "ob_scale_silu_bwd": "pppppiiiip",
     "ob_mp_sum_fwd": "ppplffp",
     "ob_mp_sum_bwd": "pppplffp",
     "ob_mp_cat_fwd": "pppliifp",

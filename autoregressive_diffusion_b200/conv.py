@@ -149,10 +149,15 @@ class MPCausal3DGatedConv(nn.Module):
         pad = cache.get('activations', None)
         pad5 = None
         if pad is not None:  # reference layout [B, C, 2, H, W] -> NHWC rows [B, 2, H, W, C]
-            pad5 = pad.permute(0, 2, 3, 4, 1).to(BF16)
-            if cin_pad != cin:
-                pad5 = torch.nn.functional.pad(pad5, (0, cin_pad - cin))
-            pad5 = pad5.contiguous()
+            pad5 = pad.permute(0, 2, 3, 4, 1)
+            fe = pad5.shape[2] * pad5.shape[3] * cin_pad
+            in_place = (pad5.dtype == BF16 and cin_pad == cin and pad5.stride()[1:] == (fe, pad5.shape[3] * cin, cin, 1)
+                        and pad5.stride(0) >= 2 * fe and pad5.stride(0) % 8 == 0 and pad5.data_ptr() % 16 == 0)
+            if not in_place:   # foreign cache (fp32, or a channel count that needs padding): make the dense bf16 copy
+                pad5 = pad5.to(BF16)
+                if cin_pad != cin:
+                    pad5 = torch.nn.functional.pad(pad5, (0, cin_pad - cin))
+                pad5 = pad5.contiguous()
         gt = self.gating
         want_grad = torch.is_grad_enabled() and (xr.requires_grad or w2.requires_grad or w3.requires_grad)
         y, ctx5 = ops.GatedConvFn.apply(xr, pad5, w2, w3, wg, gt.offset, gt.mult, gt.max_gating, gt.min_gating,

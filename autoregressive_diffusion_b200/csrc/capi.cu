@@ -180,9 +180,10 @@ int ob_gate_bwd_fused(const void* dy, const void* y, const void* d, const float*
 }
 int ob_conv_prologue(const void* x, const void* pad, void* ctx, int b, int S, int T, int64_t frame_elems, int cin,
                      int cin_pad, const float* offset, const float* mult, const float* max_gating, const float* min_gating,
-                     const float* c_noise, float* alpha, float* beta, float* scratch, int n_ctx, void* stream) {
+                     const float* c_noise, float* alpha, float* beta, float* scratch, int n_ctx, int64_t pad_batch_stride,
+                     void* stream) {
   return conv_prologue(x, pad, ctx, b, S, T, (long)frame_elems, cin, cin_pad, offset, mult, max_gating, min_gating, c_noise,
-                       alpha, beta, scratch, scratch ? 2 * b * S * T + 1 : 0, n_ctx, (cudaStream_t)stream);
+                       alpha, beta, scratch, scratch ? 2 * b * S * T + 1 : 0, n_ctx, (long)pad_batch_stride, (cudaStream_t)stream);
 }
 int ob_gate_fwd(const float* offset, const float* mult, const float* max_gating, const float* min_gating,
                 const float* c_noise, float* alpha, float* beta, int frames, int T, int half, int n_ctx, void* stream) {
@@ -206,12 +207,12 @@ int ob_pixnorm_silu_bwd(const void* x, const void* g_xn, const void* g_act, void
                         int mode, void* stream) {
   return pixnorm_silu_bwd(x, g_xn, g_act, dx, (long)rows, c, eps, mode, (cudaStream_t)stream);
 }
-int ob_scale_silu_fwd(const void* y, const float* cscale, void* out, int64_t rows, int c, int rows_per_frame, void* stream) {
-  return scale_silu_fwd(y, cscale, out, (long)rows, c, rows_per_frame, (cudaStream_t)stream);
+int ob_scale_silu_fwd(const void* y, const float* cscale, void* out, int64_t rows, int c, int rows_per_frame, int ld, void* stream) {
+  return scale_silu_fwd(y, cscale, out, (long)rows, c, rows_per_frame, ld, (cudaStream_t)stream);
 }
 int ob_scale_silu_bwd(const void* y, const float* cscale, const void* g, void* dy, float* dc, int frames, int c,
-                      int rows_per_frame, void* stream) {
-  return scale_silu_bwd(y, cscale, g, dy, dc, frames, c, rows_per_frame, (cudaStream_t)stream);
+                      int rows_per_frame, int ld, void* stream) {
+  return scale_silu_bwd(y, cscale, g, dy, dc, frames, c, rows_per_frame, ld, (cudaStream_t)stream);
 }
 int ob_mp_sum_fwd(const void* a, const void* b, void* out, int64_t n, float t, float clip, void* stream) {
   return mp_sum_fwd(a, b, out, (long)n, t, clip, (cudaStream_t)stream);

@@ -13,7 +13,7 @@ int gate_bwd(const void* dy, const void* y, const void* d, const float* alpha, c
              float* g_min, unsigned* counter, int n_ctx, cudaStream_t st);
 int conv_prologue(const void* x, const void* pad, void* ctx, int B, int S, int T, long frame_elems, int cin, int cin_pad,
                   const float* offset, const float* mult, const float* max_g, const float* min_g, const float* c_noise,
-                  float* alpha, float* beta, float* scratch, int scratch_n, int n_ctx, cudaStream_t st);
+                  float* alpha, float* beta, float* scratch, int scratch_n, int n_ctx, long pad_bstride, cudaStream_t st);
 int gate_fwd(const float* offset, const float* mult, const float* max_g, const float* min_g, const float* c_noise,
              float* alpha, float* beta, int frames, int T, int half, int n_ctx, cudaStream_t st);
 int gate_bwd_params(const float* offset, const float* mult, const float* max_g, const float* min_g, const float* c_noise,
@@ -24,9 +24,9 @@ int ctx_build(const void* x, const void* pad, void* ctx, int B, int S, int T, lo
 int pixnorm_silu_fwd(const void* x, void* xn, void* act, long rows, int C, float eps, int mode, cudaStream_t st);
 int pixnorm_silu_bwd(const void* x, const void* g_xn, const void* g_act, void* dx, long rows, int C, float eps, int mode,
                      cudaStream_t st);
-int scale_silu_fwd(const void* y, const float* cscale, void* out, long rows, int C, int rows_per_frame, cudaStream_t st);
+int scale_silu_fwd(const void* y, const float* cscale, void* out, long rows, int C, int rows_per_frame, int ld, cudaStream_t st);
 int scale_silu_bwd(const void* y, const float* cscale, const void* g, void* dy, float* dc, int frames, int C,
-                   int rows_per_frame, cudaStream_t st);
+                   int rows_per_frame, int ld, cudaStream_t st);
 int mp_sum_fwd(const void* a, const void* b, void* out, long n, float t, float clip, cudaStream_t st);
 int mp_sum_bwd(const void* g, const void* out, void* da, void* db, long n, float t, float clip, cudaStream_t st);
 int mp_cat(void* a, void* b, void* cat, long rows, int ca, int cb, float t, int backward, cudaStream_t st);

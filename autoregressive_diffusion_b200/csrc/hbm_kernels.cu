@@ -451,7 +451,7 @@ __global__ void __launch_bounds__(256) conv_prologue_kernel(const __nv_bfloat16*
                                                             const float* __restrict__ max_g, const float* __restrict__ min_g,
                                                             const float* __restrict__ c_noise, float* __restrict__ alpha,
                                                             float* __restrict__ beta, float* __restrict__ scratch,
-                                                            int scratch_n, int frames, int n_ctx) {
+                                                            int scratch_n, int frames, int n_ctx, long pad_bstride) {
   pdl_launch_dependents();
   pdl_wait();
   if (blockIdx.x == gridDim.x - 1) {
@@ -481,7 +481,7 @@ __global__ void __launch_bounds__(256) conv_prologue_kernel(const __nv_bfloat16*
   if (t >= 2) {
     out = *reinterpret_cast<const bf16x8*>(x + ((b * S) * T + (t - 2)) * frame_elems + off);
   } else if (pad != nullptr) {
-    out = *reinterpret_cast<const bf16x8*>(pad + (b * 2 + t) * frame_elems + off);
+    out = *reinterpret_cast<const bf16x8*>(pad + b * pad_bstride + t * frame_elems + off);
   } else {
     float f[8];
     const int c0 = static_cast<int>(off % cin_pad);
@@ -597,7 +597,7 @@ __global__ void __launch_bounds__(256) pixnorm_silu_bwd_kernel(const __nv_bfloat
 // Reference: edm2/networks_edm2.py:75-77:  y = mp_silu(y * c[frame, channel])   (c = emb_linear(emb)+1).
 __global__ void __launch_bounds__(256) scale_silu_fwd_kernel(const __nv_bfloat16* __restrict__ y,
                                                              const float* __restrict__ cscale,
-                                                             __nv_bfloat16* __restrict__ out, long rows, int C,
+                                                             __nv_bfloat16* __restrict__ out, long rows, int C, int ld,
                                                              int rows_per_frame) {
   pdl_launch_dependents();
   pdl_wait();
@@ -609,8 +609,8 @@ __global__ void __launch_bounds__(256) scale_silu_fwd_kernel(const __nv_bfloat16
   const long frame = row / rows_per_frame;
   float f[8], o[8];
   unpack8(*reinterpret_cast<const bf16x8*>(y + row * C + c), f);
-  const float4 s0 = *reinterpret_cast<const float4*>(cscale + frame * C + c);
-  const float4 s1 = *reinterpret_cast<const float4*>(cscale + frame * C + c + 4);
+  const float4 s0 = *reinterpret_cast<const float4*>(cscale + frame * ld + c);
+  const float4 s1 = *reinterpret_cast<const float4*>(cscale + frame * ld + c + 4);
   const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -626,7 +626,7 @@ __global__ void __launch_bounds__(256) scale_silu_fwd_kernel(const __nv_bfloat16
 __global__ void __launch_bounds__(256) scale_silu_bwd_kernel(const __nv_bfloat16* __restrict__ y,
                                                              const float* __restrict__ cscale,
                                                              const __nv_bfloat16* __restrict__ g,
-                                                             __nv_bfloat16* __restrict__ dy, float* __restrict__ dc, int C,
+                                                             __nv_bfloat16* __restrict__ dy, float* __restrict__ dc, int C, int ld,
                                                              int rows_per_frame, int rows_per_chunk) {
   pdl_launch_dependents();
   pdl_wait();
@@ -640,8 +640,8 @@ __global__ void __launch_bounds__(256) scale_silu_bwd_kernel(const __nv_bfloat16
   __shared__ float part[256][9];
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (c < C) {
-    const float4 s0 = *reinterpret_cast<const float4*>(cscale + static_cast<long>(frame) * C + c);
-    const float4 s1 = *reinterpret_cast<const float4*>(cscale + static_cast<long>(frame) * C + c + 4);
+    const float4 s0 = *reinterpret_cast<const float4*>(cscale + static_cast<long>(frame) * ld + c);
+    const float4 s1 = *reinterpret_cast<const float4*>(cscale + static_cast<long>(frame) * ld + c + 4);
     const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
     for (int p = r_lo + p0; p < r_hi; p += pl) {
       const long off = (static_cast<long>(frame) * rows_per_frame + p) * C + c;
@@ -810,15 +810,17 @@ int ctx_build(const void* x, const void* pad, void* ctx, int B, int S, int T, lo
 
 int conv_prologue(const void* x, const void* pad, void* ctx, int B, int S, int T, long frame_elems, int cin, int cin_pad,
                   const float* offset, const float* mult, const float* max_g, const float* min_g, const float* c_noise,
-                  float* alpha, float* beta, float* scratch, int scratch_n, int n_ctx, cudaStream_t st) {
+                  float* alpha, float* beta, float* scratch, int scratch_n, int n_ctx, long pad_bstride, cudaStream_t st) {
   if (frame_elems % 8 != 0 || cin_pad % 8 != 0) { set_error("conv_prologue: frame size must be a multiple of 8"); return OB_ERR_INVALID; }
+  if (pad_bstride == 0) pad_bstride = 2 * frame_elems;
+  if (pad_bstride % 8 != 0 || pad_bstride < 2 * frame_elems) { set_error("conv_prologue: bad pad batch stride %ld", pad_bstride); return OB_ERR_INVALID; }
   const long total_vec = static_cast<long>(B) * (T + 2) * frame_elems / 8;
   if (total_vec <= 0) return OB_OK;
   const unsigned blocks = static_cast<unsigned>((total_vec + 255) / 256) + 1;
   launch(conv_prologue_kernel, blocks, 256, 0, st, 1, static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(pad),
                                                static_cast<__nv_bfloat16*>(ctx), S, T, frame_elems, cin, cin_pad, total_vec,
                                                offset, mult, max_g, min_g, c_noise, alpha, beta, scratch, scratch_n,
-                                               B * S * T, n_ctx);
+                                               B * S * T, n_ctx, pad_bstride);
   return check_launch("conv_prologue");
 }
 
@@ -853,17 +855,21 @@ int pixnorm_silu_bwd(const void* x, const void* g_xn, const void* g_act, void* d
   return check_launch("pixnorm_silu_bwd");
 }
 
-int scale_silu_fwd(const void* y, const float* cscale, void* out, long rows, int C, int rows_per_frame, cudaStream_t st) {
+int scale_silu_fwd(const void* y, const float* cscale, void* out, long rows, int C, int rows_per_frame, int ld, cudaStream_t st) {
+  if (ld == 0) ld = C;
+  if (ld % 4 != 0 || ld < C || reinterpret_cast<uintptr_t>(cscale) % 16 != 0) { set_error("scale_silu: scale rows must be 16-byte aligned (ld=%d)", ld); return OB_ERR_INVALID; }
   if (C % 8 != 0) { set_error("scale_silu: C=%d must be a multiple of 8", C); return OB_ERR_INVALID; }
   if (rows <= 0) return OB_OK;
   const long n = rows * (C / 8);
   launch(scale_silu_fwd_kernel, (n + 255) / 256, 256, 0, st, 1, static_cast<const __nv_bfloat16*>(y), cscale,
-                                                         static_cast<__nv_bfloat16*>(out), rows, C, rows_per_frame);
+                                                         static_cast<__nv_bfloat16*>(out), rows, C, ld, rows_per_frame);
   return check_launch("scale_silu_fwd");
 }
 
 int scale_silu_bwd(const void* y, const float* cscale, const void* g, void* dy, float* dc, int frames, int C,
-                   int rows_per_frame, cudaStream_t st) {
+                   int rows_per_frame, int ld, cudaStream_t st) {
+  if (ld == 0) ld = C;
+  if (ld % 4 != 0 || ld < C || reinterpret_cast<uintptr_t>(cscale) % 16 != 0) { set_error("scale_silu: scale rows must be 16-byte aligned (ld=%d)", ld); return OB_ERR_INVALID; }
   if (C % 8 != 0) { set_error("scale_silu: C=%d must be a multiple of 8", C); return OB_ERR_INVALID; }
   if (frames <= 0) return OB_OK;
   const int cv = C / 8;
@@ -879,7 +885,7 @@ int scale_silu_bwd(const void* y, const float* cscale, const void* g, void* dy, 
   cudaMemsetAsync(dc, 0, static_cast<size_t>(frames) * C * sizeof(float), st);
   dim3 grid(cgroups, chunks, frames);
   launch(scale_silu_bwd_kernel, grid, 256, 0, st, 1, static_cast<const __nv_bfloat16*>(y), cscale,
-                                              static_cast<const __nv_bfloat16*>(g), static_cast<__nv_bfloat16*>(dy), dc, C,
+                                              static_cast<const __nv_bfloat16*>(g), static_cast<__nv_bfloat16*>(dy), dc, C, ld,
                                               rows_per_frame, rows_per_chunk);
   return check_launch("scale_silu_bwd");
 }

@@ -197,7 +197,7 @@ class UNet(BetterModule):
         x = torch.cat([x, torch.ones_like(x[:, :1])], dim=1)
         skips = []
         for name, block in self.enc.items():
-            kw = {"emb_scale": scales[id(block)].contiguous()} if isinstance(block, Block) else {}
+            kw = {"emb_scale": scales[id(block)]} if isinstance(block, Block) else {}
             x, cache['enc', name] = block(x, emb, batch_size, c_noise, cache=cache.get(('enc', name), None),
                                           update_cache=update_cache, just_2d=just_2d, **kw)
             skips.append(x)
@@ -205,7 +205,7 @@ class UNet(BetterModule):
             if 'block' in name:
                 x = mp_cat(x, skips.pop(), t=self.concat_balance)
             x, cache['dec', name] = block(x, emb, batch_size, c_noise, cache=cache.get(('dec', name), None),
-                                          update_cache=update_cache, just_2d=just_2d, emb_scale=scales[id(block)].contiguous())
+                                          update_cache=update_cache, just_2d=just_2d, emb_scale=scales[id(block)])
         x, cache['out_conv'] = self.out_conv(x, emb, batch_size, c_noise, cache=cache.get('out_conv', None),
                                              update_cache=update_cache, just_2d=just_2d)
         x = x.reshape(batch_size, tdim, *x.shape[1:]).float() * self.out_gain

@@ -219,6 +219,7 @@ class GatedConvFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, pad5, w2, w3, wg, g_offset, g_mult, g_max, g_min, c_noise, n_seq, S, T, n_ctx, want_grad):
+        # pad5: [n_seq, 2, h, w, cin_pad] bf16, dense apart from its batch stride (a slice of the previous context works)
         f, cin_pad, h, wd = x.shape
         cin, cout = w2.shape[1], wg.shape[0]
         dev = x.device
@@ -227,7 +228,8 @@ class GatedConvFn(torch.autograd.Function):
         scratch = torch.empty(2 * f + 1, dtype=torch.float32, device=dev) if want_grad else None
         cx = torch.empty((n_seq, T + 2, h, wd, cin_pad), dtype=BF16, device=dev)
         call("ob_conv_prologue", _vp(x), _vp(pad5), _vp(cx), n_seq, S, T, h * wd * cin_pad, cin, cin_pad, _vp(g_offset),
-             _vp(g_mult), _vp(g_max), _vp(g_min), _vp(c_noise), _vp(alpha), _vp(beta), _vp(scratch), n_ctx, stream_ptr())
+             _vp(g_mult), _vp(g_max), _vp(g_min), _vp(c_noise), _vp(alpha), _vp(beta), _vp(scratch), n_ctx,
+             pad5.stride(0) if pad5 is not None else 0, stream_ptr())
         out = empty_rows(f, cout, h, wd, dev)
         out_d = empty_rows(f, cout, h, wd, dev, torch.float32) if want_grad else None
         ws = split_workspace(n_seq, S, T, h, wd, cin_pad, cout, 3, 1, dev)
@@ -317,13 +319,14 @@ class PixnormSiluFn(torch.autograd.Function):
 
 
 class ScaleSiluFn(torch.autograd.Function):
-    """mp_silu(y * c[frame, channel])   [edm2/networks_edm2.py:75-77]"""
+    """mp_silu(y * c[frame, channel])   [edm2/networks_edm2.py:75-77].  c: fp32 [frames, C] with unit column stride; its
+    row stride is free, so a column slice of the all-blocks embedding GEMM is read in place."""
 
     @staticmethod
     def forward(ctx, y, cscale):
         f, c, h, w = y.shape
         out = torch.empty_like(y, memory_format=CL)
-        call("ob_scale_silu_fwd", _vp(y), _vp(cscale), _vp(out), f * h * w, c, h * w, stream_ptr())
+        call("ob_scale_silu_fwd", _vp(y), _vp(cscale), _vp(out), f * h * w, c, h * w, cscale.stride(0), stream_ptr())
         ctx.save_for_backward(y, cscale)
         return out
 
@@ -333,8 +336,8 @@ class ScaleSiluFn(torch.autograd.Function):
         f, c, h, w = y.shape
         g = rows(g)
         dy = torch.empty_like(y, memory_format=CL)
-        dc = torch.empty_like(cscale)
-        call("ob_scale_silu_bwd", _vp(y), _vp(cscale), _vp(g), _vp(dy), _vp(dc), f, c, h * w, stream_ptr())
+        dc = torch.empty((f, c), dtype=torch.float32, device=y.device)
+        call("ob_scale_silu_bwd", _vp(y), _vp(cscale), _vp(g), _vp(dy), _vp(dc), f, c, h * w, cscale.stride(0), stream_ptr())
         return dy, dc
 
 
@@ -420,7 +423,10 @@ def silu_only(x):
 
 
 def scale_silu(y, cscale):
-    return ScaleSiluFn.apply(rows(y), cscale.float().contiguous())
+    cscale = cscale.float()
+    if cscale.stride(1) != 1 or cscale.stride(0) % 4 != 0 or cscale.data_ptr() % 16 != 0:
+        cscale = cscale.contiguous()
+    return ScaleSiluFn.apply(rows(y), cscale)
 
 
 def mp_sum_clip(a, b, t, clip=0.0):

@@ -92,11 +92,14 @@ int ob_gate_bwd(const void* dy, const void* y, const void* d, const float* alpha
 
 /* Fused variants used by the training path (same maths as the three calls they replace, fewer launches):
  * ob_conv_prologue = ob_ctx_build + ob_gate_fwd + zeroing of `scratch` (fp32 [2*frames + 1], may be NULL in eval);
+ *   pad_batch_stride: elements between the two cached frames of consecutive sequences in `pad` (0 = dense 2*frame_elems),
+ *   so the last two frames of the previous call's context tensor can be passed in place (decode path, no copy);
  * ob_gate_bwd_fused = ob_gate_bwd with s_y = scratch, s_d = scratch + frames, and the last CTA to finish (ticket
  * counter at scratch[2*frames]) doing the work of ob_gate_bwd_params. */
 int ob_conv_prologue(const void* x, const void* pad, void* ctx, int b, int S, int T, int64_t frame_elems, int cin,
                      int cin_pad, const float* offset, const float* mult, const float* max_gating, const float* min_gating,
-                     const float* c_noise, float* alpha, float* beta, float* scratch, int n_ctx, void* stream);
+                     const float* c_noise, float* alpha, float* beta, float* scratch, int n_ctx, int64_t pad_batch_stride,
+                     void* stream);
 int ob_gate_bwd_fused(const void* dy, const void* y, const void* d, const float* alpha, const float* beta, void* gya,
                       void* gb, float* scratch, int n_seq, int S, int T, int64_t frame_elems, const float* offset,
                       const float* mult, const float* max_gating, const float* min_gating, const float* c_noise,
@@ -125,10 +128,13 @@ int ob_pixnorm_silu_fwd(const void* x, void* xn, void* act, int64_t rows, int c,
 int ob_pixnorm_silu_bwd(const void* x, const void* g_xn, const void* g_act, void* dx, int64_t rows, int c, float eps,
                         int mode, void* stream);
 
-/* edm2/networks_edm2.py:75-77: out = mp_silu(y * cscale[frame, channel]); cscale fp32 [frames][C]. */
-int ob_scale_silu_fwd(const void* y, const float* cscale, void* out, int64_t rows, int c, int rows_per_frame, void* stream);
+/* edm2/networks_edm2.py:75-77: out = mp_silu(y * cscale[frame, channel]); cscale fp32, row `frame` starts at
+ * cscale + frame*ld (ld = 0 means ld = C; a column slice of the all-blocks embedding GEMM is passed in place).
+ * dc: fp32 [frames][C] dense. */
+int ob_scale_silu_fwd(const void* y, const float* cscale, void* out, int64_t rows, int c, int rows_per_frame, int ld,
+                      void* stream);
 int ob_scale_silu_bwd(const void* y, const float* cscale, const void* g, void* dy, float* dc, int frames, int c,
-                      int rows_per_frame, void* stream);
+                      int rows_per_frame, int ld, void* stream);
 
 /* edm2/utils.py:118-123 mp_sum with float t, fused with the clip_ of edm2/networks_edm2.py:93 (clip <= 0: none). */
 int ob_mp_sum_fwd(const void* a, const void* b, void* out, int64_t n, float t, float clip, void* stream);
