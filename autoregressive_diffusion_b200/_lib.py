@@ -31,6 +31,7 @@ def stream_ptr():
 _SIGS = {
     # name: argtypes
     "ob_wnorm_fwd": "ppiiiiiiffip",
+    "ob_wnorm_bwd_gated": "pppppiiiifip",
     "ob_wnorm_bwd": "pppiiiiiiiffip",
     "ob_conv_fwd": "ppppppppiiiiiiiiiip",
     "ob_conv_dgrad": "pppppppiiiiiiiiip",

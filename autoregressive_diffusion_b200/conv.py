@@ -27,7 +27,9 @@ class NormalizedWeight(nn.Module):
 
     def __init__(self, in_channels, out_channels, kernel):
         super().__init__()
-        self.weight = nn.Parameter(torch.randn(out_channels, in_channels, *kernel))
+        # reference shape [Co, Ci, *kernel]; STORED tap-major ([Co, *kernel, Ci], i.e. channels_last): the order of the GEMM
+        # operand and of the weight-gradient partials, so the weight-norm kernels stream rows without transposing
+        self.weight = nn.Parameter(ops.to_tap_major(torch.randn(out_channels, in_channels, *kernel)))
 
     def forward(self, gain=1):
         """fp32 normalised weight tensor, reference semantics (used by the linear layers and by tests)."""

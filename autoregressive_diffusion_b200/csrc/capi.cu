@@ -67,6 +67,12 @@ int ob_wnorm_bwd(const float* w, const float* dwg, float* dw, int cout, int cin,
                    (cudaStream_t)stream);
 }
 
+int ob_wnorm_bwd_gated(const float* w2, float* dw2, const float* w3, float* dw3, const float* dwg, int cout, int cin,
+                       int cin_pad, int n_split, float eps, int accumulate, void* stream) {
+  return wnorm_bwd2(w2, dw2, 9, 0, 1.f, w3, dw3, 18, 9, 1.f, dwg, cout, cin, cin_pad, 27, n_split, eps, accumulate,
+                    (cudaStream_t)stream);
+}
+
 int64_t ob_conv_split_ws_bytes(int n_seq, int S, int T, int H, int W, int cin, int cout, int ksize, int gated) {
   int ks; long wsb;
   if (gated) tapconv_plan(n_seq, S, 1, 27, T, H, W, cin, cout, &ks, &wsb);

@@ -5,6 +5,9 @@
 namespace ob {
 int wnorm_fwd(float* w, void* wg, int Co, int Ci, int taps, int Ci_pad, int taps_total, int tap_off, float gain, float eps,
               int training, cudaStream_t st);
+int wnorm_bwd2(const float* w0, float* dw0, int taps0, int tap_off0, float gain0, const float* w1, float* dw1, int taps1,
+               int tap_off1, float gain1, const float* dwg, int Co, int Ci, int Ci_pad, int taps_total, int n_split, float eps,
+               int accumulate, cudaStream_t st);
 int wnorm_bwd(const float* w, const float* dwg, float* dw, int Co, int Ci, int taps, int Ci_pad, int taps_total,
               int tap_off, int n_split, float gain, float eps, int accumulate, cudaStream_t st);
 int gate_bwd(const void* dy, const void* y, const void* d, const float* alpha, const float* beta, void* gya, void* gb,

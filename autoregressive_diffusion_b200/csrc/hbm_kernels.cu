@@ -55,10 +55,11 @@ __device__ __forceinline__ bf16x8 pack8(const float* f) {
 
 // ============================================================================ weight norm
 // Reference: edm2/conv.py:14-21 (NormalizedWeight.forward) + edm2/utils.py:83-88 (normalize).
-// One CTA per output channel. w: fp32 [Co][Ci][taps]. Operand out: bf16 [Co][taps_total][Ci_pad] at tap_off,
-// i.e. transposed to tap-major / channel-minor so the conv kernels read it K-major; pad channels are zeroed.
+// Parameters are STORED tap-major: the reference's logical [Co, Ci, (kt,) kh, kw] tensor in channels_last memory
+// format, i.e. physically w[Co][taps][Ci] -- the order of the bf16 GEMM operand wg[Co][taps_total][Ci_pad] and of the
+// wgrad partials dwg[n_split][Co][taps_total][Ci_pad].  Forward and backward are therefore straight row streams (no
+// transposes, no index divisions): one CTA per output channel, 128-bit accesses.
 // training: w <- w/(eps+rms(w)) in place (forced weight norm), operand = normalize(that) * gain/sqrt(fan_in).
-// inv_out[co] receives the factor d(operand)/d(w_forced) scale needed by the backward pass.
 __global__ void __launch_bounds__(256) wnorm_fwd_kernel(float* __restrict__ w, __nv_bfloat16* __restrict__ wg, int Ci,
                                                         int taps, int Ci_pad, int taps_total, int tap_off, float gain,
                                                         float eps, int training) {
@@ -68,11 +69,14 @@ __global__ void __launch_bounds__(256) wnorm_fwd_kernel(float* __restrict__ w, _
   const int co = blockIdx.x;
   const int K = Ci * taps;
   float* wr = w + static_cast<long>(co) * K;
+  __nv_bfloat16* dst = wg + (static_cast<long>(co) * taps_total + tap_off) * Ci_pad;
+  const bool vec = (Ci_pad == Ci) && ((K & 7) == 0) && ((reinterpret_cast<uintptr_t>(wr) & 15) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
   float ss = 0.f;
-  if ((K & 3) == 0) {
+  if (vec) {
     const float4* w4 = reinterpret_cast<const float4*>(wr);
     for (int i = threadIdx.x; i < K / 4; i += blockDim.x) {
-      float4 v = w4[i];
+      const float4 v = w4[i];
       ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
     }
   } else {
@@ -80,147 +84,152 @@ __global__ void __launch_bounds__(256) wnorm_fwd_kernel(float* __restrict__ w, _
   }
   ss = block_sum(ss, red);
   const float rms = sqrtf(ss / K);
-  float s1 = 1.f / (eps + rms);          // first normalisation
-  float scale;
-  if (training) {
-    const float rms1 = rms * s1;          // rms of the forced weights
-    scale = s1 / (eps + rms1);
-  } else {
-    scale = s1;
-  }
+  const float s1 = 1.f / (eps + rms);          // first normalisation
+  float scale = s1;
+  if (training) scale = s1 / (eps + rms * s1);  // rms * s1 = rms of the forced weights
   scale *= gain * rsqrtf(static_cast<float>(K));
-  // operand, gathered in destination order (tap-major) so the bf16 writes coalesce
-  __nv_bfloat16* dst = wg + (static_cast<long>(co) * taps_total + tap_off) * Ci_pad;
-  for (int j = threadIdx.x; j < taps * Ci_pad; j += blockDim.x) {
-    const int tap = j / Ci_pad, ci = j - tap * Ci_pad;
-    const float v = (ci < Ci) ? wr[ci * taps + tap] * scale : 0.f;
-    dst[j] = __float2bfloat16(v);
-  }
-  if (training) {
-    __syncthreads();  // all gathers of the old values are done before the in-place overwrite
-    for (int i = threadIdx.x; i < K; i += blockDim.x) wr[i] *= s1;
+  if (vec) {   // second pass hits L1/L2
+    for (int i = threadIdx.x; i < K / 8; i += blockDim.x) {
+      const float4 a = reinterpret_cast<const float4*>(wr)[2 * i], c = reinterpret_cast<const float4*>(wr)[2 * i + 1];
+      const float o[8] = {a.x * scale, a.y * scale, a.z * scale, a.w * scale, c.x * scale, c.y * scale, c.z * scale, c.w * scale};
+      reinterpret_cast<bf16x8*>(dst)[i] = pack8(o);
+      if (training) {
+        reinterpret_cast<float4*>(wr)[2 * i] = make_float4(a.x * s1, a.y * s1, a.z * s1, a.w * s1);
+        reinterpret_cast<float4*>(wr)[2 * i + 1] = make_float4(c.x * s1, c.y * s1, c.z * s1, c.w * s1);
+      }
+    }
+  } else {
+    for (int j = threadIdx.x; j < taps * Ci_pad; j += blockDim.x) {
+      const int tap = j / Ci_pad, ci = j - tap * Ci_pad;
+      dst[j] = __float2bfloat16((ci < Ci) ? wr[tap * Ci + ci] * scale : 0.f);
+    }
+    if (training) {
+      __syncthreads();  // every read of the old values is done before the in-place overwrite
+      for (int i = threadIdx.x; i < K; i += blockDim.x) wr[i] *= s1;
+    }
   }
 }
 
-// Backward of operand = normalize(w) * gain/sqrt(K) w.r.t. the (forced) weights w.
-// dwg: fp32 [n_split][Co][taps_total][Ci_pad] partial sums from the wgrad kernel; dw: fp32 [Co][Ci][taps].
-//   d = eps + rms(w);  dw_i = c/d * (g_i - w_i * <g,w> / (K * rms * d))
-// One CTA per output channel: the split-reduced gradient row is staged in shared memory in its own (tap-major)
-// order with a +1 row pad, so both the global reads (dwg, w) and the global write (dw) are fully coalesced and the
-// [tap][ci] -> [ci][tap] transpose happens on conflict-free shared-memory reads.  accumulate != 0: dw += result
-// (gradient accumulation over micro-batches without a separate add pass).
-// TAPS is a compile-time constant (1, 9 or 18 on this path; 0 = generic) so that the [ci][tap] <-> [tap][ci] index
-// arithmetic compiles to multiply-shift instead of integer division.
-template <int TAPS>
-__global__ void __launch_bounds__(256) wnorm_bwd_kernel(const float* __restrict__ w, const float* __restrict__ dwg,
-                                                        float* __restrict__ dw, int Co, int Ci, int taps_rt, int Ci_pad,
-                                                        int taps_total, int tap_off, int n_split, float gain, float eps,
-                                                        int accumulate) {
+// Backward of operand = normalize(w) * gain/sqrt(K) w.r.t. the (forced) weights w:
+//   d = eps + rms(w);  dw_i = c/d * (g_i - w_i * <g,w> / (K * rms * d)),  g = sum of the wgrad split partials.
+// One CTA per (output channel, parameter): blockIdx.y selects one of up to two parameters that share the partials
+// tensor (the 2D and the 3D weight of a gated conv: taps 9 at offset 0, taps 18 at offset 9) so a layer is ONE launch.
+// Pass 1 streams g and w once and prefetches the old gradient row into L2; pass 2 re-reads g and w (L2 hits; short rows
+// stay in registers) and writes dw (+)= ...  The kernel runs on the weight-gradient stream BESIDE the input-gradient
+// chain, so its footprint is kept small on purpose (<= 64 registers, no shared-memory row): a variant caching whole
+// 9216-float rows in registers was 20 % faster alone but took every register of the SM and slowed the two-stream
+// backward pass (10.75 -> 10.94 ms).
+constexpr int WNB_CACHE = 2;
+struct WnormBwdPart {
+  const float* w;
+  float* dw;
+  int taps, tap_off;
+  float gain;
+};
+struct WnormBwdArgs {
+  WnormBwdPart part[2];
+  const float* dwg;
+  int Co, Ci, Ci_pad, taps_total, n_split, accumulate;
+  float eps;
+};
+
+__global__ void __launch_bounds__(256, 4) wnorm_bwd_kernel(const WnormBwdArgs a) {
   pdl_launch_dependents();
   pdl_wait();
-  __shared__ float red[32];
-  extern __shared__ float gbuf[];  // [taps][Ci + 1]
-  const int taps = TAPS > 0 ? TAPS : taps_rt;
+  __shared__ float red2[2][8];
+  const WnormBwdPart pt = a.part[blockIdx.y];
   const int co = blockIdx.x;
+  const int Ci = a.Ci, taps = pt.taps;
   const int K = Ci * taps;
-  const int ld = Ci + 1;
-  const float* wr = w + static_cast<long>(co) * K;
-  float* dwr = dw + static_cast<long>(co) * K;
-  const long split_stride = static_cast<long>(Co) * taps_total * Ci_pad;
-  const float* gsrc = dwg + (static_cast<long>(co) * taps_total + tap_off) * Ci_pad;
-  const bool vec_g = ((Ci_pad & 3) == 0) && ((split_stride & 3) == 0) && ((reinterpret_cast<uintptr_t>(gsrc) & 15) == 0);
-  const bool vec_w = ((K & 3) == 0) && (((reinterpret_cast<uintptr_t>(wr) | reinterpret_cast<uintptr_t>(dwr)) & 15) == 0);
-  // ---- stage 1: reduce the split partials, keep the row in shared memory (tap-major, padded).
-  //      warp <-> tap, lane <-> channel group: no index divisions, every thread busy, loads independent
-  {
-    // (1x1 kernels have a single tap: then the whole block walks the channels)
-    const bool flat = (TAPS == 1);
-    const int warp = flat ? 0 : (threadIdx.x >> 5), nwarps = flat ? 1 : (blockDim.x >> 5);
-    const int lane = flat ? threadIdx.x : (threadIdx.x & 31);
-    const int lanes = flat ? blockDim.x : 32;
-    for (int tap = warp; tap < taps; tap += nwarps) {
-      const float* src = gsrc + tap * Ci_pad;
-      float* dst = gbuf + tap * ld;
-      if (vec_g) {
-#pragma unroll 4
-        for (int c4 = lane; c4 < Ci_pad / 4; c4 += lanes) {
-          float4 g = *reinterpret_cast<const float4*>(src + c4 * 4);
-          for (int sp = 1; sp < n_split; ++sp) {
-            const float4 t = *reinterpret_cast<const float4*>(src + sp * split_stride + c4 * 4);
-            g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w;
-          }
-          const int ci = c4 * 4;
-          if (ci + 3 < Ci) { dst[ci] = g.x; dst[ci + 1] = g.y; dst[ci + 2] = g.z; dst[ci + 3] = g.w; }
-          else {
-            if (ci < Ci) dst[ci] = g.x;
-            if (ci + 1 < Ci) dst[ci + 1] = g.y;
-            if (ci + 2 < Ci) dst[ci + 2] = g.z;
-          }
-        }
-      } else {
-        for (int ci = lane; ci < Ci; ci += lanes) {
-          float g = 0.f;
-          for (int sp = 0; sp < n_split; ++sp) g += src[sp * split_stride + ci];
-          dst[ci] = g;
-        }
-      }
-    }
-  }
-  __syncthreads();
-  // ---- stage 2: <g,w> and |w|^2 in the parameter's own order (coalesced 128-bit reads of w, conflict-free smem gather)
+  const float* wr = pt.w + static_cast<long>(co) * K;
+  float* dwr = pt.dw + static_cast<long>(co) * K;
+  const long split_stride = static_cast<long>(a.Co) * a.taps_total * a.Ci_pad;
+  const float* gsrc = a.dwg + (static_cast<long>(co) * a.taps_total + pt.tap_off) * a.Ci_pad;
+  const bool vec = (a.Ci_pad == Ci) && ((K & 3) == 0) && ((split_stride & 3) == 0) &&
+                   (((reinterpret_cast<uintptr_t>(wr) | reinterpret_cast<uintptr_t>(dwr) | reinterpret_cast<uintptr_t>(gsrc)) & 15) == 0);
+  const int nv = K / 4;
+  const bool cached = vec && nv <= WNB_CACHE * 256;
+  float4 gv[WNB_CACHE], wv[WNB_CACHE];
   float ss = 0.f, dot = 0.f;
-  if (vec_w) {
-#pragma unroll 3
-    for (int i4 = threadIdx.x; i4 < K / 4; i4 += blockDim.x) {
-      const float4 wv = *reinterpret_cast<const float4*>(wr + i4 * 4);
-      const float wa[4] = {wv.x, wv.y, wv.z, wv.w};
+  auto load_g = [&](int i4) {
+    float4 g = *reinterpret_cast<const float4*>(gsrc + i4 * 4);
+    for (int sp = 1; sp < a.n_split; ++sp) {
+      const float4 t = *reinterpret_cast<const float4*>(gsrc + sp * split_stride + i4 * 4);
+      g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w;
+    }
+    return g;
+  };
+  if (cached) {
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int i = i4 * 4 + u;
-        const int ci = i / taps, tap = i - ci * taps;
-        ss += wa[u] * wa[u];
-        dot += gbuf[tap * ld + ci] * wa[u];
+    for (int v = 0; v < WNB_CACHE; ++v) {
+      const int i4 = threadIdx.x + v * 256;
+      if (i4 < nv) {
+        wv[v] = *reinterpret_cast<const float4*>(wr + i4 * 4);
+        gv[v] = load_g(i4);
+        if (a.accumulate) asm volatile("prefetch.global.L2 [%0];" ::"l"(dwr + i4 * 4));
       }
     }
+#pragma unroll
+    for (int v = 0; v < WNB_CACHE; ++v) {
+      if (threadIdx.x + v * 256 < nv) {
+        ss += wv[v].x * wv[v].x + wv[v].y * wv[v].y + wv[v].z * wv[v].z + wv[v].w * wv[v].w;
+        dot += gv[v].x * wv[v].x + gv[v].y * wv[v].y + gv[v].z * wv[v].z + gv[v].w * wv[v].w;
+      }
+    }
+  } else if (vec) {
+    for (int i4 = threadIdx.x; i4 < nv; i4 += 256) {
+      const float4 w4 = *reinterpret_cast<const float4*>(wr + i4 * 4);
+      const float4 g = load_g(i4);
+      ss += w4.x * w4.x + w4.y * w4.y + w4.z * w4.z + w4.w * w4.w;
+      dot += g.x * w4.x + g.y * w4.y + g.z * w4.z + g.w * w4.w;
+    }
   } else {
-    for (int i = threadIdx.x; i < K; i += blockDim.x) {
-      const int ci = i / taps, tap = i - ci * taps;
-      const float wv = wr[i];
-      ss += wv * wv;
-      dot += gbuf[tap * ld + ci] * wv;
+    for (int i = threadIdx.x; i < K; i += 256) {
+      const int tap = i / Ci, ci = i - tap * Ci;
+      float g = 0.f;
+      for (int sp = 0; sp < a.n_split; ++sp) g += gsrc[sp * split_stride + tap * a.Ci_pad + ci];
+      ss += wr[i] * wr[i];
+      dot += g * wr[i];
     }
   }
-  ss = block_sum(ss, red);
-  dot = block_sum(dot, red);
-  const float rms = sqrtf(ss / K);
-  const float d = eps + rms;
-  const float c = gain * rsqrtf(static_cast<float>(K)) / d;
-  const float proj = (rms > 0.f) ? dot / (K * rms * d) : 0.f;
-  // ---- stage 3: dw (+)= c * (g - w * proj)
-  if (vec_w) {
-#pragma unroll 3
-    for (int i4 = threadIdx.x; i4 < K / 4; i4 += blockDim.x) {
-      const float4 wv = *reinterpret_cast<const float4*>(wr + i4 * 4);
-      const float wa[4] = {wv.x, wv.y, wv.z, wv.w};
-      float o[4];
+  {   // both sums in one block reduction
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    ss = warp_sum(ss);
+    dot = warp_sum(dot);
+    if (lane == 0) { red2[0][warp] = ss; red2[1][warp] = dot; }
+    __syncthreads();
+    ss = 0.f; dot = 0.f;
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int i = i4 * 4 + u;
-        const int ci = i / taps, tap = i - ci * taps;
-        o[u] = c * (gbuf[tap * ld + ci] - wa[u] * proj);
-      }
-      float4* dst = reinterpret_cast<float4*>(dwr + i4 * 4);
-      if (accumulate) {
-        const float4 old = *dst;
-        o[0] += old.x; o[1] += old.y; o[2] += old.z; o[3] += old.w;
-      }
-      *dst = make_float4(o[0], o[1], o[2], o[3]);
+    for (int w8 = 0; w8 < 8; ++w8) { ss += red2[0][w8]; dot += red2[1][w8]; }
+  }
+  const float rms = sqrtf(ss / K);
+  const float d = a.eps + rms;
+  const float c = pt.gain * rsqrtf(static_cast<float>(K)) / d;
+  const float proj = (rms > 0.f) ? dot / (K * rms * d) : 0.f;
+  auto emit = [&](int i4, const float4& g, const float4& w4) {
+    float4 o = make_float4(c * (g.x - w4.x * proj), c * (g.y - w4.y * proj), c * (g.z - w4.z * proj), c * (g.w - w4.w * proj));
+    float4* dst = reinterpret_cast<float4*>(dwr + i4 * 4);
+    if (a.accumulate) {
+      const float4 old = *dst;
+      o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
     }
+    *dst = o;
+  };
+  if (cached) {
+#pragma unroll
+    for (int v = 0; v < WNB_CACHE; ++v) {
+      const int i4 = threadIdx.x + v * 256;
+      if (i4 < nv) emit(i4, gv[v], wv[v]);
+    }
+  } else if (vec) {
+    for (int i4 = threadIdx.x; i4 < nv; i4 += 256) emit(i4, load_g(i4), *reinterpret_cast<const float4*>(wr + i4 * 4));
   } else {
-    for (int i = threadIdx.x; i < K; i += blockDim.x) {
-      const int ci = i / taps, tap = i - ci * taps;
-      const float v = c * (gbuf[tap * ld + ci] - wr[i] * proj);
-      dwr[i] = accumulate ? dwr[i] + v : v;
+    for (int i = threadIdx.x; i < K; i += 256) {
+      const int tap = i / Ci, ci = i - tap * Ci;
+      float g = 0.f;
+      for (int sp = 0; sp < a.n_split; ++sp) g += gsrc[sp * split_stride + tap * a.Ci_pad + ci];
+      const float v = c * (g - wr[i] * proj);
+      dwr[i] = a.accumulate ? dwr[i] + v : v;
     }
   }
 }
@@ -733,29 +742,23 @@ int wnorm_fwd(float* w, void* wg, int Co, int Ci, int taps, int Ci_pad, int taps
   return check_launch("wnorm_fwd");
 }
 
+int wnorm_bwd2(const float* w0, float* dw0, int taps0, int tap_off0, float gain0, const float* w1, float* dw1, int taps1,
+               int tap_off1, float gain1, const float* dwg, int Co, int Ci, int Ci_pad, int taps_total, int n_split, float eps,
+               int accumulate, cudaStream_t st) {
+  if (Co <= 0) return OB_OK;
+  WnormBwdArgs a;
+  a.part[0] = WnormBwdPart{w0, dw0, taps0, tap_off0, gain0};
+  a.part[1] = WnormBwdPart{w1, dw1, taps1, tap_off1, gain1};
+  a.dwg = dwg; a.Co = Co; a.Ci = Ci; a.Ci_pad = Ci_pad; a.taps_total = taps_total; a.n_split = n_split;
+  a.accumulate = accumulate; a.eps = eps;
+  launch(wnorm_bwd_kernel, dim3(Co, w1 != nullptr ? 2 : 1), 256, 0, st, 1, a);
+  return check_launch("wnorm_bwd");
+}
+
 int wnorm_bwd(const float* w, const float* dwg, float* dw, int Co, int Ci, int taps, int Ci_pad, int taps_total,
               int tap_off, int n_split, float gain, float eps, int accumulate, cudaStream_t st) {
-  if (Co <= 0) return OB_OK;
-  const size_t smem = static_cast<size_t>(Ci + 1) * taps * sizeof(float);
-  if (smem > 200 * 1024) {
-    set_error("wnorm_bwd: row of %d x %d floats exceeds shared memory", Ci, taps);
-    return OB_ERR_UNSUPPORTED;
-  }
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(wnorm_bwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(wnorm_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(wnorm_bwd_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(wnorm_bwd_kernel<18>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    configured = true;
-  }
-#define OB_WNORM_BWD(T) launch(wnorm_bwd_kernel<T>, Co, 256, smem, st, 1, w, dwg, dw, Co, Ci, taps, Ci_pad, taps_total, tap_off, n_split, gain, eps, accumulate)
-  if (taps == 1) OB_WNORM_BWD(1);
-  else if (taps == 9) OB_WNORM_BWD(9);
-  else if (taps == 18) OB_WNORM_BWD(18);
-  else OB_WNORM_BWD(0);
-#undef OB_WNORM_BWD
-  return check_launch("wnorm_bwd");
+  return wnorm_bwd2(w, dw, taps, tap_off, gain, nullptr, nullptr, 0, 0, 0.f, dwg, Co, Ci, Ci_pad, taps_total, n_split, eps,
+                    accumulate, st);
 }
 
 int gate_bwd(const void* dy, const void* y, const void* d, const float* alpha, const float* beta, void* gya, void* gb,

@@ -57,16 +57,35 @@ def weight_operand(params, taps, cin, cin_pad, gains, training, eps=1e-4):
     wg = alloc((cout_pad, total, cin_pad), dtype=BF16, device=params[0].device)
     off = 0
     for p, t, g in zip(params, taps, gains):
-        assert p.dtype == torch.float32 and p.is_contiguous()
+        assert p.dtype == torch.float32 and tap_major(p), "conv weights are stored tap-major (channels_last)"
         call("ob_wnorm_fwd", _vp(p), _vp(wg), cout, cin, t, cin_pad, total, off, float(g), eps, int(training), stream_ptr())
         off += t
     return wg
 
 
+def tap_major(p):
+    """True when a conv weight [Co, Ci, *k] is stored as [Co, *k, Ci] (channels_last / channels_last_3d)."""
+    if p.ndim == 4:
+        return p.is_contiguous(memory_format=torch.channels_last)
+    if p.ndim == 5:
+        return p.is_contiguous(memory_format=torch.channels_last_3d)
+    return p.is_contiguous()
+
+
+def to_tap_major(w):
+    if w.ndim == 4:
+        return w.contiguous(memory_format=torch.channels_last)
+    if w.ndim == 5:
+        return w.contiguous(memory_format=torch.channels_last_3d)
+    return w.contiguous()
+
+
 def grad_buffer(p):
-    """The parameter's .grad, created zero-filled on first use; kernels accumulate into it directly."""
+    """The parameter's .grad (same storage order as the parameter), created zero-filled on first use; kernels
+    accumulate into it directly."""
     if p.grad is None:
-        p.grad = torch.zeros_like(p, memory_format=torch.contiguous_format)
+        p.grad = torch.zeros_like(p, memory_format=torch.preserve_format)
+    assert p.grad.stride() == p.stride()
     return p.grad
 
 
@@ -79,6 +98,10 @@ def weight_grad(params, taps, cin, cin_pad, gains, dwg, n_split, eps=1e-4):
     if dwg.shape[1] != cout:      # Cout was padded to a multiple of 8: fold the splits and drop the pad rows
         dwg = dwg.sum(0, keepdim=True)[:, :cout].contiguous()
         n_split = 1
+    if len(params) == 2 and list(taps) == [9, 18] and all(p.requires_grad for p in params) and all(float(g) == 1.0 for g in gains):
+        call("ob_wnorm_bwd_gated", _vp(params[0]), _vp(grad_buffer(params[0])), _vp(params[1]), _vp(grad_buffer(params[1])),
+             _vp(dwg), cout, cin, cin_pad, n_split, eps, 1, stream_ptr())
+        return
     off = 0
     for p, t, g in zip(params, taps, gains):
         if p.requires_grad:

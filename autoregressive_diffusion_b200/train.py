@@ -37,6 +37,11 @@ def init_distributed():
     return rank, world, local
 
 
+def _view_like(flat, off, p):
+    """A view of flat[off : off + p.numel()] with p's shape AND storage order (conv weights are stored tap-major)."""
+    return torch.as_strided(flat, p.shape, p.stride(), off)
+
+
 def _pad64(n):
     """Every per-parameter view starts 256-byte aligned (the kernels use 128-bit accesses)."""
     return (n + 63) // 64 * 64
@@ -62,7 +67,7 @@ class GradientBuckets:
         self.flat = torch.zeros(total, dtype=torch.float32, device=live[0].device)
         off = 0
         for p in live:
-            view = self.flat[off:off + p.numel()].view_as(p)
+            view = _view_like(self.flat, off, p)
             view.copy_(p.grad)
             p.grad = view
             off += _pad64(p.numel())
@@ -118,11 +123,11 @@ class FusedAdamWEMA:
         with torch.no_grad():
             for p in live:
                 n = p.numel()
-                view = self.flat_p[off:off + n].view_as(p)
+                view = _view_like(self.flat_p, off, p)
                 view.copy_(p)
                 p.data = view
                 for k, fe in enumerate(self.flat_ema):
-                    ev = fe[off:off + n].view_as(p)
+                    ev = _view_like(fe, off, p)
                     ev.copy_(self.ema[k][index[id(p)]])
                     self.ema[k][index[id(p)]] = ev
                 off += _pad64(n)

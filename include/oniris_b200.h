@@ -36,7 +36,10 @@ const char* ob_last_error(void);
 
 /* ---------------------------------------------------------------------------------------------- weights
  * edm2/conv.py:14-21 NormalizedWeight.forward (+ edm2/utils.py:83-88 normalize).
- * w: fp32 [Cout][Cin][taps] (the nn.Parameter, row-major).  Writes the bf16 GEMM operand
+ * w: fp32 [Cout][taps][Cin] -- the reference's [Cout, Cin, (kt,) kh, kw] parameter stored TAP-MAJOR (torch channels_last /
+ * channels_last_3d memory format; same logical shape and state_dict, so reference checkpoints load unchanged).  This is
+ * the order of the GEMM operand and of the weight-gradient partials, so both directions are straight row streams.
+ * Writes the bf16 GEMM operand
  * wg[Cout][taps_total][cin_pad] at tap offset tap_off (channels >= Cin zero-filled).  training != 0 also
  * overwrites w in place with its forced-normalised value and normalises THAT for the operand, exactly as the
  * reference's in-place copy_ + second normalize does. */
@@ -44,10 +47,13 @@ int ob_wnorm_fwd(float* w, void* wg, int cout, int cin, int taps, int cin_pad, i
                  float eps, int training, void* stream);
 
 /* Backward of the above w.r.t. the (forced) weights: dwg fp32 [n_split][Cout][taps_total][cin_pad] are the
- * split-K partial sums written by ob_conv_wgrad; dw fp32 [Cout][Cin][taps] is overwritten, or (accumulate != 0)
- * added to -- gradient accumulation over micro-batches (cs_train.py:108-109) without a separate pass. */
+ * split-K partial sums written by ob_conv_wgrad; dw fp32 [Cout][taps][Cin] (same storage order as w) is overwritten, or
+ * (accumulate != 0) added to -- gradient accumulation over micro-batches (cs_train.py:108-109) without a separate pass.
+ * ob_wnorm_bwd_gated does the 2D (9 taps at offset 0) and 3D (18 taps at offset 9) weights of a gated conv in one launch. */
 int ob_wnorm_bwd(const float* w, const float* dwg, float* dw, int cout, int cin, int taps, int cin_pad, int taps_total,
                  int tap_off, int n_split, float gain, float eps, int accumulate, void* stream);
+int ob_wnorm_bwd_gated(const float* w2, float* dw2, const float* w3, float* dw3, const float* dwg, int cout, int cin,
+                       int cin_pad, int n_split, float eps, int accumulate, void* stream);
 
 /* ---------------------------------------------------------------------------------------------- convolutions
  * edm2/conv.py:36-42 (MPConv: F.conv2d k=1|3) and :59-95 (MPCausal3DGatedConv: F.conv2d + F.conv3d + mp_sum).
