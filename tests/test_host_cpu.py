@@ -129,3 +129,30 @@ def test_functional_utils_on_cpu(golden):
     assert torch.allclose(ob.normalize(a, dim=1), g["norm1"], atol=1e-6)
     assert torch.allclose(ob.resample(a, mode="down"), g["down"], atol=1e-6)
     assert torch.allclose(ob.resample(a, mode="up"), g["up"], atol=1e-6)
+
+
+def test_conv_weights_are_tap_major_and_checkpoint_compatible(tmp_path):
+    """Conv parameters keep the reference's logical shape / state_dict (edm2/conv.py:11) while living in channels_last
+    storage ([Co][taps][Ci], the GEMM operand order): a reference-layout checkpoint round-trips bit-exactly."""
+    import autoregressive_diffusion_b200 as ob
+    from autoregressive_diffusion_b200.ops import tap_major
+    torch.manual_seed(0)
+    conv = ob.MPCausal3DGatedConv(16, 24, kernel=[3, 3, 3])
+    w2, w3 = conv.last_frame_conv.weight.weight, conv.weight.weight
+    assert tuple(w2.shape) == (24, 16, 3, 3) and tuple(w3.shape) == (24, 16, 2, 3, 3)
+    assert tap_major(w2) and tap_major(w3) and w2.stride() == (144, 1, 48, 16) and w3.stride() == (288, 1, 144, 48, 16)
+    ref = {k: torch.randn(v.shape) for k, v in conv.state_dict().items()}          # contiguous, as the reference saves them
+    conv.load_state_dict(ref)
+    assert tap_major(conv.weight.weight), "load_state_dict must not change the storage order"
+    path = tmp_path / "ckpt.pt"
+    torch.save(conv.state_dict(), path)
+    back = torch.load(path)
+    for k, v in ref.items():
+        assert torch.equal(back[k], v), k
+    # flat optimizer / gradient views share the parameter's storage order
+    from autoregressive_diffusion_b200.train import _view_like
+    flat = torch.zeros(w3.numel() + 64)
+    view = _view_like(flat, 64, w3)
+    view.copy_(w3)
+    assert view.stride() == w3.stride() and torch.equal(view, w3)
+    assert torch.equal(flat[64:], w3.detach().permute(0, 2, 3, 4, 1).reshape(-1))    # physically [Co][kt][kh][kw][Ci]
