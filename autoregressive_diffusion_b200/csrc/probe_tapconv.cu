@@ -238,6 +238,8 @@ int main(int argc, char** argv) {
     run(gated("CS 512->512 16x16 B2 n16", 2, 2, 16, 16, 16, 512, 512), false, 2);
     run(plain("1x1 256->128 32x32 F64", 64, 32, 32, 256, 128, 1, 0), false, 2);
     run(gated("CS 512->512 8x8 split auto", 2, 2, 16, 8, 8, 512, 512, 0, 1), false, 2);
+    run(gated("CS 512->512 4x4 split auto", 2, 2, 16, 4, 4, 512, 512, 0, 1), false, 2);
+    run(gated("CS 512->512 4x4 nosplit", 2, 2, 16, 4, 4, 512, 512, 0, 0), false, 2);
     run(dgrad("dgrad BMN 128->128 32x32 B2 n16", 2, 16, 32, 32, 128, 128, 1), false, 2);
     return 0;
   }

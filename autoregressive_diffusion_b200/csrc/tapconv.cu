@@ -152,7 +152,9 @@ static int launch_bn(int bn, const TapConvParams& p, dim3 grid, cudaStream_t s) 
 }
 
 static void tile_shape(int H, int W, int* bw, int* bh, int* bt) {
-  *bw = pow2_ceil(W) > 128 ? 128 : pow2_ceil(W);
+  // at most 16 pixels wide: a squarer box carries fewer halo rows per output row ((bh+2)/bh: 1.25 for 8 rows against
+  // 1.5 for 4), and the halo is pure extra L2->SM traffic on the operand that bounds the wide layers
+  *bw = pow2_ceil(W) > 16 ? 16 : pow2_ceil(W);
   *bh = pow2_ceil(H);
   if (*bh > 128 / *bw) *bh = 128 / *bw;
   if (*bh > 16) *bh = 16;
