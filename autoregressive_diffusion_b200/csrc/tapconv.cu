@@ -317,6 +317,8 @@ int tapconv_launch(const TapConvLaunch& L, cudaStream_t stream) {
   p.alpha = L.alpha; p.beta = L.beta; p.out = L.out; p.out_d = L.out_d;
 
   p.trace = L.trace;
+  p.wide_store = (L.Cout % 16 == 0) && (reinterpret_cast<uintptr_t>(L.out) % 32 == 0) &&
+                 (reinterpret_cast<uintptr_t>(L.out_d) % 32 == 0) && bn >= 32;
   p.ksplit = 1;
   p.split_ws = nullptr;
   if (L.split_ws != nullptr) {

@@ -67,6 +67,7 @@ struct TapConvParams {
   int n_out;    // output row sets per tile (2 in dual mode)
   int epi;      // EPI_*
   int out_f32;  // 0: bf16 out, 1: fp32 out
+  int wide_store;  // 1: the epilogue may use 256-bit stores (Cout % 16 == 0, out / out_d 32-byte aligned)
   const float* alpha;  // [n_seq*n_out*T] per output frame (EPI_GATED)
   const float* beta;
   void* out;    // [n_seq*n_out*T, H, W, Cout]
@@ -436,6 +437,36 @@ __global__ void __launch_bounds__(TAPCONV_THREADS, 1) tapconv_kernel(const __gri
           }
           const int col0 = n0 + c * CW;
           if (row_ok) {
+            if (p.wide_store) {
+              // 256-bit stores: one full 32-byte sector per thread and instruction (Cout % 16 == 0, 32-byte aligned bases)
+              if (p.out_f32) {
+                float* dst = static_cast<float*>(p.out) + row_off + col0;
+#pragma unroll
+                for (int j = 0; j < CW; j += 8)
+                  if (col0 + j + 8 <= p.Cout) st_global_f32x8(dst + j, y + j);
+              } else {
+                __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(p.out) + row_off + col0;
+#pragma unroll
+                for (int j = 0; j < CW; j += 16)
+                  if (col0 + j + 16 <= p.Cout) {
+                    uint32_t pk[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) pk[u] = pack_bf16x2(y[j + 2 * u], y[j + 2 * u + 1]);
+                    st_global_b32x8(dst + j, pk);
+                  }
+              }
+              if (p.epi == EPI_GATED && p.out_d != nullptr) {
+                float* dd = static_cast<float*>(p.out_d) + row_off + col0;
+#pragma unroll
+                for (int j = 0; j < CW; j += 8)
+                  if (col0 + j + 8 <= p.Cout) {
+                    float dv[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) dv[u] = shr[j + u] - own[j + u];
+                    st_global_f32x8(dd + j, dv);
+                  }
+              }
+            } else {
             if (p.out_f32) {
               float* dst = static_cast<float*>(p.out) + row_off + col0;
 #pragma unroll
@@ -457,6 +488,7 @@ __global__ void __launch_bounds__(TAPCONV_THREADS, 1) tapconv_kernel(const __gri
                 if (col0 + j + 4 <= p.Cout)
                   *reinterpret_cast<float4*>(dd + j) =
                       make_float4(shr[j] - own[j], shr[j + 1] - own[j + 1], shr[j + 2] - own[j + 2], shr[j + 3] - own[j + 3]);
+            }
             }
           }
         }
