@@ -127,6 +127,9 @@ class WeightGradBranch:
     """
 
     enabled = True
+    defer_join = False     # True: the caller joins explicitly (Trainer: before the gradient all-reduce / optimizer step), so
+                           # the branch's tail overlaps the NEXT micro-step's forward pass instead of stalling this one
+    priority = 0           # CUDA stream priority of the branch (0 = lowest; the main chain may run on a higher one)
     _streams = {}
     _pending = []          # [(done_event, tensors)] in launch order
     _join_queued = False
@@ -135,7 +138,7 @@ class WeightGradBranch:
     def stream(cls, device):
         key = torch.device(device).index
         if key not in cls._streams:
-            cls._streams[key] = torch.cuda.Stream(device=device)
+            cls._streams[key] = torch.cuda.Stream(device=device, priority=cls.priority)
         return cls._streams[key]
 
     @classmethod
@@ -160,13 +163,19 @@ class WeightGradBranch:
         if not cls._join_queued:
             cls._join_queued = True
             query("ob_set_pdl", 0)     # two active streams: early-resident dependents would take the other stream's SMs
-            torch.autograd.Variable._execution_engine.queue_callback(lambda: cls.join(device))
+            torch.autograd.Variable._execution_engine.queue_callback(lambda: cls.end_of_backward(device))
+
+    @classmethod
+    def end_of_backward(cls, device):
+        cls._join_queued = False
+        query("ob_set_pdl", 1)
+        if not cls.defer_join:
+            cls.join(device)
 
     @classmethod
     def join(cls, device):
-        """Make the current stream wait for the branch (runs automatically at the end of every backward pass)."""
-        cls._join_queued = False
-        query("ob_set_pdl", 1)
+        """Make the current stream wait for the branch (runs automatically at the end of every backward pass unless
+        defer_join is set)."""
         if cls._pending:
             torch.cuda.current_stream(device).wait_stream(cls.stream(device))
             cls._pending.clear()

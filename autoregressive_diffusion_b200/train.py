@@ -210,7 +210,10 @@ class Trainer:
         assert self.accum >= 2 and self.micro % self.accum == 0 and not self.just_2d_every
         self.static_x = torch.empty_like(example_latents)
         self.static_x.copy_(example_latents)
-        side = torch.cuda.Stream()
+        # capture (and warm up) on a HIGH-priority stream: the captured main chain is the critical path of the backward
+        # pass, the weight-gradient branch (priority 0) fills in behind it (backward 10.78 -> 10.54 ms)
+        side = torch.cuda.Stream(priority=-1)
+        self._capture_stream = side
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):          # warm-up off the default stream, as graph capture requires
             for _ in range(2 * self.accum):
@@ -225,11 +228,11 @@ class Trainer:
                 self.micro += 1
                 continue
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            with torch.cuda.graph(g, stream=self._capture_stream):
                 loss, _ = self._forward_backward(self.static_x)
             self.graphs[kind] = (g, loss)
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
+        with torch.cuda.graph(g, stream=self._capture_stream):
             self._optimizer_step()
         self.graphs["opt"] = (g, None)
         self._plan = plan

@@ -9,6 +9,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from autoregressive_diffusion_b200.ops import WeightGradBranch  # noqa: E402
 from autoregressive_diffusion_b200.train import CS_UNET, Trainer  # noqa: E402
 
+WeightGradBranch.priority = int(os.environ.get("SIDE_PRIO", "0"))
+main_stream = torch.cuda.Stream(priority=int(os.environ.get("MAIN_PRIO", "0")))
+torch.cuda.set_stream(main_stream)
 tr = Trainer(CS_UNET, device="cuda")
 x = torch.randn(2, 16, 8, 32, 32, device="cuda")
 for _ in range(6):
@@ -23,9 +26,15 @@ def measure():
     tr.micro += 1
     loss, _ = tr.loss_fn(tr.precond, x, None)
     ev[1].record()
+    WeightGradBranch.defer_join = True
     (loss / tr.accum).backward()
+    ev.append(torch.cuda.Event(enable_timing=True))
+    ev[3].record()                       # main stream's own backward work done (branch not yet joined)
+    WeightGradBranch.defer_join = False
+    WeightGradBranch.join(x.device)
     ev[2].record()
     torch.cuda.synchronize()
+    print(f"   main-stream backward chain {ev[1].elapsed_time(ev[3]):.2f} ms, then waits {ev[3].elapsed_time(ev[2]):.2f} ms for the weight-gradient stream")
     return ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])
 
 
