@@ -237,8 +237,8 @@ int ob_resample2x(const void* in, void* out, int64_t frames, int h, int w, int c
 }
 int ob_set_pdl(int enabled) {
   static const bool forced_off = [] { const char* e = getenv("ONIRIS_PDL"); return e != nullptr && e[0] == '0'; }();
-  const int prev = pdl_enabled() ? 1 : 0;
-  if (!forced_off) pdl_flag().store(enabled ? 1 : 0, std::memory_order_relaxed);
+  const int prev = pdl_mode();
+  if (!forced_off) pdl_flag().store(enabled < 0 ? 0 : enabled > 2 ? 2 : enabled, std::memory_order_relaxed);
   return prev;
 }
 int ob_adamw_ema(float* p, float* g, float* m, float* v, float* ema1, float* ema2, int64_t n, const float* step_lr,

@@ -21,23 +21,29 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 // Process-wide switch (ob_set_pdl).  The backward pass turns it off: there the weight-gradient kernels run on a second
 // stream, and dependents that become resident early (holding shared memory / TMEM while they wait) take SMs the other
 // stream's CTAs would have used -- measured: forward 6.05 -> 5.48 ms with PDL, two-stream backward 11.0 -> 11.4 ms.
+// Mode 2 (only the light, elementwise kernels) was measured too and is no better there (11.29 ms): the backward pass
+// runs with PDL off.
 inline std::atomic<int>& pdl_flag() {
   static std::atomic<int> flag{-1};
   return flag;
 }
-inline bool pdl_enabled() {
+// 0: off, 1: every kernel, 2: only "light" kernels (no big shared-memory / TMEM footprint: the elementwise ones)
+inline int pdl_mode() {
   int v = pdl_flag().load(std::memory_order_relaxed);
   if (v < 0) {
     const char* e = getenv("ONIRIS_PDL");
     v = (e != nullptr && e[0] == '0') ? 0 : 1;
     pdl_flag().store(v, std::memory_order_relaxed);
   }
-  return v != 0;
+  return v;
 }
 
+// cluster_x > 1 launches clusters; a kernel with more than 48 KB of dynamic shared memory counts as "heavy".
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster_x,
                           Args&&... args) {
+  const int mode = pdl_mode();
+  const bool pdl = mode == 1 || (mode == 2 && smem <= 48 * 1024);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid;
   cfg.blockDim = block;
@@ -50,7 +56,7 @@ inline cudaError_t launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t 
     attr[n].val.clusterDim.x = cluster_x; attr[n].val.clusterDim.y = 1; attr[n].val.clusterDim.z = 1;
     ++n;
   }
-  if (pdl_enabled()) {
+  if (pdl) {
     attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[n].val.programmaticStreamSerializationAllowed = 1;
     ++n;

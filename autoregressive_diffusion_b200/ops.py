@@ -129,6 +129,7 @@ class WeightGradBranch:
     enabled = True
     defer_join = False     # True: the caller joins explicitly (Trainer: before the gradient all-reduce / optimizer step), so
                            # the branch's tail overlaps the NEXT micro-step's forward pass instead of stalling this one
+    backward_pdl = 0       # ob_set_pdl mode while the branch is active: off (measured, backward ms: off 10.45, light-only 11.29, all 11.28)
     priority = 0           # CUDA stream priority of the branch (0 = lowest; the main chain may run on a higher one)
     _streams = {}
     _pending = []          # [(done_event, tensors)] in launch order
@@ -162,7 +163,7 @@ class WeightGradBranch:
         cls._pending.append((done, keep))
         if not cls._join_queued:
             cls._join_queued = True
-            query("ob_set_pdl", 0)     # two active streams: early-resident dependents would take the other stream's SMs
+            query("ob_set_pdl", int(cls.backward_pdl))   # two active streams: heavy early-resident dependents would take the other stream's SMs
             torch.autograd.Variable._execution_engine.queue_callback(lambda: cls.end_of_backward(device))
 
     @classmethod

@@ -158,9 +158,10 @@ int ob_mp_cat_bwd(const void* g, void* da, void* db, int64_t rows, int ca, int c
 int ob_resample2x(const void* in, void* out, int64_t frames, int h, int w, int c, int pool, float scale, void* stream);
 
 /* Programmatic dependent launch: when on (default; ONIRIS_PDL=0 in the environment forces it off), every kernel of the
- * library is launched so that its prologue overlaps the tail of the previous kernel on the stream.  Returns the previous
- * setting.  The training backward pass switches it off while its second stream is active (see csrc/launch.cuh). */
-int ob_set_pdl(int enabled);
+ * library is launched so that its prologue overlaps the tail of the previous kernel on the stream.  mode 0: off, 1: every
+ * kernel, 2: only the light (elementwise) kernels.  Returns the previous mode.  The training backward pass switches it off
+ * while its second stream is active (see csrc/launch.cuh). */
+int ob_set_pdl(int mode);
 
 /* Optimizer step of the training loop (cs_train.py:121-125: torch.optim.AdamW.step, zero_grad, and the EMA copies of
  * the weights) over one flat fp32 range of n elements (n % 4 == 0, 16-byte aligned buffers):

@@ -10,6 +10,7 @@ from autoregressive_diffusion_b200.ops import WeightGradBranch  # noqa: E402
 from autoregressive_diffusion_b200.train import CS_UNET, Trainer  # noqa: E402
 
 WeightGradBranch.priority = int(os.environ.get("SIDE_PRIO", "0"))
+WeightGradBranch.backward_pdl = int(os.environ.get("BWD_PDL", "0"))
 main_stream = torch.cuda.Stream(priority=int(os.environ.get("MAIN_PRIO", "0")))
 torch.cuda.set_stream(main_stream)
 tr = Trainer(CS_UNET, device="cuda")
