@@ -54,7 +54,7 @@ _SIGS = {
     "ob_mp_cat_bwd": "pppliifp",
     "ob_resample2x": "ppliiiifp",
     "ob_set_pdl": "i",
-    "ob_adamw_ema": "pppppplpffffffp",
+    "ob_adamw_ema": "pppppplpfffffffp",
     "ob_qkv_prep_fwd": "ppppppppppliifp",
     "ob_qkv_prep_bwd": "ppppppppppliifp",
     "ob_rope_k": "ppppppliip",

@@ -242,9 +242,10 @@ int ob_set_pdl(int enabled) {
   return prev;
 }
 int ob_adamw_ema(float* p, float* g, float* m, float* v, float* ema1, float* ema2, int64_t n, const float* step_lr,
-                 float beta1, float beta2, float eps, float weight_decay, float ema_beta1, float ema_beta2, void* stream) {
+                 float beta1, float beta2, float eps, float weight_decay, float ema_beta1, float ema_beta2, float grad_scale,
+                 void* stream) {
   return adamw_ema(p, g, m, v, ema1, ema2, (long)n, step_lr, beta1, beta2, eps, weight_decay, ema_beta1, ema_beta2,
-                   (cudaStream_t)stream);
+                   grad_scale, (cudaStream_t)stream);
 }
 
 int ob_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int b, int heads, int lq, int lk, int hw,

@@ -1025,7 +1025,7 @@ int resample2x(const void* in, void* out, long frames, int h, int w, int c, int 
 __global__ void __launch_bounds__(256) adamw_ema_kernel(float4* __restrict__ p, float4* __restrict__ g, float4* __restrict__ m,
                                                         float4* __restrict__ v, float4* __restrict__ e1, float4* __restrict__ e2,
                                                         long n4, const float* __restrict__ step_lr, float beta1, float beta2,
-                                                        float eps, float wd, float ema1, float ema2) {
+                                                        float eps, float wd, float ema1, float ema2, float grad_scale) {
   pdl_launch_dependents();
   pdl_wait();
   const float step = step_lr[0], lr = step_lr[1];
@@ -1036,7 +1036,8 @@ __global__ void __launch_bounds__(256) adamw_ema_kernel(float4* __restrict__ p, 
   const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
   for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += static_cast<long>(gridDim.x) * blockDim.x) {
     float4 pv = p[i], mv = m[i], vv = v[i];
-    const float4 gv = g[i];
+    float4 gv = g[i];
+    gv.x *= grad_scale; gv.y *= grad_scale; gv.z *= grad_scale; gv.w *= grad_scale;   // 1/world after a summing all-reduce
     float* pp = &pv.x; float* mm = &mv.x; float* vp = &vv.x; const float* gg = &gv.x;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -1063,7 +1064,7 @@ __global__ void __launch_bounds__(256) adamw_ema_kernel(float4* __restrict__ p, 
 }
 
 int adamw_ema(float* p, float* g, float* m, float* v, float* e1, float* e2, long n, const float* step_lr, float beta1,
-              float beta2, float eps, float wd, float ema1, float ema2, cudaStream_t st) {
+              float beta2, float eps, float wd, float ema1, float ema2, float grad_scale, cudaStream_t st) {
   if (n % 4 != 0) { set_error("adamw_ema: element count %ld must be a multiple of 4", n); return OB_ERR_INVALID; }
   for (const void* q : {(const void*)p, (const void*)g, (const void*)m, (const void*)v, (const void*)e1, (const void*)e2})
     if (reinterpret_cast<uintptr_t>(q) % 16 != 0) { set_error("adamw_ema: buffers must be 16-byte aligned"); return OB_ERR_INVALID; }
@@ -1074,7 +1075,7 @@ int adamw_ema(float* p, float* g, float* m, float* v, float* e1, float* e2, long
   launch(adamw_ema_kernel, static_cast<unsigned>(blocks), 256, 0, st, 1, reinterpret_cast<float4*>(p), reinterpret_cast<float4*>(g),
                                                                  reinterpret_cast<float4*>(m), reinterpret_cast<float4*>(v),
                                                                  reinterpret_cast<float4*>(e1), reinterpret_cast<float4*>(e2), n4,
-                                                                 step_lr, beta1, beta2, eps, wd, ema1, ema2);
+                                                                 step_lr, beta1, beta2, eps, wd, ema1, ema2, grad_scale);
   return check_launch("adamw_ema");
 }
 

@@ -51,10 +51,11 @@ class GradientBuckets:
     """Gradient mean over the data-parallel ranks (the job DistributedDataParallel does in cs_train.py:54,108-109).
 
     After the first backward has shown which parameters receive gradients (emb_time, out_res, ... never do), their
-    .grad tensors are re-homed as views of ONE flat fp32 buffer; the all-reduce then runs in place on 256 MB slices of
-    that buffer (no flatten / unflatten copies), on a side stream, and the result is divided by the world size."""
+    .grad tensors are re-homed as views of ONE flat fp32 buffer; the all-reduce then runs in place on 128 MB slices of
+    that buffer (no flatten / unflatten copies), on a side stream.  In training the sum is consumed bucket by bucket by the
+    fused optimizer (FusedAdamWEMA.step_with_all_reduce), which folds the 1/world of the mean into its update."""
 
-    def __init__(self, params, bucket_bytes=256 << 20):
+    def __init__(self, params, bucket_bytes=128 << 20):
         self.params = [p for p in params if p.requires_grad]
         self.bucket_elems = max(1, bucket_bytes // 4)
         self.flat = None
@@ -133,19 +134,56 @@ class FusedAdamWEMA:
                 off += _pad64(n)
 
     @torch.no_grad()
-    def step(self):
-        """Update from the accumulated (and already all-reduced) gradients, then zero them."""
+    def begin_step(self):
+        """Advance the step count once per optimizer step (before the first update_range of that step)."""
         if not self.params[0].is_cuda:
             raise RuntimeError("FusedAdamWEMA runs on CUDA tensors only (no CPU fallback)")
         if self.flat_p is None:
             self._flatten()
-        from ._lib import _vp, call, stream_ptr
         self.step_lr[:1] += 1
-        e = [_vp(t) for t in self.flat_ema] + [None, None]
+
+    @torch.no_grad()
+    def update_range(self, lo=0, hi=None, grad_scale=1.0):
+        """AdamW + EMA + gradient reset on elements [lo, hi) of the flat buffers (multiples of 4).  grad_scale multiplies
+        the gradients first: 1/world_size turns a summing all-reduce into the mean without another pass."""
+        from ._lib import call, stream_ptr
+        import ctypes
+        hi = self.flat_p.numel() if hi is None else hi
+        assert lo % 4 == 0 and (hi - lo) % 4 == 0
+        at = lambda t: ctypes.c_void_p(t.data_ptr() + 4 * lo)
+        e = [at(t) for t in self.flat_ema] + [None, None]
         b = list(self.ema_betas) + [0.0, 0.0]
-        call("ob_adamw_ema", _vp(self.flat_p), _vp(self.buckets.flat), _vp(self.exp_avg), _vp(self.exp_avg_sq), e[0], e[1],
-             self.flat_p.numel(), _vp(self.step_lr), self.betas[0], self.betas[1], self.eps, self.weight_decay, b[0], b[1],
-             stream_ptr())
+        call("ob_adamw_ema", at(self.flat_p), at(self.buckets.flat), at(self.exp_avg), at(self.exp_avg_sq), e[0], e[1],
+             hi - lo, ctypes.c_void_p(self.step_lr.data_ptr()), self.betas[0], self.betas[1], self.eps, self.weight_decay,
+             b[0], b[1], float(grad_scale), stream_ptr())
+
+    def step(self):
+        """Update from the accumulated (and already averaged) gradients, then zero them."""
+        self.begin_step()
+        self.update_range()
+
+    def step_with_all_reduce(self):
+        """Data-parallel optimizer step: the gradient SUM over ranks runs bucket by bucket on the communication stream
+        while the buckets already reduced are being updated here (the mean's 1/world is folded into the update), so the
+        all-reduce and the HBM-bound update overlap instead of running back to back (cs_train.py:108-124 does
+        all-reduce, then step, then EMA)."""
+        world = dist.get_world_size()
+        self.begin_step()
+        bk = self.buckets
+        main = torch.cuda.current_stream()
+        bk.stream.wait_stream(main)
+        events = []
+        with torch.cuda.stream(bk.stream):
+            for b in bk.buckets:
+                dist.all_reduce(b)
+                ev = torch.cuda.Event()
+                ev.record(bk.stream)
+                events.append(ev)
+        lo = 0
+        for b, ev in zip(bk.buckets, events):
+            main.wait_event(ev)
+            self.update_range(lo, lo + b.numel(), 1.0 / world)
+            lo += b.numel()
 
 
 class _Null:
@@ -192,12 +230,17 @@ class Trainer:
     def _optimizer_step(self):
         self.opt.step()
 
+    def _distributed(self):
+        return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
     def micro_step(self, latents, conditioning=None):
         """One micro-batch forward+backward; every `accum`-th call also syncs gradients and steps the optimizer."""
         out = self._forward_backward(latents, conditioning)
         if self.micro % self.accum == 0:
-            self.buckets.all_reduce_mean()
-            self._optimizer_step()
+            if self._distributed():
+                self.opt.step_with_all_reduce()
+            else:
+                self._optimizer_step()
         return out
 
     # ------------------------------------------------------------------ CUDA-graph replay of the micro-step
@@ -249,7 +292,9 @@ class Trainer:
         g, loss = self.graphs[kind]
         g.replay()
         if kind == "last":
-            self.buckets.all_reduce_mean()     # the one collective on the path, outside the graphs
-            self.graphs["opt"][0].replay()
+            if self._distributed():            # the one collective on the path, outside the graphs, pipelined with the update
+                self.opt.step_with_all_reduce()
+            else:
+                self.graphs["opt"][0].replay()
         self._replayed += 1
         return loss

@@ -167,9 +167,12 @@ int ob_set_pdl(int mode);
  * the weights) over one flat fp32 range of n elements (n % 4 == 0, 16-byte aligned buffers):
  *   m = b1*m + (1-b1)*g;  v = b2*v + (1-b2)*g*g;  p = p*(1 - lr*wd) - lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
  *   ema_k += (1 - ema_beta_k) * (p - ema_k)   (either pointer may be NULL);   g = 0.
- * step_lr: device fp32 {t, lr} with t the 1-based step count of THIS update. */
+ * g is multiplied by grad_scale first (1/world_size after a SUM all-reduce: the mean costs no extra pass).
+ * step_lr: device fp32 {t, lr} with t the 1-based step count of THIS update.  The call may cover any 16-byte aligned
+ * sub-range, so a bucketed all-reduce can be pipelined with the update of the buckets already reduced. */
 int ob_adamw_ema(float* p, float* g, float* m, float* v, float* ema1, float* ema2, int64_t n, const float* step_lr,
-                 float beta1, float beta2, float eps, float weight_decay, float ema_beta1, float ema_beta2, void* stream);
+                 float beta1, float beta2, float eps, float weight_decay, float ema_beta1, float ema_beta2, float grad_scale,
+                 void* stream);
 
 /* ---------------------------------------------------------------------------------------------- attention
  * edm2/attention/attention_modules.py:59-77: compiled_flex_attention(q,k,v, make_train_mask / make_infer_mask) and

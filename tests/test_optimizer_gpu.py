@@ -26,7 +26,15 @@ def test_fused_adamw_ema_matches_torch():
         if step == 2:
             opt.lr.fill_(3e-3)                                       # a schedule writing the device-side learning rate
             ref_opt.param_groups[0]["lr"] = 3e-3
-        opt.step()
+        if step % 2 == 0:
+            opt.step()
+        else:   # the data-parallel form: ranges updated one after another, the gradient mean folded in as a scale
+            opt.buckets.flat.mul_(2.0)
+            opt.begin_step()
+            n = opt.flat_p.numel()
+            cut = (n // 3) // 4 * 4
+            opt.update_range(0, cut, 0.5)
+            opt.update_range(cut, n, 0.5)
         ref_opt.step()
         with torch.no_grad():
             for beta, shadow in zip(ema_betas, ref_ema):
