@@ -261,28 +261,43 @@ __global__ void __launch_bounds__(256) gate_bwd_kernel(const __nv_bfloat16* __re
   const int b = bt / T, t = bt - b * T;
   const long chunk0 = static_cast<long>(blockIdx.x) * blockDim.x * 8 + threadIdx.x * 8;
   const long stride = static_cast<long>(gridDim.x) * blockDim.x * 8;
-  float acc_b[8];
   float sy[2] = {0.f, 0.f}, sd[2] = {0.f, 0.f};
+  const long f0 = (static_cast<long>(b) * S) * T + t, f1 = f0 + T;   // clean / noised frame of this (b, t)
+  const float al0 = alpha[f0], be0 = beta[f0];
+  const float al1 = S > 1 ? alpha[f1] : 0.f, be1 = S > 1 ? beta[f1] : 0.f;
   for (long e = chunk0; e < frame_elems; e += stride) {
+    // all loads of both halves first (8 independent 128-bit requests per thread), then the arithmetic and the stores
+    const long o0 = f0 * frame_elems + e, o1 = f1 * frame_elems + e;
+    const bf16x8 g0v = *reinterpret_cast<const bf16x8*>(dy + o0), y0v = *reinterpret_cast<const bf16x8*>(y + o0);
+    const float4 d00 = *reinterpret_cast<const float4*>(d + o0), d01 = *reinterpret_cast<const float4*>(d + o0 + 4);
+    bf16x8 g1v = g0v, y1v = y0v;
+    float4 d10 = d00, d11 = d01;
+    if (S > 1) {
+      g1v = *reinterpret_cast<const bf16x8*>(dy + o1); y1v = *reinterpret_cast<const bf16x8*>(y + o1);
+      d10 = *reinterpret_cast<const float4*>(d + o1); d11 = *reinterpret_cast<const float4*>(d + o1 + 4);
+    }
+    float g0[8], y0[8], g1[8], y1[8], oa[8], ob_[8], acc_b[8];
+    unpack8(g0v, g0); unpack8(y0v, y0);
+    const float dv0[8] = {d00.x, d00.y, d00.z, d00.w, d01.x, d01.y, d01.z, d01.w};
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc_b[j] = 0.f;
-    for (int s = 0; s < S; ++s) {
-      const long f = (static_cast<long>(b) * S + s) * T + t;
-      const long off = f * frame_elems + e;
-      float g[8], yv[8], dv[8], o[8];
-      unpack8(*reinterpret_cast<const bf16x8*>(dy + off), g);
-      unpack8(*reinterpret_cast<const bf16x8*>(y + off), yv);
-      const float4 d0 = *reinterpret_cast<const float4*>(d + off), d1 = *reinterpret_cast<const float4*>(d + off + 4);
-      dv[0] = d0.x; dv[1] = d0.y; dv[2] = d0.z; dv[3] = d0.w; dv[4] = d1.x; dv[5] = d1.y; dv[6] = d1.z; dv[7] = d1.w;
-      const float al = alpha[f], be = beta[f];
+    for (int j = 0; j < 8; ++j) {
+      oa[j] = al0 * g0[j];
+      acc_b[j] = be0 * g0[j];
+      sy[0] += g0[j] * y0[j];
+      sd[0] += g0[j] * dv0[j];
+    }
+    *reinterpret_cast<bf16x8*>(gya + o0) = pack8(oa);
+    if (S > 1) {
+      unpack8(g1v, g1); unpack8(y1v, y1);
+      const float dv1[8] = {d10.x, d10.y, d10.z, d10.w, d11.x, d11.y, d11.z, d11.w};
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        o[j] = al * g[j];
-        acc_b[j] += be * g[j];
-        sy[s] += g[j] * yv[j];
-        sd[s] += g[j] * dv[j];
+        ob_[j] = al1 * g1[j];
+        acc_b[j] += be1 * g1[j];
+        sy[1] += g1[j] * y1[j];
+        sd[1] += g1[j] * dv1[j];
       }
-      *reinterpret_cast<bf16x8*>(gya + off) = pack8(o);
+      *reinterpret_cast<bf16x8*>(gya + o1) = pack8(ob_);
     }
     *reinterpret_cast<bf16x8*>(gb + static_cast<long>(bt) * frame_elems + e) = pack8(acc_b);
   }
