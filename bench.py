@@ -133,6 +133,15 @@ def oracle_cpu_step(batch, seed=0):
     return step
 
 
+def workload_config(parallelism, launch):
+    """The workload both arms are quoted on (BASELINE.json configs[2], one GPU's share)."""
+    return {"workload": "cs_train.py Counter-Strike UNet (310M params), DART 32-frame sequence, fwd+bwd micro-step; "
+                        "gradient all-reduce + AdamW + 2 EMAs every 4th step",
+            "micro_batch_per_gpu": MICRO_BATCH, "clip_frames": CLIP, "latent": [8, 32, 32], "accumulation": 4,
+            "parallelism": parallelism, "launch": launch,
+            "l2": "no explicit flush: each step streams >2 GB of weights/operands/activations (>> 126 MB L2)"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -148,8 +157,7 @@ def run_reference(args):
         "impl": "reference", "metric": "train frames/s", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "cs_train.py Counter-Strike UNet (310M), DART 32-frame sequence, fwd+bwd micro-step on CPU",
-                   "micro_batch": batch, "clip_frames": CLIP, "latent": [8, 32, 32]},
+        "config": workload_config("cpu", "oracle port on the host cores; each step = a bounded sample, see cpu_baseline.sample"),
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
                          "sample": f"1 of the {MICRO_BATCH} sequences of a micro-batch per step (fwd+bwd, no optimizer), "
                                    f"oracle/oniris_oracle.py fp32 on {os.cpu_count()} threads"},
@@ -231,9 +239,13 @@ def run_ours(args):
     # park the stream (~0.6 s of spinning) so the host enqueues the whole cycle ahead of the GPU: the event pairs then
     # bracket back-to-back kernel executions, not host launch gaps
     torch.cuda._sleep(int(1.2e9))
+    cyc0, cyc1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    cyc0.record()
     for i in range(4):
         tr.micro_step(resident[i % n_host])
+    cyc1.record()
     torch.cuda.synchronize()
+    serial_cycle_ms = cyc0.elapsed_time(cyc1)      # 4 micro-steps + optimizer, one stream, no host gaps
     _lib.set_profiler(None)
     WeightGradBranch.enabled = True
     launches_per_step = prof.launches / 4
@@ -262,11 +274,7 @@ def run_ours(args):
         "metric": "train frames/s", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "cs_train.py Counter-Strike UNet (310M params), DART 32-frame sequence, fwd+bwd micro-step; "
-                               "gradient all-reduce + AdamW + 2 EMAs every 4th step",
-                   "micro_batch_per_gpu": MICRO_BATCH, "clip_frames": CLIP, "latent": [8, 32, 32], "accumulation": 4,
-                   "parallelism": f"dp{world}", "launch": "cuda-graph replay per micro-step" if use_graph else "eager",
-                   "l2": "no explicit flush: each step streams >2 GB of weights/operands/activations (>> 126 MB L2)"},
+        "config": workload_config(f"dp{world}", "cuda-graph replay per micro-step" if use_graph else "eager"),
         "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": MICRO_BATCH * CLIP * 8 * 32 * 32 * 4,
                 "d2h_bytes_per_step": 4},
         "gpu_launches": int(launches_per_step * args.steps),
@@ -274,7 +282,9 @@ def run_ours(args):
         "roofline": {"bound": "tensor", "kernel": "tapconv_kernel (gated 3D causal conv fwd + dgrad, tcgen05)",
                      "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                      "peak_kind": f"{peak_kind} bf16_tflops_sustained", "launches": conv_launches,
-                     "share_of_step": (conv_ms / 4) / ms, "traffic": tapconv_traffic(),
+                     "share_of_step": conv_ms / serial_cycle_ms,
+                     "share_basis": "tap-GEMM launch time / single-stream (serialised) time of the same eager cycle -- the basis of the ncu launch list in profiles/, where tapconv + its finish kernels and memsets are ~40 % of the serialised step",
+                     "traffic": tapconv_traffic(),
                      "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum per tapconv launch, mean over the 187 launches of one step, from the committed ncu pass profiles/r01_launches_step.csv",
                      "how": "CUDA events around each tap-GEMM launch over one eager 4-step cycle on the launching stream, enqueued ahead of a parked GPU so the intervals hold no host gaps; the weight-gradient stream is kept in line for this cycle so each kernel is timed alone"},
     }
