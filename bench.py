@@ -236,9 +236,9 @@ def run_ours(args):
     from autoregressive_diffusion_b200.ops import WeightGradBranch
     WeightGradBranch.enabled = False    # this cycle times each kernel alone: keep the weight-gradient branch in line
     torch.cuda.synchronize()
-    # park the stream (~0.6 s of spinning) so the host enqueues the whole cycle ahead of the GPU: the event pairs then
+    # park the stream (~1.5 s of spinning) so the host enqueues the whole cycle ahead of the GPU: the event pairs then
     # bracket back-to-back kernel executions, not host launch gaps
-    torch.cuda._sleep(int(1.2e9))
+    torch.cuda._sleep(int(3.0e9))
     cyc0, cyc1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     cyc0.record()
     for i in range(4):
