@@ -13,9 +13,12 @@
 // * Horizontal / temporal shifts and all zero padding are TMA box coordinates + out-of-bounds zero fill.
 //   No im2col buffer exists.  Channel chunks of 64/32/16 use the 128/64/32-byte hardware swizzle.
 // * Two independent smem rings: big activation tiles (A ring) and weight tiles (B ring, one per tap).
-// * tcgen05.mma (cta_group::1, M=128, N=BN, K=16) accumulates in TMEM; up to 3 accumulators per tile (clean
-//   rows, noised rows, shared causal-context term) so the context term of the DART training sequence is computed
-//   once for both halves (edm2/conv.py:90-91 duplicates it) and each current-frame weight tile feeds two MMAs.
+// * tcgen05.mma (M=128 per CTA, N=BN, K=16; cta_group::2 with M=256 across a CTA pair for the wide layers, see the
+//   kernel's comment) accumulates in TMEM; up to 3 accumulators per tile (clean rows, noised rows, shared
+//   causal-context term) so the context term of the DART training sequence is computed once for both halves
+//   (edm2/conv.py:90-91 duplicates it) and each current-frame weight tile feeds two MMAs.
+// * Persistent: a CTA (pair) walks several tiles; TMEM is double-buffered / rotated so loads and MMAs of the next tile
+//   overlap the epilogue of the previous one.  Small layers slice K over blockIdx.y instead (split-K + finish kernel).
 // * Warp roles: warp0 = activation TMA, warp1 = TMEM owner + MMA issuer, warp2 = weight TMA, warps 3..6 = epilogue
 //   (TMEM -> registers -> gated combine -> global).  Producer/MMA loops are warp-uniform with one elected lane
 //   issuing, which keeps descriptors in uniform registers (4 UTCHMMA back to back instead of an ELECT loop each).
@@ -74,7 +77,7 @@ struct TapConvParams {
   void* out_d;  // optional (EPI_GATED): shared - own accumulator, fp32, same shape as out
   int ksplit;   // >1: blockIdx.y owns a slice of the channel chunks; raw accumulators are reduced into split_ws
   long long* trace;   // optional [grid.x*grid.y][8] globaltimer stamps (probe builds only; nullptr in production)
-  float* split_ws;  // [n_acc][n_seq*n_out*T*H*W][Cout] fp32, zeroed by the host (shared acc uses rows of set 0)
+  float* split_ws;  // [n_acc][n_seq*T*H*W][Cout] fp32 (own sets first, then the shared accumulator), zeroed by tapconv_launch
 };
 
 template <int CHUNK>
