@@ -122,6 +122,9 @@ int main(int argc, char** argv) {
   fails += !run(plain("wgrad 3x3 c128 n128 8x8 F6 (two-tap, odd count)", 6, 8, 8, 128, 128, 3, 2), true, 0);
   { Problem q = plain("wgrad 1x1 c512 n512 4x4 F8 (pair)", 8, 4, 4, 512, 512, 1, 1); q.flat = 2; fails += !run(q, true, 0); }
   { Problem q = plain("wgrad 3x3 c384 n256 8x8 F3 (pair, ragged ci tile)", 3, 8, 8, 384, 256, 3, 1); q.flat = 2; fails += !run(q, true, 0); }
+  { Problem q = gated("wgrad gated c256 n256 8x8 B1 n4 (halo)", 1, 4, 8, 8, 256, 256, 2); q.flat = 3; fails += !run(q, true, 0); }
+  { Problem q = plain("wgrad 3x3 c256 n128 4x4 F9 (halo)", 9, 4, 4, 256, 128, 3, 1); q.flat = 3; fails += !run(q, true, 0); }
+  { Problem q = plain("wgrad 3x3 c384 n256 16x16 F3 (halo, ragged ci tile)", 3, 16, 16, 384, 256, 3, 1); q.flat = 3; fails += !run(q, true, 0); }
   printf("== wgrad correctness: %d failing ==\n", fails);
   if (perf) {
     run(gated("CS 512->512 16x16 B2 n16", 2, 16, 16, 16, 512, 512, 0), false, 20);
@@ -136,6 +139,8 @@ int main(int argc, char** argv) {
     { Problem q = gated("CS 512->512 8x8 FLAT", 2, 16, 8, 8, 512, 512, 0); q.flat = 1; run(q, false, 20); }
     { Problem q = gated("CS 512->512 4x4 FLAT", 2, 16, 4, 4, 512, 512, 0); q.flat = 1; run(q, false, 20); }
     { Problem q = gated("CS 512->512 16x16 PAIR", 2, 16, 16, 16, 512, 512, 0); q.flat = 2; run(q, false, 20); }
+    { Problem q = gated("CS 512->512 16x16 HALO", 2, 16, 16, 16, 512, 512, 0); q.flat = 3; run(q, false, 20); }
+    { Problem q = gated("CS 1024->512 8x8 HALO", 2, 16, 8, 8, 1024, 512, 0); q.flat = 3; run(q, false, 20); }
     run(gated("CS 256->128 32x32 B2 n16", 2, 16, 32, 32, 256, 128, 0), false, 20);
     for (int sp : {2, 3, 4, 6, 8}) run(gated("CS 256->256 16x16 splitN", 2, 16, 16, 16, 256, 256, sp), false, 20);
     for (int sp : {6, 11, 16, 22}) run(gated("CS 128->128 32x32 splitN", 2, 16, 32, 32, 128, 128, sp), false, 20);

@@ -61,7 +61,7 @@ struct WgradLaunch {
   int n_items = 0;
   int H = 0, W = 0, Cin = 0, Cout = 0, w_taps = 0;
   int n_split = 1;
-  int force_mode = 0;    // probe only: 1 = one tap per CTA and no pairs, 2 = CTA pairs where the shape allows
+  int force_mode = 0;    // probe only: 1 = one tap per CTA and no pairs, 2 = CTA pairs, 3 = halo groups, where the shape allows
   float* out = nullptr;  // [n_split, Cout, w_taps, Cin]
 };
 

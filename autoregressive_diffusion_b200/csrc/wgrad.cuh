@@ -230,4 +230,163 @@ __global__ void __launch_bounds__(WGRAD_THREADS, 1) wgrad_kernel(const __grid_co
   }
 }
 
+// ============================================================================ halo variant
+// Wide layers (256-channel input tiles, 64-channel chunks) sit on the L2->SM operand bandwidth at 87 FLOP per byte
+// (ncu: 1.8 GB moved for 155 GFLOP, 13.7 TB/s).  Here a CTA takes the TWO vertical taps (dy0, dy0+1) of one (dt, dx)
+// column: the pixel tile is ordered (row, frame, column) and the activation boxes carry ONE extra image row, so the two
+// taps are the same shared-memory boxes read through UMMA descriptors that differ by a whole number of 8-row groups,
+// and the gradient tile is shared as well: 56 KB per 8.4 MFLOP (150 FLOP/B) instead of 48 KB per 4.2 MFLOP.  The third
+// tap of a column (dy = +1) is a single-tap group of the same kernel (plain boxes, one accumulator).
+struct WgradHaloParams {
+  CUtensorMap mapG[2];    // (C, W, T, H, SEQ), box (64, bw, bt, bh, 1)
+  CUtensorMap mapA[2];    // same box
+  CUtensorMap mapAh[2];   // box (64, bw, bt, bh + 1, 1)
+  WgradGroup groups[WGRAD_MAX_ITEMS];   // dt/dy/dx[0] = first tap; pad_ = number of taps (1 or 2); wtap[j]
+  int n_groups;
+  int n_seq[2];
+  int tiles_t[2];
+  int tiles_w, tiles_h;
+  int bw, bh, bt;
+  int Cin, Cout, w_taps;
+  int ci_tiles, co_tiles;
+  int n_split;
+  int a_box_bytes;    // (bh + 1) * bt * bw * 128: one 64-channel halo box (also the box stride of single-tap groups)
+  int shift_bytes;    // bt * bw * 128: where the second tap's first pixel row sits inside a halo box
+  int stages, stage_bytes;
+  float* out;         // [n_split, Cout, w_taps, Cin] fp32
+};
+
+constexpr int WGH_BN = 256;
+constexpr int WGH_MAX_STAGES = 4;
+
+static __global__ void __launch_bounds__(WGRAD_THREADS, 1) wgrad_halo_kernel(const __grid_constant__ WgradHaloParams p) {
+  constexpr int ROW_BYTES = 128, BOX_BYTES = WGRAD_KT * ROW_BYTES, G_BYTES = 2 * BOX_BYTES, A_BOXES = WGH_BN / 64;
+  constexpr uint32_t SBO = 8 * ROW_BYTES;
+  pdl_launch_dependents();
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int stages = p.stages;
+  const uint32_t bar_base = smem_base + stages * p.stage_bytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (WGH_MAX_STAGES + s); };
+  const uint32_t tmem_full_bar = bar_base + 8u * (2 * WGH_MAX_STAGES);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * WGH_MAX_STAGES + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const WgradGroup grp = p.groups[blockIdx.y];
+  const int pr = grp.pair;
+  const int n_taps = grp.pad_;
+  const int co_tile = blockIdx.x % p.co_tiles;
+  const int ci_tile = blockIdx.x / p.co_tiles;
+  const int co0 = co_tile * 128, ci0 = ci_tile * WGH_BN;
+  const int k_tiles = p.n_seq[pr] * p.tiles_t[pr] * p.tiles_h * p.tiles_w;
+  const int k_begin = static_cast<int>(static_cast<long>(k_tiles) * blockIdx.z / p.n_split);
+  const int k_end = static_cast<int>(static_cast<long>(k_tiles) * (blockIdx.z + 1) / p.n_split);
+  constexpr uint32_t tmem_cols = 2 * WGH_BN;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&p.mapG[pr]);
+    tma_prefetch_desc(n_taps == 2 ? &p.mapAh[pr] : &p.mapA[pr]);
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, tmem_cols); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  pdl_wait();
+
+  if (warp == 0) {
+    int stage = 0;
+    uint32_t phase = 0;
+    const void* mapA = n_taps == 2 ? static_cast<const void*>(&p.mapAh[pr]) : static_cast<const void*>(&p.mapA[pr]);
+    const uint32_t tx = G_BYTES + A_BOXES * (n_taps == 2 ? p.a_box_bytes : BOX_BYTES);
+    for (int kt = k_begin; kt < k_end; ++kt) {
+      int r = kt;
+      const int tw_i = r % p.tiles_w; r /= p.tiles_w;
+      const int th_i = r % p.tiles_h; r /= p.tiles_h;
+      const int tt_i = r % p.tiles_t[pr];
+      const int seq = r / p.tiles_t[pr];
+      const int w0 = tw_i * p.bw, h0 = th_i * p.bh, t0 = tt_i * p.bt;
+      mbar_wait(empty_bar(stage), phase ^ 1);
+      if (elect_one()) {
+        const uint32_t sG = smem_base + stage * p.stage_bytes;
+        const uint32_t sA = sG + G_BYTES;
+        mbar_arrive_expect_tx(full_bar(stage), tx);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) tma_load_5d(sG + j * BOX_BYTES, &p.mapG[pr], full_bar(stage), co0 + j * 64, w0, t0, h0, seq);
+#pragma unroll
+        for (int j = 0; j < A_BOXES; ++j)
+          tma_load_5d(sA + j * p.a_box_bytes, mapA, full_bar(stage), ci0 + j * 64, w0 + grp.dx[0], t0 + grp.dt[0],
+                      h0 + grp.dy[0], seq);
+      }
+      __syncwarp();
+      if (++stage == stages) { stage = 0; phase ^= 1; }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = make_idesc_bf16(128, WGH_BN, 1, 1);
+    const uint64_t adesc0 = make_smem_desc(0, BOX_BYTES, SBO, SWZ_128B);
+    const uint64_t bdesc0 = make_smem_desc(0, p.a_box_bytes, SBO, SWZ_128B);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int kt = k_begin; kt < k_end; ++kt) {
+      mbar_wait(full_bar(stage), phase);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t sG = smem_base + stage * p.stage_bytes;
+        const uint64_t adesc = adesc0 + (sG >> 4);
+        const uint32_t acc = kt > k_begin ? 1u : 0u;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          if (j < n_taps) {
+            const uint64_t bdesc = bdesc0 + ((sG + G_BYTES + j * p.shift_bytes) >> 4);
+            umma_bf16_ss(tmem_base + j * WGH_BN, adesc, bdesc, idesc, acc);
+#pragma unroll
+            for (int k = 1; k < WGRAD_KT / 16; ++k)
+              umma_bf16_ss(tmem_base + j * WGH_BN, adesc + k * ((2 * SBO) >> 4), bdesc + k * ((2 * SBO) >> 4), idesc, 1u);
+          }
+        }
+        umma_commit(empty_bar(stage));
+      }
+      __syncwarp();
+      if (++stage == stages) { stage = 0; phase ^= 1; }
+    }
+    if (elect_one()) umma_commit(tmem_full_bar);
+    __syncwarp();
+  } else {
+    const int q = warp & 3;
+    const int co = co0 + q * 32 + lane;
+    mbar_wait_sleep(tmem_full_bar, 0);
+    tc_fence_after();
+    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const bool have = k_end > k_begin;
+    for (int j = 0; j < n_taps; ++j) {
+      float* dst_row = p.out + ((static_cast<long>(blockIdx.z) * p.Cout + co) * p.w_taps + grp.wtap[j]) * p.Cin;
+      for (int c = 0; c < WGH_BN / 32; ++c) {
+        float v[32];
+        tmem_ld32(lane_base + j * WGH_BN + c * 32, v);
+        tmem_ld_wait();
+        if (co < p.Cout) {
+          const int col0 = ci0 + c * 32;
+#pragma unroll
+          for (int u = 0; u < 32; u += 4)
+            if (col0 + u + 4 <= p.Cin)
+              *reinterpret_cast<float4*>(dst_row + col0 + u) =
+                  have ? make_float4(v[u], v[u + 1], v[u + 2], v[u + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
 }  // namespace ob
