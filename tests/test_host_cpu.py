@@ -156,3 +156,20 @@ def test_conv_weights_are_tap_major_and_checkpoint_compatible(tmp_path):
     view.copy_(w3)
     assert view.stride() == w3.stride() and torch.equal(view, w3)
     assert torch.equal(flat[64:], w3.detach().permute(0, 2, 3, 4, 1).reshape(-1))    # physically [Co][kt][kh][kw][Ci]
+
+
+def test_tiling_policy_queries_run_without_a_gpu():
+    """The planning entry points are pure host code: split-K only for long K loops on small grids, and the
+    weight-gradient K split lands on one wave of CTAs (measured policy)."""
+    from autoregressive_diffusion_b200 import _lib
+    q = lambda *a: _lib.query("ob_conv_split_ws_bytes", *a)
+    # (n_seq, S, T, H, W, cin, cout, ksize, gated)
+    assert q(2, 2, 16, 4, 4, 512, 512, 3, 1) == 3 * 2 * 16 * 16 * 512 * 4          # 4x4 level: split, 3 accumulators
+    assert q(2, 2, 16, 8, 8, 512, 512, 3, 1) > 0
+    assert q(2, 2, 16, 32, 32, 128, 128, 3, 1) == 0                                 # enough tiles: no split
+    assert q(1, 1, 64, 4, 4, 512, 512, 1, 0) == 0                                   # 1x1: K loop too short to split
+    s = lambda *a: _lib.query("ob_conv_wgrad_splits", *a)
+    assert s(2, 2, 16, 16, 16, 512, 512, 3, 1) == 1                                 # 216 CTAs already
+    assert s(2, 2, 16, 16, 16, 256, 256, 3, 1) == 3                                 # 54 CTAs -> 162
+    assert s(2, 2, 16, 32, 32, 128, 128, 3, 1) == 11                                # two-tap groups: 14 CTAs -> 154
+    assert s(1, 1, 64, 4, 4, 512, 512, 1, 0) >= 1
