@@ -174,6 +174,15 @@ class WeightGradBranch:
             cls.join(device)
 
     @classmethod
+    def recover(cls, device):
+        """Call between steps: if a backward pass died half-way (its end-of-backward callback never ran), finish what it
+        left behind -- wait for the branch, drop the kept tensors, switch PDL back on -- so the next step starts clean."""
+        if cls._join_queued or cls._pending:
+            cls._join_queued = False
+            query("ob_set_pdl", 1)
+            cls.join(device)
+
+    @classmethod
     def join(cls, device):
         """Make the current stream wait for the branch (runs automatically at the end of every backward pass unless
         defer_join is set)."""

@@ -221,6 +221,9 @@ class Trainer:
         self.graphs = None
 
     def _forward_backward(self, latents, conditioning=None):
+        if self.device.type == "cuda":
+            from .ops import WeightGradBranch
+            WeightGradBranch.recover(self.device)      # no-op unless an earlier backward pass was interrupted
         self.micro += 1
         just_2d = bool(self.just_2d_every) and (self.micro % self.just_2d_every == 0)
         loss, unweighted = self.loss_fn(self.precond, latents, conditioning, just_2d=just_2d)
