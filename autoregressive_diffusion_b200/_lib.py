@@ -54,7 +54,8 @@ _SIGS = {
     "ob_mp_cat_bwd": "pppliifp",
     "ob_resample2x": "ppliiiifp",
     "ob_set_pdl": "i",
-    "ob_adamw_ema": "pppppplpfffffffp",
+    "ob_adamw_ema": "pppppplpfffffffffp",
+    "ob_sumsq": "plpp",
     "ob_qkv_prep_fwd": "ppppppppppliifp",
     "ob_qkv_prep_bwd": "ppppppppppliifp",
     "ob_rope_k": "ppppppliip",

@@ -45,14 +45,17 @@ class _OperandCache:
     """bf16 GEMM operand of one or two NormalizedWeights, rebuilt only when a parameter or the mode changes.
 
     The reference re-normalises every weight on every forward, eval included (edm2/conv.py:14-21); the values
-    only change when an optimizer step (or a load) touches the parameter, which bumps its autograd version.
+    only change when something writes the parameter.  Writers that go through torch (torch.optim, copy_,
+    load_state_dict) bump the tensor's autograd version; writers that go through a raw pointer (the fused optimizer
+    kernel, ob_adamw_ema) do not, so they bump `ops.param_generation` instead -- both are part of the key.
     """
 
     def __init__(self):
         self.key, self.wg = None, None
 
     def get(self, params, taps, cin, cin_pad, gains, training):
-        key = tuple((p.data_ptr(), p._version) for p in params) + (bool(training), tuple(float(g) for g in gains))
+        key = tuple((p.data_ptr(), p._version) for p in params) + (bool(training), tuple(float(g) for g in gains),
+                                                                   ops.param_generation())
         if key != self.key:
             with torch.no_grad():
                 self.wg = ops.weight_operand([p.data for p in params], taps, cin, cin_pad, gains, training)

@@ -241,12 +241,13 @@ int ob_set_pdl(int enabled) {
   if (!forced_off) pdl_flag().store(enabled < 0 ? 0 : enabled > 2 ? 2 : enabled, std::memory_order_relaxed);
   return prev;
 }
-int ob_adamw_ema(float* p, float* g, float* m, float* v, float* ema1, float* ema2, int64_t n, const float* step_lr,
-                 float beta1, float beta2, float eps, float weight_decay, float ema_beta1, float ema_beta2, float grad_scale,
-                 void* stream) {
-  return adamw_ema(p, g, m, v, ema1, ema2, (long)n, step_lr, beta1, beta2, eps, weight_decay, ema_beta1, ema_beta2,
-                   grad_scale, (cudaStream_t)stream);
+int ob_adamw_ema(float* p, float* g, float* m, float* v, float* ema1, float* ema2, int64_t n, const float* opt_state,
+                 float beta1, float beta2, float eps, float weight_decay, float ema_a1, float ema_a2, float ema_ratio,
+                 float grad_scale, float max_grad_norm, void* stream) {
+  return adamw_ema(p, g, m, v, ema1, ema2, (long)n, opt_state, beta1, beta2, eps, weight_decay, ema_a1, ema_a2, ema_ratio,
+                   grad_scale, max_grad_norm, (cudaStream_t)stream);
 }
+int ob_sumsq(const float* g, int64_t n, float* out, void* stream) { return sumsq(g, (long)n, out, (cudaStream_t)stream); }
 
 int ob_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int b, int heads, int lq, int lk, int hw,
                 int n_frames, int mask, float scale, void* stream) {

@@ -34,8 +34,10 @@ int mp_sum_fwd(const void* a, const void* b, void* out, long n, float t, float c
 int mp_sum_bwd(const void* g, const void* out, void* da, void* db, long n, float t, float clip, cudaStream_t st);
 int mp_cat(void* a, void* b, void* cat, long rows, int ca, int cb, float t, int backward, cudaStream_t st);
 int resample2x(const void* in, void* out, long frames, int h, int w, int c, int pool, float scale, cudaStream_t st);
-int adamw_ema(float* p, float* g, float* m, float* v, float* e1, float* e2, long n, const float* step_lr, float beta1,
-              float beta2, float eps, float wd, float ema1, float ema2, float grad_scale, cudaStream_t st);
+int adamw_ema(float* p, float* g, float* m, float* v, float* e1, float* e2, long n, const float* opt_state, float beta1,
+              float beta2, float eps, float wd, float ema_a1, float ema_a2, float ema_ratio, float grad_scale, float max_norm,
+              cudaStream_t st);
+int sumsq(const float* g, long n, float* out, cudaStream_t st);
 int qkv_prep_fwd(const void* qkv, void* q, void* k, void* v, void* k_raw, const float* cosT, const float* sinT,
                  const float* sclT, const int* pos_q, const int* pos_k, long rows, int heads, int hw, float eps,
                  cudaStream_t st);

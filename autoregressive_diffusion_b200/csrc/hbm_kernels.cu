@@ -1037,17 +1037,31 @@ int resample2x(const void* in, void* out, long frames, int h, int w, int c, int 
 // AdamW (decoupled weight decay, bias-corrected; the update torch.optim.AdamW applies in cs_train.py:121-124) fused with
 // the two power-function-free EMA copies of the weights (cs_train.py:125) and the gradient reset, over ONE flat fp32
 // range: 6 streams read, 6 written, once per optimizer step.  step_lr points at {step (already incremented), lr}.
+// EMA coefficient of one tracked copy.  ratio > 0: power-function EMA (edm2/phema.py:68-70, beta = (1 - t_delta/t_next)^(exp+1))
+// with a = exp + 1 and t_delta/t_next = ratio / t (t = optimizer step count); ratio <= 0: constant beta = a.
+__device__ __forceinline__ float ema_beta(float a, float ratio, float step) {
+  if (ratio <= 0.f) return a;
+  const float r = fminf(ratio / step, 1.f);
+  return r >= 1.f ? 0.f : __expf(a * log1pf(-r));
+}
+
 __global__ void __launch_bounds__(256) adamw_ema_kernel(float4* __restrict__ p, float4* __restrict__ g, float4* __restrict__ m,
                                                         float4* __restrict__ v, float4* __restrict__ e1, float4* __restrict__ e2,
-                                                        long n4, const float* __restrict__ step_lr, float beta1, float beta2,
-                                                        float eps, float wd, float ema1, float ema2, float grad_scale) {
+                                                        long n4, const float* __restrict__ opt_state, float beta1, float beta2,
+                                                        float eps, float wd, float ema_a1, float ema_a2, float ema_ratio,
+                                                        float grad_scale, float max_norm) {
   pdl_launch_dependents();
   pdl_wait();
-  const float step = step_lr[0], lr = step_lr[1];
+  const float step = opt_state[0], lr = opt_state[1];
+  if (max_norm > 0.f) {   // torch.nn.utils.clip_grad_norm_ (gym_train.py:105): coefficient from the squared norm in opt_state[2]
+    const float total = sqrtf(opt_state[2]) * grad_scale;
+    grad_scale *= fminf(1.f, max_norm / (total + 1e-6f));
+  }
   const float bc1 = 1.f - powf(beta1, step);
   const float bc2_sqrt = sqrtf(1.f - powf(beta2, step));
   const float step_size = lr / bc1;
   const float decay = 1.f - lr * wd;
+  const float w1 = 1.f - ema_beta(ema_a1, ema_ratio, step), w2 = 1.f - ema_beta(ema_a2, ema_ratio, step);
   const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
   for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += static_cast<long>(gridDim.x) * blockDim.x) {
     float4 pv = p[i], mv = m[i], vv = v[i];
@@ -1066,20 +1080,21 @@ __global__ void __launch_bounds__(256) adamw_ema_kernel(float4* __restrict__ p, 
     if (e1 != nullptr) {
       float4 e = e1[i]; float* ee = &e.x;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) ee[k] += (1.f - ema1) * (pp[k] - ee[k]);
+      for (int k = 0; k < 4; ++k) ee[k] += w1 * (pp[k] - ee[k]);
       e1[i] = e;
     }
     if (e2 != nullptr) {
       float4 e = e2[i]; float* ee = &e.x;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) ee[k] += (1.f - ema2) * (pp[k] - ee[k]);
+      for (int k = 0; k < 4; ++k) ee[k] += w2 * (pp[k] - ee[k]);
       e2[i] = e;
     }
   }
 }
 
-int adamw_ema(float* p, float* g, float* m, float* v, float* e1, float* e2, long n, const float* step_lr, float beta1,
-              float beta2, float eps, float wd, float ema1, float ema2, float grad_scale, cudaStream_t st) {
+int adamw_ema(float* p, float* g, float* m, float* v, float* e1, float* e2, long n, const float* opt_state, float beta1,
+              float beta2, float eps, float wd, float ema_a1, float ema_a2, float ema_ratio, float grad_scale, float max_norm,
+              cudaStream_t st) {
   if (n % 4 != 0) { set_error("adamw_ema: element count %ld must be a multiple of 4", n); return OB_ERR_INVALID; }
   for (const void* q : {(const void*)p, (const void*)g, (const void*)m, (const void*)v, (const void*)e1, (const void*)e2})
     if (reinterpret_cast<uintptr_t>(q) % 16 != 0) { set_error("adamw_ema: buffers must be 16-byte aligned"); return OB_ERR_INVALID; }
@@ -1090,8 +1105,41 @@ int adamw_ema(float* p, float* g, float* m, float* v, float* e1, float* e2, long
   launch(adamw_ema_kernel, static_cast<unsigned>(blocks), 256, 0, st, 1, reinterpret_cast<float4*>(p), reinterpret_cast<float4*>(g),
                                                                  reinterpret_cast<float4*>(m), reinterpret_cast<float4*>(v),
                                                                  reinterpret_cast<float4*>(e1), reinterpret_cast<float4*>(e2), n4,
-                                                                 step_lr, beta1, beta2, eps, wd, ema1, ema2, grad_scale);
+                                                                 opt_state, beta1, beta2, eps, wd, ema_a1, ema_a2, ema_ratio,
+                                                                 grad_scale, max_norm);
   return check_launch("adamw_ema");
+}
+
+// out[0] += sum of g[i]^2 (fp32): the squared gradient norm clip_grad_norm_ needs (gym_train.py:105).
+__global__ void __launch_bounds__(256) sumsq_kernel(const float4* __restrict__ g, long n4, float* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
+  float acc = 0.f;
+  for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const float4 v = g[i];
+    acc += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  __shared__ float part[8];
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += part[k];
+    atomicAdd(out, t);
+  }
+}
+
+int sumsq(const float* g, long n, float* out, cudaStream_t st) {
+  if (n % 4 != 0 || reinterpret_cast<uintptr_t>(g) % 16 != 0) { set_error("sumsq: n %% 4 and 16-byte alignment required"); return OB_ERR_INVALID; }
+  if (n <= 0) return OB_OK;
+  const long n4 = n / 4;
+  long blocks = (n4 + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  launch(sumsq_kernel, static_cast<unsigned>(blocks), 256, 0, st, 1, reinterpret_cast<const float4*>(g), n4, out);
+  return check_launch("sumsq");
 }
 
 }  // namespace ob

@@ -5,9 +5,11 @@ Constructor arguments, forward signatures, state_dict keys and the nested cache 
 checkpoint saved by either loads into the other.
 """
 import inspect
+import math
 from contextlib import nullcontext
 
 import torch
+import torch.distributed as dist
 from torch import nn
 
 from . import ops
@@ -216,34 +218,106 @@ class UNet(BetterModule):
 
 
 class FourierSeriesFit(nn.Module):
-    """Evaluation side of edm2/loss_weight.py:88-162 (the loss-vs-sigma curve; all-zero coefficients mean 1)."""
+    """Loss-vs-sigma curve as a truncated Fourier series in log10(sigma) (edm2/loss_weight.py:88-162); all-zero
+    coefficients evaluate to 1."""
 
-    def __init__(self, num_terms=4):
+    def __init__(self, interval_min=-math.pi, interval_max=math.pi, num_terms=8):
         super().__init__()
+        self.interval_min, self.interval_max = interval_min, interval_max
         self.num_terms = num_terms
-        self.coefficients = nn.Parameter(torch.zeros(2 * num_terms - 1, 1), requires_grad=False)
+        self.num_basis = 2 * num_terms - 1
+        self.coefficients = nn.Parameter(torch.zeros(self.num_basis, 1), requires_grad=False)
+        self.coefficients_history = []
 
-    def forward(self, x):
-        xl = torch.log10(x.reshape(-1))
+    def fourier_series(self, x):
+        xl = torch.log10(x)
         basis = [torch.ones_like(xl) * 0.5]
         for n in range(1, self.num_terms):
             basis += [torch.cos(n * xl), torch.sin(n * xl)]
-        return (10 ** (torch.stack(basis, dim=-1) @ self.coefficients.to(xl.device))).reshape(x.shape)
+        return torch.stack(basis, dim=-1)
+
+    @torch.no_grad()
+    def fit_data(self, X, Y):
+        """Least-squares fit on rank 0, coefficients broadcast to the other ranks (edm2/loss_weight.py:121-149)."""
+        dist_on = dist.is_available() and dist.is_initialized()
+        if not dist_on or dist.get_rank() == 0:
+            X, Y = X.detach().float().cpu(), Y.detach().float().cpu()
+            xl = torch.log10(X)
+            mask = (xl >= self.interval_min) & (xl <= self.interval_max)
+            basis = self.fourier_series(X[mask].flatten())
+            sol = torch.linalg.lstsq(basis, Y[mask].flatten().log10().unsqueeze(1)).solution
+            self.coefficients.data.copy_(sol)
+            self.coefficients_history.append(sol.detach().clone())
+        if dist_on:
+            dist.broadcast(self.coefficients.data, src=0)
+
+    def forward(self, x):
+        basis = self.fourier_series(x.reshape(-1))
+        return (10 ** (basis @ self.coefficients.to(basis.device))).reshape(x.shape)
 
 
 class MultiNoiseLoss(nn.Module):
-    """State-dict-compatible holder of the fitted loss curve (edm2/loss_weight.py:9-48); fitting is out of scope."""
+    """(sigma, loss, position) history and the fitted mean-loss curve the training loss is divided by
+    (edm2/loss_weight.py:9-48).  The reference copies every micro-batch's values to the host (a sync per step); here the
+    last `history_size` samples live in a device-side ring buffer written with index ops only, so add_data is safe inside
+    a captured CUDA graph, and the host sees them when fit_loss_curve (every 500*accum steps, cs_train.py:130-131) asks."""
 
-    def __init__(self):
+    def __init__(self, history_size=10000):
         super().__init__()
-        self.fourier_approximator = FourierSeriesFit(num_terms=4)
+        self.history_size = history_size
+        self.fourier_approximator = FourierSeriesFit(-math.pi, math.pi, num_terms=4)
+        self._ring = None
 
+    def _alloc(self, device):
+        self._ring = torch.zeros(3, self.history_size, dtype=torch.float32, device=device)
+        self._count = torch.zeros((), dtype=torch.int64, device=device)
+        self._iota = torch.arange(self.history_size, dtype=torch.int64, device=device)
+
+    @torch.no_grad()
     def add_data(self, sigmas, losses):
-        return None
+        if dist.is_available() and dist.is_initialized() and dist.get_rank() != 0:
+            return
+        if self._ring is None or self._ring.device != sigmas.device:
+            self._alloc(sigmas.device)
+        n = min(sigmas.numel(), self.history_size)
+        idx = (self._count + self._iota[:n]) % self.history_size
+        self._ring[0].index_copy_(0, idx, sigmas.detach().reshape(-1)[-n:].float())
+        self._ring[1].index_copy_(0, idx, losses.detach().reshape(-1)[-n:].float())
+        self._ring[2].index_copy_(0, idx, (self._iota[:n] % sigmas.shape[1]).float())
+        self._count += n
+
+    def _history(self, row):
+        if self._ring is None:
+            return torch.tensor([], dtype=torch.float32)
+        count = int(self._count)
+        ring = self._ring[row].cpu()
+        if count <= self.history_size:
+            return ring[:count]
+        start = count % self.history_size
+        return torch.cat((ring[start:], ring[:start]))
+
+    @property
+    def sigmas(self):
+        return self._history(0)
+
+    @property
+    def losses(self):
+        return self._history(1)
+
+    @property
+    def positions(self):
+        return self._history(2).to(torch.int64)
 
     @torch.no_grad()
     def calculate_mean_loss(self, sigma):
         return self.fourier_approximator(sigma)
+
+    def fit_loss_curve(self, sigmas=None, losses=None):
+        if sigmas is None:
+            sigmas = self.sigmas
+        if losses is None:
+            losses = self.losses
+        self.fourier_approximator.fit_data(sigmas, losses)
 
 
 class Precond(BetterModule):

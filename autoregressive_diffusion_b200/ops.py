@@ -40,6 +40,20 @@ def _require_cuda(x):
 
 # ----------------------------------------------------------------------------- weights
 
+_PARAM_GENERATION = [0]
+
+
+def param_generation():
+    """Counter of raw-pointer parameter updates (see bump_param_generation)."""
+    return _PARAM_GENERATION[0]
+
+
+def bump_param_generation():
+    """Call after parameters were changed through a raw device pointer (FusedAdamWEMA): autograd's version counters
+    did not move, so every cached bf16 GEMM operand is stale and the next forward must re-run ob_wnorm_fwd (which
+    is also what re-applies the reference's forced weight normalisation, edm2/conv.py:16-18)."""
+    _PARAM_GENERATION[0] += 1
+
 
 def ceil_to(v, m):
     return (v + m - 1) // m * m
@@ -89,23 +103,48 @@ def grad_buffer(p):
     return p.grad
 
 
-def weight_grad(params, taps, cin, cin_pad, gains, dwg, n_split, eps=1e-4):
+_WEIGHT_GRAD_MODE = ["autograd"]
+
+
+def set_weight_grad_mode(mode):
+    """How the backward kernels deliver parameter gradients.  Returns the previous mode.
+
+    "autograd" (default): gradients are returned through autograd like any torch op, so stock torch.optim,
+        torch.autograd.grad and DistributedDataParallel's reducer hooks (cs_train.py:54) see them.
+    "direct": the kernels accumulate straight into param.grad on the weight-gradient stream and autograd sees None --
+        no per-parameter add kernels during gradient accumulation, and the branch overlaps the input-gradient chain.
+        train.Trainer selects this (it owns the gradient buffers and does the all-reduce itself); a DDP reducer would
+        never fire in this mode.
+    """
+    assert mode in ("autograd", "direct")
+    prev = _WEIGHT_GRAD_MODE[0]
+    _WEIGHT_GRAD_MODE[0] = mode
+    return prev
+
+
+def weight_grad_mode():
+    return _WEIGHT_GRAD_MODE[0]
+
+
+def weight_grad(params, taps, cin, cin_pad, gains, dwg, n_split, eps=1e-4, targets=None):
     """ob_wnorm_bwd for each parameter: split-K partials dwg [n_split, Cout, sum(taps), cin_pad] are reduced, pushed
-    through the weight-normalisation backward and ACCUMULATED into p.grad in the same pass (so gradient accumulation
-    over micro-batches, cs_train.py:108-109, costs no extra add kernels).  Autograd therefore sees None for them."""
+    through the weight-normalisation backward and ACCUMULATED into `targets` (default: p.grad) in the same pass (so
+    gradient accumulation over micro-batches, cs_train.py:108-109, costs no extra add kernels)."""
     cout = params[0].shape[0]
     total = sum(taps)
+    if targets is None:
+        targets = [grad_buffer(p) if p.requires_grad else None for p in params]
     if dwg.shape[1] != cout:      # Cout was padded to a multiple of 8: fold the splits and drop the pad rows
         dwg = dwg.sum(0, keepdim=True)[:, :cout].contiguous()
         n_split = 1
-    if len(params) == 2 and list(taps) == [9, 18] and all(p.requires_grad for p in params) and all(float(g) == 1.0 for g in gains):
-        call("ob_wnorm_bwd_gated", _vp(params[0]), _vp(grad_buffer(params[0])), _vp(params[1]), _vp(grad_buffer(params[1])),
+    if len(params) == 2 and list(taps) == [9, 18] and all(t is not None for t in targets) and all(float(g) == 1.0 for g in gains):
+        call("ob_wnorm_bwd_gated", _vp(params[0]), _vp(targets[0]), _vp(params[1]), _vp(targets[1]),
              _vp(dwg), cout, cin, cin_pad, n_split, eps, 1, stream_ptr())
         return
     off = 0
-    for p, t, g in zip(params, taps, gains):
-        if p.requires_grad:
-            call("ob_wnorm_bwd", _vp(p), _vp(dwg), _vp(grad_buffer(p)), cout, cin, t, cin_pad, total, off, n_split, float(g),
+    for p, t, g, tgt in zip(params, taps, gains, targets):
+        if tgt is not None:
+            call("ob_wnorm_bwd", _vp(p), _vp(dwg), _vp(tgt), cout, cin, t, cin_pad, total, off, n_split, float(g),
                  eps, 1, stream_ptr())
         off += t
 
@@ -239,18 +278,25 @@ class PlainConvFn(torch.autograd.Function):
             ws = split_workspace(1, 1, f, h, wd, cout, cin_pad, k, 0, x.device)
             call("ob_conv_dgrad", _vp(gy), None, _vp(wg), None, None, _vp(dx), _vp(ws), 1, 1, f, h, wd, cin_pad, cout, k, 0,
                  stream_ptr())
-        if w.requires_grad:
+        dw = None
+        if ctx.needs_input_grad[1]:
             gain = ctx.gain
+            direct = weight_grad_mode() == "direct"
+            if not direct:
+                dw = torch.zeros_like(w, memory_format=torch.preserve_format)
 
             def branch():
                 ns = query("ob_conv_wgrad_splits", 1, 1, f, h, wd, cin_pad, cout, k, 0)
                 dwg = torch.empty((ns, cout, k * k, cin_pad), dtype=torch.float32, device=x.device)
                 call("ob_conv_wgrad", _vp(gy), _vp(x), None, None, _vp(dwg), 1, 1, f, h, wd, cin_pad, cout, k, 0, ns,
                      stream_ptr())
-                weight_grad([w], [k * k], cin, cin_pad, [gain], dwg, ns)
+                weight_grad([w], [k * k], cin, cin_pad, [gain], dwg, ns, targets=None if direct else [dw])
 
-            WeightGradBranch.run(x.device, (gy, x), branch)
-        return dx, None, None, None, None, None
+            if direct:
+                WeightGradBranch.run(x.device, (gy, x), branch)
+            else:
+                branch()
+        return dx, dw, None, None, None, None
 
 
 class GatedConvFn(torch.autograd.Function):
@@ -298,29 +344,46 @@ class GatedConvFn(torch.autograd.Function):
         gy = pad_channels(rows(gy), 8)
         gya = empty_rows(f, cout, h, wd, dev)
         gb = empty_rows(n_seq * T, cout, h, wd, dev)
+        direct = weight_grad_mode() == "direct"
         want_gate = g_offset.requires_grad
+        gate_params = (g_offset, g_mult, g_max, g_min)
+        if not want_gate:
+            gate_grads = (None,) * 4
+        elif direct:
+            gate_grads = tuple(grad_buffer(p) for p in gate_params)
+        else:
+            gate_grads = tuple(torch.zeros_like(p) for p in gate_params)
         call("ob_gate_bwd_fused", _vp(gy), _vp(y), _vp(d), _vp(alpha), _vp(beta), _vp(gya), _vp(gb), _vp(scratch), n_seq, S, T,
              h * wd * cout, _vp(g_offset) if want_gate else None, _vp(g_mult), _vp(g_max), _vp(g_min), _vp(c_noise),
-             _vp(grad_buffer(g_offset)) if want_gate else None, _vp(grad_buffer(g_mult)) if want_gate else None,
-             _vp(grad_buffer(g_max)) if want_gate else None, _vp(grad_buffer(g_min)) if want_gate else None, n_ctx,
-             stream_ptr())
+             _vp(gate_grads[0]), _vp(gate_grads[1]), _vp(gate_grads[2]), _vp(gate_grads[3]), n_ctx, stream_ptr())
+        dw2 = dw3 = None
         if w2.requires_grad or w3.requires_grad:   # forked first: it only needs the gate pre-pass
+            targets = None
+            if not direct:
+                dw2 = torch.zeros_like(w2, memory_format=torch.preserve_format) if w2.requires_grad else None
+                dw3 = torch.zeros_like(w3, memory_format=torch.preserve_format) if w3.requires_grad else None
+                targets = [dw2, dw3]
 
             def branch():
                 ns = query("ob_conv_wgrad_splits", n_seq, S, T, h, wd, cin_pad, cout, 3, 1)
                 dwg = torch.empty((ns, cout, 27, cin_pad), dtype=torch.float32, device=dev)
                 call("ob_conv_wgrad", _vp(gya), _vp(x), _vp(gb), _vp(cx), _vp(dwg), n_seq, S, T, h, wd, cin_pad, cout, 3, 1,
                      ns, stream_ptr())
-                weight_grad([w2, w3], [9, 18], cin, cin_pad, [1.0, 1.0], dwg, ns)
+                weight_grad([w2, w3], [9, 18], cin, cin_pad, [1.0, 1.0], dwg, ns, targets=targets)
 
-            WeightGradBranch.run(dev, (gya, gb, x, cx), branch)
+            if direct:
+                WeightGradBranch.run(dev, (gya, gb, x, cx), branch)
+            else:
+                branch()
         dx = None
         if ctx.needs_input_grad[0]:
             dx = empty_rows(f, cin_pad, h, wd, dev)
             ws = split_workspace(n_seq, S, T, h, wd, cout, cin_pad, 3, 1, dev)
             call("ob_conv_dgrad", _vp(gy), _vp(gb), _vp(wg), _vp(alpha), _vp(clean_rows_mask(n_seq, S, T, dev)), _vp(dx),
                  _vp(ws), n_seq, S, T, h, wd, cin_pad, cout, 3, 1, stream_ptr())
-        return (dx,) + (None,) * 14
+        if direct:
+            return (dx,) + (None,) * 14
+        return (dx, None, dw2, dw3, None) + gate_grads + (None,) * 6
 
 
 # ----------------------------------------------------------------------------- elementwise

@@ -2,7 +2,8 @@
 """Headline benchmark: data-parallel training of the Counter-Strike latent UNet (BASELINE.json configs[2]).
 
   python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a path (one process per GPU under torchrun)
-  python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm's CPU path (oracle port) on host cores
+  python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU path on the host cores (the unmodified
+                                                           # edm2 package staged under oracle/_ref; else the oracle port)
 
 A "step" is one micro-batch pass of the hot path: forward + backward of the 310 M-parameter UNet over a
 [2, 16, 8, 32, 32] synthetic latent clip (32 frames with the clean (+) noised DART sequence); every 4th step also
@@ -75,48 +76,113 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-class ConvProfiler:
-    """CUDA-event timing of the dominant kernel (the tcgen05 tap-GEMM behind ob_conv_fwd / ob_conv_dgrad) on the
-    launching stream, plus a count of every kernel launched through the C ABI."""
+def _conv_flops(name, a):
+    # ob_conv_fwd(x,ctx,wg,alpha,beta,out,out_d,ws, n_seq,S,T,H,W,cin,cout,ksize,gated,...) / ob_conv_dgrad(gy,gb,wg,alpha,beta,dx,ws, ...)
+    off = 8 if name == "ob_conv_fwd" else 7
+    n_seq, S, T, H, W, cin, cout, k, gated = a[off:off + 9]
+    px = n_seq * T * H * W
+    if gated:
+        return 2.0 * px * S * cin * cout * 9 + 2.0 * px * cin * cout * 18
+    return 2.0 * px * S * cin * cout * k * k
 
-    def __init__(self, timed_names=("ob_conv_fwd", "ob_conv_dgrad")):
-        self.timed, self.events, self.flops, self.launches = set(timed_names), [], 0.0, 0
 
-    @staticmethod
-    def conv_flops(name, a):
-        # ob_conv_fwd(x,ctx,wg,alpha,beta,out,out_d, n_seq,S,T,H,W,cin,cout,ksize,gated,...) / ob_conv_dgrad(gy,gb,wg,alpha,beta,dx, ...)
-        off = 8 if name == "ob_conv_fwd" else 7
-        n_seq, S, T, H, W, cin, cout, k, gated = a[off:off + 9]
-        px = n_seq * T * H * W
-        if gated:
-            return 2.0 * px * S * cin * cout * 9 + 2.0 * px * cin * cout * 18
-        return 2.0 * px * S * cin * cout * k * k
+def _is_null(p):
+    return p is None or getattr(p, "value", 1) in (None, 0)
+
+
+# Algorithmic HBM bytes per launch of the bandwidth-bound kernels, from the entry point's arguments (include/oniris_b200.h;
+# DESIGN.md section 4 states the per-element figures): every operand read once, every result written once.
+HBM_BYTES = {
+    # (w, wg, cout, cin, taps, cin_pad, taps_total, tap_off, gain, eps, training): fp32 in [+ fp32 forced copy out] + bf16 operand out
+    "ob_wnorm_fwd": lambda a: a[2] * a[3] * a[4] * (4 + 4 * a[10]) + a[2] * a[4] * a[5] * 2,
+    # (w2, dw2, w3, dw3, dwg, cout, cin, cin_pad, n_split, ...): split partials in + w in + dw read-modify-write
+    "ob_wnorm_bwd_gated": lambda a: a[8] * a[5] * 27 * a[7] * 4 + 27 * a[5] * a[6] * 12,
+    # (w, dwg, dw, cout, cin, taps, cin_pad, taps_total, tap_off, n_split, ...)
+    "ob_wnorm_bwd": lambda a: a[9] * a[3] * a[5] * a[6] * 4 + a[3] * a[4] * a[5] * 12,
+    # (dy, y, d, alpha, beta, gya, gb, scratch, n_seq, S, T, frame_elems, ...): dy, y bf16 in (+ d when passed), gya + gb out
+    "ob_gate_bwd_fused": lambda a: a[8] * a[9] * a[10] * a[11] * (2 + 2 + (0 if _is_null(a[2]) else D_BYTES) + 2) + a[8] * a[10] * a[11] * 2,
+    # (p, g, m, v, e1, e2, n, ...): p, g, m, v and both EMAs read and written
+    "ob_adamw_ema": lambda a: a[6] * (32 + (0 if _is_null(a[4]) else 8) + (0 if _is_null(a[5]) else 8)),
+    "ob_pixnorm_silu_fwd": lambda a: a[3] * a[4] * (2 + (4 if a[6] == 0 else 2)),
+    "ob_pixnorm_silu_bwd": lambda a: a[4] * a[5] * (2 + 2 + 2 + (0 if _is_null(a[1]) else 2)),
+    "ob_scale_silu_fwd": lambda a: a[3] * a[4] * 4,
+    "ob_scale_silu_bwd": lambda a: a[5] * a[7] * a[6] * 6,
+    "ob_mp_sum_fwd": lambda a: a[3] * 6,
+    "ob_mp_sum_bwd": lambda a: a[4] * (6 + (2 if a[6] > 0 else 0)),
+    "ob_mp_cat_fwd": lambda a: a[3] * (a[4] + a[5]) * 4,
+    "ob_mp_cat_bwd": lambda a: a[3] * (a[4] + a[5]) * 4,
+    # (x, pad, ctx, b, S, T, frame_elems, ...): the clean frames copied into the context tensor
+    "ob_conv_prologue": lambda a: a[3] * a[5] * a[6] * 4,
+}
+D_BYTES = 4     # bytes per element of the saved context-minus-current term the gate backward re-reads
+
+
+class KernelProfiler:
+    """CUDA-event timing of every launch that goes through the C ABI, on the launching stream, aggregated per entry point:
+    FLOPs for the tcgen05 tap-GEMM (ob_conv_fwd / ob_conv_dgrad), algorithmic HBM bytes for the bandwidth-bound kernels."""
+
+    def __init__(self):
+        self.events, self.launches = [], 0
 
     def before(self, name, args):
         self.launches += KERNELS_PER_CALL.get(name, 1)
-        if name in self.timed:
-            e0 = torch.cuda.Event(enable_timing=True)
-            e0.record()
-            return e0
-        return None
+        e0 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        return e0
 
     def after(self, name, args, e0):
-        if e0 is not None:
-            e1 = torch.cuda.Event(enable_timing=True)
-            e1.record()
-            self.events.append((e0, e1))
-            self.flops += self.conv_flops(name, args)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e1.record()
+        work = 0.0
+        if name in ("ob_conv_fwd", "ob_conv_dgrad"):
+            work = _conv_flops(name, args)
+        elif name in HBM_BYTES:
+            work = float(HBM_BYTES[name](args))
+        self.events.append((name, e0, e1, work))
 
-    def summary(self):
-        ms = sum(a.elapsed_time(b) for a, b in self.events)
-        return ms, self.flops, len(self.events)
+    def table(self):
+        """{entry point: [ms, launches, work]}"""
+        t = {}
+        for name, e0, e1, work in self.events:
+            r = t.setdefault(name, [0.0, 0, 0.0])
+            r[0] += e0.elapsed_time(e1)
+            r[1] += 1
+            r[2] += work
+        return t
 
 
-def oracle_cpu_step(batch, seed=0):
-    """The reference algorithm (oracle port, fp32, dense-masked attention) for one CS micro-step on the host cores."""
-    from oracle import oniris_oracle as O
+def reference_staged():
+    from oracle import ref_shim
+    root = ref_shim.reference_root()
+    return root is not None and os.path.abspath(root).startswith(os.path.join(ROOT, "oracle", "_ref"))
+
+
+def cpu_step_fn(batch, seed=0):
+    """One Counter-Strike micro-step of the reference algorithm on the host cores (fp32), as a callable(just_2d) -> seconds,
+    plus a description.  Preferred: the UNMODIFIED reference staged under oracle/_ref (its own UNet / Precond / EDM2Loss,
+    dense-masked SDPA for the training mask as its own test does); else the oracle port."""
     from autoregressive_diffusion_b200.train import CS_UNET as C
     torch.set_num_threads(os.cpu_count())
+    if reference_staged():
+        from oracle.ref_shim import import_reference
+        ref = import_reference(force_cpu=True)
+        torch.manual_seed(seed)
+        unet = ref["nets"].UNet(**C)
+        with torch.no_grad():
+            unet.out_gain.fill_(1.0)
+        precond = ref["nets"].Precond(unet, use_fp16=False, sigma_data=1.0).train()
+        loss_fn = ref["loss"].EDM2Loss(P_mean=0.9, P_std=1.0, sigma_data=1.0, context_noise_reduction=0.1)
+        images = torch.randn(batch, CLIP, 8, 32, 32)
+
+        def step(just_2d=False):
+            t0 = time.perf_counter()
+            loss, _ = loss_fn(precond, images, None, just_2d=just_2d)
+            loss.backward()
+            for p in precond.parameters():
+                p.grad = None
+            return time.perf_counter() - t0
+        return step, "reference", "unmodified edm2 UNet/Precond/EDM2Loss (oracle/_ref), fp32 (use_fp16=False: CPU), dense-masked SDPA"
+    from oracle import oniris_oracle as O
     lay = O.unet_layout(C["img_resolution"], C["img_channels"], C["label_dim"], C["model_channels"], C["channel_mult"],
                         C["num_blocks"], C["video_attn_resolutions"], C["frame_attn_resolutions"])
     sd = O.unet_init_state(lay, C["model_channels"], seed)
@@ -126,18 +192,19 @@ def oracle_cpu_step(batch, seed=0):
                        (torch.randn(batch, CLIP, generator=g) * 1.0 + 0.9).exp()), dim=1)
     noise = torch.randn(batch, 2 * CLIP, 8, 32, 32, generator=g)
 
-    def step():
+    def step(just_2d=False):     # the port has no 2-D form: every step is the (more expensive) 3-D one
         t0 = time.perf_counter()
         O.train_step(sd, lay, images, sigma, noise)
         return time.perf_counter() - t0
-    return step
+    return step, "port", "oracle/oniris_oracle.py restatement, fp32, dense-masked attention"
 
 
-def workload_config(parallelism, launch):
+def workload_config(parallelism, launch, no_2d=False):
     """The workload both arms are quoted on (BASELINE.json configs[2], one GPU's share)."""
     return {"workload": "cs_train.py Counter-Strike UNet (310M params), DART 32-frame sequence, fwd+bwd micro-step; "
-                        "gradient all-reduce + AdamW + 2 EMAs every 4th step",
+                        "gradient all-reduce + AdamW + 2 power-function EMAs every 4th step",
             "micro_batch_per_gpu": MICRO_BATCH, "clip_frames": CLIP, "latent": [8, 32, 32], "accumulation": 4,
+            "just_2d_schedule": "none" if no_2d else "every 4th micro-step in 2-D form (cs_train.py:106)",
             "parallelism": parallelism, "launch": launch,
             "l2": "no explicit flush: each step streams >2 GB of weights/operands/activations (>> 126 MB L2)"}
 
@@ -146,21 +213,22 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    batch = 1   # bounded sample: half the micro-batch (one 32-frame DART sequence) per step
-    step = oracle_cpu_step(batch)
-    for _ in range(args.warmup):
-        step()
-    times = [step() for _ in range(args.steps)]
+    batch = 1   # bounded sample: half the micro-batch (one 16-frame clip = one 32-frame DART sequence) per step
+    step, kind, what = cpu_step_fn(batch)
+    two_d = (lambda i: False) if args.no_2d else (lambda i: (i + 1) % 4 == 0)     # cs_train.py:106 just_2d = i%4==0
+    for i in range(args.warmup):
+        step(two_d(i))
+    times = [step(two_d(i)) for i in range(args.steps)]
     ms = 1e3 * sum(times) / len(times)
     fps = batch * CLIP / (ms / 1e3)
     line = {
         "impl": "reference", "metric": "train frames/s", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config("cpu", "oracle port on the host cores; each step = a bounded sample, see cpu_baseline.sample"),
-        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
+        "config": workload_config("cpu", f"{what}; each step = a bounded sample, see cpu_baseline.sample", args.no_2d),
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": os.cpu_count(), "kind": kind,
                          "sample": f"1 of the {MICRO_BATCH} sequences of a micro-batch per step (fwd+bwd, no optimizer), "
-                                   f"oracle/oniris_oracle.py fp32 on {os.cpu_count()} threads"},
+                                   f"{what}, {os.cpu_count()} threads"},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -173,7 +241,10 @@ def dbg(msg):
 
 def tapconv_traffic():
     """DRAM bytes per tap-GEMM launch from the committed ncu capture (None when the profile is absent)."""
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_tapconv_traffic.json")
+    prof_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles")
+    path = os.path.join(prof_dir, "r02_tapconv_traffic.json")
+    if not os.path.exists(path):
+        path = os.path.join(prof_dir, "r01_tapconv_traffic.json")
     try:
         with open(path) as f:
             return float(json.load(f)["dram_bytes_per_launch"])
@@ -190,7 +261,9 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dbg("init done")
-    tr = Trainer(CS_UNET, accumulation_steps=4, device=dev, seed=42)
+    tr = Trainer(CS_UNET, accumulation_steps=4, device=dev, seed=42, just_2d_every=0 if args.no_2d else 4)
+    with torch.no_grad():
+        tr.unet.out_gain.fill_(1.0)     # random-init benchmark weights: the reference's zero init would zero every gradient
     dbg("trainer built")
     shape = (MICRO_BATCH, CLIP, 8, 32, 32)
     g = torch.Generator().manual_seed(1234 + rank)
@@ -227,34 +300,47 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item() / k
 
-    # Kernel census + dominant-kernel timing: one eager accumulation cycle with CUDA events around every tap-GEMM
-    # launch on the launching stream (the graph replays exactly this kernel sequence).
+    # Kernel census + per-kernel timing: one eager accumulation cycle with CUDA events around every launch that goes
+    # through the C ABI, on the launching stream (the graph replays exactly this kernel sequence).
+    from autoregressive_diffusion_b200.ops import WeightGradBranch
+
+    def local_cycle():
+        """4 micro-steps + the optimizer update without the collective (a parked GPU would otherwise be timed waiting for
+        its peers): with several ranks the accumulated gradients are dropped instead of applied, so replicas stay equal."""
+        for i in range(4):
+            tr._forward_backward(resident[i % n_host])
+        if world > 1:
+            tr.buckets.flat.zero_()
+        else:
+            tr._optimizer_step()
+
+    def park(t_host):
+        # park the stream for twice the host's enqueue time so the whole cycle is queued ahead of the GPU: the event pairs
+        # then bracket back-to-back kernel executions, not host launch gaps (each sleep <= 2^31 cycles)
+        for _ in range(max(2, int(2.5 * t_host / 0.4) + 1)):
+            torch.cuda._sleep(int(0.8e9))
+
+    torch.cuda.synchronize()
+    for i in range(4):                          # first cycle: flat buffers laid out, NCCL communicators created
+        tr.micro_step(resident[i % n_host])
     torch.cuda.synchronize()
     t_host = time.perf_counter()
-    for i in range(4):
-        tr.micro_step(resident[i % n_host])
-    t_host = time.perf_counter() - t_host       # eager launches are host-bound: this is the host's enqueue time per cycle
-    prof = ConvProfiler()
-    _lib.set_profiler(prof)
-    from autoregressive_diffusion_b200.ops import WeightGradBranch
-    WeightGradBranch.enabled = False    # this cycle times each kernel alone: keep the weight-gradient branch in line
+    local_cycle()
     torch.cuda.synchronize()
-    # park the stream for twice the host's enqueue time so the whole cycle is queued ahead of the GPU: the event pairs
-    # then bracket back-to-back kernel executions, not host launch gaps (each sleep <= 2^31 cycles)
-    for _ in range(max(2, int(2.5 * t_host / 0.4) + 1)):
-        torch.cuda._sleep(int(0.8e9))
-    for i in range(4):
-        tr.micro_step(resident[i % n_host])
+    t_host = time.perf_counter() - t_host       # eager launches are host-bound: this is the host's enqueue time per cycle
+    prof = KernelProfiler()
+    _lib.set_profiler(prof)
+    WeightGradBranch.enabled = False    # this cycle times each kernel alone: keep the weight-gradient branch in line
+    park(t_host)
+    local_cycle()
     torch.cuda.synchronize()
     _lib.set_profiler(None)
-    # the same serialised cycle once more WITHOUT the per-launch events (they cost ~20 us each on a deep queue): its
+    # the same serialised cycle once more WITHOUT the per-launch events (they cost time on a deep queue): its
     # GPU time is the denominator of the kernel's share, on the same basis as the ncu launch list under profiles/
-    for _ in range(max(2, int(2.5 * t_host / 0.4) + 1)):
-        torch.cuda._sleep(int(0.8e9))
+    park(t_host)
     cyc0, cyc1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     cyc0.record()
-    for i in range(4):
-        tr.micro_step(resident[i % n_host])
+    local_cycle()
     cyc1.record()
     torch.cuda.synchronize()
     serial_cycle_ms = cyc0.elapsed_time(cyc1)      # 4 micro-steps + optimizer, one stream, no host gaps
@@ -279,14 +365,25 @@ def run_ours(args):
         return
     fps = world * MICRO_BATCH * CLIP / (ms / 1e3)
     fps_e2e = world * MICRO_BATCH * CLIP / (ms_e2e / 1e3)
-    conv_ms, conv_flops, conv_launches = prof.summary()
-    peak_tf, _, peak_kind = measured_peaks()
+    table = prof.table()
+    conv_ms = sum(table[k][0] for k in ("ob_conv_fwd", "ob_conv_dgrad") if k in table)
+    conv_flops = sum(table[k][2] for k in ("ob_conv_fwd", "ob_conv_dgrad") if k in table)
+    conv_launches = sum(table[k][1] for k in ("ob_conv_fwd", "ob_conv_dgrad") if k in table)
+    peak_tf, peak_gbs, peak_kind = measured_peaks()
     achieved = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+    hbm = []
+    for name, (k_ms, k_n, k_bytes) in sorted(table.items(), key=lambda kv: -kv[1][0]):
+        if name in HBM_BYTES and k_ms > 0:
+            gbs = k_bytes / (k_ms * 1e-3) / 1e9
+            hbm.append({"kernel": name, "achieved": round(gbs, 1), "frac": round(gbs / peak_gbs, 3), "launches_per_cycle": k_n,
+                        "ms_per_cycle": round(k_ms, 3), "share_of_step": round(k_ms / serial_cycle_ms, 4),
+                        "bytes_per_launch": int(k_bytes / k_n)})
+    other = {name: round(v[0], 3) for name, v in table.items() if name not in HBM_BYTES and name not in ("ob_conv_fwd", "ob_conv_dgrad")}
     line = {
         "metric": "train frames/s", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
-        "config": workload_config(f"dp{world}", "cuda-graph replay per micro-step" if use_graph else "eager"),
+        "config": workload_config(f"dp{world}", "cuda-graph replay per micro-step" if use_graph else "eager", args.no_2d),
         "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": MICRO_BATCH * CLIP * 8 * 32 * 32 * 4,
                 "d2h_bytes_per_step": 4},
         "gpu_launches": int(launches_per_step * args.steps),
@@ -295,17 +392,22 @@ def run_ours(args):
                      "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                      "peak_kind": f"{peak_kind} bf16_tflops_sustained", "launches": conv_launches,
                      "share_of_step": conv_ms / serial_cycle_ms,
-                     "share_basis": "tap-GEMM launch time / single-stream (serialised) time of the same eager cycle -- the basis of the ncu launch list in profiles/, where tapconv + its finish kernels and memsets are ~40 % of the serialised step",
+                     "share_basis": "tap-GEMM launch time / single-stream (serialised) time of the same eager cycle -- the basis of the ncu launch list in profiles/",
                      "traffic": tapconv_traffic(),
-                     "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum per tapconv launch, mean over the 187 launches of one step, from the committed ncu pass profiles/r01_launches_step.csv",
-                     "how": "CUDA events around each tap-GEMM launch over one eager 4-step cycle on the launching stream, enqueued ahead of a parked GPU so the intervals hold no host gaps; the weight-gradient stream is kept in line for this cycle so each kernel is timed alone"},
+                     "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum per tapconv launch, mean over the launches of one step, from the committed ncu pass under profiles/",
+                     "how": "CUDA events around each launch over one eager 4-step cycle on the launching stream, enqueued ahead of a parked GPU so the intervals hold no host gaps; the weight-gradient stream is kept in line for this cycle so each kernel is timed alone"},
+        "roofline_hbm": {"peak": peak_gbs, "unit": "GB/s", "peak_kind": f"{peak_kind} hbm_gbs (copy)", "kernels": hbm[:10],
+                         "how": "same event-timed cycle; achieved = algorithmic bytes of the entry point's arguments / its launch time",
+                         "other_entry_points_ms_per_cycle": other, "serial_cycle_ms": round(serial_cycle_ms, 3)},
     }
     if world == 1 and not args.no_cpu_baseline:
-        step = oracle_cpu_step(1)
+        step, kind, what = cpu_step_fn(1)
         step()
-        t = step()
-        line["cpu_baseline"] = {"value": CLIP / t, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
-                                "sample": "one 32-frame DART sequence (half a micro-batch), fwd+bwd, 1 warm-up + 1 timed step"}
+        t3, t2 = step(False), step(True)
+        t = t3 if args.no_2d else (3 * t3 + t2) / 4
+        line["cpu_baseline"] = {"value": CLIP / t, "unit": "frames/s", "cores": os.cpu_count(), "kind": kind,
+                                "sample": f"one 16-frame clip (half a micro-batch), fwd+bwd: 1 warm-up, 1 timed 3-D step ({t3:.2f} s) and 1 timed "
+                                          f"2-D step ({t2:.2f} s) weighted 3:1 as the schedule runs them; {what}"}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -314,10 +416,11 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=16)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=4)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-2d", action="store_true", help="every micro-step in 3-D form (cs_train.py:106 runs every 4th in 2-D form)")
     ap.add_argument("--eager", action="store_true", help="launch kernels from Python instead of replaying CUDA graphs")
     args = ap.parse_args()
     if args.impl == "reference":

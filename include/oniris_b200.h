@@ -163,16 +163,25 @@ int ob_resample2x(const void* in, void* out, int64_t frames, int h, int w, int c
  * while its second stream is active (see csrc/launch.cuh). */
 int ob_set_pdl(int mode);
 
-/* Optimizer step of the training loop (cs_train.py:121-125: torch.optim.AdamW.step, zero_grad, and the EMA copies of
- * the weights) over one flat fp32 range of n elements (n % 4 == 0, 16-byte aligned buffers):
+/* Optimizer step of the training loop (cs_train.py:121-125: torch.optim.AdamW.step, zero_grad, and the
+ * PowerFunctionEMA.update copies of the weights, edm2/phema.py:104-109) over one flat fp32 range of n elements
+ * (n % 4 == 0, 16-byte aligned buffers):
  *   m = b1*m + (1-b1)*g;  v = b2*v + (1-b2)*g*g;  p = p*(1 - lr*wd) - lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
- *   ema_k += (1 - ema_beta_k) * (p - ema_k)   (either pointer may be NULL);   g = 0.
- * g is multiplied by grad_scale first (1/world_size after a SUM all-reduce: the mean costs no extra pass).
- * step_lr: device fp32 {t, lr} with t the 1-based step count of THIS update.  The call may cover any 16-byte aligned
- * sub-range, so a bucketed all-reduce can be pipelined with the update of the buckets already reduced. */
-int ob_adamw_ema(float* p, float* g, float* m, float* v, float* ema1, float* ema2, int64_t n, const float* step_lr,
-                 float beta1, float beta2, float eps, float weight_decay, float ema_beta1, float ema_beta2, float grad_scale,
-                 void* stream);
+ *   ema_k += (1 - beta_k) * (p - ema_k)   (either pointer may be NULL);   g = 0.
+ * EMA coefficient: ema_ratio > 0 selects the power-function profile of edm2/phema.py:68-70,
+ *   beta_k = (1 - ema_ratio/t)^ema_a_k   with ema_a_k = std_to_exp(std_k) + 1  and  ema_ratio/t = t_delta/t_next
+ * evaluated on the device from the step count (so a CUDA-graph replay follows the schedule); ema_ratio <= 0 uses the
+ * constant beta_k = ema_a_k (TraditionalEMA without ramp-up).
+ * g is multiplied by grad_scale first (1/world_size after a SUM all-reduce: the mean costs no extra pass) and, when
+ * max_grad_norm > 0, by min(1, max_grad_norm / (grad_scale*sqrt(opt_state[2]) + 1e-6)) -- clip_grad_norm_ of
+ * gym_train.py:105 with the squared norm accumulated by ob_sumsq.
+ * opt_state: device fp32 {t, lr, grad_sumsq} with t the 1-based step count of THIS update.  The call may cover any
+ * 16-byte aligned sub-range, so a bucketed all-reduce can be pipelined with the update of the buckets already reduced. */
+int ob_adamw_ema(float* p, float* g, float* m, float* v, float* ema1, float* ema2, int64_t n, const float* opt_state,
+                 float beta1, float beta2, float eps, float weight_decay, float ema_a1, float ema_a2, float ema_ratio,
+                 float grad_scale, float max_grad_norm, void* stream);
+/* out[0] += sum_i g[i]^2 (n % 4 == 0, g 16-byte aligned); the caller zeroes out[0]. */
+int ob_sumsq(const float* g, int64_t n, float* out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------- attention
  * edm2/attention/attention_modules.py:59-77: compiled_flex_attention(q,k,v, make_train_mask / make_infer_mask) and

@@ -10,7 +10,6 @@ with eager flex_attention (no-grad) or dense-masked SDPA built from the BlockMas
 """
 import os
 import sys
-import types
 
 import torch
 
@@ -19,42 +18,23 @@ REF = os.environ.get("ONIRIS_REFERENCE", "/root/reference")
 
 
 def import_reference():
-    for name in ["matplotlib", "matplotlib.pyplot", "matplotlib.colors"]:
-        sys.modules.setdefault(name, types.ModuleType(name))
-    sys.modules["matplotlib.colors"].LogNorm = object
-    sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
-    sys.path.insert(0, REF)
-
-    def remap(fn):
-        def w(*a, **k):
-            if str(k.get("device", "")).startswith("cuda"):
-                k["device"] = "cpu"
-            return fn(*a, **k)
-        return w
-
-    torch.arange, torch.tensor = remap(torch.arange), remap(torch.tensor)
-    torch.Tensor.cuda = lambda self, *a, **k: self
-    import edm2.attention.attention_modules as am
-    from torch.nn.attention.flex_attention import create_mask, flex_attention
-    import torch.nn.functional as F
-
-    def cpu_flex(q, k, v, score_mod=None, block_mask=None):
-        assert score_mod is not None or block_mask is not None
-        if not (q.requires_grad or k.requires_grad or v.requires_grad):
-            return flex_attention(q, k, v, score_mod=score_mod, block_mask=block_mask)
-        mask = create_mask(block_mask.mask_mod, 1, 1, q.shape[-2], k.shape[-2], device="cpu")
-        return F.scaled_dot_product_attention(q, k, v, attn_mask=mask)
-
-    am.compiled_flex_attention = cpu_flex
-    import edm2.attention.attention_masking as masking
-    import edm2.conv as conv
-    import edm2.networks_edm2 as nets
-    import edm2.utils as utils
-    return dict(am=am, masking=masking, conv=conv, nets=nets, utils=utils)
+    """The unmodified reference through oracle/ref_shim.py (stub matplotlib, CPU device remap, dense-masked SDPA for the
+    training mask)."""
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    os.environ.setdefault("ONIRIS_REFERENCE", REF)
+    from oracle.ref_shim import import_reference as imp
+    return imp(force_cpu=True)
 
 
 def t(x):
     return x.detach().clone().contiguous()
+
+
+def rb(x):
+    """Round to bf16-representable fp32: the layer inputs and upstream gradients of every per-layer fixture are exactly
+    representable in the kernels' input type, so a parity test feeds IDENTICAL values to both sides and BASELINE's
+    un-loosened budget (max 2e-2 / mean 2e-3) applies."""
+    return x.to(torch.bfloat16).to(torch.float32)
 
 
 def seeded_state(shapes, seed=1234):
@@ -81,13 +61,13 @@ def main():
     # ---- weight norm + MPConv (edm2/conv.py:8-46) fwd and grads, train and eval
     torch.manual_seed(42)
     m = conv.MPConv(24, 16, kernel=[3, 3])
-    x = torch.randn(4, 24, 8, 8, requires_grad=True)
+    x = rb(torch.randn(4, 24, 8, 8)).requires_grad_(True)
     w0 = t(m.weight.weight)
     m.eval()
     y_eval = m(x, gain=0.7)
     m.train()
     y_tr = m(x, gain=0.7)
-    gy = torch.randn_like(y_tr)
+    gy = rb(torch.randn_like(y_tr))
     y_tr.backward(gy)
     out["mpconv"] = dict(w0=w0, x=t(x), gain=0.7, y_eval=t(y_eval), y_train=t(y_tr), gy=gy, w_forced=t(m.weight.weight),
                          gw=t(m.weight.weight.grad), gx=t(x.grad))
@@ -102,17 +82,17 @@ def main():
         g.gating.max_gating.fill_(0.5)
         g.gating.min_gating.fill_(-1.0)
     sd0 = {k: t(v) for k, v in g.state_dict().items()}
-    x = torch.randn(B * 2 * n, C, R, R, requires_grad=True)
+    x = rb(torch.randn(B * 2 * n, C, R, R)).requires_grad_(True)
     cn = torch.randn(B, 2 * n)
     g.train()
     y, _ = g(x, None, B, cn)
-    gy = torch.randn_like(y)
+    gy = rb(torch.randn_like(y))
     y.backward(gy)
     rec = dict(sd0=sd0, x=t(x), c_noise=cn, y_train=t(y), gy=gy, gx=t(x.grad), B=B, n=n,
                sd_after={k: t(v) for k, v in g.state_dict().items()},
                grads={k: t(p.grad) for k, p in g.named_parameters()})
     g.eval()
-    xe = torch.randn(B * n, C, R, R)
+    xe = rb(torch.randn(B * n, C, R, R))
     cne = torch.randn(B, n)
     ye, _ = g(xe, None, B, cne)
     ctx = xe.reshape(B, n, C, R, R)[:, :-1].reshape(-1, C, R, R)
@@ -159,17 +139,17 @@ def main():
     B, n, C, R, heads = 2, 4, 128, 8, 2     # 64 tok/frame: n*hw=256 -> super-block regrouping path (F3)
     va = am.VideoAttention(C, heads)
     sd0 = {k_: t(v) for k_, v in va.state_dict().items()}
-    x = torch.randn(B * 2 * n, C, R, R, requires_grad=True)
+    x = rb(torch.randn(B * 2 * n, C, R, R)).requires_grad_(True)
     va.train()
     y, _ = va(x, B)
-    gy = torch.randn_like(y)
+    gy = rb(torch.randn_like(y))
     y.backward(gy)
     rec = dict(sd0=sd0, x=t(x), y_train=t(y), gy=gy, gx=t(x.grad), B=B, n=n, heads=heads,
                grads={k_: t(p.grad) for k_, p in va.named_parameters()},
                sd_after={k_: t(v) for k_, v in va.state_dict().items()})
     va.eval()
     with torch.no_grad():
-        xe = torch.randn(B * n, C, R, R)
+        xe = rb(torch.randn(B * n, C, R, R))
         ye, _ = va(xe, B)
         xr = xe.reshape(B, n, C, R, R)
         yc, cache = va(xr[:, :-1].reshape(-1, C, R, R), B, update_cache=True)
@@ -182,17 +162,17 @@ def main():
     torch.manual_seed(42)
     fa = am.FrameAttention(128, 2)
     sd0 = {k_: t(v) for k_, v in fa.state_dict().items()}
-    x = torch.randn(6, 128, 4, 4, requires_grad=True)
+    x = rb(torch.randn(6, 128, 4, 4)).requires_grad_(True)
     fa.train()
     y, _ = fa(x)
-    gy = torch.randn_like(y)
+    gy = rb(torch.randn_like(y))
     y.backward(gy)
     out["frame_attention"] = dict(sd0=sd0, x=t(x), y_train=t(y), gy=gy, gx=t(x.grad),
                                   grads={k_: t(p.grad) for k_, p in fa.named_parameters()})
 
     # ---- elementwise primitives (edm2/utils.py)
     torch.manual_seed(42)
-    a, b = torch.randn(6, 8, 4, 4), torch.randn(6, 8, 4, 4)
+    a, b = rb(torch.randn(6, 8, 4, 4)), rb(torch.randn(6, 8, 4, 4))
     tt = torch.rand(6)
     out["elementwise"] = dict(a=a, b=b, t=tt, mp_sum_f=utils.mp_sum(a, b, 0.3), mp_sum_t=utils.mp_sum(a, b, tt),
                               mp_silu=utils.mp_silu(a), mp_cat=utils.mp_cat(a, b[:, :4], t=0.5), norm1=utils.normalize(a, dim=1),

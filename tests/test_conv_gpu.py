@@ -17,14 +17,20 @@ def _gate_sd(m):
     return {n: getattr(m.gating, n).detach().cpu() for n in ("offset", "mult", "max_gating", "min_gating")}
 
 
-@pytest.mark.parametrize("cin,cout,res,k", [(64, 128, 16, 1), (128, 64, 8, 3), (32, 64, 16, 3), (24, 16, 8, 3), (256, 256, 4, 3)])
-def test_mpconv_fwd_bwd(cin, cout, res, k):
+# the last rows are Counter-Strike / Lunar-Lander layer shapes (cs_train.py:35-45: 64 frames per micro-batch), chosen so
+# that the tiling policy resolves to the kernel instantiations the benchmark runs: N=256 CTA pairs (cta_group::2) for the
+# 1x1 qkv / proj / skip layers and the 2-D 3x3 convs of just_2d steps, wgrad <64,256> / two-tap <64,128,2>
+@pytest.mark.parametrize("cin,cout,res,k,frames", [(64, 128, 16, 1, 6), (128, 64, 8, 3, 6), (32, 64, 16, 3, 6), (24, 16, 8, 3, 6),
+                                                   (256, 256, 4, 3, 6), (512, 1536, 8, 1, 64), (512, 1536, 4, 1, 64),
+                                                   (512, 512, 4, 1, 64), (768, 512, 8, 1, 64), (256, 256, 16, 3, 64),
+                                                   (128, 128, 32, 3, 32), (512, 512, 4, 3, 64)])
+def test_mpconv_fwd_bwd(cin, cout, res, k, frames):
     ob = _mods()
     torch.manual_seed(0)
     m = ob.MPConv(cin, cout, [k, k]).cuda()
     w0 = m.weight.weight.detach().cpu().clone()
-    x = bf16r(torch.randn(6, cin, res, res))
-    gy = bf16r(torch.randn(6, cout, res, res))
+    x = bf16r(torch.randn(frames, cin, res, res))
+    gy = bf16r(torch.randn(frames, cout, res, res))
     for training in (False, True):
         m.train(training)
         with torch.no_grad():
@@ -44,7 +50,14 @@ def test_mpconv_fwd_bwd(cin, cout, res, k):
         m.weight.weight.grad = None
 
 
-@pytest.mark.parametrize("B,n,cin,cout,res", [(2, 4, 16, 24, 8), (2, 4, 64, 64, 4), (1, 3, 128, 128, 8), (2, 2, 32, 64, 16)])
+# rows 5+ are the Counter-Strike layer shapes of the benchmark (B=2 sequences of 16+16 frames, cs_train.py:35-45,59-62):
+#   512->512 @16x16, 128->128 @32x32: CTA pairs + rotating TMEM accumulator + persistent tiles; wgrad <64,256> / two-tap <64,128,2>
+#   512->512 @4x4, 1024->512 @8x8, 768->512 @8x8: split-K over channel chunks + tapconv_finish_kernel
+#   256->128 @32x32 (decoder, skip-concatenated input), 9->128 @32x32 is covered by the 16->24 row (16-channel chunks)
+@pytest.mark.parametrize("B,n,cin,cout,res", [(2, 4, 16, 24, 8), (2, 4, 64, 64, 4), (1, 3, 128, 128, 8), (2, 2, 32, 64, 16),
+                                              (2, 16, 512, 512, 16), (2, 16, 128, 128, 32), (2, 16, 512, 512, 4),
+                                              (2, 16, 1024, 512, 8), (2, 16, 768, 512, 8), (2, 16, 256, 128, 32),
+                                              (2, 16, 256, 256, 16)])
 def test_gated_conv_train(B, n, cin, cout, res):
     ob = _mods()
     torch.manual_seed(1)
@@ -85,21 +98,21 @@ def test_gated_conv_eval_cache_golden(golden):
     xe, cn = g["x_eval"], g["c_noise_eval"]
     with torch.no_grad():
         y, _ = m(xe.cuda(), None, B, cn.cuda())
-        # golden inputs are fp32 (not bf16-representable): input rounding adds ~1.3e-3 mean error
-        assert_close(y.float(), g["y_eval"], "eval", mean_rel=4e-3)
+        # golden inputs are bf16-representable (make_golden.rb): BASELINE's un-loosened budget applies
+        assert_close(y.float(), g["y_eval"], "eval")
         xr = xe.reshape(B, n, *xe.shape[1:])
         yc, cache = m(xr[:, :-1].reshape(-1, *xe.shape[1:]).cuda(), None, B, cn[:, :-1].cuda(), update_cache=True)
-        assert_close(yc.float(), g["y_prefill"], "prefill", mean_rel=4e-3)
+        assert_close(yc.float(), g["y_prefill"], "prefill")
         assert cache["n_context_frames"] == g["cache_n"]
         assert tuple(cache["activations"].shape) == tuple(g["cache_act"].shape)
-        assert_close(cache["activations"].float(), g["cache_act"], "cache", mean_rel=4e-3)
+        assert_close(cache["activations"].float(), g["cache_act"], "cache", 1e-6, 1e-6)   # bf16 inputs are stored exactly
         yl, _ = m(xr[:, -1].cuda(), None, B, cn[:, -1:].cuda(), cache=cache)
-        assert_close(yl.float(), g["y_last"], "decode", mean_rel=4e-3)
+        assert_close(yl.float(), g["y_last"], "decode")
         # cached decode must equal the uncached pass bit-for-bit on the last frame (same kernel, same operands)
         y_full_last = y.reshape(B, n, *y.shape[1:])[:, -1]
         assert_close(yl.float(), y_full_last.float(), "cached == uncached", 1e-2, 1e-3)
         y2, _ = m(xe.cuda(), None, B, cn.cuda(), just_2d=True)
-        assert_close(y2.float(), g["y_just2d"], "just_2d", mean_rel=4e-3)
+        assert_close(y2.float(), g["y_just2d"], "just_2d")
 
 
 def test_gated_conv_train_golden(golden):
@@ -111,10 +124,63 @@ def test_gated_conv_train_golden(golden):
     x = g["x"].cuda().requires_grad_(True)
     y, _ = m(x, None, g["B"], g["c_noise"].cuda())
     y.backward(g["gy"].cuda())
-    assert_close(y.float(), g["y_train"], "y", mean_rel=4e-3)
-    assert_close(x.grad.float(), g["gx"], "dx", mean_rel=5e-3)
-    assert_close(m.last_frame_conv.weight.weight.grad, g["grads"]["last_frame_conv.weight.weight"], "dW2", mean_rel=5e-3)
-    assert_close(m.weight.weight.grad, g["grads"]["weight.weight"], "dW3", mean_rel=5e-3)
+    assert_close(y.float(), g["y_train"], "y")
+    assert_close(x.grad.float(), g["gx"], "dx")
+    assert_close(m.last_frame_conv.weight.weight.grad, g["grads"]["last_frame_conv.weight.weight"], "dW2")
+    assert_close(m.weight.weight.grad, g["grads"]["weight.weight"], "dW3")
     for k, v in g["sd_after"].items():
         if k.endswith("weight.weight"):
             assert_close(m.state_dict()[k], v, f"forced {k}", 1e-5, 1e-6)
+
+
+def test_mpconv_golden(golden):
+    """MPConv against the reference's own outputs (tests/golden/mpconv.pt): eval, train, forced weights, dx, dW."""
+    ob = _mods()
+    g = golden("mpconv")
+    m = ob.MPConv(24, 16, [3, 3]).cuda()
+    with torch.no_grad():
+        m.weight.weight.copy_(g["w0"])
+    m.eval()
+    with torch.no_grad():
+        assert_close(m(g["x"].cuda(), gain=g["gain"]).float(), g["y_eval"], "eval")
+    m.train()
+    x = g["x"].cuda().requires_grad_(True)
+    y = m(x, gain=g["gain"])
+    y.backward(g["gy"].cuda())
+    assert_close(y.float(), g["y_train"], "train")
+    assert_close(m.weight.weight.detach(), g["w_forced"], "forced weights", 1e-5, 1e-6)
+    assert_close(x.grad.float(), g["gx"], "dx")
+    assert_close(m.weight.weight.grad, g["gw"], "dW")
+
+
+def test_weight_gradients_through_autograd_and_direct_agree():
+    """ops.set_weight_grad_mode: "autograd" returns dW / gate gradients like any torch op (what torch.optim, autograd.grad and
+    DistributedDataParallel's reducer hooks need, cs_train.py:54); "direct" accumulates into .grad in the kernels."""
+    ob = _mods()
+    from autoregressive_diffusion_b200 import ops
+    torch.manual_seed(3)
+    B, n, c = 2, 3, 64
+    m = ob.MPCausal3DGatedConv(c, c, (3, 3, 3)).cuda().train()
+    x = bf16r(torch.randn(B * 2 * n, c, 8, 8)).cuda()
+    cn = torch.randn(B, 2 * n).cuda()
+    gy = bf16r(torch.randn(B * 2 * n, c, 8, 8)).cuda()
+    prev = ops.set_weight_grad_mode("autograd")
+    try:
+        y, _ = m(x, None, B, cn)
+        params = [m.last_frame_conv.weight.weight, m.weight.weight, m.gating.offset, m.gating.mult, m.gating.max_gating,
+                  m.gating.min_gating]
+        fired = []
+        hooks = [p.register_hook(lambda g_, i=i: fired.append(i)) for i, p in enumerate(params)]
+        auto = torch.autograd.grad(y, params, gy, retain_graph=False)
+        assert sorted(fired) == list(range(6)), "every parameter's autograd hook must fire (DDP's reducer relies on it)"
+        for h in hooks:
+            h.remove()
+        assert all(p.grad is None for p in params)
+        ops.set_weight_grad_mode("direct")
+        y, _ = m(x, None, B, cn)
+        y.backward(gy)
+        torch.cuda.synchronize()
+        for a, p in zip(auto, params):
+            assert_close(p.grad, a, "direct == autograd", 1e-5, 1e-6)
+    finally:
+        ops.set_weight_grad_mode(prev)

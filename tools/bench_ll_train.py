@@ -10,6 +10,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from autoregressive_diffusion_b200.train import LL_UNET, Trainer  # noqa: E402
 
 tr = Trainer(LL_UNET, accumulation_steps=2, lr=1e-2, eps=1e-8, P_mean=1.2, P_std=1.0, context_noise_reduction=0.5)
+tr.unet.out_gain.data.fill_(1.0)   # random-init weights: keep the output path live
 x = torch.randn(2, 8, 8, 64, 64, device="cuda")
 tr.capture(x)
 for _ in range(4):

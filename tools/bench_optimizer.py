@@ -8,6 +8,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from autoregressive_diffusion_b200.train import CS_UNET, Trainer  # noqa: E402
 
 tr = Trainer(CS_UNET, device="cuda")
+tr.unet.out_gain.data.fill_(1.0)   # random-init weights: keep the output path live
 x = torch.randn(2, 16, 8, 32, 32, device="cuda")
 for _ in range(4):
     tr.micro_step(x)

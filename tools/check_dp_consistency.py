@@ -13,6 +13,7 @@ from autoregressive_diffusion_b200.train import LL_UNET, Trainer, init_distribut
 rank, world, local = init_distributed()
 dev = f"cuda:{local}"
 tr = Trainer(LL_UNET, accumulation_steps=2, device=dev, seed=7)
+tr.unet.out_gain.data.fill_(1.0)   # random-init weights: keep the output path live
 g = torch.Generator(device=dev).manual_seed(100 + rank)
 for _ in range(4):
     x = torch.randn(1, 4, 8, 64, 64, device=dev, generator=g)

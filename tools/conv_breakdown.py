@@ -33,6 +33,7 @@ class Prof:
 
 
 tr = Trainer(CS_UNET, device="cuda")
+tr.unet.out_gain.data.fill_(1.0)   # random-init weights: keep the output path live
 x = torch.randn(2, 16, 8, 32, 32, device="cuda")
 for _ in range(6):
     tr.micro_step(x)

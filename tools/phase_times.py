@@ -14,6 +14,7 @@ WeightGradBranch.backward_pdl = int(os.environ.get("BWD_PDL", "0"))
 main_stream = torch.cuda.Stream(priority=int(os.environ.get("MAIN_PRIO", "0")))
 torch.cuda.set_stream(main_stream)
 tr = Trainer(CS_UNET, device="cuda")
+tr.unet.out_gain.data.fill_(1.0)   # random-init weights: keep the output path live
 x = torch.randn(2, 16, 8, 32, 32, device="cuda")
 for _ in range(6):
     tr.micro_step(x)

@@ -10,6 +10,7 @@ from autoregressive_diffusion_b200.train import CS_UNET, LL_UNET, Trainer  # noq
 
 cfg = LL_UNET if (len(sys.argv) > 1 and sys.argv[1] == "ll") else CS_UNET
 tr = Trainer(cfg, device="cuda")
+tr.unet.out_gain.data.fill_(1.0)   # random-init weights: keep the output path live
 res = cfg["img_resolution"]
 n = 8 if cfg is LL_UNET else 16
 x = torch.randn(2, n, 8, res, res, device="cuda")
