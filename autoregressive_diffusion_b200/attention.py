@@ -12,7 +12,9 @@ from torch import nn
 
 from . import ops
 from ._lib import _vp, call, stream_ptr
-from .attention_ops import CAUSAL, DART, FULL, AttentionFn
+import os
+
+from .attention_ops import CAUSAL, DART, DART_LISTED, FULL, AttentionFn
 from .conv import MPConv
 from .ops import BF16, rows
 
@@ -172,7 +174,16 @@ class FrameAttention(_AttentionBase):
 
 class VideoAttention(_AttentionBase):
     """edm2/attention/attention_modules.py:15-82: DART-masked attention over the clean+noised training sequence,
-    frame-causal prefill, and single-frame decode against the (k, v) cache."""
+    frame-causal prefill, and single-frame decode against the (k, v) cache.
+
+    Training mask.  The default is the mask the reference STATES (TrainingMask / mask_mod, attention_masking.py:8-24; what
+    its CPU / eager path and its own flex==dense test compute).  With fewer than 128 tokens per frame the reference's
+    compiled FlexAttention computes something narrower -- mask_mod AND the 128-token blocks its frame-level block list
+    happens to name (measured on the B200: profiles/r02_ref_gpu_baseline.json).  `reference_block_lists=True`
+    (or ONIRIS_REF_BLOCK_LISTS=1) reproduces exactly that, e.g. to continue training or to evaluate a checkpoint under the
+    arithmetic it was trained with."""
+
+    reference_block_lists = os.environ.get("ONIRIS_REF_BLOCK_LISTS", "0") == "1"
 
     def __init__(self, channels, num_heads, attn_balance=0.3):
         super().__init__(channels, num_heads, attn_balance)
@@ -196,7 +207,7 @@ class VideoAttention(_AttentionBase):
             pos = _frame_positions(0, n, 2 * batch_size, dev)                       # both halves use positions 0..n-1
             q, k, v = _QkvPrepFn.apply(y, cos_t, sin_t, scl_t, pos, pos, m, hw, False)
             shape = (batch_size, 2 * n * hw, m, 64)
-            o = AttentionFn.apply(q.view(shape), k.view(shape), v.view(shape), hw, n, DART)
+            o = AttentionFn.apply(q.view(shape), k.view(shape), v.view(shape), hw, n, DART_LISTED if self.reference_block_lists else DART)
         else:
             t_new = f // batch_size
             t_old = 0 if cache is None else cache[0].shape[2]

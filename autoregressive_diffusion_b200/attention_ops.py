@@ -3,7 +3,7 @@ import torch
 
 from ._lib import _vp, call, stream_ptr
 
-FULL, CAUSAL, DART = 0, 1, 2
+FULL, CAUSAL, DART, DART_LISTED = 0, 1, 2, 3
 
 
 def attn_fwd(q, k, v, hw, n_frames, mask):

@@ -21,7 +21,8 @@ int attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, i
              int n_frames, int mask, float scale, cudaStream_t st) {
   const int BH = B * heads;
   if (BH <= 0 || Lq <= 0 || Lk <= 0) return OB_OK;
-  if (hw <= 0 || mask < ATTN_FULL || mask > ATTN_DART || (mask == ATTN_DART && (n_frames <= 0 || Lq != Lk || Lq != 2 * n_frames * hw)) ||
+  if (mask == ATTN_DART_LISTED && (hw >= 128 || (static_cast<long>(n_frames) * hw) % 128 != 0)) mask = ATTN_DART;  // no regrouping: lists == mask_mod
+  if (hw <= 0 || mask < ATTN_FULL || mask > ATTN_DART_LISTED || (mask >= ATTN_DART && (n_frames <= 0 || Lq != Lk || Lq != 2 * n_frames * hw)) ||
       (mask == ATTN_CAUSAL && Lq != Lk)) {
     set_error("attn_fwd: inconsistent arguments (Lq=%d Lk=%d hw=%d n_frames=%d mask=%d)", Lq, Lk, hw, n_frames, mask);
     return OB_ERR_INVALID;
@@ -51,7 +52,8 @@ int attn_bwd(const void* q, const void* k, const void* v, const void* o, const v
              cudaStream_t st) {
   const int BH = B * heads;
   if (BH <= 0 || Lq <= 0 || Lk <= 0) return OB_OK;
-  if (hw <= 0 || mask < ATTN_FULL || mask > ATTN_DART || (mask == ATTN_DART && (n_frames <= 0 || Lq != Lk || Lq != 2 * n_frames * hw)) ||
+  if (mask == ATTN_DART_LISTED && (hw >= 128 || (static_cast<long>(n_frames) * hw) % 128 != 0)) mask = ATTN_DART;  // no regrouping: lists == mask_mod
+  if (hw <= 0 || mask < ATTN_FULL || mask > ATTN_DART_LISTED || (mask >= ATTN_DART && (n_frames <= 0 || Lq != Lk || Lq != 2 * n_frames * hw)) ||
       (mask == ATTN_CAUSAL && Lq != Lk)) {
     set_error("attn_bwd: inconsistent arguments (Lq=%d Lk=%d hw=%d n_frames=%d mask=%d)", Lq, Lk, hw, n_frames, mask);
     return OB_ERR_INVALID;

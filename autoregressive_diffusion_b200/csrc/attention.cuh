@@ -17,7 +17,7 @@
 
 namespace ob {
 
-enum : int { ATTN_FULL = 0, ATTN_CAUSAL = 1, ATTN_DART = 2 };
+enum : int { ATTN_FULL = 0, ATTN_CAUSAL = 1, ATTN_DART = 2, ATTN_DART_LISTED = 3 };
 
 constexpr int ATTN_BM = 128;  // query rows per CTA
 constexpr int ATTN_BN = 128;  // key rows per step
@@ -42,6 +42,16 @@ __device__ __forceinline__ bool frame_visible(int mask, int n, int qf, int kf) {
   // DART (attention_masking.py:15-24): clean->clean causal, noised->strictly earlier clean, noised->itself
   if (qf < n) return kf <= qf;
   return (kf < qf - n) || (kf == qf);
+}
+
+// ATTN_DART_LISTED: what COMPILED FlexAttention computes for make_train_mask when a frame has fewer than 128 tokens
+// (attention_masking.py:32-53; measured on the B200, profiles/r02_ref_gpu_baseline.json): the frames are regrouped into
+// 128-token blocks, the FRAME-level block list is reused for them, and the kernel only visits listed blocks, so the
+// effective mask is mask_mod AND listed(block(q), block(k)).  A noised query in block i of its half is listed the clean
+// blocks < i and its own block; clean queries lose nothing (frame-causal implies block-causal).  n_hw = tokens per half.
+__device__ __forceinline__ bool block_listed(int n_hw, int iq, int ik) {
+  if (iq < n_hw) return true;
+  return ik < n_hw ? (ik >> 7) < ((iq - n_hw) >> 7) : (ik >> 7) == (iq >> 7);
 }
 
 // KV tiles a query tile must visit: [0, n1) and [s2, e2) (tile indices, second range may be empty).
@@ -98,7 +108,7 @@ constexpr int ATTN_THREADS = 64 + 32 * ATTN_SOFTMAX_WARPS;
 // one against the frame rule (only for tiles that straddle a mask edge).
 template <bool MASKED>
 __device__ __forceinline__ float softmax_chunk(const float (&s)[32], uint32_t (&packed)[16], float c1, float c2, int mask,
-                                               int n_frames, int qf, int ik0, int Lk, int hw) {
+                                               int n_frames, int qf, int ik0, int Lk, int hw, int iq) {
   float sum = 0.f;
   int kf = 0, rem = 0;
   if (MASKED) { kf = ik0 / hw; rem = ik0 - kf * hw; }
@@ -109,7 +119,8 @@ __device__ __forceinline__ float softmax_chunk(const float (&s)[32], uint32_t (&
     for (int u = 0; u < 2; ++u) {
       float e = fast_exp2(s[i + u] * c1 - c2);
       if (MASKED) {
-        const bool ok = (ik0 + i + u < Lk) && frame_visible(mask, n_frames, qf, kf);
+        bool ok = (ik0 + i + u < Lk) && frame_visible(mask, n_frames, qf, kf);
+        if (mask == ATTN_DART_LISTED) ok = ok && block_listed(n_frames * hw, iq, ik0 + i + u);
         if (++rem == hw) { rem = 0; ++kf; }
         e = ok ? e : 0.f;
       }
@@ -250,6 +261,8 @@ __global__ void __launch_bounds__(ATTN_THREADS, 1) attn_fwd_kernel(const __grid_
         if (p.mask == ATTN_CAUSAL) all_vis = all_vis && (kf_b <= qf);
         else if (p.mask == ATTN_DART)
           all_vis = all_vis && ((qf < p.n_frames) ? (kf_b <= qf) : ((kf_b < qf - p.n_frames) || (kf_a == qf && kf_b == qf)));
+        else if (p.mask == ATTN_DART_LISTED)
+          all_vis = all_vis && (qf < p.n_frames) && (kf_b <= qf);      // noised rows: per-element test (block list)
       }
       mbar_wait(s_full(b), (j >> 1) & 1);
       tc_fence_after();
@@ -265,11 +278,11 @@ __global__ void __launch_bounds__(ATTN_THREADS, 1) attn_fwd_kernel(const __grid_
       uint32_t pk0[16], pk1[16];
       const int ik0 = k0 + half * 64;
       if (all_vis) {
-        l += softmax_chunk<false>(s0, pk0, c1, c2, p.mask, p.n_frames, qf, ik0, p.Lk, p.hw);
-        l += softmax_chunk<false>(s1, pk1, c1, c2, p.mask, p.n_frames, qf, ik0 + 32, p.Lk, p.hw);
+        l += softmax_chunk<false>(s0, pk0, c1, c2, p.mask, p.n_frames, qf, ik0, p.Lk, p.hw, iq);
+        l += softmax_chunk<false>(s1, pk1, c1, c2, p.mask, p.n_frames, qf, ik0 + 32, p.Lk, p.hw, iq);
       } else {
-        l += softmax_chunk<true>(s0, pk0, c1, c2, p.mask, p.n_frames, qf, ik0, p.Lk, p.hw);
-        l += softmax_chunk<true>(s1, pk1, c1, c2, p.mask, p.n_frames, qf, ik0 + 32, p.Lk, p.hw);
+        l += softmax_chunk<true>(s0, pk0, c1, c2, p.mask, p.n_frames, qf, ik0, p.Lk, p.hw, iq);
+        l += softmax_chunk<true>(s1, pk1, c1, c2, p.mask, p.n_frames, qf, ik0 + 32, p.Lk, p.hw, iq);
       }
       const uint32_t row_base = sPb + r * 128;
 #pragma unroll

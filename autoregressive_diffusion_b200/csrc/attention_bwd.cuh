@@ -147,7 +147,7 @@ __device__ __forceinline__ void store_row_chunk(uint32_t tile_base, int r, int c
 template <bool MASKED>
 __device__ __forceinline__ void ds_chunk_row(const float (&s)[32], const float (&dp)[32], uint32_t (&packed)[16], float c1,
                                              float lse2, float dsum, float scale, int mask, int n_frames, int qf, int ik0,
-                                             int Lk, int hw) {
+                                             int Lk, int hw, int iq) {
   int kf = 0, rem = 0;
   if (MASKED) { kf = ik0 / hw; rem = ik0 - kf * hw; }
 #pragma unroll
@@ -157,7 +157,8 @@ __device__ __forceinline__ void ds_chunk_row(const float (&s)[32], const float (
     for (int u = 0; u < 2; ++u) {
       float pr = fast_exp2(s[i + u] * c1 - lse2);
       if (MASKED) {
-        const bool ok = (ik0 + i + u < Lk) && frame_visible(mask, n_frames, qf, kf);
+        bool ok = (ik0 + i + u < Lk) && frame_visible(mask, n_frames, qf, kf);
+        if (mask == ATTN_DART_LISTED) ok = ok && block_listed(n_frames * hw, iq, ik0 + i + u);
         if (++rem == hw) { rem = 0; ++kf; }
         pr = ok ? pr : 0.f;
       }
@@ -171,7 +172,7 @@ __device__ __forceinline__ void ds_chunk_row(const float (&s)[32], const float (
 template <bool MASKED>
 __device__ __forceinline__ void pds_chunk_col(const float (&s)[32], const float (&dp)[32], uint32_t (&pk_p)[16],
                                               uint32_t (&pk_ds)[16], float c1, float scale, uint32_t stat_lse,
-                                              uint32_t stat_d, int mask, int n_frames, int kf, int iq0, int Lq, int hw) {
+                                              uint32_t stat_d, int mask, int n_frames, int kf, int iq0, int Lq, int hw, int ik) {
   int qf = 0, rem = 0;
   if (MASKED) { qf = iq0 / hw; rem = iq0 - qf * hw; }
 #pragma unroll
@@ -184,7 +185,8 @@ __device__ __forceinline__ void pds_chunk_col(const float (&s)[32], const float 
     for (int u = 0; u < 4; ++u) {
       float pr = fast_exp2(s[i + u] * c1 - l4[u]);
       if (MASKED) {
-        const bool ok = (iq0 + i + u < Lq) && frame_visible(mask, n_frames, qf, kf);
+        bool ok = (iq0 + i + u < Lq) && frame_visible(mask, n_frames, qf, kf);
+        if (mask == ATTN_DART_LISTED) ok = ok && block_listed(n_frames * hw, iq0 + i + u, ik);
         if (++rem == hw) { rem = 0; ++qf; }
         pr = ok ? pr : 0.f;
       }
@@ -337,9 +339,10 @@ __global__ void __launch_bounds__(ABW_THREADS, 1) attn_bwd_dq_kernel(const __gri
         if (p.mask == ATTN_CAUSAL) all_vis = all_vis && (kf_b <= qf);
         else if (p.mask == ATTN_DART)
           all_vis = all_vis && ((qf < p.n_frames) ? (kf_b <= qf) : ((kf_b < qf - p.n_frames) || (kf_a == qf && kf_b == qf)));
+        else if (p.mask == ATTN_DART_LISTED) all_vis = all_vis && (qf < p.n_frames) && (kf_b <= qf);
       }
-      if (all_vis) ds_chunk_row<false>(s, dp, packed, c1, lse2, dsum, p.scale, p.mask, p.n_frames, qf, ik0, p.Lk, p.hw);
-      else if (iq < p.Lq) ds_chunk_row<true>(s, dp, packed, c1, lse2, dsum, p.scale, p.mask, p.n_frames, qf, ik0, p.Lk, p.hw);
+      if (all_vis) ds_chunk_row<false>(s, dp, packed, c1, lse2, dsum, p.scale, p.mask, p.n_frames, qf, ik0, p.Lk, p.hw, iq);
+      else if (iq < p.Lq) ds_chunk_row<true>(s, dp, packed, c1, lse2, dsum, p.scale, p.mask, p.n_frames, qf, ik0, p.Lk, p.hw, iq);
       else {
 #pragma unroll
         for (int i = 0; i < 16; ++i) packed[i] = 0u;
@@ -522,11 +525,13 @@ __global__ void __launch_bounds__(ABW_THREADS, 1) attn_bwd_dkv_kernel(const __gr
         else if (p.mask == ATTN_DART) {
           if (kf < n) all_vis = all_vis && ((qf_b < n && kf <= qf_a) || (qf_a >= n && kf < qf_a - n));
           else all_vis = all_vis && (qf_a == kf && qf_b == kf);
+        } else if (p.mask == ATTN_DART_LISTED) {
+          all_vis = all_vis && (kf < n) && (qf_b < n) && (kf <= qf_a);   // clean x clean only; the rest is tested per element
         }
       }
       const uint32_t st_l = sStat + (b * 128 + half * 32) * 4, st_d = sStat + (b * 128 + 64 + half * 32) * 4;
-      if (all_vis) pds_chunk_col<false>(s, dp, pk_p, pk_ds, c1, p.scale, st_l, st_d, p.mask, p.n_frames, kf, iq0, p.Lq, p.hw);
-      else if (ik < p.Lk) pds_chunk_col<true>(s, dp, pk_p, pk_ds, c1, p.scale, st_l, st_d, p.mask, p.n_frames, kf, iq0, p.Lq, p.hw);
+      if (all_vis) pds_chunk_col<false>(s, dp, pk_p, pk_ds, c1, p.scale, st_l, st_d, p.mask, p.n_frames, kf, iq0, p.Lq, p.hw, ik);
+      else if (ik < p.Lk) pds_chunk_col<true>(s, dp, pk_p, pk_ds, c1, p.scale, st_l, st_d, p.mask, p.n_frames, kf, iq0, p.Lq, p.hw, ik);
       else {
 #pragma unroll
         for (int i = 0; i < 16; ++i) { pk_p[i] = 0u; pk_ds[i] = 0u; }

@@ -193,6 +193,10 @@ int ob_sumsq(const float* g, int64_t n, float* out, void* stream);
 #define OB_ATTN_FULL 0
 #define OB_ATTN_CAUSAL 1
 #define OB_ATTN_DART 2
+/* OB_ATTN_DART_LISTED: TrainingMask AND the 128-token blocks make_train_mask lists when hw < 128 (attention_masking.py:32-53)
+ * -- what the reference's compiled FlexAttention actually evaluates on the GPU for small frames (a noised query in block i
+ * of its half sees only clean blocks < i and its own block).  Identical to OB_ATTN_DART when hw >= 128. */
+#define OB_ATTN_DART_LISTED 3
 int ob_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int b, int heads, int lq, int lk, int hw,
                 int n_frames, int mask, float scale, void* stream);
 

@@ -4,6 +4,8 @@ Element-wise relative error is meaningless for tensors that cross zero (SURVEY.m
   max_rel  = max|got - ref| / max|ref|
   mean_rel = mean|got - ref| / rms(ref)
 """
+import os
+
 import torch
 
 MAX_REL = 2e-2
@@ -19,6 +21,11 @@ def errors(got, ref):
 def assert_close(got, ref, name="", max_rel=MAX_REL, mean_rel=MEAN_REL):
     assert got.shape == ref.shape, f"{name}: shape {tuple(got.shape)} vs {tuple(ref.shape)}"
     mx, mn = errors(got, ref)
+    report = os.environ.get("ONIRIS_PARITY_REPORT")
+    if report:     # evidence file: every comparison a test run made, with its measured errors and budget
+        test = os.environ.get("PYTEST_CURRENT_TEST", "").split(" ")[0]
+        with open(report, "a") as f:
+            f.write(f"{test}\t{name}\tmax_rel={mx:.3e}\tmean_rel={mn:.3e}\tbudget={max_rel:g}/{mean_rel:g}\n")
     assert mx <= max_rel and mn <= mean_rel, f"{name}: max_rel={mx:.3e} (<= {max_rel}) mean_rel={mn:.3e} (<= {mean_rel})"
     return mx, mn
 
