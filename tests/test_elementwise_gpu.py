@@ -179,8 +179,9 @@ def test_qkv_prep_eval_and_rope_k(B, t_old, t_new, heads, res):
     yg = y.cuda().to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
     q, k, v, k_raw = A._QkvPrepFn.apply(yg, cos_t, sin_t, scl_t, pos_new, pos_new, heads, hw, True)
     qo, ko_raw, vo = O._split_qkv(y, heads, B)                                   # [b, m, t_new, hw, 64]
-    old_k = O.normalize(bf16r(torch.randn(B, heads, t_old, hw, 64)), dims=(-1,))
-    k_all = torch.cat((old_k, ko_raw), dim=2)
+    k_all = ko_raw
+    if t_old > 0:
+        k_all = torch.cat((O.normalize(bf16r(torch.randn(B, heads, t_old, hw, 64)), dims=(-1,)), ko_raw), dim=2)
     qo_r, ko_r = O.rope(qo, k_all, *O.rope_buffers(64), False)
     assert_close(q.float(), _token_major(qo_r, B), "q")
     assert_close(k.float(), _token_major(ko_r.reshape(B, heads, t_all, hw, 64)[:, :, t_old:].reshape(B, heads, -1, 64), B), "k")
