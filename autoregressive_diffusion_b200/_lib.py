@@ -39,7 +39,7 @@ _SIGS = {
     "ob_conv_wgrad_splits": "iiiiiiiii",
     "ob_conv_wgrad": "pppppiiiiiiiiiip",
     "ob_gate_bwd": "pppppppppiiilp",
-    "ob_conv_prologue": "pppiiiliippppppppilp",
+    "ob_conv_prologue": "pppiiiliippppppppilpp",
     "ob_gate_bwd_fused": "ppppppppiiilpppppppppip",
     "ob_gate_fwd": "pppppppiiiip",
     "ob_gate_bwd_params": "pppppppppppppiiiip",
@@ -60,6 +60,9 @@ _SIGS = {
     "ob_qkv_prep_bwd": "ppppppppppliifp",
     "ob_rope_k": "ppppppliip",
     "ob_attn_fwd": "pppppiiiiiiifp",
+    "ob_kv_append": "pppppppppiiiiifp",
+    "ob_dart_attn_decode_splits": "iiii",
+    "ob_dart_attn_decode": "ppppppppiiiiiiifp",
     "ob_attn_bwd": "ppppppppppiiiiiiifp",
 }
 _CT = {"p": ctypes.c_void_p, "i": ctypes.c_int, "f": ctypes.c_float, "l": ctypes.c_int64}

@@ -11,7 +11,7 @@ import torch
 from torch import nn
 
 from . import ops
-from ._lib import _vp, call, stream_ptr
+from ._lib import _vp, call, query, stream_ptr
 import os
 
 from .attention_ops import CAUSAL, DART, DART_LISTED, FULL, AttentionFn
@@ -74,17 +74,23 @@ class RotaryEmbedding(nn.Module):
         self.register_buffer("scale", (torch.arange(0, dim, 2) + 0.4 * dim) / (1.4 * dim))
         self._tables = {}
 
-    def tables(self, seq_len):
-        """fp32 (cos, sin, scale) [seq_len, dim], each rounded through fp16 exactly like RoPe.py:21-32,54."""
-        key = (seq_len, self.inv_freq.device)
+    def tables(self, seq_len, centre=None):
+        """fp32 (cos, sin, scale) [seq_len, dim], each rounded through fp16 exactly like RoPe.py:21-32,54.
+
+        `centre`: the xPos exponent origin; the reference uses seq_len // 2 of the CURRENT sequence (RoPe.py:27), which
+        cancels between q and k -- the paged KV cache fixes it for the lifetime of a cache so stored keys stay valid."""
+        centre = seq_len // 2 if centre is None else centre
+        key = (seq_len, centre, self.inv_freq.device)
         if key not in self._tables:
             t = torch.arange(seq_len, device=self.inv_freq.device).type_as(self.inv_freq)
             ang = torch.outer(t, self.inv_freq)
             ang = torch.cat((ang, ang), dim=-1).to(torch.float16)
-            power = (t - (seq_len // 2)) / self.scale_base
+            power = (t - centre) / self.scale_base
             sc = self.scale ** power[:, None]
             sc = torch.cat((sc, sc), dim=-1).to(torch.float16)
-            self._tables = {key: (ang.cos().float().contiguous(), ang.sin().float().contiguous(), sc.float().contiguous())}
+            if len(self._tables) > 8:
+                self._tables.clear()
+            self._tables[key] = (ang.cos().float().contiguous(), ang.sin().float().contiguous(), sc.float().contiguous())
         return self._tables[key]
 
 
@@ -127,6 +133,102 @@ class _QkvPrepFn(torch.autograd.Function):
         call("ob_qkv_prep_bwd", _vp(qkv), _vp(dq), _vp(dk), _vp(dv), _vp(dqkv), _vp(cos_t), _vp(sin_t), _vp(scl_t), _vp(pos_q),
              _vp(pos_k), f * h * w, heads, hw, 1e-4, stream_ptr())
         return dqkv, None, None, None, None, None, None, None, None
+
+
+class PagedKV:
+    """KV cache of one VideoAttention layer for autoregressive sampling: frame-sized pages in a pool, a page table and
+    per-sequence lengths in DEVICE memory (C ABI: ob_kv_append / ob_dart_attn_decode).
+
+    The reference keeps `(k, v)` tensors [B, heads, T, hw, 64] with un-rotated keys and, on every one of the
+    2*num_steps-1 evaluations per generated frame, clones them, concatenates the new frame and re-rotates every key
+    (attention_modules.py:51-59).  Here a decode evaluation writes the new frame's rotated key / value into the page
+    slot after the committed ones and attends over the pages in place; committing the frame (update_cache=True) is
+    `lengths += 1`.  Because nothing about a launch depends on the host-side length, one CUDA graph serves every
+    generated frame.  The object round-trips through Block.forward's `cache.get('attn')` / assignment like the tuple
+    does, and indexes like it: `cache[0]`, `cache[1]` materialise the reference-layout (un-rotated k, v) tensors.
+    """
+
+    def __init__(self, batch, heads, hw, capacity, device, centre=None):
+        self.batch, self.heads, self.hw, self.capacity = batch, heads, hw, capacity
+        self.centre = capacity // 2 if centre is None else centre
+        n_pages = batch * capacity
+        self.k_pages = torch.zeros((n_pages, hw, heads, 64), dtype=BF16, device=device)
+        self.v_pages = torch.zeros_like(self.k_pages)
+        self.page_table = torch.arange(n_pages, dtype=torch.int32, device=device).reshape(batch, capacity).contiguous()
+        self.lengths = torch.zeros(batch, dtype=torch.int32, device=device)
+        self.n_frames = 0                      # host mirror of lengths (all sequences advance together in the sampler)
+        self.generation = 0                    # bumped when the pool is re-allocated (captured graphs become invalid)
+        self.n_split = query("ob_dart_attn_decode_splits", batch, heads, hw, capacity)
+        self.o_part = self.l_part = None
+        if self.n_split > 1:
+            self.o_part = torch.empty((self.n_split, batch, hw, heads, 64), dtype=torch.float32, device=device)
+            self.l_part = torch.empty((self.n_split, batch * heads, hw), dtype=torch.float32, device=device)
+
+    # ---- writes
+    def store_frames(self, k_rot, v, t0=0):
+        """Fill frames [t0, t0+T) of every sequence from token-major rows [B, T*hw, heads, 64] (prefill / import)."""
+        T = k_rot.shape[1] // self.hw
+        pages = self.page_table[:, t0:t0 + T].reshape(-1).long()
+        self.k_pages.index_copy_(0, pages, k_rot.reshape(self.batch * T, self.hw, self.heads, 64))
+        self.v_pages.index_copy_(0, pages, v.reshape(self.batch * T, self.hw, self.heads, 64))
+
+    def commit(self, n=1):
+        """Make the n frames written after the committed ones part of the cache."""
+        self.lengths += n
+        self.n_frames += n
+
+    def grow(self, capacity):
+        """Re-allocate the pool with a larger capacity (keeps pages, centre and lengths)."""
+        old = PagedKV.__new__(PagedKV)
+        old.__dict__.update(self.__dict__)
+        gen = self.generation
+        self.__init__(self.batch, self.heads, self.hw, capacity, self.k_pages.device, centre=self.centre)
+        pages_old = old.page_table[:, :old.n_frames].reshape(-1).long()
+        pages_new = self.page_table[:, :old.n_frames].reshape(-1).long()
+        self.k_pages[pages_new] = old.k_pages[pages_old]
+        self.v_pages[pages_new] = old.v_pages[pages_old]
+        self.lengths.copy_(old.lengths)
+        self.n_frames, self.generation = old.n_frames, gen + 1
+
+    # ---- reference-format view (cold path: tests, export to the reference's modules)
+    def _gather(self, pool):
+        pages = self.page_table[:, :self.n_frames].reshape(-1).long()
+        return pool[pages].reshape(self.batch, self.n_frames, self.hw, self.heads, 64)
+
+    def reference_kv(self, rope):
+        """(k, v) in the reference layout [B, heads, T, hw, 64] with UN-rotated keys (attention_modules.py:57)."""
+        cos_t, sin_t, scl_t = (t[:self.n_frames, None, None, :] for t in rope.tables(self.capacity, self.centre))
+        k = self._gather(self.k_pages).float() * scl_t
+        half = torch.cat((-k[..., 32:], k[..., :32]), dim=-1)
+        k = k * cos_t - half * sin_t                      # rotation by -theta undoes RoPe.py:57
+        return k.permute(0, 3, 1, 2, 4), self._gather(self.v_pages).float().permute(0, 3, 1, 2, 4)
+
+    @classmethod
+    def from_reference(cls, kv, rope, capacity):
+        """Import a reference-format (k, v) cache (un-rotated keys, any float dtype)."""
+        k, v = kv
+        b, heads, t, hw, _ = k.shape
+        self = cls(b, heads, hw, max(capacity, 2 * t), k.device)
+        cos_t, sin_t, scl_t = (x[:t, None, None, :] for x in rope.tables(self.capacity, self.centre))
+        kt = k.permute(0, 2, 3, 1, 4).float()
+        half = torch.cat((-kt[..., 32:], kt[..., :32]), dim=-1)
+        k_rot = (kt * cos_t + half * sin_t) / scl_t
+        self.store_frames(k_rot.to(BF16).reshape(b, t * hw, heads, 64), v.permute(0, 2, 3, 1, 4).to(BF16).reshape(b, t * hw, heads, 64))
+        self.commit(t)
+        return self
+
+    def bind(self, rope):
+        self._rope = rope
+        return self
+
+    def __len__(self):
+        return 2
+
+    def __getitem__(self, i):
+        return self.reference_kv(self._rope)[i]
+
+    def __iter__(self):
+        return iter(self.reference_kv(self._rope))
 
 
 _POS_CACHE = {}
@@ -184,6 +286,7 @@ class VideoAttention(_AttentionBase):
     arithmetic it was trained with."""
 
     reference_block_lists = os.environ.get("ONIRIS_REF_BLOCK_LISTS", "0") == "1"
+    cache_capacity = 128      # frames per sequence a new PagedKV is allocated for (it doubles when it fills up)
 
     def __init__(self, channels, num_heads, attn_balance=0.3):
         super().__init__(channels, num_heads, attn_balance)
@@ -210,35 +313,40 @@ class VideoAttention(_AttentionBase):
             o = AttentionFn.apply(q.view(shape), k.view(shape), v.view(shape), hw, n, DART_LISTED if self.reference_block_lists else DART)
         else:
             t_new = f // batch_size
-            t_old = 0 if cache is None else cache[0].shape[2]
-            t_all = t_old + t_new
-            cos_t, sin_t, scl_t = self.rope.tables(t_all)
-            pos_new = _frame_positions(t_old, t_all, batch_size, dev)
-            if cache is None:
-                outs = _QkvPrepFn.apply(y, cos_t, sin_t, scl_t, pos_new, pos_new, m, hw, update_cache)
-                q, k, v = outs[:3]
-                k_raw_all = outs[3].view(batch_size, t_all * hw, m, 64) if update_cache else None
-                k_all = k.view(batch_size, t_all * hw, m, 64)
-                v_all = v.view(batch_size, t_all * hw, m, 64)
-            else:
-                # reference cache layout [B, heads, T, hw, 64] (un-rotated keys) -> token-major rows
-                ck = cache[0].permute(0, 2, 3, 1, 4).reshape(batch_size, t_old * hw, m, 64).to(BF16)
-                cv = cache[1].permute(0, 2, 3, 1, 4).reshape(batch_size, t_old * hw, m, 64).to(BF16)
-                q, _, v, k_raw = _QkvPrepFn.apply(y, cos_t, sin_t, scl_t, pos_new, None, m, hw, True)
-                k_raw_all = torch.cat((ck, k_raw.view(batch_size, t_new * hw, m, 64)), dim=1)
-                v_all = torch.cat((cv, v.view(batch_size, t_new * hw, m, 64)), dim=1)
-                k_all = torch.empty_like(k_raw_all)
-                pos_all = _frame_positions(0, t_all, batch_size, dev)
-                call("ob_rope_k", _vp(k_raw_all), _vp(k_all), _vp(cos_t), _vp(sin_t), _vp(scl_t), _vp(pos_all),
-                     batch_size * t_all * hw, m, hw, stream_ptr())
-            if update_cache:
-                cache = (k_raw_all.view(batch_size, t_all, hw, m, 64).permute(0, 3, 1, 2, 4),
-                         v_all.view(batch_size, t_all, hw, m, 64).permute(0, 3, 1, 2, 4))
-            qv = q.view(batch_size, t_new * hw, m, 64)
-            if t_new == 1:
-                o = AttentionFn.apply(qv, k_all, v_all, hw, 0, FULL)       # one new frame sees every cached frame (:69-70)
+            if isinstance(cache, tuple):          # a cache produced by the reference's own modules
+                cache = PagedKV.from_reference(cache, self.rope, self.cache_capacity).bind(self.rope)
+            t_old = 0 if cache is None else cache.n_frames
+            if t_old > 0 and t_new == 1:
+                # one new frame against the paged cache (:69-70): rotated key + value go straight into the next page
+                # slot, attention gathers the pages in place; the frame is committed only when update_cache is set
+                if t_old + 1 > cache.capacity:
+                    cache.grow(2 * cache.capacity)
+                cos_t, sin_t, scl_t = self.rope.tables(cache.capacity, cache.centre)
+                q = torch.empty((batch_size * hw, c), dtype=BF16, device=dev)
+                call("ob_kv_append", _vp(y), _vp(q), _vp(cache.k_pages), _vp(cache.v_pages), _vp(cache.page_table), _vp(cache.lengths),
+                     _vp(cos_t), _vp(sin_t), _vp(scl_t), batch_size, m, hw, cache.capacity, cache.capacity, 1e-4, stream_ptr())
+                o = torch.empty_like(q)
+                call("ob_dart_attn_decode", _vp(q), _vp(cache.k_pages), _vp(cache.v_pages), _vp(cache.page_table), _vp(cache.lengths),
+                     _vp(o), _vp(cache.o_part), _vp(cache.l_part), batch_size, m, hw, cache.capacity, cache.k_pages.shape[0],
+                     cache.n_split, 1, 0.125, stream_ptr())
+                if update_cache:
+                    cache.commit(1)
             elif t_old == 0:
-                o = AttentionFn.apply(qv, k_all, v_all, hw, 0, CAUSAL)     # frame-causal prefill (:72-75)
+                # frame-causal prefill (:72-75); with update_cache the rotated keys / values also fill the cache pages
+                new_cache = None
+                if update_cache:
+                    new_cache = PagedKV(batch_size, m, hw, max(self.cache_capacity, 2 * t_new), dev).bind(self.rope)
+                    cos_t, sin_t, scl_t = (t_[:t_new] for t_ in self.rope.tables(new_cache.capacity, new_cache.centre))
+                else:
+                    cos_t, sin_t, scl_t = self.rope.tables(t_new)
+                pos_new = _frame_positions(0, t_new, batch_size, dev)
+                q, k, v = _QkvPrepFn.apply(y, cos_t, sin_t, scl_t, pos_new, pos_new, m, hw, False)
+                shape = (batch_size, t_new * hw, m, 64)
+                o = AttentionFn.apply(q.view(shape), k.view(shape), v.view(shape), hw, 0, CAUSAL)
+                if update_cache:
+                    new_cache.store_frames(k.view(shape), v.view(shape))
+                    new_cache.commit(t_new)
+                    cache = new_cache
             else:
                 raise NotImplementedError("The inference mask is not implemented for this case")
         o = o.reshape(f, h, w, c).permute(0, 3, 1, 2)

@@ -151,9 +151,12 @@ class MPCausal3DGatedConv(nn.Module):
         n_ctx = cache.get('n_context_frames', 0)
         if update_cache:
             cache['n_context_frames'] = n_ctx + T                       # Gating.forward's second return (conv.py:127)
+        static = cache.get('_static', None)      # decode_state.make_static: fixed buffers + device-side frame count
         pad = cache.get('activations', None)
         pad5 = None
-        if pad is not None:  # reference layout [B, C, 2, H, W] -> NHWC rows [B, 2, H, W, C]
+        if static is not None:
+            pad5 = static['buf']
+        elif pad is not None:  # reference layout [B, C, 2, H, W] -> NHWC rows [B, 2, H, W, C]
             pad5 = pad.permute(0, 2, 3, 4, 1)
             fe = pad5.shape[2] * pad5.shape[3] * cin_pad
             in_place = (pad5.dtype == BF16 and cin_pad == cin and pad5.stride()[1:] == (fe, pad5.shape[3] * cin, cin, 1)
@@ -166,9 +169,15 @@ class MPCausal3DGatedConv(nn.Module):
         gt = self.gating
         want_grad = torch.is_grad_enabled() and (xr.requires_grad or w2.requires_grad or w3.requires_grad)
         y, ctx5 = ops.GatedConvFn.apply(xr, pad5, w2, w3, wg, gt.offset, gt.mult, gt.max_gating, gt.min_gating,
-                                        c_noise.reshape(-1).float().contiguous(), batch_size, S, T, n_ctx, want_grad)
+                                        c_noise.reshape(-1).float().contiguous(), batch_size, S, T,
+                                        0 if static is not None else n_ctx, want_grad,
+                                        static['n_ctx'] if static is not None else None)
         if update_cache:
-            cache['activations'] = ctx5[:, -2:, :, :, :cin].permute(0, 4, 1, 2, 3)
+            if static is not None:     # same storage every frame: captured graphs keep pointing at live data
+                static['buf'].copy_(ctx5[:, -2:])
+                static['n_ctx'] += T
+            else:
+                cache['activations'] = ctx5[:, -2:, :, :, :cin].permute(0, 4, 1, 2, 3)
         return y, cache
 
     @torch.no_grad()

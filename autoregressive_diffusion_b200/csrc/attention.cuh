@@ -33,6 +33,15 @@ struct AttnParams {
   float scale;    // 1/sqrt(64)
   __nv_bfloat16* o;  // [B, Lq, heads, 64]
   float* lse;        // [BH, Lq]
+  // ---- paged decode (attn_fwd_kernel<true>): keys / values live in frame-sized pages of a pool
+  //      [n_pages, hw, heads, 64]; mapK / mapV are 4D maps (64, hw, heads, n_pages) with box (64, box_rows, 1, 1)
+  const int* page_table;   // [B, max_pages] page of frame t of sequence b
+  const int* lengths;      // [B] committed frames per sequence (device side: one CUDA graph serves every decode step)
+  int max_pages, n_pages, box_rows;
+  int extra_frames;        // frames visible beyond lengths[b] (1: the frame being generated sits in slot lengths[b])
+  int n_split;             // split-KV factor (gridDim.z); > 1: partial sums go to o_part / l_part
+  float* o_part;           // [n_split, B, Lq, heads, 64] un-normalised partial outputs
+  float* l_part;           // [n_split, BH, Lq] partial row sums
 };
 
 // Is key frame kf visible from query frame qf?
@@ -61,9 +70,9 @@ struct KvRange {
   __device__ __forceinline__ int tile(int j) const { return j < n1 ? j : s2 + (j - n1); }
 };
 
-__device__ __forceinline__ KvRange kv_range(const AttnParams& p, int q0) {
+__device__ __forceinline__ KvRange kv_range(const AttnParams& p, int q0, int Lk) {
   KvRange r;
-  const int kv_tiles = (p.Lk + ATTN_BN - 1) / ATTN_BN;
+  const int kv_tiles = (Lk + ATTN_BN - 1) / ATTN_BN;
   const int q_last = min(q0 + ATTN_BM, p.Lq) - 1;
   r.s2 = r.e2 = 0;
   if (p.mask == ATTN_FULL) {
@@ -132,6 +141,13 @@ __device__ __forceinline__ float softmax_chunk(const float (&s)[32], uint32_t (&
   return sum;
 }
 
+// PAGED = false: q, k, v are contiguous [B, L, heads, 64] tensors (training, prefill, per-frame attention).
+// PAGED = true : the decode path of the sampler (attention_modules.py:69-70 after the cat with the cache, :51-57): one
+//   frame of queries per sequence against the frames cached in pages + the frame being generated, unmasked.  The key
+//   length comes from device memory, every 128-key tile is gathered page by page through the page table, and
+//   blockIdx.z selects a slice of the key tiles (split-KV).  The softmax uses the fixed maximum ATTN_SMAX, so the
+//   slices' un-normalised outputs and row sums simply ADD (attn_decode_combine_kernel) -- no running-max bookkeeping.
+template <bool PAGED>
 __global__ void __launch_bounds__(ATTN_THREADS, 1) attn_fwd_kernel(const __grid_constant__ AttnParams p) {
   pdl_launch_dependents();
   pdl_wait();
@@ -156,7 +172,17 @@ __global__ void __launch_bounds__(ATTN_THREADS, 1) attn_fwd_kernel(const __grid_
   const int bh = blockIdx.y;
   const int bb = bh / p.heads, hh = bh - bb * p.heads;
   const int q0 = blockIdx.x * ATTN_BM;
-  const KvRange kr = kv_range(p, q0);
+  int Lk = p.Lk;
+  KvRange kr;
+  if constexpr (PAGED) {
+    Lk = (p.lengths[bb] + p.extra_frames) * p.hw;
+    const int kv_tiles = (Lk + ATTN_BN - 1) / ATTN_BN;
+    const int per = (kv_tiles + p.n_split - 1) / p.n_split;
+    const int lo = min(kv_tiles, static_cast<int>(blockIdx.z) * per), hi = min(kv_tiles, lo + per);
+    kr.n1 = 0; kr.s2 = lo; kr.e2 = hi;        // this slice's tiles: [lo, hi)
+  } else {
+    kr = kv_range(p, q0, Lk);
+  }
   const int n_kv = kr.count();
 
   if (threadIdx.x == 0) {
@@ -192,8 +218,20 @@ __global__ void __launch_bounds__(ATTN_THREADS, 1) attn_fwd_kernel(const __grid_
         const uint32_t sK = sKV + st * 2 * ATTN_TILE_BYTES, sV = sK + ATTN_TILE_BYTES;
         mbar_arrive_expect_tx(kv_full(st), 2 * ATTN_TILE_BYTES);
         const int k0 = kr.tile(j) * ATTN_BN;
-        tma_load_4d(sK, &p.mapK, kv_full(st), 0, k0, hh, bb);
-        tma_load_4d(sV, &p.mapV, kv_full(st), 0, k0, hh, bb);
+        if constexpr (PAGED) {
+          // gather the tile page by page; frames past the sequence's length read page n_pages, which is out of bounds for
+          // the tensor map: TMA zero-fills it (and still delivers the bytes the barrier expects)
+          const int* table = p.page_table + static_cast<long>(bb) * p.max_pages;
+          for (int r0 = 0; r0 < ATTN_BN; r0 += p.box_rows) {
+            const int tok = k0 + r0, fr = tok / p.hw, within = tok - fr * p.hw;
+            const int page = (tok < Lk && fr < p.max_pages) ? table[fr] : p.n_pages;
+            tma_load_4d(sK + r0 * 128, &p.mapK, kv_full(st), 0, within, hh, page);
+            tma_load_4d(sV + r0 * 128, &p.mapV, kv_full(st), 0, within, hh, page);
+          }
+        } else {
+          tma_load_4d(sK, &p.mapK, kv_full(st), 0, k0, hh, bb);
+          tma_load_4d(sV, &p.mapV, kv_full(st), 0, k0, hh, bb);
+        }
       }
       __syncwarp();
     }
@@ -257,7 +295,7 @@ __global__ void __launch_bounds__(ATTN_THREADS, 1) attn_fwd_kernel(const __grid_
       bool all_vis;
       {
         const int kf_a = k0 / p.hw, kf_b = (k0 + ATTN_BN - 1) / p.hw;
-        all_vis = (k0 + ATTN_BN <= p.Lk);
+        all_vis = (k0 + ATTN_BN <= Lk);
         if (p.mask == ATTN_CAUSAL) all_vis = all_vis && (kf_b <= qf);
         else if (p.mask == ATTN_DART)
           all_vis = all_vis && ((qf < p.n_frames) ? (kf_b <= qf) : ((kf_b < qf - p.n_frames) || (kf_a == qf && kf_b == qf)));
@@ -278,11 +316,11 @@ __global__ void __launch_bounds__(ATTN_THREADS, 1) attn_fwd_kernel(const __grid_
       uint32_t pk0[16], pk1[16];
       const int ik0 = k0 + half * 64;
       if (all_vis) {
-        l += softmax_chunk<false>(s0, pk0, c1, c2, p.mask, p.n_frames, qf, ik0, p.Lk, p.hw, iq);
-        l += softmax_chunk<false>(s1, pk1, c1, c2, p.mask, p.n_frames, qf, ik0 + 32, p.Lk, p.hw, iq);
+        l += softmax_chunk<false>(s0, pk0, c1, c2, p.mask, p.n_frames, qf, ik0, Lk, p.hw, iq);
+        l += softmax_chunk<false>(s1, pk1, c1, c2, p.mask, p.n_frames, qf, ik0 + 32, Lk, p.hw, iq);
       } else {
-        l += softmax_chunk<true>(s0, pk0, c1, c2, p.mask, p.n_frames, qf, ik0, p.Lk, p.hw, iq);
-        l += softmax_chunk<true>(s1, pk1, c1, c2, p.mask, p.n_frames, qf, ik0 + 32, p.Lk, p.hw, iq);
+        l += softmax_chunk<true>(s0, pk0, c1, c2, p.mask, p.n_frames, qf, ik0, Lk, p.hw, iq);
+        l += softmax_chunk<true>(s1, pk1, c1, c2, p.mask, p.n_frames, qf, ik0 + 32, Lk, p.hw, iq);
       }
       const uint32_t row_base = sPb + r * 128;
 #pragma unroll
@@ -315,6 +353,15 @@ __global__ void __launch_bounds__(ATTN_THREADS, 1) attn_fwd_kernel(const __grid_
 #pragma unroll
       for (int i = 0; i < 32; ++i) o[i] = 0.f;
     }
+    if (PAGED && p.n_split > 1) {
+      // split-KV: un-normalised partial output and row sum of this key slice (an empty slice contributes zeros)
+      if (iq < p.Lq) {
+        float* prow = p.o_part + (((static_cast<long>(blockIdx.z) * (p.BH / p.heads) + bb) * p.Lq + iq) * p.heads + hh) * ATTN_D + half * 32;
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(prow + i) = make_float4(o[i], o[i + 1], o[i + 2], o[i + 3]);
+        if (half == 0) p.l_part[(static_cast<long>(blockIdx.z) * p.BH + bh) * p.Lq + iq] = l;
+      }
+    } else
     if (iq < p.Lq) {
 #pragma unroll
       for (int i = 0; i < 32; i += 8)
@@ -327,6 +374,30 @@ __global__ void __launch_bounds__(ATTN_THREADS, 1) attn_fwd_kernel(const __grid_
   }
   __syncthreads();
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+}
+
+// Sum of the split-KV slices: o = (sum_s o_part[s]) / (sum_s l_part[s]); one thread per 4 output channels.
+__global__ void __launch_bounds__(256) attn_decode_combine_kernel(const float* __restrict__ o_part, const float* __restrict__ l_part,
+                                                                  __nv_bfloat16* __restrict__ o, int n_split, int B, int Lq,
+                                                                  int heads) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long vec = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long total = static_cast<long>(B) * Lq * heads * (ATTN_D / 4);
+  if (vec >= total) return;
+  const long row = vec / (ATTN_D / 4);                 // (b, iq, head)
+  const int hh = static_cast<int>(row % heads);
+  const long bq = row / heads;
+  const int iq = static_cast<int>(bq % Lq), bb = static_cast<int>(bq / Lq);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  float l = 0.f;
+  for (int s = 0; s < n_split; ++s) {
+    const float4 v = *reinterpret_cast<const float4*>(o_part + (static_cast<long>(s) * B * Lq * heads * (ATTN_D / 4) + vec) * 4);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    l += l_part[(static_cast<long>(s) * B * heads + bb * heads + hh) * Lq + iq];
+  }
+  const float inv = l > 0.f ? 1.f / l : 0.f;
+  *reinterpret_cast<uint2*>(o + vec * 4) = make_uint2(pack_bf16x2(acc.x * inv, acc.y * inv), pack_bf16x2(acc.z * inv, acc.w * inv));
 }
 
 }  // namespace ob

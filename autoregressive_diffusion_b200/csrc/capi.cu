@@ -18,6 +18,10 @@ int attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, i
 int attn_bwd(const void* q, const void* k, const void* v, const void* o, const void* dout, const float* lse, float* dsum,
              void* dq, void* dk, void* dv, int B, int heads, int Lq, int Lk, int hw, int n_frames, int mask, float scale,
              cudaStream_t st);
+int attn_decode_splits(int B, int heads, int hw, int max_pages);
+int attn_decode(const void* q, const void* k_pages, const void* v_pages, const int* page_table, const int* lengths, void* o,
+                float* o_part, float* l_part, int B, int heads, int hw, int max_pages, int n_pages, int n_split,
+                int extra_frames, float scale, cudaStream_t st);
 }
 
 // A column of vertical taps at horizontal shift dx.  `flip` mirrors the kernel (input-gradient passes): the tap applied
@@ -187,9 +191,10 @@ int ob_gate_bwd_fused(const void* dy, const void* y, const void* d, const float*
 int ob_conv_prologue(const void* x, const void* pad, void* ctx, int b, int S, int T, int64_t frame_elems, int cin,
                      int cin_pad, const float* offset, const float* mult, const float* max_gating, const float* min_gating,
                      const float* c_noise, float* alpha, float* beta, float* scratch, int n_ctx, int64_t pad_batch_stride,
-                     void* stream) {
+                     const int* n_ctx_dev, void* stream) {
   return conv_prologue(x, pad, ctx, b, S, T, (long)frame_elems, cin, cin_pad, offset, mult, max_gating, min_gating, c_noise,
-                       alpha, beta, scratch, scratch ? 2 * b * S * T + 1 : 0, n_ctx, (long)pad_batch_stride, (cudaStream_t)stream);
+                       alpha, beta, scratch, scratch ? 2 * b * S * T + 1 : 0, n_ctx, (long)pad_batch_stride, n_ctx_dev,
+                       (cudaStream_t)stream);
 }
 int ob_gate_fwd(const float* offset, const float* mult, const float* max_gating, const float* min_gating,
                 const float* c_noise, float* alpha, float* beta, int frames, int T, int half, int n_ctx, void* stream) {
@@ -252,6 +257,20 @@ int ob_sumsq(const float* g, int64_t n, float* out, void* stream) { return sumsq
 int ob_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int b, int heads, int lq, int lk, int hw,
                 int n_frames, int mask, float scale, void* stream) {
   return attn_fwd(q, k, v, o, lse, b, heads, lq, lk, hw, n_frames, mask, scale, (cudaStream_t)stream);
+}
+
+int ob_kv_append(const void* qkv, void* q, void* k_pages, void* v_pages, const int* page_table, const int* lengths,
+                 const float* cos_t, const float* sin_t, const float* scl_t, int b, int heads, int hw, int max_pages, int n_pos,
+                 float eps, void* stream) {
+  return kv_append(qkv, q, k_pages, v_pages, page_table, lengths, cos_t, sin_t, scl_t, b, heads, hw, max_pages, n_pos, eps,
+                   (cudaStream_t)stream);
+}
+int ob_dart_attn_decode_splits(int b, int heads, int hw, int max_pages) { return attn_decode_splits(b, heads, hw, max_pages); }
+int ob_dart_attn_decode(const void* q, const void* k_pages, const void* v_pages, const int* page_table, const int* lengths,
+                        void* o, float* o_part, float* l_part, int b, int heads, int hw, int max_pages, int n_pages,
+                        int n_split, int extra_frames, float scale, void* stream) {
+  return attn_decode(q, k_pages, v_pages, page_table, lengths, o, o_part, l_part, b, heads, hw, max_pages, n_pages, n_split,
+                     extra_frames, scale, (cudaStream_t)stream);
 }
 
 int ob_attn_bwd(const void* q, const void* k, const void* v, const void* o, const void* dout, const float* lse,

@@ -16,7 +16,8 @@ int gate_bwd(const void* dy, const void* y, const void* d, const float* alpha, c
              float* g_min, unsigned* counter, int n_ctx, cudaStream_t st);
 int conv_prologue(const void* x, const void* pad, void* ctx, int B, int S, int T, long frame_elems, int cin, int cin_pad,
                   const float* offset, const float* mult, const float* max_g, const float* min_g, const float* c_noise,
-                  float* alpha, float* beta, float* scratch, int scratch_n, int n_ctx, long pad_bstride, cudaStream_t st);
+                  float* alpha, float* beta, float* scratch, int scratch_n, int n_ctx, long pad_bstride, const int* n_ctx_dev,
+                  cudaStream_t st);
 int gate_fwd(const float* offset, const float* mult, const float* max_g, const float* min_g, const float* c_noise,
              float* alpha, float* beta, int frames, int T, int half, int n_ctx, cudaStream_t st);
 int gate_bwd_params(const float* offset, const float* mult, const float* max_g, const float* min_g, const float* c_noise,
@@ -44,6 +45,9 @@ int qkv_prep_fwd(const void* qkv, void* q, void* k, void* v, void* k_raw, const 
 int qkv_prep_bwd(const void* qkv, const void* dq, const void* dk, const void* dv, void* dqkv, const float* cosT,
                  const float* sinT, const float* sclT, const int* pos_q, const int* pos_k, long rows, int heads, int hw,
                  float eps, cudaStream_t st);
+int kv_append(const void* qkv, void* q, void* k_pages, void* v_pages, const int* page_table, const int* lengths,
+              const float* cosT, const float* sinT, const float* sclT, int B, int heads, int hw, int max_pages, int n_pos,
+              float eps, cudaStream_t st);
 int rope_k(const void* x, void* y, const float* cosT, const float* sinT, const float* sclT, const int* pos, long rows,
            int heads, int hw, cudaStream_t st);
 }  // namespace ob

@@ -475,10 +475,12 @@ __global__ void __launch_bounds__(256) conv_prologue_kernel(const __nv_bfloat16*
                                                             const float* __restrict__ max_g, const float* __restrict__ min_g,
                                                             const float* __restrict__ c_noise, float* __restrict__ alpha,
                                                             float* __restrict__ beta, float* __restrict__ scratch,
-                                                            int scratch_n, int frames, int n_ctx, long pad_bstride) {
+                                                            int scratch_n, int frames, int n_ctx, long pad_bstride,
+                                                            const int* __restrict__ n_ctx_dev) {
   pdl_launch_dependents();
   pdl_wait();
   if (blockIdx.x == gridDim.x - 1) {
+    if (n_ctx_dev != nullptr) n_ctx += n_ctx_dev[0];   // context frames counted on the device (graph-replayed decode)
     const float lo = 1.f / (1.f + expf(-min_g[0])), hi = 1.f / (1.f + expf(-max_g[0]));
     const int Trow = S * T;
     for (int f = threadIdx.x; f < frames; f += blockDim.x) {
@@ -828,7 +830,8 @@ int ctx_build(const void* x, const void* pad, void* ctx, int B, int S, int T, lo
 
 int conv_prologue(const void* x, const void* pad, void* ctx, int B, int S, int T, long frame_elems, int cin, int cin_pad,
                   const float* offset, const float* mult, const float* max_g, const float* min_g, const float* c_noise,
-                  float* alpha, float* beta, float* scratch, int scratch_n, int n_ctx, long pad_bstride, cudaStream_t st) {
+                  float* alpha, float* beta, float* scratch, int scratch_n, int n_ctx, long pad_bstride, const int* n_ctx_dev,
+                  cudaStream_t st) {
   if (frame_elems % 8 != 0 || cin_pad % 8 != 0) { set_error("conv_prologue: frame size must be a multiple of 8"); return OB_ERR_INVALID; }
   if (pad_bstride == 0) pad_bstride = 2 * frame_elems;
   if (pad_bstride % 8 != 0 || pad_bstride < 2 * frame_elems) { set_error("conv_prologue: bad pad batch stride %ld", pad_bstride); return OB_ERR_INVALID; }
@@ -838,7 +841,7 @@ int conv_prologue(const void* x, const void* pad, void* ctx, int B, int S, int T
   launch(conv_prologue_kernel, blocks, 256, 0, st, 1, static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(pad),
                                                static_cast<__nv_bfloat16*>(ctx), S, T, frame_elems, cin, cin_pad, total_vec,
                                                offset, mult, max_g, min_g, c_noise, alpha, beta, scratch, scratch_n,
-                                               B * S * T, n_ctx, pad_bstride);
+                                               B * S * T, n_ctx, pad_bstride, n_ctx_dev);
   return check_launch("conv_prologue");
 }
 

@@ -82,6 +82,46 @@ __global__ void __launch_bounds__(256) qkv_prep_fwd_kernel(const __nv_bfloat16* 
   st_bf2(k + dst, kv.x, kv.y);
 }
 
+// Decode-step flavour of the above (one new frame per sequence): the frame's position is the sequence's cached length,
+// read from DEVICE memory, and the rotated key + the value are written straight into the frame-sized page the page table
+// names for that position (in place; nothing is concatenated or copied -- attention_modules.py:51-57 clones and cats the
+// whole cache every evaluation).  Keys are stored ALREADY rotated with a fixed xPos centre (the tables' centre): the
+// centre cancels in q.k, so cached pages never have to be re-rotated when the sequence grows.
+__global__ void __launch_bounds__(256) kv_append_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ q,
+                                                        __nv_bfloat16* __restrict__ k_pages, __nv_bfloat16* __restrict__ v_pages,
+                                                        const int* __restrict__ page_table, const int* __restrict__ lengths,
+                                                        const float* __restrict__ cosT, const float* __restrict__ sinT,
+                                                        const float* __restrict__ sclT, long rows, int heads, int hw,
+                                                        int max_pages, int n_pos, float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int lane = threadIdx.x & 31;
+  const long wid = (static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (wid >= rows * heads) return;
+  const long row = wid / heads;
+  const int m = static_cast<int>(wid - row * heads);
+  const __nv_bfloat16* src = qkv + (row * heads + m) * 192 + lane * 6;
+  const float2 e0 = ld_bf2(src), e1 = ld_bf2(src + 2), e2 = ld_bf2(src + 4);
+  float2 qv = make_float2(e0.x, e1.y), kv = make_float2(e0.y, e2.x), vv = make_float2(e1.x, e2.y);
+  const float iq = 1.f / (eps + sqrtf(wsum(qv.x * qv.x + qv.y * qv.y) * (1.f / 64.f)));
+  const float ik = 1.f / (eps + sqrtf(wsum(kv.x * kv.x + kv.y * kv.y) * (1.f / 64.f)));
+  const float iv = 1.f / (eps + sqrtf(wsum(vv.x * vv.x + vv.y * vv.y) * (1.f / 64.f)));
+  qv.x *= iq; qv.y *= iq; kv.x *= ik; kv.y *= ik; vv.x *= iv; vv.y *= iv;
+  const int b = static_cast<int>(row / hw), within = static_cast<int>(row - static_cast<long>(b) * hw);
+  int pos = lengths[b];
+  if (pos >= max_pages) pos = max_pages - 1;          // the host grows the pool before this can happen; never write out of bounds
+  const int tp = pos < n_pos ? pos : n_pos - 1;
+  const long page = page_table[static_cast<long>(b) * max_pages + pos];
+  const float2 qr = rot_half(qv, lane), kr = rot_half(kv, lane);
+  const float2 c = *reinterpret_cast<const float2*>(cosT + tp * 64 + lane * 2);
+  const float2 s = *reinterpret_cast<const float2*>(sinT + tp * 64 + lane * 2);
+  const float2 f = *reinterpret_cast<const float2*>(sclT + tp * 64 + lane * 2);
+  st_bf2(q + (row * heads + m) * 64 + lane * 2, (qv.x * c.x + qr.x * s.x) * f.x, (qv.y * c.y + qr.y * s.y) * f.y);
+  const long dst = ((page * hw + within) * heads + m) * 64 + lane * 2;
+  st_bf2(k_pages + dst, (kv.x * c.x + kr.x * s.x) / f.x, (kv.y * c.y + kr.y * s.y) / f.y);
+  st_bf2(v_pages + dst, vv.x, vv.y);
+}
+
 // Backward: undo the rotary on the incoming gradients, then the RMS-norm backward, then re-interleave.
 //   y = rope(n)*f  =>  dn = f*(dy*cos - rot(dy)*sin);   n = x/d, d = eps+rms  =>  dx = dn/d - n*<dn,n>/(64*rms)
 __global__ void __launch_bounds__(256) qkv_prep_bwd_kernel(const __nv_bfloat16* __restrict__ qkv,
@@ -181,6 +221,17 @@ int qkv_prep_bwd(const void* qkv, const void* dq, const void* dk, const void* dv
       static_cast<const __nv_bfloat16*>(dv), static_cast<__nv_bfloat16*>(dqkv), cosT, sinT, sclT, pos_q, pos_k, rows, heads,
       hw, eps);
   return chk("qkv_prep_bwd");
+}
+int kv_append(const void* qkv, void* q, void* k_pages, void* v_pages, const int* page_table, const int* lengths,
+              const float* cosT, const float* sinT, const float* sclT, int B, int heads, int hw, int max_pages, int n_pos,
+              float eps, cudaStream_t st) {
+  if (B <= 0 || heads <= 0) return OB_OK;
+  if (hw <= 0 || max_pages <= 0 || n_pos <= 0) { set_error("kv_append: bad sizes hw=%d max_pages=%d n_pos=%d", hw, max_pages, n_pos); return OB_ERR_INVALID; }
+  const long rows = static_cast<long>(B) * hw, warps = rows * heads;
+  launch(kv_append_kernel, (warps * 32 + 255) / 256, 256, 0, st, 1, static_cast<const __nv_bfloat16*>(qkv),
+         static_cast<__nv_bfloat16*>(q), static_cast<__nv_bfloat16*>(k_pages), static_cast<__nv_bfloat16*>(v_pages), page_table,
+         lengths, cosT, sinT, sclT, rows, heads, hw, max_pages, n_pos, eps);
+  return chk("kv_append");
 }
 int rope_k(const void* x, void* y, const float* cosT, const float* sinT, const float* sclT, const int* pos, long rows,
            int heads, int hw, cudaStream_t st) {

@@ -306,7 +306,7 @@ class GatedConvFn(torch.autograd.Function):
     parameter gradients are accumulated straight into .grad."""
 
     @staticmethod
-    def forward(ctx, x, pad5, w2, w3, wg, g_offset, g_mult, g_max, g_min, c_noise, n_seq, S, T, n_ctx, want_grad):
+    def forward(ctx, x, pad5, w2, w3, wg, g_offset, g_mult, g_max, g_min, c_noise, n_seq, S, T, n_ctx, want_grad, n_ctx_dev=None):
         # pad5: [n_seq, 2, h, w, cin_pad] bf16, dense apart from its batch stride (a slice of the previous context works)
         f, cin_pad, h, wd = x.shape
         cin, cout = w2.shape[1], wg.shape[0]
@@ -317,7 +317,7 @@ class GatedConvFn(torch.autograd.Function):
         cx = torch.empty((n_seq, T + 2, h, wd, cin_pad), dtype=BF16, device=dev)
         call("ob_conv_prologue", _vp(x), _vp(pad5), _vp(cx), n_seq, S, T, h * wd * cin_pad, cin, cin_pad, _vp(g_offset),
              _vp(g_mult), _vp(g_max), _vp(g_min), _vp(c_noise), _vp(alpha), _vp(beta), _vp(scratch), n_ctx,
-             pad5.stride(0) if pad5 is not None else 0, stream_ptr())
+             pad5.stride(0) if pad5 is not None else 0, _vp(n_ctx_dev), stream_ptr())
         out = empty_rows(f, cout, h, wd, dev)
         out_d = empty_rows(f, cout, h, wd, dev, torch.float32) if want_grad else None
         ws = split_workspace(n_seq, S, T, h, wd, cin_pad, cout, 3, 1, dev)
@@ -336,7 +336,7 @@ class GatedConvFn(torch.autograd.Function):
         x, cx, w2, w3, wg, ab, y, d, g_offset, g_mult, g_max, g_min, c_noise, scratch = ctx.saved_tensors
         n_seq, S, T, n_ctx = ctx.dims
         if gy is None:
-            return (None,) * 15
+            return (None,) * 16
         f, cin_pad, h, wd = x.shape
         cout, cin = wg.shape[0], w2.shape[1]
         dev = x.device
@@ -382,8 +382,8 @@ class GatedConvFn(torch.autograd.Function):
             call("ob_conv_dgrad", _vp(gy), _vp(gb), _vp(wg), _vp(alpha), _vp(clean_rows_mask(n_seq, S, T, dev)), _vp(dx),
                  _vp(ws), n_seq, S, T, h, wd, cin_pad, cout, 3, 1, stream_ptr())
         if direct:
-            return (dx,) + (None,) * 14
-        return (dx, None, dw2, dw3, None) + gate_grads + (None,) * 6
+            return (dx,) + (None,) * 15
+        return (dx, None, dw2, dw3, None) + gate_grads + (None,) * 7
 
 
 # ----------------------------------------------------------------------------- elementwise

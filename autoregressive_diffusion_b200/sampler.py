@@ -13,29 +13,56 @@ def sigma_schedule(num_steps, sigma_min, sigma_max, rho, device, dtype=torch.flo
 class _GraphedEval:
     """CUDA-graph replay of the cached one-frame denoiser evaluation.
 
-    Within one generated frame the sampler calls the network 2*num_steps-1 times on identical shapes against an
-    unchanged cache; each call is ~500 tiny launches, i.e. launch-bound.  The second call is captured, the rest are
-    replays with the noisy frame and sigma copied into static buffers.  The cache tensors are baked in by address, so a
-    new graph is captured for every generated frame (the cache objects are replaced when it is updated)."""
+    The sampler calls the network 2*num_steps-1 times per generated frame on identical shapes (edm2/sampler.py:53-75);
+    each call is a few hundred tiny launches, i.e. launch-bound.  With the decode state made static
+    (decode_state.make_static: fixed conv-context buffers, paged KV pools, device-side frame counters) nothing a launch
+    depends on changes from frame to frame, so TWO graphs are captured once per (network, cache) -- "evaluate" and
+    "evaluate and commit the frame to the cache" -- and replayed for every step of every generated frame.  They live
+    on the cache dict, so successive edm_sampler_with_mse calls on the same cache reuse them."""
 
-    def __init__(self, net, conditioning):
-        self.net, self.conditioning = net, conditioning
-        self.graph, self.calls = None, 0
+    def __init__(self, net, cache, conditioning):
+        from .decode_state import cache_generation, make_static
+        make_static(cache)
+        self.net, self.cache = net, cache
+        self.graphs = {}
+        self.generation = cache_generation(cache)
+        self.warm = False
+        b = cache['shape'][0]
+        self.cond = None if conditioning is None else conditioning.clone()
 
-    def __call__(self, x, tt, cache):
-        self.calls += 1
-        if self.calls == 1:                      # eager warm-up (library handles, operand caches, rotary tables)
-            return self.net(x, tt, self.conditioning, cache=cache, update_cache=False, just_2d=False)[0]
-        if self.graph is None:
-            self.sx, self.st = x.clone(), tt.clone()
+    def _eval(self, x, tt, update):
+        return self.net(x, tt, self.cond, cache=self.cache, update_cache=update, just_2d=False)[0]
+
+    def __call__(self, x, tt, conditioning, update_cache):
+        from .decode_state import advance_host_counters, cache_generation, ensure_capacity
+        ensure_capacity(self.cache, 1)
+        if cache_generation(self.cache) != self.generation:      # a pool was re-allocated: old graphs point at freed pages
+            self.graphs, self.generation = {}, cache_generation(self.cache)
+        if self.cond is not None:
+            self.cond.copy_(conditioning)
+        if not self.warm:                        # eager warm-up (library handles, operand caches, rotary tables); a
+            self.warm = True                     # non-committing evaluation has no side effects
+            if not update_cache:
+                return self._eval(x, tt, False)
+            self._eval(x, tt, False)
+        if update_cache not in self.graphs:
+            sx, st = x.clone(), tt.clone()
             torch.cuda.synchronize()
-            self.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph):
-                self.out = self.net(self.sx, self.st, self.conditioning, cache=cache, update_cache=False, just_2d=False)[0]
-        self.sx.copy_(x)
-        self.st.copy_(tt)
-        self.graph.replay()
-        return self.out.clone()
+            g = torch.cuda.CUDAGraph()
+            # host mirrors advance while the committing evaluation is being RECORDED; undo that, the replay below is
+            # the one execution
+            with torch.cuda.graph(g):
+                out = self._eval(sx, st, update_cache)
+            if update_cache:
+                advance_host_counters(self.cache, -1)
+            self.graphs[update_cache] = (g, sx, st, out)
+        g, sx, st, out = self.graphs[update_cache]
+        sx.copy_(x)
+        st.copy_(tt)
+        g.replay()
+        if update_cache:
+            advance_host_counters(self.cache, 1)
+        return out.clone()
 
 
 @torch.no_grad()
@@ -49,15 +76,16 @@ def edm_sampler_with_mse(net, cache, target=None, gnet=None, conditioning=None, 
     net.eval()
     b, _, c, h, w = cache.get('shape', (None,) * 5)
     device = net.device
-    graphed = _GraphedEval(net, conditioning) if (use_cuda_graph and guidance == 1 and device.type == "cuda") else None
+    graphed = None
+    if use_cuda_graph and guidance == 1 and device.type == "cuda":
+        graphed = cache.get('_graphed_eval')
+        if graphed is None or graphed.net is not net:
+            graphed = cache['_graphed_eval'] = _GraphedEval(net, cache, conditioning)
 
     def denoise(x, t, cache, update_cache):
         tt = torch.ones(b, 1, device=device, dtype=dtype) * t
-        if graphed is not None and not update_cache:
-            shape = cache['shape']
-            out = graphed(x, tt, cache)
-            cache['shape'] = shape
-            return out, cache
+        if graphed is not None:
+            return graphed(x, tt, conditioning, update_cache), cache
         dx, cache = net(x, tt, conditioning, cache=cache, update_cache=update_cache, just_2d=False)
         if guidance == 1:
             return dx, cache

@@ -100,12 +100,14 @@ int ob_gate_bwd(const void* dy, const void* y, const void* d, const float* alpha
  * ob_conv_prologue = ob_ctx_build + ob_gate_fwd + zeroing of `scratch` (fp32 [2*frames + 1], may be NULL in eval);
  *   pad_batch_stride: elements between the two cached frames of consecutive sequences in `pad` (0 = dense 2*frame_elems),
  *   so the last two frames of the previous call's context tensor can be passed in place (decode path, no copy);
+ *   n_ctx_dev (optional, may be NULL): device int32 added to n_ctx -- the context-frame count of a graph-replayed decode
+ *   step lives on the device so that one captured graph serves every generated frame;
  * ob_gate_bwd_fused = ob_gate_bwd with s_y = scratch, s_d = scratch + frames, and the last CTA to finish (ticket
  * counter at scratch[2*frames]) doing the work of ob_gate_bwd_params. */
 int ob_conv_prologue(const void* x, const void* pad, void* ctx, int b, int S, int T, int64_t frame_elems, int cin,
                      int cin_pad, const float* offset, const float* mult, const float* max_gating, const float* min_gating,
                      const float* c_noise, float* alpha, float* beta, float* scratch, int n_ctx, int64_t pad_batch_stride,
-                     void* stream);
+                     const int* n_ctx_dev, void* stream);
 int ob_gate_bwd_fused(const void* dy, const void* y, const void* d, const float* alpha, const float* beta, void* gya,
                       void* gb, float* scratch, int n_seq, int S, int T, int64_t frame_elems, const float* offset,
                       const float* mult, const float* max_gating, const float* min_gating, const float* c_noise,
@@ -214,6 +216,31 @@ int ob_qkv_prep_bwd(const void* qkv, const void* dq, const void* dk, const void*
 /* Rotary (key flavour: divided by the xPos scale) over cached un-rotated keys x -> y, both bf16 [rows, heads*64]. */
 int ob_rope_k(const void* x, void* y, const float* cos_t, const float* sin_t, const float* scl_t, const int* pos,
               int64_t rows, int heads, int hw, void* stream);
+
+/* ---------------------------------------------------------------------------------------------- paged KV-cache decode
+ * The sampler's cached evaluation (edm2/sampler.py:53-75 -> attention_modules.py:51-57,69-70): the reference clones and
+ * concatenates the WHOLE (k, v) cache and re-rotates every cached key on each of the 2*num_steps-1 evaluations per frame.
+ * Here keys/values live in frame-sized pages of a pool  k_pages / v_pages: bf16 [n_pages, hw, heads, 64]  addressed through
+ * page_table: int32 [B, max_pages] (page of frame t of sequence b) with lengths: int32 [B] committed frames per sequence,
+ * both in DEVICE memory -- the launch parameters do not change as a sequence grows, so one CUDA graph serves every step.
+ *
+ * ob_kv_append: q/k/v preparation of ONE new frame per sequence (the split + RMS-norm + rotary of ob_qkv_prep_fwd) with the
+ *   frame's position taken from lengths[b]; q: bf16 [B, hw, heads, 64]; the rotated key and the value are written in place
+ *   into page page_table[b][lengths[b]].  Keys are stored rotated with the tables' fixed xPos centre (it cancels in q.k).
+ *   The length is NOT advanced: a caller commits the frame by incrementing lengths (update_cache=True) or lets the next
+ *   evaluation overwrite the slot.  cos_t/sin_t/scl_t: fp32 [n_pos][64].
+ * ob_dart_attn_decode: o[b] = softmax(q[b] K[b]^T * scale) V[b] over the (lengths[b] + extra_frames) * hw keys of sequence
+ *   b, unmasked (attention_modules.py:69-70), gathered tile by tile through the page table, with the key tiles sliced over
+ *   n_split CTAs per (sequence, head, query tile) (split-KV).  o_part: fp32 [n_split, B, hw, heads, 64], l_part: fp32
+ *   [n_split, B*heads, hw] scratch (may be NULL when n_split == 1); n_split from ob_dart_attn_decode_splits.
+ *   hw must divide 128 or be a multiple of 128 (and of 8). */
+int ob_kv_append(const void* qkv, void* q, void* k_pages, void* v_pages, const int* page_table, const int* lengths,
+                 const float* cos_t, const float* sin_t, const float* scl_t, int b, int heads, int hw, int max_pages, int n_pos,
+                 float eps, void* stream);
+int ob_dart_attn_decode_splits(int b, int heads, int hw, int max_pages);
+int ob_dart_attn_decode(const void* q, const void* k_pages, const void* v_pages, const int* page_table, const int* lengths,
+                        void* o, float* o_part, float* l_part, int b, int heads, int hw, int max_pages, int n_pages,
+                        int n_split, int extra_frames, float scale, void* stream);
 
 /* Backward of ob_attn_fwd (autograd of the same reference calls).  o, lse: the forward's outputs; dout: bf16
  * [B, Lq, heads, 64]; dsum: fp32 [B, heads, Lq] workspace (receives rowsum(dout*o)).  Writes dq, dk, dv (bf16, shaped

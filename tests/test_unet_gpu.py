@@ -92,3 +92,43 @@ def test_unet_prefill_and_sampling(golden):
             xf, _, _, cache = edm_sampler_with_mse(precond, cache, conditioning=cnew.cuda(), num_steps=4, sigma_max=80,
                                                    sigma_min=0.01, x_init=x_init.cuda())
             assert_close(xf, ref, "sampled frame", max_rel=5e-2, mean_rel=1.5e-2)
+
+
+def test_static_decode_graphs_serve_every_frame(golden):
+    """Paged KV cache + static conv-context buffers + device-side frame counters: ONE pair of CUDA graphs (evaluate /
+    evaluate-and-commit) generates every frame, and the frames equal the eager cached path's (same x_init) and the
+    reference golden's first two frames."""
+    g = golden("unet")
+    ob, unet = _build(g)
+    from autoregressive_diffusion_b200.attention import PagedKV
+    from autoregressive_diffusion_b200.sampler import edm_sampler_with_mse
+    precond = ob.Precond(unet, sigma_data=1.0).cuda()
+    precond.train()
+    cat = torch.cat((g["images"], g["images"]), dim=1)
+    with torch.no_grad():
+        precond(cat.cuda(), g["sigma"].cuda(), torch.cat((g["cond"], g["cond"]), dim=1).cuda())
+    precond.eval()
+    inits = list(g["sample_inits"]) + [torch.randn_like(g["sample_inits"][0]) for _ in range(3)]
+    conds = list(g["sample_conds"]) + [g["sample_conds"][0] for _ in range(3)]
+    frames = {}
+    with torch.no_grad():
+        for graph in (False, True):
+            ctx = g["ctx"].cuda()
+            _, cache = precond(ctx, torch.ones(ctx.shape[:2], device="cuda") * 0.05, g["cond_ctx"].cuda(), update_cache=True)
+            kvs = [v["attn"] for v in cache.values() if isinstance(v, dict) and isinstance(v.get("attn"), PagedKV)]
+            assert kvs and all(kv.n_frames == ctx.shape[1] for kv in kvs)
+            out = []
+            for x_init, cnew in zip(inits, conds):
+                xf, _, _, cache = edm_sampler_with_mse(precond, cache, conditioning=cnew.cuda(), num_steps=4, sigma_max=80,
+                                                       sigma_min=0.01, x_init=x_init.cuda(), use_cuda_graph=graph)
+                out.append(xf.float().cpu())
+            frames[graph] = out
+            assert all(kv.n_frames == ctx.shape[1] + len(inits) for kv in kvs)
+            assert all(int(kv.lengths[0]) == kv.n_frames for kv in kvs)          # device-side and host-side lengths agree
+            if graph:
+                ge = cache["_graphed_eval"]
+                assert sorted(ge.graphs) == [False, True], "one graph per kind, captured once, reused by all five frames"
+    for a, b in zip(frames[False], frames[True]):
+        assert_close(b, a, "graph replay == eager cached path", 2e-2, 2e-3)
+    for got, ref in zip(frames[True][:2], g["sample_frames"]):
+        assert_close(got, ref, "sampled frame vs reference", max_rel=5e-2, mean_rel=1.5e-2)
