@@ -31,10 +31,11 @@ def stream_ptr():
 _SIGS = {
     # name: argtypes
     "ob_wnorm_fwd": "ppiiiiiiffip",
+    "ob_wnorm_fwd_multi": "ppiifp",
     "ob_wnorm_bwd_gated": "pppppiiiifip",
     "ob_wnorm_bwd": "pppiiiiiiiffip",
-    "ob_conv_fwd": "ppppppppiiiiiiiiiip",
-    "ob_conv_dgrad": "pppppppiiiiiiiiip",
+    "ob_conv_fwd": "ppppppppiiiiiiiiiiip",
+    "ob_conv_dgrad": "pppppppiiiiiiiiiip",
     "ob_conv_split_ws_bytes": "iiiiiiiii",
     "ob_conv_wgrad_splits": "iiiiiiiii",
     "ob_conv_wgrad": "pppppiiiiiiiiiip",

@@ -48,19 +48,37 @@ class _OperandCache:
     only change when something writes the parameter.  Writers that go through torch (torch.optim, copy_,
     load_state_dict) bump the tensor's autograd version; writers that go through a raw pointer (the fused optimizer
     kernel, ob_adamw_ema) do not, so they bump `ops.param_generation` instead -- both are part of the key.
+    A stale operand triggers ops.OperandBank.refresh: ONE launch re-normalises every registered layer of the device.
     """
 
     def __init__(self):
-        self.key, self.wg = None, None
+        self.key, self.wg, self.params, self.last_training = None, None, None, None
+
+    def _key(self, training):
+        return tuple((p.data_ptr(), p._version) for p in self.params) + (bool(training), self.gains, ops.param_generation())
+
+    def stale(self, training):
+        return self._key(training) != self.key
+
+    def mark_fresh(self, training):
+        self.key, self.last_training = self._key(training), bool(training)
 
     def get(self, params, taps, cin, cin_pad, gains, training):
-        key = tuple((p.data_ptr(), p._version) for p in params) + (bool(training), tuple(float(g) for g in gains),
-                                                                   ops.param_generation())
-        if key != self.key:
+        gains = tuple(float(g) for g in gains)
+        if self.params is None or any(a is not b for a, b in zip(self.params, params)) or gains != self.gains:
+            # first use (or a re-wired layer): allocate the operand and join the bank
+            first = self.params is None
+            self.params, self.taps, self.cin, self.cin_pad, self.gains = list(params), list(taps), cin, cin_pad, gains
+            cout_pad = ops.ceil_to(params[0].shape[0], 8)
+            alloc = torch.empty if cout_pad == params[0].shape[0] else torch.zeros
+            self.wg = alloc((cout_pad, sum(taps), cin_pad), dtype=BF16, device=params[0].device)
+            self.key = None
+            if first:
+                ops.OperandBank.register(self)
+        if self.stale(training):
             with torch.no_grad():
-                self.wg = ops.weight_operand([p.data for p in params], taps, cin, cin_pad, gains, training)
+                ops.OperandBank.refresh(self, training)
             # forced normalisation rewrote the parameters through a raw pointer: the version did not move
-            self.key = key
         return self.wg
 
 
@@ -134,17 +152,16 @@ class MPCausal3DGatedConv(nn.Module):
         self._cache = _OperandCache()
 
     def forward(self, x, emb, batch_size, c_noise, cache=None, update_cache=False, just_2d=False):
-        if just_2d:
-            return self.last_frame_conv(x), cache
         ops._require_cuda(x)
-        if cache is None:
-            cache = {}
         w2, w3 = self.last_frame_conv.weight.weight, self.weight.weight
         cin = w2.shape[1]
         cin_pad = ops.ceil_to(cin, 16)
         wg = self._cache.get([w2, w3], [9, 18], cin, cin_pad, [1.0, 1.0], self.training)
-
         xr = ops.pad_channels(rows(x), 16)
+        if just_2d:     # the 2-D form (conv.py:60) reads the first 9 taps of the same operand: one normalisation per weight
+            return ops.PlainConvFn.apply(xr, w2, wg, 3, 1.0, False), cache
+        if cache is None:
+            cache = {}
         f, _, h, w = xr.shape
         S = 2 if self.training else 1
         T = f // (batch_size * S)

@@ -65,6 +65,9 @@ int ob_wnorm_fwd(float* w, void* wg, int cout, int cin, int taps, int cin_pad, i
                  float eps, int training, void* stream) {
   return wnorm_fwd(w, wg, cout, cin, taps, cin_pad, taps_total, tap_off, gain, eps, training, (cudaStream_t)stream);
 }
+int ob_wnorm_fwd_multi(const ob_wnorm_job* jobs, const int* row_start, int n_jobs, int total_rows, float eps, void* stream) {
+  return wnorm_fwd_multi(jobs, row_start, n_jobs, total_rows, eps, (cudaStream_t)stream);
+}
 int ob_wnorm_bwd(const float* w, const float* dwg, float* dw, int cout, int cin, int taps, int cin_pad, int taps_total,
                  int tap_off, int n_split, float gain, float eps, int accumulate, void* stream) {
   return wnorm_bwd(w, dwg, dw, cout, cin, taps, cin_pad, taps_total, tap_off, n_split, gain, eps, accumulate,
@@ -86,7 +89,7 @@ int64_t ob_conv_split_ws_bytes(int n_seq, int S, int T, int H, int W, int cin, i
 
 int ob_conv_fwd(const void* x, const void* ctx, const void* wg, const float* alpha, const float* beta, void* out,
                 void* out_d, void* split_ws, int n_seq, int S, int T, int H, int W, int cin, int cout, int ksize, int gated,
-                int out_f32, void* stream) {
+                int out_f32, int w_taps, void* stream) {
   if (int r = check_shape("ob_conv_fwd", n_seq, S, T, H, W, ksize, gated)) return r;
   TapConvLaunch L;
   std::vector<TapCol> cols;
@@ -96,7 +99,8 @@ int ob_conv_fwd(const void* x, const void* ctx, const void* wg, const float* alp
     set_src(L, 0, x, 1, frames, H, W, cin);
     if (ksize == 1) cols.push_back(tap_col1(0, 1, 0, 1));
     else for (int dx = -1; dx <= 1; ++dx) cols.push_back(tap_col3(0, 0, dx, 1, 0, 1, 0, false));
-    L.n_seq = 1; L.n_out = 1; L.T = frames; L.w_taps = ksize * ksize; L.epi = EPI_PLAIN; L.halo = ksize == 3;
+    L.n_seq = 1; L.n_out = 1; L.T = frames; L.w_taps = w_taps > 0 ? w_taps : ksize * ksize; L.epi = EPI_PLAIN; L.halo = ksize == 3;
+    if (L.w_taps < ksize * ksize) { set_error("ob_conv_fwd: w_taps %d < %d", w_taps, ksize * ksize); return OB_ERR_INVALID; }
   } else {
     set_src(L, 0, x, n_seq * S, T, H, W, cin);
     set_src(L, 1, ctx, n_seq, T + 2, H, W, cin);
@@ -115,7 +119,7 @@ int ob_conv_fwd(const void* x, const void* ctx, const void* wg, const float* alp
 
 int ob_conv_dgrad(const void* gy, const void* gb, const void* wg, const float* alpha, const float* beta, void* dx,
                   void* split_ws, int n_seq, int S, int T, int H, int W, int cin, int cout, int ksize, int gated,
-                  void* stream) {
+                  int w_taps, void* stream) {
   if (int r = check_shape("ob_conv_dgrad", n_seq, S, T, H, W, ksize, gated)) return r;
   // transposed problem: GEMM K = cout (channels of the incoming gradient), GEMM N = cin; taps are mirrored
   TapConvLaunch L;
@@ -125,7 +129,8 @@ int ob_conv_dgrad(const void* gy, const void* gb, const void* wg, const float* a
     set_src(L, 0, gy, 1, frames, H, W, cout);
     if (ksize == 1) cols.push_back(tap_col1(0, 1, 0, 1));
     else for (int sx = -1; sx <= 1; ++sx) cols.push_back(tap_col3(0, 0, sx, 1, 0, 1, 0, true));
-    L.n_seq = 1; L.n_out = 1; L.T = frames; L.w_taps = ksize * ksize; L.epi = EPI_PLAIN; L.halo = ksize == 3;
+    L.n_seq = 1; L.n_out = 1; L.T = frames; L.w_taps = w_taps > 0 ? w_taps : ksize * ksize; L.epi = EPI_PLAIN; L.halo = ksize == 3;
+    if (L.w_taps < ksize * ksize) { set_error("ob_conv_dgrad: w_taps %d < %d", w_taps, ksize * ksize); return OB_ERR_INVALID; }
   } else {
     set_src(L, 0, gy, n_seq * S, T, H, W, cout);
     set_src(L, 1, gb, n_seq, T, H, W, cout);

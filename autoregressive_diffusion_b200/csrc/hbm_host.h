@@ -5,6 +5,7 @@
 namespace ob {
 int wnorm_fwd(float* w, void* wg, int Co, int Ci, int taps, int Ci_pad, int taps_total, int tap_off, float gain, float eps,
               int training, cudaStream_t st);
+int wnorm_fwd_multi(const void* jobs, const int* row_start, int n_jobs, int total_rows, float eps, cudaStream_t st);
 int wnorm_bwd2(const float* w0, float* dw0, int taps0, int tap_off0, float gain0, const float* w1, float* dw1, int taps1,
                int tap_off1, float gain1, const float* dwg, int Co, int Ci, int Ci_pad, int taps_total, int n_split, float eps,
                int accumulate, cudaStream_t st);

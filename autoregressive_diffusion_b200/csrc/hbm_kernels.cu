@@ -3,6 +3,7 @@
 // All activations are bf16 NHWC ([rows, C], channel-contiguous); all arithmetic is fp32.
 // 128-bit global accesses, warp-shuffle reductions, one pass over HBM per tensor.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include "launch.cuh"
 #include <cuda_runtime.h>
 #include <cstdint>
@@ -60,13 +61,9 @@ __device__ __forceinline__ bf16x8 pack8(const float* f) {
 // wgrad partials dwg[n_split][Co][taps_total][Ci_pad].  Forward and backward are therefore straight row streams (no
 // transposes, no index divisions): one CTA per output channel, 128-bit accesses.
 // training: w <- w/(eps+rms(w)) in place (forced weight norm), operand = normalize(that) * gain/sqrt(fan_in).
-__global__ void __launch_bounds__(256) wnorm_fwd_kernel(float* __restrict__ w, __nv_bfloat16* __restrict__ wg, int Ci,
-                                                        int taps, int Ci_pad, int taps_total, int tap_off, float gain,
-                                                        float eps, int training) {
-  pdl_launch_dependents();
-  pdl_wait();
-  __shared__ float red[32];
-  const int co = blockIdx.x;
+__device__ __forceinline__ void wnorm_fwd_row(float* __restrict__ w, __nv_bfloat16* __restrict__ wg, int co, int Ci, int taps,
+                                              int Ci_pad, int taps_total, int tap_off, float gain, float eps, int training,
+                                              float* red) {
   const int K = Ci * taps;
   float* wr = w + static_cast<long>(co) * K;
   __nv_bfloat16* dst = wg + (static_cast<long>(co) * taps_total + tap_off) * Ci_pad;
@@ -108,6 +105,34 @@ __global__ void __launch_bounds__(256) wnorm_fwd_kernel(float* __restrict__ w, _
       for (int i = threadIdx.x; i < K; i += blockDim.x) wr[i] *= s1;
     }
   }
+}
+
+__global__ void __launch_bounds__(256) wnorm_fwd_kernel(float* __restrict__ w, __nv_bfloat16* __restrict__ wg, int Ci,
+                                                        int taps, int Ci_pad, int taps_total, int tap_off, float gain,
+                                                        float eps, int training) {
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ float red[32];
+  wnorm_fwd_row(w, wg, blockIdx.x, Ci, taps, Ci_pad, taps_total, tap_off, gain, eps, training, red);
+}
+
+// Every weight tensor of a network in ONE launch (the optimizer step invalidates all of them at once; 210 separate
+// launches of ~13 us are latency-bound at 0.22 of the HBM roofline).  jobs: device array, one entry per weight tensor;
+// row_start[j] = first global row (output channel) of job j, row_start[n_jobs] = total rows; one CTA per row.
+__global__ void __launch_bounds__(256) wnorm_fwd_multi_kernel(const ob_wnorm_job* __restrict__ jobs,
+                                                              const int* __restrict__ row_start, int n_jobs, float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ float red[32];
+  const int row = blockIdx.x;
+  int lo = 0, hi = n_jobs - 1;                 // last job whose first row is <= row
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (row_start[mid] <= row) lo = mid; else hi = mid - 1;
+  }
+  const ob_wnorm_job j = jobs[lo];
+  wnorm_fwd_row(j.w, static_cast<__nv_bfloat16*>(j.wg), row - row_start[lo], j.cin, j.taps, j.cin_pad, j.taps_total, j.tap_off,
+                j.gain, eps, j.training, red);
 }
 
 // Backward of operand = normalize(w) * gain/sqrt(K) w.r.t. the (forced) weights w:
@@ -236,10 +261,19 @@ __global__ void __launch_bounds__(256, 4) wnorm_bwd_kernel(const WnormBwdArgs a)
 
 // ============================================================================ gate backward pre-pass
 // Reference: the mp_sum(last_frame_conv, context, gating) of edm2/conv.py:95 differentiated.
-//   y = alpha*a + beta*b  (alpha,beta per frame), saved: y (bf16) and d = b - a (fp32).
+//   y = alpha*a + beta*b  (alpha,beta per frame), saved: y (bf16) and d = b - a (fp16: 11 mantissa bits at two bytes).
 // Produces in ONE pass over dy:  gya = alpha*dy (all frames), gb[b,t] = sum_s beta_s*dy_s (context rows),
 // and per-frame <dy,y>, <dy,d> (what the 5 gate scalars' gradients need).  S = 1 (eval-style) or 2 (clean+noised).
 // Optional tail of gate_bwd_kernel: the gate parameters, their gradient buffers and a zeroed ticket counter.
+__device__ __forceinline__ void unpack8_f16(const uint4& v, float (&f)[8]) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 p2 = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+    f[2 * i] = p2.x; f[2 * i + 1] = p2.y;
+  }
+}
+
 struct GateGradArgs {
   const float *offset, *mult, *max_g, *min_g, *c_noise;
   float *g_offset, *g_mult, *g_max, *g_min;
@@ -249,7 +283,7 @@ struct GateGradArgs {
 
 __global__ void __launch_bounds__(256) gate_bwd_kernel(const __nv_bfloat16* __restrict__ dy,
                                                        const __nv_bfloat16* __restrict__ y,
-                                                       const float* __restrict__ d,
+                                                       const __half* __restrict__ d,
                                                        const float* __restrict__ alpha, const float* __restrict__ beta,
                                                        __nv_bfloat16* __restrict__ gya, __nv_bfloat16* __restrict__ gb,
                                                        float* __restrict__ s_y, float* __restrict__ s_d, int n_seq, int S,
@@ -269,16 +303,17 @@ __global__ void __launch_bounds__(256) gate_bwd_kernel(const __nv_bfloat16* __re
     // all loads of both halves first (8 independent 128-bit requests per thread), then the arithmetic and the stores
     const long o0 = f0 * frame_elems + e, o1 = f1 * frame_elems + e;
     const bf16x8 g0v = *reinterpret_cast<const bf16x8*>(dy + o0), y0v = *reinterpret_cast<const bf16x8*>(y + o0);
-    const float4 d00 = *reinterpret_cast<const float4*>(d + o0), d01 = *reinterpret_cast<const float4*>(d + o0 + 4);
+    const uint4 d0v = *reinterpret_cast<const uint4*>(d + o0);     // 8 fp16 values
     bf16x8 g1v = g0v, y1v = y0v;
-    float4 d10 = d00, d11 = d01;
+    uint4 d1v = d0v;
     if (S > 1) {
       g1v = *reinterpret_cast<const bf16x8*>(dy + o1); y1v = *reinterpret_cast<const bf16x8*>(y + o1);
-      d10 = *reinterpret_cast<const float4*>(d + o1); d11 = *reinterpret_cast<const float4*>(d + o1 + 4);
+      d1v = *reinterpret_cast<const uint4*>(d + o1);
     }
     float g0[8], y0[8], g1[8], y1[8], oa[8], ob_[8], acc_b[8];
     unpack8(g0v, g0); unpack8(y0v, y0);
-    const float dv0[8] = {d00.x, d00.y, d00.z, d00.w, d01.x, d01.y, d01.z, d01.w};
+    float dv0[8];
+    unpack8_f16(d0v, dv0);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       oa[j] = al0 * g0[j];
@@ -289,7 +324,8 @@ __global__ void __launch_bounds__(256) gate_bwd_kernel(const __nv_bfloat16* __re
     *reinterpret_cast<bf16x8*>(gya + o0) = pack8(oa);
     if (S > 1) {
       unpack8(g1v, g1); unpack8(y1v, y1);
-      const float dv1[8] = {d10.x, d10.y, d10.z, d10.w, d11.x, d11.y, d11.z, d11.w};
+      float dv1[8];
+      unpack8_f16(d1v, dv1);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         ob_[j] = al1 * g1[j];
@@ -759,6 +795,12 @@ int wnorm_fwd(float* w, void* wg, int Co, int Ci, int taps, int Ci_pad, int taps
   return check_launch("wnorm_fwd");
 }
 
+int wnorm_fwd_multi(const void* jobs, const int* row_start, int n_jobs, int total_rows, float eps, cudaStream_t st) {
+  if (n_jobs <= 0 || total_rows <= 0) return OB_OK;
+  launch(wnorm_fwd_multi_kernel, total_rows, 256, 0, st, 1, static_cast<const ob_wnorm_job*>(jobs), row_start, n_jobs, eps);
+  return check_launch("wnorm_fwd_multi");
+}
+
 int wnorm_bwd2(const float* w0, float* dw0, int taps0, int tap_off0, float gain0, const float* w1, float* dw1, int taps1,
                int tap_off1, float gain1, const float* dwg, int Co, int Ci, int Ci_pad, int taps_total, int n_split, float eps,
                int accumulate, cudaStream_t st) {
@@ -792,7 +834,7 @@ int gate_bwd(const void* dy, const void* y, const void* d, const float* alpha, c
   while (bx > 1 && static_cast<long>(bx) * n_seq * T > 4 * 148) bx = (bx + 1) / 2;
   dim3 grid(bx, n_seq * T);
   launch(gate_bwd_kernel, grid, 256, 0, st, 1, static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(y),
-                                        static_cast<const float*>(d), alpha, beta,
+                                        static_cast<const __half*>(d), alpha, beta,
                                         static_cast<__nv_bfloat16*>(gya), static_cast<__nv_bfloat16*>(gb), s_y, s_d, n_seq,
                                         S, T, frame_elems,
                                         GateGradArgs{offset, mult, max_g, min_g, c_noise, g_offset, g_mult, g_max, g_min,

@@ -38,10 +38,10 @@ inline int pdl_mode() {
   return v;
 }
 
-// cluster_x > 1 launches clusters; a kernel with more than 48 KB of dynamic shared memory counts as "heavy".
+// cluster_x / cluster_y > 1 launches clusters; a kernel with more than 48 KB of dynamic shared memory counts as "heavy".
 template <typename... KArgs, typename... Args>
-inline cudaError_t launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster_x,
-                          Args&&... args) {
+inline cudaError_t launch_xy(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster_x,
+                             int cluster_y, Args&&... args) {
   const int mode = pdl_mode();
   const bool pdl = mode == 1 || (mode == 2 && smem <= 48 * 1024);
   cudaLaunchConfig_t cfg{};
@@ -51,9 +51,9 @@ inline cudaError_t launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t 
   cfg.stream = st;
   cudaLaunchAttribute attr[2];
   unsigned n = 0;
-  if (cluster_x > 1) {
+  if (cluster_x > 1 || cluster_y > 1) {
     attr[n].id = cudaLaunchAttributeClusterDimension;
-    attr[n].val.clusterDim.x = cluster_x; attr[n].val.clusterDim.y = 1; attr[n].val.clusterDim.z = 1;
+    attr[n].val.clusterDim.x = cluster_x; attr[n].val.clusterDim.y = cluster_y; attr[n].val.clusterDim.z = 1;
     ++n;
   }
   if (pdl) {
@@ -64,6 +64,11 @@ inline cudaError_t launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t 
   cfg.attrs = attr;
   cfg.numAttrs = n;
   return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster_x,
+                          Args&&... args) {
+  return launch_xy(kern, grid, block, smem, st, cluster_x, 1, std::forward<Args>(args)...);
 }
 
 }  // namespace ob

@@ -127,8 +127,10 @@ static int launch_inst(const TapConvParams& p, dim3 grid, cudaStream_t stream) {
       }
       attr_set = true;
     }
-    const int smem = 1024 + p.a_slots * p.a_slot_bytes + p.b_slots * Cfg::B_BYTES_AL + 256;
-    launch(tapconv_kernel<CHUNK, BN, BMN, false>, grid, TAPCONV_THREADS, smem, stream, 1, p);
+    const int smem = 1024 + p.a_slots * p.a_slot_bytes + p.b_slots * Cfg::B_BYTES_AL + p.stage_pad + 256;
+    if (smem > MAX_DYN) { set_error("tapconv<%d,%d>: %d bytes of shared memory exceed the limit", CHUNK, BN, smem); return OB_ERR_UNSUPPORTED; }
+    // cluster split-K: the ksplit CTAs of a tile (consecutive blockIdx.y) form one cluster
+    launch_xy(tapconv_kernel<CHUNK, BN, BMN, false>, grid, dim3(TAPCONV_THREADS), smem, stream, 1, p.csplit ? p.ksplit : 1, p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
       set_error("tapconv<%d,%d> launch: %s", CHUNK, BN, cudaGetErrorString(e));
@@ -165,7 +167,7 @@ static void tile_shape(int H, int W, int* bw, int* bh, int* bt) {
 // tile twice as often per FLOP), so when a layer has too few output tiles for 148 SMs the first remedy is to slice
 // its K loop (channel chunks) over extra CTAs, and only then to narrow N.
 static void pick_tiling(int n_acc, int Cout, int Cin, int chunk, int taps, int m_tiles, int force_bn, int b_mn_major, bool can_split,
-                        int* bn_out, int* ks_out) {
+                        bool cluster, int* bn_out, int* ks_out) {
   const int bn_max = (n_acc == 3) ? 128 : 256;
   int bn = pow2_ceil(Cout) < 16 ? 16 : pow2_ceil(Cout);
   if (bn > bn_max) bn = bn_max;
@@ -174,14 +176,29 @@ static void pick_tiling(int n_acc, int Cout, int Cin, int chunk, int taps, int m
     const int tiles = m_tiles * ((Cout + b - 1) / b);
     int ks = 1;
     // a split launch costs a memset and a finishing kernel: only worth it when the K loop is long (3x3 / 3x3x3 taps)
-    if (can_split && tiles <= 74 && n_chunks >= 4 && n_chunks * taps >= 48 && Cout % 4 == 0) {
+    // cluster split-K stages n_acc * b * 128 fp32 partials in shared memory beside the rings: only narrow tiles qualify
+    const bool fits = !cluster || static_cast<long>(n_acc) * b * 128 * 4 <= 100 * 1024;
+    if (can_split && fits && tiles <= 74 && n_chunks >= 4 && n_chunks * taps >= 48 && Cout % 4 == 0) {
       ks = 148 / tiles;
-      if (ks > n_chunks / 2) ks = n_chunks / 2;   // at least two chunks per slice
+      // at least two chunks per slice -- except on the 4x4 level (<= 16 wide tiles): there one chunk per slice with N=128
+      // CTA pairs beats two chunks with N=64 (512->512 4x4: 31.8 / 33.8 us against 36.1 / 36.3 us, fwd / dgrad;
+      // profiles/r02_small_layer_sweep.txt) because the pair halves the weight bytes each SM pulls through L2
+      const int min_chunks = (tiles <= 16 && b >= 128) ? 1 : 2;
+      if (ks > n_chunks / min_chunks) ks = n_chunks / min_chunks;
       if (ks > 8) ks = 8;
       if (ks < 1) ks = 1;
     }
     return ks;
   };
+  static const int env_bn = [] { const char* e = getenv("ONIRIS_SMALL_BN"); return e ? atoi(e) : 0; }();     // experiment knobs for the
+  static const int env_ks = [] { const char* e = getenv("ONIRIS_SMALL_KS"); return e ? atoi(e) : 0; }();     // 4x4 / 8x8 levels
+  if (env_bn > 0 && m_tiles <= 16 && taps >= 9 && Cout >= env_bn && n_chunks >= 4) {
+    *bn_out = (n_acc == 3 && env_bn > 128) ? 128 : env_bn;
+    int ks = env_ks > 0 ? env_ks : split_for(*bn_out);
+    if (ks > n_chunks) ks = n_chunks;
+    *ks_out = can_split ? ks : 1;
+    return;
+  }
   if (force_bn > 0) bn = force_bn;
   else {
     while (bn > 64) {
@@ -195,8 +212,25 @@ static void pick_tiling(int n_acc, int Cout, int Cin, int chunk, int taps, int m
   *ks_out = split_for(bn);
 }
 
+// Split-K reduction strategy.  Default: red.global.add into an fp32 workspace + tapconv_finish_kernel.
+// ONIRIS_CSPLIT=1 selects the experimental cluster variant (the slices of a tile form a thread-block cluster and reduce
+// their partial accumulators through distributed shared memory inside the one launch).  Measured on the CS layers
+// (profiles/r02_conv_breakdown_csplit.txt): NOT faster -- 512->512 4x4 41-43 us against 36-39 us -- because these layers are
+// bound by L2->SM operand traffic (129 MB per launch at 4x4), not by the reduction; and its staging area forces narrow
+// tiles, which costs the 8x8 level its CTA pairs (81 us against 58-62 us).  The MN-major (input-gradient) instantiation
+// with N=128 still returns garbage in columns 64..127 under it; the variant stays off and is not covered by the tests.
+static bool cluster_split_enabled() {
+  static const bool on = [] { const char* e = getenv("ONIRIS_CSPLIT"); return e != nullptr && e[0] == '1'; }();
+  return on;
+}
+static int pow2_floor(int v) {
+  int p = 1;
+  while (2 * p <= v) p <<= 1;
+  return p;
+}
+
 // Small-spatial layers (the 4x4 / 8x8 levels) have too few output tiles to occupy 148 SMs while their K loop is
-// hundreds of steps long: slice the channel chunks over blockIdx.y and reduce in an fp32 workspace.
+// hundreds of steps long: slice the channel chunks over blockIdx.y (split-K).
 void tapconv_plan(int n_seq, int n_out, int gated, int taps, int T, int H, int W, int Cin, int Cout, int* ksplit, long* ws_bytes) {
   int bw, bh, bt;
   tile_shape(H, W, &bw, &bh, &bt);
@@ -204,9 +238,9 @@ void tapconv_plan(int n_seq, int n_out, int gated, int taps, int T, int H, int W
   const int n_acc = n_out + (gated ? 1 : 0);
   const int chunk = (Cin % 64 == 0) ? 64 : (Cin % 32 == 0) ? 32 : 16;
   int bn, ks;
-  pick_tiling(n_acc, Cout, Cin, chunk, taps, m_tiles, 0, 0, true, &bn, &ks);
+  pick_tiling(n_acc, Cout, Cin, chunk, taps, m_tiles, 0, 0, true, cluster_split_enabled(), &bn, &ks);
   *ksplit = ks;
-  *ws_bytes = ks > 1 ? static_cast<long>(n_acc) * n_seq * T * H * W * Cout * 4 : 0;
+  *ws_bytes = (ks > 1 && !cluster_split_enabled()) ? static_cast<long>(n_acc) * n_seq * T * H * W * Cout * 4 : 0;
 }
 
 int tapconv_launch(const TapConvLaunch& L, cudaStream_t stream) {
@@ -240,7 +274,21 @@ int tapconv_launch(const TapConvLaunch& L, cudaStream_t stream) {
   int bn, ks_plan;
   int taps = 0;
   for (int i = 0; i < L.n_cols; ++i) taps += static_cast<const TapCol*>(L.cols)[i].n_taps;
-  pick_tiling(n_acc, L.Cout, L.Cin, chunk, taps, m_tiles, L.force_bn, L.b_mn_major, L.split_ws != nullptr, &bn, &ks_plan);
+  const bool want_cs = cluster_split_enabled() && L.split_ws == nullptr && L.trace == nullptr && !L.no_persist;
+  pick_tiling(n_acc, L.Cout, L.Cin, chunk, taps, m_tiles, L.force_bn, L.b_mn_major, L.split_ws != nullptr || want_cs, want_cs, &bn, &ks_plan);
+  // cluster split-K: power-of-two slices (rows of the tile are dealt out evenly), at most the portable cluster size, one
+  // tile per cluster
+  bool csplit = false;
+  if (want_cs && ks_plan > 1) {
+    int ks = pow2_floor(ks_plan > 8 ? 8 : ks_plan);
+    const int tiles_all = m_tiles * ((L.Cout + bn - 1) / bn);
+    while (ks > 1 && tiles_all * ks > 148) ks >>= 1;
+    const long stage = static_cast<long>(n_acc) * bn * 128 * 4;
+    if (ks > 1 && bn / ks >= 8 && stage <= 100 * 1024) { csplit = true; ks_plan = ks; }
+    else ks_plan = 1;
+  } else if (L.split_ws == nullptr) {
+    ks_plan = 1;
+  }
   if (n_acc * bn > 512) {
     set_error("tapconv: %d accumulators x N=%d exceed TMEM", n_acc, bn);
     return OB_ERR_INVALID;
@@ -249,7 +297,8 @@ int tapconv_launch(const TapConvLaunch& L, cudaStream_t stream) {
 
   // CTA pairs (cta_group::2) for the wide-N, 64-channel-chunk layers with at least one full pair of pixel tiles:
   // each CTA of a pair stages only half of every weight tile
-  const bool pair = (L.use_pair != 0) && bn >= 128 && chunk == 64 && m_tiles >= 2;
+  static const bool no_pair_env = [] { const char* e = getenv("ONIRIS_NO_PAIR"); return e != nullptr && e[0] == '1'; }();   // A/B + test hook
+  const bool pair = (L.use_pair != 0) && !no_pair_env && bn >= 128 && chunk == 64 && m_tiles >= 2 && !csplit;
   p.m_tiles_pad = pair ? (m_tiles + 1) / 2 * 2 : 0;
 
   // ---- shared-memory rings
@@ -257,7 +306,8 @@ int tapconv_launch(const TapConvLaunch& L, cudaStream_t stream) {
   p.a_tile_bytes = rows_a * chunk * 2;
   p.a_slot_bytes = (L.n_out * p.a_tile_bytes + 1023) / 1024 * 1024;
   const int b_al = ((bn * chunk * 2 + 1023) / 1024 * 1024) / (pair ? 2 : 1);
-  const int budget = 208 * 1024;
+  // cluster split-K keeps a staging area for the partial accumulators beside the rings (their K loops are short)
+  const int budget = 208 * 1024 - (csplit ? n_acc * bn * 128 * 4 : 0);
   p.a_slots = pair ? TAPCONV_MAX_A_SLOTS : 3;
   while (p.a_slots > 2 && (budget - p.a_slots * p.a_slot_bytes) / b_al < 4) --p.a_slots;   // keep >= 4 weight tiles in flight
   p.b_slots = (budget - p.a_slots * p.a_slot_bytes) / b_al;
@@ -271,7 +321,7 @@ int tapconv_launch(const TapConvLaunch& L, cudaStream_t stream) {
     // short K loops (1x1 kernels) never fill the rings: shrink them to the loop length so that two CTAs fit on an SM
     // and one's epilogue overlaps the other's loads
     const int n_chunks = (L.Cin + chunk - 1) / chunk;
-    const int per_cta = (n_chunks + (L.split_ws != nullptr ? ks_plan : 1) - 1) / (L.split_ws != nullptr ? ks_plan : 1);
+    const int per_cta = (n_chunks + ks_plan - 1) / ks_plan;
     if (p.a_slots > L.n_cols * per_cta) p.a_slots = L.n_cols * per_cta;
     if (p.b_slots > taps * per_cta) p.b_slots = taps * per_cta;
   }
@@ -321,7 +371,13 @@ int tapconv_launch(const TapConvLaunch& L, cudaStream_t stream) {
                  (reinterpret_cast<uintptr_t>(L.out_d) % 32 == 0) && bn >= 32;
   p.ksplit = 1;
   p.split_ws = nullptr;
-  if (L.split_ws != nullptr) {
+  p.csplit = 0;
+  p.stage_pad = 0;
+  if (csplit) {
+    p.ksplit = ks_plan;
+    p.csplit = 1;
+    p.stage_pad = n_acc * bn * 128 * 4;
+  } else if (L.split_ws != nullptr) {
     const int ks = ks_plan;
     const long wsb = static_cast<long>(n_acc) * L.n_seq * L.T * L.H * L.W * L.Cout * 4;
     if (ks > 1) {
@@ -363,12 +419,12 @@ int tapconv_launch(const TapConvLaunch& L, cudaStream_t stream) {
       default: rc = launch_bn<16, false>(bn, p, grid, stream); break;
     }
   }
-  if (rc != OB_OK || p.ksplit == 1) return rc;
+  if (rc != OB_OK || p.ksplit == 1 || p.csplit) return rc;
   {
     const long hw = static_cast<long>(L.H) * L.W;
     const long total = static_cast<long>(L.n_seq) * L.n_out * L.T * hw * (L.Cout / 4);
     launch(tapconv_finish_kernel, static_cast<unsigned>((total + 255) / 256), 256, 0, stream, 1, 
-        p.split_ws, p.alpha, p.beta, p.out, static_cast<float*>(p.out_d), L.n_seq, L.n_out, L.T, hw, L.Cout, p.epi, p.out_f32);
+        p.split_ws, p.alpha, p.beta, p.out, static_cast<__half*>(p.out_d), L.n_seq, L.n_out, L.T, hw, L.Cout, p.epi, p.out_f32);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("tapconv_finish launch: %s", cudaGetErrorString(e)); return OB_ERR_CUDA; }
   }

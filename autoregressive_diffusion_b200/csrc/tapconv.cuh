@@ -74,8 +74,11 @@ struct TapConvParams {
   const float* alpha;  // [n_seq*n_out*T] per output frame (EPI_GATED)
   const float* beta;
   void* out;    // [n_seq*n_out*T, H, W, Cout]
-  void* out_d;  // optional (EPI_GATED): shared - own accumulator, fp32, same shape as out
-  int ksplit;   // >1: blockIdx.y owns a slice of the channel chunks; raw accumulators are reduced into split_ws
+  void* out_d;  // optional (EPI_GATED): shared - own accumulator, fp16, same shape as out
+  int ksplit;   // >1: blockIdx.y owns a slice of the channel chunks (split-K)
+  int csplit;   // 1: the ksplit CTAs of a tile form a cluster (1, ksplit, 1) and reduce their partial accumulators through
+                //    distributed shared memory inside this launch; 0: they add into split_ws and a finish kernel follows
+  int stage_pad;  // csplit: bytes of the accumulator staging area (n_acc*BN*128*4) placed after the operand rings
   long long* trace;   // optional [grid.x*grid.y][8] globaltimer stamps (probe builds only; nullptr in production)
   float* split_ws;  // [n_acc][n_seq*T*H*W][Cout] fp32 (own sets first, then the shared accumulator), zeroed by tapconv_launch
 };
@@ -141,7 +144,8 @@ __global__ void __launch_bounds__(TAPCONV_THREADS, 1) tapconv_kernel(const __gri
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sA0 = smem_base;
   const uint32_t sB0 = sA0 + p.a_slots * p.a_slot_bytes;
-  const uint32_t bar_base = sB0 + p.b_slots * B_STRIDE;
+  const uint32_t sStage = sB0 + p.b_slots * B_STRIDE;      // csplit: staging area of the partial accumulators
+  const uint32_t bar_base = sStage + p.stage_pad;
   // barriers: a_full[MAXA], a_empty[MAXA], b_full[MAXB], b_empty[MAXB], tmem_full[2], tmem_empty[2], TMEM address slot
   constexpr int MAXA = TAPCONV_MAX_A_SLOTS;
   auto a_full = [&](int s) { return bar_base + 8u * s; };
@@ -384,7 +388,20 @@ __global__ void __launch_bounds__(TAPCONV_THREADS, 1) tapconv_kernel(const __gri
       tc_fence_after();
       if (warp == 3 && it == 0) TAPCONV_STAMP(3);   // first tile's accumulators complete
 
-      if (p.ksplit > 1) {
+      if (p.csplit) {
+        // cluster split-K: park the raw partial accumulators, column-major ([acc][column][row], rows adjacent: conflict-free
+        // writes here and coalesced distributed-shared-memory reads in the reduction below), in this CTA's shared memory
+        for (int a = 0; a < n_acc; ++a)
+          for (int c = 0; c < BN / CW; ++c) {
+            float v[CW];
+            if constexpr (CW == 32) tmem_ld32(lane_base + acc_col(a, par) + c * CW, v);
+            else tmem_ld16(lane_base + acc_col(a, par) + c * CW, v);
+            tmem_ld_wait();
+            const uint32_t dst = sStage + static_cast<uint32_t>(((a * BN + c * CW) * 128 + m) * 4);
+#pragma unroll
+            for (int j = 0; j < CW; ++j) asm volatile("st.shared.f32 [%0], %1;" ::"r"(dst + j * 512), "f"(v[j]) : "memory");
+          }
+      } else if (p.ksplit > 1) {
         // partial sums: add the raw accumulators into the fp32 workspace; tapconv_finish_kernel applies the epilogue
         const long pix = ((static_cast<long>(seq) * p.T + t) * p.H + h) * p.W + w;
         for (int a = 0; a < n_acc; ++a) {
@@ -459,14 +476,14 @@ __global__ void __launch_bounds__(TAPCONV_THREADS, 1) tapconv_kernel(const __gri
                   }
               }
               if (p.epi == EPI_GATED && p.out_d != nullptr) {
-                float* dd = static_cast<float*>(p.out_d) + row_off + col0;
+                __half* dd = static_cast<__half*>(p.out_d) + row_off + col0;
 #pragma unroll
-                for (int j = 0; j < CW; j += 8)
-                  if (col0 + j + 8 <= p.Cout) {
-                    float dv[8];
+                for (int j = 0; j < CW; j += 16)
+                  if (col0 + j + 16 <= p.Cout) {
+                    uint32_t pk[8];
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) dv[u] = shr[j + u] - own[j + u];
-                    st_global_f32x8(dd + j, dv);
+                    for (int u = 0; u < 8; ++u) pk[u] = pack_f16x2(shr[j + 2 * u] - own[j + 2 * u], shr[j + 2 * u + 1] - own[j + 2 * u + 1]);
+                    st_global_b32x8(dd + j, pk);
                   }
               }
             } else {
@@ -484,13 +501,15 @@ __global__ void __launch_bounds__(TAPCONV_THREADS, 1) tapconv_kernel(const __gri
                                                                   pack_bf16x2(y[j + 4], y[j + 5]), pack_bf16x2(y[j + 6], y[j + 7]));
             }
             if (p.epi == EPI_GATED && p.out_d != nullptr) {
-              // fp32 on purpose: <dy, d> feeds the gate scalars' gradients and bf16 rounding of d shows up there at ~2%
-              float* dd = static_cast<float*>(p.out_d) + row_off + col0;
+              // fp16, not bf16: <dy, d> feeds the gate scalars' gradients, where bf16 rounding of d shows up at ~2 %; fp16
+              // carries three more mantissa bits at the same two bytes (|d| is O(1): far inside fp16's range)
+              __half* dd = static_cast<__half*>(p.out_d) + row_off + col0;
 #pragma unroll
-              for (int j = 0; j < CW; j += 4)
-                if (col0 + j + 4 <= p.Cout)
-                  *reinterpret_cast<float4*>(dd + j) =
-                      make_float4(shr[j] - own[j], shr[j + 1] - own[j + 1], shr[j + 2] - own[j + 2], shr[j + 3] - own[j + 3]);
+              for (int j = 0; j < CW; j += 8)
+                if (col0 + j + 8 <= p.Cout)
+                  *reinterpret_cast<uint4*>(dd + j) =
+                      make_uint4(pack_f16x2(shr[j] - own[j], shr[j + 1] - own[j + 1]), pack_f16x2(shr[j + 2] - own[j + 2], shr[j + 3] - own[j + 3]),
+                                 pack_f16x2(shr[j + 4] - own[j + 4], shr[j + 5] - own[j + 5]), pack_f16x2(shr[j + 6] - own[j + 6], shr[j + 7] - own[j + 7]));
             }
             }
           }
@@ -510,6 +529,72 @@ __global__ void __launch_bounds__(TAPCONV_THREADS, 1) tapconv_kernel(const __gri
   }
 
   __syncthreads();
+  if constexpr (!PAIR) {
+    if (p.csplit) {
+      // ---- cluster split-K reduction: CTA r of the cluster finishes rows [r*128/ks, (r+1)*128/ks) of the tile.  Each of
+      // its 128 epilogue threads owns one row and BN/ks columns, sums the ks partial values of every accumulator straight
+      // out of the peers' shared memory and applies the ordinary output stage (gate combine, bf16 store, fp16 difference).
+      cluster_sync_all();                       // every CTA's partials are staged and visible cluster-wide
+      if (warp >= 3) {
+        const int ks = p.ksplit, rows_per = 128 / ks, cols_per = BN / ks;
+        const int t128 = threadIdx.x - 96;
+        const int m = static_cast<int>(blockIdx.y) * rows_per + t128 % rows_per;
+        const int col_lo = (t128 / rows_per) * cols_per;
+        const Tile tc = decode(blockIdx.x);
+        const int hh = m / (p.bt * p.bw), rem = m - hh * (p.bt * p.bw), tt = rem / p.bw, ww = rem - tt * p.bw;
+        const int t = tc.t0 + tt, h = tc.h0 + hh, w = tc.w0 + ww;
+        const bool row_ok = (t < p.T) && (h < p.H) && (w < p.W) && (tc.seq < p.n_seq);
+        uint32_t peer[8];
+#pragma unroll
+        for (int s = 0; s < 8; ++s) peer[s] = s < ks ? mapa_cluster(sStage, static_cast<uint32_t>(s)) : 0u;
+        for (int c0 = col_lo; c0 < col_lo + cols_per; c0 += 8) {
+          float shr[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) shr[j] = 0.f;
+          if (p.epi == EPI_GATED) {
+            for (int s = 0; s < ks; ++s) {
+              const uint32_t src = peer[s] + static_cast<uint32_t>(((p.n_out * BN + c0) * 128 + m) * 4);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) shr[j] += ld_cluster_f32(src + j * 512);
+            }
+          }
+          for (int o = 0; o < p.n_out; ++o) {
+            float own[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) own[j] = 0.f;
+            for (int s = 0; s < ks; ++s) {
+              const uint32_t src = peer[s] + static_cast<uint32_t>(((o * BN + c0) * 128 + m) * 4);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) own[j] += ld_cluster_f32(src + j * 512);
+            }
+            const int col = tc.n0 + c0;
+            if (!row_ok || col + 8 > p.Cout) continue;
+            const long frame = static_cast<long>(tc.seq * p.n_out + o) * p.T + t;
+            float al = 1.f, be = 0.f;
+            if (p.epi == EPI_GATED) { al = p.alpha[frame]; be = p.beta[frame]; }
+            const long off = ((frame * p.H + h) * p.W + w) * static_cast<long>(p.Cout) + col;
+            float y[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) y[j] = al * own[j] + be * shr[j];
+            if (p.out_f32) {
+              float* dst = static_cast<float*>(p.out) + off;
+              *reinterpret_cast<float4*>(dst) = make_float4(y[0], y[1], y[2], y[3]);
+              *reinterpret_cast<float4*>(dst + 4) = make_float4(y[4], y[5], y[6], y[7]);
+            } else {
+              *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + off) =
+                  make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
+            }
+            if (p.epi == EPI_GATED && p.out_d != nullptr) {
+              *reinterpret_cast<uint4*>(static_cast<__half*>(p.out_d) + off) =
+                  make_uint4(pack_f16x2(shr[0] - own[0], shr[1] - own[1]), pack_f16x2(shr[2] - own[2], shr[3] - own[3]),
+                             pack_f16x2(shr[4] - own[4], shr[5] - own[5]), pack_f16x2(shr[6] - own[6], shr[7] - own[7]));
+            }
+          }
+        }
+      }
+      cluster_sync_all();                       // no CTA leaves while a peer may still read its staging area
+    }
+  }
   if constexpr (PAIR) cluster_sync_all();   // the peer has consumed every multicast arrival and drained its accumulators
   if (warp == 1) {
     tc_fence_after();
@@ -521,7 +606,7 @@ __global__ void __launch_bounds__(TAPCONV_THREADS, 1) tapconv_kernel(const __gri
 // as the fused epilogue (gate combine, bf16 / fp32 store, optional fp32 difference tensor).
 static __global__ void __launch_bounds__(256) tapconv_finish_kernel(const float* __restrict__ ws, const float* __restrict__ alpha,
                                                              const float* __restrict__ beta, void* __restrict__ out,
-                                                             float* __restrict__ out_d, int n_seq, int n_out, int T,
+                                                             __half* __restrict__ out_d, int n_seq, int n_out, int T,
                                                              long hw, int Cout, int epi, int out_f32) {
   pdl_launch_dependents();
   pdl_wait();
@@ -545,7 +630,7 @@ static __global__ void __launch_bounds__(256) tapconv_finish_kernel(const float*
     const float4 shr = *reinterpret_cast<const float4*>(ws + (static_cast<long>(n_out) * rows_per_set + pix) * Cout + c);
     const float al = alpha[frame], be = beta[frame];
     y = make_float4(al * own.x + be * shr.x, al * own.y + be * shr.y, al * own.z + be * shr.z, al * own.w + be * shr.w);
-    if (out_d) *reinterpret_cast<float4*>(out_d + orow * Cout + c) = make_float4(shr.x - own.x, shr.y - own.y, shr.z - own.z, shr.w - own.w);
+    if (out_d) *reinterpret_cast<uint2*>(out_d + orow * Cout + c) = make_uint2(pack_f16x2(shr.x - own.x, shr.y - own.y), pack_f16x2(shr.z - own.z, shr.w - own.w));
   }
   if (out_f32) *reinterpret_cast<float4*>(static_cast<float*>(out) + orow * Cout + c) = y;
   else *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(out) + orow * Cout + c) = make_uint2(pack_bf16x2(y.x, y.y), pack_bf16x2(y.z, y.w));

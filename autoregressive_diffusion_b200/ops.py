@@ -3,7 +3,9 @@
 Tensor convention: activations are bf16 tensors of LOGICAL shape [frames, C, H, W] in channels_last memory
 format, i.e. physically [frames, H, W, C] -- the NHWC rows the kernels read.  `rows()` converts anything else.
 """
+import ctypes
 import math
+import weakref
 
 import torch
 
@@ -75,6 +77,60 @@ def weight_operand(params, taps, cin, cin_pad, gains, training, eps=1e-4):
         call("ob_wnorm_fwd", _vp(p), _vp(wg), cout, cin, t, cin_pad, total, off, float(g), eps, int(training), stream_ptr())
         off += t
     return wg
+
+
+class _WnormJob(ctypes.Structure):
+    """include/oniris_b200.h: ob_wnorm_job."""
+    _fields_ = [("w", ctypes.c_void_p), ("wg", ctypes.c_void_p), ("cin", ctypes.c_int32), ("taps", ctypes.c_int32),
+                ("cin_pad", ctypes.c_int32), ("taps_total", ctypes.c_int32), ("tap_off", ctypes.c_int32),
+                ("training", ctypes.c_int32), ("gain", ctypes.c_float), ("pad_", ctypes.c_int32)]
+
+
+class OperandBank:
+    """Every conv layer's bf16 GEMM operand, refreshed by ONE ob_wnorm_fwd_multi launch.
+
+    An optimizer step makes all operands of a network stale at the same moment; refreshing them layer by layer is ~210
+    launches of ~13 us per step on the Counter-Strike UNet (latency-bound, 0.22 of the HBM roofline).  Layers register
+    their operand once (conv._OperandCache); the first layer to find its operand stale refreshes, in one launch, every
+    registered operand of the device that is stale too and was last used in the same mode -- forced weight normalisation
+    included when training (edm2/conv.py:16-18) -- and the others then find theirs fresh.  Operands that are up to date
+    (another, frozen model) or that belong to layers in the other mode are never touched.  The job table lives on the
+    device and is rebuilt only when the set of stale layers or a parameter's storage changes."""
+
+    _entries = {}      # device index -> [weakref(_OperandCache)]
+    _tables = {}       # device index -> (signature, jobs tensor, row_start tensor, n_jobs, total_rows)
+
+    @classmethod
+    def register(cls, cache):
+        cls._entries.setdefault(cache.params[0].device.index, []).append(weakref.ref(cache))
+
+    @classmethod
+    def refresh(cls, requester, training, eps=1e-4):
+        device = requester.params[0].device
+        dev = device.index
+        caches = [c for c in (r() for r in cls._entries.get(dev, [])) if c is not None]
+        cls._entries[dev] = [weakref.ref(c) for c in caches]
+        todo = [c for c in caches if c is requester or (c.last_training == bool(training) and c.stale(training))]
+        sig = tuple((p.data_ptr(), c.wg.data_ptr()) for c in todo for p in c.params) + (bool(training),)
+        tab = cls._tables.get(dev)
+        if tab is None or tab[0] != sig:
+            jobs, starts, row = [], [], 0
+            for c in todo:
+                off, total = 0, sum(c.taps)
+                for p, t, g in zip(c.params, c.taps, c.gains):
+                    assert p.dtype == torch.float32 and tap_major(p), "conv weights are stored tap-major (channels_last)"
+                    jobs.append(_WnormJob(p.data_ptr(), c.wg.data_ptr(), c.cin, t, c.cin_pad, total, off, int(training), float(g), 0))
+                    starts.append(row)
+                    row += p.shape[0]
+                    off += t
+            starts.append(row)
+            raw = bytearray(b"".join(bytes(j) for j in jobs))
+            tab = cls._tables[dev] = (sig, torch.frombuffer(raw, dtype=torch.uint8).to(device),
+                                      torch.tensor(starts, dtype=torch.int32, device=device), len(jobs), row)
+        _, jobs_t, starts_t, n_jobs, rows_total = tab
+        call("ob_wnorm_fwd_multi", _vp(jobs_t), _vp(starts_t), n_jobs, rows_total, eps, stream_ptr())
+        for c in todo:
+            c.mark_fresh(training)
 
 
 def tap_major(p):
@@ -260,7 +316,7 @@ class PlainConvFn(torch.autograd.Function):
         out = empty_rows(f, cout_pad, h, wd, x.device, torch.float32 if out_f32 else BF16)
         ws = split_workspace(1, 1, f, h, wd, cin_pad, cout_pad, ksize, 0, x.device)
         call("ob_conv_fwd", _vp(x), None, _vp(wg), None, None, _vp(out), None, _vp(ws), 1, 1, f, h, wd, cin_pad, cout_pad, ksize,
-             0, int(out_f32), stream_ptr())
+             0, int(out_f32), wg.shape[1], stream_ptr())
         ctx.save_for_backward(x, w, wg)
         ctx.ksize, ctx.gain = ksize, gain
         return out if cout_pad == cout else out[:, :cout]
@@ -277,7 +333,7 @@ class PlainConvFn(torch.autograd.Function):
             dx = empty_rows(f, cin_pad, h, wd, x.device)
             ws = split_workspace(1, 1, f, h, wd, cout, cin_pad, k, 0, x.device)
             call("ob_conv_dgrad", _vp(gy), None, _vp(wg), None, None, _vp(dx), _vp(ws), 1, 1, f, h, wd, cin_pad, cout, k, 0,
-                 stream_ptr())
+                 wg.shape[1], stream_ptr())
         dw = None
         if ctx.needs_input_grad[1]:
             gain = ctx.gain
@@ -319,10 +375,10 @@ class GatedConvFn(torch.autograd.Function):
              _vp(g_mult), _vp(g_max), _vp(g_min), _vp(c_noise), _vp(alpha), _vp(beta), _vp(scratch), n_ctx,
              pad5.stride(0) if pad5 is not None else 0, _vp(n_ctx_dev), stream_ptr())
         out = empty_rows(f, cout, h, wd, dev)
-        out_d = empty_rows(f, cout, h, wd, dev, torch.float32) if want_grad else None
+        out_d = empty_rows(f, cout, h, wd, dev, torch.float16) if want_grad else None
         ws = split_workspace(n_seq, S, T, h, wd, cin_pad, cout, 3, 1, dev)
         call("ob_conv_fwd", _vp(x), _vp(cx), _vp(wg), _vp(alpha), _vp(beta), _vp(out), _vp(out_d), _vp(ws), n_seq, S, T, h, wd,
-             cin_pad, cout, 3, 1, 0, stream_ptr())
+             cin_pad, cout, 3, 1, 0, 27, stream_ptr())
         if want_grad:
             ctx.save_for_backward(x, cx, w2, w3, wg, ab, out, out_d, g_offset, g_mult, g_max, g_min, c_noise, scratch)
         ctx.dims = (n_seq, S, T, n_ctx)
@@ -380,7 +436,7 @@ class GatedConvFn(torch.autograd.Function):
             dx = empty_rows(f, cin_pad, h, wd, dev)
             ws = split_workspace(n_seq, S, T, h, wd, cout, cin_pad, 3, 1, dev)
             call("ob_conv_dgrad", _vp(gy), _vp(gb), _vp(wg), _vp(alpha), _vp(clean_rows_mask(n_seq, S, T, dev)), _vp(dx),
-                 _vp(ws), n_seq, S, T, h, wd, cin_pad, cout, 3, 1, stream_ptr())
+                 _vp(ws), n_seq, S, T, h, wd, cin_pad, cout, 3, 1, 27, stream_ptr())
         if direct:
             return (dx,) + (None,) * 15
         return (dx, None, dw2, dw3, None) + gate_grads + (None,) * 7

@@ -114,7 +114,9 @@ HBM_BYTES = {
     # (x, pad, ctx, b, S, T, frame_elems, ...): the clean frames copied into the context tensor
     "ob_conv_prologue": lambda a: a[3] * a[5] * a[6] * 4,
 }
-D_BYTES = 4     # bytes per element of the saved context-minus-current term the gate backward re-reads
+WNORM_MULTI_BYTES = [0]   # set once the model exists: 4 B read + 4 B forced-weight write + 2 B operand per conv weight element
+HBM_BYTES["ob_wnorm_fwd_multi"] = lambda a: WNORM_MULTI_BYTES[0]
+D_BYTES = 2     # bytes per element of the saved context-minus-current term the gate backward re-reads
 
 
 class KernelProfiler:
@@ -264,6 +266,7 @@ def run_ours(args):
     tr = Trainer(CS_UNET, accumulation_steps=4, device=dev, seed=42, just_2d_every=0 if args.no_2d else 4)
     with torch.no_grad():
         tr.unet.out_gain.fill_(1.0)     # random-init benchmark weights: the reference's zero init would zero every gradient
+    WNORM_MULTI_BYTES[0] = 10 * sum(p.numel() for p in tr.params if p.ndim >= 4)
     dbg("trainer built")
     shape = (MICRO_BATCH, CLIP, 8, 32, 32)
     g = torch.Generator().manual_seed(1234 + rank)

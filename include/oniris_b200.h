@@ -46,6 +46,18 @@ const char* ob_last_error(void);
 int ob_wnorm_fwd(float* w, void* wg, int cout, int cin, int taps, int cin_pad, int taps_total, int tap_off, float gain,
                  float eps, int training, void* stream);
 
+/* The same for MANY weight tensors in one launch (an optimizer step invalidates every operand of a network at once).
+ * jobs: DEVICE array of n_jobs descriptors; row_start: DEVICE int32 [n_jobs + 1], row_start[j] = sum of cout of the jobs
+ * before j (row_start[n_jobs] = total_rows).  Field meaning as the arguments of ob_wnorm_fwd. */
+typedef struct ob_wnorm_job {
+  float* w;
+  void* wg;
+  int32_t cin, taps, cin_pad, taps_total, tap_off, training;
+  float gain;
+  int32_t pad_;
+} ob_wnorm_job;
+int ob_wnorm_fwd_multi(const ob_wnorm_job* jobs, const int* row_start, int n_jobs, int total_rows, float eps, void* stream);
+
 /* Backward of the above w.r.t. the (forced) weights: dwg fp32 [n_split][Cout][taps_total][cin_pad] are the
  * split-K partial sums written by ob_conv_wgrad; dw fp32 [Cout][taps][Cin] (same storage order as w) is overwritten, or
  * (accumulate != 0) added to -- gradient accumulation over micro-batches (cs_train.py:108-109) without a separate pass.
@@ -62,8 +74,11 @@ int ob_wnorm_bwd_gated(const float* w2, float* dw2, const float* w3, float* dw3,
  *                           + beta[b,s,t]  * sum_{tau in {0,1}} conv3x3(ctx[b, t+tau], wg[:, 9+9*tau : 18+9*tau])
  *                ctx: bf16 [n_seq, T+2, H, W, Cin] = two pad frames (ones, or the cached activations) followed
  *                by the T clean frames; the context term is computed ONCE per (b,t) and shared by both halves.
- *                out_d (optional, may be NULL): fp32, context term minus current-frame term (saved for backward).
+ *                out_d (optional, may be NULL): fp16, context term minus current-frame term (saved for backward; its inner
+ *                product with dy feeds the gate scalars' gradients: fp16 keeps 11 mantissa bits at bf16's two bytes).
  * out: [n_seq*S*T, H, W, Cout], bf16 or (out_f32 != 0) fp32.  alpha/beta: fp32 [n_seq*S*T].
+ * w_taps (plain convs; 0 = ksize*ksize): taps per row of wg -- 27 lets the 2-D form of a gated conv (just_2d, edm2/conv.py:60)
+ * read the first 9 taps of the SAME operand matrix the gated form uses (one operand, one normalisation per weight).
  * split_ws (optional, may be NULL): fp32 scratch sized by ob_conv_split_ws_bytes.  When given and the layer has too
  * few output tiles for 148 SMs (the 4x4 / 8x8 levels), the channel chunks are sliced over extra CTAs and reduced there
  * (split-K); the call zeroes it itself.  For the input gradient pass query with cin/cout SWAPPED (it is the transposed
@@ -71,7 +86,7 @@ int ob_wnorm_bwd_gated(const float* w2, float* dw2, const float* w3, float* dw3,
 int64_t ob_conv_split_ws_bytes(int n_seq, int S, int T, int H, int W, int cin, int cout, int ksize, int gated);
 int ob_conv_fwd(const void* x, const void* ctx, const void* wg, const float* alpha, const float* beta, void* out,
                 void* out_d, void* split_ws, int n_seq, int S, int T, int H, int W, int cin, int cout, int ksize, int gated,
-                int out_f32, void* stream);
+                int out_f32, int w_taps, void* stream);
 
 /* Input gradient of ob_conv_fwd.  gy: bf16 [n_seq*S*T, H, W, Cout] = dL/dout (unscaled);
  * gated: gb: bf16 [n_seq*T, H, W, Cout] = sum_s beta_s*dL/dout_s (from ob_gate_bwd) and
@@ -81,7 +96,7 @@ int ob_conv_fwd(const void* x, const void* ctx, const void* wg, const float* alp
  * dx: bf16 [n_seq*S*T, H, W, Cin].  Reads the SAME wg as the forward pass (as an MN-major operand). */
 int ob_conv_dgrad(const void* gy, const void* gb, const void* wg, const float* alpha, const float* beta, void* dx,
                   void* split_ws, int n_seq, int S, int T, int H, int W, int cin, int cout, int ksize, int gated,
-                  void* stream);
+                  int w_taps, void* stream);
 
 /* Weight gradient of ob_conv_fwd into dwg fp32 [n_split][Cout][taps][Cin] (taps = k*k or 27).  n_split must come
  * from ob_conv_wgrad_splits for the same shape. */
@@ -90,7 +105,7 @@ int ob_conv_wgrad(const void* gya, const void* x, const void* gb, const void* ct
                   int H, int W, int cin, int cout, int ksize, int gated, int n_split, void* stream);
 
 /* Backward pre-pass of the gate (mp_sum with a per-frame tensor t, edm2/conv.py:95 -> edm2/utils.py:122-123):
- * from dy, the saved y (bf16) and d (fp32) it emits gya = alpha*dy, gb = sum_s beta*dy and the per-frame inner products
+ * from dy, the saved y (bf16) and d (fp16) it emits gya = alpha*dy, gb = sum_s beta*dy and the per-frame inner products
  * s_y[f] += <dy,y>, s_d[f] += <dy,d> (fp32 [n_seq*S*T], must be zeroed by the caller) that the five Gating
  * scalars' gradients are built from. */
 int ob_gate_bwd(const void* dy, const void* y, const void* d, const float* alpha, const float* beta, void* gya, void* gb,

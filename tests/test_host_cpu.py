@@ -164,8 +164,12 @@ def test_tiling_policy_queries_run_without_a_gpu():
     from autoregressive_diffusion_b200 import _lib
     q = lambda *a: _lib.query("ob_conv_split_ws_bytes", *a)
     # (n_seq, S, T, H, W, cin, cout, ksize, gated)
-    assert q(2, 2, 16, 4, 4, 512, 512, 3, 1) == 3 * 2 * 16 * 16 * 512 * 4          # 4x4 level: split, 3 accumulators
-    assert q(2, 2, 16, 8, 8, 512, 512, 3, 1) > 0
+    # (ONIRIS_CSPLIT=1, the experimental cluster reduction through distributed shared memory, needs no workspace)
+    if os.environ.get("ONIRIS_CSPLIT", "0") != "1":
+        assert q(2, 2, 16, 4, 4, 512, 512, 3, 1) == 3 * 2 * 16 * 16 * 512 * 4      # 4x4 level: split, 3 accumulators
+        assert q(2, 2, 16, 8, 8, 512, 512, 3, 1) > 0
+    else:
+        assert q(2, 2, 16, 4, 4, 512, 512, 3, 1) == 0 and q(2, 2, 16, 8, 8, 512, 512, 3, 1) == 0
     assert q(2, 2, 16, 32, 32, 128, 128, 3, 1) == 0                                 # enough tiles: no split
     assert q(1, 1, 64, 4, 4, 512, 512, 1, 0) == 0                                   # 1x1: K loop too short to split
     s = lambda *a: _lib.query("ob_conv_wgrad_splits", *a)

@@ -1,7 +1,14 @@
 set -x
 mkdir -p gpurun_out
 rm -f gpurun_out/r02_parity_report.tsv
-ONIRIS_PARITY_REPORT=gpurun_out/r02_parity_report.tsv timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -80 > gpurun_out/r02_gputest3.log
-tail -50 gpurun_out/r02_gputest3.log
-NO_CPU=1 N_GEN=8 timeout 900 python tools/bench_sampling.py > gpurun_out/r02_sampling.log 2>&1
-tail -12 gpurun_out/r02_sampling.log
+ONIRIS_PARITY_REPORT=gpurun_out/r02_parity_report.tsv timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -40 > gpurun_out/r02_gputest5.log
+tail -25 gpurun_out/r02_gputest5.log
+timeout 600 python bench.py --steps 40 --warmup 5 --no-cpu-baseline > gpurun_out/r02_bench2.json 2> gpurun_out/r02_bench2.err
+tail -3 gpurun_out/r02_bench2.err
+python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/r02_bench2.json').read().strip().splitlines()[-1])
+print(d['value'], d['ms_per_step'], d['e2e']['value'], d['roofline']['achieved'], d['roofline']['frac'])
+for k in d['roofline_hbm']['kernels']: print(k)
+print(d['roofline_hbm']['other_entry_points_ms_per_cycle'], d['roofline_hbm']['serial_cycle_ms'])
+PY
