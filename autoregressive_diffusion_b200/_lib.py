@@ -34,7 +34,7 @@ _SIGS = {
     "ob_wnorm_fwd_multi": "ppiifp",
     "ob_wnorm_bwd_gated": "pppppiiiifip",
     "ob_wnorm_bwd": "pppiiiiiiiffip",
-    "ob_conv_fwd": "ppppppppiiiiiiiiiiip",
+    "ob_conv_fwd": "ppppppppiiiiiiiiiiipp",
     "ob_conv_dgrad": "pppppppiiiiiiiiiip",
     "ob_conv_split_ws_bytes": "iiiiiiiii",
     "ob_conv_wgrad_splits": "iiiiiiiii",
@@ -54,6 +54,8 @@ _SIGS = {
     "ob_mp_cat_fwd": "pppliifp",
     "ob_mp_cat_bwd": "pppliifp",
     "ob_resample2x": "ppliiiifp",
+    "ob_vae_norm_silu_fwd": "pppiliifp",
+    "ob_vae_norm_silu_bwd": "pppppiliifp",
     "ob_set_pdl": "i",
     "ob_adamw_ema": "pppppplpfffffffffp",
     "ob_sumsq": "plpp",

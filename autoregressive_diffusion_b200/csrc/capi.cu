@@ -89,7 +89,7 @@ int64_t ob_conv_split_ws_bytes(int n_seq, int S, int T, int H, int W, int cin, i
 
 int ob_conv_fwd(const void* x, const void* ctx, const void* wg, const float* alpha, const float* beta, void* out,
                 void* out_d, void* split_ws, int n_seq, int S, int T, int H, int W, int cin, int cout, int ksize, int gated,
-                int out_f32, int w_taps, void* stream) {
+                int out_f32, int w_taps, const float* bias, void* stream) {
   if (int r = check_shape("ob_conv_fwd", n_seq, S, T, H, W, ksize, gated)) return r;
   TapConvLaunch L;
   std::vector<TapCol> cols;
@@ -114,6 +114,8 @@ int ob_conv_fwd(const void* x, const void* ctx, const void* wg, const float* alp
   }
   L.wg = wg; L.cols = cols.data(); L.n_cols = (int)cols.size();
   L.H = H; L.W = W; L.Cin = cin; L.Cout = cout; L.out_f32 = out_f32; L.out = out; L.split_ws = (float*)split_ws;
+  if (bias != nullptr && gated) { set_error("ob_conv_fwd: bias is supported for plain convs only"); return OB_ERR_INVALID; }
+  L.bias = bias;
   return tapconv_launch(L, (cudaStream_t)stream);
 }
 
@@ -244,6 +246,14 @@ int ob_mp_cat_bwd(const void* g, void* da, void* db, int64_t rows, int ca, int c
 }
 int ob_resample2x(const void* in, void* out, int64_t frames, int h, int w, int c, int pool, float scale, void* stream) {
   return resample2x(in, out, (long)frames, h, w, c, pool, scale, (cudaStream_t)stream);
+}
+int ob_vae_norm_silu_fwd(const void* x, const float* film, void* out, int b, int64_t rows_per_batch, int c, int c_mean, float eps,
+                         void* stream) {
+  return vae_norm_silu_fwd(x, film, out, b, (long)rows_per_batch, c, c_mean, eps, (cudaStream_t)stream);
+}
+int ob_vae_norm_silu_bwd(const void* x, const float* film, const void* g, void* dx, float* dfilm, int b, int64_t rows_per_batch,
+                         int c, int c_mean, float eps, void* stream) {
+  return vae_norm_silu_bwd(x, film, g, dx, dfilm, b, (long)rows_per_batch, c, c_mean, eps, (cudaStream_t)stream);
 }
 int ob_set_pdl(int enabled) {
   static const bool forced_off = [] { const char* e = getenv("ONIRIS_PDL"); return e != nullptr && e[0] == '0'; }();

@@ -35,6 +35,10 @@ int scale_silu_bwd(const void* y, const float* cscale, const void* g, void* dy, 
 int mp_sum_fwd(const void* a, const void* b, void* out, long n, float t, float clip, cudaStream_t st);
 int mp_sum_bwd(const void* g, const void* out, void* da, void* db, long n, float t, float clip, cudaStream_t st);
 int mp_cat(void* a, void* b, void* cat, long rows, int ca, int cb, float t, int backward, cudaStream_t st);
+int vae_norm_silu_fwd(const void* x, const float* film, void* out, int B, long rows_per_batch, int C, int c_mean, float eps,
+                      cudaStream_t st);
+int vae_norm_silu_bwd(const void* x, const float* film, const void* g, void* dx, float* dfilm, int B, long rows_per_batch, int C,
+                      int c_mean, float eps, cudaStream_t st);
 int resample2x(const void* in, void* out, long frames, int h, int w, int c, int pool, float scale, cudaStream_t st);
 int adamw_ema(float* p, float* g, float* m, float* v, float* e1, float* e2, long n, const float* opt_state, float beta1,
               float beta2, float eps, float wd, float ema_a1, float ema_a2, float ema_ratio, float grad_scale, float max_norm,

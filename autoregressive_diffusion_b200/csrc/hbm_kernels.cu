@@ -1018,6 +1018,164 @@ int mp_cat(void* a, void* b, void* cat, long rows, int ca, int cb, float t, int 
   return check_launch("mp_cat");
 }
 
+// ============================================================================ VAE ResBlock activation
+// Reference: edm2/vae/vae.py:77-83 and :86-87 --  y = x / sqrt(mean_c(x^2) + eps);  [y = y*(1+scale_b) + shift_b  (the
+// decoder's FiLM from t_cond)];  out = silu(y).  The reference runs it as ~7 eager kernels forward and ~15 backward over
+// the largest activations of the VAE (up to 16x256x256x32); here one pass each way, fp32 arithmetic, bf16 in / out, the
+// input recomputed (not saved) in the backward.  One warp per pixel row of C channels (C % 8 == 0, C <= 1024); a CTA's
+// rows all belong to one batch element (blockIdx.y) so the FiLM gradients reduce in registers -> shared memory -> one
+// atomicAdd per (CTA, channel).  film: fp32 [B][2C] = (scale | shift), or nullptr.
+constexpr int VNS_MAXV = 4;   // 8-channel vectors per lane
+__device__ __forceinline__ float silu_f(float y) { return y / (1.f + __expf(-y)); }
+
+__global__ void __launch_bounds__(256) vae_norm_silu_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ film,
+                                                                __nv_bfloat16* __restrict__ out, long rows_per_batch, int C,
+                                                                int c_mean, float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.y;
+  const float* fs = film ? film + static_cast<long>(b) * 2 * C : nullptr;
+  for (long r = static_cast<long>(blockIdx.x) * 8 + warp; r < rows_per_batch; r += static_cast<long>(gridDim.x) * 8) {
+    const long off = (static_cast<long>(b) * rows_per_batch + r) * C;
+    float v[VNS_MAXV][8];
+    float ss = 0.f;
+#pragma unroll
+    for (int k = 0; k < VNS_MAXV; ++k) {
+      const int c = lane * 8 + k * 256;
+      if (c < C) {
+        unpack8(*reinterpret_cast<const bf16x8*>(x + off + c), v[k]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ss += v[k][j] * v[k][j];
+      }
+    }
+    const float inv = rsqrtf(warp_sum(ss) / c_mean + eps);
+#pragma unroll
+    for (int k = 0; k < VNS_MAXV; ++k) {
+      const int c = lane * 8 + k * 256;
+      if (c < C) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float y = v[k][j] * inv;
+          if (fs) y = y * (1.f + fs[c + j]) + fs[C + c + j];
+          o[j] = silu_f(y);
+        }
+        *reinterpret_cast<bf16x8*>(out + off + c) = pack8(o);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) vae_norm_silu_bwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ film,
+                                                                const __nv_bfloat16* __restrict__ g, __nv_bfloat16* __restrict__ dx,
+                                                                float* __restrict__ dfilm, long rows_per_batch, int C, int c_mean,
+                                                                float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
+  extern __shared__ float sh[];          // FILM: [2C] per-CTA partial sums of (dscale | dshift)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.y;
+  const float* fs = film ? film + static_cast<long>(b) * 2 * C : nullptr;
+  float a_scale[VNS_MAXV][8], a_shift[VNS_MAXV][8];
+#pragma unroll
+  for (int k = 0; k < VNS_MAXV; ++k)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { a_scale[k][j] = 0.f; a_shift[k][j] = 0.f; }
+  if (fs) {
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sh[i] = 0.f;
+    __syncthreads();
+  }
+  for (long r = static_cast<long>(blockIdx.x) * 8 + warp; r < rows_per_batch; r += static_cast<long>(gridDim.x) * 8) {
+    const long off = (static_cast<long>(b) * rows_per_batch + r) * C;
+    float n[VNS_MAXV][8], gn[VNS_MAXV][8];
+    float ss = 0.f;
+#pragma unroll
+    for (int k = 0; k < VNS_MAXV; ++k) {
+      const int c = lane * 8 + k * 256;
+      if (c < C) {
+        unpack8(*reinterpret_cast<const bf16x8*>(x + off + c), n[k]);
+        unpack8(*reinterpret_cast<const bf16x8*>(g + off + c), gn[k]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ss += n[k][j] * n[k][j];
+      }
+    }
+    const float inv = rsqrtf(warp_sum(ss) / c_mean + eps);
+    float dot = 0.f;
+#pragma unroll
+    for (int k = 0; k < VNS_MAXV; ++k) {
+      const int c = lane * 8 + k * 256;
+      if (c < C) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float nn = n[k][j] * inv;
+          float y = nn, sc = 1.f;
+          if (fs) { sc = 1.f + fs[c + j]; y = nn * sc + fs[C + c + j]; }
+          const float sg = 1.f / (1.f + __expf(-y));
+          const float gy = gn[k][j] * sg * (1.f + y * (1.f - sg));     // through silu
+          if (fs) { a_shift[k][j] += gy; a_scale[k][j] += gy * nn; }
+          n[k][j] = nn;
+          gn[k][j] = gy * sc;                                           // gradient w.r.t. the normalised value
+          dot += gn[k][j] * nn;
+        }
+      }
+    }
+    dot = warp_sum(dot) / c_mean;
+#pragma unroll
+    for (int k = 0; k < VNS_MAXV; ++k) {
+      const int c = lane * 8 + k * 256;
+      if (c < C) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = inv * (gn[k][j] - n[k][j] * dot);
+        *reinterpret_cast<bf16x8*>(dx + off + c) = pack8(o);
+      }
+    }
+  }
+  if (fs) {
+#pragma unroll
+    for (int k = 0; k < VNS_MAXV; ++k) {
+      const int c = lane * 8 + k * 256;
+      if (c < C) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { atomicAdd(&sh[c + j], a_scale[k][j]); atomicAdd(&sh[C + c + j], a_shift[k][j]); }
+      }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(&dfilm[static_cast<long>(b) * 2 * C + i], sh[i]);
+  }
+}
+
+static int vns_grid(long rows_per_batch, int B) {
+  long bx = (rows_per_batch + 7) / 8;
+  const long cap = (8L * 148 + B - 1) / B;       // ~8 CTAs per SM in total
+  if (bx > cap) bx = cap;
+  return static_cast<int>(bx < 1 ? 1 : bx);
+}
+
+int vae_norm_silu_fwd(const void* x, const float* film, void* out, int B, long rows_per_batch, int C, int c_mean, float eps,
+                      cudaStream_t st) {
+  if (c_mean <= 0 || c_mean > C) c_mean = C;
+  if (C % 8 != 0 || C > 256 * VNS_MAXV) { set_error("vae_norm_silu: C=%d must be a multiple of 8 and <= %d", C, 256 * VNS_MAXV); return OB_ERR_UNSUPPORTED; }
+  if (B <= 0 || rows_per_batch <= 0) return OB_OK;
+  launch(vae_norm_silu_fwd_kernel, dim3(vns_grid(rows_per_batch, B), B), 256, 0, st, 1, static_cast<const __nv_bfloat16*>(x), film,
+         static_cast<__nv_bfloat16*>(out), rows_per_batch, C, c_mean, eps);
+  return check_launch("vae_norm_silu_fwd");
+}
+
+int vae_norm_silu_bwd(const void* x, const float* film, const void* g, void* dx, float* dfilm, int B, long rows_per_batch, int C,
+                      int c_mean, float eps, cudaStream_t st) {
+  if (c_mean <= 0 || c_mean > C) c_mean = C;
+  if (C % 8 != 0 || C > 256 * VNS_MAXV) { set_error("vae_norm_silu: C=%d must be a multiple of 8 and <= %d", C, 256 * VNS_MAXV); return OB_ERR_UNSUPPORTED; }
+  if (film != nullptr && dfilm == nullptr) { set_error("vae_norm_silu_bwd: dfilm is required with film"); return OB_ERR_INVALID; }
+  if (B <= 0 || rows_per_batch <= 0) return OB_OK;
+  if (film != nullptr) cudaMemsetAsync(dfilm, 0, static_cast<size_t>(B) * 2 * C * sizeof(float), st);
+  launch(vae_norm_silu_bwd_kernel, dim3(vns_grid(rows_per_batch, B), B), 256, film ? 2 * C * sizeof(float) : 0, st, 1,
+         static_cast<const __nv_bfloat16*>(x), film, static_cast<const __nv_bfloat16*>(g), static_cast<__nv_bfloat16*>(dx), dfilm,
+         rows_per_batch, C, c_mean, eps);
+  return check_launch("vae_norm_silu_bwd");
+}
+
 // ============================================================================ 2x resampling
 // Reference: edm2/utils.py:94-107 with the [1,1] filter the UNet uses: 'down' = 2x2 mean, 'up' = nearest-neighbour 2x.
 // Each is the other's transpose, so two kernels cover both directions of both modes:

@@ -364,7 +364,7 @@ int tapconv_launch(const TapConvLaunch& L, cudaStream_t stream) {
   p.n_seq = L.n_seq; p.T = L.T; p.H = L.H; p.W = L.W;
   p.Cin = L.Cin; p.Cout = L.Cout;
   p.n_out = L.n_out; p.epi = L.epi; p.out_f32 = L.out_f32;
-  p.alpha = L.alpha; p.beta = L.beta; p.out = L.out; p.out_d = L.out_d;
+  p.alpha = L.alpha; p.beta = L.beta; p.bias = L.bias; p.out = L.out; p.out_d = L.out_d;
 
   p.trace = L.trace;
   p.wide_store = (L.Cout % 16 == 0) && (reinterpret_cast<uintptr_t>(L.out) % 32 == 0) &&
@@ -424,7 +424,7 @@ int tapconv_launch(const TapConvLaunch& L, cudaStream_t stream) {
     const long hw = static_cast<long>(L.H) * L.W;
     const long total = static_cast<long>(L.n_seq) * L.n_out * L.T * hw * (L.Cout / 4);
     launch(tapconv_finish_kernel, static_cast<unsigned>((total + 255) / 256), 256, 0, stream, 1, 
-        p.split_ws, p.alpha, p.beta, p.out, static_cast<__half*>(p.out_d), L.n_seq, L.n_out, L.T, hw, L.Cout, p.epi, p.out_f32);
+        p.split_ws, p.alpha, p.beta, p.out, static_cast<__half*>(p.out_d), L.n_seq, L.n_out, L.T, hw, L.Cout, p.epi, p.out_f32, p.bias);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("tapconv_finish launch: %s", cudaGetErrorString(e)); return OB_ERR_CUDA; }
   }

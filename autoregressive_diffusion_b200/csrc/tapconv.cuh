@@ -73,6 +73,7 @@ struct TapConvParams {
   int wide_store;  // 1: the epilogue may use 256-bit stores (Cout % 16 == 0, out / out_d 32-byte aligned)
   const float* alpha;  // [n_seq*n_out*T] per output frame (EPI_GATED)
   const float* beta;
+  const float* bias;   // optional fp32 [Cout] added to every output row (EPI_PLAIN; the VAE's nn.Conv3d layers)
   void* out;    // [n_seq*n_out*T, H, W, Cout]
   void* out_d;  // optional (EPI_GATED): shared - own accumulator, fp16, same shape as out
   int ksplit;   // >1: blockIdx.y owns a slice of the channel chunks (split-K)
@@ -456,6 +457,10 @@ __global__ void __launch_bounds__(TAPCONV_THREADS, 1) tapconv_kernel(const __gri
             for (int j = 0; j < CW; ++j) y[j] = own[j];
           }
           const int col0 = n0 + c * CW;
+          if (p.bias != nullptr) {
+#pragma unroll
+            for (int j = 0; j < CW; ++j) y[j] += (col0 + j < p.Cout) ? p.bias[col0 + j] : 0.f;
+          }
           if (row_ok) {
             if (p.wide_store) {
               // 256-bit stores: one full 32-byte sector per thread and instruction (Cout % 16 == 0, 32-byte aligned bases)
@@ -575,7 +580,7 @@ __global__ void __launch_bounds__(TAPCONV_THREADS, 1) tapconv_kernel(const __gri
             const long off = ((frame * p.H + h) * p.W + w) * static_cast<long>(p.Cout) + col;
             float y[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) y[j] = al * own[j] + be * shr[j];
+            for (int j = 0; j < 8; ++j) y[j] = al * own[j] + be * shr[j] + (p.bias != nullptr ? p.bias[col + j] : 0.f);
             if (p.out_f32) {
               float* dst = static_cast<float*>(p.out) + off;
               *reinterpret_cast<float4*>(dst) = make_float4(y[0], y[1], y[2], y[3]);
@@ -607,7 +612,8 @@ __global__ void __launch_bounds__(TAPCONV_THREADS, 1) tapconv_kernel(const __gri
 static __global__ void __launch_bounds__(256) tapconv_finish_kernel(const float* __restrict__ ws, const float* __restrict__ alpha,
                                                              const float* __restrict__ beta, void* __restrict__ out,
                                                              __half* __restrict__ out_d, int n_seq, int n_out, int T,
-                                                             long hw, int Cout, int epi, int out_f32) {
+                                                             long hw, int Cout, int epi, int out_f32,
+                                                             const float* __restrict__ bias) {
   pdl_launch_dependents();
   pdl_wait();
   const long rows_per_set = static_cast<long>(n_seq) * T * hw;
@@ -632,6 +638,7 @@ static __global__ void __launch_bounds__(256) tapconv_finish_kernel(const float*
     y = make_float4(al * own.x + be * shr.x, al * own.y + be * shr.y, al * own.z + be * shr.z, al * own.w + be * shr.w);
     if (out_d) *reinterpret_cast<uint2*>(out_d + orow * Cout + c) = make_uint2(pack_f16x2(shr.x - own.x, shr.y - own.y), pack_f16x2(shr.z - own.z, shr.w - own.w));
   }
+  if (bias != nullptr) { y.x += bias[c]; y.y += bias[c + 1]; y.z += bias[c + 2]; y.w += bias[c + 3]; }
   if (out_f32) *reinterpret_cast<float4*>(static_cast<float*>(out) + orow * Cout + c) = y;
   else *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(out) + orow * Cout + c) = make_uint2(pack_bf16x2(y.x, y.y), pack_bf16x2(y.z, y.w));
 }

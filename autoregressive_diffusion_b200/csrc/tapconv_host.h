@@ -32,6 +32,7 @@ struct TapConvLaunch {
   int epi = 0, out_f32 = 0;
   const float* alpha = nullptr;
   const float* beta = nullptr;
+  const float* bias = nullptr;   // optional fp32 [Cout] (plain epilogue)
   void* out = nullptr;
   void* out_d = nullptr;
   int force_bn = 0;  // test hook: pin the N tile

@@ -316,7 +316,7 @@ class PlainConvFn(torch.autograd.Function):
         out = empty_rows(f, cout_pad, h, wd, x.device, torch.float32 if out_f32 else BF16)
         ws = split_workspace(1, 1, f, h, wd, cin_pad, cout_pad, ksize, 0, x.device)
         call("ob_conv_fwd", _vp(x), None, _vp(wg), None, None, _vp(out), None, _vp(ws), 1, 1, f, h, wd, cin_pad, cout_pad, ksize,
-             0, int(out_f32), wg.shape[1], stream_ptr())
+             0, int(out_f32), wg.shape[1], None, stream_ptr())
         ctx.save_for_backward(x, w, wg)
         ctx.ksize, ctx.gain = ksize, gain
         return out if cout_pad == cout else out[:, :cout]
@@ -355,6 +355,98 @@ class PlainConvFn(torch.autograd.Function):
         return dx, dw, None, None, None, None
 
 
+class RawConvFn(torch.autograd.Function):
+    """conv2d(x, w) with PLAIN (not weight-normalised) weights on the tap-GEMM kernels -- the convolutions of the VAE
+    (edm2/vae/vae.py: nn.Conv3d layers expressed as per-frame 3x3 / 1x1 GEMMs).  wmat: fp32 [Cout, k*k, Cin] (any autograd
+    view of the layer's weight); its gradient is returned through autograd."""
+
+    @staticmethod
+    def forward(ctx, x, wmat, bias, ksize):
+        f, cin_pad, h, wd = x.shape
+        cout, kk, cin = wmat.shape
+        cout_pad = ceil_to(cout, 8)
+        wg = torch.zeros((cout_pad, kk, cin_pad), dtype=BF16, device=x.device)
+        wg[:cout, :, :cin] = wmat
+        bias_p = None
+        if bias is not None:      # added to the fp32 accumulator in the epilogue: one rounding for conv + bias
+            bias_p = torch.zeros(cout_pad, dtype=torch.float32, device=x.device)
+            bias_p[:cout] = bias
+        out = empty_rows(f, cout_pad, h, wd, x.device)
+        ws = split_workspace(1, 1, f, h, wd, cin_pad, cout_pad, ksize, 0, x.device)
+        call("ob_conv_fwd", _vp(x), None, _vp(wg), None, None, _vp(out), None, _vp(ws), 1, 1, f, h, wd, cin_pad, cout_pad, ksize,
+             0, 0, kk, _vp(bias_p), stream_ptr())
+        ctx.save_for_backward(x, wg)
+        ctx.dims = (ksize, cout, cin)
+        return out if cout_pad == cout else out[:, :cout]
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, wg = ctx.saved_tensors
+        ksize, cout, cin = ctx.dims
+        f, cin_pad, h, wd = x.shape
+        cout_pad, kk = wg.shape[0], wg.shape[1]
+        gy = pad_channels(rows(gy), 8)
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            dx = empty_rows(f, cin_pad, h, wd, x.device)
+            ws = split_workspace(1, 1, f, h, wd, cout_pad, cin_pad, ksize, 0, x.device)
+            call("ob_conv_dgrad", _vp(gy), None, _vp(wg), None, None, _vp(dx), _vp(ws), 1, 1, f, h, wd, cin_pad, cout_pad, ksize, 0,
+                 kk, stream_ptr())
+        if ctx.needs_input_grad[1]:
+            ns = query("ob_conv_wgrad_splits", 1, 1, f, h, wd, cin_pad, cout_pad, ksize, 0)
+            dwg = torch.empty((ns, cout_pad, kk, cin_pad), dtype=torch.float32, device=x.device)
+            call("ob_conv_wgrad", _vp(gy), _vp(x), None, None, _vp(dwg), 1, 1, f, h, wd, cin_pad, cout_pad, ksize, 0, ns,
+                 stream_ptr())
+            dw = dwg.sum(0)[:cout, :, :cin]
+        db = gy[:, :cout].float().sum(dim=(0, 2, 3)) if ctx.needs_input_grad[2] else None
+        return dx, dw, db, None
+
+
+class VaeNormSiluFn(torch.autograd.Function):
+    """silu(film(x / sqrt(mean_c(x^2) + 1e-4)))  [edm2/vae/vae.py:77-83,86-87] over bf16 rows [B, rows, C]; film: fp32 [B, 2C] or None."""
+
+    @staticmethod
+    def forward(ctx, x, film, batch, c_mean):
+        f, c, h, w = x.shape
+        out = torch.empty_like(x, memory_format=CL)
+        call("ob_vae_norm_silu_fwd", _vp(x), _vp(film), _vp(out), batch, f * h * w // batch, c, c_mean, 1e-4, stream_ptr())
+        ctx.save_for_backward(x, film)
+        ctx.batch, ctx.c_mean = batch, c_mean
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, film = ctx.saved_tensors
+        f, c, h, w = x.shape
+        g = rows(g)
+        dx = torch.empty_like(x, memory_format=CL)
+        dfilm = torch.empty_like(film) if film is not None else None
+        call("ob_vae_norm_silu_bwd", _vp(x), _vp(film), _vp(g), _vp(dx), _vp(dfilm), ctx.batch, f * h * w // ctx.batch, c, ctx.c_mean,
+             1e-4, stream_ptr())
+        return dx, dfilm, None, None
+
+
+def vae_norm_silu(x, film, batch):
+    """x: bf16 channels_last [batch*t, C, H, W]; film: [batch, 2C] (scale | shift) or None."""
+    c = x.shape[1]
+    if c % 8 != 0:       # tiny channel counts (the latent): zero channels up to a multiple of 8, mean over the real ones
+        pad = 8 - c % 8
+        x = torch.nn.functional.pad(x, (0, 0, 0, 0, 0, pad))
+        if film is not None:
+            z = film.new_zeros(film.shape[0], pad)
+            film = torch.cat((film[:, :c], z, film[:, c:], z), dim=1)
+    if film is not None:
+        film = film.float().contiguous()
+    out = VaeNormSiluFn.apply(rows(x), film, batch, c)
+    return out if out.shape[1] == c else out[:, :c]
+
+
+def raw_conv(x, wmat, ksize, bias=None):
+    """x: logical [F, C, H, W] (any dtype / layout) -> bf16 channels_last [F, Cout, H, W] = conv2d(x, w) + bias."""
+    _require_cuda(x)
+    return RawConvFn.apply(pad_channels(rows(x), 16), wmat, bias, ksize)
+
+
 class GatedConvFn(torch.autograd.Function):
     """MPCausal3DGatedConv (edm2/conv.py:59-95) as three launches: gate scalars, causal-context assembly, and ONE
     tcgen05 implicit GEMM  y = alpha*conv2d(x) + beta*conv3d(context)  with the gate applied in its epilogue.
@@ -378,7 +470,7 @@ class GatedConvFn(torch.autograd.Function):
         out_d = empty_rows(f, cout, h, wd, dev, torch.float16) if want_grad else None
         ws = split_workspace(n_seq, S, T, h, wd, cin_pad, cout, 3, 1, dev)
         call("ob_conv_fwd", _vp(x), _vp(cx), _vp(wg), _vp(alpha), _vp(beta), _vp(out), _vp(out_d), _vp(ws), n_seq, S, T, h, wd,
-             cin_pad, cout, 3, 1, 0, 27, stream_ptr())
+             cin_pad, cout, 3, 1, 0, 27, None, stream_ptr())
         if want_grad:
             ctx.save_for_backward(x, cx, w2, w3, wg, ab, out, out_d, g_offset, g_mult, g_max, g_min, c_noise, scratch)
         ctx.dims = (n_seq, S, T, n_ctx)

@@ -77,6 +77,7 @@ int ob_wnorm_bwd_gated(const float* w2, float* dw2, const float* w3, float* dw3,
  *                out_d (optional, may be NULL): fp16, context term minus current-frame term (saved for backward; its inner
  *                product with dy feeds the gate scalars' gradients: fp16 keeps 11 mantissa bits at bf16's two bytes).
  * out: [n_seq*S*T, H, W, Cout], bf16 or (out_f32 != 0) fp32.  alpha/beta: fp32 [n_seq*S*T].
+ * bias (plain convs; may be NULL): fp32 [cout] added in the epilogue before the rounding to bf16 (nn.Conv3d(bias=True) of the VAE).
  * w_taps (plain convs; 0 = ksize*ksize): taps per row of wg -- 27 lets the 2-D form of a gated conv (just_2d, edm2/conv.py:60)
  * read the first 9 taps of the SAME operand matrix the gated form uses (one operand, one normalisation per weight).
  * split_ws (optional, may be NULL): fp32 scratch sized by ob_conv_split_ws_bytes.  When given and the layer has too
@@ -86,7 +87,7 @@ int ob_wnorm_bwd_gated(const float* w2, float* dw2, const float* w3, float* dw3,
 int64_t ob_conv_split_ws_bytes(int n_seq, int S, int T, int H, int W, int cin, int cout, int ksize, int gated);
 int ob_conv_fwd(const void* x, const void* ctx, const void* wg, const float* alpha, const float* beta, void* out,
                 void* out_d, void* split_ws, int n_seq, int S, int T, int H, int W, int cin, int cout, int ksize, int gated,
-                int out_f32, int w_taps, void* stream);
+                int out_f32, int w_taps, const float* bias, void* stream);
 
 /* Input gradient of ob_conv_fwd.  gy: bf16 [n_seq*S*T, H, W, Cout] = dL/dout (unscaled);
  * gated: gb: bf16 [n_seq*T, H, W, Cout] = sum_s beta_s*dL/dout_s (from ob_gate_bwd) and
@@ -173,6 +174,17 @@ int ob_mp_cat_bwd(const void* g, void* da, void* db, int64_t rows, int ca, int c
  * pool != 0: out[f,y,x,:] = scale * sum of in's 2x2 block (down: scale 0.25; gradient of up: scale 1);
  * pool == 0: out[f,2y+i,2x+j,:] = scale * in[f,y,x,:]     (up: scale 1; gradient of down: scale 0.25). */
 int ob_resample2x(const void* in, void* out, int64_t frames, int h, int w, int c, int pool, float scale, void* stream);
+
+/* VAE ResBlock activation (edm2/vae/vae.py:77-83, :86-87), one pass each way over bf16 [B, rows_per_batch, C] rows:
+ *   y = x / sqrt(mean_c(x^2) + eps);   film != NULL: y = y*(1 + film[b][c]) + film[b][C + c]  (fp32 [B][2C], the decoder's
+ *   t_cond scale | shift);   out = silu(y).
+ * bwd: g = dL/dout -> dx (the input is re-normalised, nothing but x was saved) and, with film, dfilm fp32 [B][2C]
+ * (overwritten).  c % 8 == 0, c <= 1024; c_mean <= c is the number of REAL channels the mean runs over (rows padded
+ * with zero channels up to a multiple of 8). */
+int ob_vae_norm_silu_fwd(const void* x, const float* film, void* out, int b, int64_t rows_per_batch, int c, int c_mean, float eps,
+                         void* stream);
+int ob_vae_norm_silu_bwd(const void* x, const float* film, const void* g, void* dx, float* dfilm, int b, int64_t rows_per_batch,
+                         int c, int c_mean, float eps, void* stream);
 
 /* Programmatic dependent launch: when on (default; ONIRIS_PDL=0 in the environment forces it off), every kernel of the
  * library is launched so that its prologue overlaps the tail of the previous kernel on the stream.  mode 0: off, 1: every

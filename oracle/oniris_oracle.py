@@ -590,3 +590,46 @@ def train_step(sd, layout, images, sigma, noise, conditioning=None, sigma_data: 
     loss = edm2_loss(leaves, layout, images, sigma, noise, conditioning, sigma_data)
     loss.backward()
     return loss.detach(), {k: v.grad for k, v in leaves.items() if isinstance(v, Tensor) and v.requires_grad}
+
+
+# ----------------------------------------------------------------------------- VAE conv path
+
+
+def group_causal_conv(x: Tensor, weight: Tensor, bias: Tensor, group_size: int, cache: Optional[Tensor] = None,
+                      training: bool = True):
+    """edm2/vae/vae.py:40-53 (GroupCausal3DConvVAE.forward).  x: [b, c, t, h, w]; weight: [cout*g, cin, 2g, 3, 3].
+
+    Spatial zero padding 1; temporal left padding of kt - g frames taken from `cache` (already spatially padded, as the
+    reference stores it) or, without one, a copy of the FIRST kt - g frames (:43-44); conv3d with temporal stride g;
+    un-group 'b (c g) t h w -> b c (t g) h w'.  Returns (y, new_cache) with new_cache None in training (:47)."""
+    kt = weight.shape[2]
+    pad_t = kt - group_size
+    x = F.pad(x, (1, 1, 1, 1))
+    if cache is None:
+        cache = x[:, :, :pad_t].clone().detach()
+    x = torch.cat((cache, x), dim=2)
+    new_cache = None if training else x[:, :, -pad_t:].clone().detach()
+    y = F.conv3d(x, weight, bias, stride=(group_size, 1, 1))
+    b, cg, t, h, w = y.shape
+    y = y.reshape(b, cg // group_size, group_size, t, h, w).permute(0, 1, 3, 2, 4, 5).reshape(b, cg // group_size, t * group_size, h, w)
+    return y, new_cache
+
+
+def vae_rms_norm(x: Tensor) -> Tensor:
+    """edm2/vae/vae.py:77,86 -- x / sqrt(mean_c(x^2) + 1e-4) (NOT utils.normalize: the epsilon sits under the root)."""
+    return x / torch.sqrt(torch.mean(x ** 2, dim=1, keepdim=True) + 1e-4)
+
+
+def vae_res_block(x: Tensor, sd: Dict[str, Tensor], group_size: int, t_emb: Optional[Tensor] = None, cache=None,
+                  training: bool = True):
+    """edm2/vae/vae.py:74-93 (ResBlock.forward).  sd keys: conv3d0.conv3d.{weight,bias}, conv3d1.{weight,bias};
+    t_emb: the already evaluated t_cond(fourier_cond(t)) [b, 2c] of the decoder blocks, or None."""
+    y = vae_rms_norm(x)
+    if t_emb is not None:
+        scale, shift = t_emb[..., None, None, None].split(x.shape[1], dim=1)
+        y = y * (1 + scale) + shift
+    y = F.silu(y)
+    y, cache = group_causal_conv(y, sd["conv3d0.conv3d.weight"], sd["conv3d0.conv3d.bias"], group_size, cache, training)
+    y = F.silu(vae_rms_norm(y))
+    y = F.conv3d(y, sd["conv3d1.weight"], sd["conv3d1.bias"], padding=(0, 1, 1))
+    return x + y, cache

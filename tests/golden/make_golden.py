@@ -237,6 +237,55 @@ def main():
         rec.update(sample_inits=inits, sample_conds=conds, sample_frames=frames)
     out["unet"] = rec
 
+    # ---- VAE conv path (edm2/vae/vae.py): grouped causal conv, ResBlock, a small encoder/decoder
+    import edm2.vae.vae as V
+    torch.manual_seed(42)
+    gc = V.GroupCausal3DConvVAE(16, 24, (4, 3, 3), 2)
+    with torch.no_grad():
+        gc.conv3d.weight.copy_(torch.randn_like(gc.conv3d.weight) * 0.1)       # non-zero look-back taps
+        gc.conv3d.bias.copy_(torch.randn_like(gc.conv3d.bias) * 0.1)
+    x = rb(torch.randn(2, 16, 8, 8, 8)).requires_grad_(True)
+    gc.train()
+    y, _ = gc(x)
+    gy = rb(torch.randn_like(y))
+    y.backward(gy)
+    rec = dict(sd={k_: t(v) for k_, v in gc.state_dict().items()}, x=t(x), y_train=t(y), gy=gy, gx=t(x.grad),
+               grads={k_: t(p.grad) for k_, p in gc.named_parameters()})
+    gc.eval()
+    with torch.no_grad():
+        y1, c1 = gc(x[:, :, :4])
+        y2, c2 = gc(x[:, :, 4:], cache=c1)
+    rec.update(y_chunk0=t(y1), y_chunk1=t(y2), cache0=t(c1), cache1=t(c2))
+    torch.manual_seed(43)
+    rbk = V.ResBlock(32, (4, 3, 3), 2, t_cond=True)
+    with torch.no_grad():
+        for p in rbk.parameters():
+            p.copy_(torch.randn_like(p) * 0.1)
+    x = rb(torch.randn(2, 32, 4, 8, 8)).requires_grad_(True)
+    tt = torch.rand(2)
+    rbk.train()
+    y, _ = rbk(x, tt)
+    gy = rb(torch.randn_like(y))
+    y.backward(gy)
+    rec["resblock"] = dict(sd={k_: t(v) for k_, v in rbk.state_dict().items()}, x=t(x), t=tt, y=t(y), gy=gy, gx=t(x.grad),
+                           grads={k_: t(p.grad) for k_, p in rbk.named_parameters()})
+    torch.manual_seed(44)
+    kwv = dict(channels=[3, 16, 32, 4], n_res_blocks=1, time_compressions=[1, 2, 2], spatial_compressions=[1, 2, 2])
+    vae = V.VAE(**kwv)
+    with torch.no_grad():
+        for p in vae.parameters():
+            p.copy_(torch.randn_like(p) * 0.1)
+        vae.decoder.logvar_multiplier.fill_(-2.0)
+    x = rb(torch.randn(1, 3, 8, 16, 16))
+    vae.train()
+    mean, _ = vae.encode(x)
+    tv = torch.tensor([0.07])
+    z = rb(mean.detach() * (1 - tv) + torch.randn_like(mean) * tv)
+    r_mean, r_logvar, _ = vae.decode(z, tv)
+    rec["vae"] = dict(kwargs=kwv, sd={k_: t(v) for k_, v in vae.state_dict().items()}, x=x, mean=t(mean), t=tv, z=z,
+                      r_mean=t(r_mean), r_logvar=t(r_logvar))
+    out["vae_conv"] = rec
+
     for name, rec in out.items():
         torch.save(rec, os.path.join(HERE, f"{name}.pt"))
         print(f"wrote {name}.pt  {os.path.getsize(os.path.join(HERE, name + '.pt')) / 1e6:.2f} MB")

@@ -1,14 +1,8 @@
 set -x
 mkdir -p gpurun_out
-rm -f gpurun_out/r02_parity_report.tsv
-ONIRIS_PARITY_REPORT=gpurun_out/r02_parity_report.tsv timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -40 > gpurun_out/r02_gputest5.log
-tail -25 gpurun_out/r02_gputest5.log
-timeout 600 python bench.py --steps 40 --warmup 5 --no-cpu-baseline > gpurun_out/r02_bench2.json 2> gpurun_out/r02_bench2.err
-tail -3 gpurun_out/r02_bench2.err
-python - <<'PY'
-import json
-d=json.loads(open('gpurun_out/r02_bench2.json').read().strip().splitlines()[-1])
-print(d['value'], d['ms_per_step'], d['e2e']['value'], d['roofline']['achieved'], d['roofline']['frac'])
-for k in d['roofline_hbm']['kernels']: print(k)
-print(d['roofline_hbm']['other_entry_points_ms_per_cycle'], d['roofline_hbm']['serial_cycle_ms'])
-PY
+rm -f gpurun_out/vae_parity.tsv
+ONIRIS_PARITY_REPORT=gpurun_out/vae_parity.tsv timeout 600 python -m pytest tests/test_vae_gpu.py tests/test_conv_gpu.py -m gpu -q 2>&1 | tail -12 > gpurun_out/r02_gputest_vae.log
+tail -12 gpurun_out/r02_gputest_vae.log
+grep test_vae gpurun_out/vae_parity.tsv | cut -f1-4 | sed 's/tests.test_vae_gpu.py:://' | head -40
+timeout 900 python tools/bench_vae.py > gpurun_out/r02_vae.log 2>&1
+tail -3 gpurun_out/r02_vae.log | head -1
