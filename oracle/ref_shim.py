@@ -32,6 +32,14 @@ def reference_root():
     return None
 
 
+def undo_cpu_remap():
+    """Restore torch.arange / torch.tensor / Tensor.cuda after a force_cpu import (a process that also runs GPU code)."""
+    saved = getattr(torch, "_oniris_cpu_remap", None)
+    if saved:
+        torch.arange, torch.tensor, torch.Tensor.cuda = saved
+        torch._oniris_cpu_remap = None
+
+
 def import_reference(force_cpu=None):
     """Returns a dict of the reference's modules; raises ImportError when no copy of the reference is available."""
     root = reference_root()
@@ -44,7 +52,7 @@ def import_reference(force_cpu=None):
     if root not in sys.path:
         sys.path.insert(0, root)
     cpu = (not torch.cuda.is_available()) if force_cpu is None else force_cpu
-    if cpu and not getattr(torch, "_oniris_cpu_remap", False):
+    if cpu and not getattr(torch, "_oniris_cpu_remap", None):
         def remap(fn):
             def w(*a, **k):
                 if str(k.get("device", "")).startswith("cuda"):
@@ -52,9 +60,9 @@ def import_reference(force_cpu=None):
                 return fn(*a, **k)
             return w
 
+        torch._oniris_cpu_remap = (torch.arange, torch.tensor, torch.Tensor.cuda)      # undo_cpu_remap() restores these
         torch.arange, torch.tensor = remap(torch.arange), remap(torch.tensor)
         torch.Tensor.cuda = lambda self, *a, **k: self
-        torch._oniris_cpu_remap = True
     import edm2.attention.attention_modules as am
     if cpu:
         import torch.nn.functional as F

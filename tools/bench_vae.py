@@ -36,6 +36,33 @@ def step(vae, x):
     return loss
 
 
+def measure(steps=5, res=256):
+    """clips/s of ONE fwd+bwd pass of the configs[4] VAE on this GPU (our path only)."""
+    torch.manual_seed(0)
+    x = torch.randn(1, 3, 16, res, res, device="cuda")
+    vae = VAE(**CFG).cuda().train()
+    with torch.no_grad():
+        for p in vae.parameters():
+            if p.ndim >= 2:
+                p.copy_(torch.randn_like(p) * (2.0 / max(1, p[0].numel())) ** 0.5)
+    fl = Flops()
+    _lib.set_profiler(fl)
+    step(vae, x)
+    _lib.set_profiler(None)
+    step(vae, x)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step(vae, x)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return {"what": "cs_vae_train.py VAE (272.6M params), clip [1,3,16,256,256], fwd+bwd of the Gaussian NLL, bf16 tap-GEMM convs",
+            "ms_per_clip_fwd_bwd": ms, "clips_per_s": 1e3 / ms, "conv_gemm_fwd_gflop": fl.fwd / 1e9,
+            "conv_gemm_tflops_fwd_bwd": 3 * fl.fwd / (ms * 1e-3) / 1e12}
+
+
 def main():
     torch.manual_seed(0)
     res = int(os.environ.get("RES", "256"))

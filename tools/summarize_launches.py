@@ -55,5 +55,5 @@ open(out_txt, "w").write("\n".join(out) + "\n")
 tc = [d for d in L.values() if "tapconv_kernel" in d["name"]]
 json.dump({"kernel": "tapconv_kernel", "launches_per_step": len(tc),
            "dram_bytes_per_launch": sum(d.get("rd", 0) + d.get("wr", 0) for d in tc) / len(tc),
-           "share_of_step": sum(d["us"] for d in tc) / tot, "source": "profiles/r01_launches_step.csv"}, open(out_json, "w"), indent=1)
+           "share_of_step": sum(d["us"] for d in tc) / tot, "source": src}, open(out_json, "w"), indent=1)
 print("\n".join(out[:16] + out[-2:]))
