@@ -62,6 +62,7 @@ _SIGS = {
     "ob_qkv_prep_fwd": "ppppppppppliifp",
     "ob_qkv_prep_bwd": "ppppppppppliifp",
     "ob_rope_k": "ppppppliip",
+    "ob_build_block_lists": "iiipppp",
     "ob_attn_fwd": "pppppiiiiiiifp",
     "ob_kv_append": "pppppppppiiiiifp",
     "ob_dart_attn_decode_splits": "iiii",

@@ -269,6 +269,34 @@ int ob_adamw_ema(float* p, float* g, float* m, float* v, float* ema1, float* ema
 }
 int ob_sumsq(const float* g, int64_t n, float* out, void* stream) { return sumsq(g, (long)n, out, (cudaStream_t)stream); }
 
+int ob_build_block_lists(int training, int n_frames, int image_size, int32_t* kv_num_blocks, int32_t* kv_indices, int* n_rows,
+                         int* block_size) {
+  // attention_masking.py:27-53 (make_train_mask) / :64-90 (make_infer_mask): HOST arrays, one (batch, head) slice -- the
+  // reference broadcasts it over batch and heads.  Frames below 128 tokens are regrouped into 128-token blocks (F3).
+  if (n_frames <= 0 || image_size <= 0 || n_rows == nullptr || block_size == nullptr) { set_error("ob_build_block_lists: bad arguments"); return OB_ERR_INVALID; }
+  long n = n_frames;
+  int bs = image_size;
+  if (!training && static_cast<long>(n_frames) * image_size < 128) { *n_rows = 0; *block_size = 0; return OB_OK; }   // reference: score_mod path
+  if (image_size < 128) {
+    if ((n * image_size) % 128 != 0) { *n_rows = 0; *block_size = 0; return OB_OK; }                  // reference returns None / dense mask
+    n = n * image_size / 128;
+    bs = 128;
+  }
+  const long rows = training ? 2 * n : n;
+  *n_rows = static_cast<int>(rows);
+  *block_size = bs;
+  if (kv_num_blocks == nullptr || kv_indices == nullptr) return OB_OK;                                  // size query
+  for (long r = 0; r < rows; ++r) {
+    const long i = r % n;
+    kv_num_blocks[r] = static_cast<int32_t>(i + 1);
+    int32_t* row = kv_indices + r * rows;
+    for (long c = 0; c < rows; ++c) row[c] = 0;
+    if (!training || r < n) { for (long c = 0; c <= i; ++c) row[c] = static_cast<int32_t>(c); }
+    else { for (long c = 0; c < i; ++c) row[c] = static_cast<int32_t>(c); row[i] = static_cast<int32_t>(n + i); }
+  }
+  return OB_OK;
+}
+
 int ob_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int b, int heads, int lq, int lk, int hw,
                 int n_frames, int mask, float scale, void* stream) {
   return attn_fwd(q, k, v, o, lse, b, heads, lq, lk, hw, n_frames, mask, scale, (cudaStream_t)stream);

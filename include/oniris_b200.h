@@ -219,6 +219,15 @@ int ob_sumsq(const float* g, int64_t n, float* out, void* stream);
  * frame vs the whole cache; per-frame attention), OB_ATTN_CAUSAL (frame-causal prefill, InferenceMask
  * attention_masking.py:56-62) or OB_ATTN_DART (TrainingMask attention_masking.py:8-24 over 2*n_frames frames).
  * hw = tokens per frame.  o: bf16 [B, Lq, heads, 64]; lse: fp32 [B, heads, Lq] (log-sum-exp of the scaled logits), may be NULL. */
+/* Block lists of edm2/attention/attention_masking.py:27-53 (training != 0: make_train_mask) / :64-90 (make_infer_mask),
+ * bit-exact with the reference's BlockMask.from_kv_blocks inputs, for ONE (batch, head) slice, written to HOST memory:
+ * kv_num_blocks int32 [n_rows], kv_indices int32 [n_rows][n_rows].  n_rows = 2n' (training) or n' with n' = n_frames, or
+ * n_frames*image_size/128 when image_size < 128 (the 128-token regrouping); *n_rows = 0 where the reference
+ * builds no block list (returns None / takes its dense path).  Call with NULL arrays first to query n_rows / block_size.
+ * The kernels do not consume these lists (they iterate the same pattern implicitly); they exist for callers and tests. */
+int ob_build_block_lists(int training, int n_frames, int image_size, int32_t* kv_num_blocks, int32_t* kv_indices, int* n_rows,
+                         int* block_size);
+
 #define OB_ATTN_FULL 0
 #define OB_ATTN_CAUSAL 1
 #define OB_ATTN_DART 2

@@ -84,6 +84,28 @@ def test_block_lists_bit_exact(golden):
     assert n_checked >= 20
 
 
+def test_c_abi_block_lists_bit_exact(golden):
+    """ob_build_block_lists (host code of the C ABI) against the reference's own kv_num_blocks / kv_indices tensors."""
+    import ctypes
+    from autoregressive_diffusion_b200 import _lib
+    L = _lib.lib()
+    n_checked = 0
+    for (kind, n, hw), ref in golden("block_lists").items():
+        rows, bs = ctypes.c_int(0), ctypes.c_int(0)
+        assert L.ob_build_block_lists(int(kind == "train"), n, hw, None, None, ctypes.byref(rows), ctypes.byref(bs)) == 0
+        if ref is None:
+            assert rows.value == 0
+            continue
+        assert rows.value == ref[0].numel() and bs.value == ref[2]
+        num = np.zeros(rows.value, dtype=np.int32)
+        idx = np.zeros((rows.value, rows.value), dtype=np.int32)
+        assert L.ob_build_block_lists(int(kind == "train"), n, hw, num.ctypes.data_as(ctypes.c_void_p), idx.ctypes.data_as(ctypes.c_void_p),
+                                      ctypes.byref(rows), ctypes.byref(bs)) == 0
+        assert np.array_equal(num, ref[0].numpy()) and np.array_equal(idx, ref[1].numpy())
+        n_checked += 1
+    assert n_checked >= 20
+
+
 def test_rope_tables_match_reference(golden):
     import autoregressive_diffusion_b200 as ob
     g = golden("rope")
