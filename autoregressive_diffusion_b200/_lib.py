@@ -35,6 +35,7 @@ _SIGS = {
     "ob_wnorm_bwd_gated": "pppppiiiifip",
     "ob_wnorm_bwd": "pppiiiiiiiffip",
     "ob_conv_fwd": "ppppppppiiiiiiiiiiipp",
+    "ob_conv_fwd_fused": "ppppppppiiiiiiiiiiippipffp",
     "ob_conv_dgrad": "pppppppiiiiiiiiiip",
     "ob_conv_split_ws_bytes": "iiiiiiiii",
     "ob_conv_wgrad_splits": "iiiiiiiii",

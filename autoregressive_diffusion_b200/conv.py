@@ -141,6 +141,8 @@ class MPCausal3DGatedConv(nn.Module):
     """3x3 conv on the current frame (+) gated 2x3x3 causal conv on the two previous clean frames
     (edm2/conv.py:49-101), as ONE tcgen05 implicit-GEMM launch with the gate applied in the epilogue."""
 
+    fuse_epilogue_in_training = False
+
     def __init__(self, in_channels, out_channels, kernel):
         super().__init__()
         assert len(kernel) == 3 and tuple(kernel) == (3, 3, 3), "the kernels implement the reference's 3x3x3 case"
@@ -151,7 +153,10 @@ class MPCausal3DGatedConv(nn.Module):
         self.gating = Gating()
         self._cache = _OperandCache()
 
-    def forward(self, x, emb, batch_size, c_noise, cache=None, update_cache=False, just_2d=False):
+    def forward(self, x, emb, batch_size, c_noise, cache=None, update_cache=False, just_2d=False, post=None):
+        """`post` (not in the reference signature; networks.Block uses it): fuse the op that follows the conv in
+        edm2/networks_edm2.py into its epilogue -- ("scale_silu", c[frames, C]) for `mp_silu(y * c)` (:75-77) or
+        ("mp_sum", x_residual, t, clip) for `clip(mp_sum(x, y, t))` (:86,93) -- and return THAT tensor instead of y."""
         ops._require_cuda(x)
         w2, w3 = self.last_frame_conv.weight.weight, self.weight.weight
         cin = w2.shape[1]
@@ -159,7 +164,7 @@ class MPCausal3DGatedConv(nn.Module):
         wg = self._cache.get([w2, w3], [9, 18], cin, cin_pad, [1.0, 1.0], self.training)
         xr = ops.pad_channels(rows(x), 16)
         if just_2d:     # the 2-D form (conv.py:60) reads the first 9 taps of the same operand: one normalisation per weight
-            return ops.PlainConvFn.apply(xr, w2, wg, 3, 1.0, False), cache
+            return self._post_separately(ops.PlainConvFn.apply(xr, w2, wg, 3, 1.0, False), post), cache
         if cache is None:
             cache = {}
         f, _, h, w = xr.shape
@@ -185,10 +190,29 @@ class MPCausal3DGatedConv(nn.Module):
                 pad5 = pad5.contiguous()
         gt = self.gating
         want_grad = torch.is_grad_enabled() and (xr.requires_grad or w2.requires_grad or w3.requires_grad)
-        y, ctx5 = ops.GatedConvFn.apply(xr, pad5, w2, w3, wg, gt.offset, gt.mult, gt.max_gating, gt.min_gating,
-                                        c_noise.reshape(-1).float().contiguous(), batch_size, S, T,
-                                        0 if static is not None else n_ctx, want_grad,
-                                        static['n_ctx'] if static is not None else None)
+        # fused epilogue: always when no backward pass will follow (the raw result is then never written); in training it is opt-in
+        # -- measured on the CS step it LOSES (14.18 vs 13.6 ms per micro-step): the backward pass needs y, so the epilogue
+        # stores two tensors per tile in its store-bound phase, while the separate kernels overlap the weight-gradient stream
+        fuse = post is not None and w2.shape[0] % 8 == 0 and (self.fuse_epilogue_in_training or not want_grad)
+        if fuse and post[0] == "scale_silu":
+            post = ("scale_silu", ops.scale_rows(post[1]))
+        elif fuse:
+            post = ("mp_sum", rows(post[1]), float(post[2]), float(post[3]))
+        outs = ops.GatedConvFn.apply(xr, pad5, w2, w3, wg, gt.offset, gt.mult, gt.max_gating, gt.min_gating,
+                                     c_noise.reshape(-1).float().contiguous(), batch_size, S, T,
+                                     0 if static is not None else n_ctx, want_grad,
+                                     static['n_ctx'] if static is not None else None, post if fuse else None)
+        y, ctx5 = outs[0], outs[1]
+        if fuse:
+            z = outs[2]
+            if want_grad and post[0] == "scale_silu":
+                y = ops.ScaleSiluPreFn.apply(y, post[1], z)
+            elif want_grad:
+                y = ops.MpSumPreFn.apply(post[1], y, z, post[2], post[3])
+            else:
+                y = z
+        elif post is not None:
+            y = self._post_separately(y, post)
         if update_cache:
             if static is not None:     # same storage every frame: captured graphs keep pointing at live data
                 static['buf'].copy_(ctx5[:, -2:])
@@ -196,6 +220,14 @@ class MPCausal3DGatedConv(nn.Module):
             else:
                 cache['activations'] = ctx5[:, -2:, :, :, :cin].permute(0, 4, 1, 2, 3)
         return y, cache
+
+    @staticmethod
+    def _post_separately(y, post):
+        if post is None:
+            return y
+        if post[0] == "scale_silu":
+            return ops.scale_silu(y, post[1])
+        return ops.mp_sum_clip(post[1], y, post[2], post[3])
 
     @torch.no_grad()
     def load_from_2d(self, weight):

@@ -87,9 +87,10 @@ int64_t ob_conv_split_ws_bytes(int n_seq, int S, int T, int H, int W, int cin, i
   return (int64_t)wsb;
 }
 
-int ob_conv_fwd(const void* x, const void* ctx, const void* wg, const float* alpha, const float* beta, void* out,
-                void* out_d, void* split_ws, int n_seq, int S, int T, int H, int W, int cin, int cout, int ksize, int gated,
-                int out_f32, int w_taps, const float* bias, void* stream) {
+struct PostArgs { int post; void* out2; const float* cscale; int cscale_ld; const void* res; float t, clip; };
+static int conv_fwd_impl(const void* x, const void* ctx, const void* wg, const float* alpha, const float* beta, void* out,
+                         void* out_d, void* split_ws, int n_seq, int S, int T, int H, int W, int cin, int cout, int ksize, int gated,
+                         int out_f32, int w_taps, const float* bias, const PostArgs& pa, void* stream) {
   if (int r = check_shape("ob_conv_fwd", n_seq, S, T, H, W, ksize, gated)) return r;
   TapConvLaunch L;
   std::vector<TapCol> cols;
@@ -116,8 +117,31 @@ int ob_conv_fwd(const void* x, const void* ctx, const void* wg, const float* alp
   L.H = H; L.W = W; L.Cin = cin; L.Cout = cout; L.out_f32 = out_f32; L.out = out; L.split_ws = (float*)split_ws;
   if (bias != nullptr && gated) { set_error("ob_conv_fwd: bias is supported for plain convs only"); return OB_ERR_INVALID; }
   L.bias = bias;
+  if (pa.post != 0) {
+    const float nrm = 1.f / sqrtf((1.f - pa.t) * (1.f - pa.t) + pa.t * pa.t);
+    L.post = pa.post; L.out2 = pa.out2; L.cscale = pa.cscale; L.cscale_ld = pa.cscale_ld ? pa.cscale_ld : cout; L.res = pa.res;
+    L.post_wa = (1.f - pa.t) * nrm; L.post_wb = pa.t * nrm; L.post_clip = pa.clip;
+  }
   return tapconv_launch(L, (cudaStream_t)stream);
 }
+}  // extern "C" (re-opened below)
+
+extern "C" {
+int ob_conv_fwd(const void* x, const void* ctx, const void* wg, const float* alpha, const float* beta, void* out,
+                void* out_d, void* split_ws, int n_seq, int S, int T, int H, int W, int cin, int cout, int ksize, int gated,
+                int out_f32, int w_taps, const float* bias, void* stream) {
+  return conv_fwd_impl(x, ctx, wg, alpha, beta, out, out_d, split_ws, n_seq, S, T, H, W, cin, cout, ksize, gated, out_f32, w_taps,
+                       bias, PostArgs{0, nullptr, nullptr, 0, nullptr, 0.f, 0.f}, stream);
+}
+int ob_conv_fwd_fused(const void* x, const void* ctx, const void* wg, const float* alpha, const float* beta, void* out,
+                      void* out_d, void* split_ws, int n_seq, int S, int T, int H, int W, int cin, int cout, int ksize, int gated,
+                      int w_taps, int post, void* out2, const float* cscale, int cscale_ld, const void* res, float t, float clip,
+                      void* stream) {
+  if (post != 1 && post != 2) { set_error("ob_conv_fwd_fused: post must be OB_POST_SCALE_SILU or OB_POST_MP_SUM"); return OB_ERR_INVALID; }
+  return conv_fwd_impl(x, ctx, wg, alpha, beta, out, out_d, split_ws, n_seq, S, T, H, W, cin, cout, ksize, gated, 0, w_taps, nullptr,
+                       PostArgs{post, out2, cscale, cscale_ld, res, t, clip}, stream);
+}
+
 
 int ob_conv_dgrad(const void* gy, const void* gb, const void* wg, const float* alpha, const float* beta, void* dx,
                   void* split_ws, int n_seq, int S, int T, int H, int W, int cin, int cout, int ksize, int gated,

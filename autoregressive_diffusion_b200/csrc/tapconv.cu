@@ -274,7 +274,7 @@ int tapconv_launch(const TapConvLaunch& L, cudaStream_t stream) {
   int bn, ks_plan;
   int taps = 0;
   for (int i = 0; i < L.n_cols; ++i) taps += static_cast<const TapCol*>(L.cols)[i].n_taps;
-  const bool want_cs = cluster_split_enabled() && L.split_ws == nullptr && L.trace == nullptr && !L.no_persist;
+  const bool want_cs = cluster_split_enabled() && L.split_ws == nullptr && L.trace == nullptr && !L.no_persist && L.post == 0;
   pick_tiling(n_acc, L.Cout, L.Cin, chunk, taps, m_tiles, L.force_bn, L.b_mn_major, L.split_ws != nullptr || want_cs, want_cs, &bn, &ks_plan);
   // cluster split-K: power-of-two slices (rows of the tile are dealt out evenly), at most the portable cluster size, one
   // tile per cluster
@@ -365,6 +365,14 @@ int tapconv_launch(const TapConvLaunch& L, cudaStream_t stream) {
   p.Cin = L.Cin; p.Cout = L.Cout;
   p.n_out = L.n_out; p.epi = L.epi; p.out_f32 = L.out_f32;
   p.alpha = L.alpha; p.beta = L.beta; p.bias = L.bias; p.out = L.out; p.out_d = L.out_d;
+  p.post = L.post; p.out2 = L.out2; p.cscale = L.cscale; p.cscale_ld = L.cscale_ld; p.res = L.res;
+  p.post_wa = L.post_wa; p.post_wb = L.post_wb; p.post_clip = L.post_clip;
+  if (L.post != POST_NONE && (L.out2 == nullptr || L.Cout % 8 != 0 || (L.post == POST_SCALE_SILU && (L.cscale == nullptr || L.cscale_ld % 4 != 0)) ||
+                              (L.post == POST_MP_SUM && L.res == nullptr))) {
+    set_error("tapconv: inconsistent post-op arguments");
+    return OB_ERR_INVALID;
+  }
+  if (L.out == nullptr && L.post == POST_NONE) { set_error("tapconv: no output"); return OB_ERR_INVALID; }
 
   p.trace = L.trace;
   p.wide_store = (L.Cout % 16 == 0) && (reinterpret_cast<uintptr_t>(L.out) % 32 == 0) &&
@@ -424,7 +432,8 @@ int tapconv_launch(const TapConvLaunch& L, cudaStream_t stream) {
     const long hw = static_cast<long>(L.H) * L.W;
     const long total = static_cast<long>(L.n_seq) * L.n_out * L.T * hw * (L.Cout / 4);
     launch(tapconv_finish_kernel, static_cast<unsigned>((total + 255) / 256), 256, 0, stream, 1, 
-        p.split_ws, p.alpha, p.beta, p.out, static_cast<__half*>(p.out_d), L.n_seq, L.n_out, L.T, hw, L.Cout, p.epi, p.out_f32, p.bias);
+        p.split_ws, p.alpha, p.beta, p.out, static_cast<__half*>(p.out_d), L.n_seq, L.n_out, L.T, hw, L.Cout, p.epi, p.out_f32, p.bias,
+        p.post, static_cast<__nv_bfloat16*>(p.out2), p.cscale, p.cscale_ld, static_cast<const __nv_bfloat16*>(p.res), p.post_wa, p.post_wb, p.post_clip);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("tapconv_finish launch: %s", cudaGetErrorString(e)); return OB_ERR_CUDA; }
   }

@@ -36,6 +36,11 @@ constexpr int TAPCONV_THREADS = 224;   // warp0: activation TMA, warp1: MMA, war
 constexpr int TAPCONV_MAX_A_SLOTS = 4;
 
 enum : int { EPI_PLAIN = 0, EPI_GATED = 1 };
+// Post-ops fused behind the output stage (edm2/networks_edm2.py:75-77 and :86,93): a SECOND bf16 output
+//   POST_SCALE_SILU: out2 = mp_silu(y * cscale[frame, channel])            (conv_res0 -> embedding scale -> mp_silu)
+//   POST_MP_SUM:     out2 = clip(res * wa + y * wb)                         (conv_res1 -> mp_sum with the residual -> clip)
+// computed from the fp32 result y before it is rounded.  `out` (the raw y) may then be NULL (evaluation: nothing needs it).
+enum : int { POST_NONE = 0, POST_SCALE_SILU = 1, POST_MP_SUM = 2 };
 
 // One "column" of taps: fixed (source, dt, dx); its n_taps entries are the vertical taps dy = -1,0,+1 (or the single
 // centre tap of a 1x1 kernel).
@@ -74,6 +79,12 @@ struct TapConvParams {
   const float* alpha;  // [n_seq*n_out*T] per output frame (EPI_GATED)
   const float* beta;
   const float* bias;   // optional fp32 [Cout] added to every output row (EPI_PLAIN; the VAE's nn.Conv3d layers)
+  int post;            // POST_*
+  void* out2;          // bf16, same shape as out
+  const float* cscale; // POST_SCALE_SILU: fp32, row `frame` at cscale + frame*cscale_ld
+  int cscale_ld;
+  const void* res;     // POST_MP_SUM: bf16 residual, same shape as out
+  float post_wa, post_wb, post_clip;
   void* out;    // [n_seq*n_out*T, H, W, Cout]
   void* out_d;  // optional (EPI_GATED): shared - own accumulator, fp16, same shape as out
   int ksplit;   // >1: blockIdx.y owns a slice of the channel chunks (split-K)
@@ -461,7 +472,48 @@ __global__ void __launch_bounds__(TAPCONV_THREADS, 1) tapconv_kernel(const __gri
 #pragma unroll
             for (int j = 0; j < CW; ++j) y[j] += (col0 + j < p.Cout) ? p.bias[col0 + j] : 0.f;
           }
-          if (row_ok) {
+          if (row_ok && p.post != POST_NONE) {
+            // fused post-op on the fp32 result: second output
+            float z[CW];
+            if (p.post == POST_SCALE_SILU) {
+              const float* cs = p.cscale + frame * p.cscale_ld + col0;
+#pragma unroll
+              for (int j = 0; j < CW; ++j) {
+                const float v = y[j] * ((col0 + j < p.Cout) ? cs[j] : 0.f);
+                z[j] = v / (1.f + __expf(-v)) * (1.f / 0.596f);
+              }
+            } else {
+              const __nv_bfloat16* rr = static_cast<const __nv_bfloat16*>(p.res) + row_off + col0;
+#pragma unroll
+              for (int j = 0; j < CW; j += 8) {
+                if (col0 + j + 8 <= p.Cout) {
+                  const uint4 raw = *reinterpret_cast<const uint4*>(rr + j);
+                  const uint32_t w4[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+                  for (int u = 0; u < 4; ++u) {
+                    const float2 f2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w4[u]));
+                    z[j + 2 * u] = f2.x; z[j + 2 * u + 1] = f2.y;
+                  }
+                } else {
+#pragma unroll
+                  for (int u = 0; u < 8; ++u) z[j + u] = 0.f;
+                }
+              }
+#pragma unroll
+              for (int j = 0; j < CW; ++j) {
+                float v = z[j] * p.post_wa + y[j] * p.post_wb;
+                if (p.post_clip > 0.f) v = fminf(fmaxf(v, -p.post_clip), p.post_clip);
+                z[j] = v;
+              }
+            }
+            __nv_bfloat16* dst2 = static_cast<__nv_bfloat16*>(p.out2) + row_off + col0;
+#pragma unroll
+            for (int j = 0; j < CW; j += 8)
+              if (col0 + j + 8 <= p.Cout)
+                *reinterpret_cast<uint4*>(dst2 + j) = make_uint4(pack_bf16x2(z[j], z[j + 1]), pack_bf16x2(z[j + 2], z[j + 3]),
+                                                                 pack_bf16x2(z[j + 4], z[j + 5]), pack_bf16x2(z[j + 6], z[j + 7]));
+          }
+          if (row_ok && p.out != nullptr) {
             if (p.wide_store) {
               // 256-bit stores: one full 32-byte sector per thread and instruction (Cout % 16 == 0, 32-byte aligned bases)
               if (p.out_f32) {
@@ -613,7 +665,10 @@ static __global__ void __launch_bounds__(256) tapconv_finish_kernel(const float*
                                                              const float* __restrict__ beta, void* __restrict__ out,
                                                              __half* __restrict__ out_d, int n_seq, int n_out, int T,
                                                              long hw, int Cout, int epi, int out_f32,
-                                                             const float* __restrict__ bias) {
+                                                             const float* __restrict__ bias, int post, __nv_bfloat16* __restrict__ out2,
+                                                             const float* __restrict__ cscale, int cscale_ld,
+                                                             const __nv_bfloat16* __restrict__ res, float post_wa, float post_wb,
+                                                             float post_clip) {
   pdl_launch_dependents();
   pdl_wait();
   const long rows_per_set = static_cast<long>(n_seq) * T * hw;
@@ -639,6 +694,29 @@ static __global__ void __launch_bounds__(256) tapconv_finish_kernel(const float*
     if (out_d) *reinterpret_cast<uint2*>(out_d + orow * Cout + c) = make_uint2(pack_f16x2(shr.x - own.x, shr.y - own.y), pack_f16x2(shr.z - own.z, shr.w - own.w));
   }
   if (bias != nullptr) { y.x += bias[c]; y.y += bias[c + 1]; y.z += bias[c + 2]; y.w += bias[c + 3]; }
+  if (post != POST_NONE) {
+    float4 z;
+    if (post == POST_SCALE_SILU) {
+      const float4 cs = *reinterpret_cast<const float4*>(cscale + frame * cscale_ld + c);
+      const float v[4] = {y.x * cs.x, y.y * cs.y, y.z * cs.z, y.w * cs.w};
+      float o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[j] = v[j] / (1.f + __expf(-v[j])) * (1.f / 0.596f);
+      z = make_float4(o[0], o[1], o[2], o[3]);
+    } else {
+      const uint2 raw = *reinterpret_cast<const uint2*>(res + orow * Cout + c);
+      const float2 r0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
+      const float2 r1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
+      float o[4] = {r0.x * post_wa + y.x * post_wb, r0.y * post_wa + y.y * post_wb, r1.x * post_wa + y.z * post_wb, r1.y * post_wa + y.w * post_wb};
+      if (post_clip > 0.f) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[j] = fminf(fmaxf(o[j], -post_clip), post_clip);
+      }
+      z = make_float4(o[0], o[1], o[2], o[3]);
+    }
+    *reinterpret_cast<uint2*>(out2 + orow * Cout + c) = make_uint2(pack_bf16x2(z.x, z.y), pack_bf16x2(z.z, z.w));
+  }
+  if (out == nullptr) return;
   if (out_f32) *reinterpret_cast<float4*>(static_cast<float*>(out) + orow * Cout + c) = y;
   else *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(out) + orow * Cout + c) = make_uint2(pack_bf16x2(y.x, y.y), pack_bf16x2(y.z, y.w));
 }

@@ -33,6 +33,12 @@ struct TapConvLaunch {
   const float* alpha = nullptr;
   const float* beta = nullptr;
   const float* bias = nullptr;   // optional fp32 [Cout] (plain epilogue)
+  int post = 0;                  // POST_* (tapconv.cuh): fused second output
+  void* out2 = nullptr;
+  const float* cscale = nullptr;
+  int cscale_ld = 0;
+  const void* res = nullptr;
+  float post_wa = 0.f, post_wb = 0.f, post_clip = 0.f;
   void* out = nullptr;
   void* out_d = nullptr;
   int force_bn = 0;  // test hook: pin the N tile

@@ -53,19 +53,20 @@ class Block(nn.Module):
         else:
             x = ops.rows(x)
             act = ops.silu_only(x)
-        y, cache['conv_res0'] = self.conv_res0(act, emb, batch_size, c_noise, cache.get('conv_res0', None), update_cache, just_2d)
         c = emb_scale if emb_scale is not None else self.emb_linear(emb, gain=self.emb_gain) + 1
-        y = ops.scale_silu(y, c)                         # y * c -> mp_silu (:75-77)
+        # conv_res0 with `y * c -> mp_silu` (:75-77) fused into its epilogue
+        y, cache['conv_res0'] = self.conv_res0(act, emb, batch_size, c_noise, cache.get('conv_res0', None), update_cache, just_2d,
+                                               post=("scale_silu", c))
         if self.training and self.dropout != 0:
             y = torch.nn.functional.dropout(y, p=self.dropout)
-        y, cache['conv_res1'] = self.conv_res1(y, emb, batch_size, c_noise, cache.get('conv_res1', None), update_cache, just_2d)
         if self.flavor == 'dec' and self.conv_skip is not None:
             x = self.conv_skip(x)
+        # conv_res1 with `mp_sum(x, y, res_balance)` (+ clip when no attention follows) (:86,93) fused into its epilogue
+        x, cache['conv_res1'] = self.conv_res1(y, emb, batch_size, c_noise, cache.get('conv_res1', None), update_cache, just_2d,
+                                               post=("mp_sum", x, self.res_balance, clip if self.num_heads == 0 else 0.0))
         if self.num_heads == 0:
-            x = ops.mp_sum_clip(x, y, self.res_balance, clip)      # mp_sum + clip (:86,93)
             cache['attn'] = None
         else:
-            x = ops.mp_sum_clip(x, y, self.res_balance, 0.0)
             x, cache['attn'] = self.attn(x, batch_size, cache.get('attn', None), update_cache, just_2d, clip=clip)
         return x, cache
 

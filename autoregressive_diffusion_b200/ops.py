@@ -454,7 +454,8 @@ class GatedConvFn(torch.autograd.Function):
     parameter gradients are accumulated straight into .grad."""
 
     @staticmethod
-    def forward(ctx, x, pad5, w2, w3, wg, g_offset, g_mult, g_max, g_min, c_noise, n_seq, S, T, n_ctx, want_grad, n_ctx_dev=None):
+    def forward(ctx, x, pad5, w2, w3, wg, g_offset, g_mult, g_max, g_min, c_noise, n_seq, S, T, n_ctx, want_grad, n_ctx_dev=None,
+                post=None):
         # pad5: [n_seq, 2, h, w, cin_pad] bf16, dense apart from its batch stride (a slice of the previous context works)
         f, cin_pad, h, wd = x.shape
         cin, cout = w2.shape[1], wg.shape[0]
@@ -466,25 +467,43 @@ class GatedConvFn(torch.autograd.Function):
         call("ob_conv_prologue", _vp(x), _vp(pad5), _vp(cx), n_seq, S, T, h * wd * cin_pad, cin, cin_pad, _vp(g_offset),
              _vp(g_mult), _vp(g_max), _vp(g_min), _vp(c_noise), _vp(alpha), _vp(beta), _vp(scratch), n_ctx,
              pad5.stride(0) if pad5 is not None else 0, _vp(n_ctx_dev), stream_ptr())
-        out = empty_rows(f, cout, h, wd, dev)
+        # post = ("scale_silu", cscale fp32 [frames, >=cout]) | ("mp_sum", residual rows, t, clip): fused second output z; the
+        # raw result y is written only when the backward pass will need it
+        out = empty_rows(f, cout, h, wd, dev) if (post is None or want_grad) else None
         out_d = empty_rows(f, cout, h, wd, dev, torch.float16) if want_grad else None
         ws = split_workspace(n_seq, S, T, h, wd, cin_pad, cout, 3, 1, dev)
-        call("ob_conv_fwd", _vp(x), _vp(cx), _vp(wg), _vp(alpha), _vp(beta), _vp(out), _vp(out_d), _vp(ws), n_seq, S, T, h, wd,
-             cin_pad, cout, 3, 1, 0, 27, None, stream_ptr())
+        z = None
+        if post is None:
+            call("ob_conv_fwd", _vp(x), _vp(cx), _vp(wg), _vp(alpha), _vp(beta), _vp(out), _vp(out_d), _vp(ws), n_seq, S, T, h, wd,
+                 cin_pad, cout, 3, 1, 0, 27, None, stream_ptr())
+        else:
+            z = empty_rows(f, cout, h, wd, dev)
+            if post[0] == "scale_silu":
+                cs = post[1]
+                call("ob_conv_fwd_fused", _vp(x), _vp(cx), _vp(wg), _vp(alpha), _vp(beta), _vp(out), _vp(out_d), _vp(ws), n_seq, S, T,
+                     h, wd, cin_pad, cout, 3, 1, 27, 1, _vp(z), _vp(cs), cs.stride(0), None, 0.0, 0.0, stream_ptr())
+            else:
+                call("ob_conv_fwd_fused", _vp(x), _vp(cx), _vp(wg), _vp(alpha), _vp(beta), _vp(out), _vp(out_d), _vp(ws), n_seq, S, T,
+                     h, wd, cin_pad, cout, 3, 1, 27, 2, _vp(z), None, 0, _vp(post[1]), float(post[2]), float(post[3]), stream_ptr())
         if want_grad:
             ctx.save_for_backward(x, cx, w2, w3, wg, ab, out, out_d, g_offset, g_mult, g_max, g_min, c_noise, scratch)
         ctx.dims = (n_seq, S, T, n_ctx)
         ctx.mark_non_differentiable(cx)
         ctx.set_materialize_grads(False)   # otherwise autograd zero-fills a context-sized tensor per layer for cx
-        y = out if cout == w2.shape[0] else out[:, : w2.shape[0]]
-        return y, cx
+        y = None
+        if out is not None:
+            y = out if cout == w2.shape[0] else out[:, : w2.shape[0]]
+        if post is None:
+            return y, cx
+        ctx.mark_non_differentiable(z)     # its gradient reaches y through ScaleSiluPreFn / MpSumPreFn
+        return y, cx, z
 
     @staticmethod
-    def backward(ctx, gy, _gcx):
+    def backward(ctx, gy, _gcx, _gz=None):
         x, cx, w2, w3, wg, ab, y, d, g_offset, g_mult, g_max, g_min, c_noise, scratch = ctx.saved_tensors
         n_seq, S, T, n_ctx = ctx.dims
         if gy is None:
-            return (None,) * 16
+            return (None,) * 17
         f, cin_pad, h, wd = x.shape
         cout, cin = wg.shape[0], w2.shape[1]
         dev = x.device
@@ -530,8 +549,8 @@ class GatedConvFn(torch.autograd.Function):
             call("ob_conv_dgrad", _vp(gy), _vp(gb), _vp(wg), _vp(alpha), _vp(clean_rows_mask(n_seq, S, T, dev)), _vp(dx),
                  _vp(ws), n_seq, S, T, h, wd, cin_pad, cout, 3, 1, 27, stream_ptr())
         if direct:
-            return (dx,) + (None,) * 15
-        return (dx, None, dw2, dw3, None) + gate_grads + (None,) * 7
+            return (dx,) + (None,) * 16
+        return (dx, None, dw2, dw3, None) + gate_grads + (None,) * 8
 
 
 # ----------------------------------------------------------------------------- elementwise
@@ -592,6 +611,37 @@ class ScaleSiluFn(torch.autograd.Function):
         dc = torch.empty((f, c), dtype=torch.float32, device=y.device)
         call("ob_scale_silu_bwd", _vp(y), _vp(cscale), _vp(g), _vp(dy), _vp(dc), f, c, h * w, cscale.stride(0), stream_ptr())
         return dy, dc
+
+
+class ScaleSiluPreFn(torch.autograd.Function):
+    """ScaleSiluFn whose forward result was already produced by the conv's fused epilogue (ob_conv_fwd_fused): only the
+    backward runs a kernel."""
+
+    @staticmethod
+    def forward(ctx, y, cscale, z):
+        ctx.save_for_backward(y, cscale)
+        return z.detach()
+
+    @staticmethod
+    def backward(ctx, g):
+        dy, dc = ScaleSiluFn.backward(ctx, g)
+        return dy, dc, None
+
+
+class MpSumPreFn(torch.autograd.Function):
+    """MpSumFn (a = residual, b = conv result) with the forward result taken from the conv's fused epilogue."""
+
+    @staticmethod
+    def forward(ctx, a, b, z, t, clip):
+        ctx.t, ctx.clip = t, clip
+        if clip > 0:
+            ctx.save_for_backward(z)
+        return z.detach()
+
+    @staticmethod
+    def backward(ctx, g):
+        da, db, _, _ = MpSumFn.backward(ctx, g)
+        return da, db, None, None, None
 
 
 class MpSumFn(torch.autograd.Function):
@@ -675,11 +725,17 @@ def silu_only(x):
     return PixnormSiluFn.apply(rows(x), 1, 0.0)
 
 
-def scale_silu(y, cscale):
+def scale_rows(cscale):
+    """fp32 [frames, C] scale with unit column stride and 16-byte aligned rows (a column slice of the all-blocks embedding
+    GEMM qualifies in place)."""
     cscale = cscale.float()
     if cscale.stride(1) != 1 or cscale.stride(0) % 4 != 0 or cscale.data_ptr() % 16 != 0:
         cscale = cscale.contiguous()
-    return ScaleSiluFn.apply(rows(y), cscale)
+    return cscale
+
+
+def scale_silu(y, cscale):
+    return ScaleSiluFn.apply(rows(y), scale_rows(cscale))
 
 
 def mp_sum_clip(a, b, t, clip=0.0):

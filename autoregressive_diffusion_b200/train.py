@@ -78,7 +78,9 @@ class GradientBuckets:
     bucket by bucket by the fused optimizer (FusedAdamWEMA.step_with_all_reduce), which folds the 1/world of the mean
     into its update."""
 
-    def __init__(self, params, bucket_bytes=128 << 20):
+    def __init__(self, params, bucket_bytes=None):
+        if bucket_bytes is None:
+            bucket_bytes = int(os.environ.get("ONIRIS_BUCKET_MB", "128")) << 20
         self.params = [p for p in params if p.requires_grad]
         self.bucket_elems = max(1, bucket_bytes // 4)
         self.flat = None
@@ -377,6 +379,14 @@ class Trainer:
 
     def _distributed(self):
         return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+    def logged_loss(self, unweighted):
+        """cs_train.py:112-115: the un-weighted loss averaged over the ranks (one scalar all-reduce, logging only)."""
+        t = torch.as_tensor(unweighted, dtype=torch.float32, device=self.device).clone()
+        if self._distributed():
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            t /= dist.get_world_size()
+        return float(t)
 
     def micro_step(self, latents, conditioning=None):
         """One micro-batch forward+backward; every `accum`-th call also syncs gradients and steps the optimizer."""

@@ -89,6 +89,20 @@ int ob_conv_fwd(const void* x, const void* ctx, const void* wg, const float* alp
                 void* out_d, void* split_ws, int n_seq, int S, int T, int H, int W, int cin, int cout, int ksize, int gated,
                 int out_f32, int w_taps, const float* bias, void* stream);
 
+/* ob_conv_fwd with a fused post-op behind the output stage (the "E1" / "E4" epilogues of edm2/networks_edm2.py:75-77 and :86,93;
+ * the reference runs them as separate eager kernels).  A SECOND bf16 output out2 (same shape as out) is computed from the fp32
+ * result y before it is rounded:
+ *   OB_POST_SCALE_SILU: out2 = mp_silu(y * cscale[frame][channel])   cscale fp32, row stride cscale_ld (0 = cout)
+ *   OB_POST_MP_SUM:     out2 = clip(mp_sum(res, y, t))               res bf16 like out; clip <= 0: none
+ * out (the raw y) may be NULL when nothing needs it (evaluation); in training it is still written (the backward pass reads
+ * it).  Works for plain and gated convs, with and without split-K. */
+#define OB_POST_SCALE_SILU 1
+#define OB_POST_MP_SUM 2
+int ob_conv_fwd_fused(const void* x, const void* ctx, const void* wg, const float* alpha, const float* beta, void* out,
+                      void* out_d, void* split_ws, int n_seq, int S, int T, int H, int W, int cin, int cout, int ksize, int gated,
+                      int w_taps, int post, void* out2, const float* cscale, int cscale_ld, const void* res, float t, float clip,
+                      void* stream);
+
 /* Input gradient of ob_conv_fwd.  gy: bf16 [n_seq*S*T, H, W, Cout] = dL/dout (unscaled);
  * gated: gb: bf16 [n_seq*T, H, W, Cout] = sum_s beta_s*dL/dout_s (from ob_gate_bwd) and
  *        dx[b,s,t] = alpha[b,s,t] * convT3x3(gy[b,s,t]) + beta[b,s,t] * causal_convT(gb[b, t+1..t+2]),

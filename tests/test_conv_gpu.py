@@ -184,3 +184,66 @@ def test_weight_gradients_through_autograd_and_direct_agree():
             assert_close(p.grad, a, "direct == autograd", 1e-5, 1e-6)
     finally:
         ops.set_weight_grad_mode(prev)
+
+
+@pytest.mark.parametrize("kind", ["scale_silu", "mp_sum", "mp_sum_clip"])
+@pytest.mark.parametrize("B,n,cin,cout,res", [(2, 3, 64, 64, 8), (2, 16, 128, 128, 32), (2, 16, 512, 512, 4), (2, 16, 512, 512, 8)])
+def test_gated_conv_fused_epilogues(B, n, cin, cout, res, kind):
+    """ob_conv_fwd_fused: the op that follows the conv in the block (edm2/networks_edm2.py:75-77 `mp_silu(y * c)`, :86,93
+    `clip(mp_sum(x, y, t))`) computed in the tap-GEMM's epilogue (and in the split-K finish kernel on the 4x4 / 8x8 levels)
+    -- training forward + every gradient, and the evaluation form that never writes y -- against the oracle's composition."""
+    ob = _mods()
+    torch.manual_seed(7)
+    m = ob.MPCausal3DGatedConv(cin, cout, (3, 3, 3)).cuda()
+    with torch.no_grad():
+        m.gating.offset.copy_(torch.tensor([0.3, -0.2])); m.gating.mult.copy_(torch.tensor([1.2, -0.7]))
+        m.gating.max_gating.fill_(0.5); m.gating.min_gating.fill_(-1.0)
+    w2 = m.last_frame_conv.weight.weight.detach().cpu().clone()
+    w3 = m.weight.weight.detach().cpu().clone()
+    gp = _gate_sd(m)
+    f = B * 2 * n
+    x = bf16r(torch.randn(f, cin, res, res))
+    cn = torch.randn(B, 2 * n)
+    gy = bf16r(torch.randn(f, cout, res, res))
+    cs = torch.randn(f, cout) * 0.3 + 1
+    # clamp case: 10 % of the residuals are pushed far beyond the threshold (robustly clamped), the rest stay far inside -- an
+    # element within one bf16 step of the threshold would be clamped on one side only, and dx sees such flips as sqrt(fraction)
+    r = torch.randn(f, cout, res, res)
+    if kind == "mp_sum_clip":
+        r = r + torch.sign(r) * 60.0 * (torch.rand_like(r) < 0.1)
+    r = bf16r(r)
+    clip = 16.0 if kind == "mp_sum_clip" else 0.0
+
+    def oracle_post(y, cso, ro):
+        if kind == "scale_silu":
+            return O.mp_silu(y * cso[:, :, None, None])
+        out = O.mp_sum(ro, y, 0.3)
+        return out.clamp(-clip, clip) if clip > 0 else out
+
+    m.train()
+    m.fuse_epilogue_in_training = True       # off by default (measured slower in the training step); the evaluation form is always fused
+    xg, csg, rg = x.cuda().requires_grad_(True), cs.cuda().requires_grad_(True), r.cuda().requires_grad_(True)
+    post = ("scale_silu", csg) if kind == "scale_silu" else ("mp_sum", rg, 0.3, clip)
+    z, _ = m(xg, None, B, cn.cuda(), post=post)
+    z.backward(gy.cuda())
+    xo, cso, ro = x.clone().requires_grad_(True), cs.clone().requires_grad_(True), r.clone().requires_grad_(True)
+    w2o, w3o = w2.clone().requires_grad_(True), w3.clone().requires_grad_(True)
+    yo, _ = O.gated_conv(xo, w2o, w3o, gp, B, cn, training=True)
+    zo = oracle_post(yo, cso, ro)
+    zo.backward(gy)
+    assert_close(z.float(), zo, "fused output")
+    # dx sits behind two bf16 kernels here (the post-op's backward rounds dy before the conv's input-gradient pass): measured 2.5e-3
+    assert_close(xg.grad.float(), xo.grad, "dx", mean_rel=3e-3)
+    assert_close(m.last_frame_conv.weight.weight.grad, w2o.grad, "dW2", mean_rel=3e-3)
+    assert_close(m.weight.weight.grad, w3o.grad, "dW3", mean_rel=3e-3)
+    if kind == "scale_silu":
+        assert_close(csg.grad, cso.grad, "dc", 2e-2, 3e-3)       # per-(frame, channel) sums of bf16 products
+    else:
+        inner = ((zo.detach().abs() - clip).abs() > 0.05).float() if clip > 0 else 1.0
+        assert_close(rg.grad.float().cpu() * inner, ro.grad * inner, "d residual")
+    m.eval()
+    with torch.no_grad():
+        ze, _ = m(x[: B * n].cuda(), None, B, cn[:, :n].cuda(), post=(("scale_silu", cs[: B * n].cuda()) if kind == "scale_silu"
+                                                                    else ("mp_sum", r[: B * n].cuda(), 0.3, clip)))
+        ye, _ = O.gated_conv(x[: B * n], O.normalize(w2), O.normalize(w3), gp, B, cn[:, :n], training=False)
+        assert_close(ze.float(), oracle_post(ye, cs[: B * n], r[: B * n]), "fused output (eval, y never written)")

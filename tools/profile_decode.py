@@ -30,5 +30,5 @@ rows = sorted([e for e in prof.key_averages() if e.device_time_total > 0 and e.d
               key=lambda e: -e.device_time_total)
 tot = sum(e.device_time_total for e in rows)
 print(f"GPU busy {tot / 4e3:.2f} ms/eval, {sum(e.count for e in rows) // 4} launches/eval")
-for e in rows[:25]:
+for e in rows[:45]:
     print(f"{e.device_time_total / 4e3:8.3f} ms  {e.count // 4:4d}x  {e.key[:100]}")
