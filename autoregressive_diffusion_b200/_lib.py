@@ -57,6 +57,8 @@ _SIGS = {
     "ob_resample2x": "ppliiiifp",
     "ob_vae_norm_silu_fwd": "pppiliifp",
     "ob_vae_norm_silu_bwd": "pppppiliifp",
+    "ob_time_window": "pppiiliiiip",
+    "ob_ungroup": "ppllliip",
     "ob_set_pdl": "i",
     "ob_adamw_ema": "pppppplpfffffffffp",
     "ob_sumsq": "plpp",

@@ -279,6 +279,12 @@ int ob_vae_norm_silu_bwd(const void* x, const float* film, const void* g, void* 
                          int c, int c_mean, float eps, void* stream) {
   return vae_norm_silu_bwd(x, film, g, dx, dfilm, b, (long)rows_per_batch, c, c_mean, eps, (cudaStream_t)stream);
 }
+int ob_time_window(const void* src, const void* pad, void* dst, int b, int t, int64_t hw, int c, int g, int kt, int backward, void* stream) {
+  return time_window(src, pad, dst, b, t, (long)hw, c, g, kt, backward, (cudaStream_t)stream);
+}
+int ob_ungroup(const void* in, void* out, int64_t frames, int64_t hw, int g, int cc, int inverse, void* stream) {
+  return ungroup(in, out, (long)frames, (long)hw, g, cc, inverse, (cudaStream_t)stream);
+}
 int ob_set_pdl(int enabled) {
   static const bool forced_off = [] { const char* e = getenv("ONIRIS_PDL"); return e != nullptr && e[0] == '0'; }();
   const int prev = pdl_mode();

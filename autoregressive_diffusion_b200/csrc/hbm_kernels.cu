@@ -1027,33 +1027,46 @@ int mp_cat(void* a, void* b, void* cat, long rows, int ca, int cb, float t, int 
 // atomicAdd per (CTA, channel).  film: fp32 [B][2C] = (scale | shift), or nullptr.
 constexpr int VNS_MAXV = 4;   // 8-channel vectors per lane
 __device__ __forceinline__ float silu_f(float y) { return y / (1.f + __expf(-y)); }
+// LPR lanes share one row (LPR = min(32, C/8) rounded up to a power of two): a warp works on 32/LPR rows at once, so
+// narrow rows (the VAE's 32-channel level is 64 bytes per pixel) still fill every lane and every 128-byte line.
+template <int LPR>
+__device__ __forceinline__ float row_sum(float v) {
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
 
+template <int LPR>
 __global__ void __launch_bounds__(256) vae_norm_silu_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ film,
                                                                 __nv_bfloat16* __restrict__ out, long rows_per_batch, int C,
                                                                 int c_mean, float eps) {
   pdl_launch_dependents();
   pdl_wait();
+  constexpr int RPW = 32 / LPR;                   // rows per warp and iteration
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = lane % LPR, rsel = lane / LPR;
   const int b = blockIdx.y;
   const float* fs = film ? film + static_cast<long>(b) * 2 * C : nullptr;
-  for (long r = static_cast<long>(blockIdx.x) * 8 + warp; r < rows_per_batch; r += static_cast<long>(gridDim.x) * 8) {
-    const long off = (static_cast<long>(b) * rows_per_batch + r) * C;
+  for (long r0 = (static_cast<long>(blockIdx.x) * 8 + warp) * RPW; r0 < rows_per_batch; r0 += static_cast<long>(gridDim.x) * 8 * RPW) {
+    const long r = r0 + rsel;
+    const bool live = r < rows_per_batch;
+    const long off = (static_cast<long>(b) * rows_per_batch + (live ? r : 0)) * C;
     float v[VNS_MAXV][8];
     float ss = 0.f;
 #pragma unroll
     for (int k = 0; k < VNS_MAXV; ++k) {
-      const int c = lane * 8 + k * 256;
-      if (c < C) {
+      const int c = (sub + k * LPR) * 8;
+      if (c < C && live) {
         unpack8(*reinterpret_cast<const bf16x8*>(x + off + c), v[k]);
 #pragma unroll
         for (int j = 0; j < 8; ++j) ss += v[k][j] * v[k][j];
       }
     }
-    const float inv = rsqrtf(warp_sum(ss) / c_mean + eps);
+    const float inv = rsqrtf(row_sum<LPR>(ss) / c_mean + eps);
 #pragma unroll
     for (int k = 0; k < VNS_MAXV; ++k) {
-      const int c = lane * 8 + k * 256;
-      if (c < C) {
+      const int c = (sub + k * LPR) * 8;
+      if (c < C && live) {
         float o[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -1067,6 +1080,7 @@ __global__ void __launch_bounds__(256) vae_norm_silu_fwd_kernel(const __nv_bfloa
   }
 }
 
+template <int LPR>
 __global__ void __launch_bounds__(256) vae_norm_silu_bwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ film,
                                                                 const __nv_bfloat16* __restrict__ g, __nv_bfloat16* __restrict__ dx,
                                                                 float* __restrict__ dfilm, long rows_per_batch, int C, int c_mean,
@@ -1074,38 +1088,42 @@ __global__ void __launch_bounds__(256) vae_norm_silu_bwd_kernel(const __nv_bfloa
   pdl_launch_dependents();
   pdl_wait();
   extern __shared__ float sh[];          // FILM: [2C] per-CTA partial sums of (dscale | dshift)
+  constexpr int RPW = 32 / LPR;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = lane % LPR, rsel = lane / LPR;
   const int b = blockIdx.y;
   const float* fs = film ? film + static_cast<long>(b) * 2 * C : nullptr;
   float a_scale[VNS_MAXV][8], a_shift[VNS_MAXV][8];
-#pragma unroll
-  for (int k = 0; k < VNS_MAXV; ++k)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { a_scale[k][j] = 0.f; a_shift[k][j] = 0.f; }
   if (fs) {
+#pragma unroll
+    for (int k = 0; k < VNS_MAXV; ++k)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { a_scale[k][j] = 0.f; a_shift[k][j] = 0.f; }
     for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sh[i] = 0.f;
     __syncthreads();
   }
-  for (long r = static_cast<long>(blockIdx.x) * 8 + warp; r < rows_per_batch; r += static_cast<long>(gridDim.x) * 8) {
-    const long off = (static_cast<long>(b) * rows_per_batch + r) * C;
+  for (long r0 = (static_cast<long>(blockIdx.x) * 8 + warp) * RPW; r0 < rows_per_batch; r0 += static_cast<long>(gridDim.x) * 8 * RPW) {
+    const long r = r0 + rsel;
+    const bool live = r < rows_per_batch;
+    const long off = (static_cast<long>(b) * rows_per_batch + (live ? r : 0)) * C;
     float n[VNS_MAXV][8], gn[VNS_MAXV][8];
     float ss = 0.f;
 #pragma unroll
     for (int k = 0; k < VNS_MAXV; ++k) {
-      const int c = lane * 8 + k * 256;
-      if (c < C) {
+      const int c = (sub + k * LPR) * 8;
+      if (c < C && live) {
         unpack8(*reinterpret_cast<const bf16x8*>(x + off + c), n[k]);
         unpack8(*reinterpret_cast<const bf16x8*>(g + off + c), gn[k]);
 #pragma unroll
         for (int j = 0; j < 8; ++j) ss += n[k][j] * n[k][j];
       }
     }
-    const float inv = rsqrtf(warp_sum(ss) / c_mean + eps);
+    const float inv = rsqrtf(row_sum<LPR>(ss) / c_mean + eps);
     float dot = 0.f;
 #pragma unroll
     for (int k = 0; k < VNS_MAXV; ++k) {
-      const int c = lane * 8 + k * 256;
-      if (c < C) {
+      const int c = (sub + k * LPR) * 8;
+      if (c < C && live) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float nn = n[k][j] * inv;
@@ -1120,11 +1138,11 @@ __global__ void __launch_bounds__(256) vae_norm_silu_bwd_kernel(const __nv_bfloa
         }
       }
     }
-    dot = warp_sum(dot) / c_mean;
+    dot = row_sum<LPR>(dot) / c_mean;
 #pragma unroll
     for (int k = 0; k < VNS_MAXV; ++k) {
-      const int c = lane * 8 + k * 256;
-      if (c < C) {
+      const int c = (sub + k * LPR) * 8;
+      if (c < C && live) {
         float o[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[j] = inv * (gn[k][j] - n[k][j] * dot);
@@ -1135,7 +1153,7 @@ __global__ void __launch_bounds__(256) vae_norm_silu_bwd_kernel(const __nv_bfloa
   if (fs) {
 #pragma unroll
     for (int k = 0; k < VNS_MAXV; ++k) {
-      const int c = lane * 8 + k * 256;
+      const int c = (sub + k * LPR) * 8;
       if (c < C) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) { atomicAdd(&sh[c + j], a_scale[k][j]); atomicAdd(&sh[C + c + j], a_shift[k][j]); }
@@ -1146,8 +1164,15 @@ __global__ void __launch_bounds__(256) vae_norm_silu_bwd_kernel(const __nv_bfloa
   }
 }
 
-static int vns_grid(long rows_per_batch, int B) {
-  long bx = (rows_per_batch + 7) / 8;
+static int vns_lpr(int C) {
+  const int v = C / 8;
+  int l = 1;
+  while (l < v && l < 32) l <<= 1;
+  return l;
+}
+static int vns_grid(long rows_per_batch, int B, int lpr) {
+  const long rpb = 8L * (32 / lpr);                 // rows per CTA and iteration
+  long bx = (rows_per_batch + rpb - 1) / rpb;
   const long cap = (8L * 148 + B - 1) / B;       // ~8 CTAs per SM in total
   if (bx > cap) bx = cap;
   return static_cast<int>(bx < 1 ? 1 : bx);
@@ -1158,8 +1183,15 @@ int vae_norm_silu_fwd(const void* x, const float* film, void* out, int B, long r
   if (c_mean <= 0 || c_mean > C) c_mean = C;
   if (C % 8 != 0 || C > 256 * VNS_MAXV) { set_error("vae_norm_silu: C=%d must be a multiple of 8 and <= %d", C, 256 * VNS_MAXV); return OB_ERR_UNSUPPORTED; }
   if (B <= 0 || rows_per_batch <= 0) return OB_OK;
-  launch(vae_norm_silu_fwd_kernel, dim3(vns_grid(rows_per_batch, B), B), 256, 0, st, 1, static_cast<const __nv_bfloat16*>(x), film,
-         static_cast<__nv_bfloat16*>(out), rows_per_batch, C, c_mean, eps);
+  const int lpr = vns_lpr(C);
+  const dim3 grid(vns_grid(rows_per_batch, B, lpr), B);
+#define VNS_FWD(L) launch(vae_norm_silu_fwd_kernel<L>, grid, 256, 0, st, 1, static_cast<const __nv_bfloat16*>(x), film, \
+                          static_cast<__nv_bfloat16*>(out), rows_per_batch, C, c_mean, eps)
+  switch (lpr) {
+    case 1: VNS_FWD(1); break; case 2: VNS_FWD(2); break; case 4: VNS_FWD(4); break;
+    case 8: VNS_FWD(8); break; case 16: VNS_FWD(16); break; default: VNS_FWD(32); break;
+  }
+#undef VNS_FWD
   return check_launch("vae_norm_silu_fwd");
 }
 
@@ -1170,10 +1202,122 @@ int vae_norm_silu_bwd(const void* x, const float* film, const void* g, void* dx,
   if (film != nullptr && dfilm == nullptr) { set_error("vae_norm_silu_bwd: dfilm is required with film"); return OB_ERR_INVALID; }
   if (B <= 0 || rows_per_batch <= 0) return OB_OK;
   if (film != nullptr) cudaMemsetAsync(dfilm, 0, static_cast<size_t>(B) * 2 * C * sizeof(float), st);
-  launch(vae_norm_silu_bwd_kernel, dim3(vns_grid(rows_per_batch, B), B), 256, film ? 2 * C * sizeof(float) : 0, st, 1,
-         static_cast<const __nv_bfloat16*>(x), film, static_cast<const __nv_bfloat16*>(g), static_cast<__nv_bfloat16*>(dx), dfilm,
-         rows_per_batch, C, c_mean, eps);
+  const int lpr = vns_lpr(C);
+  const dim3 grid(vns_grid(rows_per_batch, B, lpr), B);
+  const size_t shb = film ? 2 * C * sizeof(float) : 0;
+#define VNS_BWD(L) launch(vae_norm_silu_bwd_kernel<L>, grid, 256, shb, st, 1, static_cast<const __nv_bfloat16*>(x), film, \
+                          static_cast<const __nv_bfloat16*>(g), static_cast<__nv_bfloat16*>(dx), dfilm, rows_per_batch, C, c_mean, eps)
+  switch (lpr) {
+    case 1: VNS_BWD(1); break; case 2: VNS_BWD(2); break; case 4: VNS_BWD(4); break;
+    case 8: VNS_BWD(8); break; case 16: VNS_BWD(16); break; default: VNS_BWD(32); break;
+  }
+#undef VNS_BWD
   return check_launch("vae_norm_silu_bwd");
+}
+
+// ============================================================================ VAE grouped causal conv: data movement
+// Reference: edm2/vae/vae.py:40-53.  The conv3d with kernel (kt, 3, 3) and temporal stride g reads, for output group t', the
+// input frames t'g - p .. t'g - p + kt - 1 (p = kt - g frames of left padding: the cache, or a copy of the first p frames).
+// time_window_gather lays those kt frames side by side on the channel axis (one pass; the reference does pad + cat + the
+// strided conv), time_window_scatter is its transpose (every input frame collects its <= kt/g windows), and ungroup moves
+// the (g, Cc)-ordered output channels of a group into g consecutive frames ('b (c g) t h w -> b c (t g) h w').
+// All tensors bf16 NHWC rows; one thread per 8 channels.
+__global__ void __launch_bounds__(256) time_window_gather_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ pad,
+                                                                 __nv_bfloat16* __restrict__ xs, long total8, int T, long hw, int C8,
+                                                                 int g, int kt) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total8) return;
+  const int p = kt - g, Tg = T / g;
+  long r = i;
+  const int c8 = static_cast<int>(r % C8); r /= C8;
+  const int j = static_cast<int>(r % kt); r /= kt;
+  const long px = r % hw; r /= hw;
+  const int tg = static_cast<int>(r % Tg);
+  const long b = r / Tg;
+  const int t = tg * g + j - p;
+  const bf16x8* src;
+  if (t >= 0) src = reinterpret_cast<const bf16x8*>(x) + ((b * T + t) * hw + px) * C8 + c8;
+  else if (pad != nullptr) src = reinterpret_cast<const bf16x8*>(pad) + ((b * p + (t + p)) * hw + px) * C8 + c8;
+  else src = reinterpret_cast<const bf16x8*>(x) + ((b * T + (t + p)) * hw + px) * C8 + c8;     // first p frames stand in for the past
+  reinterpret_cast<bf16x8*>(xs)[i] = *src;
+}
+
+__global__ void __launch_bounds__(256) time_window_scatter_kernel(const __nv_bfloat16* __restrict__ dxs, __nv_bfloat16* __restrict__ dx,
+                                                                  long total8, int T, long hw, int C8, int g, int kt) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total8) return;
+  const int p = kt - g, Tg = T / g;
+  long r = i;
+  const int c8 = static_cast<int>(r % C8); r /= C8;
+  const long px = r % hw; r /= hw;
+  const int t = static_cast<int>(r % T);
+  const long b = r / T;
+  float acc[8];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) acc[u] = 0.f;
+  // windows t' with 0 <= j = t + p - t'g < kt   (the padding frames are detached copies: they receive nothing)
+  for (int tg = (t + p) / g; tg >= 0 && t + p - tg * g < kt; --tg) {
+    if (tg >= Tg) continue;
+    const int j = t + p - tg * g;
+    float f[8];
+    unpack8(reinterpret_cast<const bf16x8*>(dxs)[(((b * Tg + tg) * hw + px) * kt + j) * C8 + c8], f);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) acc[u] += f[u];
+  }
+  reinterpret_cast<bf16x8*>(dx)[i] = pack8(acc);
+}
+
+// inverse == 0: out[(f*g + r), px, c] = in[f, px, r*Cc + c];  inverse != 0: the other way round
+__global__ void __launch_bounds__(256) ungroup_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, long total8,
+                                                      long hw, int g, int Cc8, int inverse) {
+  pdl_launch_dependents();
+  pdl_wait();
+  // one CTA row = one pixel of one group: its g*Cc8 vectors are contiguous in the grouped tensor and form g runs of Cc8
+  // vectors, hw*Cc8 apart, in the un-grouped one (32-bit index math: 64-bit divisions dominated the first version)
+  const unsigned per_px = static_cast<unsigned>(g) * Cc8;
+  const long n_px = total8 / per_px;                       // f * hw pixels
+  for (long p0 = static_cast<long>(blockIdx.x) * (blockDim.x / 32) + (threadIdx.x >> 5); p0 < n_px; p0 += static_cast<long>(gridDim.x) * (blockDim.x / 32)) {
+    const long f = p0 / hw, px = p0 - f * hw;
+    const long grouped0 = p0 * per_px;
+    for (unsigned v = threadIdx.x & 31; v < per_px; v += 32) {
+      const unsigned rr = v / Cc8, c8 = v - rr * Cc8;
+      const long ung = ((f * g + rr) * hw + px) * Cc8 + c8;
+      if (inverse) reinterpret_cast<bf16x8*>(out)[grouped0 + v] = reinterpret_cast<const bf16x8*>(in)[ung];
+      else reinterpret_cast<bf16x8*>(out)[ung] = reinterpret_cast<const bf16x8*>(in)[grouped0 + v];
+    }
+  }
+}
+
+int time_window(const void* src, const void* pad, void* dst, int B, int T, long hw, int C, int g, int kt, int backward, cudaStream_t st) {
+  if (C % 8 != 0 || g <= 0 || kt < g || T % g != 0) { set_error("time_window: C=%d %% 8, g=%d, kt=%d, T=%d", C, g, kt, T); return OB_ERR_INVALID; }
+  if (B <= 0 || T <= 0) return OB_OK;
+  const int C8 = C / 8;
+  if (!backward) {
+    const long total8 = static_cast<long>(B) * (T / g) * hw * kt * C8;
+    launch(time_window_gather_kernel, static_cast<unsigned>((total8 + 255) / 256), 256, 0, st, 1, static_cast<const __nv_bfloat16*>(src),
+           static_cast<const __nv_bfloat16*>(pad), static_cast<__nv_bfloat16*>(dst), total8, T, hw, C8, g, kt);
+  } else {
+    const long total8 = static_cast<long>(B) * T * hw * C8;
+    launch(time_window_scatter_kernel, static_cast<unsigned>((total8 + 255) / 256), 256, 0, st, 1, static_cast<const __nv_bfloat16*>(src),
+           static_cast<__nv_bfloat16*>(dst), total8, T, hw, C8, g, kt);
+  }
+  return check_launch("time_window");
+}
+
+int ungroup(const void* in, void* out, long frames, long hw, int g, int Cc, int inverse, cudaStream_t st) {
+  if (Cc % 8 != 0 || g <= 0) { set_error("ungroup: Cc=%d must be a multiple of 8", Cc); return OB_ERR_INVALID; }
+  const long total8 = frames * g * hw * (Cc / 8);
+  if (total8 <= 0) return OB_OK;
+  const long n_px = frames * hw;
+  long blocks = (n_px + 7) / 8;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  launch(ungroup_kernel, static_cast<unsigned>(blocks), 256, 0, st, 1, static_cast<const __nv_bfloat16*>(in),
+         static_cast<__nv_bfloat16*>(out), total8, hw, g, Cc / 8, inverse);
+  return check_launch("ungroup");
 }
 
 // ============================================================================ 2x resampling

@@ -398,7 +398,7 @@ class RawConvFn(torch.autograd.Function):
             call("ob_conv_wgrad", _vp(gy), _vp(x), None, None, _vp(dwg), 1, 1, f, h, wd, cin_pad, cout_pad, ksize, 0, ns,
                  stream_ptr())
             dw = dwg.sum(0)[:cout, :, :cin]
-        db = gy[:, :cout].float().sum(dim=(0, 2, 3)) if ctx.needs_input_grad[2] else None
+        db = gy[:, :cout].sum(dim=(0, 2, 3), dtype=torch.float32) if ctx.needs_input_grad[2] else None
         return dx, dw, db, None
 
 
@@ -439,6 +439,47 @@ def vae_norm_silu(x, film, batch):
         film = film.float().contiguous()
     out = VaeNormSiluFn.apply(rows(x), film, batch, c)
     return out if out.shape[1] == c else out[:, :c]
+
+
+class TimeWindowFn(torch.autograd.Function):
+    """Temporal im2col of the VAE's grouped causal conv (ob_time_window): x [b*t, C, h, w] (+ pad [b*p, C, h, w] or None)
+    -> xs [b*t/g, kt*C, h, w]."""
+
+    @staticmethod
+    def forward(ctx, x, pad, b, g, kt):
+        f, c, h, w = x.shape
+        t = f // b
+        xs = empty_rows(b * (t // g), kt * c, h, w, x.device)
+        call("ob_time_window", _vp(x), _vp(pad), _vp(xs), b, t, h * w, c, g, kt, 0, stream_ptr())
+        ctx.dims = (b, t, c, h, w, g, kt)
+        return xs
+
+    @staticmethod
+    def backward(ctx, gxs):
+        b, t, c, h, w, g, kt = ctx.dims
+        dx = empty_rows(b * t, c, h, w, gxs.device)
+        call("ob_time_window", _vp(rows(gxs)), None, _vp(dx), b, t, h * w, c, g, kt, 1, stream_ptr())
+        return dx, None, None, None, None
+
+
+class UngroupFn(torch.autograd.Function):
+    """'b (c g) t h w -> b c (t g) h w' for (g, cc)-ordered channels (ob_ungroup): [F, g*cc, h, w] -> [F*g, cc, h, w]."""
+
+    @staticmethod
+    def forward(ctx, y, g):
+        f, gc, h, w = y.shape
+        out = empty_rows(f * g, gc // g, h, w, y.device)
+        call("ob_ungroup", _vp(y), _vp(out), f, h * w, g, gc // g, 0, stream_ptr())
+        ctx.g = g
+        return out
+
+    @staticmethod
+    def backward(ctx, go):
+        g = ctx.g
+        fg, cc, h, w = go.shape
+        dy = empty_rows(fg // g, cc * g, h, w, go.device)
+        call("ob_ungroup", _vp(rows(go)), _vp(dy), fg // g, h * w, g, cc, 1, stream_ptr())
+        return dy, None
 
 
 def raw_conv(x, wmat, ksize, bias=None):

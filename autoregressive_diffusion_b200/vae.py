@@ -71,24 +71,31 @@ class GroupCausal3DConvVAE(nn.Module):
         b, c, t, h, w = x.shape
         g, kt, p = self.group_size, self.conv3d.weight.shape[2], self.time_padding_size
         assert t % g == 0, "the sequence length must be a multiple of the group size"
-        xr = _frames(x).reshape(b, t, c, h, w)
-        if cache is None:
-            pad = xr[:, :p].detach()                                 # :43-44 the first kt-g frames stand in for the past
-        else:                                                        # the reference caches spatially PADDED frames
-            pad = cache[:, :, :, 1:-1, 1:-1].permute(0, 2, 1, 3, 4).to(BF16)
-        xp = torch.cat((pad, xr), dim=1)                             # [b, t+p, c, h, w]
+        xr = _frames(x)                                               # [b*t, c, h, w] bf16 rows
+        fast = c % 8 == 0 and self.out_channels % 8 == 0 and p > 0
+        pad = None
+        if cache is not None:                                         # the reference caches spatially PADDED frames
+            pad = cache[:, :, :, 1:-1, 1:-1].permute(0, 2, 1, 3, 4).to(BF16)   # [b, p, c, h, w]
         new_cache = None
         if not self.training:
-            new_cache = F.pad(xp[:, -p:].permute(0, 2, 1, 3, 4).to(x.dtype), (1, 1, 1, 1)).detach()
-        # temporal im2col: group t' sees frames t'g .. t'g+kt-1 of xp, side by side on the channel axis (kt-major)
-        win = xp.unfold(1, kt, g)                                    # [b, t/g, c, h, w, kt]
-        xs = win.permute(0, 1, 5, 2, 3, 4).reshape(b * (t // g), kt * c, h, w)
+            tail = xr.reshape(b, t, c, h, w)[:, -p:] if t >= p else torch.cat((pad if pad is not None else xr.reshape(b, t, c, h, w)[:, :p], xr.reshape(b, t, c, h, w)), dim=1)[:, -p:]
+            new_cache = F.pad(tail.permute(0, 2, 1, 3, 4).to(x.dtype), (1, 1, 1, 1)).detach()
         wt = self.conv3d.weight                                      # [cout*g, cin, kt, 3, 3], rows ordered (cout, g)
         o = wt.shape[0]
         wmat = wt.reshape(self.out_channels, g, c, kt, 3, 3).permute(1, 0, 4, 5, 3, 2).reshape(o, 9, kt * c)   # rows (g, cout)
-        y = ops.raw_conv(xs, wmat, 3, self.conv3d.bias.reshape(self.out_channels, g).t().reshape(-1))   # [b*t/g, g*cout, h, w]
-        # un-group 'b (c g) t h w -> b c (t g) h w': whole [cout, h, w] frames move
-        y = y.reshape(b, t // g, g, self.out_channels, h, w).reshape(b, t, self.out_channels, h, w).permute(0, 2, 1, 3, 4)
+        bias = self.conv3d.bias.reshape(self.out_channels, g).t().reshape(-1)
+        if fast:
+            # temporal im2col in one pass: group t' sees frames t'g-p .. t'g+g-1, side by side on the channel axis (kt-major)
+            pad_rows = ops.rows(pad.reshape(b * p, c, h, w)) if pad is not None else None
+            xs = ops.TimeWindowFn.apply(xr, pad_rows, b, g, kt)
+            y = ops.raw_conv(xs, wmat, 3, bias)                      # [b*t/g, g*cout, h, w]
+            y = _video(ops.UngroupFn.apply(ops.rows(y), g) if g > 1 else y, b)   # un-group: whole [cout, h, w] frames move
+        else:                                                        # odd channel counts (the RGB input layer): torch glue
+            x5 = xr.reshape(b, t, c, h, w)
+            xp = torch.cat((pad if pad is not None else x5[:, :p].detach(), x5), dim=1)
+            xs = xp.unfold(1, kt, g).permute(0, 1, 5, 2, 3, 4).reshape(b * (t // g), kt * c, h, w)
+            y = ops.raw_conv(xs, wmat, 3, bias)
+            y = y.reshape(b, t // g, g, self.out_channels, h, w).reshape(b, t, self.out_channels, h, w).permute(0, 2, 1, 3, 4)
         return y, new_cache
 
 

@@ -200,6 +200,16 @@ int ob_vae_norm_silu_fwd(const void* x, const float* film, void* out, int b, int
 int ob_vae_norm_silu_bwd(const void* x, const float* film, const void* g, void* dx, float* dfilm, int b, int64_t rows_per_batch,
                          int c, int c_mean, float eps, void* stream);
 
+/* Data movement of the VAE's grouped causal conv (edm2/vae/vae.py:40-53), bf16 NHWC rows, c % 8 == 0:
+ * ob_time_window, backward == 0: xs[b, t', px, j*c + ch] = x[b, t'*g + j - (kt-g), px, ch] for j < kt -- the kt input frames output
+ *   group t' reads, side by side on the channel axis (x: [b, t, hw, c]; xs: [b, t/g, hw, kt*c]); frames before the start come
+ *   from pad [b, kt-g, hw, c] (the conv cache) or, pad == NULL, from the first kt-g frames of x (:43-44);
+ * backward != 0: the transpose, src = dxs -> dst = dx (padding frames receive nothing: they are detached copies).
+ * ob_ungroup: 'b (c g) t h w -> b c (t g) h w' for channels ordered (g, cc): out[f*g + r, px, ch] = in[f, px, r*cc + ch]
+ *   (inverse != 0: the other direction, used by the backward pass). */
+int ob_time_window(const void* src, const void* pad, void* dst, int b, int t, int64_t hw, int c, int g, int kt, int backward, void* stream);
+int ob_ungroup(const void* in, void* out, int64_t frames, int64_t hw, int g, int cc, int inverse, void* stream);
+
 /* Programmatic dependent launch: when on (default; ONIRIS_PDL=0 in the environment forces it off), every kernel of the
  * library is launched so that its prologue overlaps the tail of the previous kernel on the stream.  mode 0: off, 1: every
  * kernel, 2: only the light (elementwise) kernels.  Returns the previous mode.  The training backward pass switches it off
