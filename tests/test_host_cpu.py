@@ -199,3 +199,30 @@ def test_tiling_policy_queries_run_without_a_gpu():
     assert s(2, 2, 16, 16, 16, 256, 256, 3, 1) == 3                                 # 54 CTAs -> 162
     assert s(2, 2, 16, 32, 32, 128, 128, 3, 1) == 11                                # two-tap groups: 14 CTAs -> 154
     assert s(1, 1, 64, 4, 4, 512, 512, 1, 0) >= 1
+
+
+def test_latent_shard_round_trip_and_clip_slicing(tmp_path):
+    """The latent wire format: write episodes as MDS-layout shards, read them back bit-exactly, and cut them into
+    clips exactly as edm2/cs_dataloading.py:53-71 does (un-pinned against the real library: it is not installed here)."""
+    from autoregressive_diffusion_b200 import latent_shards as ls
+    rng = np.random.default_rng(0)
+    episodes = [{"mean": rng.standard_normal((8, t, 4, 4)).astype(np.float16), "action": rng.integers(0, 4, size=(t, 3)).astype(np.int64)}
+                for t in (40, 16, 37)]
+    with ls.ShardWriter(str(tmp_path), size_limit=12000) as w:
+        for e in episodes:
+            w.write(e)
+    index = __import__("json").load(open(tmp_path / "index.json"))
+    assert index["version"] == 2 and sum(s["samples"] for s in index["shards"]) == 3 and len(index["shards"]) >= 2
+    back = [ex for s in index["shards"] for ex in ls.read_shard(str(tmp_path / s["raw_data"]["basename"]))]
+    for a, b in zip(episodes, back):
+        assert np.array_equal(a["mean"], b["mean"]) and a["mean"].dtype == b["mean"].dtype and np.array_equal(a["action"], b["action"])
+    clips = list(ls.LatentClips(str(tmp_path), clip_size=16))
+    assert len(clips) == 40 // 16 + 16 // 16 + 37 // 16
+    m0, a0 = clips[0]
+    assert tuple(m0.shape) == (16, 8, 4, 4) and torch.equal(m0, torch.from_numpy(episodes[0]["mean"]).permute(1, 0, 2, 3)[:16])
+    assert torch.equal(clips[1][1], torch.from_numpy(episodes[0]["action"])[16:32])
+    both = [c for r in range(2) for c in ls.LatentClips(str(tmp_path), 16, rank=r, world=2)]
+    assert len(both) == len(clips)
+    means, actions = ls.collate(clips[:2])
+    lat = ls.normalize_latents(means, torch.arange(8.0), torch.full((8,), 2.0))
+    assert torch.allclose(lat, (means.float() - torch.arange(8.0)[:, None, None]) / 2.0)
