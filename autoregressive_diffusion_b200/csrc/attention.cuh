@@ -106,6 +106,23 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
+// exp2 on the FMA pipe: round-to-nearest split x = i + f with the 1.5*2^23 trick, a degree-3 minimax polynomial for 2^f on
+// [-0.5, 0.5] (max relative error 7.5e-5, far below the bf16 rounding of P), and 2^i added into the exponent field.
+// ncu (profiles/r02_ncu_attention_summary.txt + source page): 31 % of the forward kernel's stall samples sit on MUFU.EX2
+// -- the softmax warps are bound by the 16/clk/SM transcendental unit, not by the tensor pipe (24 % active) -- so every
+// third exponential is computed here instead (9 FMA-pipe operations at 128/clk/SM), which balances the two pipes.
+// Valid for x in [-120, 120]: the callers' arguments lie in [-45, 0] (|logit| <= 8, fixed maximum / saved lse).
+__device__ __forceinline__ float poly_exp2(float x) {
+  const float t = x + 12582912.f;                  // 1.5 * 2^23: the integer part lands in the low mantissa bits
+  const float f = x - (t - 12582912.f);            // in [-0.5, 0.5]
+  float p = fmaf(0.0551706217f, f, 0.242608815f);
+  p = fmaf(p, f, 0.693260968f);
+  p = fmaf(p, f, 0.999928236f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+// which elements of an unrolled chunk take the polynomial
+#define ATTN_EXP_POLY(idx) (((idx) % 3) == 2)
+
 constexpr int ATTN_KV_STAGES = 3;
 constexpr int ATTN_TILE_BYTES = 128 * 128;  // [128 rows][64 bf16]
 constexpr int ATTN_SMEM_BYTES = 1024 + ATTN_TILE_BYTES /*Q*/ + ATTN_KV_STAGES * 2 * ATTN_TILE_BYTES /*K,V*/ +
@@ -126,7 +143,8 @@ __device__ __forceinline__ float softmax_chunk(const float (&s)[32], uint32_t (&
     float pv[2];
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
-      float e = fast_exp2(s[i + u] * c1 - c2);
+      const float arg = s[i + u] * c1 - c2;
+      float e = ATTN_EXP_POLY(i + u) ? poly_exp2(arg) : fast_exp2(arg);
       if (MASKED) {
         bool ok = (ik0 + i + u < Lk) && frame_visible(mask, n_frames, qf, kf);
         if (mask == ATTN_DART_LISTED) ok = ok && block_listed(n_frames * hw, iq, ik0 + i + u);

@@ -155,7 +155,8 @@ __device__ __forceinline__ void ds_chunk_row(const float (&s)[32], const float (
     float ds[2];
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
-      float pr = fast_exp2(s[i + u] * c1 - lse2);
+      const float arg = s[i + u] * c1 - lse2;
+      float pr = ATTN_EXP_POLY(i + u) ? poly_exp2(arg) : fast_exp2(arg);
       if (MASKED) {
         bool ok = (ik0 + i + u < Lk) && frame_visible(mask, n_frames, qf, kf);
         if (mask == ATTN_DART_LISTED) ok = ok && block_listed(n_frames * hw, iq, ik0 + i + u);
@@ -183,7 +184,8 @@ __device__ __forceinline__ void pds_chunk_col(const float (&s)[32], const float 
     float pv[4], ds[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      float pr = fast_exp2(s[i + u] * c1 - l4[u]);
+      const float arg = s[i + u] * c1 - l4[u];
+      float pr = ATTN_EXP_POLY(i + u) ? poly_exp2(arg) : fast_exp2(arg);
       if (MASKED) {
         bool ok = (iq0 + i + u < Lq) && frame_visible(mask, n_frames, qf, kf);
         if (mask == ATTN_DART_LISTED) ok = ok && block_listed(n_frames * hw, iq0 + i + u, ik);
