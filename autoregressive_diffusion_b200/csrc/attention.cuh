@@ -126,8 +126,16 @@ __device__ __forceinline__ float poly_exp2(float x) {
 constexpr int ATTN_KV_STAGES = 3;
 constexpr int ATTN_TILE_BYTES = 128 * 128;  // [128 rows][64 bf16]
 constexpr int ATTN_SMEM_BYTES = 1024 + ATTN_TILE_BYTES /*Q*/ + ATTN_KV_STAGES * 2 * ATTN_TILE_BYTES /*K,V*/ +
-                                2 * 2 * ATTN_TILE_BYTES /*P x2*/ + 1024 /*row sums*/ + 256;
-constexpr int ATTN_SOFTMAX_WARPS = 8;   // two warps per TMEM lane quarter, each owning 64 of the 128 key columns
+                                2 * 2 * ATTN_TILE_BYTES /*P x2*/ + 2048 /*row sums*/ + 256;
+#ifndef ATTN_SOFTMAX_WARPS_N
+#define ATTN_SOFTMAX_WARPS_N 16
+#endif
+// ATTN_PARTS warps per TMEM lane quarter, each owning 128/ATTN_PARTS of the tile's key columns (the softmax warps are
+// latency-bound -- MUFU + tcgen05.ld round trips -- so four warps per scheduler hide more of it than two)
+constexpr int ATTN_SOFTMAX_WARPS = ATTN_SOFTMAX_WARPS_N;
+constexpr int ATTN_PARTS = ATTN_SOFTMAX_WARPS / 4;
+constexpr int ATTN_PART_COLS = ATTN_BN / ATTN_PARTS;
+static_assert(ATTN_PARTS == 2 || ATTN_PARTS == 4, "softmax warps: 8 or 16");
 constexpr int ATTN_THREADS = 64 + 32 * ATTN_SOFTMAX_WARPS;
 
 // p = exp2(s*c1 - c2) for 32 logits, rounded to bf16 pairs; returns the (fp32) sum.  MASKED: keys are tested one by
@@ -174,8 +182,8 @@ __global__ void __launch_bounds__(ATTN_THREADS, 1) attn_fwd_kernel(const __grid_
   const uint32_t sQ = base;
   const uint32_t sKV = sQ + ATTN_TILE_BYTES;                       // stage s: K at +s*32K, V at +s*32K+16K
   const uint32_t sP = sKV + ATTN_KV_STAGES * 2 * ATTN_TILE_BYTES;  // buffer b: two 16 KB K-major sub-tiles
-  const uint32_t sL = sP + 2 * 2 * ATTN_TILE_BYTES;                // [2 halves][128 rows] partial row sums
-  const uint32_t bar = sL + 1024;
+  const uint32_t sL = sP + 2 * 2 * ATTN_TILE_BYTES;                // [ATTN_PARTS][128 rows] partial row sums
+  const uint32_t bar = sL + 2048;
   const uint32_t q_full = bar;
   auto kv_full = [&](int s) { return bar + 8u * (1 + s); };
   auto kv_empty = [&](int s) { return bar + 8u * (1 + ATTN_KV_STAGES + s); };
@@ -296,10 +304,11 @@ __global__ void __launch_bounds__(ATTN_THREADS, 1) attn_fwd_kernel(const __grid_
       __syncwarp();
     }
   } else {
-    // ---- softmax: 8 warps; warp pair (q, q+4) shares TMEM lane quarter q, each owns 64 key columns of the tile
+    // ---- softmax: warps (q, q+4, ...) share TMEM lane quarter q, each owns ATTN_PART_COLS key columns of the tile
     const int sw = warp - 2;
     const int qw = warp & 3;
-    const int half = sw >> 2;
+    const int part = sw >> 2;
+    const int half = part / (ATTN_PARTS / 2);          // which 64-column K-major sub-tile of P
     const int r = qw * 32 + lane;          // row of the tile == TMEM lane
     const int iq = q0 + r;
     const int qf = iq / p.hw;
@@ -324,41 +333,67 @@ __global__ void __launch_bounds__(ATTN_THREADS, 1) attn_fwd_kernel(const __grid_
       tc_fence_after();
       if (j >= 2) mbar_wait(p_empty(b), ((j >> 1) & 1) ^ 1);
       const uint32_t sPb = sP + b * 2 * ATTN_TILE_BYTES + half * ATTN_TILE_BYTES;   // this half's K-major sub-tile
-      float s0[32], s1[32];
-      tmem_ld32(tS0 + lane_off + b * ATTN_BN + half * 64, s0);
-      tmem_ld32(tS0 + lane_off + b * ATTN_BN + half * 64 + 32, s1);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(s_empty(b));          // S buffer may be overwritten by the MMA of tile j+2
-      uint32_t pk0[16], pk1[16];
-      const int ik0 = k0 + half * 64;
-      if (all_vis) {
-        l += softmax_chunk<false>(s0, pk0, c1, c2, p.mask, p.n_frames, qf, ik0, Lk, p.hw, iq);
-        l += softmax_chunk<false>(s1, pk1, c1, c2, p.mask, p.n_frames, qf, ik0 + 32, Lk, p.hw, iq);
-      } else {
-        l += softmax_chunk<true>(s0, pk0, c1, c2, p.mask, p.n_frames, qf, ik0, Lk, p.hw, iq);
-        l += softmax_chunk<true>(s1, pk1, c1, c2, p.mask, p.n_frames, qf, ik0 + 32, Lk, p.hw, iq);
-      }
+      const int ik0 = k0 + part * ATTN_PART_COLS;
       const uint32_t row_base = sPb + r * 128;
+      if constexpr (ATTN_PARTS == 2) {
+        float s0[32], s1[32];
+        tmem_ld32(tS0 + lane_off + b * ATTN_BN + part * 64, s0);
+        tmem_ld32(tS0 + lane_off + b * ATTN_BN + part * 64 + 32, s1);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(s_empty(b));          // S buffer may be overwritten by the MMA of tile j+2
+        uint32_t pk0[16], pk1[16];
+        if (all_vis) {
+          l += softmax_chunk<false>(s0, pk0, c1, c2, p.mask, p.n_frames, qf, ik0, Lk, p.hw, iq);
+          l += softmax_chunk<false>(s1, pk1, c1, c2, p.mask, p.n_frames, qf, ik0 + 32, Lk, p.hw, iq);
+        } else {
+          l += softmax_chunk<true>(s0, pk0, c1, c2, p.mask, p.n_frames, qf, ik0, Lk, p.hw, iq);
+          l += softmax_chunk<true>(s1, pk1, c1, c2, p.mask, p.n_frames, qf, ik0 + 32, Lk, p.hw, iq);
+        }
 #pragma unroll
-      for (int ch = 0; ch < 8; ++ch) {
-        const uint32_t chunk = static_cast<uint32_t>(ch) ^ static_cast<uint32_t>(r & 7);
-        const uint32_t* src = ch < 4 ? &pk0[ch * 4] : &pk1[(ch - 4) * 4];
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row_base + (chunk << 4)), "r"(src[0]), "r"(src[1]),
-                     "r"(src[2]), "r"(src[3])
-                     : "memory");
+        for (int ch = 0; ch < 8; ++ch) {
+          const uint32_t chunk = static_cast<uint32_t>(ch) ^ static_cast<uint32_t>(r & 7);
+          const uint32_t* src = ch < 4 ? &pk0[ch * 4] : &pk1[(ch - 4) * 4];
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row_base + (chunk << 4)), "r"(src[0]), "r"(src[1]),
+                       "r"(src[2]), "r"(src[3])
+                       : "memory");
+        }
+      } else {
+        float s0[32];
+        tmem_ld32(tS0 + lane_off + b * ATTN_BN + part * 32, s0);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(s_empty(b));
+        uint32_t pk0[16];
+        if (all_vis) l += softmax_chunk<false>(s0, pk0, c1, c2, p.mask, p.n_frames, qf, ik0, Lk, p.hw, iq);
+        else l += softmax_chunk<true>(s0, pk0, c1, c2, p.mask, p.n_frames, qf, ik0, Lk, p.hw, iq);
+        const int ch0 = (part & 1) * 4;                  // 16-byte chunks [ch0, ch0+4) of the 128-byte row
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          const uint32_t chunk = static_cast<uint32_t>(ch0 + ch) ^ static_cast<uint32_t>(r & 7);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row_base + (chunk << 4)), "r"(pk0[ch * 4]),
+                       "r"(pk0[ch * 4 + 1]), "r"(pk0[ch * 4 + 2]), "r"(pk0[ch * 4 + 3])
+                       : "memory");
+        }
       }
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full(b));
     }
-    // ---- combine the two halves' row sums, then O / l; each half writes 32 of the 64 output channels
-    asm volatile("st.shared.f32 [%0], %1;" ::"r"(sL + (half * 128 + r) * 4), "f"(l) : "memory");
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    float l_other;
-    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(l_other) : "r"(sL + ((half ^ 1) * 128 + r) * 4));
-    l += l_other;
+    // ---- combine the parts' row sums, then O / l; parts 0 and 1 each write 32 of the 64 output channels
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(sL + (part * 128 + r) * 4), "f"(l) : "memory");
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * ATTN_SOFTMAX_WARPS) : "memory");
+    l = 0.f;
+#pragma unroll
+    for (int pp = 0; pp < ATTN_PARTS; ++pp) {            // same order in every part: identical l in all of them
+      float lp;
+      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(lp) : "r"(sL + (pp * 128 + r) * 4));
+      l += lp;
+    }
+    if (part < 2) {
+    const int half = part;
     if (n_kv > 0) {
       mbar_wait(o_full, 0);
       tc_fence_after();
@@ -387,6 +422,7 @@ __global__ void __launch_bounds__(ATTN_THREADS, 1) attn_fwd_kernel(const __grid_
             make_uint4(pack_bf16x2(o[i] * inv_l, o[i + 1] * inv_l), pack_bf16x2(o[i + 2] * inv_l, o[i + 3] * inv_l),
                        pack_bf16x2(o[i + 4] * inv_l, o[i + 5] * inv_l), pack_bf16x2(o[i + 6] * inv_l, o[i + 7] * inv_l));
       if (half == 0 && p.lse != nullptr) p.lse[static_cast<long>(bh) * p.Lq + iq] = ATTN_SMAX + __logf(fmaxf(l, 1e-37f));
+    }
     }
     tc_fence_before();
   }

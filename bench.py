@@ -127,7 +127,7 @@ class KernelProfiler:
     FLOPs for the tcgen05 tap-GEMM (ob_conv_fwd / ob_conv_dgrad), algorithmic HBM bytes for the bandwidth-bound kernels."""
 
     def __init__(self):
-        self.events, self.launches = [], 0
+        self.events, self.launches, self.tag = [], 0, None
 
     def before(self, name, args):
         self.launches += KERNELS_PER_CALL.get(name, 1)
@@ -143,12 +143,14 @@ class KernelProfiler:
             work = _conv_flops(name, args)
         elif name in HBM_BYTES:
             work = float(HBM_BYTES[name](args))
-        self.events.append((name, e0, e1, work))
+        self.events.append((name, e0, e1, work, self.tag))
 
-    def table(self):
-        """{entry point: [ms, launches, work]}"""
+    def table(self, tag=None):
+        """{entry point: [ms, launches, work]} (optionally only the launches recorded under `tag`)"""
         t = {}
-        for name, e0, e1, work in self.events:
+        for name, e0, e1, work, tg in self.events:
+            if tag is not None and tg != tag:
+                continue
             r = t.setdefault(name, [0.0, 0, 0.0])
             r[0] += e0.elapsed_time(e1)
             r[1] += 1
@@ -354,6 +356,8 @@ def run_ours(args):
         """4 micro-steps + the optimizer update without the collective (a parked GPU would otherwise be timed waiting for
         its peers): with several ranks the accumulated gradients are dropped instead of applied, so replicas stay equal."""
         for i in range(4):
+            if _lib._profiler is not None:
+                _lib._profiler.tag = "2d" if tr._is_2d(tr.micro + 1) else "3d"
             tr._forward_backward(resident[i % n_host])
         if world > 1:
             tr.buckets.flat.zero_()
@@ -417,6 +421,9 @@ def run_ours(args):
     conv_launches = sum(table[k][1] for k in CONV_CALLS if k in table)
     peak_tf, peak_gbs, peak_kind = measured_peaks()
     achieved = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+    t3 = prof.table("3d")
+    ms3 = sum(t3[k][0] for k in CONV_CALLS if k in t3)
+    achieved_3d = sum(t3[k][2] for k in CONV_CALLS if k in t3) / (ms3 * 1e-3) / 1e12 if ms3 > 0 else None
     hbm = []
     for name, (k_ms, k_n, k_bytes) in sorted(table.items(), key=lambda kv: -kv[1][0]):
         if name in HBM_BYTES and k_ms > 0:
@@ -437,6 +444,9 @@ def run_ours(args):
         "roofline": {"bound": "tensor", "kernel": "tapconv_kernel (gated 3D causal conv fwd incl. fused scale-silu / mp_sum epilogues + dgrad, tcgen05)",
                      "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                      "peak_kind": f"{peak_kind} bf16_tflops_sustained", "launches": conv_launches,
+                     "achieved_3d_microsteps": achieved_3d, "frac_3d_microsteps": achieved_3d / peak_tf if achieved_3d else None,
+                     "note_3d": "the same measurement restricted to the three 3-D (DART) micro-steps of the cycle: the basis of the round-1 figure; "
+                                "`achieved` / `frac` average every tap-GEMM launch of the cycle including the 2-D micro-step's smaller GEMMs",
                      "share_of_step": conv_ms / serial_cycle_ms,
                      "share_basis": "tap-GEMM launch time / single-stream (serialised) time of the same eager cycle -- the basis of the ncu launch list in profiles/",
                      "traffic": tapconv_traffic(),
