@@ -40,7 +40,7 @@ int attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, i
     if (e != cudaSuccess) { set_error("attn_fwd smem attr: %s", cudaGetErrorString(e)); return OB_ERR_CUDA; }
     attr = true;
   }
-  dim3 grid((Lq + ATTN_BM - 1) / ATTN_BM, BH);
+  dim3 grid(BH, (Lq + ATTN_BM - 1) / ATTN_BM);   // query tiles on grid.y, heaviest first (attn_fwd_kernel)
   launch(attn_fwd_kernel<false>, grid, ATTN_THREADS, ATTN_SMEM_BYTES, st, 1, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("attn_fwd launch: %s", cudaGetErrorString(e)); return OB_ERR_CUDA; }

@@ -123,48 +123,130 @@ __device__ __forceinline__ float poly_exp2(float x) {
 // which elements of an unrolled chunk take the polynomial
 #define ATTN_EXP_POLY(idx) (((idx) % 3) == 2)
 
-constexpr int ATTN_KV_STAGES = 3;
+#ifndef ATTN_KV_STAGES_N
+#define ATTN_KV_STAGES_N 4
+#endif
+constexpr int ATTN_KV_STAGES = ATTN_KV_STAGES_N;
 constexpr int ATTN_TILE_BYTES = 128 * 128;  // [128 rows][64 bf16]
 constexpr int ATTN_SMEM_BYTES = 1024 + ATTN_TILE_BYTES /*Q*/ + ATTN_KV_STAGES * 2 * ATTN_TILE_BYTES /*K,V*/ +
                                 2 * 2 * ATTN_TILE_BYTES /*P x2*/ + 2048 /*row sums*/ + 256;
-#ifndef ATTN_SOFTMAX_WARPS_N
-#define ATTN_SOFTMAX_WARPS_N 16
+// four softmax warps per TMEM lane quarter (= per scheduler): with two the warps were latency-bound (MUFU + tcgen05.ld
+// round trips; 526 -> 628 TFLOP/s at 131k tokens going to four)
+#ifndef ATTN_DIAG
+#define ATTN_DIAG 0
 #endif
-// ATTN_PARTS warps per TMEM lane quarter, each owning 128/ATTN_PARTS of the tile's key columns (the softmax warps are
-// latency-bound -- MUFU + tcgen05.ld round trips -- so four warps per scheduler hide more of it than two)
-constexpr int ATTN_SOFTMAX_WARPS = ATTN_SOFTMAX_WARPS_N;
+#ifndef ATTN_HEAVY_FIRST
+#define ATTN_HEAVY_FIRST 1
+#endif
+constexpr int ATTN_SOFTMAX_WARPS = 16;
 constexpr int ATTN_PARTS = ATTN_SOFTMAX_WARPS / 4;
-constexpr int ATTN_PART_COLS = ATTN_BN / ATTN_PARTS;
-static_assert(ATTN_PARTS == 2 || ATTN_PARTS == 4, "softmax warps: 8 or 16");
 constexpr int ATTN_THREADS = 64 + 32 * ATTN_SOFTMAX_WARPS;
 
-// p = exp2(s*c1 - c2) for 32 logits, rounded to bf16 pairs; returns the (fp32) sum.  MASKED: keys are tested one by
-// one against the frame rule (only for tiles that straddle a mask edge).
-template <bool MASKED>
-__device__ __forceinline__ float softmax_chunk(const float (&s)[32], uint32_t (&packed)[16], float c1, float c2, int mask,
-                                               int n_frames, int qf, int ik0, int Lk, int hw, int iq) {
-  float sum = 0.f;
-  int kf = 0, rem = 0;
-  if (MASKED) { kf = ik0 / hw; rem = ik0 - kf * hw; }
-#pragma unroll
-  for (int i = 0; i < 32; i += 2) {
-    float pv[2];
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const float arg = s[i + u] * c1 - c2;
-      float e = ATTN_EXP_POLY(i + u) ? poly_exp2(arg) : fast_exp2(arg);
-      if (MASKED) {
-        bool ok = (ik0 + i + u < Lk) && frame_visible(mask, n_frames, qf, kf);
-        if (mask == ATTN_DART_LISTED) ok = ok && block_listed(n_frames * hw, iq, ik0 + i + u);
-        if (++rem == hw) { rem = 0; ++kf; }
-        e = ok ? e : 0.f;
-      }
-      pv[u] = e;
-    }
-    sum += pv[0] + pv[1];
-    packed[i >> 1] = pack_bf16x2(pv[0], pv[1]);
+// ---- packed fp32 pairs: one FFMA2 / FADD2 issue slot does two lanes' worth of work per thread (sm_100 fma.rn.f32x2)
+__device__ __forceinline__ uint64_t pack2(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// poly_exp2 on a pair
+__device__ __forceinline__ void poly_exp2_pair(uint64_t x, float& e0, float& e1) {
+  const uint64_t magic = pack2(12582912.f, 12582912.f);
+  const uint64_t t = add2(x, magic);
+  const uint64_t f = sub2(x, sub2(t, magic));
+  uint64_t q = fma2(pack2(0.0551706217f, 0.0551706217f), f, pack2(0.242608815f, 0.242608815f));
+  q = fma2(q, f, pack2(0.693260968f, 0.693260968f));
+  q = fma2(q, f, pack2(0.999928236f, 0.999928236f));
+  float q0, q1, t0, t1;
+  unpack2(q, q0, q1);
+  unpack2(t, t0, t1);
+  e0 = __int_as_float(__float_as_int(q0) + (__float_as_int(t0) << 23));
+  e1 = __int_as_float(__float_as_int(q1) + (__float_as_int(t1) << 23));
+}
+// which PAIRS of an unrolled 32-element chunk take the polynomial (5 of 16)
+#define ATTN_PAIR_POLY(pi) (((pi) % 3) == 2)
+
+// The keys a query row sees, as two windows of token indices: [0, w1_end) and [w2_lo, w2_hi).  Every mask of this file
+// has that shape per row -- causal / clean DART rows: one window up to the end of the row's frame; noised DART rows: the
+// clean frames strictly before their own, plus their own frame; ATTN_DART_LISTED clips both to the listed 128-token
+// blocks (block_listed) -- so tile and element tests are integer compares, no per-tile division.
+struct RowWindows {
+  int w1_end, w2_lo, w2_hi;
+  __device__ __forceinline__ bool whole_tile(int k0) const {
+    return (k0 + ATTN_BN <= w1_end) || (k0 >= w2_lo && k0 + ATTN_BN <= w2_hi);
   }
-  return sum;
+};
+__device__ __forceinline__ RowWindows row_windows(int mask, int n_frames, int hw, int iq, int Lk) {
+  RowWindows w;
+  w.w2_lo = w.w2_hi = 0;
+  const int qf = iq / hw;
+  if (mask == ATTN_FULL) w.w1_end = Lk;
+  else if (mask == ATTN_CAUSAL || qf < n_frames) w.w1_end = (qf + 1) * hw;
+  else {
+    w.w1_end = (qf - n_frames) * hw;
+    w.w2_lo = qf * hw;
+    w.w2_hi = w.w2_lo + hw;
+    if (mask == ATTN_DART_LISTED) {
+      const int n_hw = n_frames * hw, blk = (iq >> 7) << 7;
+      w.w1_end = min(w.w1_end, ((iq - n_hw) >> 7) << 7);
+      w.w2_lo = max(w.w2_lo, blk);
+      w.w2_hi = min(w.w2_hi, blk + 128);
+    }
+  }
+  w.w1_end = min(w.w1_end, Lk);
+  w.w2_hi = min(w.w2_hi, Lk);
+  return w;
+}
+
+// p = exp2(s*c1 - c2) for 32 logits, rounded to bf16 pairs; returns the (fp32) sum.  MASKED: keys are tested one by
+// one against the row's windows, given relative to the chunk's first key (only for tiles that straddle a mask edge).
+template <bool MASKED>
+__device__ __forceinline__ float softmax_chunk(const float (&s)[32], uint32_t (&packed)[16], float c1, float c2, int rel_end,
+                                               int rel_lo, int rel_hi) {
+  const uint64_t C1 = pack2(c1, c1), C2 = pack2(-c2, -c2);
+  uint64_t acc = pack2(0.f, 0.f);
+  const unsigned w2_len = static_cast<unsigned>(rel_hi - rel_lo);
+#pragma unroll
+  for (int pi = 0; pi < 16; ++pi) {
+    const uint64_t arg = fma2(pack2(s[2 * pi], s[2 * pi + 1]), C1, C2);
+    float e0, e1;
+#if ATTN_DIAG == 1
+    if (true) unpack2(arg, e0, e1);
+    else
+#endif
+    if (ATTN_PAIR_POLY(pi)) poly_exp2_pair(arg, e0, e1);
+    else {
+      float a0, a1;
+      unpack2(arg, a0, a1);
+      e0 = fast_exp2(a0);
+      e1 = fast_exp2(a1);
+    }
+    if (MASKED) {
+      const int i0 = 2 * pi, i1 = 2 * pi + 1;
+      e0 = (i0 < rel_end || static_cast<unsigned>(i0 - rel_lo) < w2_len) ? e0 : 0.f;
+      e1 = (i1 < rel_end || static_cast<unsigned>(i1 - rel_lo) < w2_len) ? e1 : 0.f;
+    }
+    acc = add2(acc, pack2(e0, e1));
+    packed[pi] = pack_bf16x2(e0, e1);
+  }
+  float x, y;
+  unpack2(acc, x, y);
+  return x + y;
 }
 
 // PAGED = false: q, k, v are contiguous [B, L, heads, 64] tensors (training, prefill, per-frame attention).
@@ -195,9 +277,25 @@ __global__ void __launch_bounds__(ATTN_THREADS, 1) attn_fwd_kernel(const __grid_
   const uint32_t tmem_slot = bar + 8u * (10 + 2 * ATTN_KV_STAGES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int bh = blockIdx.y;
+  // Non-paged launches put (batch, head) on grid.x and the query tiles on grid.y in order of DECREASING work: under the
+  // causal / DART masks a tile's key range grows with its position in its half, and CTAs are dispatched in grid order, so
+  // the long tiles start first and the short ones fill the tail (ncu: SMs idle 9 % of the launch in ascending order).
+  int bh, qt;
+  if constexpr (PAGED) { bh = blockIdx.y; qt = blockIdx.x; }
+  else {
+    bh = blockIdx.x;
+    const int nt = gridDim.y, i = blockIdx.y;
+#if ATTN_HEAVY_FIRST
+    if ((p.mask == ATTN_DART || p.mask == ATTN_DART_LISTED) && !(nt & 1) && (p.n_frames * p.hw) % ATTN_BM == 0) {
+      const int th = nt >> 1;
+      qt = (i & 1) * th + th - 1 - (i >> 1);           // clean and noised halves interleaved, each descending
+    } else qt = p.mask == ATTN_FULL ? i : nt - 1 - i;
+#else
+    qt = i;
+#endif
+  }
   const int bb = bh / p.heads, hh = bh - bb * p.heads;
-  const int q0 = blockIdx.x * ATTN_BM;
+  const int q0 = qt * ATTN_BM;
   int Lk = p.Lk;
   KvRange kr;
   if constexpr (PAGED) {
@@ -304,80 +402,53 @@ __global__ void __launch_bounds__(ATTN_THREADS, 1) attn_fwd_kernel(const __grid_
       __syncwarp();
     }
   } else {
-    // ---- softmax: warps (q, q+4, ...) share TMEM lane quarter q, each owns ATTN_PART_COLS key columns of the tile
+    // ---- softmax: warps (q, q+4, q+8, q+12) share TMEM lane quarter q, each owns 32 key columns of the tile
+    //      (measured against two groups of eight warps ping-ponging over alternate tiles: 718 vs 672 TFLOP/s at 131k tokens)
     const int sw = warp - 2;
     const int qw = warp & 3;
     const int part = sw >> 2;
-    const int half = part / (ATTN_PARTS / 2);          // which 64-column K-major sub-tile of P
     const int r = qw * 32 + lane;          // row of the tile == TMEM lane
     const int iq = q0 + r;
-    const int qf = iq / p.hw;
+    const RowWindows win = row_windows(p.mask, p.n_frames, p.hw, iq, Lk);
     const uint32_t lane_off = static_cast<uint32_t>(qw * 32) << 16;
     const float c1 = p.scale * 1.4426950408889634f, c2 = ATTN_SMAX * 1.4426950408889634f;
+    // this warp's 64 bytes of the row in P's K-major sub-tile (part >> 1), 16-byte chunks swizzled like TMA's SWIZZLE_128B
+    uint32_t p_off[4];
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch)
+      p_off[ch] = sP + (part >> 1) * ATTN_TILE_BYTES + r * 128 +
+                  ((static_cast<uint32_t>((part & 1) * 4 + ch) ^ static_cast<uint32_t>(r & 7)) << 4);
+    const uint32_t t_col = tS0 + lane_off + part * 32;
     float l = 0.f;
     for (int j = 0; j < n_kv; ++j) {
       const int b = j & 1;
       const int k0 = kr.tile(j) * ATTN_BN;
-      // does this row see EVERY key of the tile?  (then the per-element frame test is skipped)
-      bool all_vis;
-      {
-        const int kf_a = k0 / p.hw, kf_b = (k0 + ATTN_BN - 1) / p.hw;
-        all_vis = (k0 + ATTN_BN <= Lk);
-        if (p.mask == ATTN_CAUSAL) all_vis = all_vis && (kf_b <= qf);
-        else if (p.mask == ATTN_DART)
-          all_vis = all_vis && ((qf < p.n_frames) ? (kf_b <= qf) : ((kf_b < qf - p.n_frames) || (kf_a == qf && kf_b == qf)));
-        else if (p.mask == ATTN_DART_LISTED)
-          all_vis = all_vis && (qf < p.n_frames) && (kf_b <= qf);      // noised rows: per-element test (block list)
-      }
+      const bool all_vis = win.whole_tile(k0);     // does this row see EVERY key of the tile?
       mbar_wait(s_full(b), (j >> 1) & 1);
       tc_fence_after();
-      if (j >= 2) mbar_wait(p_empty(b), ((j >> 1) & 1) ^ 1);
-      const uint32_t sPb = sP + b * 2 * ATTN_TILE_BYTES + half * ATTN_TILE_BYTES;   // this half's K-major sub-tile
-      const int ik0 = k0 + part * ATTN_PART_COLS;
-      const uint32_t row_base = sPb + r * 128;
-      if constexpr (ATTN_PARTS == 2) {
-        float s0[32], s1[32];
-        tmem_ld32(tS0 + lane_off + b * ATTN_BN + part * 64, s0);
-        tmem_ld32(tS0 + lane_off + b * ATTN_BN + part * 64 + 32, s1);
-        tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(s_empty(b));          // S buffer may be overwritten by the MMA of tile j+2
-        uint32_t pk0[16], pk1[16];
-        if (all_vis) {
-          l += softmax_chunk<false>(s0, pk0, c1, c2, p.mask, p.n_frames, qf, ik0, Lk, p.hw, iq);
-          l += softmax_chunk<false>(s1, pk1, c1, c2, p.mask, p.n_frames, qf, ik0 + 32, Lk, p.hw, iq);
-        } else {
-          l += softmax_chunk<true>(s0, pk0, c1, c2, p.mask, p.n_frames, qf, ik0, Lk, p.hw, iq);
-          l += softmax_chunk<true>(s1, pk1, c1, c2, p.mask, p.n_frames, qf, ik0 + 32, Lk, p.hw, iq);
-        }
+      float s0[32];
+#if ATTN_DIAG == 2
 #pragma unroll
-        for (int ch = 0; ch < 8; ++ch) {
-          const uint32_t chunk = static_cast<uint32_t>(ch) ^ static_cast<uint32_t>(r & 7);
-          const uint32_t* src = ch < 4 ? &pk0[ch * 4] : &pk1[(ch - 4) * 4];
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row_base + (chunk << 4)), "r"(src[0]), "r"(src[1]),
-                       "r"(src[2]), "r"(src[3])
-                       : "memory");
-        }
-      } else {
-        float s0[32];
-        tmem_ld32(tS0 + lane_off + b * ATTN_BN + part * 32, s0);
-        tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(s_empty(b));
-        uint32_t pk0[16];
-        if (all_vis) l += softmax_chunk<false>(s0, pk0, c1, c2, p.mask, p.n_frames, qf, ik0, Lk, p.hw, iq);
-        else l += softmax_chunk<true>(s0, pk0, c1, c2, p.mask, p.n_frames, qf, ik0, Lk, p.hw, iq);
-        const int ch0 = (part & 1) * 4;                  // 16-byte chunks [ch0, ch0+4) of the 128-byte row
-#pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
-          const uint32_t chunk = static_cast<uint32_t>(ch0 + ch) ^ static_cast<uint32_t>(r & 7);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row_base + (chunk << 4)), "r"(pk0[ch * 4]),
-                       "r"(pk0[ch * 4 + 1]), "r"(pk0[ch * 4 + 2]), "r"(pk0[ch * 4 + 3])
-                       : "memory");
-        }
+      for (int i = 0; i < 32; ++i) s0[i] = __int_as_float(j + i);
+#else
+      tmem_ld32(t_col + b * ATTN_BN, s0);
+      tmem_ld_wait();
+#endif
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_empty(b));          // S buffer may be overwritten by the MMA of tile j+2
+      uint32_t pk0[16];
+      if (all_vis) l += softmax_chunk<false>(s0, pk0, c1, c2, 0, 0, 0);
+      else {
+        const int ik0 = k0 + part * 32;
+        l += softmax_chunk<true>(s0, pk0, c1, c2, win.w1_end - ik0, win.w2_lo - ik0, win.w2_hi - ik0);
       }
+      if (j >= 2) mbar_wait(p_empty(b), ((j >> 1) & 1) ^ 1);   // P(j-2) consumed by its PV MMA
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch)
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(p_off[ch] + b * 2 * ATTN_TILE_BYTES), "r"(pk0[ch * 4]),
+                     "r"(pk0[ch * 4 + 1]), "r"(pk0[ch * 4 + 2]), "r"(pk0[ch * 4 + 3])
+                     : "memory");
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full(b));
