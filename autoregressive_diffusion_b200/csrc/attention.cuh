@@ -129,7 +129,7 @@ __device__ __forceinline__ float poly_exp2(float x) {
 constexpr int ATTN_KV_STAGES = ATTN_KV_STAGES_N;
 constexpr int ATTN_TILE_BYTES = 128 * 128;  // [128 rows][64 bf16]
 constexpr int ATTN_SMEM_BYTES = 1024 + ATTN_TILE_BYTES /*Q*/ + ATTN_KV_STAGES * 2 * ATTN_TILE_BYTES /*K,V*/ +
-                                2 * 2 * ATTN_TILE_BYTES /*P x2*/ + 2048 /*row sums*/ + 256;
+                                2048 /*row sums*/ + 256;
 // four softmax warps per TMEM lane quarter (= per scheduler): with two the warps were latency-bound (MUFU + tcgen05.ld
 // round trips; 526 -> 628 TFLOP/s at 131k tokens going to four)
 #ifndef ATTN_DIAG
@@ -263,8 +263,7 @@ __global__ void __launch_bounds__(ATTN_THREADS, 1) attn_fwd_kernel(const __grid_
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sQ = base;
   const uint32_t sKV = sQ + ATTN_TILE_BYTES;                       // stage s: K at +s*32K, V at +s*32K+16K
-  const uint32_t sP = sKV + ATTN_KV_STAGES * 2 * ATTN_TILE_BYTES;  // buffer b: two 16 KB K-major sub-tiles
-  const uint32_t sL = sP + 2 * 2 * ATTN_TILE_BYTES;                // [ATTN_PARTS][128 rows] partial row sums
+  const uint32_t sL = sKV + ATTN_KV_STAGES * 2 * ATTN_TILE_BYTES;  // [ATTN_PARTS][128 rows] partial row sums
   const uint32_t bar = sL + 2048;
   const uint32_t q_full = bar;
   auto kv_full = [&](int s) { return bar + 8u * (1 + s); };
@@ -326,7 +325,11 @@ __global__ void __launch_bounds__(ATTN_THREADS, 1) attn_fwd_kernel(const __grid_
   tc_fence_after();
   uint32_t tmem;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem) : "r"(tmem_slot));
-  const uint32_t tS0 = tmem, tO = tmem + 256;  // S buffers at cols [0,128) and [128,256); O at [256,320)
+  // S buffers at cols [0,128) and [128,256); O at [256,320); P buffers (bf16 pairs, the A operand of the PV MMA) at
+  // [320,384) and [384,448).  P never touches shared memory: with P staged there the kernel was bound by shared-memory
+  // bandwidth (Q+K operand reads 32 KB, P+V reads 48 KB, P stores 32 KB, TMA fills 32 KB per tile at 128 B/clk ~ 1150 clk
+  // against 512 clk of tensor time; removing the exponentials altogether only reached 896 TFLOP/s).
+  const uint32_t tS0 = tmem, tO = tmem + 256, tP0 = tmem + 320;
 
   if (warp == 0) {
     // ---- TMA producer (warp-uniform loop, elected lane issues)
@@ -388,11 +391,9 @@ __global__ void __launch_bounds__(ATTN_THREADS, 1) attn_fwd_kernel(const __grid_
         tc_fence_after();
         if (elect_one()) {
           const uint64_t vd = vdesc0 + ((sKV + st * 2 * ATTN_TILE_BYTES + ATTN_TILE_BYTES) >> 4);
-          const uint64_t pd = kdesc0 + ((sP + b * 2 * ATTN_TILE_BYTES) >> 4);
 #pragma unroll
-          for (int kk = 0; kk < ATTN_BN / 16; ++kk)
-            umma_bf16_ss(tO, pd + (kk >> 2) * (ATTN_TILE_BYTES >> 4) + (kk & 3) * 2, vd + kk * (2048 >> 4), idesc_o,
-                         (j > 0) || (kk > 0));
+          for (int kk = 0; kk < ATTN_BN / 16; ++kk)     // 16 keys of P = 8 TMEM columns
+            umma_bf16_ts(tO, tP0 + b * 64 + kk * 8, vd + kk * (2048 >> 4), idesc_o, (j > 0) || (kk > 0));
           umma_commit(kv_empty(st));
           umma_commit(p_empty(b));
         }
@@ -412,12 +413,7 @@ __global__ void __launch_bounds__(ATTN_THREADS, 1) attn_fwd_kernel(const __grid_
     const RowWindows win = row_windows(p.mask, p.n_frames, p.hw, iq, Lk);
     const uint32_t lane_off = static_cast<uint32_t>(qw * 32) << 16;
     const float c1 = p.scale * 1.4426950408889634f, c2 = ATTN_SMAX * 1.4426950408889634f;
-    // this warp's 64 bytes of the row in P's K-major sub-tile (part >> 1), 16-byte chunks swizzled like TMA's SWIZZLE_128B
-    uint32_t p_off[4];
-#pragma unroll
-    for (int ch = 0; ch < 4; ++ch)
-      p_off[ch] = sP + (part >> 1) * ATTN_TILE_BYTES + r * 128 +
-                  ((static_cast<uint32_t>((part & 1) * 4 + ch) ^ static_cast<uint32_t>(r & 7)) << 4);
+    const uint32_t t_p = tP0 + lane_off + part * 16;   // this warp's 32 keys of P: 16 columns of bf16 pairs
     const uint32_t t_col = tS0 + lane_off + part * 32;
     float l = 0.f;
     for (int j = 0; j < n_kv; ++j) {
@@ -444,12 +440,9 @@ __global__ void __launch_bounds__(ATTN_THREADS, 1) attn_fwd_kernel(const __grid_
         l += softmax_chunk<true>(s0, pk0, c1, c2, win.w1_end - ik0, win.w2_lo - ik0, win.w2_hi - ik0);
       }
       if (j >= 2) mbar_wait(p_empty(b), ((j >> 1) & 1) ^ 1);   // P(j-2) consumed by its PV MMA
-#pragma unroll
-      for (int ch = 0; ch < 4; ++ch)
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(p_off[ch] + b * 2 * ATTN_TILE_BYTES), "r"(pk0[ch * 4]),
-                     "r"(pk0[ch * 4 + 1]), "r"(pk0[ch * 4 + 2]), "r"(pk0[ch * 4 + 3])
-                     : "memory");
-      fence_proxy_async_smem();
+      tmem_st16(t_p + b * 64, pk0);
+      tmem_st_wait();
+      tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full(b));
     }
