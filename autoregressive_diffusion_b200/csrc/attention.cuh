@@ -124,7 +124,7 @@ __device__ __forceinline__ float poly_exp2(float x) {
 #define ATTN_EXP_POLY(idx) (((idx) % 3) == 2)
 
 #ifndef ATTN_KV_STAGES_N
-#define ATTN_KV_STAGES_N 4
+#define ATTN_KV_STAGES_N 6
 #endif
 constexpr int ATTN_KV_STAGES = ATTN_KV_STAGES_N;
 constexpr int ATTN_TILE_BYTES = 128 * 128;  // [128 rows][64 bf16]
@@ -138,9 +138,13 @@ constexpr int ATTN_SMEM_BYTES = 1024 + ATTN_TILE_BYTES /*Q*/ + ATTN_KV_STAGES * 
 #ifndef ATTN_HEAVY_FIRST
 #define ATTN_HEAVY_FIRST 1
 #endif
+#ifndef ATTN_P_BUFS_N
+#define ATTN_P_BUFS_N 3
+#endif
+constexpr int ATTN_P_BUFS = ATTN_P_BUFS_N;
 constexpr int ATTN_SOFTMAX_WARPS = 16;
 constexpr int ATTN_PARTS = ATTN_SOFTMAX_WARPS / 4;
-constexpr int ATTN_THREADS = 64 + 32 * ATTN_SOFTMAX_WARPS;
+constexpr int ATTN_THREADS = 96 + 32 * ATTN_SOFTMAX_WARPS;   // TMA, S-MMA and PV-MMA warps + softmax warps
 
 // ---- packed fp32 pairs: one FFMA2 / FADD2 issue slot does two lanes' worth of work per thread (sm_100 fma.rn.f32x2)
 __device__ __forceinline__ uint64_t pack2(float a, float b) {
@@ -271,9 +275,9 @@ __global__ void __launch_bounds__(ATTN_THREADS, 1) attn_fwd_kernel(const __grid_
   auto s_full = [&](int b) { return bar + 8u * (1 + 2 * ATTN_KV_STAGES + b); };
   auto s_empty = [&](int b) { return bar + 8u * (3 + 2 * ATTN_KV_STAGES + b); };
   auto p_full = [&](int b) { return bar + 8u * (5 + 2 * ATTN_KV_STAGES + b); };
-  auto p_empty = [&](int b) { return bar + 8u * (7 + 2 * ATTN_KV_STAGES + b); };
-  const uint32_t o_full = bar + 8u * (9 + 2 * ATTN_KV_STAGES);
-  const uint32_t tmem_slot = bar + 8u * (10 + 2 * ATTN_KV_STAGES);
+  auto p_empty = [&](int b) { return bar + 8u * (8 + 2 * ATTN_KV_STAGES + b); };
+  const uint32_t o_full = bar + 8u * (11 + 2 * ATTN_KV_STAGES);
+  const uint32_t tmem_slot = bar + 8u * (12 + 2 * ATTN_KV_STAGES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // Non-paged launches put (batch, head) on grid.x and the query tiles on grid.y in order of DECREASING work: under the
@@ -313,8 +317,8 @@ __global__ void __launch_bounds__(ATTN_THREADS, 1) attn_fwd_kernel(const __grid_
     for (int s = 0; s < ATTN_KV_STAGES; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1); }
     for (int b = 0; b < 2; ++b) {
       mbar_init(s_full(b), 1); mbar_init(s_empty(b), ATTN_SOFTMAX_WARPS);
-      mbar_init(p_full(b), ATTN_SOFTMAX_WARPS); mbar_init(p_empty(b), 1);
     }
+    for (int b = 0; b < ATTN_P_BUFS; ++b) { mbar_init(p_full(b), ATTN_SOFTMAX_WARPS); mbar_init(p_empty(b), 1); }
     mbar_init(o_full, 1);
     fence_barrier_init();
     tma_prefetch_desc(&p.mapQ); tma_prefetch_desc(&p.mapK); tma_prefetch_desc(&p.mapV);
@@ -325,23 +329,21 @@ __global__ void __launch_bounds__(ATTN_THREADS, 1) attn_fwd_kernel(const __grid_
   tc_fence_after();
   uint32_t tmem;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem) : "r"(tmem_slot));
-  // S buffers at cols [0,128) and [128,256); O at [256,320); P buffers (bf16 pairs, the A operand of the PV MMA) at
-  // [320,384) and [384,448).  P never touches shared memory: with P staged there the kernel was bound by shared-memory
+  // S buffers at cols [0,128) and [128,256); O at [256,320); three P buffers (bf16 pairs, the A operand of the PV MMA)
+  // at [320,384), [384,448), [448,512).  P never touches shared memory: with P staged there the kernel was bound by shared-memory
   // bandwidth (Q+K operand reads 32 KB, P+V reads 48 KB, P stores 32 KB, TMA fills 32 KB per tile at 128 B/clk ~ 1150 clk
   // against 512 clk of tensor time; removing the exponentials altogether only reached 896 TFLOP/s).
   const uint32_t tS0 = tmem, tO = tmem + 256, tP0 = tmem + 320;
 
   if (warp == 0) {
-    // ---- TMA producer (warp-uniform loop, elected lane issues)
+    // ---- TMA producer: ONE elected thread runs the whole loop (no per-tile elect / reconvergence)
     if (elect_one()) {
       mbar_arrive_expect_tx(q_full, ATTN_TILE_BYTES);
       tma_load_4d(sQ, &p.mapQ, q_full, 0, q0, hh, bb);
-    }
-    __syncwarp();
-    for (int j = 0; j < n_kv; ++j) {
-      const int st = j % ATTN_KV_STAGES;
-      mbar_wait(kv_empty(st), ((j / ATTN_KV_STAGES) & 1) ^ 1);
-      if (elect_one()) {
+      int st = 0;
+      uint32_t ph = 1;                                   // kv_empty parity to wait for (first pass falls through)
+      for (int j = 0; j < n_kv; ++j) {
+        mbar_wait(kv_empty(st), ph);
         const uint32_t sK = sKV + st * 2 * ATTN_TILE_BYTES, sV = sK + ATTN_TILE_BYTES;
         mbar_arrive_expect_tx(kv_full(st), 2 * ATTN_TILE_BYTES);
         const int k0 = kr.tile(j) * ATTN_BN;
@@ -359,54 +361,65 @@ __global__ void __launch_bounds__(ATTN_THREADS, 1) attn_fwd_kernel(const __grid_
           tma_load_4d(sK, &p.mapK, kv_full(st), 0, k0, hh, bb);
           tma_load_4d(sV, &p.mapV, kv_full(st), 0, k0, hh, bb);
         }
+        if (++st == ATTN_KV_STAGES) { st = 0; ph ^= 1; }
       }
-      __syncwarp();
     }
+    __syncwarp();
   } else if (warp == 1) {
-    // ---- MMA issuer
-    if (n_kv > 0) {
+    // ---- S = Q K^T issuer (one elected thread).  S runs up to two tiles ahead of the softmax: S(j) only needs its K tile
+    //      and the S buffer (j & 1) drained by the softmax of tile j-2.  A separate warp issues the PV MMAs: with one
+    //      warp doing both, that warp was busy 70 % of the time (ncu source page: ~130 dependent instructions per tile)
+    //      and its latency sat in the S -> softmax -> PV round trip.
+    if (n_kv > 0 && elect_one()) {
       constexpr uint32_t idesc_s = make_idesc_bf16(128, ATTN_BN, 0, 0);
-      constexpr uint32_t idesc_o = make_idesc_bf16(128, ATTN_D, 0, 1);
-      const uint64_t kdesc0 = make_smem_desc(0, 16, 1024, SWZ_128B);               // K-major operands (Q, K, P)
-      const uint64_t vdesc0 = make_smem_desc(0, ATTN_TILE_BYTES, 1024, SWZ_128B);  // MN-major operand (V)
-      auto issue_s = [&](int j) {
-        const int st = j % ATTN_KV_STAGES, b = j & 1;
-        mbar_wait(kv_full(st), (j / ATTN_KV_STAGES) & 1);
+      const uint64_t kdesc0 = make_smem_desc(0, 16, 1024, SWZ_128B);               // K-major operands (Q, K)
+      const uint64_t qd = kdesc0 + (sQ >> 4);
+      uint64_t kd = kdesc0 + (sKV >> 4);
+      int st = 0;
+      uint32_t ph = 0;
+      mbar_wait(q_full, 0);
+      for (int j = 0; j < n_kv; ++j) {
+        const int b = j & 1;
+        mbar_wait(kv_full(st), ph);
         if (j >= 2) mbar_wait(s_empty(b), ((j >> 1) & 1) ^ 1);
         tc_fence_after();
-        if (elect_one()) {
-          const uint64_t qd = kdesc0 + (sQ >> 4), kd = kdesc0 + ((sKV + st * 2 * ATTN_TILE_BYTES) >> 4);
 #pragma unroll
-          for (int k = 0; k < ATTN_D / 16; ++k) umma_bf16_ss(tS0 + b * ATTN_BN, qd + 2 * k, kd + 2 * k, idesc_s, k > 0);
-          umma_commit(s_full(b));
-        }
-        __syncwarp();
-      };
-      mbar_wait(q_full, 0);
-      issue_s(0);
-      for (int j = 0; j < n_kv; ++j) {
-        if (j + 1 < n_kv) issue_s(j + 1);
-        const int st = j % ATTN_KV_STAGES, b = j & 1;
-        mbar_wait(p_full(b), (j >> 1) & 1);
-        tc_fence_after();
-        if (elect_one()) {
-          const uint64_t vd = vdesc0 + ((sKV + st * 2 * ATTN_TILE_BYTES + ATTN_TILE_BYTES) >> 4);
-#pragma unroll
-          for (int kk = 0; kk < ATTN_BN / 16; ++kk)     // 16 keys of P = 8 TMEM columns
-            umma_bf16_ts(tO, tP0 + b * 64 + kk * 8, vd + kk * (2048 >> 4), idesc_o, (j > 0) || (kk > 0));
-          umma_commit(kv_empty(st));
-          umma_commit(p_empty(b));
-        }
-        __syncwarp();
+        for (int k = 0; k < ATTN_D / 16; ++k) umma_bf16_ss(tS0 + b * ATTN_BN, qd + 2 * k, kd + 2 * k, idesc_s, k > 0);
+        umma_commit(s_full(b));
+        kd += (2 * ATTN_TILE_BYTES) >> 4;
+        if (++st == ATTN_KV_STAGES) { st = 0; ph ^= 1; kd = kdesc0 + (sKV >> 4); }
       }
-      if (elect_one()) umma_commit(o_full);
-      __syncwarp();
     }
+    __syncwarp();
+  } else if (warp == 2) {
+    // ---- O += P V issuer (one elected thread): P from tensor memory (TS mode), V from shared memory
+    if (n_kv > 0 && elect_one()) {
+      constexpr uint32_t idesc_o = make_idesc_bf16(128, ATTN_D, 0, 1);
+      const uint64_t vdesc0 = make_smem_desc(0, ATTN_TILE_BYTES, 1024, SWZ_128B);  // MN-major operand (V)
+      uint64_t vd = vdesc0 + ((sKV + ATTN_TILE_BYTES) >> 4);
+      int st = 0, pb = 0;
+      uint32_t ph = 0, pph = 0;
+      for (int j = 0; j < n_kv; ++j) {
+        mbar_wait(kv_full(st), ph);                      // V(j) landed (already true: S(j) needed the same barrier)
+        mbar_wait(p_full(pb), pph);
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < ATTN_BN / 16; ++kk)       // 16 keys of P = 8 TMEM columns
+          umma_bf16_ts(tO, tP0 + pb * 64 + kk * 8, vd + kk * (2048 >> 4), idesc_o, (j > 0) || (kk > 0));
+        umma_commit(kv_empty(st));                       // K(j) and V(j) are both consumed once this PV retires
+        umma_commit(p_empty(pb));
+        vd += (2 * ATTN_TILE_BYTES) >> 4;
+        if (++st == ATTN_KV_STAGES) { st = 0; ph ^= 1; vd = vdesc0 + ((sKV + ATTN_TILE_BYTES) >> 4); }
+        if (++pb == ATTN_P_BUFS) { pb = 0; pph ^= 1; }
+      }
+      umma_commit(o_full);
+    }
+    __syncwarp();
   } else {
     // ---- softmax: warps (q, q+4, q+8, q+12) share TMEM lane quarter q, each owns 32 key columns of the tile
     //      (measured against two groups of eight warps ping-ponging over alternate tiles: 718 vs 672 TFLOP/s at 131k tokens)
-    const int sw = warp - 2;
-    const int qw = warp & 3;
+    const int sw = warp - 3;
+    const int qw = warp & 3;               // the TMEM lane quarter a warp may access is fixed by its index
     const int part = sw >> 2;
     const int r = qw * 32 + lane;          // row of the tile == TMEM lane
     const int iq = q0 + r;
@@ -416,6 +429,8 @@ __global__ void __launch_bounds__(ATTN_THREADS, 1) attn_fwd_kernel(const __grid_
     const uint32_t t_p = tP0 + lane_off + part * 16;   // this warp's 32 keys of P: 16 columns of bf16 pairs
     const uint32_t t_col = tS0 + lane_off + part * 32;
     float l = 0.f;
+    int pb = 0;
+    uint32_t pph = 0;
     for (int j = 0; j < n_kv; ++j) {
       const int b = j & 1;
       const int k0 = kr.tile(j) * ATTN_BN;
@@ -439,12 +454,13 @@ __global__ void __launch_bounds__(ATTN_THREADS, 1) attn_fwd_kernel(const __grid_
         const int ik0 = k0 + part * 32;
         l += softmax_chunk<true>(s0, pk0, c1, c2, win.w1_end - ik0, win.w2_lo - ik0, win.w2_hi - ik0);
       }
-      if (j >= 2) mbar_wait(p_empty(b), ((j >> 1) & 1) ^ 1);   // P(j-2) consumed by its PV MMA
-      tmem_st16(t_p + b * 64, pk0);
+      mbar_wait(p_empty(pb), pph ^ 1);                 // the buffer's previous P consumed by its PV MMA (first pass falls through)
+      tmem_st16(t_p + pb * 64, pk0);
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(p_full(b));
+      if (lane == 0) mbar_arrive(p_full(pb));
+      if (++pb == ATTN_P_BUFS) { pb = 0; pph ^= 1; }
     }
     // ---- combine the parts' row sums, then O / l; parts 0 and 1 each write 32 of the 64 output channels
     asm volatile("st.shared.f32 [%0], %1;" ::"r"(sL + (part * 128 + r) * 4), "f"(l) : "memory");
