@@ -118,7 +118,7 @@ int attn_bwd(const void* q, const void* k, const void* v, const void* o, const v
   if (int r = make_qkv_map(&p.mapQ64, q, B, heads, Lq, 64)) return r;
   if (int r = make_qkv_map(&p.mapdO64, dout, B, heads, Lq, 64)) return r;
   p.BH = BH; p.heads = heads; p.Lq = Lq; p.Lk = Lk; p.hw = hw; p.n_frames = n_frames; p.mask = mask; p.scale = scale;
-  p.lse = lse; p.dsum = dsum;
+  p.lse = lse; p.ws = dsum;
   p.dq = static_cast<__nv_bfloat16*>(dq); p.dk = static_cast<__nv_bfloat16*>(dk); p.dv = static_cast<__nv_bfloat16*>(dv);
   static bool attr = false;
   if (!attr) {
@@ -127,11 +127,12 @@ int attn_bwd(const void* q, const void* k, const void* v, const void* o, const v
     if (e != cudaSuccess) { set_error("attn_bwd smem attr: %s", cudaGetErrorString(e)); return OB_ERR_CUDA; }
     attr = true;
   }
-  const long rows = static_cast<long>(BH) * Lq;
+  const int Lp = (Lq + ABW_BN - 1) / ABW_BN * ABW_BN;
+  const long rows = static_cast<long>(BH) * Lp;          // padded positions are zero-filled
   launch(attn_bwd_prep_kernel, (rows * 8 + 255) / 256, 256, 0, st, 1, static_cast<const __nv_bfloat16*>(o),
-                                                               static_cast<const __nv_bfloat16*>(dout), dsum, rows, Lq, heads);
-  launch(attn_bwd_dq_kernel, dim3((Lq + ABW_BM - 1) / ABW_BM, BH), ABW_THREADS, ABW_DQ_SMEM, st, 1, p);
-  launch(attn_bwd_dkv_kernel, dim3((Lk + ABW_BM - 1) / ABW_BM, BH), ABW_THREADS, ABW_DKV_SMEM, st, 1, p);
+         static_cast<const __nv_bfloat16*>(dout), lse, dsum, rows, Lq, Lp, heads, static_cast<long>(BH), scale);
+  launch(attn_bwd_dq_kernel, dim3(BH, (Lq + ABW_BM - 1) / ABW_BM), ABW_THREADS, ABW_DQ_SMEM, st, 1, p);
+  launch(attn_bwd_dkv_kernel, dim3(BH, (Lk + ABW_BM - 1) / ABW_BM), ABW_THREADS, ABW_DKV_SMEM, st, 1, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("attn_bwd launch: %s", cudaGetErrorString(e)); return OB_ERR_CUDA; }
   return OB_OK;

@@ -24,7 +24,7 @@ struct AttnBwdParams {
   int BH, heads, Lq, Lk, hw, n_frames, mask;
   float scale;
   const float* lse;  // [BH, Lq]
-  const float* dsum; // [BH, Lq]  D = rowsum(dO*O)
+  const float* ws;   // [2][BH][Lp] pre-scaled row statistics written by attn_bwd_prep_kernel (Lp = Lq rounded up to 64)
   __nv_bfloat16 *dq, *dk, *dv;
 };
 
@@ -93,116 +93,142 @@ __device__ __forceinline__ TileRanges visible_queries(const AttnBwdParams& p, in
   return r;
 }
 
-// D = rowsum(dO * O): one 8-lane group per (token, head) row of the [B, L, heads, 64] tensors; dsum is [B, heads, L].
+// Per-row statistics of the backward pass, pre-scaled so the hot loops use them as FMA addends:
+//   ws[0][bh][i] = -D[i] * scale   with D = rowsum(dO * O)          (dS = P * (dP*scale - D*scale))
+//   ws[1][bh][i] = -lse[i] * log2(e)                                 (P = exp2(S*scale*log2e - lse*log2e))
+// Rows are padded to Lp = ceil(L / 64) * 64 floats (padding zero-filled) so the dK/dV kernel can fetch the 64 values of a
+// streamed query tile with one aligned bulk copy.  One 8-lane group per (token, head) row of the [B, L, heads, 64] tensors.
 __global__ void __launch_bounds__(256) attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ o,
                                                             const __nv_bfloat16* __restrict__ dout,
-                                                            float* __restrict__ dsum, long rows, int L, int heads) {
+                                                            const float* __restrict__ lse, float* __restrict__ ws, long rows,
+                                                            int L, int Lp, int heads, long BH, float scale) {
   pdl_launch_dependents();
   pdl_wait();
   const long gid = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const long row = gid >> 3;
+  const long row = gid >> 3;                 // over [B, Lp, heads]: padded positions write zeros
   const int sub = static_cast<int>(gid & 7);
+  const bool valid = row < rows;
+  const long tok_p = (valid ? row : 0) / heads;
+  const int hh = static_cast<int>((valid ? row : 0) - tok_p * heads);
+  const long bb = tok_p / Lp;
+  const int i = static_cast<int>(tok_p - bb * Lp);
   float acc = 0.f;
-  if (row < rows) {
-    const uint4 a = *reinterpret_cast<const uint4*>(o + row * 64 + sub * 8);
-    const uint4 b = *reinterpret_cast<const uint4*>(dout + row * 64 + sub * 8);
+  if (valid && i < L) {
+    const long src = ((bb * L + i) * heads + hh) * 64 + sub * 8;
+    const uint4 a = *reinterpret_cast<const uint4*>(o + src);
+    const uint4 b = *reinterpret_cast<const uint4*>(dout + src);
     const uint32_t av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-      acc += __uint_as_float(av[i] << 16) * __uint_as_float(bv[i] << 16) +
-             __uint_as_float(av[i] & 0xffff0000u) * __uint_as_float(bv[i] & 0xffff0000u);
+    for (int t = 0; t < 4; ++t)
+      acc += __uint_as_float(av[t] << 16) * __uint_as_float(bv[t] << 16) +
+             __uint_as_float(av[t] & 0xffff0000u) * __uint_as_float(bv[t] & 0xffff0000u);
   }
   acc += __shfl_xor_sync(0xffffffffu, acc, 1);
   acc += __shfl_xor_sync(0xffffffffu, acc, 2);
   acc += __shfl_xor_sync(0xffffffffu, acc, 4);
-  if (row < rows && sub == 0) {
-    const long tok = row / heads;
-    const int hh = static_cast<int>(row - tok * heads);
-    const long bb = tok / L;
-    dsum[(bb * heads + hh) * L + (tok - bb * L)] = acc;
+  if (valid && sub == 0) {
+    const long bh = bb * heads + hh;
+    const long dst = bh * Lp + i;
+    ws[dst] = -acc * scale;
+    ws[BH * Lp + dst] = i < L ? -lse[bh * L + i] * 1.4426950408889634f : 0.f;
   }
 }
 
-constexpr int ABW_STAGES = 3;
+constexpr int ABW_STAGES = 6;
 constexpr int ABW_T128 = 128 * 128;  // [128 rows][64 bf16]
 constexpr int ABW_T64 = 64 * 128;    // [64 rows][64 bf16]
-constexpr int ABW_SM_WARPS = 8;      // two softmax warps per TMEM lane quarter, 32 streamed columns each
-constexpr int ABW_THREADS = 64 + 32 * ABW_SM_WARPS;
-constexpr int ABW_DQ_SMEM = 1024 + 2 * ABW_T128 + ABW_STAGES * 2 * ABW_T64 + 2 * ABW_T128 + 256;
-constexpr int ABW_DKV_SMEM = 1024 + 2 * ABW_T128 + ABW_STAGES * 2 * ABW_T64 + 4 * ABW_T128 + 2 * 2 * 64 * 4 + 256;
+constexpr int ABW_SM_WARPS = 16;     // four softmax warps per TMEM lane quarter, 16 streamed columns each
+constexpr int ABW_COLS = ABW_BN / (ABW_SM_WARPS / 4);
+constexpr int ABW_THREADS = 96 + 32 * ABW_SM_WARPS;   // TMA, two MMA issuers, softmax warps
+constexpr int ABW_DS_BUFS = 3;       // dS buffers of the dQ kernel in tensor memory
+constexpr int ABW_STAT_BYTES = 2 * ABW_BN * 4;        // per stage of the dK/dV kernel: -lse*log2e | -D*scale of 64 queries
+constexpr int ABW_DQ_SMEM = 1024 + 2 * ABW_T128 + ABW_STAGES * 2 * ABW_T64 + 512;
+constexpr int ABW_DKV_SMEM = 1024 + 2 * ABW_T128 + ABW_STAGES * (2 * ABW_T64 + ABW_STAT_BYTES) + 512;
 
-// store 32 packed bf16 columns [c*32, c*32+32) of row r into a K-major, 128B-swizzled [128][64] tile
-__device__ __forceinline__ void store_row_chunk(uint32_t tile_base, int r, int c, const uint32_t (&packed)[16]) {
-  const uint32_t row_base = tile_base + r * 128;
+// Visibility of the streamed index (keys for a query row, queries for a key row) as two windows [a1, b1) u [a2, b2):
+// every mask of this file has that shape per row, so tile and element tests are integer compares.
+struct Win2 {
+  int a1, b1, a2, b2;
+  __device__ __forceinline__ bool whole(int c0, int len) const {
+    return (c0 >= a1 && c0 + len <= b1) || (c0 >= a2 && c0 + len <= b2);
+  }
+};
+// keys seen by query iq
+__device__ __forceinline__ Win2 key_windows(int mask, int n_frames, int hw, int iq, int Lq, int Lk) {
+  Win2 w;
+  if (iq >= Lq) { w.a1 = w.b1 = w.a2 = w.b2 = 0; return w; }
+  const RowWindows r = row_windows(mask, n_frames, hw, iq, Lk);
+  w.a1 = 0; w.b1 = r.w1_end; w.a2 = r.w2_lo; w.b2 = max(r.w2_hi, r.w2_lo);
+  return w;
+}
+// queries that see key ik (the transpose of row_windows, including the ATTN_DART_LISTED block rule)
+__device__ __forceinline__ Win2 query_windows(int mask, int n_frames, int hw, int ik, int Lq, int Lk) {
+  Win2 w;
+  w.a1 = w.b1 = w.a2 = w.b2 = 0;
+  if (ik >= Lk) return w;
+  const int kf = ik / hw;
+  if (mask == ATTN_FULL) { w.b1 = Lq; return w; }
+  if (mask == ATTN_CAUSAL) { w.a1 = kf * hw; w.b1 = Lq; return w; }
+  const int n_hw = n_frames * hw;
+  if (kf < n_frames) {
+    w.a1 = kf * hw; w.b1 = n_hw;                       // clean queries of frames >= kf
+    w.a2 = (n_frames + kf + 1) * hw; w.b2 = 2 * n_hw;  // noised queries of strictly later frames
+    if (mask == ATTN_DART_LISTED) w.a2 = max(w.a2, n_hw + (((ik >> 7) + 1) << 7));
+  } else {
+    w.a1 = kf * hw; w.b1 = w.a1 + hw;                  // noised keys: their own frame's queries
+    if (mask == ATTN_DART_LISTED) { const int blk = (ik >> 7) << 7; w.a1 = max(w.a1, blk); w.b1 = min(w.b1, blk + 128); }
+  }
+  w.b1 = max(min(w.b1, Lq), w.a1);
+  w.b2 = max(min(w.b2, Lq), w.a2);
+  return w;
+}
+
+// One 16-element chunk of a row: P = exp2(s*c1 + nl), dS = P * (dp*scale + nd).  nl / nd are pairs (per column) so the
+// same code serves the dQ kernel (row statistics, broadcast) and the dK/dV kernel (column statistics).  MASKED: elements
+// outside the row's windows (given relative to the chunk's first column) are zeroed.
+template <bool MASKED, bool WANT_P, typename NL, typename ND>
+__device__ __forceinline__ void pds_chunk16(const float (&s)[16], const float (&dp)[16], uint32_t (&pk_p)[8],
+                                            uint32_t (&pk_ds)[8], float c1, float scale, NL nl, ND nd, int rel_a1,
+                                            unsigned len1, int rel_a2, unsigned len2) {
+  const uint64_t C1 = pack2(c1, c1), SC = pack2(scale, scale);
 #pragma unroll
-  for (int ch = 0; ch < 4; ++ch) {
-    const uint32_t chunk = static_cast<uint32_t>(c * 4 + ch) ^ static_cast<uint32_t>(r & 7);
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row_base + (chunk << 4)), "r"(packed[ch * 4]),
-                 "r"(packed[ch * 4 + 1]), "r"(packed[ch * 4 + 2]), "r"(packed[ch * 4 + 3])
-                 : "memory");
+  for (int pi = 0; pi < 8; ++pi) {
+    const uint64_t arg = fma2(pack2(s[2 * pi], s[2 * pi + 1]), C1, nl(pi));
+    float e0, e1;
+    if (ATTN_PAIR_POLY(pi)) poly_exp2_pair(arg, e0, e1);
+    else {
+      float a0, a1;
+      unpack2(arg, a0, a1);
+      e0 = fast_exp2(a0);
+      e1 = fast_exp2(a1);
+    }
+    if (MASKED) {
+      const int i0 = 2 * pi, i1 = 2 * pi + 1;
+      e0 = (static_cast<unsigned>(i0 - rel_a1) < len1 || static_cast<unsigned>(i0 - rel_a2) < len2) ? e0 : 0.f;
+      e1 = (static_cast<unsigned>(i1 - rel_a1) < len1 || static_cast<unsigned>(i1 - rel_a2) < len2) ? e1 : 0.f;
+    }
+    const uint64_t t = fma2(pack2(dp[2 * pi], dp[2 * pi + 1]), SC, nd(pi));
+    float d0, d1;
+    unpack2(mul2(pack2(e0, e1), t), d0, d1);
+    if (WANT_P) pk_p[pi] = pack_bf16x2(e0, e1);
+    pk_ds[pi] = pack_bf16x2(d0, d1);
   }
 }
 
-// dS = P * (dP - D) * scale for 32 (query row, key) pairs of one row; P = exp2(s*c1 - lse2).
-template <bool MASKED>
-__device__ __forceinline__ void ds_chunk_row(const float (&s)[32], const float (&dp)[32], uint32_t (&packed)[16], float c1,
-                                             float lse2, float dsum, float scale, int mask, int n_frames, int qf, int ik0,
-                                             int Lk, int hw, int iq) {
-  int kf = 0, rem = 0;
-  if (MASKED) { kf = ik0 / hw; rem = ik0 - kf * hw; }
-#pragma unroll
-  for (int i = 0; i < 32; i += 2) {
-    float ds[2];
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const float arg = s[i + u] * c1 - lse2;
-      float pr = ATTN_EXP_POLY(i + u) ? poly_exp2(arg) : fast_exp2(arg);
-      if (MASKED) {
-        bool ok = (ik0 + i + u < Lk) && frame_visible(mask, n_frames, qf, kf);
-        if (mask == ATTN_DART_LISTED) ok = ok && block_listed(n_frames * hw, iq, ik0 + i + u);
-        if (++rem == hw) { rem = 0; ++kf; }
-        pr = ok ? pr : 0.f;
-      }
-      ds[u] = pr * (dp[i + u] - dsum) * scale;
-    }
-    packed[i >> 1] = pack_bf16x2(ds[0], ds[1]);
+// heaviest query tiles first (same mapping as attn_fwd_kernel)
+__device__ __forceinline__ int abw_heavy_first(int mask, int n_frames, int hw, int nt, int i) {
+  if ((mask == ATTN_DART || mask == ATTN_DART_LISTED) && !(nt & 1) && (n_frames * hw) % ABW_BM == 0) {
+    const int th = nt >> 1;
+    return (i & 1) * th + th - 1 - (i >> 1);
   }
-}
-
-// Transposed flavour (one key row, 32 query columns with their own lse / D read from shared memory).
-template <bool MASKED>
-__device__ __forceinline__ void pds_chunk_col(const float (&s)[32], const float (&dp)[32], uint32_t (&pk_p)[16],
-                                              uint32_t (&pk_ds)[16], float c1, float scale, uint32_t stat_lse,
-                                              uint32_t stat_d, int mask, int n_frames, int kf, int iq0, int Lq, int hw, int ik) {
-  int qf = 0, rem = 0;
-  if (MASKED) { qf = iq0 / hw; rem = iq0 - qf * hw; }
-#pragma unroll
-  for (int i = 0; i < 32; i += 4) {
-    float l4[4], d4[4];
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(l4[0]), "=f"(l4[1]), "=f"(l4[2]), "=f"(l4[3]) : "r"(stat_lse + i * 4));
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(d4[0]), "=f"(d4[1]), "=f"(d4[2]), "=f"(d4[3]) : "r"(stat_d + i * 4));
-    float pv[4], ds[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const float arg = s[i + u] * c1 - l4[u];
-      float pr = ATTN_EXP_POLY(i + u) ? poly_exp2(arg) : fast_exp2(arg);
-      if (MASKED) {
-        bool ok = (iq0 + i + u < Lq) && frame_visible(mask, n_frames, qf, kf);
-        if (mask == ATTN_DART_LISTED) ok = ok && block_listed(n_frames * hw, iq0 + i + u, ik);
-        if (++rem == hw) { rem = 0; ++qf; }
-        pr = ok ? pr : 0.f;
-      }
-      pv[u] = pr;
-      ds[u] = pr * (dp[i + u] - d4[u]) * scale;
-    }
-    pk_p[i >> 1] = pack_bf16x2(pv[0], pv[1]);
-    pk_p[(i >> 1) + 1] = pack_bf16x2(pv[2], pv[3]);
-    pk_ds[i >> 1] = pack_bf16x2(ds[0], ds[1]);
-    pk_ds[(i >> 1) + 1] = pack_bf16x2(ds[2], ds[3]);
-  }
+  return mask == ATTN_FULL ? i : nt - 1 - i;
 }
 
 // ------------------------------------------------------------------------------------------------ dQ
+// Warp roles: 0 = TMA producer, 1 = S / dP MMA issuer, 2 = dQ MMA issuer (each ONE elected thread running its whole loop),
+// 3..18 = softmax warps.  dS goes from the softmax warps to the dQ MMA through tensor memory (TS mode: the A operand is
+// read from TMEM), not shared memory -- with dS staged in shared memory the kernel was bound by shared-memory bandwidth.
+// TMEM columns: S [0,64) [64,128); dP [128,192) [192,256); dQ [256,320); dS (bf16 pairs) 3 x 32 from 320.
 __global__ void __launch_bounds__(ABW_THREADS, 1) attn_bwd_dq_kernel(const __grid_constant__ AttnBwdParams p) {
   pdl_launch_dependents();
   pdl_wait();
@@ -210,29 +236,29 @@ __global__ void __launch_bounds__(ABW_THREADS, 1) attn_bwd_dq_kernel(const __gri
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sQ = base, sdO = sQ + ABW_T128;
   const uint32_t sKV = sdO + ABW_T128;                       // stage s: K at +s*16K, V at +s*16K+8K
-  const uint32_t sdS = sKV + ABW_STAGES * 2 * ABW_T64;       // 2 buffers of [128][64]
-  const uint32_t bar = sdS + 2 * ABW_T128;
+  const uint32_t bar = sKV + ABW_STAGES * 2 * ABW_T64;
   const uint32_t q_full = bar;
   auto kv_full = [&](int s) { return bar + 8u * (1 + s); };
-  auto kv_empty = [&](int s) { return bar + 8u * (4 + s); };
-  auto sdp_full = [&](int b) { return bar + 8u * (7 + b); };
-  auto sdp_empty = [&](int b) { return bar + 8u * (9 + b); };
-  auto ds_full = [&](int b) { return bar + 8u * (11 + b); };
-  auto ds_empty = [&](int b) { return bar + 8u * (13 + b); };
-  const uint32_t acc_full = bar + 8u * 15;
-  const uint32_t tmem_slot = bar + 8u * 16;
+  auto kv_empty = [&](int s) { return bar + 8u * (1 + ABW_STAGES + s); };
+  auto sdp_full = [&](int b) { return bar + 8u * (1 + 2 * ABW_STAGES + b); };
+  auto sdp_empty = [&](int b) { return bar + 8u * (3 + 2 * ABW_STAGES + b); };
+  auto ds_full = [&](int b) { return bar + 8u * (5 + 2 * ABW_STAGES + b); };
+  auto ds_empty = [&](int b) { return bar + 8u * (8 + 2 * ABW_STAGES + b); };
+  const uint32_t acc_full = bar + 8u * (11 + 2 * ABW_STAGES);
+  const uint32_t tmem_slot = bar + 8u * (12 + 2 * ABW_STAGES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int bh = blockIdx.y;
+  const int bh = blockIdx.x;
   const int bb = bh / p.heads, hh = bh - bb * p.heads;
-  const int q0 = blockIdx.x * ABW_BM;
+  const int q0 = abw_heavy_first(p.mask, p.n_frames, p.hw, gridDim.y, blockIdx.y) * ABW_BM;
   const TileRanges kr = visible_keys(p, q0, min(q0 + ABW_BM, p.Lq));
   const int n_kv = kr.count();
 
   if (threadIdx.x == 0) {
     mbar_init(q_full, 1);
     for (int s = 0; s < ABW_STAGES; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(sdp_full(b), 1); mbar_init(sdp_empty(b), ABW_SM_WARPS); mbar_init(ds_full(b), ABW_SM_WARPS); mbar_init(ds_empty(b), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(sdp_full(b), 1); mbar_init(sdp_empty(b), ABW_SM_WARPS); }
+    for (int b = 0; b < ABW_DS_BUFS; ++b) { mbar_init(ds_full(b), ABW_SM_WARPS); mbar_init(ds_empty(b), 1); }
     mbar_init(acc_full, 1);
     fence_barrier_init();
   }
@@ -242,130 +268,132 @@ __global__ void __launch_bounds__(ABW_THREADS, 1) attn_bwd_dq_kernel(const __gri
   tc_fence_after();
   uint32_t tmem;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem) : "r"(tmem_slot));
-  // S buffers: cols [0,64) [64,128); dP buffers: [128,192) [192,256); dQ: [256,320)
+  const uint32_t tS = tmem, tdP = tmem + 128, tdQ = tmem + 256, tdS = tmem + 320;
 
   if (warp == 0) {
     if (elect_one()) {
       mbar_arrive_expect_tx(q_full, 2 * ABW_T128);
       tma_load_4d(sQ, &p.mapQ128, q_full, 0, q0, hh, bb);
       tma_load_4d(sdO, &p.mapdO128, q_full, 0, q0, hh, bb);
-    }
-    __syncwarp();
-    for (int j = 0; j < n_kv; ++j) {
-      const int st = j % ABW_STAGES;
-      mbar_wait(kv_empty(st), ((j / ABW_STAGES) & 1) ^ 1);
-      if (elect_one()) {
+      int st = 0;
+      uint32_t ph = 1;
+      for (int j = 0; j < n_kv; ++j) {
+        mbar_wait(kv_empty(st), ph);
         const uint32_t sK = sKV + st * 2 * ABW_T64, sV = sK + ABW_T64;
         mbar_arrive_expect_tx(kv_full(st), 2 * ABW_T64);
         const int k0 = kr.tile(j) * ABW_BN;
         tma_load_4d(sK, &p.mapK64, kv_full(st), 0, k0, hh, bb);
         tma_load_4d(sV, &p.mapV64, kv_full(st), 0, k0, hh, bb);
+        if (++st == ABW_STAGES) { st = 0; ph ^= 1; }
       }
-      __syncwarp();
     }
+    __syncwarp();
   } else if (warp == 1) {
-    if (n_kv > 0) {
+    // ---- S = Q K^T and dP = dO V^T, up to two tiles ahead of the softmax
+    if (n_kv > 0 && elect_one()) {
       constexpr uint32_t idesc_s = make_idesc_bf16(128, ABW_BN, 0, 0);
-      constexpr uint32_t idesc_q = make_idesc_bf16(128, ATTN_D, 0, 1);
       const uint64_t kdesc0 = make_smem_desc(0, 16, 1024, SWZ_128B);
-      const uint64_t mdesc0 = make_smem_desc(0, ABW_T64, 1024, SWZ_128B);
-      auto issue_sdp = [&](int j) {
-        const int st = j % ABW_STAGES, b = j & 1;
-        mbar_wait(kv_full(st), (j / ABW_STAGES) & 1);
+      const uint64_t qd = kdesc0 + (sQ >> 4), dod = kdesc0 + (sdO >> 4);
+      int st = 0;
+      uint32_t ph = 0;
+      mbar_wait(q_full, 0);
+      for (int j = 0; j < n_kv; ++j) {
+        const int b = j & 1;
+        mbar_wait(kv_full(st), ph);
         if (j >= 2) mbar_wait(sdp_empty(b), ((j >> 1) & 1) ^ 1);
         tc_fence_after();
-        if (elect_one()) {
-          const uint32_t sK = sKV + st * 2 * ABW_T64, sV = sK + ABW_T64;
-          const uint64_t qd = kdesc0 + (sQ >> 4), dod = kdesc0 + (sdO >> 4), kd = kdesc0 + (sK >> 4), vd = kdesc0 + (sV >> 4);
+        const uint64_t kd = kdesc0 + ((sKV + st * 2 * ABW_T64) >> 4), vd = kd + (ABW_T64 >> 4);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16_ss(tmem + b * 64, qd + 2 * k, kd + 2 * k, idesc_s, k > 0);
+        for (int k = 0; k < 4; ++k) umma_bf16_ss(tS + b * 64, qd + 2 * k, kd + 2 * k, idesc_s, k > 0);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16_ss(tmem + 128 + b * 64, dod + 2 * k, vd + 2 * k, idesc_s, k > 0);
-          umma_commit(sdp_full(b));
-        }
-        __syncwarp();
-      };
-      mbar_wait(q_full, 0);
-      issue_sdp(0);
-      for (int j = 0; j < n_kv; ++j) {
-        if (j + 1 < n_kv) issue_sdp(j + 1);
-        const int st = j % ABW_STAGES, b = j & 1;
-        mbar_wait(ds_full(b), (j >> 1) & 1);
-        tc_fence_after();
-        if (elect_one()) {
-          const uint64_t dsd = kdesc0 + ((sdS + b * ABW_T128) >> 4);
-          const uint64_t kd = mdesc0 + ((sKV + st * 2 * ABW_T64) >> 4);
-#pragma unroll
-          for (int kk = 0; kk < 4; ++kk)   // dQ += dS[128 x 64 keys] * K[64 keys x 64]
-            umma_bf16_ss(tmem + 256, dsd + 2 * kk, kd + kk * (2048 >> 4), idesc_q, (j > 0) || (kk > 0));
-          umma_commit(kv_empty(st));
-          umma_commit(ds_empty(b));
-        }
-        __syncwarp();
+        for (int k = 0; k < 4; ++k) umma_bf16_ss(tdP + b * 64, dod + 2 * k, vd + 2 * k, idesc_s, k > 0);
+        umma_commit(sdp_full(b));
+        if (++st == ABW_STAGES) { st = 0; ph ^= 1; }
       }
-      if (elect_one()) umma_commit(acc_full);
-      __syncwarp();
     }
+    __syncwarp();
+  } else if (warp == 2) {
+    // ---- dQ += dS[128 x 64 keys] * K[64 keys x 64]: dS from tensor memory, K (MN-major) from shared memory
+    if (n_kv > 0 && elect_one()) {
+      constexpr uint32_t idesc_q = make_idesc_bf16(128, ATTN_D, 0, 1);
+      const uint64_t mdesc0 = make_smem_desc(0, ABW_T64, 1024, SWZ_128B);
+      int st = 0, db = 0;
+      uint32_t ph = 0, dph = 0;
+      for (int j = 0; j < n_kv; ++j) {
+        mbar_wait(kv_full(st), ph);
+        mbar_wait(ds_full(db), dph);
+        tc_fence_after();
+        const uint64_t kd = mdesc0 + ((sKV + st * 2 * ABW_T64) >> 4);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+          umma_bf16_ts(tdQ, tdS + db * 32 + kk * 8, kd + kk * (2048 >> 4), idesc_q, (j > 0) || (kk > 0));
+        umma_commit(kv_empty(st));       // S(j), dP(j) retired before the softmax produced dS(j): K and V are free
+        umma_commit(ds_empty(db));
+        if (++st == ABW_STAGES) { st = 0; ph ^= 1; }
+        if (++db == ABW_DS_BUFS) { db = 0; dph ^= 1; }
+      }
+      umma_commit(acc_full);
+    }
+    __syncwarp();
   } else {
     const int qw = warp & 3;
-    const int half = (warp - 2) >> 2;      // which 32 of the 64 streamed key columns this warp owns
+    const int part = (warp - 3) >> 2;      // which 16 of the 64 streamed key columns this warp owns
     const int r = qw * 32 + lane;
     const int iq = q0 + r;
-    const int qf = iq / p.hw;
     const uint32_t lane_off = static_cast<uint32_t>(qw * 32) << 16;
-    const float LOG2E = 1.4426950408889634f;
-    const float c1 = p.scale * LOG2E;
-    float lse2 = 0.f, dsum = 0.f;
+    const float c1 = p.scale * 1.4426950408889634f;
+    const int Lp = (p.Lq + ABW_BN - 1) / ABW_BN * ABW_BN;
+    float nlse2 = 0.f, ndsum = 0.f;
     if (iq < p.Lq) {
-      lse2 = p.lse[static_cast<long>(bh) * p.Lq + iq] * LOG2E;
-      dsum = p.dsum[static_cast<long>(bh) * p.Lq + iq];
+      ndsum = p.ws[static_cast<long>(bh) * Lp + iq];
+      nlse2 = p.ws[(static_cast<long>(p.BH) + bh) * Lp + iq];
     }
+    const uint64_t NL = pack2(nlse2, nlse2), ND = pack2(ndsum, ndsum);
+    const Win2 win = key_windows(p.mask, p.n_frames, p.hw, iq, p.Lq, p.Lk);
+    const uint32_t t_s = tS + lane_off + part * ABW_COLS, t_dp = tdP + lane_off + part * ABW_COLS;
+    const uint32_t t_ds = tdS + lane_off + part * (ABW_COLS / 2);
+    int db = 0;
+    uint32_t dph = 0;
     for (int j = 0; j < n_kv; ++j) {
       const int b = j & 1;
-      const int k0 = kr.tile(j) * ABW_BN;
+      const int ik0 = kr.tile(j) * ABW_BN + part * ABW_COLS;
+      const bool all_vis = win.whole(ik0, ABW_COLS);
       mbar_wait(sdp_full(b), (j >> 1) & 1);
       tc_fence_after();
-      if (j >= 2) mbar_wait(ds_empty(b), ((j >> 1) & 1) ^ 1);
-      float s[32], dp[32];
-      tmem_ld32(tmem + lane_off + b * 64 + half * 32, s);
-      tmem_ld32(tmem + lane_off + 128 + b * 64 + half * 32, dp);
+      float s[16], dp[16];
+      tmem_ld16(t_s + b * 64, s);
+      tmem_ld16(t_dp + b * 64, dp);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(sdp_empty(b));
-      uint32_t packed[16];
-      const int ik0 = k0 + half * 32;
-      bool all_vis = (iq < p.Lq) && (ik0 + 32 <= p.Lk);
-      {
-        const int kf_a = ik0 / p.hw, kf_b = (ik0 + 31) / p.hw;
-        if (p.mask == ATTN_CAUSAL) all_vis = all_vis && (kf_b <= qf);
-        else if (p.mask == ATTN_DART)
-          all_vis = all_vis && ((qf < p.n_frames) ? (kf_b <= qf) : ((kf_b < qf - p.n_frames) || (kf_a == qf && kf_b == qf)));
-        else if (p.mask == ATTN_DART_LISTED) all_vis = all_vis && (qf < p.n_frames) && (kf_b <= qf);
-      }
-      if (all_vis) ds_chunk_row<false>(s, dp, packed, c1, lse2, dsum, p.scale, p.mask, p.n_frames, qf, ik0, p.Lk, p.hw, iq);
-      else if (iq < p.Lq) ds_chunk_row<true>(s, dp, packed, c1, lse2, dsum, p.scale, p.mask, p.n_frames, qf, ik0, p.Lk, p.hw, iq);
-      else {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) packed[i] = 0u;
-      }
-      store_row_chunk(sdS + b * ABW_T128, r, half, packed);
-      fence_proxy_async_smem();
+      uint32_t pk_ds[8], unused[8];
+      auto nl = [&](int) { return NL; };
+      auto nd = [&](int) { return ND; };
+      if (all_vis) pds_chunk16<false, false>(s, dp, unused, pk_ds, c1, p.scale, nl, nd, 0, 0u, 0, 0u);
+      else
+        pds_chunk16<true, false>(s, dp, unused, pk_ds, c1, p.scale, nl, nd, win.a1 - ik0, static_cast<unsigned>(win.b1 - win.a1),
+                                 win.a2 - ik0, static_cast<unsigned>(win.b2 - win.a2));
+      mbar_wait(ds_empty(db), dph ^ 1);    // first pass falls through
+      tmem_st8(t_ds + db * 32, pk_ds);
+      tmem_st_wait();
+      tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(ds_full(b));
+      if (lane == 0) mbar_arrive(ds_full(db));
+      if (++db == ABW_DS_BUFS) { db = 0; dph ^= 1; }
     }
     if (n_kv > 0) { mbar_wait(acc_full, 0); tc_fence_after(); }
-    __nv_bfloat16* drow = p.dq + ((static_cast<long>(bb) * p.Lq + iq) * p.heads + hh) * ATTN_D + half * 32;
+    __nv_bfloat16* drow = p.dq + ((static_cast<long>(bb) * p.Lq + iq) * p.heads + hh) * ATTN_D + part * 16;
     {
-      float o[32];
-      if (n_kv > 0) { tmem_ld32(tmem + lane_off + 256 + half * 32, o); tmem_ld_wait(); }
+      float o[16];
+      if (n_kv > 0) { tmem_ld16(tdQ + lane_off + part * 16, o); tmem_ld_wait(); }
       else {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) o[i] = 0.f;
+        for (int i = 0; i < 16; ++i) o[i] = 0.f;
       }
       if (iq < p.Lq) {
 #pragma unroll
-        for (int i = 0; i < 32; i += 8)
+        for (int i = 0; i < 16; i += 8)
           *reinterpret_cast<uint4*>(drow + i) = make_uint4(pack_bf16x2(o[i], o[i + 1]), pack_bf16x2(o[i + 2], o[i + 3]),
                                                            pack_bf16x2(o[i + 4], o[i + 5]), pack_bf16x2(o[i + 6], o[i + 7]));
       }
@@ -377,6 +405,10 @@ __global__ void __launch_bounds__(ABW_THREADS, 1) attn_bwd_dq_kernel(const __gri
 }
 
 // ------------------------------------------------------------------------------------------------ dK, dV
+// Same warp roles; rows are keys, streamed columns are queries.  P^T and dS^T go to the dV / dK MMAs through tensor memory.
+// The 64 streamed queries' statistics (-lse*log2e, -D*scale) ride along with their Q / dO tiles as one bulk copy per stage.
+// TMEM columns: S^T [0,64) [64,128); dP^T [128,192) [192,256); dK [256,320); dV [320,384); P^T 2 x 32 from 384; dS^T 2 x 32
+// from 448.
 __global__ void __launch_bounds__(ABW_THREADS, 1) attn_bwd_dkv_kernel(const __grid_constant__ AttnBwdParams p) {
   pdl_launch_dependents();
   pdl_wait();
@@ -384,30 +416,33 @@ __global__ void __launch_bounds__(ABW_THREADS, 1) attn_bwd_dkv_kernel(const __gr
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sK = base, sV = sK + ABW_T128;
   const uint32_t sQdO = sV + ABW_T128;                       // stage s: Q at +s*16K, dO at +s*16K+8K
-  const uint32_t sP = sQdO + ABW_STAGES * 2 * ABW_T64;       // P^T buffers 0,1 then dS^T buffers 0,1, each [128][64]
-  const uint32_t sStat = sP + 4 * ABW_T128;                  // [2 buffers][lse(64) | D(64)] floats
-  const uint32_t bar = sStat + 2 * 2 * 64 * 4;
+  const uint32_t sStat = sQdO + ABW_STAGES * 2 * ABW_T64;    // stage s: [-lse*log2e (64) | -D*scale (64)] floats
+  const uint32_t bar = sStat + ABW_STAGES * ABW_STAT_BYTES;
   const uint32_t kv_full = bar;
   auto q_full = [&](int s) { return bar + 8u * (1 + s); };
-  auto q_empty = [&](int s) { return bar + 8u * (4 + s); };
-  auto sdp_full = [&](int b) { return bar + 8u * (7 + b); };
-  auto sdp_empty = [&](int b) { return bar + 8u * (9 + b); };
-  auto pds_full = [&](int b) { return bar + 8u * (11 + b); };
-  auto pds_empty = [&](int b) { return bar + 8u * (13 + b); };
-  const uint32_t acc_full = bar + 8u * 15;
-  const uint32_t tmem_slot = bar + 8u * 16;
+  auto q_empty = [&](int s) { return bar + 8u * (1 + ABW_STAGES + s); };
+  auto sdp_full = [&](int b) { return bar + 8u * (1 + 2 * ABW_STAGES + b); };
+  auto sdp_empty = [&](int b) { return bar + 8u * (3 + 2 * ABW_STAGES + b); };
+  auto pds_full = [&](int b) { return bar + 8u * (5 + 2 * ABW_STAGES + b); };
+  auto pds_empty = [&](int b) { return bar + 8u * (7 + 2 * ABW_STAGES + b); };
+  const uint32_t acc_full = bar + 8u * (9 + 2 * ABW_STAGES);
+  const uint32_t tmem_slot = bar + 8u * (10 + 2 * ABW_STAGES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int bh = blockIdx.y;
+  const int bh = blockIdx.x;
   const int bb = bh / p.heads, hh = bh - bb * p.heads;
-  const int k0 = blockIdx.x * ABW_BM;
+  const int k0 = blockIdx.y * ABW_BM;       // ascending key tiles already run heaviest first (clean keys, early frames)
   const TileRanges qr = visible_queries(p, k0, min(k0 + ABW_BM, p.Lk));
   const int n_q = qr.count();
+  const int Lp = (p.Lq + ABW_BN - 1) / ABW_BN * ABW_BN;
 
   if (threadIdx.x == 0) {
     mbar_init(kv_full, 1);
     for (int s = 0; s < ABW_STAGES; ++s) { mbar_init(q_full(s), 1); mbar_init(q_empty(s), 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(sdp_full(b), 1); mbar_init(sdp_empty(b), ABW_SM_WARPS); mbar_init(pds_full(b), ABW_SM_WARPS); mbar_init(pds_empty(b), 1); }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(sdp_full(b), 1); mbar_init(sdp_empty(b), ABW_SM_WARPS);
+      mbar_init(pds_full(b), ABW_SM_WARPS); mbar_init(pds_empty(b), 1);
+    }
     mbar_init(acc_full, 1);
     fence_barrier_init();
   }
@@ -417,146 +452,145 @@ __global__ void __launch_bounds__(ABW_THREADS, 1) attn_bwd_dkv_kernel(const __gr
   tc_fence_after();
   uint32_t tmem;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem) : "r"(tmem_slot));
-  // S^T buffers: cols [0,64) [64,128); dP^T: [128,192) [192,256); dK: [256,320); dV: [320,384)
+  const uint32_t tS = tmem, tdP = tmem + 128, tdK = tmem + 256, tdV = tmem + 320, tP = tmem + 384, tdS = tmem + 448;
 
   if (warp == 0) {
     if (elect_one()) {
       mbar_arrive_expect_tx(kv_full, 2 * ABW_T128);
       tma_load_4d(sK, &p.mapK128, kv_full, 0, k0, hh, bb);
       tma_load_4d(sV, &p.mapV128, kv_full, 0, k0, hh, bb);
-    }
-    __syncwarp();
-    for (int j = 0; j < n_q; ++j) {
-      const int st = j % ABW_STAGES;
-      mbar_wait(q_empty(st), ((j / ABW_STAGES) & 1) ^ 1);
-      if (elect_one()) {
-        const uint32_t sQ = sQdO + st * 2 * ABW_T64, sdO = sQ + ABW_T64;
-        mbar_arrive_expect_tx(q_full(st), 2 * ABW_T64);
+      const float* nd_row = p.ws + static_cast<long>(bh) * Lp;
+      const float* nl_row = p.ws + (static_cast<long>(p.BH) + bh) * Lp;
+      int st = 0;
+      uint32_t ph = 1;
+      for (int j = 0; j < n_q; ++j) {
+        mbar_wait(q_empty(st), ph);
+        const uint32_t sQ = sQdO + st * 2 * ABW_T64, sdO = sQ + ABW_T64, sS = sStat + st * ABW_STAT_BYTES;
+        mbar_arrive_expect_tx(q_full(st), 2 * ABW_T64 + ABW_STAT_BYTES);
         const int q0 = qr.tile(j) * ABW_BN;
         tma_load_4d(sQ, &p.mapQ64, q_full(st), 0, q0, hh, bb);
         tma_load_4d(sdO, &p.mapdO64, q_full(st), 0, q0, hh, bb);
+        bulk_load_1d(sS, nl_row + q0, ABW_BN * 4, q_full(st));
+        bulk_load_1d(sS + ABW_BN * 4, nd_row + q0, ABW_BN * 4, q_full(st));
+        if (++st == ABW_STAGES) { st = 0; ph ^= 1; }
       }
-      __syncwarp();
     }
+    __syncwarp();
   } else if (warp == 1) {
-    if (n_q > 0) {
+    // ---- S^T = K Q^T and dP^T = V dO^T
+    if (n_q > 0 && elect_one()) {
       constexpr uint32_t idesc_s = make_idesc_bf16(128, ABW_BN, 0, 0);
-      constexpr uint32_t idesc_a = make_idesc_bf16(128, ATTN_D, 0, 1);
       const uint64_t kdesc0 = make_smem_desc(0, 16, 1024, SWZ_128B);
-      const uint64_t mdesc0 = make_smem_desc(0, ABW_T64, 1024, SWZ_128B);
-      auto issue_sdp = [&](int j) {
-        const int st = j % ABW_STAGES, b = j & 1;
-        mbar_wait(q_full(st), (j / ABW_STAGES) & 1);
+      const uint64_t kd = kdesc0 + (sK >> 4), vd = kdesc0 + (sV >> 4);
+      int st = 0;
+      uint32_t ph = 0;
+      mbar_wait(kv_full, 0);
+      for (int j = 0; j < n_q; ++j) {
+        const int b = j & 1;
+        mbar_wait(q_full(st), ph);
         if (j >= 2) mbar_wait(sdp_empty(b), ((j >> 1) & 1) ^ 1);
         tc_fence_after();
-        if (elect_one()) {
-          const uint32_t sQ = sQdO + st * 2 * ABW_T64, sdO = sQ + ABW_T64;
-          const uint64_t kd = kdesc0 + (sK >> 4), vd = kdesc0 + (sV >> 4), qd = kdesc0 + (sQ >> 4), dod = kdesc0 + (sdO >> 4);
+        const uint64_t qd = kdesc0 + ((sQdO + st * 2 * ABW_T64) >> 4), dod = qd + (ABW_T64 >> 4);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16_ss(tmem + b * 64, kd + 2 * k, qd + 2 * k, idesc_s, k > 0);          // S^T = K Q^T
+        for (int k = 0; k < 4; ++k) umma_bf16_ss(tS + b * 64, kd + 2 * k, qd + 2 * k, idesc_s, k > 0);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16_ss(tmem + 128 + b * 64, vd + 2 * k, dod + 2 * k, idesc_s, k > 0);   // dP^T = V dO^T
-          umma_commit(sdp_full(b));
-        }
-        __syncwarp();
-      };
-      mbar_wait(kv_full, 0);
-      issue_sdp(0);
+        for (int k = 0; k < 4; ++k) umma_bf16_ss(tdP + b * 64, vd + 2 * k, dod + 2 * k, idesc_s, k > 0);
+        umma_commit(sdp_full(b));
+        if (++st == ABW_STAGES) { st = 0; ph ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 2) {
+    // ---- dV += P^T[128 keys x 64 q] * dO[64 q x 64];  dK += dS^T * Q   (A operands from tensor memory)
+    if (n_q > 0 && elect_one()) {
+      constexpr uint32_t idesc_a = make_idesc_bf16(128, ATTN_D, 0, 1);
+      const uint64_t mdesc0 = make_smem_desc(0, ABW_T64, 1024, SWZ_128B);
+      int st = 0;
+      uint32_t ph = 0;
       for (int j = 0; j < n_q; ++j) {
-        if (j + 1 < n_q) issue_sdp(j + 1);
-        const int st = j % ABW_STAGES, b = j & 1;
+        const int b = j & 1;
+        mbar_wait(q_full(st), ph);
         mbar_wait(pds_full(b), (j >> 1) & 1);
         tc_fence_after();
-        if (elect_one()) {
-          const uint32_t sQ = sQdO + st * 2 * ABW_T64, sdO = sQ + ABW_T64;
-          const uint64_t pd = kdesc0 + ((sP + b * ABW_T128) >> 4), dsd = kdesc0 + ((sP + (2 + b) * ABW_T128) >> 4);
-          const uint64_t dod = mdesc0 + (sdO >> 4), qd = mdesc0 + (sQ >> 4);
+        const uint64_t qd = mdesc0 + ((sQdO + st * 2 * ABW_T64) >> 4), dod = qd + (ABW_T64 >> 4);
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk)   // dV += P^T[128 keys x 64 q] * dO[64 q x 64]
-            umma_bf16_ss(tmem + 320, pd + 2 * kk, dod + kk * (2048 >> 4), idesc_a, (j > 0) || (kk > 0));
+        for (int kk = 0; kk < 4; ++kk)
+          umma_bf16_ts(tdV, tP + b * 32 + kk * 8, dod + kk * (2048 >> 4), idesc_a, (j > 0) || (kk > 0));
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk)   // dK += dS^T * Q
-            umma_bf16_ss(tmem + 256, dsd + 2 * kk, qd + kk * (2048 >> 4), idesc_a, (j > 0) || (kk > 0));
-          umma_commit(q_empty(st));
-          umma_commit(pds_empty(b));
-        }
-        __syncwarp();
+        for (int kk = 0; kk < 4; ++kk)
+          umma_bf16_ts(tdK, tdS + b * 32 + kk * 8, qd + kk * (2048 >> 4), idesc_a, (j > 0) || (kk > 0));
+        umma_commit(q_empty(st));
+        umma_commit(pds_empty(b));
+        if (++st == ABW_STAGES) { st = 0; ph ^= 1; }
       }
-      if (elect_one()) umma_commit(acc_full);
-      __syncwarp();
+      umma_commit(acc_full);
     }
+    __syncwarp();
   } else {
     const int qw = warp & 3;
-    const int half = (warp - 2) >> 2;     // which 32 of the 64 streamed query columns this warp owns
+    const int part = (warp - 3) >> 2;     // which 16 of the 64 streamed query columns this warp owns
     const int r = qw * 32 + lane;         // key row of the tile
-    const int tid = threadIdx.x - 64;     // 0..255 among the softmax threads
     const int ik = k0 + r;
-    const int kf = ik / p.hw;
     const uint32_t lane_off = static_cast<uint32_t>(qw * 32) << 16;
-    const float LOG2E = 1.4426950408889634f;
-    const float c1 = p.scale * LOG2E;
+    const float c1 = p.scale * 1.4426950408889634f;
+    const Win2 win = query_windows(p.mask, p.n_frames, p.hw, ik, p.Lq, p.Lk);
+    const uint32_t t_s = tS + lane_off + part * ABW_COLS, t_dp = tdP + lane_off + part * ABW_COLS;
+    const uint32_t t_p = tP + lane_off + part * (ABW_COLS / 2), t_ds = tdS + lane_off + part * (ABW_COLS / 2);
+    int st = 0;
+    uint32_t ph = 0;
     for (int j = 0; j < n_q; ++j) {
       const int b = j & 1;
-      const int q0 = qr.tile(j) * ABW_BN;
-      {  // stage this step's 64 (lse, D) pairs; the named barrier also orders reuse of the buffer (see header note)
-        if (tid < 128) {
-          const int i = tid & 63;
-          const long gi = static_cast<long>(bh) * p.Lq + q0 + i;
-          float v = 0.f;
-          if (q0 + i < p.Lq) v = (tid < 64) ? p.lse[gi] * LOG2E : p.dsum[gi];
-          asm volatile("st.shared.f32 [%0], %1;" ::"r"(sStat + (b * 128 + tid) * 4), "f"(v) : "memory");
-        }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-      }
+      const int iq0 = qr.tile(j) * ABW_BN + part * ABW_COLS;
+      const bool all_vis = win.whole(iq0, ABW_COLS);
+      mbar_wait(q_full(st), ph);           // this stage's statistics are visible (the S^T MMA needed the same barrier)
       mbar_wait(sdp_full(b), (j >> 1) & 1);
       tc_fence_after();
-      if (j >= 2) mbar_wait(pds_empty(b), ((j >> 1) & 1) ^ 1);
-      float s[32], dp[32];
-      tmem_ld32(tmem + lane_off + b * 64 + half * 32, s);
-      tmem_ld32(tmem + lane_off + 128 + b * 64 + half * 32, dp);
+      float s[16], dp[16];
+      tmem_ld16(t_s + b * 64, s);
+      tmem_ld16(t_dp + b * 64, dp);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(sdp_empty(b));
-      uint32_t pk_p[16], pk_ds[16];
-      const int iq0 = q0 + half * 32;
-      bool all_vis = (ik < p.Lk) && (iq0 + 32 <= p.Lq);
+      // this chunk's column statistics: 16 + 16 floats, the same for every lane (broadcast reads)
+      uint64_t nlv[8], ndv[8];
       {
-        const int qf_a = iq0 / p.hw, qf_b = (iq0 + 31) / p.hw, n = p.n_frames;
-        if (p.mask == ATTN_CAUSAL) all_vis = all_vis && (kf <= qf_a);
-        else if (p.mask == ATTN_DART) {
-          if (kf < n) all_vis = all_vis && ((qf_b < n && kf <= qf_a) || (qf_a >= n && kf < qf_a - n));
-          else all_vis = all_vis && (qf_a == kf && qf_b == kf);
-        } else if (p.mask == ATTN_DART_LISTED) {
-          all_vis = all_vis && (kf < n) && (qf_b < n) && (kf <= qf_a);   // clean x clean only; the rest is tested per element
+        const uint32_t a_l = sStat + st * ABW_STAT_BYTES + part * ABW_COLS * 4, a_d = a_l + ABW_BN * 4;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(nlv[2 * i]), "=l"(nlv[2 * i + 1]) : "r"(a_l + i * 16));
+          asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(ndv[2 * i]), "=l"(ndv[2 * i + 1]) : "r"(a_d + i * 16));
         }
       }
-      const uint32_t st_l = sStat + (b * 128 + half * 32) * 4, st_d = sStat + (b * 128 + 64 + half * 32) * 4;
-      if (all_vis) pds_chunk_col<false>(s, dp, pk_p, pk_ds, c1, p.scale, st_l, st_d, p.mask, p.n_frames, kf, iq0, p.Lq, p.hw, ik);
-      else if (ik < p.Lk) pds_chunk_col<true>(s, dp, pk_p, pk_ds, c1, p.scale, st_l, st_d, p.mask, p.n_frames, kf, iq0, p.Lq, p.hw, ik);
-      else {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) { pk_p[i] = 0u; pk_ds[i] = 0u; }
-      }
-      store_row_chunk(sP + b * ABW_T128, r, half, pk_p);
-      store_row_chunk(sP + (2 + b) * ABW_T128, r, half, pk_ds);
-      fence_proxy_async_smem();
+      uint32_t pk_p[8], pk_ds[8];
+      auto nl = [&](int pi) { return nlv[pi]; };
+      auto nd = [&](int pi) { return ndv[pi]; };
+      if (all_vis) pds_chunk16<false, true>(s, dp, pk_p, pk_ds, c1, p.scale, nl, nd, 0, 0u, 0, 0u);
+      else
+        pds_chunk16<true, true>(s, dp, pk_p, pk_ds, c1, p.scale, nl, nd, win.a1 - iq0, static_cast<unsigned>(win.b1 - win.a1),
+                                win.a2 - iq0, static_cast<unsigned>(win.b2 - win.a2));
+      if (j >= 2) mbar_wait(pds_empty(b), ((j >> 1) & 1) ^ 1);
+      tmem_st8(t_p + b * 32, pk_p);
+      tmem_st8(t_ds + b * 32, pk_ds);
+      tmem_st_wait();
+      tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(pds_full(b));
+      if (++st == ABW_STAGES) { st = 0; ph ^= 1; }
     }
     if (n_q > 0) { mbar_wait(acc_full, 0); tc_fence_after(); }
 #pragma unroll
     for (int which = 0; which < 2; ++which) {
-      __nv_bfloat16* drow = (which == 0 ? p.dk : p.dv) + ((static_cast<long>(bb) * p.Lk + ik) * p.heads + hh) * ATTN_D + half * 32;
-      float o[32];
-      if (n_q > 0) { tmem_ld32(tmem + lane_off + 256 + which * 64 + half * 32, o); tmem_ld_wait(); }
+      __nv_bfloat16* drow = (which == 0 ? p.dk : p.dv) + ((static_cast<long>(bb) * p.Lk + ik) * p.heads + hh) * ATTN_D + part * 16;
+      float o[16];
+      if (n_q > 0) { tmem_ld16((which == 0 ? tdK : tdV) + lane_off + part * 16, o); tmem_ld_wait(); }
       else {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) o[i] = 0.f;
+        for (int i = 0; i < 16; ++i) o[i] = 0.f;
       }
       if (ik < p.Lk) {
 #pragma unroll
-        for (int i = 0; i < 32; i += 8)
+        for (int i = 0; i < 16; i += 8)
           *reinterpret_cast<uint4*>(drow + i) = make_uint4(pack_bf16x2(o[i], o[i + 1]), pack_bf16x2(o[i + 2], o[i + 3]),
                                                            pack_bf16x2(o[i + 4], o[i + 5]), pack_bf16x2(o[i + 6], o[i + 7]));
       }
