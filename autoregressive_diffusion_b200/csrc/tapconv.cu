@@ -203,7 +203,9 @@ static void pick_tiling(int n_acc, int Cout, int Cin, int chunk, int taps, int m
   else {
     while (bn > 64) {
       const int tiles = m_tiles * ((Cout + bn - 1) / bn);
-      if (tiles * split_for(bn) >= 100) break;
+      // 96: the 768-channel 8x8 input gradient (16 x 6 tiles) stays on N=128 CTA pairs in one wave instead of 192 N=64
+      // tiles in two (140 -> ~75 us, the time of the 1024-channel layer with the same K)
+      if (tiles * split_for(bn) >= 96) break;
       bn >>= 1;
     }
   }

@@ -140,6 +140,9 @@ __device__ __forceinline__ long long global_ns() {
 }
 #define TAPCONV_STAMP(slot) \
   do { if (p.trace != nullptr && lane == 0) p.trace[(static_cast<long>(blockIdx.y) * gridDim.x + blockIdx.x) * 8 + (slot)] = global_ns(); } while (0)
+// inside a region that only one elected thread executes
+#define TAPCONV_STAMP1(slot) \
+  do { if (p.trace != nullptr) p.trace[(static_cast<long>(blockIdx.y) * gridDim.x + blockIdx.x) * 8 + (slot)] = global_ns(); } while (0)
 
 template <int CHUNK, int BN, bool BMN, bool PAIR>
 __global__ void __launch_bounds__(TAPCONV_THREADS, 1) tapconv_kernel(const __grid_constant__ TapConvParams p) {
@@ -234,7 +237,8 @@ __global__ void __launch_bounds__(TAPCONV_THREADS, 1) tapconv_kernel(const __gri
   pdl_wait();   // everything above overlapped the previous kernel's tail; global memory is touched only from here on
 
   if (warp == 0) {
-    // ===================== activation (A) TMA producer (warp-uniform loop, one elected lane issues) ============
+    // ===================== activation (A) TMA producer: ONE elected thread runs the whole loop ============
+    if (elect_one()) {
     int as = 0;
     uint32_t aph = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -244,26 +248,26 @@ __global__ void __launch_bounds__(TAPCONV_THREADS, 1) tapconv_kernel(const __gri
         const void* mapA = &p.mapA[col.src];
         for (int ck = ck_lo; ck < ck_hi; ++ck) {
           mbar_wait(a_empty(as), aph ^ 1);
-          if (elect_one()) {
-            if constexpr (PAIR) {
-              if (leader) mbar_arrive_expect_tx(a_full(as), 2 * col.n_a * p.a_tile_bytes);   // both CTAs' tiles
-              for (int i = 0; i < col.n_a; ++i)
-                tma_load_5d_pair(sA0 + as * p.a_slot_bytes + i * p.a_tile_bytes, mapA, a_full(as), ck * CHUNK,
-                                 tc.w0 + col.dx, tc.t0 + col.dt, tc.h0 - p.halo, tc.seq * col.seq_mul + i);
-            } else {
-              mbar_arrive_expect_tx(a_full(as), col.n_a * p.a_tile_bytes);
-              for (int i = 0; i < col.n_a; ++i)
-                tma_load_5d(sA0 + as * p.a_slot_bytes + i * p.a_tile_bytes, mapA, a_full(as), ck * CHUNK, tc.w0 + col.dx,
-                            tc.t0 + col.dt, tc.h0 - p.halo, tc.seq * col.seq_mul + i);
-            }
+          if constexpr (PAIR) {
+            if (leader) mbar_arrive_expect_tx(a_full(as), 2 * col.n_a * p.a_tile_bytes);   // both CTAs' tiles
+            for (int i = 0; i < col.n_a; ++i)
+              tma_load_5d_pair(sA0 + as * p.a_slot_bytes + i * p.a_tile_bytes, mapA, a_full(as), ck * CHUNK,
+                               tc.w0 + col.dx, tc.t0 + col.dt, tc.h0 - p.halo, tc.seq * col.seq_mul + i);
+          } else {
+            mbar_arrive_expect_tx(a_full(as), col.n_a * p.a_tile_bytes);
+            for (int i = 0; i < col.n_a; ++i)
+              tma_load_5d(sA0 + as * p.a_slot_bytes + i * p.a_tile_bytes, mapA, a_full(as), ck * CHUNK, tc.w0 + col.dx,
+                          tc.t0 + col.dt, tc.h0 - p.halo, tc.seq * col.seq_mul + i);
           }
-          __syncwarp();
           if (++as == p.a_slots) { as = 0; aph ^= 1; }
         }
       }
     }
+    }
+    __syncwarp();
   } else if (warp == 2) {
-    // ===================== weight (B) TMA producer: runs ahead independently of the A ring =====================
+    // ===================== weight (B) TMA producer (one elected thread): runs ahead independently of the A ring ======
+    if (elect_one()) {
     int bs = 0;
     uint32_t bph = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -273,41 +277,41 @@ __global__ void __launch_bounds__(TAPCONV_THREADS, 1) tapconv_kernel(const __gri
         for (int ck = ck_lo; ck < ck_hi; ++ck) {
           for (int d = 0; d < col.n_taps; ++d) {
             mbar_wait(b_empty(bs), bph ^ 1);
-            if (elect_one()) {
-              const uint32_t sB = sB0 + bs * B_STRIDE;
-              if constexpr (PAIR) {
-                // this CTA stages output channels [n0 + rank*BN/2, +BN/2) of the tile; the MMA reads both halves
-                if (leader) mbar_arrive_expect_tx(b_full(bs), Cfg::B_BYTES);
-                if constexpr (!BMN) {
-                  tma_load_2d_pair(sB, &p.mapB, b_full(bs), col.wtap[d] * p.Cin + ck * CHUNK, n0 + rank * (BN / 2));
-                } else {
-#pragma unroll
-                  for (int j = 0; j < BN / 2 / CHUNK; ++j)
-                    tma_load_2d_pair(sB + j * (CHUNK * Cfg::ROW_BYTES), &p.mapB, b_full(bs),
-                                     col.wtap[d] * p.Cout + n0 + rank * (BN / 2) + j * CHUNK, ck * CHUNK);
-                }
+            const uint32_t sB = sB0 + bs * B_STRIDE;
+            if constexpr (PAIR) {
+              // this CTA stages output channels [n0 + rank*BN/2, +BN/2) of the tile; the MMA reads both halves
+              if (leader) mbar_arrive_expect_tx(b_full(bs), Cfg::B_BYTES);
+              if constexpr (!BMN) {
+                tma_load_2d_pair(sB, &p.mapB, b_full(bs), col.wtap[d] * p.Cin + ck * CHUNK, n0 + rank * (BN / 2));
               } else {
-                mbar_arrive_expect_tx(b_full(bs), Cfg::B_BYTES);
-                if constexpr (!BMN) {
-                  tma_load_2d(sB, &p.mapB, b_full(bs), col.wtap[d] * p.Cin + ck * CHUNK, n0);
-                } else {
 #pragma unroll
-                  for (int j = 0; j < BN / CHUNK; ++j)
-                    tma_load_2d(sB + j * (CHUNK * Cfg::ROW_BYTES), &p.mapB, b_full(bs), col.wtap[d] * p.Cout + n0 + j * CHUNK,
-                                ck * CHUNK);
-                }
+                for (int j = 0; j < BN / 2 / CHUNK; ++j)
+                  tma_load_2d_pair(sB + j * (CHUNK * Cfg::ROW_BYTES), &p.mapB, b_full(bs),
+                                   col.wtap[d] * p.Cout + n0 + rank * (BN / 2) + j * CHUNK, ck * CHUNK);
+              }
+            } else {
+              mbar_arrive_expect_tx(b_full(bs), Cfg::B_BYTES);
+              if constexpr (!BMN) {
+                tma_load_2d(sB, &p.mapB, b_full(bs), col.wtap[d] * p.Cin + ck * CHUNK, n0);
+              } else {
+#pragma unroll
+                for (int j = 0; j < BN / CHUNK; ++j)
+                  tma_load_2d(sB + j * (CHUNK * Cfg::ROW_BYTES), &p.mapB, b_full(bs), col.wtap[d] * p.Cout + n0 + j * CHUNK,
+                              ck * CHUNK);
               }
             }
-            __syncwarp();
             if (++bs == p.b_slots) { bs = 0; bph ^= 1; }
           }
         }
       }
     }
+    }
+    __syncwarp();
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    // The whole warp walks the (warp-uniform) loop; one elected lane issues.  Descriptors differ only in their
-    // 14-bit start-address field, so they are formed by adding to a base descriptor.
+    // One elected thread runs the whole loop (no per-tap elect / reconvergence: measured on the attention kernels, the
+    // issuer's dependent instruction count per step is what limits how far it runs ahead).  Descriptors differ only in
+    // their 14-bit start-address field, so they are formed by adding to a base descriptor.
     constexpr uint32_t idesc = make_idesc_bf16(PAIR ? 256 : 128, BN, 0, BMN ? 1 : 0);
     const uint64_t adesc0 = make_smem_desc(0, 16, SBO, SWZ);
     const uint64_t bdesc0 = BMN ? make_smem_desc(0, CHUNK * Cfg::ROW_BYTES, SBO, SWZ) : make_smem_desc(0, 16, SBO, SWZ);
@@ -318,7 +322,7 @@ __global__ void __launch_bounds__(TAPCONV_THREADS, 1) tapconv_kernel(const __gri
     const int own_depth = mode == TMEM_DOUBLE ? 2 : 1;
     const int shr_depth = mode == TMEM_SINGLE ? 1 : 2;
     int drained = -1;   // epilogues of iterations <= drained are known complete
-    if (leader) {          // in pair mode the peer's MMA warp only owns its half of the TMEM allocation
+    if (leader && elect_one()) {   // in pair mode the peer's MMA warp only owns its half of the TMEM allocation
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int par = it & 1;
@@ -337,46 +341,42 @@ __global__ void __launch_bounds__(TAPCONV_THREADS, 1) tapconv_kernel(const __gri
         }
         for (int ck = ck_lo; ck < ck_hi; ++ck) {
           mbar_wait(a_full(as), aph);
-          if (it == 0 && ic == 0 && ck == ck_lo) TAPCONV_STAMP(1);   // first activation tile landed
+          if (it == 0 && ic == 0 && ck == ck_lo) TAPCONV_STAMP1(1);   // first activation tile landed
           const uint32_t sA = sA0 + as * p.a_slot_bytes;
           for (int d = 0; d < col.n_taps; ++d) {
             mbar_wait(b_full(bs), bph);
             tc_fence_after();
             const uint64_t bdesc = bdesc0 + ((sB0 + bs * B_STRIDE) >> 4);
-            if (elect_one()) {
 #pragma unroll
-              for (int i = 0; i < 2; ++i) {
-                if (i < col.n_a) {
-                  const int acc = col.acc + i;
-                  const uint32_t d_tmem = d_tmem0 + static_cast<uint32_t>(i * BN);
-                  const uint64_t adesc = adesc0 + ((sA + i * p.a_tile_bytes + d * dy_stride) >> 4);
-                  if constexpr (PAIR) {
-                    umma_bf16_ss_pair(d_tmem, adesc, bdesc, idesc, (started >> acc) & 1u);
+            for (int i = 0; i < 2; ++i) {
+              if (i < col.n_a) {
+                const int acc = col.acc + i;
+                const uint32_t d_tmem = d_tmem0 + static_cast<uint32_t>(i * BN);
+                const uint64_t adesc = adesc0 + ((sA + i * p.a_tile_bytes + d * dy_stride) >> 4);
+                if constexpr (PAIR) {
+                  umma_bf16_ss_pair(d_tmem, adesc, bdesc, idesc, (started >> acc) & 1u);
 #pragma unroll
-                    for (int k = 1; k < CHUNK / 16; ++k) umma_bf16_ss_pair(d_tmem, adesc + 2 * k, bdesc + B_KSTEP * k, idesc, 1u);
-                  } else {
-                    umma_bf16_ss(d_tmem, adesc, bdesc, idesc, (started >> acc) & 1u);
+                  for (int k = 1; k < CHUNK / 16; ++k) umma_bf16_ss_pair(d_tmem, adesc + 2 * k, bdesc + B_KSTEP * k, idesc, 1u);
+                } else {
+                  umma_bf16_ss(d_tmem, adesc, bdesc, idesc, (started >> acc) & 1u);
 #pragma unroll
-                    for (int k = 1; k < CHUNK / 16; ++k) umma_bf16_ss(d_tmem, adesc + 2 * k, bdesc + B_KSTEP * k, idesc, 1u);
-                  }
+                  for (int k = 1; k < CHUNK / 16; ++k) umma_bf16_ss(d_tmem, adesc + 2 * k, bdesc + B_KSTEP * k, idesc, 1u);
                 }
               }
-              if constexpr (PAIR) umma_commit_pair(b_empty(bs)); else umma_commit(b_empty(bs));  // frees the weight slot(s)
             }
-            __syncwarp();
+            if constexpr (PAIR) umma_commit_pair(b_empty(bs)); else umma_commit(b_empty(bs));  // frees the weight slot(s)
             started |= ((1u << col.n_a) - 1u) << col.acc;
             if (++bs == p.b_slots) { bs = 0; bph ^= 1; }
           }
-          if (elect_one()) { if constexpr (PAIR) umma_commit_pair(a_empty(as)); else umma_commit(a_empty(as)); }
-          __syncwarp();
+          if constexpr (PAIR) umma_commit_pair(a_empty(as)); else umma_commit(a_empty(as));
           if (++as == p.a_slots) { as = 0; aph ^= 1; }
         }
       }
-      if (elect_one()) { if constexpr (PAIR) umma_commit_pair(tmem_full(par)); else umma_commit(tmem_full(par)); }
-      __syncwarp();
+      if constexpr (PAIR) umma_commit_pair(tmem_full(par)); else umma_commit(tmem_full(par));
     }
-    TAPCONV_STAMP(2);   // all MMAs issued
+    TAPCONV_STAMP1(2);   // all MMAs issued
     }
+    __syncwarp();
   } else {
     // ===================== epilogue (warps 3..6) =====================
     constexpr int CW = Cfg::CW;
