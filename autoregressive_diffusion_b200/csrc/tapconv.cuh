@@ -32,7 +32,14 @@
 namespace ob {
 
 constexpr int TAPCONV_MAX_COLS = 12;
-constexpr int TAPCONV_THREADS = 224;   // warp0: activation TMA, warp1: MMA, warp2: weight TMA, warps 3..6: epilogue
+#ifndef TAPCONV_EPI_WARPS_N
+#define TAPCONV_EPI_WARPS_N 8
+#endif
+// warp0: activation TMA, warp1: MMA, warp2: weight TMA, then the epilogue warps: one (4 warps) or two (8 warps) per TMEM lane
+// quarter; with two, each takes half of the tile's columns -- the epilogue is a fixed, fully exposed cost of every
+// single-wave launch (5-9 us of a 30-55 us layer: profiles/r02_tapconv_phase_trace.txt)
+constexpr int TAPCONV_EPI_WARPS = TAPCONV_EPI_WARPS_N;
+constexpr int TAPCONV_THREADS = 96 + 32 * TAPCONV_EPI_WARPS;
 constexpr int TAPCONV_MAX_A_SLOTS = 4;
 
 enum : int { EPI_PLAIN = 0, EPI_GATED = 1 };
@@ -217,7 +224,7 @@ __global__ void __launch_bounds__(TAPCONV_THREADS, 1) tapconv_kernel(const __gri
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.a_slots; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
     for (int s = 0; s < p.b_slots; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tmem_full(s), 1); mbar_init(tmem_empty(s), PAIR ? 8 : 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tmem_full(s), 1); mbar_init(tmem_empty(s), (PAIR ? 2 : 1) * TAPCONV_EPI_WARPS); }
     fence_barrier_init();
     tma_prefetch_desc(&p.mapA[0]);
     tma_prefetch_desc(&p.mapA[1]);
@@ -378,8 +385,12 @@ __global__ void __launch_bounds__(TAPCONV_THREADS, 1) tapconv_kernel(const __gri
     }
     __syncwarp();
   } else {
-    // ===================== epilogue (warps 3..6) =====================
+    // ===================== epilogue (warps 3..) =====================
     constexpr int CW = Cfg::CW;
+    constexpr int NCH = BN / CW;                                       // column chunks of the tile
+    constexpr int CH_PER = (NCH + TAPCONV_EPI_WARPS / 4 - 1) / (TAPCONV_EPI_WARPS / 4);
+    const int c_lo = ((warp - 3) >> 2) * CH_PER;                       // this warp's chunks [c_lo, c_hi)
+    const int c_hi = c_lo + CH_PER < NCH ? c_lo + CH_PER : NCH;
     const int q = warp & 3;  // TMEM lane quarter this warp may read
     const int m = q * 32 + lane;
     const int hh = m / (p.bt * p.bw);        // tile rows are ordered (hh, tt, ww)
@@ -404,7 +415,7 @@ __global__ void __launch_bounds__(TAPCONV_THREADS, 1) tapconv_kernel(const __gri
         // cluster split-K: park the raw partial accumulators, column-major ([acc][column][row], rows adjacent: conflict-free
         // writes here and coalesced distributed-shared-memory reads in the reduction below), in this CTA's shared memory
         for (int a = 0; a < n_acc; ++a)
-          for (int c = 0; c < BN / CW; ++c) {
+          for (int c = c_lo; c < c_hi; ++c) {
             float v[CW];
             if constexpr (CW == 32) tmem_ld32(lane_base + acc_col(a, par) + c * CW, v);
             else tmem_ld16(lane_base + acc_col(a, par) + c * CW, v);
@@ -419,7 +430,7 @@ __global__ void __launch_bounds__(TAPCONV_THREADS, 1) tapconv_kernel(const __gri
         for (int a = 0; a < n_acc; ++a) {
           // own accumulators: row = (set a, pixel); shared accumulator: stored after the n_out own sets
           float* dst_row = p.split_ws + (static_cast<long>(a) * rows_per_set + pix) * p.Cout;
-          for (int c = 0; c < BN / CW; ++c) {
+          for (int c = c_lo; c < c_hi; ++c) {
             float v[CW];
             if constexpr (CW == 32) tmem_ld32(lane_base + acc_col(a, par) + c * CW, v);
             else tmem_ld16(lane_base + acc_col(a, par) + c * CW, v);
@@ -441,7 +452,7 @@ __global__ void __launch_bounds__(TAPCONV_THREADS, 1) tapconv_kernel(const __gri
         float al = 1.f, be = 0.f;
         if (p.epi == EPI_GATED && row_ok) { al = p.alpha[frame]; be = p.beta[frame]; }
         const long row_off = ((frame * p.H + h) * p.W + w) * static_cast<long>(p.Cout);
-        for (int c = 0; c < BN / CW; ++c) {
+        for (int c = c_lo; c < c_hi; ++c) {
           float own[CW], shr[CW];
           if constexpr (CW == 32) tmem_ld32(lane_base + acc_col(o, par) + c * CW, own);
           else tmem_ld16(lane_base + acc_col(o, par) + c * CW, own);
@@ -450,7 +461,7 @@ __global__ void __launch_bounds__(TAPCONV_THREADS, 1) tapconv_kernel(const __gri
             else tmem_ld16(lane_base + acc_col(p.n_out, par) + c * CW, shr);
           }
           tmem_ld_wait();
-          if (o == p.n_out - 1 && c == BN / CW - 1) {
+          if (o == p.n_out - 1 && c == c_hi - 1) {
             // last TMEM read of this tile: hand the accumulators back to the MMA issuer before the stores go out
             tc_fence_before();
             __syncwarp();
@@ -572,7 +583,7 @@ __global__ void __launch_bounds__(TAPCONV_THREADS, 1) tapconv_kernel(const __gri
           }
         }
       }
-      if (p.ksplit > 1) {
+      if (p.ksplit > 1 || c_lo >= c_hi) {     // (a warp without columns -- one-chunk tiles -- only hands the accumulators back)
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
@@ -592,7 +603,7 @@ __global__ void __launch_bounds__(TAPCONV_THREADS, 1) tapconv_kernel(const __gri
       // its 128 epilogue threads owns one row and BN/ks columns, sums the ks partial values of every accumulator straight
       // out of the peers' shared memory and applies the ordinary output stage (gate combine, bf16 store, fp16 difference).
       cluster_sync_all();                       // every CTA's partials are staged and visible cluster-wide
-      if (warp >= 3) {
+      if (warp >= 3 && warp < 7) {
         const int ks = p.ksplit, rows_per = 128 / ks, cols_per = BN / ks;
         const int t128 = threadIdx.x - 96;
         const int m = static_cast<int>(blockIdx.y) * rows_per + t128 % rows_per;
