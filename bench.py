@@ -286,6 +286,9 @@ def secondary_records(trainer, peak_tf, peak_gbs):
         rows = [bench_attention.run(n, hw, reps=3) for n, hw in ((64, 64), (128, 256), (256, 256))]
         for r in rows:
             r["fwd_frac_of_bf16_burst"] = r["fwd_tflops_sparse"] / 1629.2
+            # the two backward kernels recompute S and dP (7 GEMMs executed, 5 counted in bwd_tflops_sparse)
+            r["bwd_tflops_executed"] = r["bwd_tflops_sparse"] * 7.0 / 5.0
+            r["bwd_frac_of_bf16_burst_executed"] = r["bwd_tflops_executed"] / 1629.2
         out["config4_attention_microbench"] = {"what": "DART-masked VideoAttention kernel, 4 heads x 64, fwd and bwd, TFLOP/s on the VISITED "
                                                        "(sparse) FLOPs; dense-equivalent = what a mask-everything kernel would need", "rows": rows}
     except Exception as e:  # noqa: BLE001
