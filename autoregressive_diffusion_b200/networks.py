@@ -124,6 +124,7 @@ class UNet(BetterModule):
         cnoise = model_channels * channel_mult_noise if channel_mult_noise is not None else cblock[0]
         cemb = model_channels * channel_mult_emb if channel_mult_emb is not None else max(cblock)
         self.label_balance, self.concat_balance = label_balance, concat_balance
+        self.boundary_hook = None       # train.Trainer: called (as a tensor hook) when the backward pass leaves the decoder
         self.out_res = Gating()
         self.out_gain = nn.Parameter(torch.zeros([]))
         self.emb_fourier_sigma = MPFourier(cnoise)
@@ -204,6 +205,9 @@ class UNet(BetterModule):
             x, cache['enc', name] = block(x, emb, batch_size, c_noise, cache=cache.get(('enc', name), None),
                                           update_cache=update_cache, just_2d=just_2d, **kw)
             skips.append(x)
+        # the encoder's output: its gradient is complete exactly when every decoder block has run its backward
+        if self.boundary_hook is not None and torch.is_grad_enabled() and x.requires_grad:
+            x.register_hook(self.boundary_hook)
         for name, block in self.dec.items():
             if 'block' in name:
                 x = mp_cat(x, skips.pop(), t=self.concat_balance)

@@ -78,18 +78,26 @@ class GradientBuckets:
     bucket by bucket by the fused optimizer (FusedAdamWEMA.step_with_all_reduce), which folds the 1/world of the mean
     into its update."""
 
-    def __init__(self, params, bucket_bytes=None):
+    def __init__(self, params, bucket_bytes=None, early=()):
+        """`early`: parameters whose gradients are complete well before the backward pass ends (the decoder's conv weights
+        and gates: everything upstream of them in the backward order).  They are laid out as the TAIL of the flat buffer
+        in buckets of their own, so their all-reduce can start while the rest of the backward pass is still running
+        (FusedAdamWEMA.step_with_all_reduce(early_event=...))."""
         if bucket_bytes is None:
             bucket_bytes = int(os.environ.get("ONIRIS_BUCKET_MB", "128")) << 20
         self.params = [p for p in params if p.requires_grad]
+        self.early_ids = {id(p) for p in early}
         self.bucket_elems = max(1, bucket_bytes // 4)
         self.flat = None
         self.buckets = None
+        self.n_late_buckets = 0          # buckets[:n_late_buckets] hold the late gradients, the rest the early ones
         self.live = None
         self.stream = torch.cuda.Stream() if torch.cuda.is_available() else None
 
     def flatten(self):
         live = [p for p in self.params if p.grad is not None]
+        live = [p for p in live if id(p) not in self.early_ids] + [p for p in live if id(p) in self.early_ids]
+        late_total = sum(_pad64(p.numel()) for p in live if id(p) not in self.early_ids)
         total = sum(_pad64(p.numel()) for p in live)
         self.flat = torch.zeros(total, dtype=torch.float32, device=live[0].device)
         off = 0
@@ -100,7 +108,9 @@ class GradientBuckets:
             off += _pad64(p.numel())
         self.live = live
         self._live_ids = {id(p) for p in live}
-        self.buckets = [self.flat[i:i + self.bucket_elems] for i in range(0, total, self.bucket_elems)]
+        self.buckets = [self.flat[i:min(i + self.bucket_elems, late_total)] for i in range(0, late_total, self.bucket_elems)]
+        self.n_late_buckets = len(self.buckets)
+        self.buckets += [self.flat[i:min(i + self.bucket_elems, total)] for i in range(late_total, total, self.bucket_elems)]
 
     def check_no_late_gradients(self):
         """A parameter that first receives a gradient AFTER the flat buffers were laid out would be silently left out of
@@ -235,34 +245,49 @@ class FusedAdamWEMA:
             self._grad_sumsq()
         self.update_range()
 
-    def step_with_all_reduce(self):
+    def step_with_all_reduce(self, early_event=None):
         """Data-parallel optimizer step: the gradient SUM over ranks runs bucket by bucket on the communication stream
         while the buckets already reduced are being updated here (the mean's 1/world is folded into the update), so the
         all-reduce and the HBM-bound update overlap instead of running back to back (cs_train.py:108-124 does
         all-reduce, then step, then EMA).  With gradient clipping the norm of the complete mean is needed first, so the
-        update waits for the whole reduction."""
+        update waits for the whole reduction.
+
+        `early_event`: recorded (by the backward pass that is still running on the current stream, or by the CUDA graph
+        just launched on it) once the gradients of GradientBuckets' early group are final: their buckets are reduced
+        behind that event, concurrently with the rest of the backward pass; only the late buckets wait for its end."""
         world = dist.get_world_size()
         self.begin_step()
         bk = self.buckets
         main = torch.cuda.current_stream()
+        n_late = bk.n_late_buckets if early_event is not None else len(bk.buckets)
+        events = [None] * len(bk.buckets)
+
+        def reduce(i):
+            dist.all_reduce(bk.buckets[i])
+            events[i] = torch.cuda.Event()
+            events[i].record(bk.stream)
+
+        if n_late < len(bk.buckets):
+            bk.stream.wait_event(early_event)
+            with torch.cuda.stream(bk.stream):
+                for i in range(n_late, len(bk.buckets)):
+                    reduce(i)
         bk.stream.wait_stream(main)
-        events = []
         with torch.cuda.stream(bk.stream):
-            for b in bk.buckets:
-                dist.all_reduce(b)
-                ev = torch.cuda.Event()
-                ev.record(bk.stream)
-                events.append(ev)
+            for i in range(n_late):
+                reduce(i)
         if self.max_grad_norm > 0:
-            main.wait_event(events[-1])
+            main.wait_stream(bk.stream)
             self._grad_sumsq()
             self.update_range(0, None, 1.0 / world)
             return
-        lo = 0
-        for b, ev in zip(bk.buckets, events):
-            main.wait_event(ev)
-            self.update_range(lo, lo + b.numel(), 1.0 / world)
-            lo += b.numel()
+        lo = [0]
+        for b in bk.buckets:
+            lo.append(lo[-1] + b.numel())
+        order = list(range(n_late, len(bk.buckets))) + list(range(n_late))     # the order the reductions complete in
+        for i in order:
+            main.wait_event(events[i])
+            self.update_range(lo[i], lo[i + 1], 1.0 / world)
 
     # ------------------------------------------------------------------ checkpointing (cs_train.py:153-159, :85-93)
     def state_dict(self):
@@ -347,7 +372,17 @@ class Trainer:
         self.all_params = list(self.precond.parameters())
         self.params = [p for p in self.all_params if p.requires_grad]
         self.accum = accumulation_steps
-        self.buckets = GradientBuckets(self.params)
+        # gradients that are final once the backward pass leaves the decoder (70 % of the CS UNet): decoder / output conv
+        # weights and gates.  The embedding linears are excluded: their gradient comes from the ONE batched embedding op,
+        # whose backward runs last.  Only with this package's UNet (it announces the boundary, networks.UNet.boundary_hook).
+        early = []
+        if isinstance(self.unet, UNet) and self.device.type == "cuda" and os.environ.get("ONIRIS_NO_EARLY_REDUCE", "0") != "1":
+            early = [p for n, p in self.unet.named_parameters()
+                     if (n.startswith("dec.") or n.startswith("out_conv.")) and "emb" not in n and p.requires_grad]
+            self.unet.boundary_hook = self._decoder_backward_done
+        self._early_ev = torch.cuda.Event(external=True) if early else None
+        self._early_fired = False
+        self.buckets = GradientBuckets(self.params, early=early)
         self.opt = FusedAdamWEMA(self.all_params, self.buckets, lr=lr, eps=eps, ema_betas=ema_betas,
                                  ema_stds=() if ema_betas else ema_stds, ema_ratio=1.0 / accumulation_steps,
                                  max_grad_norm=max_grad_norm)
@@ -374,6 +409,24 @@ class Trainer:
         loss.backward()
         return loss.detach(), unweighted
 
+    def _decoder_backward_done(self, grad):
+        """Tensor hook on the encoder's output (networks.UNet.forward): fires when every decoder block has run its
+        backward.  Marks, on the weight-gradient stream, the point where the early gradient group is complete -- an
+        EXTERNAL event, so that inside a captured micro-step it becomes an event-record node the communication stream
+        can wait on after the graph launch."""
+        from .ops import WeightGradBranch
+        main = torch.cuda.current_stream(grad.device)
+        if WeightGradBranch.enabled:
+            side = WeightGradBranch.stream(grad.device)      # (keyed by device index: self.device may be a bare "cuda")
+            here = torch.cuda.Event()
+            here.record(main)
+            side.wait_event(here)                 # the gates' gradients are written by main-stream kernels
+            self._early_ev.record(side)
+        else:
+            self._early_ev.record(main)
+        self._early_fired = True
+        return None
+
     def _optimizer_step(self):
         self.opt.step()
 
@@ -390,10 +443,11 @@ class Trainer:
 
     def micro_step(self, latents, conditioning=None):
         """One micro-batch forward+backward; every `accum`-th call also syncs gradients and steps the optimizer."""
+        self._early_fired = False
         out = self._forward_backward(latents, conditioning)
         if self.micro % self.accum == 0:
             if self._distributed():
-                self.opt.step_with_all_reduce()
+                self.opt.step_with_all_reduce(self._early_ev if self._early_fired else None)
             else:
                 self._optimizer_step()
         return out
@@ -469,14 +523,15 @@ class Trainer:
                 continue
             gen = param_generation()
             g = torch.cuda.CUDAGraph()
+            self._early_fired = False
             with torch.cuda.graph(g, stream=self._capture_stream):
                 loss, _ = self._forward_backward(self.static_x)
-            self.graphs[kind] = (g, loss)
+            self.graphs[kind] = (g, loss, self._early_fired)     # does this graph record the early-gradient event?
             assert param_generation() == gen
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g, stream=self._capture_stream):
             self._optimizer_step()
-        self.graphs["opt"] = (g, None)
+        self.graphs["opt"] = (g, None, False)
         self._plan = plan
         self._replayed = 0
         # the captures recorded but did not execute a cycle: gradients are still zero, weights unchanged
@@ -488,11 +543,11 @@ class Trainer:
         pos = self._replayed % self.accum
         if latents is not None:
             self.static_x.copy_(latents, non_blocking=True)
-        g, loss = self.graphs[self._plan[pos]]
+        g, loss, early = self.graphs[self._plan[pos]]
         g.replay()
         if pos == self.accum - 1:
             if self._distributed():            # the one collective on the path, outside the graphs, pipelined with the update
-                self.opt.step_with_all_reduce()
+                self.opt.step_with_all_reduce(self._early_ev if early else None)
             else:
                 self.graphs["opt"][0].replay()
         self._replayed += 1

@@ -181,3 +181,44 @@ def test_trainer_matches_reference_loop_over_several_optimizer_steps():
         assert float((ema_a - ema_b).abs().mean()) <= 1e-4 * float(pa.abs().mean())
     finally:
         ops.set_weight_grad_mode(prev_mode)
+
+
+def test_early_gradient_group_is_final_when_the_backward_pass_leaves_the_decoder():
+    """train.Trainer starts the all-reduce of the decoder's gradients behind an event recorded at the encoder / decoder
+    boundary of the backward pass: every gradient of that (tail) group must already hold its final value there, in the 3-D
+    and in the 2-D micro-step, with the weight-gradient stream on."""
+    from autoregressive_diffusion_b200.train import Trainer
+    from autoregressive_diffusion_b200 import ops
+    prev_mode = ops.weight_grad_mode()
+    try:
+        torch.manual_seed(5)
+        x = torch.randn(2, 4, 8, 16, 16, device="cuda")
+        tr = Trainer(SMALL_UNET, accumulation_steps=2, lr=1e-3, device="cuda", seed=3, just_2d_every=2)
+        with torch.no_grad():
+            tr.unet.out_gain.fill_(1.0)
+        for _ in range(4):                       # lays the flat buffers out (two cycles, both kinds of micro-step)
+            tr.micro_step(x)
+        bk = tr.buckets
+        assert 0 < bk.n_late_buckets < len(bk.buckets), "the small UNet must have both groups"
+        lo = sum(b.numel() for b in bk.buckets[:bk.n_late_buckets])
+        assert lo < bk.flat.numel()
+        snaps = []
+        inner = tr.unet.boundary_hook
+
+        def hook(grad):
+            inner(grad)
+            tr._early_ev.synchronize()           # what the communication stream waits for
+            snaps.append(bk.flat[lo:].clone())
+            return None
+
+        tr.unet.boundary_hook = hook
+        for step in range(2):                    # one 3-D and one 2-D micro-step; the second ends with the optimizer step
+            tr._forward_backward(x)
+            torch.cuda.synchronize()
+            assert len(snaps) == step + 1
+            assert float(snaps[-1].abs().max()) > 0
+            assert torch.equal(snaps[-1], bk.flat[lo:]), "a gradient of the early group changed after the boundary event"
+            # and the late group did still change after it (the event is not simply the end of the pass)
+        assert tr._early_fired
+    finally:
+        ops.set_weight_grad_mode(prev_mode)

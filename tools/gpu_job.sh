@@ -1,9 +1,9 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_conv_gpu.py tests/test_unet_gpu.py tests/test_vae_gpu.py -m gpu -q -x 2>&1 | tail -3
-cp autoregressive_diffusion_b200/liboniris_b200.so build/variants/lib_main.so
-for v in old e8 old e8; do
-  cp build/variants/lib_$v.so autoregressive_diffusion_b200/liboniris_b200.so
-  echo "== $v"
-  timeout 600 python tools/conv_breakdown.py > gpurun_out/breakdown_$v.txt 2>&1; head -1 gpurun_out/breakdown_$v.txt
+for c in 4 8 16; do
+NCCL_MAX_CTAS=$c timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29524 bench.py --gpus 8 --steps 20 --warmup 5 --no-secondary 2>/dev/null | python -c "
+import sys,json
+for l in sys.stdin:
+    if l.startswith('{'):
+        d=json.loads(l); print('max_ctas=$c', d['value'], d['ms_per_step'], d['e2e']['value'])
+"
 done
-cp build/variants/lib_main.so autoregressive_diffusion_b200/liboniris_b200.so
