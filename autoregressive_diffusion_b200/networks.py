@@ -125,6 +125,7 @@ class UNet(BetterModule):
         cemb = model_channels * channel_mult_emb if channel_mult_emb is not None else max(cblock)
         self.label_balance, self.concat_balance = label_balance, concat_balance
         self.boundary_hook = None       # train.Trainer: called (as a tensor hook) when the backward pass leaves the decoder
+        self.enc_boundary = None        # (encoder block name, hook): called when the pass has finished that block and all later ones
         self.out_res = Gating()
         self.out_gain = nn.Parameter(torch.zeros([]))
         self.emb_fourier_sigma = MPFourier(cnoise)
@@ -201,6 +202,8 @@ class UNet(BetterModule):
         x = torch.cat([x, torch.ones_like(x[:, :1])], dim=1)
         skips = []
         for name, block in self.enc.items():
+            if self.enc_boundary is not None and name == self.enc_boundary[0] and torch.is_grad_enabled() and x.requires_grad:
+                x.register_hook(self.enc_boundary[1])
             kw = {"emb_scale": scales[id(block)]} if isinstance(block, Block) else {}
             x, cache['enc', name] = block(x, emb, batch_size, c_noise, cache=cache.get(('enc', name), None),
                                           update_cache=update_cache, just_2d=just_2d, **kw)

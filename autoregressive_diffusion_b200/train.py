@@ -79,38 +79,48 @@ class GradientBuckets:
     into its update."""
 
     def __init__(self, params, bucket_bytes=None, early=()):
-        """`early`: parameters whose gradients are complete well before the backward pass ends (the decoder's conv weights
-        and gates: everything upstream of them in the backward order).  They are laid out as the TAIL of the flat buffer
-        in buckets of their own, so their all-reduce can start while the rest of the backward pass is still running
-        (FusedAdamWEMA.step_with_all_reduce(early_event=...))."""
+        """`early`: groups of parameters (lists, in the order their gradients become complete during the backward pass)
+        whose gradients are final well before the pass ends -- the decoder's conv weights and gates first, then the deep
+        encoder levels'.  They are laid out as the TAIL of the flat buffer, the group that completes first last, each in
+        buckets of its own, so that its all-reduce can start while the rest of the backward pass is still running
+        (FusedAdamWEMA.step_with_all_reduce(early_events=...))."""
         if bucket_bytes is None:
             bucket_bytes = int(os.environ.get("ONIRIS_BUCKET_MB", "128")) << 20
         self.params = [p for p in params if p.requires_grad]
-        self.early_ids = {id(p) for p in early}
+        early = [list(g) for g in early] if (early and isinstance(early[0], (list, tuple))) else ([list(early)] if early else [])
+        self.early_groups = [{id(p) for p in g} for g in early]
         self.bucket_elems = max(1, bucket_bytes // 4)
         self.flat = None
         self.buckets = None
-        self.n_late_buckets = 0          # buckets[:n_late_buckets] hold the late gradients, the rest the early ones
+        self.bucket_group = []           # per bucket: -1 = late (reduced after the backward pass), k = early group k
+        self.n_late_buckets = 0          # buckets[:n_late_buckets] hold the late gradients
         self.live = None
         self.stream = torch.cuda.Stream() if torch.cuda.is_available() else None
 
     def flatten(self):
-        live = [p for p in self.params if p.grad is not None]
-        live = [p for p in live if id(p) not in self.early_ids] + [p for p in live if id(p) in self.early_ids]
-        late_total = sum(_pad64(p.numel()) for p in live if id(p) not in self.early_ids)
+        live_all = [p for p in self.params if p.grad is not None]
+        taken = set().union(*self.early_groups) if self.early_groups else set()
+        sections = [(-1, [p for p in live_all if id(p) not in taken])]
+        for k in reversed(range(len(self.early_groups))):            # the group that completes first goes last
+            sections.append((k, [p for p in live_all if id(p) in self.early_groups[k]]))
+        live = [p for _, ps in sections for p in ps]
         total = sum(_pad64(p.numel()) for p in live)
         self.flat = torch.zeros(total, dtype=torch.float32, device=live[0].device)
         off = 0
-        for p in live:
-            view = _view_like(self.flat, off, p)
-            view.copy_(p.grad)
-            p.grad = view
-            off += _pad64(p.numel())
+        self.buckets, self.bucket_group = [], []
+        for k, ps in sections:
+            start = off
+            for p in ps:
+                view = _view_like(self.flat, off, p)
+                view.copy_(p.grad)
+                p.grad = view
+                off += _pad64(p.numel())
+            for i in range(start, off, self.bucket_elems):
+                self.buckets.append(self.flat[i:min(i + self.bucket_elems, off)])
+                self.bucket_group.append(k)
+        self.n_late_buckets = sum(1 for k in self.bucket_group if k < 0)
         self.live = live
         self._live_ids = {id(p) for p in live}
-        self.buckets = [self.flat[i:min(i + self.bucket_elems, late_total)] for i in range(0, late_total, self.bucket_elems)]
-        self.n_late_buckets = len(self.buckets)
-        self.buckets += [self.flat[i:min(i + self.bucket_elems, total)] for i in range(late_total, total, self.bucket_elems)]
 
     def check_no_late_gradients(self):
         """A parameter that first receives a gradient AFTER the flat buffers were laid out would be silently left out of
@@ -245,37 +255,42 @@ class FusedAdamWEMA:
             self._grad_sumsq()
         self.update_range()
 
-    def step_with_all_reduce(self, early_event=None):
+    def step_with_all_reduce(self, early_events=None):
         """Data-parallel optimizer step: the gradient SUM over ranks runs bucket by bucket on the communication stream
         while the buckets already reduced are being updated here (the mean's 1/world is folded into the update), so the
         all-reduce and the HBM-bound update overlap instead of running back to back (cs_train.py:108-124 does
         all-reduce, then step, then EMA).  With gradient clipping the norm of the complete mean is needed first, so the
         update waits for the whole reduction.
 
-        `early_event`: recorded (by the backward pass that is still running on the current stream, or by the CUDA graph
-        just launched on it) once the gradients of GradientBuckets' early group are final: their buckets are reduced
-        behind that event, concurrently with the rest of the backward pass; only the late buckets wait for its end."""
+        `early_events[k]`: recorded (by the backward pass that is still running on the current stream, or by the CUDA graph
+        just launched on it) once the gradients of GradientBuckets' early group k are final: that group's buckets are
+        reduced behind it, concurrently with the rest of the backward pass; only the late buckets wait for its end."""
         world = dist.get_world_size()
         self.begin_step()
         bk = self.buckets
         main = torch.cuda.current_stream()
-        n_late = bk.n_late_buckets if early_event is not None else len(bk.buckets)
         events = [None] * len(bk.buckets)
+        order = []                                  # the order the reductions are issued (and complete) in
 
         def reduce(i):
             dist.all_reduce(bk.buckets[i])
             events[i] = torch.cuda.Event()
             events[i].record(bk.stream)
+            order.append(i)
 
-        if n_late < len(bk.buckets):
-            bk.stream.wait_event(early_event)
+        for k in range(len(bk.early_groups) if early_events else 0):
+            if k >= len(early_events) or early_events[k] is None:
+                continue
+            bk.stream.wait_event(early_events[k])
             with torch.cuda.stream(bk.stream):
-                for i in range(n_late, len(bk.buckets)):
-                    reduce(i)
+                for i, g in enumerate(bk.bucket_group):
+                    if g == k:
+                        reduce(i)
         bk.stream.wait_stream(main)
         with torch.cuda.stream(bk.stream):
-            for i in range(n_late):
-                reduce(i)
+            for i in range(len(bk.buckets)):
+                if events[i] is None:
+                    reduce(i)
         if self.max_grad_norm > 0:
             main.wait_stream(bk.stream)
             self._grad_sumsq()
@@ -284,7 +299,6 @@ class FusedAdamWEMA:
         lo = [0]
         for b in bk.buckets:
             lo.append(lo[-1] + b.numel())
-        order = list(range(n_late, len(bk.buckets))) + list(range(n_late))     # the order the reductions complete in
         for i in order:
             main.wait_event(events[i])
             self.update_range(lo[i], lo[i + 1], 1.0 / world)
@@ -372,16 +386,27 @@ class Trainer:
         self.all_params = list(self.precond.parameters())
         self.params = [p for p in self.all_params if p.requires_grad]
         self.accum = accumulation_steps
-        # gradients that are final once the backward pass leaves the decoder (70 % of the CS UNet): decoder / output conv
-        # weights and gates.  The embedding linears are excluded: their gradient comes from the ONE batched embedding op,
-        # whose backward runs last.  Only with this package's UNet (it announces the boundary, networks.UNet.boundary_hook).
+        # Gradients that are final well before the backward pass ends, in completion order:
+        #   group 0: decoder / output conv weights and gates (70 % of the CS UNet) -- final when the pass leaves the decoder;
+        #   group 1: the deep encoder blocks (the smallest suffix holding >= 80 % of the encoder: 8x8 and 4x4 levels, 25 %) --
+        #            final when the pass reaches the input of the first of them.
+        # The embedding linears are excluded: their gradient comes from the ONE batched embedding op, whose backward runs
+        # last.  Only with this package's UNet (it announces the boundaries, networks.UNet.boundary_hook / enc_boundary).
         early = []
         if isinstance(self.unet, UNet) and self.device.type == "cuda" and os.environ.get("ONIRIS_NO_EARLY_REDUCE", "0") != "1":
-            early = [p for n, p in self.unet.named_parameters()
-                     if (n.startswith("dec.") or n.startswith("out_conv.")) and "emb" not in n and p.requires_grad]
-            self.unet.boundary_hook = self._decoder_backward_done
-        self._early_ev = torch.cuda.Event(external=True) if early else None
-        self._early_fired = False
+            ok = lambda n, p: "emb" not in n and p.requires_grad
+            early.append([p for n, p in self.unet.named_parameters() if (n.startswith("dec.") or n.startswith("out_conv.")) and ok(n, p)])
+            self.unet.boundary_hook = lambda grad: self._boundary_done(0, grad)
+            names = list(self.unet.enc.keys())
+            sizes = [sum(p.numel() for p in self.unet.enc[n].parameters()) for n in names]
+            first = len(names) - 1
+            while first > 1 and sum(sizes[first:]) < 0.8 * sum(sizes):
+                first -= 1
+            if first >= 2:                        # something shallow must remain to hide the transfer behind
+                early.append([p for k in names[first:] for n, p in self.unet.enc[k].named_parameters() if ok(n, p)])
+                self.unet.enc_boundary = (names[first], lambda grad: self._boundary_done(1, grad))
+        self._early_ev = [torch.cuda.Event(external=True) for _ in early]
+        self._early_fired = [False] * len(early)
         self.buckets = GradientBuckets(self.params, early=early)
         self.opt = FusedAdamWEMA(self.all_params, self.buckets, lr=lr, eps=eps, ema_betas=ema_betas,
                                  ema_stds=() if ema_betas else ema_stds, ema_ratio=1.0 / accumulation_steps,
@@ -409,11 +434,11 @@ class Trainer:
         loss.backward()
         return loss.detach(), unweighted
 
-    def _decoder_backward_done(self, grad):
-        """Tensor hook on the encoder's output (networks.UNet.forward): fires when every decoder block has run its
-        backward.  Marks, on the weight-gradient stream, the point where the early gradient group is complete -- an
-        EXTERNAL event, so that inside a captured micro-step it becomes an event-record node the communication stream
-        can wait on after the graph launch."""
+    def _boundary_done(self, k, grad):
+        """Tensor hook (networks.UNet.forward) on the encoder's output (k = 0: every decoder block has run its backward) or
+        on the input of the first deep encoder block (k = 1).  Marks, on the weight-gradient stream, the point where early
+        gradient group k is complete -- an EXTERNAL event, so that inside a captured micro-step it becomes an event-record
+        node the communication stream can wait on after the graph launch."""
         from .ops import WeightGradBranch
         main = torch.cuda.current_stream(grad.device)
         if WeightGradBranch.enabled:
@@ -421,11 +446,14 @@ class Trainer:
             here = torch.cuda.Event()
             here.record(main)
             side.wait_event(here)                 # the gates' gradients are written by main-stream kernels
-            self._early_ev.record(side)
+            self._early_ev[k].record(side)
         else:
-            self._early_ev.record(main)
-        self._early_fired = True
+            self._early_ev[k].record(main)
+        self._early_fired[k] = True
         return None
+
+    def _fired_events(self, fired):
+        return [ev if f else None for ev, f in zip(self._early_ev, fired)] if any(fired) else None
 
     def _optimizer_step(self):
         self.opt.step()
@@ -443,11 +471,11 @@ class Trainer:
 
     def micro_step(self, latents, conditioning=None):
         """One micro-batch forward+backward; every `accum`-th call also syncs gradients and steps the optimizer."""
-        self._early_fired = False
+        self._early_fired = [False] * len(self._early_ev)
         out = self._forward_backward(latents, conditioning)
         if self.micro % self.accum == 0:
             if self._distributed():
-                self.opt.step_with_all_reduce(self._early_ev if self._early_fired else None)
+                self.opt.step_with_all_reduce(self._fired_events(self._early_fired))
             else:
                 self._optimizer_step()
         return out
@@ -523,15 +551,15 @@ class Trainer:
                 continue
             gen = param_generation()
             g = torch.cuda.CUDAGraph()
-            self._early_fired = False
+            self._early_fired = [False] * len(self._early_ev)
             with torch.cuda.graph(g, stream=self._capture_stream):
                 loss, _ = self._forward_backward(self.static_x)
-            self.graphs[kind] = (g, loss, self._early_fired)     # does this graph record the early-gradient event?
+            self.graphs[kind] = (g, loss, list(self._early_fired))     # which early-gradient events this graph records
             assert param_generation() == gen
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g, stream=self._capture_stream):
             self._optimizer_step()
-        self.graphs["opt"] = (g, None, False)
+        self.graphs["opt"] = (g, None, [])
         self._plan = plan
         self._replayed = 0
         # the captures recorded but did not execute a cycle: gradients are still zero, weights unchanged
@@ -547,7 +575,7 @@ class Trainer:
         g.replay()
         if pos == self.accum - 1:
             if self._distributed():            # the one collective on the path, outside the graphs, pipelined with the update
-                self.opt.step_with_all_reduce(self._early_ev if early else None)
+                self.opt.step_with_all_reduce(self._fired_events(early))
             else:
                 self.graphs["opt"][0].replay()
         self._replayed += 1

@@ -183,42 +183,49 @@ def test_trainer_matches_reference_loop_over_several_optimizer_steps():
         ops.set_weight_grad_mode(prev_mode)
 
 
-def test_early_gradient_group_is_final_when_the_backward_pass_leaves_the_decoder():
+def test_early_gradient_groups_are_final_at_their_boundary_events():
     """train.Trainer starts the all-reduce of the decoder's gradients behind an event recorded at the encoder / decoder
-    boundary of the backward pass: every gradient of that (tail) group must already hold its final value there, in the 3-D
-    and in the 2-D micro-step, with the weight-gradient stream on."""
+    boundary of the backward pass, and that of the deep encoder blocks behind a second one: every gradient of a group (a
+    tail section of the flat buffer) must already hold its final value at its event, in the 3-D and in the 2-D micro-step,
+    with the weight-gradient stream on."""
     from autoregressive_diffusion_b200.train import Trainer
     from autoregressive_diffusion_b200 import ops
     prev_mode = ops.weight_grad_mode()
+    three_levels = dict(SMALL_UNET, channel_mult=[1, 2, 2], video_attn_resolutions=[4], frame_attn_resolutions=[8])
     try:
         torch.manual_seed(5)
         x = torch.randn(2, 4, 8, 16, 16, device="cuda")
-        tr = Trainer(SMALL_UNET, accumulation_steps=2, lr=1e-3, device="cuda", seed=3, just_2d_every=2)
+        tr = Trainer(three_levels, accumulation_steps=2, lr=1e-3, device="cuda", seed=3, just_2d_every=2)
         with torch.no_grad():
             tr.unet.out_gain.fill_(1.0)
         for _ in range(4):                       # lays the flat buffers out (two cycles, both kinds of micro-step)
             tr.micro_step(x)
         bk = tr.buckets
-        assert 0 < bk.n_late_buckets < len(bk.buckets), "the small UNet must have both groups"
-        lo = sum(b.numel() for b in bk.buckets[:bk.n_late_buckets])
-        assert lo < bk.flat.numel()
-        snaps = []
-        inner = tr.unet.boundary_hook
+        assert len(bk.early_groups) == 2 and set(bk.bucket_group) == {-1, 0, 1}, "this UNet must have all three sections"
+        lo = [0]
+        for b in bk.buckets:
+            lo.append(lo[-1] + b.numel())
+        start = {k: min(lo[i] for i, g in enumerate(bk.bucket_group) if g == k) for k in (0, 1)}
+        end = {k: max(lo[i + 1] for i, g in enumerate(bk.bucket_group) if g == k) for k in (0, 1)}
+        assert end[0] == bk.flat.numel() and end[1] == start[0] and start[1] > 0      # late | group 1 | group 0
+        snaps = {}
+        inner = tr._boundary_done
 
-        def hook(grad):
-            inner(grad)
-            tr._early_ev.synchronize()           # what the communication stream waits for
-            snaps.append(bk.flat[lo:].clone())
+        def spy(k, grad):
+            inner(k, grad)
+            tr._early_ev[k].synchronize()        # what the communication stream waits for
+            snaps[k] = bk.flat[start[k]:end[k]].clone()
             return None
 
-        tr.unet.boundary_hook = hook
-        for step in range(2):                    # one 3-D and one 2-D micro-step; the second ends with the optimizer step
+        tr._boundary_done = spy
+        for step in range(2):                    # one 3-D and one 2-D micro-step
+            snaps.clear()
             tr._forward_backward(x)
             torch.cuda.synchronize()
-            assert len(snaps) == step + 1
-            assert float(snaps[-1].abs().max()) > 0
-            assert torch.equal(snaps[-1], bk.flat[lo:]), "a gradient of the early group changed after the boundary event"
-            # and the late group did still change after it (the event is not simply the end of the pass)
-        assert tr._early_fired
+            assert sorted(snaps) == [0, 1]
+            for k in (0, 1):
+                assert float(snaps[k].abs().max()) > 0
+                assert torch.equal(snaps[k], bk.flat[start[k]:end[k]]), f"a gradient of early group {k} changed after its event"
+        assert all(tr._early_fired)
     finally:
         ops.set_weight_grad_mode(prev_mode)

@@ -35,9 +35,9 @@ def run(mode):
     gathered = [torch.zeros_like(digest) for _ in range(world)]
     dist.all_gather(gathered, digest)
     same = all(torch.equal(gathered[0], t) for t in gathered)
-    early = tr.buckets.n_late_buckets < len(tr.buckets.buckets)
+    early = len(tr.buckets.early_groups)
     if rank == 0:
-        print(f"world={world} [{mode}]: early-gradient group {'on' if early else 'off'}; parameter digests identical across ranks: {same}; "
+        print(f"world={world} [{mode}]: early-gradient groups {early}; parameter digests identical across ranks: {same}; "
               f"finite: {bool(torch.isfinite(digest).all())}; optimizer steps {tr.opt.opt_state[0].item():.0f}; digest {digest.tolist()}", flush=True)
     assert same and torch.isfinite(digest).all()
     return digest
