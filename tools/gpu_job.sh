@@ -1,8 +1,3 @@
 mkdir -p gpurun_out
-timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29523 bench.py --gpus 8 --steps 20 --warmup 5 2>/dev/null > gpurun_out/r02_bench_n8_two_groups.json
-python -c "
-import sys,json
-for l in open('gpurun_out/r02_bench_n8_two_groups.json'):
-    if l.startswith('{'):
-        d=json.loads(l); print('two groups', d['value'], d['ms_per_step'], d['e2e']['value'])
-"
+timeout 900 python -m pytest tests/test_attention_gpu.py -m gpu -q -x 2>&1 | tail -3
+timeout 600 python tools/bench_attention.py 2>&1 | grep -v "^\[" | sed -E "s/.*'tokens_per_frame': ([0-9]+), 'seq_len': ([0-9]+).*'fwd_ms': ([0-9.]+), 'bwd_ms': ([0-9.]+), 'fwd_tflops_sparse': ([0-9.]+), 'bwd_tflops_sparse': ([0-9.]+).*/hw=\1 L=\2 fwd_ms=\3 bwd_ms=\4 fwdTF=\5 bwdTF=\6/"
