@@ -1,5 +1,8 @@
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -q -x 2>&1 | tail -3
-timeout 600 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -3
-timeout 1200 python bench.py --steps 20 --warmup 5 > gpurun_out/r02_bench_final.json 2> gpurun_out/r02_bench_final.err; echo "bench rc=$?"; tail -c 400 gpurun_out/r02_bench_final.json
-timeout 900 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/r02_bench_ref.json 2> gpurun_out/r02_bench_ref.err; echo "ref rc=$?"; head -c 600 gpurun_out/r02_bench_ref.json
+timeout 1500 python -m pytest tests/test_unet_gpu.py tests/test_train_gpu.py tests/test_reference_swap_gpu.py -m gpu -q -x 2>&1 | tail -3
+timeout 900 python bench.py --steps 40 --warmup 5 --no-secondary --no-cpu-baseline 2>/dev/null | python -c "
+import sys,json
+for l in sys.stdin:
+    if l.startswith('{'):
+        d=json.loads(l); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['roofline']['frac'])
+"
