@@ -281,7 +281,7 @@ struct GateGradArgs {
   int n_ctx;
 };
 
-__global__ void __launch_bounds__(256) gate_bwd_kernel(const __nv_bfloat16* __restrict__ dy,
+__global__ void __launch_bounds__(256, 4) gate_bwd_kernel(const __nv_bfloat16* __restrict__ dy,
                                                        const __nv_bfloat16* __restrict__ y,
                                                        const __half* __restrict__ d,
                                                        const float* __restrict__ alpha, const float* __restrict__ beta,
@@ -1081,7 +1081,7 @@ __global__ void __launch_bounds__(256) vae_norm_silu_fwd_kernel(const __nv_bfloa
 }
 
 template <int LPR>
-__global__ void __launch_bounds__(256) vae_norm_silu_bwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ film,
+__global__ void __launch_bounds__(256, 2) vae_norm_silu_bwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ film,
                                                                 const __nv_bfloat16* __restrict__ g, __nv_bfloat16* __restrict__ dx,
                                                                 float* __restrict__ dfilm, long rows_per_batch, int C, int c_mean,
                                                                 float eps) {
