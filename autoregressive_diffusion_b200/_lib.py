@@ -59,6 +59,7 @@ _SIGS = {
     "ob_vae_norm_silu_bwd": "pppppiliifp",
     "ob_time_window": "pppiiliiiip",
     "ob_ungroup": "ppllliip",
+    "ob_colsum": "pplip",
     "ob_set_pdl": "i",
     "ob_adamw_ema": "pppppplpfffffffffp",
     "ob_sumsq": "plpp",

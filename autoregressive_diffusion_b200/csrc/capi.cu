@@ -285,6 +285,9 @@ int ob_time_window(const void* src, const void* pad, void* dst, int b, int t, in
 int ob_ungroup(const void* in, void* out, int64_t frames, int64_t hw, int g, int cc, int inverse, void* stream) {
   return ungroup(in, out, (long)frames, (long)hw, g, cc, inverse, (cudaStream_t)stream);
 }
+int ob_colsum(const void* g, float* out, int64_t rows, int c, void* stream) {
+  return colsum(g, out, (long)rows, c, (cudaStream_t)stream);
+}
 int ob_set_pdl(int enabled) {
   static const bool forced_off = [] { const char* e = getenv("ONIRIS_PDL"); return e != nullptr && e[0] == '0'; }();
   const int prev = pdl_mode();

@@ -41,6 +41,7 @@ int vae_norm_silu_bwd(const void* x, const float* film, const void* g, void* dx,
                       int c_mean, float eps, cudaStream_t st);
 int time_window(const void* src, const void* pad, void* dst, int B, int T, long hw, int C, int g, int kt, int backward, cudaStream_t st);
 int ungroup(const void* in, void* out, long frames, long hw, int g, int Cc, int inverse, cudaStream_t st);
+int colsum(const void* g, float* out, long rows, int C, cudaStream_t st);
 int resample2x(const void* in, void* out, long frames, int h, int w, int c, int pool, float scale, cudaStream_t st);
 int adamw_ema(float* p, float* g, float* m, float* v, float* e1, float* e2, long n, const float* opt_state, float beta1,
               float beta2, float eps, float wd, float ema_a1, float ema_a2, float ema_ratio, float grad_scale, float max_norm,

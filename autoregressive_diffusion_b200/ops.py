@@ -361,12 +361,20 @@ class RawConvFn(torch.autograd.Function):
     view of the layer's weight); its gradient is returned through autograd."""
 
     @staticmethod
-    def forward(ctx, x, wmat, bias, ksize):
+    def forward(ctx, x, wmat, bias, ksize, dims=None):
+        """wmat: fp32 weights whose row-major flattening is [Cout, k*k, Cin] -- given as that 3-D tensor or (dims=(Cout, k*k,
+        Cin)) as ANY strided view with that element order, e.g. a permuted view of an nn.Conv3d weight: it is then cast and
+        re-laid out into the bf16 operand in ONE strided copy instead of an fp32 reshape-copy plus a cast (1 GB of fp32
+        weights per VAE step)."""
         f, cin_pad, h, wd = x.shape
-        cout, kk, cin = wmat.shape
+        cout, kk, cin = wmat.shape if dims is None else dims
         cout_pad = ceil_to(cout, 8)
-        wg = torch.zeros((cout_pad, kk, cin_pad), dtype=BF16, device=x.device)
-        wg[:cout, :, :cin] = wmat
+        if cout_pad == cout and cin_pad == cin:
+            wg = torch.empty((cout_pad, kk, cin_pad), dtype=BF16, device=x.device)
+            wg.view(wmat.shape).copy_(wmat)
+        else:
+            wg = torch.zeros((cout_pad, kk, cin_pad), dtype=BF16, device=x.device)
+            wg[:cout, :, :cin] = wmat.reshape(cout, kk, cin)
         bias_p = None
         if bias is not None:      # added to the fp32 accumulator in the epilogue: one rounding for conv + bias
             bias_p = torch.zeros(cout_pad, dtype=torch.float32, device=x.device)
@@ -377,6 +385,7 @@ class RawConvFn(torch.autograd.Function):
              0, 0, kk, _vp(bias_p), stream_ptr())
         ctx.save_for_backward(x, wg)
         ctx.dims = (ksize, cout, cin)
+        ctx.wshape = tuple(wmat.shape)
         return out if cout_pad == cout else out[:, :cout]
 
     @staticmethod
@@ -397,9 +406,13 @@ class RawConvFn(torch.autograd.Function):
             dwg = torch.empty((ns, cout_pad, kk, cin_pad), dtype=torch.float32, device=x.device)
             call("ob_conv_wgrad", _vp(gy), _vp(x), None, None, _vp(dwg), 1, 1, f, h, wd, cin_pad, cout_pad, ksize, 0, ns,
                  stream_ptr())
-            dw = dwg.sum(0)[:cout, :, :cin]
-        db = gy[:, :cout].sum(dim=(0, 2, 3), dtype=torch.float32) if ctx.needs_input_grad[2] else None
-        return dx, dw, db, None
+            dw = (dwg[0] if ns == 1 else dwg.sum(0))[:cout, :, :cin].reshape(ctx.wshape)
+        db = None
+        if ctx.needs_input_grad[2]:       # one pass over gy (torch: an fp32 copy + a reduction, 12 ms of the 74 ms VAE step)
+            dbp = torch.zeros(cout_pad, dtype=torch.float32, device=x.device)
+            call("ob_colsum", _vp(gy), _vp(dbp), f * h * wd, cout_pad, stream_ptr())
+            db = dbp[:cout]
+        return dx, dw, db, None, None
 
 
 class VaeNormSiluFn(torch.autograd.Function):
@@ -482,10 +495,11 @@ class UngroupFn(torch.autograd.Function):
         return dy, None
 
 
-def raw_conv(x, wmat, ksize, bias=None):
-    """x: logical [F, C, H, W] (any dtype / layout) -> bf16 channels_last [F, Cout, H, W] = conv2d(x, w) + bias."""
+def raw_conv(x, wmat, ksize, bias=None, dims=None):
+    """x: logical [F, C, H, W] (any dtype / layout) -> bf16 channels_last [F, Cout, H, W] = conv2d(x, w) + bias.
+    wmat: [Cout, k*k, Cin], or with dims=(Cout, k*k, Cin) any strided view in that element order (RawConvFn.forward)."""
     _require_cuda(x)
-    return RawConvFn.apply(pad_channels(rows(x), 16), wmat, bias, ksize)
+    return RawConvFn.apply(pad_channels(rows(x), 16), wmat, bias, ksize, dims)
 
 
 class GatedConvFn(torch.autograd.Function):

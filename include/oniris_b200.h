@@ -210,6 +210,11 @@ int ob_vae_norm_silu_bwd(const void* x, const float* film, const void* g, void* 
 int ob_time_window(const void* src, const void* pad, void* dst, int b, int t, int64_t hw, int c, int g, int kt, int backward, void* stream);
 int ob_ungroup(const void* in, void* out, int64_t frames, int64_t hw, int g, int cc, int inverse, void* stream);
 
+/* Bias gradient of a conv with bias (autograd of nn.Conv3d(bias=True), edm2/vae/vae.py:26-31): out[ch] += sum over rows of
+ * g[row, ch]; g: bf16 [rows, c] (c % 8 == 0), out: fp32 [c], zeroed by the caller (partial sums are added with
+ * atomics). */
+int ob_colsum(const void* g, float* out, int64_t rows, int c, void* stream);
+
 /* Programmatic dependent launch: when on (default; ONIRIS_PDL=0 in the environment forces it off), every kernel of the
  * library is launched so that its prologue overlaps the tail of the previous kernel on the stream.  mode 0: off, 1: every
  * kernel, 2: only the light (elementwise) kernels.  Returns the previous mode.  The training backward pass switches it off

@@ -196,3 +196,16 @@ def test_qkv_prep_eval_and_rope_k(B, t_old, t_new, heads, res):
          stream_ptr())
     _, ref = O.rope(qo, k_all_b, *O.rope_buffers(64), False)
     assert_close(rows_out.float(), _token_major(ref, B), "rope_k")
+
+
+@pytest.mark.parametrize("rows,c", [(1, 8), (37, 24), (4096, 32), (100003, 64), (2 * 16 * 64 * 64, 256), (513, 2048), (300, 4096), (77, 2056)])
+def test_colsum_is_the_bias_gradient(rows, c):
+    """ob_colsum (the bias gradient of the VAE convs) against torch's fp32 column sum of the same bf16 matrix."""
+    import ctypes
+    from autoregressive_diffusion_b200 import _lib
+    g = torch.randn(rows, c, device="cuda").to(torch.bfloat16)
+    out = torch.zeros(c, device="cuda")
+    _lib.call("ob_colsum", ctypes.c_void_p(g.data_ptr()), ctypes.c_void_p(out.data_ptr()), rows, c, _lib.stream_ptr())
+    ref = g.double().sum(0)
+    tol = 1e-5 * float(g.double().abs().sum(0).max()) + 1e-6        # fp32 accumulation in a different order
+    assert float((out.double() - ref).abs().max()) <= tol
