@@ -1,3 +1,3 @@
-timeout 900 python -m pytest tests/test_elementwise_gpu.py tests/test_vae_gpu.py tests/test_conv_gpu.py -m gpu -q -x 2>&1 | tail -2
-timeout 600 python tools/bench_vae.py 2>&1 | tail -2 | cut -c1-300
-timeout 400 python tools/profile_vae.py 2>&1 | grep -v Warn | sed -n 2,22p
+mkdir -p gpurun_out; rm -f gpurun_out/r02_parity_report.tsv
+ONIRIS_PARITY_REPORT=$PWD/gpurun_out/r02_parity_report.tsv timeout 1500 python -m pytest tests -m gpu -q -x 2>&1 | tail -2
+wc -l gpurun_out/r02_parity_report.tsv
