@@ -188,7 +188,9 @@ __device__ __forceinline__ void poly_exp2_pair(uint64_t x, float& e0, float& e1)
   e1 = __int_as_float(__float_as_int(q1) + (__float_as_int(t1) << 23));
 }
 // which PAIRS of an unrolled 32-element chunk take the polynomial (5 of 16)
+#ifndef ATTN_PAIR_POLY
 #define ATTN_PAIR_POLY(pi) (((pi) % 3) == 2)
+#endif
 
 // The keys a query row sees, as two windows of token indices: [0, w1_end) and [w2_lo, w2_hi).  Every mask of this file
 // has that shape per row -- causal / clean DART rows: one window up to the end of the row's frame; noised DART rows: the
