@@ -187,9 +187,11 @@ __device__ __forceinline__ void poly_exp2_pair(uint64_t x, float& e0, float& e1)
   e0 = __int_as_float(__float_as_int(q0) + (__float_as_int(t0) << 23));
   e1 = __int_as_float(__float_as_int(q1) + (__float_as_int(t1) << 23));
 }
-// which PAIRS of an unrolled 32-element chunk take the polynomial (5 of 16)
+// which PAIRS of an unrolled 32-element chunk take the polynomial
+// (3 of 16: once the kernel stopped being MUFU-bound -- P in tensor memory, packed math -- fewer polynomial pairs won:
+//  0 / 2 / 3 / 5 of 16 measured 873 / 918 / 923 / 882 TFLOP/s at 65 536 tokens)
 #ifndef ATTN_PAIR_POLY
-#define ATTN_PAIR_POLY(pi) (((pi) % 3) == 2)
+#define ATTN_PAIR_POLY(pi) (((pi) % 5) == 4)
 #endif
 
 // The keys a query row sees, as two windows of token indices: [0, w1_end) and [w2_lo, w2_hi).  Every mask of this file

@@ -183,6 +183,11 @@ __device__ __forceinline__ Win2 query_windows(int mask, int n_frames, int hw, in
   return w;
 }
 
+// which pairs of a 16-element chunk take the FMA-pipe exponential in the backward kernels (tuned separately from the forward)
+#ifndef ABW_PAIR_POLY
+#define ABW_PAIR_POLY(pi) (((pi) % 3) == 2)
+#endif
+
 // One 16-element chunk of a row: P = exp2(s*c1 + nl), dS = P * (dp*scale + nd).  nl / nd are pairs (per column) so the
 // same code serves the dQ kernel (row statistics, broadcast) and the dK/dV kernel (column statistics).  MASKED: elements
 // outside the row's windows (given relative to the chunk's first column) are zeroed.
@@ -195,7 +200,7 @@ __device__ __forceinline__ void pds_chunk16(const float (&s)[16], const float (&
   for (int pi = 0; pi < 8; ++pi) {
     const uint64_t arg = fma2(pack2(s[2 * pi], s[2 * pi + 1]), C1, nl(pi));
     float e0, e1;
-    if (ATTN_PAIR_POLY(pi)) poly_exp2_pair(arg, e0, e1);
+    if (ABW_PAIR_POLY(pi)) poly_exp2_pair(arg, e0, e1);
     else {
       float a0, a1;
       unpack2(arg, a0, a1);
