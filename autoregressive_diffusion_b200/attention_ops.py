@@ -23,7 +23,7 @@ def attn_bwd(q, k, v, o, lse, dout, hw, n_frames, mask):
     b, lq, heads, _ = q.shape
     lk = k.shape[1]
     dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
-    lq_pad = (lq + 63) // 64 * 64       # ob_attn_bwd workspace: two padded planes of per-row statistics
+    lq_pad = (lq + 127) // 128 * 128    # ob_attn_bwd workspace: two padded planes of per-row statistics
     ws = torch.empty((2, b, heads, lq_pad), dtype=torch.float32, device=q.device)
     call("ob_attn_bwd", _vp(q), _vp(k), _vp(v), _vp(o), _vp(dout), _vp(lse), _vp(ws), _vp(dq), _vp(dk), _vp(dv), b, heads,
          lq, lk, hw, n_frames, mask, 0.125, stream_ptr())

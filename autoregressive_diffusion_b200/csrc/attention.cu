@@ -111,12 +111,8 @@ int attn_bwd(const void* q, const void* k, const void* v, const void* o, const v
   memset(&p, 0, sizeof(p));
   if (int r = make_qkv_map(&p.mapQ128, q, B, heads, Lq, 128)) return r;
   if (int r = make_qkv_map(&p.mapdO128, dout, B, heads, Lq, 128)) return r;
-  if (int r = make_qkv_map(&p.mapK64, k, B, heads, Lk, 64)) return r;
-  if (int r = make_qkv_map(&p.mapV64, v, B, heads, Lk, 64)) return r;
   if (int r = make_qkv_map(&p.mapK128, k, B, heads, Lk, 128)) return r;
   if (int r = make_qkv_map(&p.mapV128, v, B, heads, Lk, 128)) return r;
-  if (int r = make_qkv_map(&p.mapQ64, q, B, heads, Lq, 64)) return r;
-  if (int r = make_qkv_map(&p.mapdO64, dout, B, heads, Lq, 64)) return r;
   p.BH = BH; p.heads = heads; p.Lq = Lq; p.Lk = Lk; p.hw = hw; p.n_frames = n_frames; p.mask = mask; p.scale = scale;
   p.lse = lse; p.ws = dsum;
   p.dq = static_cast<__nv_bfloat16*>(dq); p.dk = static_cast<__nv_bfloat16*>(dk); p.dv = static_cast<__nv_bfloat16*>(dv);

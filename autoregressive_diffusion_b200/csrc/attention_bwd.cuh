@@ -2,9 +2,9 @@
 // reference, edm2/attention/attention_modules.py:66,70,75), as two tcgen05 kernels that each recompute the
 // probabilities from the saved log-sum-exp:
 //
-//   dq kernel : one CTA per 128-row query tile, loops over visible 64-row key tiles
+//   dq kernel : one CTA per 128-row query tile, loops over visible 128-row key tiles
 //               S = Q K^T, dP = dO V^T  ->  dS = P*(dP - D)*scale  ->  dQ += dS K
-//   dkv kernel: one CTA per 128-row key tile, loops over visible 64-row query tiles, transposed scores
+//   dkv kernel: one CTA per 128-row key tile, loops over visible 128-row query tiles, transposed scores
 //               S^T = K Q^T, dP^T = V dO^T  ->  P^T, dS^T  ->  dV += P^T dO,  dK += dS^T Q
 //
 // No atomics and no fp32 dQ scratch: every output element is owned by exactly one CTA.
@@ -16,11 +16,11 @@
 namespace ob {
 
 constexpr int ABW_BM = 128;  // rows owned by the CTA (queries for dq, keys for dkv)
-constexpr int ABW_BN = 64;   // rows streamed per step
+constexpr int ABW_BN = 128;  // rows streamed per step (64 before: every step pays ~60 fixed instructions per softmax warp and three
+                             // barrier round trips, which 128-wide steps halve per element)
 
 struct AttnBwdParams {
-  CUtensorMap mapQ128, mapdO128, mapK64, mapV64;   // dq kernel
-  CUtensorMap mapK128, mapV128, mapQ64, mapdO64;   // dkv kernel
+  CUtensorMap mapQ128, mapdO128, mapK128, mapV128;   // 4-D maps (64, L, heads, B) with a 128-row box: own and streamed tiles
   int BH, heads, Lq, Lk, hw, n_frames, mask;
   float scale;
   const float* lse;  // [BH, Lq]
@@ -96,7 +96,7 @@ __device__ __forceinline__ TileRanges visible_queries(const AttnBwdParams& p, in
 // Per-row statistics of the backward pass, pre-scaled so the hot loops use them as FMA addends:
 //   ws[0][bh][i] = -D[i] * scale   with D = rowsum(dO * O)          (dS = P * (dP*scale - D*scale))
 //   ws[1][bh][i] = -lse[i] * log2(e)                                 (P = exp2(S*scale*log2e - lse*log2e))
-// Rows are padded to Lp = ceil(L / 64) * 64 floats (padding zero-filled) so the dK/dV kernel can fetch the 64 values of a
+// Rows are padded to Lp = ceil(L / 128) * 128 floats (padding zero-filled) so the dK/dV kernel can fetch the 128 values of a
 // streamed query tile with one aligned bulk copy.  One 8-lane group per (token, head) row of the [B, L, heads, 64] tensors.
 __global__ void __launch_bounds__(256) attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ o,
                                                             const __nv_bfloat16* __restrict__ dout,
@@ -134,16 +134,15 @@ __global__ void __launch_bounds__(256) attn_bwd_prep_kernel(const __nv_bfloat16*
   }
 }
 
-constexpr int ABW_STAGES = 6;
+constexpr int ABW_STAGES = 4;
 constexpr int ABW_T128 = 128 * 128;  // [128 rows][64 bf16]
-constexpr int ABW_T64 = 64 * 128;    // [64 rows][64 bf16]
-constexpr int ABW_SM_WARPS = 16;     // four softmax warps per TMEM lane quarter, 16 streamed columns each
+constexpr int ABW_SM_WARPS = 16;     // four softmax warps per TMEM lane quarter, 32 streamed columns each (as two chunks of 16)
 constexpr int ABW_COLS = ABW_BN / (ABW_SM_WARPS / 4);
 constexpr int ABW_THREADS = 96 + 32 * ABW_SM_WARPS;   // TMA, two MMA issuers, softmax warps
-constexpr int ABW_DS_BUFS = 3;       // dS buffers of the dQ kernel in tensor memory
-constexpr int ABW_STAT_BYTES = 2 * ABW_BN * 4;        // per stage of the dK/dV kernel: -lse*log2e | -D*scale of 64 queries
-constexpr int ABW_DQ_SMEM = 1024 + 2 * ABW_T128 + ABW_STAGES * 2 * ABW_T64 + 512;
-constexpr int ABW_DKV_SMEM = 1024 + 2 * ABW_T128 + ABW_STAGES * (2 * ABW_T64 + ABW_STAT_BYTES) + 512;
+constexpr int ABW_DS_BUFS = 2;       // dS buffers of the dQ kernel in tensor memory
+constexpr int ABW_STAT_BYTES = 2 * ABW_BN * 4;        // per stage of the dK/dV kernel: -lse*log2e | -D*scale of 128 queries
+constexpr int ABW_DQ_SMEM = 1024 + 2 * ABW_T128 + ABW_STAGES * 2 * ABW_T128 + 512;
+constexpr int ABW_DKV_SMEM = 1024 + 2 * ABW_T128 + ABW_STAGES * (2 * ABW_T128 + ABW_STAT_BYTES) + 512;
 
 // Visibility of the streamed index (keys for a query row, queries for a key row) as two windows [a1, b1) u [a2, b2):
 // every mask of this file has that shape per row, so tile and element tests are integer compares.
@@ -233,24 +232,24 @@ __device__ __forceinline__ int abw_heavy_first(int mask, int n_frames, int hw, i
 // Warp roles: 0 = TMA producer, 1 = S / dP MMA issuer, 2 = dQ MMA issuer (each ONE elected thread running its whole loop),
 // 3..18 = softmax warps.  dS goes from the softmax warps to the dQ MMA through tensor memory (TS mode: the A operand is
 // read from TMEM), not shared memory -- with dS staged in shared memory the kernel was bound by shared-memory bandwidth.
-// TMEM columns: S [0,64) [64,128); dP [128,192) [192,256); dQ [256,320); dS (bf16 pairs) 3 x 32 from 320.
+// TMEM columns: S [0,128); dP [128,256) (single-buffered: the next step's MMAs start as soon as the softmax warps have
+// drained them, early in their step); dQ [256,320); dS (bf16 pairs) 2 x 64 from 320.
 __global__ void __launch_bounds__(ABW_THREADS, 1) attn_bwd_dq_kernel(const __grid_constant__ AttnBwdParams p) {
   pdl_launch_dependents();
   pdl_wait();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sQ = base, sdO = sQ + ABW_T128;
-  const uint32_t sKV = sdO + ABW_T128;                       // stage s: K at +s*16K, V at +s*16K+8K
-  const uint32_t bar = sKV + ABW_STAGES * 2 * ABW_T64;
+  const uint32_t sKV = sdO + ABW_T128;                       // stage s: K at +s*32K, V at +s*32K+16K
+  const uint32_t bar = sKV + ABW_STAGES * 2 * ABW_T128;
   const uint32_t q_full = bar;
   auto kv_full = [&](int s) { return bar + 8u * (1 + s); };
   auto kv_empty = [&](int s) { return bar + 8u * (1 + ABW_STAGES + s); };
-  auto sdp_full = [&](int b) { return bar + 8u * (1 + 2 * ABW_STAGES + b); };
-  auto sdp_empty = [&](int b) { return bar + 8u * (3 + 2 * ABW_STAGES + b); };
-  auto ds_full = [&](int b) { return bar + 8u * (5 + 2 * ABW_STAGES + b); };
-  auto ds_empty = [&](int b) { return bar + 8u * (8 + 2 * ABW_STAGES + b); };
-  const uint32_t acc_full = bar + 8u * (11 + 2 * ABW_STAGES);
-  const uint32_t tmem_slot = bar + 8u * (12 + 2 * ABW_STAGES);
+  const uint32_t sdp_full = bar + 8u * (1 + 2 * ABW_STAGES), sdp_empty = bar + 8u * (2 + 2 * ABW_STAGES);
+  auto ds_full = [&](int b) { return bar + 8u * (3 + 2 * ABW_STAGES + b); };
+  auto ds_empty = [&](int b) { return bar + 8u * (3 + ABW_DS_BUFS + 2 * ABW_STAGES + b); };
+  const uint32_t acc_full = bar + 8u * (3 + 2 * ABW_DS_BUFS + 2 * ABW_STAGES);
+  const uint32_t tmem_slot = bar + 8u * (4 + 2 * ABW_DS_BUFS + 2 * ABW_STAGES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int bh = blockIdx.x;
@@ -262,7 +261,7 @@ __global__ void __launch_bounds__(ABW_THREADS, 1) attn_bwd_dq_kernel(const __gri
   if (threadIdx.x == 0) {
     mbar_init(q_full, 1);
     for (int s = 0; s < ABW_STAGES; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(sdp_full(b), 1); mbar_init(sdp_empty(b), ABW_SM_WARPS); }
+    mbar_init(sdp_full, 1); mbar_init(sdp_empty, ABW_SM_WARPS);
     for (int b = 0; b < ABW_DS_BUFS; ++b) { mbar_init(ds_full(b), ABW_SM_WARPS); mbar_init(ds_empty(b), 1); }
     mbar_init(acc_full, 1);
     fence_barrier_init();
@@ -284,17 +283,17 @@ __global__ void __launch_bounds__(ABW_THREADS, 1) attn_bwd_dq_kernel(const __gri
       uint32_t ph = 1;
       for (int j = 0; j < n_kv; ++j) {
         mbar_wait(kv_empty(st), ph);
-        const uint32_t sK = sKV + st * 2 * ABW_T64, sV = sK + ABW_T64;
-        mbar_arrive_expect_tx(kv_full(st), 2 * ABW_T64);
+        const uint32_t sK = sKV + st * 2 * ABW_T128, sV = sK + ABW_T128;
+        mbar_arrive_expect_tx(kv_full(st), 2 * ABW_T128);
         const int k0 = kr.tile(j) * ABW_BN;
-        tma_load_4d(sK, &p.mapK64, kv_full(st), 0, k0, hh, bb);
-        tma_load_4d(sV, &p.mapV64, kv_full(st), 0, k0, hh, bb);
+        tma_load_4d(sK, &p.mapK128, kv_full(st), 0, k0, hh, bb);
+        tma_load_4d(sV, &p.mapV128, kv_full(st), 0, k0, hh, bb);
         if (++st == ABW_STAGES) { st = 0; ph ^= 1; }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ---- S = Q K^T and dP = dO V^T, up to two tiles ahead of the softmax
+    // ---- S = Q K^T and dP = dO V^T
     if (n_kv > 0 && elect_one()) {
       constexpr uint32_t idesc_s = make_idesc_bf16(128, ABW_BN, 0, 0);
       const uint64_t kdesc0 = make_smem_desc(0, 16, 1024, SWZ_128B);
@@ -303,35 +302,34 @@ __global__ void __launch_bounds__(ABW_THREADS, 1) attn_bwd_dq_kernel(const __gri
       uint32_t ph = 0;
       mbar_wait(q_full, 0);
       for (int j = 0; j < n_kv; ++j) {
-        const int b = j & 1;
         mbar_wait(kv_full(st), ph);
-        if (j >= 2) mbar_wait(sdp_empty(b), ((j >> 1) & 1) ^ 1);
+        if (j >= 1) mbar_wait(sdp_empty, (j & 1) ^ 1);      // the softmax warps have drained S(j-1), dP(j-1)
         tc_fence_after();
-        const uint64_t kd = kdesc0 + ((sKV + st * 2 * ABW_T64) >> 4), vd = kd + (ABW_T64 >> 4);
+        const uint64_t kd = kdesc0 + ((sKV + st * 2 * ABW_T128) >> 4), vd = kd + (ABW_T128 >> 4);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16_ss(tS + b * 64, qd + 2 * k, kd + 2 * k, idesc_s, k > 0);
+        for (int k = 0; k < 4; ++k) umma_bf16_ss(tS, qd + 2 * k, kd + 2 * k, idesc_s, k > 0);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16_ss(tdP + b * 64, dod + 2 * k, vd + 2 * k, idesc_s, k > 0);
-        umma_commit(sdp_full(b));
+        for (int k = 0; k < 4; ++k) umma_bf16_ss(tdP, dod + 2 * k, vd + 2 * k, idesc_s, k > 0);
+        umma_commit(sdp_full);
         if (++st == ABW_STAGES) { st = 0; ph ^= 1; }
       }
     }
     __syncwarp();
   } else if (warp == 2) {
-    // ---- dQ += dS[128 x 64 keys] * K[64 keys x 64]: dS from tensor memory, K (MN-major) from shared memory
+    // ---- dQ += dS[128 x 128 keys] * K[128 keys x 64]: dS from tensor memory, K (MN-major) from shared memory
     if (n_kv > 0 && elect_one()) {
       constexpr uint32_t idesc_q = make_idesc_bf16(128, ATTN_D, 0, 1);
-      const uint64_t mdesc0 = make_smem_desc(0, ABW_T64, 1024, SWZ_128B);
+      const uint64_t mdesc0 = make_smem_desc(0, ABW_T128, 1024, SWZ_128B);
       int st = 0, db = 0;
       uint32_t ph = 0, dph = 0;
       for (int j = 0; j < n_kv; ++j) {
         mbar_wait(kv_full(st), ph);
         mbar_wait(ds_full(db), dph);
         tc_fence_after();
-        const uint64_t kd = mdesc0 + ((sKV + st * 2 * ABW_T64) >> 4);
+        const uint64_t kd = mdesc0 + ((sKV + st * 2 * ABW_T128) >> 4);
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk)
-          umma_bf16_ts(tdQ, tdS + db * 32 + kk * 8, kd + kk * (2048 >> 4), idesc_q, (j > 0) || (kk > 0));
+        for (int kk = 0; kk < ABW_BN / 16; ++kk)     // 16 keys of dS = 8 TMEM columns
+          umma_bf16_ts(tdQ, tdS + db * 64 + kk * 8, kd + kk * (2048 >> 4), idesc_q, (j > 0) || (kk > 0));
         umma_commit(kv_empty(st));       // S(j), dP(j) retired before the softmax produced dS(j): K and V are free
         umma_commit(ds_empty(db));
         if (++st == ABW_STAGES) { st = 0; ph ^= 1; }
@@ -342,7 +340,7 @@ __global__ void __launch_bounds__(ABW_THREADS, 1) attn_bwd_dq_kernel(const __gri
     __syncwarp();
   } else {
     const int qw = warp & 3;
-    const int part = (warp - 3) >> 2;      // which 16 of the 64 streamed key columns this warp owns
+    const int part = (warp - 3) >> 2;      // which 32 of the 128 streamed key columns this warp owns
     const int r = qw * 32 + lane;
     const int iq = q0 + r;
     const uint32_t lane_off = static_cast<uint32_t>(qw * 32) << 16;
@@ -357,30 +355,36 @@ __global__ void __launch_bounds__(ABW_THREADS, 1) attn_bwd_dq_kernel(const __gri
     const Win2 win = key_windows(p.mask, p.n_frames, p.hw, iq, p.Lq, p.Lk);
     const uint32_t t_s = tS + lane_off + part * ABW_COLS, t_dp = tdP + lane_off + part * ABW_COLS;
     const uint32_t t_ds = tdS + lane_off + part * (ABW_COLS / 2);
+    auto nl = [&](int) { return NL; };
+    auto nd = [&](int) { return ND; };
     int db = 0;
     uint32_t dph = 0;
     for (int j = 0; j < n_kv; ++j) {
-      const int b = j & 1;
       const int ik0 = kr.tile(j) * ABW_BN + part * ABW_COLS;
-      const bool all_vis = win.whole(ik0, ABW_COLS);
-      mbar_wait(sdp_full(b), (j >> 1) & 1);
+      mbar_wait(sdp_full, j & 1);
       tc_fence_after();
-      float s[16], dp[16];
-      tmem_ld16(t_s + b * 64, s);
-      tmem_ld16(t_dp + b * 64, dp);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(sdp_empty(b));
-      uint32_t pk_ds[8], unused[8];
-      auto nl = [&](int) { return NL; };
-      auto nd = [&](int) { return ND; };
-      if (all_vis) pds_chunk16<false, false>(s, dp, unused, pk_ds, c1, p.scale, nl, nd, 0, 0u, 0, 0u);
-      else
-        pds_chunk16<true, false>(s, dp, unused, pk_ds, c1, p.scale, nl, nd, win.a1 - ik0, static_cast<unsigned>(win.b1 - win.a1),
-                                 win.a2 - ik0, static_cast<unsigned>(win.b2 - win.a2));
+      uint32_t pk_ds[16];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {          // two chunks of 16 columns: 32 live accumulator registers at a time
+        float s[16], dp[16];
+        tmem_ld16(t_s + h * 16, s);
+        tmem_ld16(t_dp + h * 16, dp);
+        tmem_ld_wait();
+        if (h == 1) {                         // S and dP of this step are in registers: the next step's MMAs may overwrite them
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(sdp_empty);
+        }
+        uint32_t unused[8];
+        uint32_t (&out)[8] = *reinterpret_cast<uint32_t (*)[8]>(&pk_ds[h * 8]);
+        const int c0 = ik0 + h * 16;
+        if (win.whole(c0, 16)) pds_chunk16<false, false>(s, dp, unused, out, c1, p.scale, nl, nd, 0, 0u, 0, 0u);
+        else
+          pds_chunk16<true, false>(s, dp, unused, out, c1, p.scale, nl, nd, win.a1 - c0, static_cast<unsigned>(win.b1 - win.a1),
+                                   win.a2 - c0, static_cast<unsigned>(win.b2 - win.a2));
+      }
       mbar_wait(ds_empty(db), dph ^ 1);    // first pass falls through
-      tmem_st8(t_ds + db * 32, pk_ds);
+      tmem_st16(t_ds + db * 64, pk_ds);
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
@@ -411,27 +415,25 @@ __global__ void __launch_bounds__(ABW_THREADS, 1) attn_bwd_dq_kernel(const __gri
 
 // ------------------------------------------------------------------------------------------------ dK, dV
 // Same warp roles; rows are keys, streamed columns are queries.  P^T and dS^T go to the dV / dK MMAs through tensor memory.
-// The 64 streamed queries' statistics (-lse*log2e, -D*scale) ride along with their Q / dO tiles as one bulk copy per stage.
-// TMEM columns: S^T [0,64) [64,128); dP^T [128,192) [192,256); dK [256,320); dV [320,384); P^T 2 x 32 from 384; dS^T 2 x 32
-// from 448.
+// The 128 streamed queries' statistics (-lse*log2e, -D*scale) ride along with their Q / dO tiles as bulk copies per stage.
+// TMEM columns (all 512, everything single-buffered): S^T [0,128); dP^T [128,256); dK [256,320); dV [320,384); P^T (bf16
+// pairs) [384,448); dS^T [448,512).
 __global__ void __launch_bounds__(ABW_THREADS, 1) attn_bwd_dkv_kernel(const __grid_constant__ AttnBwdParams p) {
   pdl_launch_dependents();
   pdl_wait();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sK = base, sV = sK + ABW_T128;
-  const uint32_t sQdO = sV + ABW_T128;                       // stage s: Q at +s*16K, dO at +s*16K+8K
-  const uint32_t sStat = sQdO + ABW_STAGES * 2 * ABW_T64;    // stage s: [-lse*log2e (64) | -D*scale (64)] floats
+  const uint32_t sQdO = sV + ABW_T128;                       // stage s: Q at +s*32K, dO at +s*32K+16K
+  const uint32_t sStat = sQdO + ABW_STAGES * 2 * ABW_T128;   // stage s: [-lse*log2e (128) | -D*scale (128)] floats
   const uint32_t bar = sStat + ABW_STAGES * ABW_STAT_BYTES;
   const uint32_t kv_full = bar;
   auto q_full = [&](int s) { return bar + 8u * (1 + s); };
   auto q_empty = [&](int s) { return bar + 8u * (1 + ABW_STAGES + s); };
-  auto sdp_full = [&](int b) { return bar + 8u * (1 + 2 * ABW_STAGES + b); };
-  auto sdp_empty = [&](int b) { return bar + 8u * (3 + 2 * ABW_STAGES + b); };
-  auto pds_full = [&](int b) { return bar + 8u * (5 + 2 * ABW_STAGES + b); };
-  auto pds_empty = [&](int b) { return bar + 8u * (7 + 2 * ABW_STAGES + b); };
-  const uint32_t acc_full = bar + 8u * (9 + 2 * ABW_STAGES);
-  const uint32_t tmem_slot = bar + 8u * (10 + 2 * ABW_STAGES);
+  const uint32_t sdp_full = bar + 8u * (1 + 2 * ABW_STAGES), sdp_empty = bar + 8u * (2 + 2 * ABW_STAGES);
+  const uint32_t pds_full = bar + 8u * (3 + 2 * ABW_STAGES), pds_empty = bar + 8u * (4 + 2 * ABW_STAGES);
+  const uint32_t acc_full = bar + 8u * (5 + 2 * ABW_STAGES);
+  const uint32_t tmem_slot = bar + 8u * (6 + 2 * ABW_STAGES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int bh = blockIdx.x;
@@ -444,10 +446,8 @@ __global__ void __launch_bounds__(ABW_THREADS, 1) attn_bwd_dkv_kernel(const __gr
   if (threadIdx.x == 0) {
     mbar_init(kv_full, 1);
     for (int s = 0; s < ABW_STAGES; ++s) { mbar_init(q_full(s), 1); mbar_init(q_empty(s), 1); }
-    for (int b = 0; b < 2; ++b) {
-      mbar_init(sdp_full(b), 1); mbar_init(sdp_empty(b), ABW_SM_WARPS);
-      mbar_init(pds_full(b), ABW_SM_WARPS); mbar_init(pds_empty(b), 1);
-    }
+    mbar_init(sdp_full, 1); mbar_init(sdp_empty, ABW_SM_WARPS);
+    mbar_init(pds_full, ABW_SM_WARPS); mbar_init(pds_empty, 1);
     mbar_init(acc_full, 1);
     fence_barrier_init();
   }
@@ -470,11 +470,11 @@ __global__ void __launch_bounds__(ABW_THREADS, 1) attn_bwd_dkv_kernel(const __gr
       uint32_t ph = 1;
       for (int j = 0; j < n_q; ++j) {
         mbar_wait(q_empty(st), ph);
-        const uint32_t sQ = sQdO + st * 2 * ABW_T64, sdO = sQ + ABW_T64, sS = sStat + st * ABW_STAT_BYTES;
-        mbar_arrive_expect_tx(q_full(st), 2 * ABW_T64 + ABW_STAT_BYTES);
+        const uint32_t sQ = sQdO + st * 2 * ABW_T128, sdO = sQ + ABW_T128, sS = sStat + st * ABW_STAT_BYTES;
+        mbar_arrive_expect_tx(q_full(st), 2 * ABW_T128 + ABW_STAT_BYTES);
         const int q0 = qr.tile(j) * ABW_BN;
-        tma_load_4d(sQ, &p.mapQ64, q_full(st), 0, q0, hh, bb);
-        tma_load_4d(sdO, &p.mapdO64, q_full(st), 0, q0, hh, bb);
+        tma_load_4d(sQ, &p.mapQ128, q_full(st), 0, q0, hh, bb);
+        tma_load_4d(sdO, &p.mapdO128, q_full(st), 0, q0, hh, bb);
         bulk_load_1d(sS, nl_row + q0, ABW_BN * 4, q_full(st));
         bulk_load_1d(sS + ABW_BN * 4, nd_row + q0, ABW_BN * 4, q_full(st));
         if (++st == ABW_STAGES) { st = 0; ph ^= 1; }
@@ -491,41 +491,39 @@ __global__ void __launch_bounds__(ABW_THREADS, 1) attn_bwd_dkv_kernel(const __gr
       uint32_t ph = 0;
       mbar_wait(kv_full, 0);
       for (int j = 0; j < n_q; ++j) {
-        const int b = j & 1;
         mbar_wait(q_full(st), ph);
-        if (j >= 2) mbar_wait(sdp_empty(b), ((j >> 1) & 1) ^ 1);
+        if (j >= 1) mbar_wait(sdp_empty, (j & 1) ^ 1);
         tc_fence_after();
-        const uint64_t qd = kdesc0 + ((sQdO + st * 2 * ABW_T64) >> 4), dod = qd + (ABW_T64 >> 4);
+        const uint64_t qd = kdesc0 + ((sQdO + st * 2 * ABW_T128) >> 4), dod = qd + (ABW_T128 >> 4);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16_ss(tS + b * 64, kd + 2 * k, qd + 2 * k, idesc_s, k > 0);
+        for (int k = 0; k < 4; ++k) umma_bf16_ss(tS, kd + 2 * k, qd + 2 * k, idesc_s, k > 0);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16_ss(tdP + b * 64, vd + 2 * k, dod + 2 * k, idesc_s, k > 0);
-        umma_commit(sdp_full(b));
+        for (int k = 0; k < 4; ++k) umma_bf16_ss(tdP, vd + 2 * k, dod + 2 * k, idesc_s, k > 0);
+        umma_commit(sdp_full);
         if (++st == ABW_STAGES) { st = 0; ph ^= 1; }
       }
     }
     __syncwarp();
   } else if (warp == 2) {
-    // ---- dV += P^T[128 keys x 64 q] * dO[64 q x 64];  dK += dS^T * Q   (A operands from tensor memory)
+    // ---- dV += P^T[128 keys x 128 q] * dO[128 q x 64];  dK += dS^T * Q   (A operands from tensor memory)
     if (n_q > 0 && elect_one()) {
       constexpr uint32_t idesc_a = make_idesc_bf16(128, ATTN_D, 0, 1);
-      const uint64_t mdesc0 = make_smem_desc(0, ABW_T64, 1024, SWZ_128B);
+      const uint64_t mdesc0 = make_smem_desc(0, ABW_T128, 1024, SWZ_128B);
       int st = 0;
       uint32_t ph = 0;
       for (int j = 0; j < n_q; ++j) {
-        const int b = j & 1;
         mbar_wait(q_full(st), ph);
-        mbar_wait(pds_full(b), (j >> 1) & 1);
+        mbar_wait(pds_full, j & 1);
         tc_fence_after();
-        const uint64_t qd = mdesc0 + ((sQdO + st * 2 * ABW_T64) >> 4), dod = qd + (ABW_T64 >> 4);
+        const uint64_t qd = mdesc0 + ((sQdO + st * 2 * ABW_T128) >> 4), dod = qd + (ABW_T128 >> 4);
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk)
-          umma_bf16_ts(tdV, tP + b * 32 + kk * 8, dod + kk * (2048 >> 4), idesc_a, (j > 0) || (kk > 0));
+        for (int kk = 0; kk < ABW_BN / 16; ++kk)
+          umma_bf16_ts(tdV, tP + kk * 8, dod + kk * (2048 >> 4), idesc_a, (j > 0) || (kk > 0));
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk)
-          umma_bf16_ts(tdK, tdS + b * 32 + kk * 8, qd + kk * (2048 >> 4), idesc_a, (j > 0) || (kk > 0));
+        for (int kk = 0; kk < ABW_BN / 16; ++kk)
+          umma_bf16_ts(tdK, tdS + kk * 8, qd + kk * (2048 >> 4), idesc_a, (j > 0) || (kk > 0));
         umma_commit(q_empty(st));
-        umma_commit(pds_empty(b));
+        umma_commit(pds_empty);
         if (++st == ABW_STAGES) { st = 0; ph ^= 1; }
       }
       umma_commit(acc_full);
@@ -533,7 +531,7 @@ __global__ void __launch_bounds__(ABW_THREADS, 1) attn_bwd_dkv_kernel(const __gr
     __syncwarp();
   } else {
     const int qw = warp & 3;
-    const int part = (warp - 3) >> 2;     // which 16 of the 64 streamed query columns this warp owns
+    const int part = (warp - 3) >> 2;     // which 32 of the 128 streamed query columns this warp owns
     const int r = qw * 32 + lane;         // key row of the tile
     const int ik = k0 + r;
     const uint32_t lane_off = static_cast<uint32_t>(qw * 32) << 16;
@@ -544,43 +542,49 @@ __global__ void __launch_bounds__(ABW_THREADS, 1) attn_bwd_dkv_kernel(const __gr
     int st = 0;
     uint32_t ph = 0;
     for (int j = 0; j < n_q; ++j) {
-      const int b = j & 1;
       const int iq0 = qr.tile(j) * ABW_BN + part * ABW_COLS;
-      const bool all_vis = win.whole(iq0, ABW_COLS);
       mbar_wait(q_full(st), ph);           // this stage's statistics are visible (the S^T MMA needed the same barrier)
-      mbar_wait(sdp_full(b), (j >> 1) & 1);
+      mbar_wait(sdp_full, j & 1);
       tc_fence_after();
-      float s[16], dp[16];
-      tmem_ld16(t_s + b * 64, s);
-      tmem_ld16(t_dp + b * 64, dp);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(sdp_empty(b));
-      // this chunk's column statistics: 16 + 16 floats, the same for every lane (broadcast reads)
-      uint64_t nlv[8], ndv[8];
-      {
-        const uint32_t a_l = sStat + st * ABW_STAT_BYTES + part * ABW_COLS * 4, a_d = a_l + ABW_BN * 4;
+      uint32_t pk_p[16], pk_ds[16];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(nlv[2 * i]), "=l"(nlv[2 * i + 1]) : "r"(a_l + i * 16));
-          asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(ndv[2 * i]), "=l"(ndv[2 * i + 1]) : "r"(a_d + i * 16));
+      for (int h = 0; h < 2; ++h) {
+        float s[16], dp[16];
+        tmem_ld16(t_s + h * 16, s);
+        tmem_ld16(t_dp + h * 16, dp);
+        tmem_ld_wait();
+        if (h == 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(sdp_empty);
         }
+        // this chunk's column statistics: 16 + 16 floats, the same for every lane (broadcast reads)
+        uint64_t nlv[8], ndv[8];
+        {
+          const uint32_t a_l = sStat + st * ABW_STAT_BYTES + (part * ABW_COLS + h * 16) * 4, a_d = a_l + ABW_BN * 4;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(nlv[2 * i]), "=l"(nlv[2 * i + 1]) : "r"(a_l + i * 16));
+            asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(ndv[2 * i]), "=l"(ndv[2 * i + 1]) : "r"(a_d + i * 16));
+          }
+        }
+        auto nl = [&](int pi) { return nlv[pi]; };
+        auto nd = [&](int pi) { return ndv[pi]; };
+        uint32_t (&op)[8] = *reinterpret_cast<uint32_t (*)[8]>(&pk_p[h * 8]);
+        uint32_t (&od)[8] = *reinterpret_cast<uint32_t (*)[8]>(&pk_ds[h * 8]);
+        const int c0 = iq0 + h * 16;
+        if (win.whole(c0, 16)) pds_chunk16<false, true>(s, dp, op, od, c1, p.scale, nl, nd, 0, 0u, 0, 0u);
+        else
+          pds_chunk16<true, true>(s, dp, op, od, c1, p.scale, nl, nd, win.a1 - c0, static_cast<unsigned>(win.b1 - win.a1),
+                                  win.a2 - c0, static_cast<unsigned>(win.b2 - win.a2));
       }
-      uint32_t pk_p[8], pk_ds[8];
-      auto nl = [&](int pi) { return nlv[pi]; };
-      auto nd = [&](int pi) { return ndv[pi]; };
-      if (all_vis) pds_chunk16<false, true>(s, dp, pk_p, pk_ds, c1, p.scale, nl, nd, 0, 0u, 0, 0u);
-      else
-        pds_chunk16<true, true>(s, dp, pk_p, pk_ds, c1, p.scale, nl, nd, win.a1 - iq0, static_cast<unsigned>(win.b1 - win.a1),
-                                win.a2 - iq0, static_cast<unsigned>(win.b2 - win.a2));
-      if (j >= 2) mbar_wait(pds_empty(b), ((j >> 1) & 1) ^ 1);
-      tmem_st8(t_p + b * 32, pk_p);
-      tmem_st8(t_ds + b * 32, pk_ds);
+      if (j >= 1) mbar_wait(pds_empty, (j & 1) ^ 1);     // the dV / dK MMAs of the previous step have consumed P^T, dS^T
+      tmem_st16(t_p, pk_p);
+      tmem_st16(t_ds, pk_ds);
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(pds_full(b));
+      if (lane == 0) mbar_arrive(pds_full);
       if (++st == ABW_STAGES) { st = 0; ph ^= 1; }
     }
     if (n_q > 0) { mbar_wait(acc_full, 0); tc_fence_after(); }

@@ -308,7 +308,7 @@ int ob_dart_attn_decode(const void* q, const void* k_pages, const void* v_pages,
                         int n_split, int extra_frames, float scale, void* stream);
 
 /* Backward of ob_attn_fwd (autograd of the same reference calls).  o, lse: the forward's outputs; dout: bf16
- * [B, Lq, heads, 64]; ws: fp32 workspace of 2 * B * heads * Lp floats, Lp = lq rounded up to a multiple of 64, 256-byte
+ * [B, Lq, heads, 64]; ws: fp32 workspace of 2 * B * heads * Lp floats, Lp = lq rounded up to a multiple of 128, 256-byte
  * aligned (receives -rowsum(dout*o)*scale and -lse*log2(e), zero-padded per row).  Writes dq, dk, dv (bf16, shaped like
  * q, k, v).
  * Every output element is produced by exactly one CTA (no atomics, deterministic). */
