@@ -1,4 +1,2 @@
 mkdir -p gpurun_out
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:attn_ -c 12 -f -o gpurun_out/r02_prof_attn_v3 python tools/ncu_attention.py > gpurun_out/ncu_attn_v3.log 2>&1
-tail -1 gpurun_out/ncu_attn_v3.log
-timeout 1500 python -m pytest tests -m gpu -q -x 2>&1 | tail -2
+timeout 1500 compute-sanitizer --tool memcheck --report-api-errors no --error-exitcode 7 python -m pytest tests/test_conv_gpu.py tests/test_elementwise_gpu.py tests/test_vae_gpu.py tests/test_optimizer_gpu.py -m gpu -q -x > gpurun_out/sanitizer_conv_final.log 2>&1; echo "sanitizer rc=$?"; tail -4 gpurun_out/sanitizer_conv_final.log
