@@ -114,6 +114,41 @@ def time_train(ref, kw, B, n, res, steps, warmup, P_mean, ctx_red, label, result
     torch.cuda.empty_cache()
 
 
+def time_sampling(ref, result):
+    """Config 2 on the reference itself: Lunar-Lander UNet, 8 cached context frames, its own edm_sampler_with_mse with 32
+    Heun steps (63 network evaluations per generated frame), batch 1 and 16."""
+    import importlib
+    nets = ref["nets"]
+    sampler = importlib.import_module("edm2.sampler")
+    rows = []
+    for B in (1, 16):
+        torch.manual_seed(0)
+        unet = nets.UNet(**LL_UNET).cuda()
+        with torch.no_grad():
+            unet.out_gain.fill_(1.0)
+        precond = nets.Precond(unet, use_fp16=True, sigma_data=1.0).cuda().eval()
+        with torch.no_grad():
+            ctx = torch.randn(B, 8, 8, 64, 64, device="cuda")
+            cctx = torch.randint(0, 4, (B, 8), device="cuda")
+            _, cache = precond(ctx, torch.ones(B, 8, device="cuda") * 0.05, cctx, update_cache=True)
+            cnew = torch.randint(0, 4, (B, 1), device="cuda")
+            for _ in range(1):     # warm-up frame
+                _, _, _, cache = sampler.edm_sampler_with_mse(precond, cache, conditioning=cnew, num_steps=32)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            n = 2
+            for _ in range(n):
+                _, _, _, cache = sampler.edm_sampler_with_mse(precond, cache, conditioning=cnew, num_steps=32)
+            torch.cuda.synchronize()
+            dt = (time.perf_counter() - t0) / n
+        rows.append(dict(batch=B, s_per_frame_step=dt, frames_per_s=B / dt, ms_per_eval=dt / 63 * 1e3,
+                         what="unmodified reference sampler (eager PyTorch: cuDNN + SDPA), 63 evals per frame"))
+        print("sampling", rows[-1], flush=True)
+        del precond, unet, cache
+        torch.cuda.empty_cache()
+    result["config2_ll_sampling"] = rows
+
+
 def main():
     assert torch.cuda.is_available()
     ref = import_reference()
@@ -126,7 +161,8 @@ def main():
 
     for name, fn in [("f3", lambda: f3_experiment(ref, result)), ("dtype", lambda: dtype_trace(ref, result)),
                      ("cs", lambda: time_train(ref, CS_UNET, 2, 16, 32, 5, 3, 0.9, 0.1, "config3_cs_train_micro_step", result)),
-                     ("ll", lambda: time_train(ref, LL_UNET, 2, 8, 64, 5, 3, 1.2, 0.5, "config1_ll_train_step", result))]:
+                     ("ll", lambda: time_train(ref, LL_UNET, 2, 8, 64, 5, 3, 1.2, 0.5, "config1_ll_train_step", result)),
+                     ("sampling", lambda: time_sampling(ref, result))]:
         if len(sys.argv) > 1 and name not in sys.argv[1:]:
             continue
         try:
