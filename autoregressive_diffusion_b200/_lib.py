@@ -40,6 +40,7 @@ _SIGS = {
     "ob_conv_split_ws_bytes": "iiiiiiiii",
     "ob_conv_wgrad_splits": "iiiiiiiii",
     "ob_conv_wgrad": "pppppiiiiiiiiiip",
+    "ob_conv_wgrad_acc": "pppppiiiiiiiiiip",
     "ob_gate_bwd": "pppppppppiiilp",
     "ob_conv_prologue": "pppiiiliippppppppilpp",
     "ob_gate_bwd_fused": "ppppppppiiilpppppppppip",

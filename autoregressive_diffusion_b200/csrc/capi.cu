@@ -178,10 +178,11 @@ int ob_conv_wgrad_splits(int n_seq, int S, int T, int H, int W, int cin, int cou
   return wgrad_suggest_split(gated ? 27 : ksize * ksize, n_seq * S * T, H, W, cin, cout);
 }
 
-int ob_conv_wgrad(const void* gya, const void* x, const void* gb, const void* ctx, float* dwg, int n_seq, int S, int T,
-                  int H, int W, int cin, int cout, int ksize, int gated, int n_split, void* stream) {
+static int conv_wgrad_impl(const void* gya, const void* x, const void* gb, const void* ctx, float* dwg, int n_seq, int S, int T,
+                           int H, int W, int cin, int cout, int ksize, int gated, int n_split, int accumulate, void* stream) {
   if (int r = check_shape("ob_conv_wgrad", n_seq, S, T, H, W, ksize, gated)) return r;
   WgradLaunch L;
+  L.accumulate = accumulate;
   std::vector<WgradItem> items;
   auto mk = [](int pair, int dt, int dy, int dx, int wtap) {
     WgradItem t{}; t.pair = (int8_t)pair; t.dt = (int8_t)dt; t.dy = (int8_t)dy; t.dx = (int8_t)dx; t.wtap = wtap; return t;
@@ -203,6 +204,14 @@ int ob_conv_wgrad(const void* gya, const void* x, const void* gb, const void* ct
   L.items = items.data(); L.n_items = (int)items.size();
   L.H = H; L.W = W; L.Cin = cin; L.Cout = cout; L.n_split = n_split; L.out = dwg;
   return wgrad_launch(L, (cudaStream_t)stream);
+}
+int ob_conv_wgrad(const void* gya, const void* x, const void* gb, const void* ctx, float* dwg, int n_seq, int S, int T,
+                  int H, int W, int cin, int cout, int ksize, int gated, int n_split, void* stream) {
+  return conv_wgrad_impl(gya, x, gb, ctx, dwg, n_seq, S, T, H, W, cin, cout, ksize, gated, n_split, 0, stream);
+}
+int ob_conv_wgrad_acc(const void* gya, const void* x, const void* gb, const void* ctx, float* dw_sum, int n_seq, int S, int T,
+                      int H, int W, int cin, int cout, int ksize, int gated, int n_split, void* stream) {
+  return conv_wgrad_impl(gya, x, gb, ctx, dw_sum, n_seq, S, T, H, W, cin, cout, ksize, gated, n_split, 1, stream);
 }
 
 int ob_gate_bwd(const void* dy, const void* y, const void* d, const float* alpha, const float* beta, void* gya, void* gb,

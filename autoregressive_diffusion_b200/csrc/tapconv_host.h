@@ -68,6 +68,7 @@ struct WgradLaunch {
   int n_items = 0;
   int H = 0, W = 0, Cin = 0, Cout = 0, w_taps = 0;
   int n_split = 1;
+  int accumulate = 0;    // 1: the K slices add into out[0] (a running sum the caller zeroed) instead of storing n_split slices
   int force_mode = 0;    // probe only: 1 = one tap per CTA and no pairs, 2 = CTA pairs, 3 = halo groups, where the shape allows
   float* out = nullptr;  // [n_split, Cout, w_taps, Cin]
 };

@@ -177,6 +177,7 @@ static int wgrad_halo_launch(const WgradLaunch& L, const WgradPlan& q, cudaStrea
   p.Cin = L.Cin; p.Cout = L.Cout; p.w_taps = L.w_taps;
   p.ci_tiles = q.ci_tiles; p.co_tiles = q.co_tiles;
   p.n_split = L.n_split;
+  p.accumulate = L.accumulate;
   p.out = L.out;
   p.shift_bytes = p.bt * p.bw * 128;
   p.a_box_bytes = (p.bh + 1) * p.bt * p.bw * 128;
@@ -265,6 +266,7 @@ int wgrad_launch(const WgradLaunch& L, cudaStream_t stream) {
   p.ci_tiles = q.ci_tiles;
   p.co_tiles = q.co_tiles;
   p.n_split = L.n_split;
+  p.accumulate = L.accumulate;
   p.out = L.out;
   dim3 grid(q.co_tiles * q.ci_tiles, ng, L.n_split);
   switch (chunk) {

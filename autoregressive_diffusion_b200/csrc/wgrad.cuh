@@ -47,7 +47,8 @@ struct WgradParams {
   int tiles_t[2];
   int ci_tiles, co_tiles;
   int n_split;
-  float* out;  // [n_split, Cout, w_taps, Cin] fp32
+  int accumulate;   // 1: every K slice adds (red.global.add) into slice 0 of out instead of storing its own slice
+  float* out;  // [n_split, Cout, w_taps, Cin] fp32 (accumulate: [1, Cout, w_taps, Cin], holding the running sum)
 };
 
 // BN = input-channel span of one tap; the MMA's N is BN*NT.  PAIR: two CTAs (adjacent output-channel tiles) run one
@@ -211,13 +212,24 @@ __global__ void __launch_bounds__(WGRAD_THREADS, 1) wgrad_kernel(const __grid_co
       const int tap = (c * CW) / BN;              // CW divides BN
       const int wtap = grp.wtap[tap];
       if (co < p.Cout && wtap >= 0) {
-        float* dst_row = p.out + ((static_cast<long>(blockIdx.z) * p.Cout + co) * p.w_taps + wtap) * p.Cin;
+        float* dst_row = p.out + ((static_cast<long>(p.accumulate ? 0 : blockIdx.z) * p.Cout + co) * p.w_taps + wtap) * p.Cin;
         const int col0 = ci0 + (c * CW) % BN;
+        if (p.accumulate) {           // running sum over K slices AND over the micro-steps of an accumulation cycle
+          if (have) {
+#pragma unroll
+            for (int j = 0; j < CW; j += 4)
+              if (col0 + j + 4 <= p.Cin)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst_row + col0 + j), "f"(v[j]), "f"(v[j + 1]),
+                             "f"(v[j + 2]), "f"(v[j + 3])
+                             : "memory");
+          }
+        } else {
 #pragma unroll
         for (int j = 0; j < CW; j += 4)
           if (col0 + j + 4 <= p.Cin)
             *reinterpret_cast<float4*>(dst_row + col0 + j) =
                 have ? make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
       }
     }
     tc_fence_before();
@@ -250,6 +262,7 @@ struct WgradHaloParams {
   int Cin, Cout, w_taps;
   int ci_tiles, co_tiles;
   int n_split;
+  int accumulate;     // as WgradParams::accumulate
   int a_box_bytes;    // (bh + 1) * bt * bw * 128: one 64-channel halo box (also the box stride of single-tap groups)
   int shift_bytes;    // bt * bw * 128: where the second tap's first pixel row sits inside a halo box
   int stages, stage_bytes;
@@ -365,18 +378,29 @@ static __global__ void __launch_bounds__(WGRAD_THREADS, 1) wgrad_halo_kernel(con
     const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const bool have = k_end > k_begin;
     for (int j = 0; j < n_taps; ++j) {
-      float* dst_row = p.out + ((static_cast<long>(blockIdx.z) * p.Cout + co) * p.w_taps + grp.wtap[j]) * p.Cin;
+      float* dst_row = p.out + ((static_cast<long>(p.accumulate ? 0 : blockIdx.z) * p.Cout + co) * p.w_taps + grp.wtap[j]) * p.Cin;
       for (int c = 0; c < WGH_BN / 32; ++c) {
         float v[32];
         tmem_ld32(lane_base + j * WGH_BN + c * 32, v);
         tmem_ld_wait();
         if (co < p.Cout) {
           const int col0 = ci0 + c * 32;
+          if (p.accumulate) {
+            if (have) {
+#pragma unroll
+              for (int u = 0; u < 32; u += 4)
+                if (col0 + u + 4 <= p.Cin)
+                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst_row + col0 + u), "f"(v[u]), "f"(v[u + 1]),
+                               "f"(v[u + 2]), "f"(v[u + 3])
+                               : "memory");
+            }
+          } else {
 #pragma unroll
           for (int u = 0; u < 32; u += 4)
             if (col0 + u + 4 <= p.Cin)
               *reinterpret_cast<float4*>(dst_row + col0 + u) =
                   have ? make_float4(v[u], v[u + 1], v[u + 2], v[u + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
         }
       }
     }

@@ -205,6 +205,61 @@ def weight_grad(params, taps, cin, cin_pad, gains, dwg, n_split, eps=1e-4, targe
         off += t
 
 
+class RawGradBank:
+    """Deferred weight-norm backward for gradient accumulation ("direct" mode, train.Trainer).
+
+    The weight-norm backward (ob_wnorm_bwd) is linear in the raw weight gradient for fixed weights, and the weights do not
+    change inside an accumulation cycle.  So instead of  wgrad -> n_split fp32 partial slices -> wnorm_bwd  on every
+    micro-batch (18 B per parameter and micro-batch of HBM traffic on the weight-gradient stream, which paces the whole
+    backward pass: skipping it shortened the CS micro-step from 13.5 to 11.9 ms), every layer keeps ONE fp32 running sum of
+    its raw gradient: ob_conv_wgrad_acc adds into it (the K slices and the micro-batches alike), and only the LAST
+    micro-batch of the cycle runs ob_wnorm_bwd on the sum (n_split = 1) and zeroes it."""
+
+    enabled = False          # set by train.Trainer when accumulation_steps > 1
+    finalize_now = True      # set by train.Trainer before every micro-batch: True on the last one of the cycle
+    _layers = {}             # id(first parameter) -> {total taps: entry}; a gated layer has a 27-tap entry (3-D form) and a
+                             # 9-tap entry (its 2-D form, cs_train.py:106): whichever form the LAST micro-batch runs in
+                             # finalizes both
+
+    @classmethod
+    def entry(cls, params, taps, cin, cin_pad, gains, cout, device):
+        layer = cls._layers.setdefault(id(params[0]), {})
+        total = sum(taps)
+        e = layer.get(total)
+        if e is None or e["raw"].device != device or e["raw"].shape != (1, cout, total, cin_pad) or e["params"][0] is not params[0]:
+            e = dict(raw=torch.zeros((1, cout, total, cin_pad), dtype=torch.float32, device=device), params=list(params),
+                     taps=list(taps), cin=cin, cin_pad=cin_pad, gains=list(gains), dirty=False)
+            layer[total] = e
+        return e, layer
+
+    @classmethod
+    def reset(cls):
+        cls._layers.clear()
+
+
+def _wgrad_direct(params, taps, cin, cin_pad, gains, shape_args, ptrs, device):
+    """Weight gradient of one conv layer in "direct" mode: into .grad through ob_wnorm_bwd, either at once or -- inside an
+    accumulation cycle -- through the layer's running raw sum (RawGradBank).  shape_args / ptrs: ob_conv_wgrad's arguments
+    (n_seq, S, T, h, w, cin_pad, cout, ksize, gated) / (gya, x, gb, ctx)."""
+    cout = shape_args[6]
+    total = sum(taps)
+    ns = query("ob_conv_wgrad_splits", *shape_args)
+    if RawGradBank.enabled:
+        e, layer = RawGradBank.entry(params, taps, cin, cin_pad, gains, cout, device)
+        call("ob_conv_wgrad_acc", *ptrs, _vp(e["raw"]), *shape_args, ns, stream_ptr())
+        e["dirty"] = True
+        if RawGradBank.finalize_now:
+            for o in layer.values():       # this form's sum and, if another micro-batch of the cycle ran the other form, that one
+                if o["dirty"]:
+                    weight_grad(o["params"], o["taps"], o["cin"], o["cin_pad"], o["gains"], o["raw"], 1)
+                    o["raw"].zero_()
+                    o["dirty"] = False
+        return
+    dwg = torch.empty((ns, cout, total, cin_pad), dtype=torch.float32, device=device)
+    call("ob_conv_wgrad", *ptrs, _vp(dwg), *shape_args, ns, stream_ptr())
+    weight_grad(params, taps, cin, cin_pad, gains, dwg, ns)
+
+
 _CONST = {}
 
 
@@ -342,11 +397,15 @@ class PlainConvFn(torch.autograd.Function):
                 dw = torch.zeros_like(w, memory_format=torch.preserve_format)
 
             def branch():
+                if direct:
+                    _wgrad_direct([w], [k * k], cin, cin_pad, [gain], (1, 1, f, h, wd, cin_pad, cout, k, 0),
+                                  (_vp(gy), _vp(x), None, None), x.device)
+                    return
                 ns = query("ob_conv_wgrad_splits", 1, 1, f, h, wd, cin_pad, cout, k, 0)
                 dwg = torch.empty((ns, cout, k * k, cin_pad), dtype=torch.float32, device=x.device)
                 call("ob_conv_wgrad", _vp(gy), _vp(x), None, None, _vp(dwg), 1, 1, f, h, wd, cin_pad, cout, k, 0, ns,
                      stream_ptr())
-                weight_grad([w], [k * k], cin, cin_pad, [gain], dwg, ns, targets=None if direct else [dw])
+                weight_grad([w], [k * k], cin, cin_pad, [gain], dwg, ns, targets=[dw])
 
             if direct:
                 WeightGradBranch.run(x.device, (gy, x), branch)
@@ -587,6 +646,10 @@ class GatedConvFn(torch.autograd.Function):
                 targets = [dw2, dw3]
 
             def branch():
+                if direct:
+                    _wgrad_direct([w2, w3], [9, 18], cin, cin_pad, [1.0, 1.0], (n_seq, S, T, h, wd, cin_pad, cout, 3, 1),
+                                  (_vp(gya), _vp(x), _vp(gb), _vp(cx)), dev)
+                    return
                 ns = query("ob_conv_wgrad_splits", n_seq, S, T, h, wd, cin_pad, cout, 3, 1)
                 dwg = torch.empty((ns, cout, 27, cin_pad), dtype=torch.float32, device=dev)
                 call("ob_conv_wgrad", _vp(gya), _vp(x), _vp(gb), _vp(cx), _vp(dwg), n_seq, S, T, h, wd, cin_pad, cout, 3, 1,

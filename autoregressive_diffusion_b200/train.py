@@ -376,6 +376,8 @@ class Trainer:
         if self.device.type == "cuda":
             from .ops import set_weight_grad_mode
             set_weight_grad_mode("direct")    # this class owns the gradient buffers and the all-reduce (see ops.set_weight_grad_mode)
+            from .ops import RawGradBank
+            RawGradBank.reset()               # running raw-gradient sums belong to the network being trained
         if precond is not None:
             self.precond = precond.to(self.device)
             self.unet = precond.unet
@@ -430,6 +432,11 @@ class Trainer:
             from .ops import WeightGradBranch
             WeightGradBranch.recover(self.device)      # no-op unless an earlier backward pass was interrupted
         self.micro += 1
+        if self.device.type == "cuda":
+            from .ops import RawGradBank
+            # raw weight gradients are summed over the cycle; the weight-norm backward runs on the last micro-batch only
+            RawGradBank.enabled = self.accum > 1 and os.environ.get("ONIRIS_NO_DEFERRED_WNORM_BWD", "0") != "1"
+            RawGradBank.finalize_now = self.micro % self.accum == 0
         loss, unweighted = self.loss_fn(self.precond, latents, conditioning, just_2d=self._is_2d(self.micro))
         loss.backward()
         return loss.detach(), unweighted
@@ -517,12 +524,13 @@ class Trainer:
     def _plan_kind(self, pos):
         """Kind of the micro-step at cycle position pos (0-based): whether it is the first after an optimizer step (its
         forward re-normalises the weights the optimizer just changed) and whether it runs in 2-D form."""
-        return ("first" if pos == 0 else "rest", self._is_2d(pos + 1))
+        return ("first" if pos == 0 else "last" if pos == self.accum - 1 else "rest", self._is_2d(pos + 1))
 
     def capture(self, example_latents):
         """Capture the distinct micro-steps of an accumulation cycle and the optimizer step as CUDA graphs:
           ("first", 2d?)  forward+backward including ob_wnorm_fwd of every weight (forced normalisation + bf16 operand),
-          ("rest", 2d?)   forward+backward on the cached operands,
+          ("rest", 2d?)   forward+backward on the cached operands; raw weight gradients added to the layers' running sums,
+          ("last", 2d?)   the same plus the weight-norm backward of every layer on its sum (ops.RawGradBank),
           "opt"           AdamW + EMA + gradient reset.
         A cycle replays first, rest x (accum-1), [NCCL gradient sum, launched eagerly between the graphs], opt.
         ~1400 kernel launches per step become one graph launch, which removes the host from the critical path."""

@@ -118,6 +118,12 @@ int ob_conv_dgrad(const void* gy, const void* gb, const void* wg, const float* a
 int ob_conv_wgrad_splits(int n_seq, int S, int T, int H, int W, int cin, int cout, int ksize, int gated);
 int ob_conv_wgrad(const void* gya, const void* x, const void* gb, const void* ctx, float* dwg, int n_seq, int S, int T,
                   int H, int W, int cin, int cout, int ksize, int gated, int n_split, void* stream);
+/* Same, ADDED into dw_sum fp32 [Cout][taps][Cin] (every K slice uses red.global.add on the one buffer): the running sum of
+ * the raw weight gradient over the micro-batches of a gradient-accumulation cycle (cs_train.py:108-109).  The weight-norm
+ * backward is linear in it for fixed weights, so ob_wnorm_bwd runs once per cycle on the sum (n_split = 1) instead of once
+ * per micro-batch; the caller zeroes dw_sum when a cycle starts. */
+int ob_conv_wgrad_acc(const void* gya, const void* x, const void* gb, const void* ctx, float* dw_sum, int n_seq, int S, int T,
+                      int H, int W, int cin, int cout, int ksize, int gated, int n_split, void* stream);
 
 /* Backward pre-pass of the gate (mp_sum with a per-frame tensor t, edm2/conv.py:95 -> edm2/utils.py:122-123):
  * from dy, the saved y (bf16) and d (fp16) it emits gya = alpha*dy, gb = sum_s beta*dy and the per-frame inner products
