@@ -12,7 +12,7 @@ from autoregressive_diffusion_b200.train import CS_UNET, Trainer  # noqa: E402
 
 
 class Prof:
-    names = {"ob_conv_fwd": 8, "ob_conv_fwd_fused": 8, "ob_conv_dgrad": 7, "ob_conv_wgrad": 5}
+    names = {"ob_conv_fwd": 8, "ob_conv_fwd_fused": 8, "ob_conv_dgrad": 7, "ob_conv_wgrad": 5, "ob_conv_wgrad_acc": 5}
 
     def __init__(self):
         self.ev = []
