@@ -1,9 +1,5 @@
 # scratch job script for `gpurun -- 'bash tools/gpu_job.sh'`
 mkdir -p gpurun_out
-timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29523 bench.py --gpus 8 --steps 20 --warmup 5 2>/dev/null > gpurun_out/r02_bench_n8_final.json
-python -c "
-import json
-for l in open('gpurun_out/r02_bench_n8_final.json'):
-    if l.startswith('{'):
-        d=json.loads(l); print('N=8', d['value'], d['ms_per_step'], d['e2e']['value'])
-"
+for w in mid last; do
+NCU_STEP=$w timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv --log-file gpurun_out/r02_launches_step_$w.csv python tools/ncu_step.py > gpurun_out/ncu_step_$w.log 2>&1; wc -l gpurun_out/r02_launches_step_$w.csv
+done
