@@ -164,12 +164,14 @@ __global__ void __launch_bounds__(256, 4) wnorm_bwd_kernel(const WnormBwdArgs a)
   __shared__ float red2[2][8];
   const WnormBwdPart pt = a.part[blockIdx.y];
   const int co = blockIdx.x;
+  const bool accumulate = (a.accumulate & 1) != 0;
+  const bool zero_src = (a.accumulate & 2) != 0;     // the partials are a running sum (ob_conv_wgrad_acc): consume and clear it
   const int Ci = a.Ci, taps = pt.taps;
   const int K = Ci * taps;
   const float* wr = pt.w + static_cast<long>(co) * K;
   float* dwr = pt.dw + static_cast<long>(co) * K;
   const long split_stride = static_cast<long>(a.Co) * a.taps_total * a.Ci_pad;
-  const float* gsrc = a.dwg + (static_cast<long>(co) * a.taps_total + pt.tap_off) * a.Ci_pad;
+  float* gsrc = const_cast<float*>(a.dwg) + (static_cast<long>(co) * a.taps_total + pt.tap_off) * a.Ci_pad;
   const bool vec = (a.Ci_pad == Ci) && ((K & 3) == 0) && ((split_stride & 3) == 0) &&
                    (((reinterpret_cast<uintptr_t>(wr) | reinterpret_cast<uintptr_t>(dwr) | reinterpret_cast<uintptr_t>(gsrc)) & 15) == 0);
   const int nv = K / 4;
@@ -191,7 +193,7 @@ __global__ void __launch_bounds__(256, 4) wnorm_bwd_kernel(const WnormBwdArgs a)
       if (i4 < nv) {
         wv[v] = *reinterpret_cast<const float4*>(wr + i4 * 4);
         gv[v] = load_g(i4);
-        if (a.accumulate) asm volatile("prefetch.global.L2 [%0];" ::"l"(dwr + i4 * 4));
+        if (accumulate) asm volatile("prefetch.global.L2 [%0];" ::"l"(dwr + i4 * 4));
       }
     }
 #pragma unroll
@@ -234,11 +236,12 @@ __global__ void __launch_bounds__(256, 4) wnorm_bwd_kernel(const WnormBwdArgs a)
   auto emit = [&](int i4, const float4& g, const float4& w4) {
     float4 o = make_float4(c * (g.x - w4.x * proj), c * (g.y - w4.y * proj), c * (g.z - w4.z * proj), c * (g.w - w4.w * proj));
     float4* dst = reinterpret_cast<float4*>(dwr + i4 * 4);
-    if (a.accumulate) {
+    if (accumulate) {
       const float4 old = *dst;
       o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
     }
     *dst = o;
+    if (zero_src) *reinterpret_cast<float4*>(gsrc + i4 * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
   };
   if (cached) {
 #pragma unroll
@@ -254,7 +257,8 @@ __global__ void __launch_bounds__(256, 4) wnorm_bwd_kernel(const WnormBwdArgs a)
       float g = 0.f;
       for (int sp = 0; sp < a.n_split; ++sp) g += gsrc[sp * split_stride + tap * a.Ci_pad + ci];
       const float v = c * (g - wr[i] * proj);
-      dwr[i] = a.accumulate ? dwr[i] + v : v;
+      dwr[i] = accumulate ? dwr[i] + v : v;
+      if (zero_src) gsrc[tap * a.Ci_pad + ci] = 0.f;
     }
   }
 }

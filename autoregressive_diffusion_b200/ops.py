@@ -182,7 +182,7 @@ def weight_grad_mode():
     return _WEIGHT_GRAD_MODE[0]
 
 
-def weight_grad(params, taps, cin, cin_pad, gains, dwg, n_split, eps=1e-4, targets=None):
+def weight_grad(params, taps, cin, cin_pad, gains, dwg, n_split, eps=1e-4, targets=None, consume=False):
     """ob_wnorm_bwd for each parameter: split-K partials dwg [n_split, Cout, sum(taps), cin_pad] are reduced, pushed
     through the weight-normalisation backward and ACCUMULATED into `targets` (default: p.grad) in the same pass (so
     gradient accumulation over micro-batches, cs_train.py:108-109, costs no extra add kernels)."""
@@ -191,18 +191,28 @@ def weight_grad(params, taps, cin, cin_pad, gains, dwg, n_split, eps=1e-4, targe
     if targets is None:
         targets = [grad_buffer(p) if p.requires_grad else None for p in params]
     if dwg.shape[1] != cout:      # Cout was padded to a multiple of 8: fold the splits and drop the pad rows
+        full = dwg
         dwg = dwg.sum(0, keepdim=True)[:, :cout].contiguous()
         n_split = 1
+        if consume:               # the kernel would clear the folded copy, not the running sum
+            full.zero_()
+            consume = False
+    flags = 3 if consume else 1        # add into the target; consume: clear the (running-sum) partials as they are read
     if len(params) == 2 and list(taps) == [9, 18] and all(t is not None for t in targets) and all(float(g) == 1.0 for g in gains):
         call("ob_wnorm_bwd_gated", _vp(params[0]), _vp(targets[0]), _vp(params[1]), _vp(targets[1]),
-             _vp(dwg), cout, cin, cin_pad, n_split, eps, 1, stream_ptr())
+             _vp(dwg), cout, cin, cin_pad, n_split, eps, flags, stream_ptr())
         return
     off = 0
+    done = True
     for p, t, g, tgt in zip(params, taps, gains, targets):
         if tgt is not None:
             call("ob_wnorm_bwd", _vp(p), _vp(dwg), _vp(tgt), cout, cin, t, cin_pad, total, off, n_split, float(g),
-                 eps, 1, stream_ptr())
+                 eps, flags, stream_ptr())
+        else:
+            done = False
         off += t
+    if consume and not done:           # a frozen parameter's slice of the sum was not visited
+        dwg.zero_()
 
 
 class RawGradBank:
@@ -251,8 +261,7 @@ def _wgrad_direct(params, taps, cin, cin_pad, gains, shape_args, ptrs, device):
         if RawGradBank.finalize_now:
             for o in layer.values():       # this form's sum and, if another micro-batch of the cycle ran the other form, that one
                 if o["dirty"]:
-                    weight_grad(o["params"], o["taps"], o["cin"], o["cin_pad"], o["gains"], o["raw"], 1)
-                    o["raw"].zero_()
+                    weight_grad(o["params"], o["taps"], o["cin"], o["cin_pad"], o["gains"], o["raw"], 1, consume=True)
                     o["dirty"] = False
         return
     dwg = torch.empty((ns, cout, total, cin_pad), dtype=torch.float32, device=device)

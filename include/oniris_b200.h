@@ -60,7 +60,9 @@ int ob_wnorm_fwd_multi(const ob_wnorm_job* jobs, const int* row_start, int n_job
 
 /* Backward of the above w.r.t. the (forced) weights: dwg fp32 [n_split][Cout][taps_total][cin_pad] are the
  * split-K partial sums written by ob_conv_wgrad; dw fp32 [Cout][taps][Cin] (same storage order as w) is overwritten, or
- * (accumulate != 0) added to -- gradient accumulation over micro-batches (cs_train.py:108-109) without a separate pass.
+ * (accumulate & 1) added to -- gradient accumulation over micro-batches (cs_train.py:108-109) without a separate pass.
+ * accumulate & 2: dwg is the running sum kept by the accumulating weight-gradient entry point below, n_split = 1: it is
+ * cleared as it is consumed (the kernel writes through the const pointer), ready for the next accumulation cycle.
  * ob_wnorm_bwd_gated does the 2D (9 taps at offset 0) and 3D (18 taps at offset 9) weights of a gated conv in one launch. */
 int ob_wnorm_bwd(const float* w, const float* dwg, float* dw, int cout, int cin, int taps, int cin_pad, int taps_total,
                  int tap_off, int n_split, float gain, float eps, int accumulate, void* stream);

@@ -1,5 +1,8 @@
 # scratch job script for `gpurun -- 'bash tools/gpu_job.sh'`
 mkdir -p gpurun_out
-for w in mid last; do
-NCU_STEP=$w timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv --log-file gpurun_out/r02_launches_step_$w.csv python tools/ncu_step.py > gpurun_out/ncu_step_$w.log 2>&1; wc -l gpurun_out/r02_launches_step_$w.csv
-done
+timeout 200 python -m pytest tests -m gpu -q -x 2>&1 | tail -1
+timeout 120 python bench.py --steps 20 --warmup 5 --no-secondary --no-cpu-baseline > gpurun_out/r02_bench_quick.json 2>/dev/null; python - <<'PY'
+import json
+d=json.loads([l for l in open("gpurun_out/r02_bench_quick.json") if l.startswith("{")][-1])
+print(d["value"], d["ms_per_step"], d["e2e"]["value"], d["gpu_launches"], d["roofline"]["frac"])
+PY
