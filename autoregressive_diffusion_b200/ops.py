@@ -175,6 +175,9 @@ def set_weight_grad_mode(mode):
     assert mode in ("autograd", "direct")
     prev = _WEIGHT_GRAD_MODE[0]
     _WEIGHT_GRAD_MODE[0] = mode
+    # a mode switch ends any deferred accumulation (train.Trainer re-arms it before each of its micro-batches): "direct"
+    # used on its own writes finished gradients on every backward pass
+    RawGradBank.enabled, RawGradBank.finalize_now = False, True
     return prev
 
 
